@@ -1,0 +1,128 @@
+/*
+ * rlvae_b200 C ABI  --  the drop-in boundary for RlVAE's metric-evaluation and
+ * sampling hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (antoinelfg/RlVAE) has no FFI: its boundary is the Python
+ * interface of MetricTensor / the samplers.  This header is
+ * what a binding for that interface calls; rlvae_b200/_capi.py is the ctypes
+ * binding we ship, INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with h_;
+ *     tensors are fp32, row-major, contiguous;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     every call is asynchronous on that stream and allocates nothing
+ *     (callers pass workspaces; only rlvae_tables_create allocates);
+ *   - return value 0 = ok, non-zero = error, text in rlvae_last_error()
+ *     (thread-local);
+ *   - a handle is thread-compatible, not thread-safe.
+ *
+ * Citations "ref:" are file:line in the reference checkout.
+ */
+#ifndef RLVAE_B200_H_
+#define RLVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rlvae_tables rlvae_tables_t;
+
+/* which implementation evaluates the weighted sum / gradient contraction */
+enum {
+  RLVAE_PATH_AUTO   = 0, /* tensor path when eligible (d==16, accuracy criterion), else direct */
+  RLVAE_PATH_DIRECT = 1, /* fp32 CUDA-core kernel, direct ||z-c||^2 differences (any d <= 64)   */
+  RLVAE_PATH_TENSOR = 2  /* tcgen05/TMEM 3xTF32 kernel (d == 16 only); error if not available   */
+};
+
+/* log_pi / gradient flavours of the HMC sampler */
+enum {
+  RLVAE_GRAD_MODULAR = 0, /* ref: src/models/samplers/hmc_sampler.py:33-68  == (1 - lambda*G_ii)/T^2 */
+  RLVAE_GRAD_EXACT   = 1  /* grad_z 1/2 log det G^{-1}  (autograd of hmc_sampler.py:26-30)           */
+};
+
+const char* rlvae_last_error(void);
+int         rlvae_abi_version(void);
+
+/* ---- tables: replaces MetricTensor.load_pretrained's buffers --------------------------------
+ * ref: src/models/components/metric_tensor.py:59-96 (centroids [K,d], metric_matrices [K,d,d],
+ * temperature, regularization).  Packs device-side derived copies: zero-padded tables,
+ * ||c_k||^2, TF32 hi/lo splits, the transposed M table and its TMA descriptors.            */
+int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const float* matrices,
+                        int n_centroids, int latent_dim, float temperature, float regularization,
+                        void* stream);
+int rlvae_tables_destroy(rlvae_tables_t* t);
+/* info[0]=K, [1]=d, [2]=K padded, [3]=1 if every M_k is exactly symmetric,
+ * [4]=1 if the tensor path exists for this d, [5]=1 if AUTO would pick the tensor path */
+int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]);
+
+/* ---- A2: G^{-1}(z) = sum_k M_k exp(-||z-c_k||^2/T^2) + lambda I ------------------------------
+ * ref: src/models/components/metric_tensor.py:98-137.   z [N,d] -> ginv [N,d,d]               */
+int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv,
+                         int path, void* stream);
+
+/* ---- A3/A4/A5: batched d x d inverse, log|det|, sign, diagonal of the inverse ----------------
+ * ref: torch.linalg.inv / slogdet / det at metric_tensor.py:152,175 and hmc_sampler.py:28.
+ * a [N,d,d] -> inv [N,d,d], logabsdet [N], sign [N], diag_inv [N,d]; any output may be NULL.
+ * Partial-pivoting Gauss-Jordan, one matrix per d lanes.                                      */
+int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
+                          float* sign, float* diag_inv, void* stream);
+
+/* ---- K4: (scale) * sum_k w_k <U, M_k> (c_k - z) ----------------------------------------------
+ * u [N,d,d].  With U = G and scale = -2/T^2 this is grad_z log det G (north_star);
+ * with U = dL/dG^{-1} and scale = 2/T^2 it is the autograd backward of A2.
+ * out [N,d].                                                                                  */
+int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, int64_t n,
+                      float scale, float* out, int path, void* stream);
+
+/* ---- variant C (pythae): (1/T^2) G^T sum_k w_k M_k^T (c_k - z) -------------------------------
+ * ref: src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187.
+ * g [N,d,d] (the metric at z) -> out [N,d].  Direct path only.                                */
+int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
+                             float* out, void* stream);
+
+/* ---- fused metric evaluation -----------------------------------------------------------------
+ * z -> any subset of { ginv [N,d,d], g [N,d,d], logdet_g [N] (= log|det G|, ref
+ * metric_tensor.py:162-182), grad_logdet_g [N,d] (= grad_z log det G) }.  NULL outputs are
+ * skipped.  `work` must hold rlvae_metric_eval_workspace(n, d) bytes.                         */
+int64_t rlvae_metric_eval_workspace(int64_t n, int d);
+int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
+                      float* logdet_g, float* grad_logdet_g, void* work, int path, void* stream);
+
+/* ---- A11: one MCMC iteration of RiemannianHMCSampler.sample ----------------------------------
+ * ref: src/models/samplers/hmc_sampler.py:120-163.  In/out: z [N,d] (chain state, replaced by
+ * the accepted state).  gamma [N,d] and acc [N] are the random draws of lines 122 and 158.
+ * h_scales [n_lf] (HOST) = beta_sqrt_old/beta_sqrt per leapfrog step (lines 147-149).
+ * Optional outputs: h0 [N], h1 [N], alpha [N], moves [N] (1.0 = accepted).
+ * One metric evaluation per leapfrog step (+1 for H0).  work: rlvae_hmc_workspace(n,d) bytes. */
+int64_t rlvae_hmc_workspace(int64_t n, int d);
+int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, const float* acc,
+                        int64_t n, int n_lf, float eps_lf, float beta_zero_sqrt,
+                        const float* h_scales, int grad_mode, float* h0, float* h1, float* alpha,
+                        float* moves, void* work, int path, void* stream);
+
+/* ---- A13: z <- z + step * (-grad_func(z)), n_steps times (variant A) -------------------------
+ * ref: src/models/samplers/hmc_sampler.py:242-257.  In/out z [N,d].                           */
+int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, float step_size,
+                     void* work, int path, void* stream);
+
+/* ---- A14/A15: two nearest centroids by Euclidean distance ------------------------------------
+ * ref: src/models/samplers/riemannian_sampler.py:58-67,125-131.
+ * mu [N,d] -> idx [N,2] (int64), dist [N,2]                                                   */
+int rlvae_nearest2(const rlvae_tables_t* t, const float* mu, int64_t n, int64_t* idx, float* dist,
+                   void* stream);
+
+/* ---- A14-A17: out = cholesky(A + jitter I) @ eps ----------------------------------------------
+ * ref: src/models/samplers/riemannian_sampler.py:83-84,156-157,200-201,271-272.
+ * a [N,d,d], eps [N,d] -> out [N,d]; status [N] (int32, 0 ok / 1 not positive definite) or NULL */
+int rlvae_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
+                     int32_t* status, void* stream);
+
+/* ---- A20: (z1-z2)^T G((z1+z2)/2) (z1-z2) is composed in the host mirror from the calls above. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLVAE_B200_H_ */

@@ -1,1 +1,14 @@
-"""rlvae_b200 — B200-native metric evaluation + sampling for RlVAE."""
+"""rlvae_b200 -- B200-native (sm_100a) metric evaluation + sampling for RlVAE.
+
+Drop-in names for the reference's hot-path API: ``MetricTensor``,
+``MetricLoader``, ``BaseRiemannianSampler``, ``RiemannianHMCSampler``,
+``WorkingRiemannianSampler``, ``FlowManager``.  See DESIGN.md.
+"""
+from .metric_loader import MetricLoader
+from .metric_tensor import MetricTensor
+from .samplers import (BaseRiemannianSampler, MetricModel, RiemannianHMCSampler,
+                       WorkingRiemannianSampler)
+
+__all__ = ['MetricTensor', 'MetricLoader', 'BaseRiemannianSampler', 'MetricModel',
+           'RiemannianHMCSampler', 'WorkingRiemannianSampler']
+__version__ = '0.1.0'

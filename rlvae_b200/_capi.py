@@ -1,0 +1,261 @@
+"""ctypes binding of librlvae_b200.so (the C ABI in include/rlvae_b200.h).
+
+This is the only module that touches the shared library.  There is NO CPU
+fallback: if the library is missing, or a call is made with non-CUDA tensors,
+it raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"``
+(or ``rlvae_b200.build.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'librlvae_b200.so')
+
+PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
+GRAD_MODULAR, GRAD_EXACT = 0, 1
+
+# every symbol include/rlvae_b200.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ('rlvae_last_error', c_char_p, []),
+    ('rlvae_abi_version', c_int, []),
+    ('rlvae_tables_create', c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    ('rlvae_tables_destroy', c_int, [c_void_p]),
+    ('rlvae_tables_info', c_int, [c_void_p, POINTER(c_int64)]),
+    ('rlvae_inverse_metric', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ('rlvae_metric_grad', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p]),
+    ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_metric_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ('rlvae_hmc_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_hmc_iteration', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float,
+                                    POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_void_p]),
+    ('rlvae_hmc_refine', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int, c_void_p]),
+    ('rlvae_nearest2', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    ('rlvae_chol_apply', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f'rlvae_b200: CUDA library not built ({LIB_PATH} missing). '
+                'Run `python -c "import __graft_entry__ as g; g.build()"` first; there is no CPU fallback.')
+        h = ctypes.CDLL(LIB_PATH)
+        for name, res, args in _SIGNATURES:
+            fn = getattr(h, name)       # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().rlvae_last_error()
+        raise RuntimeError(f'{what} failed (code {rc}): {msg.decode() if msg else "?"}')
+
+
+def _stream(t: torch.Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name}: expected a torch.Tensor')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: rlvae_b200 kernels need CUDA tensors (got {t.device}); '
+                           'there is no CPU fallback')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    return t.contiguous()
+
+
+class Tables:
+    """Owner of a ``rlvae_tables_t`` handle (packed device copies of the metric tables)."""
+
+    def __init__(self, centroids: torch.Tensor, matrices: torch.Tensor, temperature: float,
+                 regularization: float):
+        c = _req(centroids, 'centroids')
+        m = _req(matrices, 'metric_matrices')
+        if c.dim() != 2 or m.dim() != 3 or m.shape != (c.shape[0], c.shape[1], c.shape[1]):
+            raise ValueError(f'inconsistent table shapes: centroids {tuple(c.shape)}, matrices {tuple(m.shape)}')
+        self.device = c.device
+        self.K, self.d = int(c.shape[0]), int(c.shape[1])
+        self.temperature, self.regularization = float(temperature), float(regularization)
+        h = c_void_p()
+        with torch.cuda.device(self.device):
+            _check(lib().rlvae_tables_create(ctypes.byref(h), _ptr(c), _ptr(m), self.K, self.d,
+                                             c_float(self.temperature), c_float(self.regularization),
+                                             _stream(c)), 'rlvae_tables_create')
+        self._h = h
+        info = (c_int64 * 8)()
+        _check(lib().rlvae_tables_info(self._h, info), 'rlvae_tables_info')
+        self.Kpad, self.symmetric = int(info[2]), bool(info[3])
+        self.tensor_capable, self.tensor_auto = bool(info[4]), bool(info[5])
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError('rlvae_b200: tables handle already destroyed')
+        return self._h
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and _lib is not None:
+            _lib.rlvae_tables_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- thin call wrappers
+def inverse_metric(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO) -> torch.Tensor:
+    z = _req(z, 'z')
+    n, d = z.shape
+    out = torch.empty((n, d, d), device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_inverse_metric(tab.handle, _ptr(z), n, _ptr(out), path, _stream(z)),
+               'rlvae_inverse_metric')
+    return out
+
+
+def batched_inverse(a: torch.Tensor, want_inv=True, want_logabsdet=False, want_sign=False,
+                    want_diag=False):
+    a = _req(a, 'a')
+    n, d = a.shape[0], a.shape[-1]
+    dev = a.device
+    inv = torch.empty_like(a) if want_inv else None
+    lad = torch.empty(n, device=dev) if want_logabsdet else None
+    sgn = torch.empty(n, device=dev) if want_sign else None
+    diag = torch.empty((n, d), device=dev) if want_diag else None
+    with torch.cuda.device(dev):
+        _check(lib().rlvae_batched_inverse(_ptr(a), n, d, _ptr(inv), _ptr(lad), _ptr(sgn), _ptr(diag),
+                                           _stream(a)), 'rlvae_batched_inverse')
+    return inv, lad, sgn, diag
+
+
+def metric_grad(tab: Tables, z: torch.Tensor, u: torch.Tensor, scale: float, path: int = PATH_AUTO):
+    z = _req(z, 'z')
+    u = _req(u, 'u')
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_metric_grad(tab.handle, _ptr(z), _ptr(u), z.shape[0], c_float(scale), _ptr(out),
+                                       path, _stream(z)), 'rlvae_metric_grad')
+    return out
+
+
+def metric_grad_pythae(tab: Tables, z: torch.Tensor, g: torch.Tensor):
+    z = _req(z, 'z')
+    g = _req(g, 'g')
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_metric_grad_pythae(tab.handle, _ptr(z), _ptr(g), z.shape[0], _ptr(out), _stream(z)),
+               'rlvae_metric_grad_pythae')
+    return out
+
+
+def metric_eval(tab: Tables, z: torch.Tensor, want_ginv=True, want_g=False, want_logdet=True,
+                want_grad=False, path: int = PATH_AUTO, out=None):
+    """-> dict(ginv, g, logdet_g, grad_logdet_g) (missing keys are None)."""
+    z = _req(z, 'z')
+    n, d = z.shape
+    dev = z.device
+    out = out or {}
+    ginv = out.get('ginv') if want_ginv else None
+    if want_ginv and ginv is None:
+        ginv = torch.empty((n, d, d), device=dev)
+    g = out.get('g') if want_g else None
+    if want_g and g is None:
+        g = torch.empty((n, d, d), device=dev)
+    ld = out.get('logdet_g') if want_logdet else None
+    if want_logdet and ld is None:
+        ld = torch.empty(n, device=dev)
+    gr = out.get('grad_logdet_g') if want_grad else None
+    if want_grad and gr is None:
+        gr = torch.empty((n, d), device=dev)
+    work = out.get('work')
+    need = int(lib().rlvae_metric_eval_workspace(n, d))
+    if work is None or work.numel() < need:
+        work = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _check(lib().rlvae_metric_eval(tab.handle, _ptr(z), n, _ptr(ginv), _ptr(g), _ptr(ld), _ptr(gr),
+                                       _ptr(work), path, _stream(z)), 'rlvae_metric_eval')
+    return dict(ginv=ginv, g=g, logdet_g=ld, grad_logdet_g=gr, work=work)
+
+
+def hmc_workspace(n: int, d: int, device) -> torch.Tensor:
+    return torch.empty(max(int(lib().rlvae_hmc_workspace(n, d)), 1), device=device, dtype=torch.uint8)
+
+
+def hmc_iteration(tab: Tables, z: torch.Tensor, gamma: torch.Tensor, acc: torch.Tensor, n_lf: int,
+                  eps_lf: float, beta_zero_sqrt: float, scales, grad_mode: int = GRAD_MODULAR,
+                  work: torch.Tensor | None = None, path: int = PATH_AUTO, want_stats: bool = False):
+    """One MCMC iteration, in place on ``z``.  Returns (h0, h1, alpha, moves) if want_stats."""
+    if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
+        raise RuntimeError('hmc_iteration: z must be a contiguous fp32 CUDA tensor (updated in place)')
+    gamma = _req(gamma, 'gamma')
+    acc = _req(acc, 'acc')
+    n, d = z.shape
+    if work is None:
+        work = hmc_workspace(n, d, z.device)
+    sc = (c_float * n_lf)(*[float(s) for s in scales])
+    stats = [torch.empty(n, device=z.device) for _ in range(4)] if want_stats else [None] * 4
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_hmc_iteration(tab.handle, _ptr(z), _ptr(gamma), _ptr(acc), n, n_lf, c_float(eps_lf),
+                                         c_float(beta_zero_sqrt), sc, grad_mode, _ptr(stats[0]), _ptr(stats[1]),
+                                         _ptr(stats[2]), _ptr(stats[3]), _ptr(work), path, _stream(z)),
+               'rlvae_hmc_iteration')
+    return tuple(stats) if want_stats else None
+
+
+def hmc_refine(tab: Tables, z: torch.Tensor, n_steps: int, step_size: float, path: int = PATH_AUTO):
+    if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
+        raise RuntimeError('hmc_refine: z must be a contiguous fp32 CUDA tensor (updated in place)')
+    n, d = z.shape
+    work = hmc_workspace(n, d, z.device)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_hmc_refine(tab.handle, _ptr(z), n, n_steps, c_float(step_size), _ptr(work), path,
+                                      _stream(z)), 'rlvae_hmc_refine')
+    return z
+
+
+def nearest2(tab: Tables, mu: torch.Tensor):
+    mu = _req(mu, 'mu')
+    n = mu.shape[0]
+    idx = torch.empty((n, 2), device=mu.device, dtype=torch.int64)
+    dist = torch.empty((n, 2), device=mu.device)
+    with torch.cuda.device(mu.device):
+        _check(lib().rlvae_nearest2(tab.handle, _ptr(mu), n, _ptr(idx), _ptr(dist), _stream(mu)), 'rlvae_nearest2')
+    return idx, dist
+
+
+def chol_apply(a: torch.Tensor, eps: torch.Tensor, jitter: float = 1e-6):
+    a = _req(a, 'a')
+    eps = _req(eps, 'eps')
+    n, d = eps.shape
+    out = torch.empty_like(eps)
+    status = torch.empty(n, device=a.device, dtype=torch.int32)
+    with torch.cuda.device(a.device):
+        _check(lib().rlvae_chol_apply(_ptr(a), _ptr(eps), n, d, c_float(jitter), _ptr(out), _ptr(status),
+                                      _stream(a)), 'rlvae_chol_apply')
+    return out, status

@@ -1,0 +1,399 @@
+// extern "C" entry points of librlvae_b200.so (declared in include/rlvae_b200.h) plus the
+// table-packing kernels behind rlvae_tables_create.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "rlvae_internal.h"
+
+namespace rlvae {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+void pythae_cache_release(const rlvae_tables* t);
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// centroid-side tables: padded c, ||c||^2, [hi|lo] stack and the exp2 bias of the tensor path
+__global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int Kpad, int d,
+                                      float inv_T2_log2e, float* __restrict__ c, float* __restrict__ cn,
+                                      float* __restrict__ cstack, float* __restrict__ cbias,
+                                      float* __restrict__ caug, float* __restrict__ stats) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  float nrm = 0.f;
+  for (int j = 0; j < d; ++j) {
+    const float v = (k < K) ? c_in[(int64_t)k * d + j] : 0.f;
+    c[(int64_t)k * d + j] = v;
+    nrm = fmaf(v, v, nrm);
+  }
+  cn[k] = nrm;
+  if (k < K) {
+    atomicAdd(&stats[0], nrm);                                  // sum ||c||^2
+    atomicMax(reinterpret_cast<int*>(&stats[1]), __float_as_int(nrm));  // max (nrm >= 0)
+  }
+  if (cstack != nullptr) {  // d == 16
+    for (int j = 0; j < 16; ++j) {
+      const float v = (k < K) ? c_in[(int64_t)k * 16 + j] : 0.f;
+      const float hi = tf32_hi(v);
+      cstack[(int64_t)k * 32 + j] = hi;
+      cstack[(int64_t)k * 32 + 16 + j] = v - hi;
+      // gradient-pass B operand: row = [hi(c) (16) | lo(c) (16)], same as cstack (kept separate
+      // so either pass can change its layout independently)
+      caug[(int64_t)k * 32 + j] = hi;
+      caug[(int64_t)k * 32 + 16 + j] = v - hi;
+    }
+    cbias[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
+  }
+}
+
+// matrix-side tables: padded natural M, and for d == 16 the TF32 hi/lo splits in both the
+// natural [Kpad,256] and the transposed [256,Kpad] (centroid-contiguous) layouts.
+__global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int Kpad, int dd,
+                                     float* __restrict__ M, float* __restrict__ mt_hi,
+                                     float* __restrict__ mt_lo, float* __restrict__ mn_hi,
+                                     float* __restrict__ mn_lo) {
+  const int64_t total = (int64_t)Kpad * dd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / dd), q = (int)(i - (int64_t)k * dd);
+    const float v = (k < K) ? m_in[i] : 0.f;
+    M[i] = v;
+    if (mt_hi != nullptr) {
+      const float hi = tf32_hi(v);
+      mn_hi[i] = hi;
+      mn_lo[i] = v - hi;
+      mt_hi[(int64_t)q * Kpad + k] = hi;
+      mt_lo[(int64_t)q * Kpad + k] = v - hi;
+    }
+  }
+}
+
+__global__ void symmetry_kernel(const float* __restrict__ m_in, int K, int d, int* __restrict__ asym) {
+  const int64_t total = (int64_t)K * d * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / (d * d);
+    const int r = (int)((i / d) % d), cidx = (int)(i % d);
+    if (r < cidx && m_in[i] != m_in[k * d * d + (int64_t)cidx * d + r]) atomicExch(asym, 1);
+  }
+}
+
+__global__ void negate_copy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = -x[i];
+}
+static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
+  negate_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, n);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static void free_tables(rlvae_tables* t) {
+  pythae_cache_release(t);
+  float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
+                    &t->Mn_hi, &t->Mn_lo, &t->caug};
+  for (float** p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
+}  // namespace rlvae
+
+using namespace rlvae;
+
+extern "C" {
+
+const char* rlvae_last_error(void) { return g_last_error.c_str(); }
+int rlvae_abi_version(void) { return 1; }
+
+int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const float* matrices,
+                        int n_centroids, int latent_dim, float temperature, float regularization,
+                        void* stream) {
+  RLVAE_REQUIRE(out != nullptr, "tables_create: out is NULL");
+  *out = nullptr;
+  RLVAE_REQUIRE(n_centroids >= 1, "tables_create: need at least one centroid");
+  RLVAE_REQUIRE(latent_dim >= 1 && latent_dim <= kMaxLatentDim, "tables_create: latent_dim must be in [1,64]");
+  RLVAE_REQUIRE(centroids != nullptr && matrices != nullptr, "tables_create: NULL table pointer");
+  RLVAE_REQUIRE(temperature != 0.f, "tables_create: temperature must be non-zero");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  rlvae_tables* t = new (std::nothrow) rlvae_tables();
+  RLVAE_REQUIRE(t != nullptr, "tables_create: out of host memory");
+  const int K = n_centroids, d = latent_dim, dd = d * d;
+  const int Kpad = (K + kKPad - 1) / kKPad * kKPad;
+  t->K = K; t->d = d; t->Kpad = Kpad;
+  t->T = temperature; t->T2 = temperature * temperature; t->lambda = regularization;
+  const bool tc = (d == 16);
+
+  float* stats = nullptr;  // [0] sum ||c||^2, [1] max ||c||^2, [2] (int) asymmetric flag
+#define ALLOC(ptr, elems)                                                          \
+  do {                                                                             \
+    cudaError_t _e = cudaMalloc(&(ptr), sizeof(float) * (size_t)(elems));          \
+    if (_e != cudaSuccess) {                                                       \
+      set_error(std::string("tables_create: cudaMalloc: ") + cudaGetErrorString(_e)); \
+      free_tables(t); delete t; if (stats) cudaFree(stats);                        \
+      return 1;                                                                    \
+    }                                                                              \
+  } while (0)
+  ALLOC(stats, 4);
+  ALLOC(t->c, (size_t)Kpad * d);
+  ALLOC(t->cn, Kpad);
+  ALLOC(t->M, (size_t)Kpad * dd);
+  if (tc) {
+    ALLOC(t->cstack, (size_t)Kpad * 32);
+    ALLOC(t->caug, (size_t)Kpad * 32);
+    ALLOC(t->cbias, Kpad);
+    ALLOC(t->Mt_hi, (size_t)Kpad * dd);
+    ALLOC(t->Mt_lo, (size_t)Kpad * dd);
+    ALLOC(t->Mn_hi, (size_t)Kpad * dd);
+    ALLOC(t->Mn_lo, (size_t)Kpad * dd);
+  }
+#undef ALLOC
+  auto fail = [&](int code) { free_tables(t); delete t; cudaFree(stats); return code; };
+#define OK_OR_FAIL(expr)                                                           \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return fail(1);                                                              \
+    }                                                                              \
+  } while (0)
+  OK_OR_FAIL(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
+  const float inv_T2_log2e = 1.4426950408889634f / t->T2;
+  pack_centroids_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(centroids, K, Kpad, d, inv_T2_log2e, t->c,
+                                                           t->cn, t->cstack, t->cbias, t->caug, stats);
+  OK_OR_FAIL(cudaGetLastError());
+  pack_matrices_kernel<<<592, 256, 0, s>>>(matrices, K, Kpad, dd, t->M, t->Mt_hi, t->Mt_lo, t->Mn_hi,
+                                           t->Mn_lo);
+  OK_OR_FAIL(cudaGetLastError());
+  symmetry_kernel<<<592, 256, 0, s>>>(matrices, K, d, reinterpret_cast<int*>(stats + 2));
+  OK_OR_FAIL(cudaGetLastError());
+  float h_stats[4];
+  OK_OR_FAIL(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
+  OK_OR_FAIL(cudaStreamSynchronize(s));
+  cudaFree(stats);
+  stats = nullptr;
+  int asym;
+  std::memcpy(&asym, &h_stats[2], sizeof(int));
+  t->symmetric = asym ? 0 : 1;
+  t->r2max = h_stats[1];
+  const float r2mean = h_stats[0] / (float)K;
+  // Accuracy gate of the expanded form ||z||^2+||c||^2-2 z.c (DESIGN.md "precision"): its
+  // absolute error ~2.5e-7*mean||c||^2 becomes a relative error /T^2 in every weight.
+  t->tensor_auto = 0;
+  if (tc) {
+    int rc = tc_build_descriptors(t);
+    if (rc != 0) return fail(rc);
+    t->tensor_capable = 1;
+    const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
+    t->tensor_auto = (rel < 2.0e-6f) ? 1 : 0;
+  }
+  *out = t;
+  return 0;
+}
+
+int rlvae_tables_destroy(rlvae_tables_t* t) {
+  if (t == nullptr) return 0;
+  free_tables(t);
+  delete t;
+  return 0;
+}
+
+int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]) {
+  RLVAE_REQUIRE(t != nullptr && info != nullptr, "tables_info: NULL argument");
+  info[0] = t->K; info[1] = t->d; info[2] = t->Kpad; info[3] = t->symmetric;
+  info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = 0; info[7] = 0;
+  return 0;
+}
+
+static int resolve_path(const rlvae_tables* t, int path, bool* use_tc) {
+  if (path == RLVAE_PATH_DIRECT) { *use_tc = false; return 0; }
+  if (path == RLVAE_PATH_TENSOR) {
+    RLVAE_REQUIRE(t->tensor_capable, "tensor path requested but not available (latent_dim must be 16)");
+    *use_tc = true; return 0;
+  }
+  RLVAE_REQUIRE(path == RLVAE_PATH_AUTO, "unknown path selector");
+  *use_tc = t->tensor_capable && t->tensor_auto;
+  return 0;
+}
+
+int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, int path,
+                         void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "inverse_metric: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "inverse_metric: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && ginv != nullptr, "inverse_metric: NULL pointer");
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return use_tc ? launch_inverse_metric_tc(t, z, n, ginv, s)
+                : launch_inverse_metric_direct(t, z, n, ginv, s);
+}
+
+int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet, float* sign,
+                          float* diag_inv, void* stream) {
+  RLVAE_REQUIRE(n >= 0, "batched_inverse: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(a != nullptr, "batched_inverse: NULL input");
+  return launch_batched_inverse(a, n, d, inv, logabsdet, sign, diag_inv,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, int64_t n, float scale,
+                      float* out, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "metric_grad: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "metric_grad: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && u != nullptr && out != nullptr, "metric_grad: NULL pointer");
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return use_tc ? launch_metric_grad_tc(t, z, u, n, scale, out, s)
+                : launch_metric_grad_direct(t, z, u, n, scale, out, s);
+}
+
+int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
+                             float* out, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "metric_grad_pythae: tables handle is NULL");
+  RLVAE_REQUIRE(n >= 0, "metric_grad_pythae: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && g != nullptr && out != nullptr, "metric_grad_pythae: NULL pointer");
+  return launch_metric_grad_pythae(t, z, g, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t rlvae_metric_eval_workspace(int64_t n, int d) {
+  return (int64_t)sizeof(float) * (2 * n * d * d + n);
+}
+
+int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
+                      float* logdet_g, float* grad_logdet_g, void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "metric_eval: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "metric_eval: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr, "metric_eval: z is NULL");
+  const int d = t->d;
+  const int64_t mat = n * d * d;
+  float* w = static_cast<float*>(work);
+  const bool need_g = (g != nullptr) || (grad_logdet_g != nullptr);
+  RLVAE_REQUIRE(work != nullptr, "metric_eval: workspace required");
+  float* ginv_buf = ginv ? ginv : w;
+  float* g_buf = g ? g : (w + mat);
+  float* lad_buf = w + 2 * mat;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = rlvae_inverse_metric(t, z, n, ginv_buf, path, stream)) return rc;
+  if (need_g || logdet_g != nullptr) {
+    if (int rc = launch_batched_inverse(ginv_buf, n, d, need_g ? g_buf : nullptr,
+                                        logdet_g ? lad_buf : nullptr, nullptr, nullptr, s))
+      return rc;
+  }
+  if (logdet_g != nullptr) {
+    // log|det G| = -log|det G^{-1}|
+    if (int rc = negate_copy(lad_buf, logdet_g, n, s)) return rc;
+  }
+  if (grad_logdet_g != nullptr) {
+    // grad_z log det G = -(2/T^2) sum_k w_k tr(G M_k) (c_k - z)
+    if (int rc = rlvae_metric_grad(t, z, g_buf, n, -2.f / t->T2, grad_logdet_g, path, stream)) return rc;
+  }
+  return 0;
+}
+
+int64_t rlvae_hmc_workspace(int64_t n, int d) {
+  // ginv, g (exact mode), diag, rho_half, z_prev, grad, logabsdet, sign, h0
+  return (int64_t)sizeof(float) * (2 * n * d * d + 4 * n * d + 3 * n);
+}
+
+int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, const float* acc,
+                        int64_t n, int n_lf, float eps_lf, float beta_zero_sqrt, const float* h_scales,
+                        int grad_mode, float* h0_out, float* h1, float* alpha, float* moves, void* work,
+                        int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "hmc_iteration: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0 && n_lf >= 1, "hmc_iteration: need n >= 0 and n_lf >= 1");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z && gamma && acc && h_scales && work, "hmc_iteration: NULL pointer");
+  RLVAE_REQUIRE(grad_mode == RLVAE_GRAD_MODULAR || grad_mode == RLVAE_GRAD_EXACT,
+                "hmc_iteration: unknown grad_mode");
+  const int d = t->d;
+  const int64_t mat = n * d * d, vec = n * d;
+  float* w = static_cast<float*>(work);
+  float* ginv = w;
+  float* gfull = w + mat;
+  float* diag = w + 2 * mat;
+  float* rho_half = diag + vec;
+  float* z_prev = rho_half + vec;
+  float* gex = z_prev + vec;
+  float* lad = gex + vec;
+  float* sgn = lad + n;
+  float* h0 = sgn + n;
+  const bool exact = grad_mode == RLVAE_GRAD_EXACT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  // one metric evaluation at the chain's current position: G^{-1}, then diag(G)/log|det|
+  auto eval = [&](const float* zz) -> int {
+    if (int rc = rlvae_inverse_metric(t, zz, n, ginv, path, stream)) return rc;
+    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, s)) return rc;
+    if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
+      if (int rc = rlvae_metric_grad(t, zz, gfull, n, 1.f / t->T2, gex, path, stream)) return rc;
+    return 0;
+  };
+
+  RLVAE_CUDA_OK(cudaMemcpyAsync(z_prev, z, sizeof(float) * vec, cudaMemcpyDeviceToDevice, s));
+  if (int rc = eval(z)) return rc;
+  if (int rc = launch_hmc_begin(z_prev, gamma, diag, lad, sgn, exact ? gex : nullptr, n, d,
+                                beta_zero_sqrt, eps_lf, t->lambda, t->T2, grad_mode, rho_half, z, h0, s))
+    return rc;
+  for (int k = 1; k <= n_lf; ++k) {
+    if (int rc = eval(z)) return rc;
+    if (int rc = launch_hmc_step(diag, lad, sgn, exact ? gex : nullptr, n, d, eps_lf, t->lambda, t->T2,
+                                 grad_mode, h_scales[k - 1], k == n_lf, rho_half, z, z_prev, acc, h0, h1,
+                                 alpha, moves, z, s))
+      return rc;
+  }
+  if (h0_out != nullptr)
+    RLVAE_CUDA_OK(cudaMemcpyAsync(h0_out, h0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, float step_size,
+                     void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "hmc_refine: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0 && n_steps >= 0, "hmc_refine: bad sizes");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z && work, "hmc_refine: NULL pointer");
+  const int d = t->d;
+  float* w = static_cast<float*>(work);
+  float* ginv = w;
+  float* diag = w + 2 * n * d * d;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_steps; ++i) {
+    if (int rc = rlvae_inverse_metric(t, z, n, ginv, path, stream)) return rc;
+    if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, s)) return rc;
+    if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;
+  }
+  return 0;
+}
+
+int rlvae_nearest2(const rlvae_tables_t* t, const float* mu, int64_t n, int64_t* idx, float* dist,
+                   void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "nearest2: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "nearest2: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(mu && idx && dist, "nearest2: NULL pointer");
+  return launch_nearest2(t, mu, n, idx, dist, static_cast<cudaStream_t>(stream));
+}
+
+int rlvae_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
+                     int32_t* status, void* stream) {
+  RLVAE_REQUIRE(n >= 0, "chol_apply: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(a && eps && out, "chol_apply: NULL pointer");
+  return launch_chol_apply(a, eps, n, d, jitter, out, status, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+

@@ -1,0 +1,98 @@
+// Internal declarations shared by the rlvae_b200 CUDA translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/rlvae_b200.h"
+
+namespace rlvae {
+
+void set_error(const std::string& msg);
+
+#define RLVAE_CUDA_OK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::rlvae::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define RLVAE_REQUIRE(cond, msg)                                                         \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::rlvae::set_error(std::string("rlvae_b200: ") + (msg));                           \
+      return 2;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+constexpr int kMaxLatentDim = 64;
+constexpr int kKPad = 128;  // centroid tables are zero-padded to a multiple of this
+
+}  // namespace rlvae
+
+// Device-resident packed tables (derived caches of the MetricTensor buffers).
+struct rlvae_tables {
+  int K = 0, d = 0, Kpad = 0;
+  float T = 0.f, T2 = 0.f, lambda = 0.f;
+  int symmetric = 0;       // every M_k bitwise symmetric
+  int tensor_capable = 0;  // d == 16 and TMA descriptors built
+  int tensor_auto = 0;     // accuracy criterion for the expanded-distance form holds
+  float r2max = 0.f;       // max_k ||c_k||^2
+
+  // natural layouts, zero padded to Kpad rows
+  float* c = nullptr;   // [Kpad, d]
+  float* cn = nullptr;  // [Kpad]  ||c_k||^2
+  float* M = nullptr;   // [Kpad, d*d]
+
+  // tensor path (d == 16)
+  float* cstack = nullptr;  // [Kpad, 32] = [tf32_hi(c) | c - hi]
+  float* cbias = nullptr;   // [Kpad]  -||c||^2 * log2(e)/T^2  (padding rows: -1e30)
+  float* Mt_hi = nullptr;   // [256, Kpad]  tf32_hi(M) transposed (centroid index contiguous)
+  float* Mt_lo = nullptr;   // [256, Kpad]  M - hi
+  float* Mn_hi = nullptr;   // [Kpad, 256]  natural, for the gradient pass
+  float* Mn_lo = nullptr;   // [Kpad, 256]
+  float* caug = nullptr;    // [Kpad, 32] gradient pass B operand: [hi(c) | 1 | 0.. | lo(c) | 0..]
+  CUtensorMap tm_cstack, tm_mt_hi, tm_mt_lo, tm_mn_hi, tm_mn_lo;
+};
+
+namespace rlvae {
+
+// ---- launchers (each returns 0 / error code, asynchronous on `s`) -----------------------------
+int launch_inverse_metric_direct(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
+                                 cudaStream_t s);
+int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float* u, int64_t n,
+                              float scale, float* out, cudaStream_t s);
+int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
+                              float* out, cudaStream_t s);
+int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
+                           float* sign, float* diag_inv, cudaStream_t s);
+int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
+                      int32_t* status, cudaStream_t s);
+int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist,
+                    cudaStream_t s);
+
+// tensor path (rlvae_tc.cu)
+int tc_build_descriptors(rlvae_tables* t);
+int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
+                             cudaStream_t s);
+int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n,
+                          float scale, float* out, cudaStream_t s);
+
+// HMC elementwise stages (rlvae_hmc.cu)
+struct HmcBeginArgs;
+int launch_hmc_begin(const float* z, const float* gamma, const float* diag_g, const float* logabsdet,
+                     const float* sign, const float* grad_exact, int64_t n, int d, float inv_b0,
+                     float eps, float lambda, float T2, int grad_mode, float* rho_half, float* z_new,
+                     float* h0, cudaStream_t s);
+int launch_hmc_step(const float* diag_g, const float* logabsdet, const float* sign,
+                    const float* grad_exact, int64_t n, int d, float eps, float lambda, float T2,
+                    int grad_mode, float scale, int last, float* rho_half, float* z_cur,
+                    const float* z_prev, const float* acc, const float* h0, float* h1, float* alpha,
+                    float* moves, float* z_out, cudaStream_t s);
+int launch_axpy_grad_modular(float* z, const float* diag_g, int64_t n, int d, float step,
+                             float lambda, float T2, cudaStream_t s);
+
+}  // namespace rlvae

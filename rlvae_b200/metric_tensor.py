@@ -1,0 +1,266 @@
+"""Drop-in ``MetricTensor`` backed by the rlvae_b200 CUDA library.
+
+Host-side mirror of ref ``src/models/components/metric_tensor.py`` (class
+``MetricTensor`` :21-275): same constructor, buffer names, method names, argument
+meaning and error behaviour, so the models, samplers and losses of the
+reference (``modular_rlvae.py:239-261``, ``loss_manager.py:106-113``,
+``base_sampler.py:60-68``) can use it unchanged.  What differs is underneath:
+
+* ``compute_inverse_metric``  -> ``rlvae_inverse_metric``  (tcgen05 3xTF32 kernel
+  or the fp32 direct kernel; never materialises [N,K] or [N,K,d,d]);
+* ``compute_metric`` / ``compute_log_det_metric`` -> ``rlvae_batched_inverse``
+  (register/shuffle Gauss-Jordan, one matrix per d lanes);
+* backward w.r.t. ``z`` -> ``rlvae_metric_grad`` (closed-form contraction), wired
+  through ``torch.autograd.Function`` so ``loss_manager.py:110-142`` and
+  ``riemannian_flow_vae.py:1030-1069`` can back-propagate through the metric.
+
+There is no CPU fallback: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+
+
+class _InverseMetricFn(torch.autograd.Function):
+    """G^{-1}(z); backward dL/dz = (2/T^2) sum_k w_k <dL/dG^{-1}, M_k> (c_k - z)."""
+
+    @staticmethod
+    def forward(ctx, z, owner, path):
+        tab = owner._tables(z.device)
+        zc = z.detach().contiguous()
+        ctx.tab, ctx.path = tab, path
+        ctx.save_for_backward(zc)
+        return _capi.inverse_metric(tab, zc, path)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (zc,) = ctx.saved_tensors
+        tab = ctx.tab
+        gz = _capi.metric_grad(tab, zc, grad_out.contiguous(), 2.0 / (tab.temperature ** 2), ctx.path)
+        return gz, None, None
+
+
+class _InverseFn(torch.autograd.Function):
+    """A -> (A^{-1}, sign det A) (batched); backward dL/dA = -A^{-T} (dL/dA^{-1}) A^{-T}."""
+
+    @staticmethod
+    def forward(ctx, a):
+        inv, _, sgn, _ = _capi.batched_inverse(a.detach(), want_inv=True, want_sign=True)
+        ctx.save_for_backward(inv)
+        ctx.mark_non_differentiable(sgn)
+        return inv, sgn
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_sign):
+        (inv,) = ctx.saved_tensors
+        it = inv.transpose(-1, -2)
+        return -(it @ grad_out @ it)
+
+
+class _LogAbsDetFn(torch.autograd.Function):
+    """A -> log|det A| (batched); backward dL/dA = g * A^{-T}."""
+
+    @staticmethod
+    def forward(ctx, a):
+        inv, lad, _, _ = _capi.batched_inverse(a.detach(), want_inv=True, want_logabsdet=True)
+        ctx.save_for_backward(inv)
+        return lad
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (inv,) = ctx.saved_tensors
+        return grad_out[:, None, None] * inv.transpose(-1, -2)
+
+
+class MetricTensor(nn.Module):
+    """G^{-1}(z) = sum_k M_k exp(-||z - c_k||^2 / T^2) + lambda I,  G = (G^{-1})^{-1}.
+
+    Buffers (names are part of the contract, ref metric_tensor.py:50-53):
+    ``centroids [K,d]``, ``metric_matrices [K,d,d]``, ``temperature``, ``regularization``.
+    ``kernel_path`` selects the implementation: 'auto' | 'direct' | 'tensor'.
+    """
+
+    _PATHS = {'auto': _capi.PATH_AUTO, 'direct': _capi.PATH_DIRECT, 'tensor': _capi.PATH_TENSOR}
+
+    def __init__(self, latent_dim: int, temperature: float = 0.1, regularization: float = 0.01,
+                 device: Optional[torch.device] = None, kernel_path: str = 'auto'):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.device = device or torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        self.register_buffer('centroids', torch.empty(0, latent_dim))
+        self.register_buffer('metric_matrices', torch.empty(0, latent_dim, latent_dim))
+        self.register_buffer('temperature', torch.tensor(temperature))
+        self.register_buffer('regularization', torch.tensor(regularization))
+        self._is_loaded = False
+        self._diagnostic_counter = 0
+        self.kernel_path = kernel_path
+        self.check_singular = True   # one [N]-sized device->host check per compute_metric call
+        self._tab = None
+        self._tab_key = None
+
+    # ------------------------------------------------------------------ loading / caches
+    def load_pretrained(self, centroids: torch.Tensor, metric_matrices: torch.Tensor,
+                        temperature: Optional[float] = None,
+                        regularization: Optional[float] = None) -> None:
+        """Install pretrained tables (accepts ``**MetricLoader.load_from_file(...)``).
+        Shape errors are ``ValueError`` like ref metric_tensor.py:76-83."""
+        if centroids.shape[1] != self.latent_dim:
+            raise ValueError(f'Centroids dimension {centroids.shape[1]} != latent_dim {self.latent_dim}')
+        if metric_matrices.shape[0] != centroids.shape[0]:
+            raise ValueError(f'Number of metric matrices {metric_matrices.shape[0]} != number of '
+                             f'centroids {centroids.shape[0]}')
+        if tuple(metric_matrices.shape[1:]) != (self.latent_dim, self.latent_dim):
+            raise ValueError(f'Metric matrix shape {tuple(metric_matrices.shape[1:])} != '
+                             f'({self.latent_dim}, {self.latent_dim})')
+        self.register_buffer('centroids', centroids.to(self.device))
+        self.register_buffer('metric_matrices', metric_matrices.to(self.device))
+        if temperature is not None:
+            self.register_buffer('temperature', torch.tensor(temperature, device=self.device))
+        if regularization is not None:
+            self.register_buffer('regularization', torch.tensor(regularization, device=self.device))
+        self._is_loaded = True
+        self._tab = None
+        print(f'✅ MetricTensor loaded: {len(centroids)} centroids, T={self.temperature.item():.3f}, '
+              f'λ={self.regularization.item():.3f}')
+
+    def _tables(self, device) -> _capi.Tables:
+        """Packed device tables: a derived cache of the four buffers, rebuilt whenever
+        they change (load_pretrained, load_state_dict, .to(), in-place edits)."""
+        c, m = self.centroids, self.metric_matrices
+        if c.device != device:
+            raise RuntimeError(f'MetricTensor tables live on {c.device} but z is on {device}; '
+                               'call .to(device) on the module first')
+        key = (c.data_ptr(), c._version, m.data_ptr(), m._version, tuple(c.shape),
+               self.temperature.data_ptr(), self.temperature._version,
+               self.regularization.data_ptr(), self.regularization._version)
+        if self._tab is None or self._tab_key != key:
+            if self._tab is not None:
+                torch.cuda.synchronize(device)   # kernels may still read the old packed copy
+                self._tab.close()
+            self._tab = _capi.Tables(c.float(), m.float(), float(self.temperature.item()),
+                                     float(self.regularization.item()))
+            self._tab_key = key
+        return self._tab
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # buffers registered empty must take the checkpoint's shapes (ref keeps tables in state_dict)
+        for name in ('centroids', 'metric_matrices'):
+            k = prefix + name
+            if k in state_dict and state_dict[k].shape != getattr(self, name).shape:
+                setattr(self, name, torch.empty_like(state_dict[k], device=getattr(self, name).device))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        if self.centroids.numel() > 0:
+            self._is_loaded = True
+        self._tab = None
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.device = self.centroids.device
+        self._tab = None
+        return out
+
+    def _path(self) -> int:
+        return self._PATHS[self.kernel_path]
+
+    def _check_ready(self, z):
+        if not self._is_loaded:
+            raise RuntimeError('Metric tensor not loaded. Call load_pretrained() first.')
+        if z.dim() != 2 or z.shape[1] != self.latent_dim:
+            raise ValueError(f'z must be [batch, {self.latent_dim}], got {tuple(z.shape)}')
+        if not z.is_cuda:
+            raise RuntimeError('rlvae_b200.MetricTensor evaluates on CUDA only (no CPU fallback); '
+                               f'got z on {z.device}')
+
+    # ------------------------------------------------------------------ A2 / A3 / A4 / A20
+    def compute_inverse_metric(self, z: torch.Tensor) -> torch.Tensor:
+        """G^{-1}(z) [N,d,d]  (ref metric_tensor.py:98-137)."""
+        self._check_ready(z)
+        return _InverseMetricFn.apply(z.float(), self, self._path())
+
+    def compute_metric(self, z: torch.Tensor) -> torch.Tensor:
+        """G(z) = inv(G^{-1}(z)) [N,d,d]  (ref metric_tensor.py:139-160).  A singular G^{-1}
+        is retried once with +1e-6 I, like the reference's LinAlgError handler."""
+        g_inv = self.compute_inverse_metric(z)
+        g, sgn = _InverseFn.apply(g_inv)
+        if self.check_singular and bool((sgn == 0).any()):   # exact zero pivot == LinAlgError
+            warnings.warn('Metric tensor inversion failed: singular matrix. Adding regularization.')
+            eye = torch.eye(self.latent_dim, device=z.device, dtype=g_inv.dtype).unsqueeze(0)
+            g, _ = _InverseFn.apply(g_inv + 1e-6 * eye)
+        return g
+
+    def compute_log_det_metric(self, z: torch.Tensor) -> torch.Tensor:
+        """log|det G(z)| [N]  (ref metric_tensor.py:162-182) = -log|det G^{-1}(z)|."""
+        return -_LogAbsDetFn.apply(self.compute_inverse_metric(z))
+
+    def compute_riemannian_distance_squared(self, z1: torch.Tensor, z2: torch.Tensor) -> torch.Tensor:
+        """(z1-z2)^T G((z1+z2)/2) (z1-z2) [N]  (ref metric_tensor.py:184-207)."""
+        g_mid = self.compute_metric(0.5 * (z1 + z2))
+        dz = z1 - z2
+        return torch.einsum('bi,bij,bj->b', dz, g_mid, dz)
+
+    # ------------------------------------------------------------------ fused / extended entry points
+    def evaluate(self, z: torch.Tensor, want_ginv=True, want_g=False, want_logdet=True,
+                 want_grad=False, out=None) -> Dict[str, Optional[torch.Tensor]]:
+        """One fused 'metric eval' (no autograd): any subset of G^{-1}, G, log det G and the
+        analytic grad_z log det G, through ``rlvae_metric_eval``."""
+        self._check_ready(z)
+        with torch.no_grad():
+            return _capi.metric_eval(self._tables(z.device), z.float(), want_ginv, want_g, want_logdet,
+                                     want_grad, self._path(), out)
+
+    def compute_grad_log_det_metric(self, z: torch.Tensor) -> torch.Tensor:
+        """Analytic grad_z log det G(z) [N,d] (north_star)."""
+        return self.evaluate(z, want_ginv=False, want_logdet=False, want_grad=True)['grad_logdet_g']
+
+    # ------------------------------------------------------------------ diagnostics (host side)
+    def diagnose_metric_properties(self, z: torch.Tensor, verbose: bool = False) -> Dict[str, Any]:
+        """Same dictionary as ref metric_tensor.py:209-261 (keys consumed by hybrid_rlvae.py:324-331)."""
+        with torch.no_grad():
+            g = self.compute_metric(z)
+            g_inv = self.compute_inverse_metric(z)
+            ev_g = torch.linalg.eigvals(g[0].cpu()).real
+            ev_gi = torch.linalg.eigvals(g_inv[0].cpu()).real
+            _, lad, sgn, _ = _capi.batched_inverse(g_inv, want_inv=False, want_logabsdet=True, want_sign=True)
+            det_gi = sgn * torch.exp(lad)
+            det_g = sgn * torch.exp(-lad)
+            tr_g = torch.diagonal(g, dim1=-2, dim2=-1).sum(-1)
+            tr_gi = torch.diagonal(g_inv, dim1=-2, dim2=-1).sum(-1)
+            d = {
+                'eigenvals_G_min': ev_g.min().item(), 'eigenvals_G_max': ev_g.max().item(),
+                'eigenvals_G_mean': ev_g.mean().item(),
+                'eigenvals_G_inv_min': ev_gi.min().item(), 'eigenvals_G_inv_max': ev_gi.max().item(),
+                'eigenvals_G_inv_mean': ev_gi.mean().item(),
+                'condition_number_G': (ev_g.max() / (ev_g.min() + 1e-8)).item(),
+                'condition_number_G_inv': (ev_gi.max() / (ev_gi.min() + 1e-8)).item(),
+                'det_G_mean': det_g.mean().item(), 'det_G_inv_mean': det_gi.mean().item(),
+                'trace_G_mean': tr_g.mean().item(), 'trace_G_inv_mean': tr_gi.mean().item(),
+                'batch_size': z.shape[0], 'n_centroids': len(self.centroids),
+                'temperature': self.temperature.item(), 'regularization': self.regularization.item(),
+            }
+            if verbose:
+                print('🔍 METRIC DIAGNOSTICS:')
+                print(f"   G eigenvalues: min={d['eigenvals_G_min']:.3e}, max={d['eigenvals_G_max']:.3e}, "
+                      f"mean={d['eigenvals_G_mean']:.3e}")
+                print(f"   G condition number: {d['condition_number_G']:.2e}")
+                print(f"   det(G): mean={d['det_G_mean']:.3e}")
+                print(f"   trace(G): mean={d['trace_G_mean']:.3e}")
+                print(f"   Batch size: {d['batch_size']}, Centroids: {d['n_centroids']}")
+            return d
+
+    def is_loaded(self) -> bool:
+        return self._is_loaded
+
+    def get_config(self) -> Dict[str, Any]:
+        return {
+            'latent_dim': self.latent_dim,
+            'temperature': self.temperature.item() if self._is_loaded else None,
+            'regularization': self.regularization.item() if self._is_loaded else None,
+            'n_centroids': len(self.centroids) if self._is_loaded else 0,
+            'is_loaded': self._is_loaded,
+        }

@@ -1,0 +1,346 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI via rlvae_b200) against
+(a) the committed outputs of the real reference (tests/golden), (b) the CPU oracle on
+fresh seeded inputs, (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are the ones north_star states: rel 1e-5 on G^{-1} and G (per-matrix
+Frobenius), 1e-4 on log det and on gradients, identical HMC accept decisions.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_fro, tables_of
+from oracle import metric_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAT = 1e-5     # G, G^{-1}: relative Frobenius per matrix
+TOL_LD = 1e-4      # log det, gradients
+
+METRIC_CASES = ['ident_k10_T01', 'metricpt_T07', 'metricpt_T30', 'scaled_T07', 'synth_d16_k300',
+                'synth_d8_k100', 'synth_d2_k20', 'synth_d32_k64', 'nonsym_d16_k48']
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def make_mt(tables, path='auto'):
+    import contextlib
+    import io
+    from rlvae_b200 import MetricTensor
+    c, M, T, lam = tables
+    mt = MetricTensor(latent_dim=c.shape[1], device=dev(), kernel_path=path)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt.load_pretrained(c.clone(), M.clone(), temperature=T, regularization=lam)
+    return mt
+
+
+def paths_for(tables):
+    """direct everywhere; the tcgen05 path additionally wherever the library itself would
+    choose it (d == 16 and its accuracy gate passes)."""
+    mt = make_mt(tables)
+    tab = mt._tables(dev())
+    return ['direct', 'tensor'] if (tab.tensor_capable and tab.tensor_auto) else ['direct']
+
+
+def close_ld(a, b, tol=TOL_LD):
+    a, b = a.double().cpu(), b.double().cpu()
+    assert torch.all((a - b).abs() <= tol * (1.0 + b.abs())), (a - b).abs().max().item()
+
+
+@pytest.mark.parametrize('case', METRIC_CASES)
+def test_metric_against_reference_golden(case):
+    g = load_golden(case)
+    t = tables_of(g)
+    for path in paths_for(t):
+        mt = make_mt(t, path)
+        z = g['z'].to(dev())
+        assert rel_fro(mt.compute_inverse_metric(z).cpu(), g['G_inv']) < TOL_MAT, path
+        assert rel_fro(mt.compute_metric(z).cpu(), g['G']) < TOL_MAT, path
+        close_ld(mt.compute_log_det_metric(z), g['logdet_G'])
+        assert rel_fro(mt.compute_grad_log_det_metric(z).cpu(), g['grad_logdet_G']) < TOL_LD, path
+        if 'riem_dist2' in g:
+            d2 = mt.compute_riemannian_distance_squared(z, g['z2'].to(dev()))
+            close_ld(d2, g['riem_dist2'], 2e-5)
+        ev = mt.evaluate(z, want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+        assert rel_fro(ev['ginv'].cpu(), g['G_inv']) < TOL_MAT
+        assert rel_fro(ev['g'].cpu(), g['G']) < TOL_MAT
+        close_ld(ev['logdet_g'], g['logdet_G'])
+        assert rel_fro(ev['grad_logdet_g'].cpu(), g['grad_logdet_G']) < TOL_LD
+
+
+@pytest.mark.parametrize('case', METRIC_CASES)
+def test_autograd_backward_against_reference(case):
+    g = load_golden(case)
+    t = tables_of(g)
+    for path in paths_for(t):
+        mt = make_mt(t, path)
+        z = g['z'].to(dev()).requires_grad_(True)
+        (mt.compute_inverse_metric(z) * g['U'].to(dev())).sum().backward()
+        assert rel_fro(z.grad.cpu(), g['grad_ginv_U']) < TOL_LD, path
+        z2 = g['z'].to(dev()).requires_grad_(True)
+        mt.compute_log_det_metric(z2).sum().backward()
+        assert rel_fro(z2.grad.cpu(), g['grad_logdet_G']) < TOL_LD, path
+        z3 = g['z'].to(dev()).requires_grad_(True)
+        w = torch.randn(g['G'].shape, generator=torch.Generator().manual_seed(5))
+        (mt.compute_metric(z3) * w.to(dev())).sum().backward()
+        zc = g['z'].clone().requires_grad_(True)
+        (O.metric(zc, *t) * w).sum().backward()
+        assert rel_fro(z3.grad.cpu(), zc.grad) < 5e-4, path
+
+
+@pytest.mark.parametrize('case', METRIC_CASES)
+def test_hmc_callables_against_reference(case):
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    g = load_golden(case)
+    t = tables_of(g)
+    if t[0].shape[0] < 2:
+        pytest.skip('needs 2 centroids')
+    for path in paths_for(t):
+        s = RiemannianHMCSampler(MetricModel(make_mt(t, path)))
+        z = g['z'].to(dev())
+        close_ld(s.log_pi(z), g['log_pi'])
+        assert rel_fro(s.grad_func(z).cpu(), g['grad_modular']) < TOL_LD
+        live = g['log_pi'] > 0.5 * math.log(1e-10) + 1e-3
+        if live.any():
+            assert rel_fro(s.grad_exact(z).cpu()[live], g['grad_log_pi'][live]) < 2e-4
+        # variant C (pythae) against the oracle restatement
+        from rlvae_b200 import _capi
+        mt = s.model.metric_tensor
+        gp = _capi.metric_grad_pythae(mt._tables(dev()), z, mt.compute_metric(z))
+        assert rel_fro(gp.cpu(), O.grad_pythae(g['z'], *t)) < 2e-4
+
+
+def test_config1_shape_against_oracle():
+    """BASELINE.json configs[0]: N=4096, d=16, K=3000 -- first 256 points vs the CPU oracle."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(3000, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    z = make_points(4096, 16, seed=1)
+    ref_ginv = O.chunked(O.inverse_metric, z[:256], *t, chunk=128)
+    ref_g = torch.linalg.inv(ref_ginv)
+    ref_ld = torch.linalg.slogdet(ref_g).logabsdet
+    ref_grad = O.chunked(O.grad_log_sqrt_det_ginv_exact, z[:256], *t, chunk=128) * -2.0
+    for path in paths_for(t):
+        mt = make_mt(t, path)
+        ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+        assert rel_fro(ev['ginv'][:256].cpu(), ref_ginv) < TOL_MAT, path
+        assert rel_fro(ev['g'][:256].cpu(), ref_g) < TOL_MAT, path
+        close_ld(ev['logdet_g'][:256], ref_ld)
+        assert rel_fro(ev['grad_logdet_g'][:256].cpu(), ref_grad) < TOL_LD, path
+
+
+def test_tensor_and_direct_paths_agree_k10k():
+    """config #2 tables (K=10k): the two independent CUDA implementations agree to tolerance on
+    8192 points, and both match the oracle on 64 of them."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    if 'tensor' not in paths_for(t):
+        pytest.skip('tensor path not selected for these tables')
+    z = make_points(8192, 16, seed=1).to(dev())
+    a = make_mt(t, 'direct').evaluate(z, want_g=True, want_grad=True)
+    b = make_mt(t, 'tensor').evaluate(z, want_g=True, want_grad=True)
+    assert rel_fro(b['ginv'].cpu(), a['ginv'].cpu()) < TOL_MAT
+    assert rel_fro(b['g'].cpu(), a['g'].cpu()) < TOL_MAT
+    close_ld(b['logdet_g'], a['logdet_g'])
+    assert rel_fro(b['grad_logdet_g'].cpu(), a['grad_logdet_g'].cpu()) < TOL_LD
+    ref = O.chunked(O.inverse_metric, z[:64].cpu(), *t, chunk=32)
+    assert rel_fro(b['ginv'][:64].cpu(), ref) < TOL_MAT
+    assert rel_fro(a['ginv'][:64].cpu(), ref) < TOL_MAT
+
+
+def test_full_size_properties_config2():
+    """N = 2^20, K = 10k, d = 16 (BASELINE.json configs[1]): properties that need no oracle."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    mt = make_mt(t, 'auto')
+    n = 1 << 20
+    z = make_points(n, 16, seed=1).to(dev())
+    ev = mt.evaluate(z, want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    ginv, g, ld = ev['ginv'], ev['g'], ev['logdet_g']
+    assert torch.isfinite(ginv).all() and torch.isfinite(g).all() and torch.isfinite(ld).all()
+    # symmetric tables -> symmetric G^{-1}
+    assert (ginv - ginv.transpose(1, 2)).abs().max().item() <= 1e-5 * ginv.abs().max().item()
+    # G G^{-1} = I on a strided subset (the reference's own printed check, test_modular_components.py:128-132)
+    sub = torch.arange(0, n, 997, device=dev())
+    eye = torch.eye(16, device=dev())
+    err = (g[sub] @ ginv[sub] - eye).flatten(1).norm(dim=1).max().item()
+    assert err < 1e-4, err
+    # log det G = -slogdet(G^{-1}) in fp64
+    ref_ld = -torch.linalg.slogdet(ginv[sub].double()).logabsdet
+    close_ld(ld[sub], ref_ld)
+    # batch-slicing invariance (tile tails): a ragged slice reproduces the same rows
+    lo, hi = 777, 777 + 4097
+    part = mt.evaluate(z[lo:hi].contiguous(), want_ginv=True, want_logdet=True)
+    assert rel_fro(part['ginv'].cpu(), ginv[lo:hi].cpu()) < 1e-6
+    # gradient: finite-difference check of log det G along a random direction (fp64 step on fp32 eval)
+    sub2 = sub[:256]
+    dirn = torch.randn(256, 16, device=dev(), generator=torch.Generator(device=dev()).manual_seed(3))
+    h = 1e-2
+    ldp = mt.evaluate((z[sub2] + h * dirn).contiguous(), want_ginv=False)['logdet_g']
+    ldm = mt.evaluate((z[sub2] - h * dirn).contiguous(), want_ginv=False)['logdet_g']
+    fd = (ldp.double() - ldm.double()) / (2 * h)
+    an = (ev['grad_logdet_g'][sub2].double() * dirn.double()).sum(1)
+    assert (fd - an).abs().max().item() < 5e-3 * (1 + an.abs().max().item())
+
+
+def test_linearity_in_tables():
+    """G^{-1} - lambda I is linear in M: eval(M1 + M2) == eval(M1) + eval(M2) - lambda I."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    a = make_synthetic_metric(500, 16, seed=4)
+    b = make_synthetic_metric(500, 16, seed=5)
+    z = make_points(1000, 16, seed=6).to(dev())
+    lam = a.regularization
+    for path in paths_for((a.centroids, a.metric_matrices, a.temperature, lam)):
+        f = lambda M: make_mt((a.centroids, M, a.temperature, lam), path).compute_inverse_metric(z)
+        lhs = f(a.metric_matrices + b.metric_matrices)
+        rhs = f(a.metric_matrices) + f(b.metric_matrices) - lam * torch.eye(16, device=dev())
+        assert rel_fro(lhs.cpu(), rhs.cpu()) < 1e-5
+
+
+def test_edge_cases_and_errors():
+    from rlvae_b200 import MetricTensor
+    from rlvae_b200.synthetic import make_synthetic_metric
+    sm = make_synthetic_metric(37, 16, seed=8)      # K not a multiple of anything
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    mt = make_mt(t)
+    # empty batch
+    out = mt.compute_inverse_metric(torch.empty(0, 16, device=dev()))
+    assert out.shape == (0, 16, 16)
+    assert mt.compute_log_det_metric(torch.empty(0, 16, device=dev())).shape == (0,)
+    # ragged batch sizes around the tile sizes
+    for n in (1, 63, 64, 65, 127, 128, 129, 257):
+        z = torch.randn(n, 16, generator=torch.Generator().manual_seed(n))
+        for path in paths_for(t):
+            got = make_mt(t, path).compute_inverse_metric(z.to(dev()))
+            assert rel_fro(got.cpu(), O.inverse_metric(z, *t)) < TOL_MAT, (n, path)
+    # far-away points: every weight underflows, G^{-1} = lambda I exactly
+    far = torch.full((5, 16), 1e3, device=dev())
+    gi = mt.compute_inverse_metric(far)
+    assert torch.equal(gi, sm.regularization * torch.eye(16, device=dev()).expand(5, 16, 16))
+    # errors mirror the reference
+    fresh = MetricTensor(latent_dim=16, device=dev())
+    with pytest.raises(RuntimeError, match='not loaded'):
+        fresh.compute_inverse_metric(torch.zeros(2, 16, device=dev()))
+    with pytest.raises(ValueError):
+        fresh.load_pretrained(torch.zeros(4, 8), torch.zeros(4, 8, 8))
+    with pytest.raises(ValueError):
+        fresh.load_pretrained(torch.zeros(4, 16), torch.zeros(5, 16, 16))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        mt.compute_inverse_metric(torch.zeros(2, 16))
+    with pytest.raises(RuntimeError, match='tensor path'):
+        sm8 = make_synthetic_metric(10, 8, seed=1)
+        make_mt((sm8.centroids, sm8.metric_matrices, sm8.temperature, sm8.regularization),
+                'tensor').compute_inverse_metric(torch.zeros(2, 8, device=dev()))
+
+
+def test_batched_inverse_general_matrices():
+    """pivoting / sign / singular handling of rlvae_batched_inverse vs torch.linalg on CPU."""
+    from rlvae_b200 import _capi
+    g = torch.Generator().manual_seed(12)
+    for d in (1, 2, 4, 8, 16, 32):
+        a = torch.randn(300, d, d, generator=g)           # general, both determinant signs
+        a[0] = torch.eye(d)[torch.randperm(d, generator=g)]   # a pure permutation
+        inv, lad, sgn, diag = _capi.batched_inverse(a.to(dev()), True, True, True, True)
+        ref = torch.linalg.inv(a.double())
+        sl = torch.linalg.slogdet(a.double())
+        good = torch.linalg.cond(a.double()) < 1e3
+        assert rel_fro(inv.cpu()[good], ref[good].float()) < 1e-3, d
+        assert torch.equal(sgn.cpu()[good].double(), sl.sign[good]), d
+        close_ld(lad.cpu()[good], sl.logabsdet[good], 1e-4)
+        assert torch.allclose(diag.cpu(), torch.diagonal(inv.cpu(), dim1=1, dim2=2))
+    sing = torch.zeros(3, 4, 4)
+    sing[1] = torch.eye(4)
+    _, lad, sgn, _ = _capi.batched_inverse(sing.to(dev()), False, True, True, False)
+    assert sgn.cpu().tolist() == [0.0, 1.0, 0.0]
+    assert lad[1].item() == 0.0 and lad[0].item() == -math.inf
+
+
+@pytest.mark.parametrize('case', ['hmc_d16_k300', 'hmc_d16_k300_beta03'])
+def test_hmc_matches_reference_chain(case):
+    """A11: same RNG stream -> same accept decisions and the same final state as the reference;
+    per-iteration teacher forcing against the oracle isolates any borderline flip."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    g = load_golden(case)
+    t = tables_of(g)
+    rec = {}
+    O.hmc_sample(t, g['z0'], g['gamma'], g['acc'], int(g['n_lf']), float(g['eps_lf']),
+                 float(g['beta_zero']), record=rec)
+    for path in paths_for(t):
+        s = RiemannianHMCSampler(MetricModel(make_mt(t, path)), mcmc_steps_nbr=g['gamma'].shape[0],
+                                 n_lf=int(g['n_lf']), eps_lf=float(g['eps_lf']),
+                                 beta_zero=float(g['beta_zero']))
+        # free-running chain vs the real reference's final state
+        zf = s.sample_with_streams(g['z0'].to(dev()), g['gamma'].to(dev()), g['acc'].to(dev()))
+        torch.testing.assert_close(zf.cpu(), g['z_final'], rtol=1e-4, atol=1e-4)
+        # teacher-forced, per iteration
+        forced = [g['z0']] + rec['z'][:-1]
+        got = {}
+        s.sample_with_streams(g['z0'].to(dev()), g['gamma'].to(dev()), g['acc'].to(dev()),
+                              z_forced=[f.to(dev()) for f in forced], record=got)
+        mism = 0
+        for i in range(len(forced)):
+            close_ld(got['H0'][i], rec['H0'][i], 1e-4)
+            close_ld(got['H'][i], rec['H'][i], 1e-4)
+            flip = got['moves'][i].cpu() != rec['moves'][i]
+            # a flip is only tolerable when acc sits within rounding of alpha
+            assert torch.all((g['acc'][i][flip] - rec['alpha'][i][flip]).abs() < 1e-5)
+            mism += int(flip.sum())
+            same = ~flip
+            torch.testing.assert_close(got['z'][i].cpu()[same], rec['z'][i][same], rtol=1e-4, atol=1e-4)
+        assert mism == 0, f'{mism} accept decisions differ'
+
+
+@pytest.mark.parametrize('case', ['samplers_metricpt_T07', 'samplers_synth_d16_k300'])
+def test_samplers_match_reference(case):
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler, WorkingRiemannianSampler, _capi
+    g = load_golden(case)
+    t = tables_of(g)
+    for path in paths_for(t):
+        model = MetricModel(make_mt(t, path))
+        ws, hs = WorkingRiemannianSampler(model), RiemannianHMCSampler(model)
+        D = lambda k: g[k].to(dev())
+        mu, lv = D('mu'), D('log_var')
+        idx, dist = _capi.nearest2(model.metric_tensor._tables(dev()), mu)
+        assert torch.equal(idx.cpu(), g['near_idx'])
+        torch.testing.assert_close(dist.cpu(), g['near_dist'], rtol=1e-5, atol=1e-6)
+        tc = lambda a, b: torch.testing.assert_close(a.cpu(), b, rtol=2e-5, atol=2e-5)
+        tc(ws.enhanced_with_noise(mu, lv, D('enhanced_eps')), g['enhanced_z'])
+        tc(ws.geodesic_with_noise(mu, lv, D('geodesic_eps'), D('geodesic_t')), g['geodesic_z'])
+        tc(ws.basic_with_noise(mu, lv, D('basic_eps')), g['basic_z'])
+        tc(ws.geodesic_prior_with_noise(D('prior_idx1'), D('prior_idx2'), D('prior_t'), D('prior_eps')),
+           g['prior_z'])
+        tc(hs.refine_with_eps(mu, lv, D('refine_eps')), g['refine_z'])
+        zp = hs.sample_posterior_with_streams(mu[:8], lv[:8], D('post_eps0'), D('post_gamma'))
+        torch.testing.assert_close(zp.cpu(), g['post_z'], rtol=1e-4, atol=1e-4)
+        # public entry points run, keep shapes, and stay differentiable w.r.t. mu where the reference is
+        for m in ('enhanced', 'geodesic', 'basic', 'standard'):
+            assert ws.sample_riemannian_latents(mu, lv, method=m).shape == mu.shape
+        for m in ('geodesic', 'centroid_aware', 'weighted_mixture', 'basic'):
+            assert ws.sample_prior(7, method=m).shape == (7, mu.shape[1])
+        mug = mu.clone().requires_grad_(True)
+        ws.enhanced_with_noise(mug, lv, D('enhanced_eps')).sum().backward()
+        mur = g['mu'].clone().requires_grad_(True)
+        O.sample_enhanced(mur, g['log_var'], g['enhanced_eps'], t).sum().backward()
+        torch.testing.assert_close(mug.grad.cpu(), mur.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_state_dict_and_device_moves_rebuild_tables():
+    from rlvae_b200 import MetricTensor
+    from rlvae_b200.synthetic import make_synthetic_metric
+    a = make_synthetic_metric(40, 16, seed=1)
+    b = make_synthetic_metric(55, 16, seed=2)
+    mta = make_mt((a.centroids, a.metric_matrices, a.temperature, a.regularization))
+    mtb = make_mt((b.centroids, b.metric_matrices, b.temperature, b.regularization))
+    z = torch.randn(9, 16, device=dev())
+    ga, gb = mta.compute_inverse_metric(z), mtb.compute_inverse_metric(z)
+    fresh = MetricTensor(latent_dim=16, device=dev())
+    fresh.load_state_dict(mtb.state_dict())
+    fresh.to(dev())
+    assert torch.equal(fresh.compute_inverse_metric(z), gb)
+    mta.load_state_dict(mtb.state_dict())
+    assert torch.equal(mta.compute_inverse_metric(z), gb) and not torch.equal(ga, gb)
