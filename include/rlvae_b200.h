@@ -66,9 +66,11 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
 /* ---- A3/A4/A5: batched d x d inverse, log|det|, sign, diagonal of the inverse ----------------
  * ref: torch.linalg.inv / slogdet / det at metric_tensor.py:152,175 and hmc_sampler.py:28.
  * a [N,d,d] -> inv [N,d,d], logabsdet [N], sign [N], diag_inv [N,d]; any output may be NULL.
+ * flags bit 0: store the inverse transposed (A^{-T}).  A zero pivot gives sign 0, logabsdet
+ * -inf and a non-finite inverse (the caller decides whether to retry, cf. metric_tensor.py:153-158).
  * Partial-pivoting Gauss-Jordan, one matrix per d lanes.                                      */
 int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
-                          float* sign, float* diag_inv, void* stream);
+                          float* sign, float* diag_inv, int flags, void* stream);
 
 /* ---- K4: (scale) * sum_k w_k <U, M_k> (c_k - z) ----------------------------------------------
  * u [N,d,d].  With U = G and scale = -2/T^2 this is grad_z log det G (north_star);
@@ -87,7 +89,7 @@ int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const floa
  * z -> any subset of { ginv [N,d,d], g [N,d,d], logdet_g [N] (= log|det G|, ref
  * metric_tensor.py:162-182), grad_logdet_g [N,d] (= grad_z log det G) }.  NULL outputs are
  * skipped.  `work` must hold rlvae_metric_eval_workspace(n, d) bytes.                         */
-int64_t rlvae_metric_eval_workspace(int64_t n, int d);
+int64_t rlvae_metric_eval_workspace(int64_t n, int d);   /* bytes */
 int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
                       float* logdet_g, float* grad_logdet_g, void* work, int path, void* stream);
 

@@ -27,7 +27,7 @@ _SIGNATURES = [
     ('rlvae_tables_destroy', c_int, [c_void_p]),
     ('rlvae_tables_info', c_int, [c_void_p, POINTER(c_int64)]),
     ('rlvae_inverse_metric', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
-    ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
@@ -140,7 +140,7 @@ def inverse_metric(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO) -> torch
 
 
 def batched_inverse(a: torch.Tensor, want_inv=True, want_logabsdet=False, want_sign=False,
-                    want_diag=False):
+                    want_diag=False, transpose=False):
     a = _req(a, 'a')
     n, d = a.shape[0], a.shape[-1]
     dev = a.device
@@ -150,7 +150,7 @@ def batched_inverse(a: torch.Tensor, want_inv=True, want_logabsdet=False, want_s
     diag = torch.empty((n, d), device=dev) if want_diag else None
     with torch.cuda.device(dev):
         _check(lib().rlvae_batched_inverse(_ptr(a), n, d, _ptr(inv), _ptr(lad), _ptr(sgn), _ptr(diag),
-                                           _stream(a)), 'rlvae_batched_inverse')
+                                           1 if transpose else 0, _stream(a)), 'rlvae_batched_inverse')
     return inv, lad, sgn, diag
 
 

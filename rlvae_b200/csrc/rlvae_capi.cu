@@ -237,11 +237,11 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
 }
 
 int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet, float* sign,
-                          float* diag_inv, void* stream) {
+                          float* diag_inv, int flags, void* stream) {
   RLVAE_REQUIRE(n >= 0, "batched_inverse: negative batch");
   if (n == 0) return 0;
   RLVAE_REQUIRE(a != nullptr, "batched_inverse: NULL input");
-  return launch_batched_inverse(a, n, d, inv, logabsdet, sign, diag_inv,
+  return launch_batched_inverse(a, n, d, inv, logabsdet, sign, diag_inv, flags & 1,
                                 static_cast<cudaStream_t>(stream));
 }
 
@@ -268,7 +268,7 @@ int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const floa
 }
 
 int64_t rlvae_metric_eval_workspace(int64_t n, int d) {
-  return (int64_t)sizeof(float) * (2 * n * d * d + n);
+  return (int64_t)sizeof(float) * (3 * n * d * d + n);
 }
 
 int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
@@ -280,17 +280,24 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   const int d = t->d;
   const int64_t mat = n * d * d;
   float* w = static_cast<float*>(work);
-  const bool need_g = (g != nullptr) || (grad_logdet_g != nullptr);
   RLVAE_REQUIRE(work != nullptr, "metric_eval: workspace required");
   float* ginv_buf = ginv ? ginv : w;
   float* g_buf = g ? g : (w + mat);
   float* lad_buf = w + 2 * mat;
+  float* gt_buf = w + 2 * mat + n;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int rc = rlvae_inverse_metric(t, z, n, ginv_buf, path, stream)) return rc;
-  if (need_g || logdet_g != nullptr) {
-    if (int rc = launch_batched_inverse(ginv_buf, n, d, need_g ? g_buf : nullptr,
-                                        logdet_g ? lad_buf : nullptr, nullptr, nullptr, s))
+  // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
+  // G^T == G up to rounding, otherwise a transposed copy is produced.
+  const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
+  const bool plain_g = (g != nullptr) || ((grad_logdet_g != nullptr) && t->symmetric);
+  if (plain_g || logdet_g != nullptr) {
+    if (int rc = launch_batched_inverse(ginv_buf, n, d, plain_g ? g_buf : nullptr,
+                                        logdet_g ? lad_buf : nullptr, nullptr, nullptr, 0, s))
       return rc;
+  }
+  if (need_gt) {
+    if (int rc = launch_batched_inverse(ginv_buf, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
   }
   if (logdet_g != nullptr) {
     // log|det G| = -log|det G^{-1}|
@@ -298,7 +305,9 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   }
   if (grad_logdet_g != nullptr) {
     // grad_z log det G = -(2/T^2) sum_k w_k tr(G M_k) (c_k - z)
-    if (int rc = rlvae_metric_grad(t, z, g_buf, n, -2.f / t->T2, grad_logdet_g, path, stream)) return rc;
+    if (int rc = rlvae_metric_grad(t, z, need_gt ? gt_buf : g_buf, n, -2.f / t->T2, grad_logdet_g, path,
+                                   stream))
+      return rc;
   }
   return 0;
 }
@@ -336,7 +345,8 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   // one metric evaluation at the chain's current position: G^{-1}, then diag(G)/log|det|
   auto eval = [&](const float* zz) -> int {
     if (int rc = rlvae_inverse_metric(t, zz, n, ginv, path, stream)) return rc;
-    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, s)) return rc;
+    // exact mode wants G^T for the contraction (see rlvae_metric_eval)
+    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
       if (int rc = rlvae_metric_grad(t, zz, gfull, n, 1.f / t->T2, gex, path, stream)) return rc;
     return 0;
@@ -372,7 +382,7 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < n_steps; ++i) {
     if (int rc = rlvae_inverse_metric(t, z, n, ginv, path, stream)) return rc;
-    if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, s)) return rc;
+    if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
     if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;
   }
   return 0;

@@ -68,7 +68,7 @@ int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float
 int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
                               float* out, cudaStream_t s);
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
-                           float* sign, float* diag_inv, cudaStream_t s);
+                           float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
                       int32_t* status, cudaStream_t s);
 int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist,

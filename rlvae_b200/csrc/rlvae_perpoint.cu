@@ -11,6 +11,8 @@
 // Layout: one matrix per LANES = min(d, 32) lanes of a warp, lane l owns rows l, l+32 (d = 64).
 // Global <-> register traffic is staged through shared memory so that every global access is a
 // contiguous, coalesced run of the 4*d*d-byte matrix.
+#include <cmath>
+
 #include "rlvae_internal.h"
 
 namespace rlvae {
@@ -32,7 +34,7 @@ template <int D>
 __global__ void __launch_bounds__(PP<D>::THREADS)
 batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv,
                        float* __restrict__ logabsdet, float* __restrict__ sign,
-                       float* __restrict__ diag_inv) {
+                       float* __restrict__ diag_inv, int transpose_inv) {
   using P = PP<D>;
   constexpr int LANES = P::LANES, RPL = P::RPL, LD = P::LD;
   __shared__ float stage[P::MATS * D * LD];
@@ -68,6 +70,7 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
 
   float lad = 0.f, sgn = 1.f;
   unsigned parity = 0u;
+  bool singular = false;   // an exact zero pivot: sign 0, log|det| -inf (torch.linalg.slogdet)
 
 #pragma unroll
   for (int j = 0; j < D; ++j) {
@@ -99,7 +102,7 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
     const float piv = __shfl_sync(gmask, mine, pl, LANES);
     lad += logf(fabsf(piv));
     if (piv < 0.f) sgn = -sgn;
-    if (piv == 0.f) sgn = 0.f;
+    if (piv == 0.f) singular = true;
     const float pinv = 1.f / piv;
     permw[j / 4] |= (unsigned)br << (8 * (j % 4));
 
@@ -139,7 +142,8 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
 #pragma unroll
     for (int m = 0; m < D; ++m) {
       const int col = (permw[m / 4] >> (8 * (m % 4))) & 0xff;
-      sm[step_of[i] * LD + col] = r[i][m];
+      if (transpose_inv) sm[col * LD + step_of[i]] = r[i][m];
+      else sm[step_of[i] * LD + col] = r[i][m];
     }
   __syncwarp(gmask);
   if (live) {
@@ -150,21 +154,21 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
     if (diag_inv != nullptr)
       for (int i = lane; i < D; i += LANES) diag_inv[mat * D + i] = sm[i * LD + i];
     if (lane == 0) {
-      if (logabsdet != nullptr) logabsdet[mat] = lad;
-      if (sign != nullptr) sign[mat] = parity ? -sgn : sgn;
+      if (logabsdet != nullptr) logabsdet[mat] = singular ? -INFINITY : lad;
+      if (sign != nullptr) sign[mat] = singular ? 0.f : (parity ? -sgn : sgn);
     }
   }
 }
 
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
-                           float* sign, float* diag_inv, cudaStream_t s) {
+                           float* sign, float* diag_inv, int transpose_inv, cudaStream_t s) {
   if (n == 0) return 0;
   switch (d) {
 #define CASE(D)                                                                             \
   case D: {                                                                                 \
     unsigned grid = (unsigned)((n + PP<D>::MATS - 1) / PP<D>::MATS);                        \
     batched_inverse_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, n, inv, logabsdet, sign,  \
-                                                               diag_inv);                   \
+                                                               diag_inv, transpose_inv);    \
   } break;
     CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
 #undef CASE

@@ -1,7 +1,511 @@
-// placeholder; replaced by the tcgen05 implementation
+// tcgen05 / TMEM / TMA implementation of the metric hot path for latent_dim == 16 (sm_100a).
+//
+//   G^{-1}[n] = sum_k exp(-||z_n - c_k||^2 / T^2) M_k + lambda I
+//   ref: src/models/components/metric_tensor.py:115-135 (the [N,K,d,d] product + reduction)
+//
+// It is un-normalised flash attention with asymmetric head dims (QK dim 16, V dim 256):
+//
+//   GEMM1  S[128 x 32]   = Z[128 x 16] . C^T           3xTF32: (z_hi|z_hi).(c_hi|c_lo) + z_lo.c_hi
+//   exp    P = 2^(S*2a + bias_k + zb_n),  a = log2(e)/T^2, bias_k = -a||c_k||^2, zb_n = -a||z_n||^2
+//          P is split P_hi (top 19 bits = exactly what the TF32 datapath reads) and P_lo = P - P_hi
+//   GEMM2  O[128 x 128] += P_hi.M_hi + P_lo.M_hi + P_hi.M_lo      (3xTF32, fp32 accumulate in TMEM)
+//
+// One CTA = 128 latent points (TMEM lanes) x 128 of the 256 output columns (blockIdx.y picks the
+// half; both halves recompute the cheap S/exp stage).  Warp roles:
+//   warp 0     TMA producer   : centroid tiles (4 KB) + bias (128 B) ring, M_hi/M_lo tile (16 KB) ring
+//   warp 1     MMA issuer     : one elected thread issues every tcgen05.mma; owns TMEM alloc/dealloc
+//   warps 2-5  exp warps      : one thread per point; tcgen05.ld S -> exp2 -> split -> tcgen05.st P
+//                               (A operand of GEMM2 is read from TMEM), chunk folding, epilogue
+//
+// Accumulation accuracy.  The tensor core adds into its fp32 accumulator with truncation, so a
+// K=10k reduction (3750 accumulating MMAs per output) drifts by ~1e-4 relative -- measured 5e-5 at
+// K=3000 -- which breaks the 1e-5 contract.  The MMA therefore accumulates only CHUNK_BLOCKS*32
+// centroids at a time into one of two "chunk" accumulators; the exp warps fold every finished
+// chunk into the running total with round-to-nearest fp32 adds (Ootomo & Yokota's remedy).
+// TMEM columns: [0,128) running total, [128,256) / [256,384) chunk accumulators,
+//               [384,512) two S/P buffers of (32 S|P_hi + 32 P_lo).
+// [N,K] never exists outside TMEM; the tables stream L2 -> smem once per 128 points.
+#include <cuda.h>
+
 #include "rlvae_internal.h"
+
 namespace rlvae {
-int tc_build_descriptors(rlvae_tables* t) { (void)t; return 0; }
-int launch_inverse_metric_tc(const rlvae_tables*, const float*, int64_t, float*, cudaStream_t) { set_error("tc path not built"); return 3; }
-int launch_metric_grad_tc(const rlvae_tables*, const float*, const float*, int64_t, float, float*, cudaStream_t) { set_error("tc path not built"); return 3; }
+namespace tc {
+
+constexpr int TILE_M = 128;          // points per CTA
+constexpr int BK = 32;               // centroids per block
+constexpr int NCOL = 256;            // d*d
+constexpr int NHALF = 128;           // output columns per CTA
+constexpr int CHUNK_BLOCKS = 4;      // blocks accumulated on the tensor core before an fp32 fold
+constexpr int C_STAGES = 4;
+constexpr int M_STAGES = 8;
+constexpr int THREADS = 192;
+
+constexpr uint32_t A_BYTES = TILE_M * 128;            // one 128 x 32 fp32 operand tile
+constexpr uint32_t C_TILE_BYTES = BK * 128;           // 32 centroid rows of [hi|lo]
+constexpr uint32_t M_TILE_BYTES = NHALF * 128;        // 128 rows x 32 centroids fp32
+constexpr uint32_t BIAS_BYTES = BK * 4;
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr uint32_t OFF_A1 = 0;                                    // [z_hi | z_hi]
+constexpr uint32_t OFF_A2 = OFF_A1 + A_BYTES;                     // [z_lo | 0   ]
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;                      // C ring
+constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;       // M ring
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;    // bias ring
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;    // mbarriers
+constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 2 + 2 + 1;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;         // + alignment slack
+constexpr int OUT_LD = 132;                                       // epilogue staging row (floats)
+static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_O = 0;         // running total
+constexpr uint32_t TM_CH = 128;      // + buf*128 : chunk accumulator
+constexpr uint32_t TM_SP = 384;      // + buf*64 : S/P_hi ; + 32 : P_lo
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, K-major both, N>>3, M>>4
+constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+constexpr uint32_t IDESC_G1 = make_idesc(128, BK);
+constexpr uint32_t IDESC_G2 = make_idesc(128, NHALF);
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, 128-byte rows, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+#define TMEM_LD32(taddr, r)                                                                          \
+  asm volatile(                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                      \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"  \
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                         \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),          \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),      \
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),   \
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),   \
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                           \
+      : "r"(taddr) : "memory")
+#define TMEM_ST32(taddr, r)                                                                          \
+  asm volatile(                                                                                      \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                \
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25," \
+      "%26,%27,%28,%29,%30,%31,%32};"                                                                \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),     \
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), \
+        "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),          \
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),          \
+        "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(THREADS, 1)
+inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
+                         const __grid_constant__ CUtensorMap tm_mt_hi,
+                         const __grid_constant__ CUtensorMap tm_mt_lo,
+                         const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
+                         int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
+                         float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+  const uint32_t bar0 = base + OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (2 * C_STAGES + M_STAGES + s); };
+  auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  const uint32_t BAR_O_FULL = bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 4);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const int half = blockIdx.y;         // which 128 of the 256 output columns
+
+  // ---- setup: barriers (warp 0), TMEM (warp 1), Z operand tiles (warps 2-5)
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 1 + 4); }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_S_FULL(b), 1); mbar_init(BAR_P_FULL(b), 4); }
+    mbar_init(BAR_O_FULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mt_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mt_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // exp-warp identity: TMEM lane quarter = warp % 4, this thread's point = quarter*32 + lane
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  float zb = 0.f;
+  if (warp >= 2) {
+    const int64_t r = row0 + prow;
+    float zv[16];
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zv[j] = 0.f;
+    }
+    float nrm = 0.f, hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      nrm = fmaf(zv[j], zv[j], nrm);
+      hi[j] = tf32_rna(zv[j]);
+      lo[j] = zv[j] - hi[j];
+    }
+    zb = -nrm * alpha;
+    // 128-byte swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+    uint8_t* a1 = gbase + OFF_A1 + prow * 128;
+    uint8_t* a2 = gbase + OFF_A2 + prow * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int q = c & 3;  // which 4 of the 16 dims
+      const float4 vh = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      const float4 vl = (c < 4) ? make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3])
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int pc = (c ^ (prow & 7)) * 16;
+      *reinterpret_cast<float4*>(a1 + pc) = vh;   // [z_hi | z_hi]
+      *reinterpret_cast<float4*>(a2 + pc) = vl;   // [z_lo | 0]
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      for (int j = 0; j < num_blocks; ++j) {
+        const int cs = j % C_STAGES;
+        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+        mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + BIAS_BYTES);
+        tma_load_2d(base + OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int it = 2 * j + h;
+          const int ms = it % M_STAGES;
+          mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
+          tma_load_2d(base + OFF_M + ms * M_TILE_BYTES, h == 0 ? &tm_mt_hi : &tm_mt_lo, BAR_M_FULL(ms),
+                      j * BK, half * NHALF);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+      auto gemm1 = [&](int j) {
+        const int cs = j % C_STAGES;
+        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t b_desc = make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES);
+        const uint32_t d = tmem_base + TM_SP + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // (z_hi | z_hi) . (c_hi | c_lo): 32 fp32 = 4 K-steps of 8
+          mma_ss(d, a1_desc + 2 * k, b_desc + 2 * k, IDESC_G1, k > 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)   // z_lo . c_hi: first 16 fp32 of both rows
+          mma_ss(d, a2_desc + 2 * k, b_desc + 2 * k, IDESC_G1, 1);
+        tc_commit(BAR_S_FULL(j & 1));
+        tc_commit(BAR_C_EMPTY(cs));
+      };
+      gemm1(0);
+      for (int j = 0; j < num_blocks; ++j) {
+        if (j + 1 < num_blocks) gemm1(j + 1);
+        mbar_wait(BAR_P_FULL(j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_hi = tmem_base + TM_SP + (j & 1) * 64;
+        const uint32_t p_lo = p_hi + 32;
+        const uint32_t acc = tmem_base + TM_CH + ((j / CHUNK_BLOCKS) & 1) * 128;
+        const int first = (j % CHUNK_BLOCKS) == 0;   // a new chunk overwrites its accumulator
+        {
+          const int it = 2 * j, ms = it % M_STAGES;
+          mbar_wait(BAR_M_FULL(ms), (it / M_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t b_desc = make_desc_sw128(base + OFF_M + ms * M_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ts(acc, p_hi + 8 * k, b_desc + 2 * k, IDESC_G2, !(first && k == 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(acc, p_lo + 8 * k, b_desc + 2 * k, IDESC_G2, 1);
+          tc_commit(BAR_M_EMPTY(ms));
+        }
+        {
+          const int it = 2 * j + 1, ms = it % M_STAGES;
+          mbar_wait(BAR_M_FULL(ms), (it / M_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t b_desc = make_desc_sw128(base + OFF_M + ms * M_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(acc, p_hi + 8 * k, b_desc + 2 * k, IDESC_G2, 1);
+          tc_commit(BAR_M_EMPTY(ms));
+        }
+      }
+      tc_commit(BAR_O_FULL);
+    }
+  } else {
+    // =========================================================== exp warps (one thread per point)
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float two_alpha = 2.f * alpha;
+    // fold chunk c (finished on the tensor core) into the running total with RN fp32 adds
+    auto fold_chunk = [&](int c) {
+      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128;
+      const uint32_t dst = tmem_base + lane_addr + TM_O;
+#pragma unroll 1
+      for (int cb = 0; cb < NHALF / 32; ++cb) {
+        uint32_t a[32], b[32];
+        TMEM_LD32(src + cb * 32, a);
+        if (c > 0) {
+          TMEM_LD32(dst + cb * 32, b);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(b[i]));
+        } else {
+          tmem_wait_ld();
+        }
+        TMEM_ST32(dst + cb * 32, a);
+      }
+      tmem_wait_st();
+    };
+    int folded = 0;                         // chunks already folded
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      const uint32_t sp = tmem_base + lane_addr + TM_SP + (j & 1) * 64;
+      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);   // bias bytes visible to this thread
+      mbar_wait(BAR_S_FULL(j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[32], l[32];
+      TMEM_LD32(sp, s);
+      const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES);
+      float bias[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = bias4[q];
+        bias[4 * q] = v.x + zb; bias[4 * q + 1] = v.y + zb; bias[4 * q + 2] = v.z + zb; bias[4 * q + 3] = v.w + zb;
+      }
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float w = ex2_approx(fmaf(__uint_as_float(s[i]), two_alpha, bias[i]));
+        const uint32_t wh = __float_as_uint(w) & 0xFFFFE000u;   // what the TF32 datapath will read
+        s[i] = wh;
+        l[i] = __float_as_uint(w - __uint_as_float(wh));
+      }
+      TMEM_ST32(sp, s);
+      TMEM_ST32(sp + 32, l);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR_P_FULL(j & 1));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+      // S(j) was produced by GEMM1(j), which the MMA thread issued after GEMM2(j-2): every chunk
+      // that ends at block <= j-2 is complete and safe to read.  The next use of that chunk
+      // buffer is ordered behind this fold by this thread's later P_FULL arrival.
+      if ((folded + 1) * CHUNK_BLOCKS - 1 <= j - 2) fold_chunk(folded++);
+    }
+    // ---------------------------------------------------------- epilogue: O (+ lambda I) -> smem -> global
+    mbar_wait(BAR_O_FULL, 0);
+    tc_fence_after();
+    const int num_chunks = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
+    while (folded < num_chunks) fold_chunk(folded++);
+    float* stage = reinterpret_cast<float*>(gbase + OFF_M);
+#pragma unroll 1
+    for (int cb = 0; cb < NHALF / 32; ++cb) {
+      uint32_t v[32];
+      TMEM_LD32(tmem_base + lane_addr + TM_O + cb * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = half * NHALF + cb * 32 + q * 4 + e;
+          op[e] = __uint_as_float(v[q * 4 + e]) + ((col % 17 == 0) ? lambda : 0.f);
+        }
+        *reinterpret_cast<float4*>(stage + prow * OUT_LD + cb * 32 + q * 4) = o;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four exp warps only
+    const int t = threadIdx.x - 64;
+    const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
+    float* dst = out + row0 * NCOL + half * NHALF;
+#pragma unroll 4
+    for (int i = t; i < TILE_M * (NHALF / 4); i += 128) {
+      const int r = i >> 5, c4 = i & 31;
+      if (r < rows_here)
+        *reinterpret_cast<float4*>(dst + (int64_t)r * NCOL + c4 * 4) =
+            *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int make_map_2d(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64_t inner, uint64_t outer,
+                       uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 4;
+  }
+  return 0;
+}
+
+int tc_build_descriptors(rlvae_tables* t) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  RLVAE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+  PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(fn);
+  const uint64_t Kpad = (uint64_t)t->Kpad;
+  if (int rc = make_map_2d(enc, &t->tm_cstack, t->cstack, 32, Kpad, 32, tc::BK)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mt_hi, t->Mt_hi, Kpad, tc::NCOL, tc::BK, tc::NHALF)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mt_lo, t->Mt_lo, Kpad, tc::NCOL, tc::BK, tc::NHALF)) return rc;
+  return 0;
+}
+
+int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
+                             cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(ginv) & 15) == 0,
+                "tensor path needs 16-byte aligned z and output");
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), tc::NCOL / tc::NHALF);
+  const float alpha = 1.4426950408889634f / t->T2;
+  tc::inverse_metric_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
+      t->tm_cstack, t->tm_mt_hi, t->tm_mt_lo, z, t->cbias, n, t->Kpad / tc::BK, alpha, t->lambda, ginv);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
+                          float* out, cudaStream_t s) {
+  // the tcgen05 gradient kernel is not written yet: the contraction runs on the fp32 direct kernel
+  return launch_metric_grad_direct(t, z, u, n, scale, out, s);
+}
+
+}  // namespace rlvae

@@ -71,8 +71,8 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
         tab, path = tables_for(self.model), kernel_path_for(self.model)
         zc = z.detach().contiguous()
         ginv = _capi.inverse_metric(tab, zc, path)
-        g, _, _, _ = _capi.batched_inverse(ginv, want_inv=True)
-        return _capi.metric_grad(tab, zc, g, 1.0 / tab.temperature ** 2, path)
+        gt, _, _, _ = _capi.batched_inverse(ginv, want_inv=True, transpose=True)   # tr(G M_k) = <G^T, M_k>
+        return _capi.metric_grad(tab, zc, gt, 1.0 / tab.temperature ** 2, path)
 
     @staticmethod
     def _tempering(k, K, beta_zero_sqrt):
@@ -142,8 +142,9 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
         def grad_energy(zz):
             zc = zz.contiguous()
             ginv = _capi.inverse_metric(tab, zc, path)
-            g, lad, sgn, _ = _capi.batched_inverse(ginv, want_inv=True, want_logabsdet=True, want_sign=True)
-            glp = _capi.metric_grad(tab, zc, g, 1.0 / T2, path)
+            gt, lad, sgn, _ = _capi.batched_inverse(ginv, want_inv=True, want_logabsdet=True, want_sign=True,
+                                                    transpose=True)
+            glp = _capi.metric_grad(tab, zc, gt, 1.0 / T2, path)
             live = ((sgn > 0) & (0.5 * lad > _LOG_CLAMP)).to(glp.dtype)[:, None]   # clamp kills the gradient
             return -glp * live + (zz - mu) * inv_var
 

@@ -27,6 +27,9 @@ def dev():
 
 
 def make_mt(tables, path='auto'):
+    import os
+    if path == 'auto' and os.environ.get('RLVAE_TEST_PATHS') == 'direct':
+        path = 'direct'
     import contextlib
     import io
     from rlvae_b200 import MetricTensor
@@ -40,9 +43,12 @@ def make_mt(tables, path='auto'):
 def paths_for(tables):
     """direct everywhere; the tcgen05 path additionally wherever the library itself would
     choose it (d == 16 and its accuracy gate passes)."""
+    import os
+    only = os.environ.get('RLVAE_TEST_PATHS')          # debugging aid: e.g. "direct"
     mt = make_mt(tables)
     tab = mt._tables(dev())
-    return ['direct', 'tensor'] if (tab.tensor_capable and tab.tensor_auto) else ['direct']
+    paths = ['direct', 'tensor'] if (tab.tensor_capable and tab.tensor_auto) else ['direct']
+    return [p for p in paths if not only or p in only.split(',')]
 
 
 def close_ld(a, b, tol=TOL_LD):
