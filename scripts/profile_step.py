@@ -1,0 +1,26 @@
+"""One fused metric-evaluation step at BASELINE.json configs[1] size, for ncu (see profiles/README.md).
+usage: python scripts/profile_step.py [n_points] [steps]"""
+import contextlib
+import io
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from rlvae_b200 import MetricTensor
+from rlvae_b200.synthetic import make_points, make_synthetic_metric
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = torch.device('cuda:0')
+sm = make_synthetic_metric(10000, 16, seed=0)
+mt = MetricTensor(16, device=dev)
+with contextlib.redirect_stdout(io.StringIO()):
+    mt.load_pretrained(**sm.as_load_kwargs())
+z = make_points(n, 16, seed=1).to(dev)
+out = {}
+for _ in range(steps):
+    out = mt.evaluate(z, want_ginv=True, want_logdet=True, want_grad=True, out=out)
+torch.cuda.synchronize()
+print('ok', float(out['logdet_g'][:8].sum()))
