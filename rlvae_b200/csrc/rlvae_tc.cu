@@ -14,36 +14,54 @@
 // half; both halves recompute the cheap S/exp stage).  Warp roles:
 //   warp 0     TMA producer   : centroid tiles (4 KB) + bias (128 B) ring, M_hi/M_lo tile (16 KB) ring
 //   warp 1     MMA issuer     : one elected thread issues every tcgen05.mma; owns TMEM alloc/dealloc
-//   warps 2-5  exp warps      : one thread per point; tcgen05.ld S -> exp2 -> split -> tcgen05.st P
-//                               (A operand of GEMM2 is read from TMEM), chunk folding, epilogue
+//   warps 2-5  exp group A    : even blocks; one thread per point: tcgen05.ld S -> exp2 -> split ->
+//   warps 6-9  exp group B    : odd blocks;   tcgen05.st P (A operand of GEMM2 is read from TMEM),
+//                               chunk folding (64 columns each) and the epilogue
 //
 // Accumulation accuracy.  The tensor core adds into its fp32 accumulator with truncation, so a
 // K=10k reduction (3750 accumulating MMAs per output) drifts by ~1e-4 relative -- measured 5e-5 at
 // K=3000 -- which breaks the 1e-5 contract.  The MMA therefore accumulates only CHUNK_BLOCKS*32
 // centroids at a time into one of two "chunk" accumulators; the exp warps fold every finished
 // chunk into the running total with round-to-nearest fp32 adds (Ootomo & Yokota's remedy).
-// TMEM columns: [0,128) running total, [128,256) / [256,384) chunk accumulators,
-//               [384,512) two S/P buffers of (32 S|P_hi + 32 P_lo).
+// The running total lives in the exp threads' registers (64 columns each).
+// The exp stage is the latency-critical path (S -> P must finish inside the MMA time of the blocks
+// in flight), so two exp warpgroups alternate blocks and GEMM1 runs two blocks ahead of GEMM2.
+// A tcgen05.mma never takes less than ~45 cycles on this part (measured, scripts/micro/mma_rate.cu),
+// so GEMM1 is issued per 64-centroid super-block (N = 64), not per 32.
+// TMEM columns: [0,128) / [128,256) chunk accumulators, [256,512) two S/P buffers of
+//               (64 S|P_hi + 64 P_lo).
 // [N,K] never exists outside TMEM; the tables stream L2 -> smem once per 128 points.
 #include <cuda.h>
+#include <cstdio>
 
 #include "rlvae_internal.h"
+
+// -DRLVAE_TC_PROFILE: CTA (0,0) prints where its MMA thread and exp group A spend their cycles
+#ifdef RLVAE_TC_PROFILE
+#define PROF_T0() long long _pt = clock64()
+#define PROF_ADD(acc) do { long long _n = clock64(); (acc) += _n - _pt; _pt = _n; } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(acc) do {} while (0)
+#endif
 
 namespace rlvae {
 namespace tc {
 
 constexpr int TILE_M = 128;          // points per CTA
-constexpr int BK = 32;               // centroids per block
+constexpr int BK = 64;               // centroids per super-block (two 32-wide swizzle atoms)
 constexpr int NCOL = 256;            // d*d
 constexpr int NHALF = 128;           // output columns per CTA
-constexpr int CHUNK_BLOCKS = 4;      // blocks accumulated on the tensor core before an fp32 fold
-constexpr int C_STAGES = 4;
-constexpr int M_STAGES = 8;
-constexpr int THREADS = 192;
+constexpr int CHUNK_BLOCKS = 2;      // super-blocks accumulated on the tensor core before an fp32 fold
+constexpr int C_STAGES = 3;
+constexpr int SP_BUFS = 2;           // S/P TMEM buffers
+constexpr int M_STAGES = 5;
+constexpr int THREADS = 320;         // TMA warp, MMA warp, two exp warpgroups of 4 warps
 
 constexpr uint32_t A_BYTES = TILE_M * 128;            // one 128 x 32 fp32 operand tile
-constexpr uint32_t C_TILE_BYTES = BK * 128;           // 32 centroid rows of [hi|lo]
-constexpr uint32_t M_TILE_BYTES = NHALF * 128;        // 128 rows x 32 centroids fp32
+constexpr uint32_t C_TILE_BYTES = BK * 128;           // 64 centroid rows of [hi|lo]
+constexpr uint32_t M_ATOM_BYTES = NHALF * 128;        // 128 rows x 32 centroids fp32
+constexpr uint32_t M_TILE_BYTES = 2 * M_ATOM_BYTES;   // one stage = both atoms of a super-block
 constexpr uint32_t BIAS_BYTES = BK * 4;
 
 // shared memory map (offsets from a 1024-aligned base)
@@ -53,7 +71,7 @@ constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;                      // C ring
 constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;       // M ring
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;    // bias ring
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;    // mbarriers
-constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 2 + 2 + 1;
+constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + 1;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;         // + alignment slack
 constexpr int OUT_LD = 132;                                       // epilogue staging row (floats)
@@ -61,15 +79,14 @@ static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging 
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_O = 0;         // running total
-constexpr uint32_t TM_CH = 128;      // + buf*128 : chunk accumulator
-constexpr uint32_t TM_SP = 384;      // + buf*64 : S/P_hi ; + 32 : P_lo
+constexpr uint32_t TM_CH = 0;        // + buf*128 : chunk accumulator (2 buffers)
+constexpr uint32_t TM_SP = 256;      // + buf*128 : S/P_hi (64) ; + 64 : P_lo (64)
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, K-major both, N>>3, M>>4
 constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-constexpr uint32_t IDESC_G1 = make_idesc(128, BK);
+constexpr uint32_t IDESC_G1 = make_idesc(128, BK);      // N = 64
 constexpr uint32_t IDESC_G2 = make_idesc(128, NHALF);
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -101,6 +118,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -165,6 +188,14 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
         "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// One lane of a converged warp.  Issuing tcgen05.mma / TMA under `if (lane == 0)` makes ptxas wrap
+// every UTCHMMA in a per-lane ELECT loop (~45 cycles per MMA, measured); under elect.sync the
+// issue cost drops to the hardware floor (N/2 cycles for M=128 kind::tf32).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -176,7 +207,55 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
-// ------------------------------------------------------------------------------------------ kernel
+// ------------------------------------------------------------------------------------------ shared pieces
+// Z operand tiles for GEMM1 (written by one thread per point), returns zb = -alpha*||z||^2.
+__device__ __forceinline__ float write_z_tiles(uint8_t* gbase, const float* __restrict__ z, int64_t r,
+                                               int64_t n, int prow, float alpha) {
+  float zv[16];
+  if (r < n) {
+    const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v = __ldg(src + q);
+      zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zv[j] = 0.f;
+  }
+  float nrm = 0.f, hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    nrm = fmaf(zv[j], zv[j], nrm);
+    hi[j] = tf32_rna(zv[j]);
+    lo[j] = zv[j] - hi[j];
+  }
+  // 128-byte swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+  uint8_t* a1 = gbase + OFF_A1 + prow * 128;
+  uint8_t* a2 = gbase + OFF_A2 + prow * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int q = c & 3;  // which 4 of the 16 dims
+    const float4 vh = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    const float4 vl = (c < 4) ? make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3])
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int pc = (c ^ (prow & 7)) * 16;
+    *reinterpret_cast<float4*>(a1 + pc) = vh;   // [z_hi | z_hi]
+    *reinterpret_cast<float4*>(a2 + pc) = vl;   // [z_lo | 0]
+  }
+  return -nrm * alpha;
+}
+
+// GEMM1: S[128 x 32] = (z_hi|z_hi).(c_hi|c_lo) + z_lo.c_hi   (6 tcgen05.mma, K = 8 each)
+__device__ __forceinline__ void issue_gemm1(uint32_t d_tmem, uint64_t a1_desc, uint64_t a2_desc,
+                                            uint64_t b_desc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mma_ss(d_tmem, a1_desc + 2 * k, b_desc + 2 * k, IDESC_G1, k > 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) mma_ss(d_tmem, a2_desc + 2 * k, b_desc + 2 * k, IDESC_G1, 1);
+}
+
+// ------------------------------------------------------------------------------------------ forward kernel
 __global__ void __launch_bounds__(THREADS, 1)
 inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                          const __grid_constant__ CUtensorMap tm_mt_hi,
@@ -194,8 +273,9 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
   auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (2 * C_STAGES + M_STAGES + s); };
   auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + b); };
-  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 + b); };
-  const uint32_t BAR_O_FULL = bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 4);
+  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
+  const uint32_t BAR_O_FULL = bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2);
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -203,11 +283,11 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
   const int half = blockIdx.y;         // which 128 of the 256 output columns
 
-  // ---- setup: barriers (warp 0), TMEM (warp 1), Z operand tiles (warps 2-5)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 1 + 4); }
+    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4); }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR_S_FULL(b), 1); mbar_init(BAR_P_FULL(b), 4); }
+    for (int b = 0; b < 2; ++b) mbar_init(BAR_CH_FREE(b), 8);
     mbar_init(BAR_O_FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
@@ -220,46 +300,29 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // exp-warp identity: TMEM lane quarter = warp % 4, this thread's point = quarter*32 + lane
+  // exp-thread identity: TMEM lane quarter = warp % 4, point = quarter*32 + lane, group = even/odd blocks
   const int quarter = warp & 3;
   const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
   float zb = 0.f;
   if (warp >= 2) {
-    const int64_t r = row0 + prow;
-    float zv[16];
-    if (r < n) {
-      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 v = __ldg(src + q);
-        zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
-      }
+    // both groups need zb; group A also writes the operand tiles
+    if (grp == 0) {
+      zb = write_z_tiles(gbase, z, row0 + prow, n, prow, alpha);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
     } else {
+      const int64_t r = row0 + prow;
+      float nrm = 0.f;
+      if (r < n) {
+        const float4* src = reinterpret_cast<const float4*>(z + r * 16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) zv[j] = 0.f;
+        for (int q = 0; q < 4; ++q) {
+          float4 v = __ldg(src + q);
+          nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+        }
+      }
+      zb = -nrm * alpha;
     }
-    float nrm = 0.f, hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      nrm = fmaf(zv[j], zv[j], nrm);
-      hi[j] = tf32_rna(zv[j]);
-      lo[j] = zv[j] - hi[j];
-    }
-    zb = -nrm * alpha;
-    // 128-byte swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
-    uint8_t* a1 = gbase + OFF_A1 + prow * 128;
-    uint8_t* a2 = gbase + OFF_A2 + prow * 128;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int q = c & 3;  // which 4 of the 16 dims
-      const float4 vh = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-      const float4 vl = (c < 4) ? make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3])
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int pc = (c ^ (prow & 7)) * 16;
-      *reinterpret_cast<float4*>(a1 + pc) = vh;   // [z_hi | z_hi]
-      *reinterpret_cast<float4*>(a2 + pc) = vl;   // [z_lo | 0]
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
   }
   tc_fence_before();
   __syncthreads();
@@ -267,128 +330,184 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // =========================================================== TMA producer
-    if (lane == 0) {
-      for (int j = 0; j < num_blocks; ++j) {
-        const int cs = j % C_STAGES;
-        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+    // =========================================================== TMA producer (warp-converged)
+    auto load_m = [&](int jm) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int it = 2 * jm + h, ms = it % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
+          const CUtensorMap* map = (h == 0) ? &tm_mt_hi : &tm_mt_lo;
+          const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
+          tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, half * NHALF);
+          tma_load_2d(dst + M_ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, half * NHALF);
+        }
+        __syncwarp();
+      }
+    };
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + BIAS_BYTES);
         tma_load_2d(base + OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int it = 2 * j + h;
-          const int ms = it % M_STAGES;
-          mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
-          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
-          tma_load_2d(base + OFF_M + ms * M_TILE_BYTES, h == 0 ? &tm_mt_hi : &tm_mt_lo, BAR_M_FULL(ms),
-                      j * BK, half * NHALF);
-        }
       }
+      __syncwarp();
+      // the M tiles trail the centroid tiles by two super-blocks, like GEMM2 trails GEMM1
+      if (j >= 2) load_m(j - 2);
     }
+    for (int jm = (num_blocks >= 2 ? num_blocks - 2 : 0); jm < num_blocks; ++jm) load_m(jm);
   } else if (warp == 1) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================== MMA issuer (warp-converged)
+    {
       const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
       const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
-      auto gemm1 = [&](int j) {
+      // GEMM1 for super-block j; `waited` = its C_FULL wait already happened
+      auto gemm1 = [&](int j, bool waited) {
         const int cs = j % C_STAGES;
-        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        if (!waited) mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
         tc_fence_after();
-        const uint64_t b_desc = make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES);
-        const uint32_t d = tmem_base + TM_SP + (j & 1) * 64;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // (z_hi | z_hi) . (c_hi | c_lo): 32 fp32 = 4 K-steps of 8
-          mma_ss(d, a1_desc + 2 * k, b_desc + 2 * k, IDESC_G1, k > 0);
-#pragma unroll
-        for (int k = 0; k < 2; ++k)   // z_lo . c_hi: first 16 fp32 of both rows
-          mma_ss(d, a2_desc + 2 * k, b_desc + 2 * k, IDESC_G1, 1);
-        tc_commit(BAR_S_FULL(j & 1));
-        tc_commit(BAR_C_EMPTY(cs));
+        if (elect_one()) {
+          issue_gemm1(tmem_base + TM_SP + (j & 1) * 128, a1_desc, a2_desc,
+                      make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
+          tc_commit(BAR_S_FULL(j & 1));
+          tc_commit(BAR_C_EMPTY(cs));
+        }
+        __syncwarp();
       };
-      gemm1(0);
+      auto wait_m = [&](int it) { mbar_wait(BAR_M_FULL(it % M_STAGES), (it / M_STAGES) & 1); };
+      long long pw_g1 = 0, pw_w = 0, pw_p = 0, pw_issue = 0;
+      (void)pw_g1; (void)pw_w; (void)pw_p; (void)pw_issue;
+      gemm1(0, false);
+      if (num_blocks > 1) gemm1(1, false);
+      wait_m(0);
+      wait_m(1);
+      mbar_wait(BAR_P_FULL(0), 0);
+#ifdef RLVAE_TC_PROFILE
+      const long long loop_t0 = clock64();
+#endif
+      // Every wait below is for something that is (normally) long complete; each is placed behind
+      // a group of 8 queued MMAs so that its ~60-90 cycle latency never drains the tensor pipe.
       for (int j = 0; j < num_blocks; ++j) {
-        if (j + 1 < num_blocks) gemm1(j + 1);
-        mbar_wait(BAR_P_FULL(j & 1), (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t p_hi = tmem_base + TM_SP + (j & 1) * 64;
-        const uint32_t p_lo = p_hi + 32;
-        const uint32_t acc = tmem_base + TM_CH + ((j / CHUNK_BLOCKS) & 1) * 128;
+        PROF_T0();
+        const int chunk = j / CHUNK_BLOCKS;
         const int first = (j % CHUNK_BLOCKS) == 0;   // a new chunk overwrites its accumulator
-        {
-          const int it = 2 * j, ms = it % M_STAGES;
-          mbar_wait(BAR_M_FULL(ms), (it / M_STAGES) & 1);
-          tc_fence_after();
-          const uint64_t b_desc = make_desc_sw128(base + OFF_M + ms * M_TILE_BYTES);
+        const int sb = j & 1;
+        tc_fence_after();
+        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+        const uint32_t p_hi = tmem_base + TM_SP + sb * 128;
+        const uint32_t p_lo = p_hi + 64;
+        const uint32_t acc = tmem_base + TM_CH + (chunk & 1) * 128;
+        const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
+        const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
+        // K index kk = 8 centroids; atom = kk / 4 (16 KB apart = +1024 in descriptor units)
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ts(acc, p_hi + 8 * k, b_desc + 2 * k, IDESC_G2, !(first && k == 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ts(acc, p_lo + 8 * k, b_desc + 2 * k, IDESC_G2, 1);
-          tc_commit(BAR_M_EMPTY(ms));
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts(acc, p_hi + 8 * kk, bh + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, !(first && kk == 0));
         }
-        {
-          const int it = 2 * j + 1, ms = it % M_STAGES;
-          mbar_wait(BAR_M_FULL(ms), (it / M_STAGES) & 1);
-          tc_fence_after();
-          const uint64_t b_desc = make_desc_sw128(base + OFF_M + ms * M_TILE_BYTES);
+        __syncwarp();
+        PROF_ADD(pw_issue);
+        if (j + 1 < num_blocks) wait_m(2 * j + 2);
+        if (j + 2 < num_blocks) mbar_wait(BAR_C_FULL((j + 2) % C_STAGES), ((j + 2) / C_STAGES) & 1);
+        PROF_ADD(pw_w);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ts(acc, p_hi + 8 * k, b_desc + 2 * k, IDESC_G2, 1);
-          tc_commit(BAR_M_EMPTY(ms));
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts(acc, p_lo + 8 * kk, bh + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, 1);
+          tc_commit(BAR_M_EMPTY(ms_hi));
         }
+        __syncwarp();
+        PROF_ADD(pw_issue);
+        if (j + 1 < num_blocks) {
+          wait_m(2 * j + 3);
+          const int nchunk = (j + 1) / CHUNK_BLOCKS;   // chunk buffer of the next super-block
+          if (((j + 1) % CHUNK_BLOCKS) == 0 && nchunk >= 2)   // both exp groups folded chunk-2
+            mbar_wait(BAR_CH_FREE(nchunk & 1), ((nchunk >> 1) - 1) & 1);
+        }
+        PROF_ADD(pw_w);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts(acc, p_hi + 8 * kk, bl + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, 1);
+          tc_commit(BAR_M_EMPTY(ms_lo));
+        }
+        __syncwarp();
+        PROF_ADD(pw_issue);
+        // GEMM1 two super-blocks ahead re-uses this S/P buffer: ordered behind GEMM2(j) in the pipe
+        if (j + 2 < num_blocks) gemm1(j + 2, true);
+        PROF_ADD(pw_g1);
+        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) & 1), ((j + 1) >> 1) & 1);
+        PROF_ADD(pw_p);
       }
-      tc_commit(BAR_O_FULL);
+      if (elect_one()) tc_commit(BAR_O_FULL);
+      __syncwarp();
+#ifdef RLVAE_TC_PROFILE
+      if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+        printf("[tc prof] MMA warp per super-block: total %lld | gemm1 issue %lld  hidden waits %lld  p_full %lld  gemm2 issue %lld\n",
+               (clock64() - loop_t0) / num_blocks, pw_g1 / num_blocks, pw_w / num_blocks, pw_p / num_blocks,
+               pw_issue / num_blocks);
+#endif
     }
   } else {
-    // =========================================================== exp warps (one thread per point)
+    // =========================================================== exp groups (one thread per point)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float two_alpha = 2.f * alpha;
-    // fold chunk c (finished on the tensor core) into the running total with RN fp32 adds
-    auto fold_chunk = [&](int c) {
-      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128;
-      const uint32_t dst = tmem_base + lane_addr + TM_O;
-#pragma unroll 1
-      for (int cb = 0; cb < NHALF / 32; ++cb) {
-        uint32_t a[32], b[32];
-        TMEM_LD32(src + cb * 32, a);
-        if (c > 0) {
-          TMEM_LD32(dst + cb * 32, b);
-          tmem_wait_ld();
+    float omain[64];                        // running total: columns [64*grp, 64*grp+64) of this row
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(b[i]));
-        } else {
-          tmem_wait_ld();
-        }
-        TMEM_ST32(dst + cb * 32, a);
+    for (int i = 0; i < 64; ++i) omain[i] = 0.f;
+    // fold chunk c (finished on the tensor core) into the running total with RN fp32 adds
+    auto fold_chunk = [&](int c, bool signal) {
+      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128 + grp * 64;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t a[32];
+        TMEM_LD32(src + cb * 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) omain[cb * 32 + i] += __uint_as_float(a[i]);
       }
-      tmem_wait_st();
+      if (signal) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR_CH_FREE(c & 1));
+      }
     };
-    int folded = 0;                         // chunks already folded
-    for (int j = 0; j < num_blocks; ++j) {
+    int folded = 0;                         // chunks already folded by this group
+    long long pe_wait = 0, pe_work = 0, pe_fold = 0;
+    (void)pe_wait; (void)pe_work; (void)pe_fold;
+    for (int j = grp; j < num_blocks; j += 2) {
+      PROF_T0();
       const int cs = j % C_STAGES;
-      const uint32_t sp = tmem_base + lane_addr + TM_SP + (j & 1) * 64;
+      const uint32_t sp = tmem_base + lane_addr + TM_SP + (j & 1) * 128;
       mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);   // bias bytes visible to this thread
       mbar_wait(BAR_S_FULL(j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s[32], l[32];
-      TMEM_LD32(sp, s);
-      const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES);
-      float bias[32];
+      PROF_ADD(pe_wait);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 v = bias4[q];
-        bias[4 * q] = v.x + zb; bias[4 * q + 1] = v.y + zb; bias[4 * q + 2] = v.z + zb; bias[4 * q + 3] = v.w + zb;
-      }
-      tmem_wait_ld();
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t s[32], l[32];
+        TMEM_LD32(sp + rnd * 32, s);
+        const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float w = ex2_approx(fmaf(__uint_as_float(s[i]), two_alpha, bias[i]));
-        const uint32_t wh = __float_as_uint(w) & 0xFFFFE000u;   // what the TF32 datapath will read
-        s[i] = wh;
-        l[i] = __float_as_uint(w - __uint_as_float(wh));
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = bias4[q];
+          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * q + e;
+            const float w = ex2_approx(fmaf(__uint_as_float(s[i]), two_alpha, b4[e] + zb));
+            const uint32_t wh = __float_as_uint(w) & 0xFFFFE000u;   // what the TF32 datapath will read
+            s[i] = wh;
+            l[i] = __float_as_uint(w - __uint_as_float(wh));
+          }
+        }
+        TMEM_ST32(sp + rnd * 32, s);
+        TMEM_ST32(sp + 64 + rnd * 32, l);
       }
-      TMEM_ST32(sp, s);
-      TMEM_ST32(sp + 32, l);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -396,44 +515,319 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         mbar_arrive(BAR_P_FULL(j & 1));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
-      // S(j) was produced by GEMM1(j), which the MMA thread issued after GEMM2(j-2): every chunk
-      // that ends at block <= j-2 is complete and safe to read.  The next use of that chunk
-      // buffer is ordered behind this fold by this thread's later P_FULL arrival.
-      if ((folded + 1) * CHUNK_BLOCKS - 1 <= j - 2) fold_chunk(folded++);
+      PROF_ADD(pe_work);
+      // S(j) came from GEMM1(j), issued after GEMM2(j-2): every chunk ending at a super-block
+      // <= j-2 is complete.  CH_FREE tells the MMA thread when both groups have drained a buffer.
+      while ((folded + 1) * CHUNK_BLOCKS - 1 <= j - 2) { fold_chunk(folded, true); ++folded; }
+      PROF_ADD(pe_fold);
     }
-    // ---------------------------------------------------------- epilogue: O (+ lambda I) -> smem -> global
+#ifdef RLVAE_TC_PROFILE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64)
+      printf("[tc prof] exp group A per own block: wait %lld  work %lld  fold %lld\n",
+             pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2), pe_fold / (num_blocks / 2));
+#endif
+    // ---------------------------------------------------------- epilogue
     mbar_wait(BAR_O_FULL, 0);
     tc_fence_after();
     const int num_chunks = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
-    while (folded < num_chunks) fold_chunk(folded++);
+    while (folded < num_chunks) { fold_chunk(folded, false); ++folded; }
     float* stage = reinterpret_cast<float*>(gbase + OFF_M);
-#pragma unroll 1
-    for (int cb = 0; cb < NHALF / 32; ++cb) {
-      uint32_t v[32];
-      TMEM_LD32(tmem_base + lane_addr + TM_O + cb * 32, v);
-      tmem_wait_ld();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 o;
-        float* op = reinterpret_cast<float*>(&o);
+    for (int q = 0; q < 16; ++q) {
+      float4 o;
+      float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = half * NHALF + cb * 32 + q * 4 + e;
-          op[e] = __uint_as_float(v[q * 4 + e]) + ((col % 17 == 0) ? lambda : 0.f);
-        }
-        *reinterpret_cast<float4*>(stage + prow * OUT_LD + cb * 32 + q * 4) = o;
+      for (int e = 0; e < 4; ++e) {
+        const int col = half * NHALF + grp * 64 + q * 4 + e;
+        op[e] = omain[q * 4 + e] + ((col % 17 == 0) ? lambda : 0.f);
       }
+      *reinterpret_cast<float4*>(stage + prow * OUT_LD + grp * 64 + q * 4) = o;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four exp warps only
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight exp warps only
     const int t = threadIdx.x - 64;
     const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
     float* dst = out + row0 * NCOL + half * NHALF;
 #pragma unroll 4
-    for (int i = t; i < TILE_M * (NHALF / 4); i += 128) {
+    for (int i = t; i < TILE_M * (NHALF / 4); i += 256) {
       const int r = i >> 5, c4 = i & 31;
       if (r < rows_here)
         *reinterpret_cast<float4*>(dst + (int64_t)r * NCOL + c4 * 4) =
             *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ==========================================================================================
+// Gradient / backward kernel:  out[n,:] += scale * sum_k w_nk <U_n, M_k> (c_k - z_n)
+//   (with U = G^T, scale = -2/T^2 it is grad_z log det G; with
+//    U = dL/dG^{-1}, scale = 2/T^2 it is the autograd backward of metric_tensor.py:98-137)
+//
+// Same skeleton as the forward kernel.  Per 64-centroid super-block the tensor core produces
+//   S[128 x 64] = Z.C^T                      (GEMM1, as in the forward kernel)
+//   T[128 x 64] = U_hi.Mhi^T + U_lo.Mhi^T + U_hi.Mlo^T      (3xTF32, 48 MMAs of N = 64, K = 8)
+// with U (this CTA's 128 of the 256 (i,j) columns, hi/lo split) resident in TMEM as the A operand
+// and the natural-layout table tile [64 centroids x 128] as the K-major B operand.  The exp groups
+// then form w = exp2(..), u = w*t and accumulate g += u*c_k, su += u in fp32 registers; the two
+// column halves (blockIdx.y) add their partial results into `out` (zeroed by the launcher).
+// T is re-started every super-block, so the accumulator-truncation drift is bounded by 48 MMAs.
+// TMEM columns: [0,128) U_hi, [128,256) U_lo, [256,512) two (S 64 | T 64) buffers.
+// ==========================================================================================
+namespace grad {
+constexpr int C_STAGES = 3;
+constexpr int M_STAGES = 4;
+constexpr uint32_t C_TILE_BYTES = BK * 128;        // [hi|lo] rows for GEMM1
+constexpr uint32_t CN_BYTES = BK * 64;             // natural fp32 centroid rows for the FMA stage
+constexpr uint32_t BIAS_BYTES = BK * 4;
+constexpr uint32_t M_ATOM_BYTES = BK * 128;        // 64 centroid rows x 32 fp32
+constexpr uint32_t M_TILE_BYTES = 4 * M_ATOM_BYTES;
+constexpr uint32_t OFF_A1 = 0;
+constexpr uint32_t OFF_A2 = OFF_A1 + A_BYTES;
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
+constexpr uint32_t OFF_CN = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_CN + C_STAGES * CN_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 4;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+constexpr int RED_LD = 20;                          // group-B partials staged in the M ring
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TM_UHI = 0, TM_ULO = 128, TM_ST = 256;   // ST + buf*128 : S (64) | T (64)
+constexpr uint32_t IDESC_T = make_idesc(128, BK);
+}  // namespace grad
+
+__global__ void __launch_bounds__(THREADS, 1)
+metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
+                      const __grid_constant__ CUtensorMap tm_mn_hi,
+                      const __grid_constant__ CUtensorMap tm_mn_lo,
+                      const float* __restrict__ z, const float* __restrict__ u,
+                      const float* __restrict__ cnat, const float* __restrict__ cbias, int64_t n,
+                      int num_blocks, float alpha, float scale, float* __restrict__ out) {
+  // local names shadow the forward kernel's constants of the same name
+  constexpr int C_STAGES = grad::C_STAGES, M_STAGES = grad::M_STAGES, RED_LD = grad::RED_LD;
+  constexpr uint32_t C_TILE_BYTES = grad::C_TILE_BYTES, CN_BYTES = grad::CN_BYTES,
+                     BIAS_BYTES = grad::BIAS_BYTES, M_TILE_BYTES = grad::M_TILE_BYTES,
+                     OFF_CN = grad::OFF_CN, TM_UHI = grad::TM_UHI, TM_ULO = grad::TM_ULO,
+                     TM_ST = grad::TM_ST, IDESC_T = grad::IDESC_T;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + grad::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (2 * C_STAGES + M_STAGES + s); };
+  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_ST_FREE = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + grad::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const int half = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_ST_FREE(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(base + grad::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();            // TMEM base published before the exp threads store U into it
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  float zb = 0.f;
+  float zrow[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
+  if (warp >= 2) {
+    const int64_t r = row0 + prow;
+    if (grp == 0) {
+      zb = write_z_tiles(gbase, z, r, n, prow, alpha);   // uses the forward kernel's A1/A2 offsets
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+      float nrm = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+      }
+      if (grp == 1) zb = -nrm * alpha;
+    }
+    // this thread's 64 columns of U (hi/lo split) -> TMEM, the A operand of the T GEMM
+    const float* usrc = u + r * NCOL + half * NHALF + grp * 64;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      uint32_t h[32], l[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = (r < n) ? __ldg(reinterpret_cast<const float4*>(usrc + cb * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float hi = tf32_rna(vv[e]);
+          h[4 * q + e] = __float_as_uint(hi);
+          l[4 * q + e] = __float_as_uint(vv[e] - hi);
+        }
+      }
+      TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 64 + cb * 32, h);
+      TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 64 + cb * 32, l);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (warp-converged)
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + CN_BYTES + BIAS_BYTES);
+        tma_load_2d(base + grad::OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+        bulk_load_1d(base + OFF_CN + cs * CN_BYTES, cnat + (int64_t)j * BK * 16, CN_BYTES, BAR_C_FULL(cs));
+        bulk_load_1d(base + grad::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int it = 2 * j + h, ms = it % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
+          tma_load_3d(base + grad::OFF_M + ms * M_TILE_BYTES, h == 0 ? &tm_mn_hi : &tm_mn_lo, BAR_M_FULL(ms), 0,
+                      j * BK, half * 4);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (warp-converged)
+    const uint64_t a1_desc = make_desc_sw128(base + grad::OFF_A1);
+    const uint64_t a2_desc = make_desc_sw128(base + grad::OFF_A2);
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES, sb = j & 1;
+      const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+      mbar_wait(BAR_ST_FREE(sb), ((j >> 1) & 1) ^ 1);       // exp groups done with super-block j-2
+      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t s_t = tmem_base + TM_ST + sb * 128;
+      const uint32_t t_t = s_t + 64;
+      const uint64_t bh = make_desc_sw128(base + grad::OFF_M + ms_hi * M_TILE_BYTES);
+      const uint64_t bl = make_desc_sw128(base + grad::OFF_M + ms_lo * M_TILE_BYTES);
+      if (elect_one()) {
+        issue_gemm1(s_t, a1_desc, a2_desc, make_desc_sw128(base + grad::OFF_C + cs * C_TILE_BYTES));
+        // K index kk = 8 of this half's 128 (i,j) columns; atom = kk / 4 (8 KB apart = +512)
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          mma_ts(t_t, tmem_base + TM_UHI + 8 * kk, bh + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          mma_ts(t_t, tmem_base + TM_ULO + 8 * kk, bh + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, 1);
+        tc_commit(BAR_M_EMPTY(ms_hi));
+      }
+      __syncwarp();
+      mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          mma_ts(t_t, tmem_base + TM_UHI + 8 * kk, bl + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, 1);
+        tc_commit(BAR_M_EMPTY(ms_lo));
+        tc_commit(BAR_ST_FULL(sb));
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== exp groups (one thread per point)
+    const float two_alpha = 2.f * alpha;
+    float g[16], su = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) g[e] = 0.f;
+    for (int j = grp; j < num_blocks; j += 2) {
+      const int cs = j % C_STAGES, sb = j & 1;
+      const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
+      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t sv[32], tv[32];
+        TMEM_LD32(st + rnd * 32, sv);
+        TMEM_LD32(st + 64 + rnd * 32, tv);
+        const float* bias = reinterpret_cast<const float*>(gbase + grad::OFF_BIAS + cs * BIAS_BYTES) + rnd * 32;
+        const float4* crow = reinterpret_cast<const float4*>(gbase + OFF_CN + cs * CN_BYTES) + rnd * 32 * 4;
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, bias[i] + zb));
+          const float uv = w * __uint_as_float(tv[i]);
+          su += uv;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 c4 = crow[i * 4 + q];
+            g[4 * q] = fmaf(uv, c4.x, g[4 * q]);
+            g[4 * q + 1] = fmaf(uv, c4.y, g[4 * q + 1]);
+            g[4 * q + 2] = fmaf(uv, c4.z, g[4 * q + 2]);
+            g[4 * q + 3] = fmaf(uv, c4.w, g[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR_ST_FREE(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+    }
+    // ---------------------------------------------------------- combine the two groups, then the halves
+    // All TMA/MMA traffic of this CTA is complete once both groups have consumed their last
+    // super-block, so the M ring can be reused as scratch.
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* red = reinterpret_cast<float*>(gbase + grad::OFF_M);
+    if (grp == 1) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) red[prow * RED_LD + e] = g[e];
+      red[prow * RED_LD + 16] = su;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const int64_t r = row0 + prow;
+      su += red[prow * RED_LD + 16];
+      if (r < n) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float ge = g[e] + red[prow * RED_LD + e];
+          atomicAdd(out + r * 16 + e, scale * (ge - zrow[e] * su));   // exactly two addends per element
+        }
+      }
     }
   }
 
@@ -469,6 +863,22 @@ static int make_map_2d(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64
   return 0;
 }
 
+// natural table [Kpad, 256] viewed as [8 column atoms][Kpad][32]: one box = 4 atoms x 64 rows
+static int make_map_atoms(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64_t Kpad) {
+  cuuint64_t dims[3] = {32, Kpad, 8};
+  cuuint64_t strides[2] = {256 * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, (cuuint32_t)tc::BK, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string((int)r));
+    return 4;
+  }
+  return 0;
+}
+
 int tc_build_descriptors(rlvae_tables* t) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -477,8 +887,11 @@ int tc_build_descriptors(rlvae_tables* t) {
   PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(fn);
   const uint64_t Kpad = (uint64_t)t->Kpad;
   if (int rc = make_map_2d(enc, &t->tm_cstack, t->cstack, 32, Kpad, 32, tc::BK)) return rc;
-  if (int rc = make_map_2d(enc, &t->tm_mt_hi, t->Mt_hi, Kpad, tc::NCOL, tc::BK, tc::NHALF)) return rc;
-  if (int rc = make_map_2d(enc, &t->tm_mt_lo, t->Mt_lo, Kpad, tc::NCOL, tc::BK, tc::NHALF)) return rc;
+  // M^T tiles are fetched one 32-centroid swizzle atom (128 B rows) at a time
+  if (int rc = make_map_2d(enc, &t->tm_mt_hi, t->Mt_hi, Kpad, tc::NCOL, 32, tc::NHALF)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mt_lo, t->Mt_lo, Kpad, tc::NCOL, 32, tc::NHALF)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mn_hi, t->Mn_hi, Kpad)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mn_lo, t->Mn_lo, Kpad)) return rc;
   return 0;
 }
 
@@ -504,8 +917,23 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
 
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                           float* out, cudaStream_t s) {
-  // the tcgen05 gradient kernel is not written yet: the contraction runs on the fp32 direct kernel
-  return launch_metric_grad_direct(t, z, u, n, scale, out, s);
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0,
+                "tensor path needs 16-byte aligned z and u");
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::metric_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::grad::SMEM_BYTES));
+    attr_set = true;
+  }
+  RLVAE_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 16, s));   // the two column halves add
+  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), tc::NCOL / tc::NHALF);
+  const float alpha = 1.4426950408889634f / t->T2;
+  tc::metric_grad_tc_kernel<<<grid, tc::THREADS, tc::grad::SMEM_BYTES, s>>>(
+      t->tm_cstack, t->tm_mn_hi, t->tm_mn_lo, z, u, t->c, t->cbias, n, t->Kpad / tc::BK, alpha, scale, out);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace rlvae
