@@ -4,11 +4,12 @@ Drop-in names for the reference's hot-path API: ``MetricTensor`
 ``MetricLoader``, ``BaseRiemannianSampler``, ``RiemannianHMCSampler``,
 ``WorkingRiemannianSampler``, ``FlowManager``.  See DESIGN.md.
 """
+from .flow_manager import FlowManager
 from .metric_loader import MetricLoader
 from .metric_tensor import MetricTensor
 from .samplers import (BaseRiemannianSampler, MetricModel, RiemannianHMCSampler,
                        WorkingRiemannianSampler)
 
 __all__ = ['MetricTensor', 'MetricLoader', 'BaseRiemannianSampler', 'MetricModel',
-           'RiemannianHMCSampler', 'WorkingRiemannianSampler']
+           'RiemannianHMCSampler', 'WorkingRiemannianSampler', 'FlowManager']
 __version__ = '0.1.0'

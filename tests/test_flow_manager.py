@@ -1,0 +1,69 @@
+"""FlowManager / IAF parity with the reference's vendored pythae flows (golden: flow_d16.npz,
+made by oracle/make_golden.py from the real reference) and, on the GPU, the fused
+metric-per-flow-step consumer."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def _load(fm, g):
+    sd = {k[4:]: v for k, v in g.items() if k.startswith('sd::')}
+    assert set(sd) == set(fm.state_dict()), set(sd) ^ set(fm.state_dict())
+    fm.load_state_dict(sd)
+
+
+def test_flow_manager_matches_reference_outputs():
+    from rlvae_b200.flow_manager import FlowManager
+    g = load_golden('flow_d16')
+    fm = FlowManager(latent_dim=16, n_flows=3, flow_hidden_size=32, flow_n_blocks=2, flow_n_hidden=1)
+    # masks are derived buffers: identical before loading anything
+    for k, v in fm.state_dict().items():
+        if k.endswith('mask'):
+            assert torch.equal(v, g['sd::' + k]), k
+    _load(fm, g)
+    with torch.no_grad():
+        zs, lds = fm.apply_flows([g['z0']], n_obs=6)       # beyond n_flows: last flow is re-used
+    assert len(zs) == 6 and len(lds) == 5
+    torch.testing.assert_close(torch.stack(zs), g['z_seq'], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(torch.stack(lds), g['log_dets'], rtol=1e-5, atol=1e-5)
+    # provided-sequence mode uses one flow per step and ignores the later inputs' values
+    with torch.no_grad():
+        zs2, lds2 = fm.apply_flows([g['z0'], g['z0'], g['z0']])
+    torch.testing.assert_close(torch.stack(zs2), g['z_seq'][:3], rtol=1e-5, atol=1e-6)
+    assert len(fm.get_log_det_jacobians([g['z0'], g['z0']])) == 1
+    with pytest.raises(NotImplementedError):
+        fm.invert_flows(zs)
+    assert fm.get_flow_params()['n_flows'] == 3 and fm.diagnose_flows()['total_params'] > 0
+
+
+def test_default_flow_manager_size_matches_survey():
+    from rlvae_b200.flow_manager import FlowManager
+    fm = FlowManager(16, n_flows=8)
+    assert fm.diagnose_flows()['total_params'] == 2306560      # SURVEY.md §8c (verified on the reference)
+
+
+@pytest.mark.gpu
+def test_metric_along_flow_fused_equals_per_step_loop():
+    import contextlib
+    import io
+    from oracle import metric_oracle as O
+    from rlvae_b200 import MetricTensor
+    from rlvae_b200.flow_manager import FlowManager
+    from rlvae_b200.synthetic import make_synthetic_metric
+    dev = torch.device('cuda:0')
+    g = load_golden('flow_d16')
+    fm = FlowManager(latent_dim=16, n_flows=3, flow_hidden_size=32, device=dev)
+    _load(fm, g)
+    fm.to(dev)
+    sm = make_synthetic_metric(300, 16, seed=0)
+    mt = MetricTensor(16, device=dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt.load_pretrained(**sm.as_load_kwargs())
+    out = fm.metric_along_flow(mt, g['z0'].to(dev), n_obs=6, want_g=True)
+    assert out['z'].shape == (6, 6, 16) and out['logdet_G'].shape == (6, 6) and out['G'].shape == (6, 6, 16, 16)
+    torch.testing.assert_close(out['z'].cpu(), g['z_seq'].transpose(0, 1), rtol=1e-4, atol=1e-5)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    for step in range(6):                                       # the reference's per-t loop
+        ref = O.log_det_metric(out['z'][:, step].cpu(), *t)
+        torch.testing.assert_close(out['logdet_G'][:, step].cpu(), ref, rtol=1e-4, atol=1e-4)
