@@ -241,13 +241,18 @@ def run_ours(args):
 
     # ---- dominant kernel alone (tcgen05 weighted sum): CUDA events around the launch
     ginv = out['ginv']
+    packed_path = path_name == 'tensor' and tab.symmetric
     kev = []
     for i in range(3 + 5):
         flush.zero_()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        _capi.lib().rlvae_inverse_metric(tab.handle, _capi._ptr(z), n, _capi._ptr(ginv), _capi.PATH_AUTO,
-                                         _capi._stream(z))
+        if packed_path:     # the tcgen05 kernel alone: symmetric tables -> packed [N,144] output
+            _capi.lib().rlvae_inverse_metric_packed(tab.handle, _capi._ptr(z), n, _capi._ptr(ginv),
+                                                    _capi._stream(z))
+        else:
+            _capi.lib().rlvae_inverse_metric(tab.handle, _capi._ptr(z), n, _capi._ptr(ginv), None,
+                                             _capi.PATH_AUTO, _capi._stream(z))
         e1.record(); e1.synchronize()
         if i >= 3:
             kev.append(e0.elapsed_time(e1))
@@ -260,9 +265,18 @@ def run_ours(args):
         if path_name == 'tensor':
             tf32_peak = measure_tf32_peak(dev)
             ach = 3 * f_alg / (k_ms * 1e-3) / 1e12            # 3xTF32: three tensor MACs per fp32 MAC
+            # tensor work actually issued: GEMM2 columns (144 packed / 256 dense) + GEMM1 (N=64, K=48)
+            cols = 2 * (80 + 64) / 2 if packed_path else 256
+            kp = tab.Kpad
+            issued = n * 2 * kp * (3 * cols + 2 * 48) / (k_ms * 1e-3) / 1e12
             roof = {'bound': 'tensor', 'kernel': 'inverse_metric_tc_kernel', 'achieved': ach,
                     'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak, 'traffic': None,
+                    'tensor_issued_tflops': issued, 'tensor_issued_frac': issued / tf32_peak,
                     'achieved_fp32_equiv_tflops': f_alg / (k_ms * 1e-3) / 1e12, 'kernel_ms': k_ms,
+                    'note': ('algorithmic flops count dense M (2Kd(d+1) per point, SURVEY.md 8d); the '
+                             'tables are symmetric, so the kernel accumulates 136 of the 256 columns '
+                             '(144/256 of the dense tensor work is issued)') if packed_path else
+                            'dense 256-column kernel',
                     'peak_source': 'cuBLAS TF32 8192^3 best-of-8 measured in this run (MEASURED_PEAKS.json '
                                    f'({peak_src}) holds bf16 only: {peaks.get("bf16_tflops")} TF/s burst)'}
         else:

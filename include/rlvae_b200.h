@@ -59,9 +59,17 @@ int rlvae_tables_destroy(rlvae_tables_t* t);
 int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]);
 
 /* ---- A2: G^{-1}(z) = sum_k M_k exp(-||z-c_k||^2/T^2) + lambda I ------------------------------
- * ref: src/models/components/metric_tensor.py:98-137.   z [N,d] -> ginv [N,d,d]               */
+ * ref: src/models/components/metric_tensor.py:98-137.   z [N,d] -> ginv [N,d,d]
+ * `work` (optional, rlvae_inverse_metric_workspace(n,d) bytes) lets symmetric tables use the
+ * packed 136-column tensor kernel; with work == NULL the dense 256-column kernel runs.        */
+int64_t rlvae_inverse_metric_workspace(int64_t n, int d);   /* bytes */
 int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv,
-                         int path, void* stream);
+                         void* work, int path, void* stream);
+/* Same quantity in the packed symmetric layout the tensor kernel produces for symmetric tables
+ * (d == 16): packed [N,144], entry 16 i - i (i-1)/2 + (j - i) holds G^{-1}_ij for i <= j (lambda
+ * included), entries 136..143 are zero.  Error unless the tables are symmetric and d == 16.    */
+int rlvae_inverse_metric_packed(const rlvae_tables_t* t, const float* z, int64_t n, float* packed,
+                                void* stream);
 
 /* ---- A3/A4/A5: batched d x d inverse, log|det|, sign, diagonal of the inverse ----------------
  * ref: torch.linalg.inv / slogdet / det at metric_tensor.py:152,175 and hmc_sampler.py:28.

@@ -26,7 +26,9 @@ _SIGNATURES = [
     ('rlvae_tables_create', c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     ('rlvae_tables_destroy', c_int, [c_void_p]),
     ('rlvae_tables_info', c_int, [c_void_p, POINTER(c_int64)]),
-    ('rlvae_inverse_metric', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    ('rlvae_inverse_metric_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_inverse_metric', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    ('rlvae_inverse_metric_packed', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -133,9 +135,23 @@ def inverse_metric(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO) -> torch
     z = _req(z, 'z')
     n, d = z.shape
     out = torch.empty((n, d, d), device=z.device, dtype=torch.float32)
+    need = int(lib().rlvae_inverse_metric_workspace(n, d))
+    work = torch.empty(need, device=z.device, dtype=torch.uint8) if need > 0 else None
     with torch.cuda.device(z.device):
-        _check(lib().rlvae_inverse_metric(tab.handle, _ptr(z), n, _ptr(out), path, _stream(z)),
+        _check(lib().rlvae_inverse_metric(tab.handle, _ptr(z), n, _ptr(out), _ptr(work), path, _stream(z)),
                'rlvae_inverse_metric')
+    return out
+
+
+def inverse_metric_packed(tab: Tables, z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """G^{-1} in the packed symmetric [N,144] layout (symmetric tables, d == 16)."""
+    z = _req(z, 'z')
+    n = z.shape[0]
+    if out is None:
+        out = torch.empty((n, 144), device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_inverse_metric_packed(tab.handle, _ptr(z), n, _ptr(out), _stream(z)),
+               'rlvae_inverse_metric_packed')
     return out
 
 

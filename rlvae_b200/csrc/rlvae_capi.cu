@@ -73,6 +73,26 @@ __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int 
   }
 }
 
+// symmetric tables: packed upper triangle (row p = (i<=j)), transposed [144, Kpad], TF32 hi/lo
+__global__ void pack_sym_kernel(const float* __restrict__ M, int Kpad, float* __restrict__ hi_t,
+                                float* __restrict__ lo_t) {
+  const int64_t total = (int64_t)kSymCols * Kpad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / Kpad), k = (int)(idx - (int64_t)p * Kpad);
+    float v = 0.f;
+    if (p < 136) {
+      int i = 0, base = 0;                 // invert p = 16 i - i (i-1)/2 + (j - i)
+      while (p >= base + (16 - i)) { base += 16 - i; ++i; }
+      const int j = i + (p - base);
+      v = M[(int64_t)k * 256 + i * 16 + j];
+    }
+    const float hi = tf32_hi(v);
+    hi_t[idx] = hi;
+    lo_t[idx] = v - hi;
+  }
+}
+
 __global__ void symmetry_kernel(const float* __restrict__ m_in, int K, int d, int* __restrict__ asym) {
   const int64_t total = (int64_t)K * d * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -96,7 +116,7 @@ static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
 static void free_tables(rlvae_tables* t) {
   pythae_cache_release(t);
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
-                    &t->Mn_hi, &t->Mn_lo, &t->caug};
+                    &t->Mn_hi, &t->Mn_lo, &t->caug, &t->Mts_hi, &t->Mts_lo};
   for (float** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -193,6 +213,19 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     t->tensor_capable = 1;
     const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
     t->tensor_auto = (rel < 2.0e-6f) ? 1 : 0;
+    if (t->symmetric) {   // 136 instead of 256 accumulated columns
+      cudaError_t e1 = cudaMalloc(&t->Mts_hi, sizeof(float) * (size_t)kSymCols * Kpad);
+      cudaError_t e2 = cudaMalloc(&t->Mts_lo, sizeof(float) * (size_t)kSymCols * Kpad);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        set_error("tables_create: cudaMalloc (packed tables) failed");
+        return fail(1);
+      }
+      pack_sym_kernel<<<592, 256, 0, s>>>(t->M, Kpad, t->Mts_hi, t->Mts_lo);
+      OK_OR_FAIL(cudaGetLastError());
+      OK_OR_FAIL(cudaStreamSynchronize(s));
+      rc = tc_build_sym_descriptors(t);
+      if (rc != 0) return fail(rc);
+    }
   }
   *out = t;
   return 0;
@@ -223,8 +256,12 @@ static int resolve_path(const rlvae_tables* t, int path, bool* use_tc) {
   return 0;
 }
 
-int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, int path,
-                         void* stream) {
+int64_t rlvae_inverse_metric_workspace(int64_t n, int d) {
+  return d == 16 ? (int64_t)sizeof(float) * n * kSymCols : 0;
+}
+
+int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, void* work,
+                         int path, void* stream) {
   RLVAE_REQUIRE(t != nullptr, "inverse_metric: tables handle is NULL (metric not loaded)");
   RLVAE_REQUIRE(n >= 0, "inverse_metric: negative batch");
   if (n == 0) return 0;
@@ -232,8 +269,46 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
   bool use_tc;
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return use_tc ? launch_inverse_metric_tc(t, z, n, ginv, s)
-                : launch_inverse_metric_direct(t, z, n, ginv, s);
+  if (!use_tc) return launch_inverse_metric_direct(t, z, n, ginv, s);
+  if (t->symmetric && t->Mts_hi != nullptr && work != nullptr) {
+    // symmetric tables: accumulate the 136 packed entries, then expand to [N,16,16]
+    float* packed = static_cast<float*>(work);
+    if (int rc = launch_inverse_metric_tc_sym(t, z, n, packed, s)) return rc;
+    return launch_unpack_sym16(packed, n, ginv, s);
+  }
+  return launch_inverse_metric_tc(t, z, n, ginv, s);
+}
+
+int rlvae_inverse_metric_packed(const rlvae_tables_t* t, const float* z, int64_t n, float* packed,
+                                void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "inverse_metric_packed: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "inverse_metric_packed: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && packed != nullptr, "inverse_metric_packed: NULL pointer");
+  RLVAE_REQUIRE(t->tensor_capable && t->symmetric && t->Mts_hi != nullptr,
+                "inverse_metric_packed: needs latent_dim == 16 and symmetric metric matrices");
+  return launch_inverse_metric_tc_sym(t, z, n, packed, static_cast<cudaStream_t>(stream));
+}
+
+// G^{-1} in whichever layout is cheapest for the consumers inside this library:
+// *packed = 1 -> `buf` holds the symmetric packed [N,144] layout, else the full [N,d,d].
+static int inverse_metric_internal(const rlvae_tables* t, const float* z, int64_t n, float* buf, int path,
+                                   cudaStream_t s, int* packed) {
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  *packed = 0;
+  if (!use_tc) return launch_inverse_metric_direct(t, z, n, buf, s);
+  if (t->symmetric && t->Mts_hi != nullptr) {
+    *packed = 1;
+    return launch_inverse_metric_tc_sym(t, z, n, buf, s);
+  }
+  return launch_inverse_metric_tc(t, z, n, buf, s);
+}
+
+static int inverse_from(const float* a, int packed, int64_t n, int d, float* inv, float* lad, float* sgn,
+                        float* diag, int transpose, cudaStream_t s) {
+  return packed ? launch_batched_inverse_packed16(a, n, inv, lad, sgn, diag, transpose, s)
+                : launch_batched_inverse(a, n, d, inv, lad, sgn, diag, transpose, s);
 }
 
 int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet, float* sign,
@@ -277,27 +352,32 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   RLVAE_REQUIRE(n >= 0, "metric_eval: negative batch");
   if (n == 0) return 0;
   RLVAE_REQUIRE(z != nullptr, "metric_eval: z is NULL");
+  RLVAE_REQUIRE(work != nullptr, "metric_eval: workspace required");
   const int d = t->d;
   const int64_t mat = n * d * d;
   float* w = static_cast<float*>(work);
-  RLVAE_REQUIRE(work != nullptr, "metric_eval: workspace required");
-  float* ginv_buf = ginv ? ginv : w;
+  float* a_buf = w;                    // G^{-1}, full or packed (both fit in n*d*d floats)
   float* g_buf = g ? g : (w + mat);
   float* lad_buf = w + 2 * mat;
   float* gt_buf = w + 2 * mat + n;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = rlvae_inverse_metric(t, z, n, ginv_buf, path, stream)) return rc;
+  int packed = 0;
+  if (int rc = inverse_metric_internal(t, z, n, a_buf, path, s, &packed)) return rc;
+  if (ginv != nullptr) {
+    if (packed) { if (int rc = launch_unpack_sym16(a_buf, n, ginv, s)) return rc; }
+    else RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
+  }
   // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
   // G^T == G up to rounding, otherwise a transposed copy is produced.
   const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
   const bool plain_g = (g != nullptr) || ((grad_logdet_g != nullptr) && t->symmetric);
   if (plain_g || logdet_g != nullptr) {
-    if (int rc = launch_batched_inverse(ginv_buf, n, d, plain_g ? g_buf : nullptr,
-                                        logdet_g ? lad_buf : nullptr, nullptr, nullptr, 0, s))
+    if (int rc = inverse_from(a_buf, packed, n, d, plain_g ? g_buf : nullptr, logdet_g ? lad_buf : nullptr,
+                              nullptr, nullptr, 0, s))
       return rc;
   }
   if (need_gt) {
-    if (int rc = launch_batched_inverse(ginv_buf, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
+    if (int rc = inverse_from(a_buf, packed, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
   }
   if (logdet_g != nullptr) {
     // log|det G| = -log|det G^{-1}|
@@ -344,9 +424,10 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
 
   // one metric evaluation at the chain's current position: G^{-1}, then diag(G)/log|det|
   auto eval = [&](const float* zz) -> int {
-    if (int rc = rlvae_inverse_metric(t, zz, n, ginv, path, stream)) return rc;
+    int packed = 0;
+    if (int rc = inverse_metric_internal(t, zz, n, ginv, path, s, &packed)) return rc;
     // exact mode wants G^T for the contraction (see rlvae_metric_eval)
-    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
+    if (int rc = inverse_from(ginv, packed, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
       if (int rc = rlvae_metric_grad(t, zz, gfull, n, 1.f / t->T2, gex, path, stream)) return rc;
     return 0;
@@ -381,8 +462,9 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
   float* diag = w + 2 * n * d * d;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < n_steps; ++i) {
-    if (int rc = rlvae_inverse_metric(t, z, n, ginv, path, stream)) return rc;
-    if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
+    int packed = 0;
+    if (int rc = inverse_metric_internal(t, z, n, ginv, path, s, &packed)) return rc;
+    if (int rc = inverse_from(ginv, packed, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
     if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;
   }
   return 0;

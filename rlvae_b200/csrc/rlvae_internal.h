@@ -54,8 +54,11 @@ struct rlvae_tables {
   float* Mt_lo = nullptr;   // [256, Kpad]  M - hi
   float* Mn_hi = nullptr;   // [Kpad, 256]  natural, for the gradient pass
   float* Mn_lo = nullptr;   // [Kpad, 256]
-  float* caug = nullptr;    // [Kpad, 32] gradient pass B operand: [hi(c) | 1 | 0.. | lo(c) | 0..]
-  CUtensorMap tm_cstack, tm_mt_hi, tm_mt_lo, tm_mn_hi, tm_mn_lo;
+  float* caug = nullptr;    // [Kpad, 32] (reserved)
+  // symmetric tables only: packed upper triangle (136 -> 144 rows), transposed, hi/lo
+  float* Mts_hi = nullptr;  // [144, Kpad]
+  float* Mts_lo = nullptr;  // [144, Kpad]
+  CUtensorMap tm_cstack, tm_mt_hi, tm_mt_lo, tm_mn_hi, tm_mn_lo, tm_mts_hi, tm_mts_lo;
 };
 
 namespace rlvae {
@@ -69,6 +72,11 @@ int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float
                               float* out, cudaStream_t s);
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
                            float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
+// d == 16 only: `a` is the packed symmetric layout [N,144] written by the symmetric tensor kernel
+int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv, float* logabsdet,
+                                    float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
+int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s);
+constexpr int kSymCols = 144;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
                       int32_t* status, cudaStream_t s);
 int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist,
@@ -78,6 +86,10 @@ int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* 
 int tc_build_descriptors(rlvae_tables* t);
 int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
                              cudaStream_t s);
+// symmetric tables: packed [N,144] result (lambda already on the packed diagonal)
+int launch_inverse_metric_tc_sym(const rlvae_tables* t, const float* z, int64_t n, float* packed,
+                                 cudaStream_t s);
+int tc_build_sym_descriptors(rlvae_tables* t);
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n,
                           float scale, float* out, cudaStream_t s);
 

@@ -30,7 +30,12 @@ struct PP {
 // In-place Gauss-Jordan with implicit partial (row) pivoting.
 // After the sweep the lane that served as pivot at step j holds row j of A^{-1}; its slot m
 // holds column perm[m] (perm[m] = pivot row chosen at step m).
-template <int D>
+__host__ __device__ constexpr int sym16_index(int i, int j) {   // packed upper triangle, i <= j
+  return i * 16 - (i * (i - 1)) / 2 + (j - i);
+}
+
+// PACKED (D == 16 only): the input is the symmetric packed layout [N, 144] of the tensor kernel
+template <int D, bool PACKED = false>
 __global__ void __launch_bounds__(PP<D>::THREADS)
 batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv,
                        float* __restrict__ logabsdet, float* __restrict__ sign,
@@ -49,8 +54,16 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
   const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                        : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
 
-  const float* src = a + msafe * D * D;
-  for (int i = lane; i < D * D; i += LANES) sm[(i / D) * LD + (i % D)] = src[i];
+  if (PACKED) {
+    const float* src = a + msafe * kSymCols;
+    for (int i = lane; i < D * D; i += LANES) {
+      const int rr = i / D, cc = i % D;
+      sm[rr * LD + cc] = src[rr <= cc ? sym16_index(rr, cc) : sym16_index(cc, rr)];
+    }
+  } else {
+    const float* src = a + msafe * D * D;
+    for (int i = lane; i < D * D; i += LANES) sm[(i / D) * LD + (i % D)] = src[i];
+  }
   __syncwarp(gmask);
 
   float r[RPL][D];
@@ -174,6 +187,32 @@ int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* 
 #undef CASE
     default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be 1,2,4,8,16 or 32");
   }
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv, float* logabsdet,
+                                    float* sign, float* diag_inv, int transpose_inv, cudaStream_t s) {
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)((n + PP<16>::MATS - 1) / PP<16>::MATS);
+  batched_inverse_kernel<16, true><<<grid, PP<16>::THREADS, 0, s>>>(a_packed, n, inv, logabsdet, sign,
+                                                                     diag_inv, transpose_inv);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void unpack_sym16_kernel(const float* __restrict__ packed, int64_t n, float* __restrict__ full) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * 256) return;
+  const int64_t p = gid >> 8;
+  const int e = (int)(gid & 255), i = e >> 4, j = e & 15;
+  full[gid] = packed[p * kSymCols + (i <= j ? sym16_index(i, j) : sym16_index(j, i))];
+}
+
+int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int64_t total = n * 256;
+  unpack_sym16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a_packed, n, full);
   RLVAE_CUDA_OK(cudaGetLastError());
   return 0;
 }

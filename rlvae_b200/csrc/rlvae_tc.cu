@@ -76,6 +76,7 @@ constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;         // + alignment slack
 constexpr int OUT_LD = 132;                                       // epilogue staging row (floats)
 static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
+static_assert(144 == kSymCols, "packed row length");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t TMEM_COLS = 512;
@@ -83,11 +84,21 @@ constexpr uint32_t TM_CH = 0;        // + buf*128 : chunk accumulator (2 buffers
 constexpr uint32_t TM_SP = 256;      // + buf*128 : S/P_hi (64) ; + 64 : P_lo (64)
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, K-major both, N>>3, M>>4
-constexpr uint32_t make_idesc(int M, int N) {
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 constexpr uint32_t IDESC_G1 = make_idesc(128, BK);      // N = 64
 constexpr uint32_t IDESC_G2 = make_idesc(128, NHALF);
+// Symmetric tables: only the 136 entries i <= j of every M_k (packed row-major upper triangle,
+// padded to 144) are accumulated.  Column half 0 owns packed columns [0,80), half 1 [80,144).
+constexpr int SYM_COLS = 144;        // packed row length in HBM (136 real + 8 zero)
+constexpr int SYM_H0 = 80;           // columns of half 0 (MMA N = 80), half 1 has 64 (N = 64)
+constexpr uint32_t SYM_ATOM_BYTES = SYM_H0 * 128;
+constexpr int SYM_FOLD = 48;         // running-total columns per exp thread (2 groups x 48 >= 80)
+constexpr int SYM_OUT_LD = 100;
+__host__ __device__ constexpr int sym_index(int i, int j) {   // i <= j
+  return i * 16 - (i * (i - 1)) / 2 + (j - i);
+}
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -176,6 +187,14 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
         "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),   \
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                           \
       : "r"(taddr) : "memory")
+#define TMEM_LD16(taddr, r)                                                                          \
+  asm volatile(                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                      \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                              \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),          \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),      \
+        "=r"(r[14]), "=r"(r[15])                                                                     \
+      : "r"(taddr) : "memory")
 #define TMEM_ST32(taddr, r)                                                                          \
   asm volatile(                                                                                      \
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                \
@@ -256,6 +275,7 @@ __device__ __forceinline__ void issue_gemm1(uint32_t d_tmem, uint64_t a1_desc, u
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
+template <bool SYM>
 __global__ void __launch_bounds__(THREADS, 1)
 inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                          const __grid_constant__ CUtensorMap tm_mt_hi,
@@ -281,7 +301,13 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
-  const int half = blockIdx.y;         // which 128 of the 256 output columns
+  const int half = blockIdx.y;         // which 128 of the 256 output columns (SYM: 80 + 64 of 144)
+  const int ncols = SYM ? (half == 0 ? SYM_H0 : SYM_COLS - SYM_H0) : NHALF;   // MMA N of GEMM2
+  const int col_base = SYM ? half * SYM_H0 : half * NHALF;
+  constexpr uint32_t ATOM_BYTES = SYM ? SYM_ATOM_BYTES : M_ATOM_BYTES;
+  constexpr uint32_t TILE_BYTES = 2 * ATOM_BYTES;                             // bytes TMA delivers per stage
+  constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
+  const uint32_t idesc_g2 = make_idesc(128, ncols);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 1 + 4); }
@@ -337,11 +363,11 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const int it = 2 * jm + h, ms = it % M_STAGES;
         mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
+          mbar_expect_tx(BAR_M_FULL(ms), TILE_BYTES);
           const CUtensorMap* map = (h == 0) ? &tm_mt_hi : &tm_mt_lo;
           const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
-          tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, half * NHALF);
-          tma_load_2d(dst + M_ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, half * NHALF);
+          tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, col_base);
+          tma_load_2d(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, col_base);
         }
         __syncwarp();
       }
@@ -402,11 +428,11 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const uint32_t acc = tmem_base + TM_CH + (chunk & 1) * 128;
         const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
         const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
-        // K index kk = 8 centroids; atom = kk / 4 (16 KB apart = +1024 in descriptor units)
+        // K index kk = 8 centroids; atom = kk / 4 (ATOM_BYTES apart)
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_hi + 8 * kk, bh + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, !(first && kk == 0));
+            mma_ts(acc, p_hi + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, !(first && kk == 0));
         }
         __syncwarp();
         PROF_ADD(pw_issue);
@@ -416,7 +442,7 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_lo + 8 * kk, bh + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, 1);
+            mma_ts(acc, p_lo + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
           tc_commit(BAR_M_EMPTY(ms_hi));
         }
         __syncwarp();
@@ -431,7 +457,7 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_hi + 8 * kk, bl + (kk >> 2) * 1024 + 2 * (kk & 3), IDESC_G2, 1);
+            mma_ts(acc, p_hi + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
           tc_commit(BAR_M_EMPTY(ms_lo));
         }
         __syncwarp();
@@ -455,19 +481,33 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     // =========================================================== exp groups (one thread per point)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float two_alpha = 2.f * alpha;
-    float omain[64];                        // running total: columns [64*grp, 64*grp+64) of this row
+    // running total: FOLD columns of this row per thread (dense 2x64 = 128, packed 2x48 >= 80)
+    constexpr int FOLD = SYM ? SYM_FOLD : 64;
+    float omain[FOLD];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) omain[i] = 0.f;
+    for (int i = 0; i < FOLD; ++i) omain[i] = 0.f;
     // fold chunk c (finished on the tensor core) into the running total with RN fp32 adds
     auto fold_chunk = [&](int c, bool signal) {
-      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128 + grp * 64;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128 + grp * FOLD;
+      {
         uint32_t a[32];
-        TMEM_LD32(src + cb * 32, a);
+        TMEM_LD32(src, a);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) omain[cb * 32 + i] += __uint_as_float(a[i]);
+        for (int i = 0; i < 32; ++i) omain[i] += __uint_as_float(a[i]);
+      }
+      if (SYM) {     // columns 32..47 of this group's range (beyond ncols: never-written TMEM, unused)
+        uint32_t a[16];
+        TMEM_LD16(src + 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) omain[32 + i] += __uint_as_float(a[i]);
+      } else {
+        uint32_t a[32];
+        TMEM_LD32(src + 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) omain[32 + i] += __uint_as_float(a[i]);
       }
       if (signal) {
         tc_fence_before();
@@ -532,27 +572,55 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     const int num_chunks = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
     while (folded < num_chunks) { fold_chunk(folded, false); ++folded; }
     float* stage = reinterpret_cast<float*>(gbase + OFF_M);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      float4 o;
-      float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = half * NHALF + grp * 64 + q * 4 + e;
-        op[e] = omain[q * 4 + e] + ((col % 17 == 0) ? lambda : 0.f);
-      }
-      *reinterpret_cast<float4*>(stage + prow * OUT_LD + grp * 64 + q * 4) = o;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight exp warps only
     const int t = threadIdx.x - 64;
     const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
-    float* dst = out + row0 * NCOL + half * NHALF;
+    if (!SYM) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float4 o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = half * NHALF + grp * 64 + q * 4 + e;
+          op[e] = omain[q * 4 + e] + ((col % 17 == 0) ? lambda : 0.f);
+        }
+        *reinterpret_cast<float4*>(stage + prow * OUT_LD + grp * 64 + q * 4) = o;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight exp warps only
+      float* dst = out + row0 * NCOL + half * NHALF;
 #pragma unroll 4
-    for (int i = t; i < TILE_M * (NHALF / 4); i += 256) {
-      const int r = i >> 5, c4 = i & 31;
-      if (r < rows_here)
-        *reinterpret_cast<float4*>(dst + (int64_t)r * NCOL + c4 * 4) =
-            *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+      for (int i = t; i < TILE_M * (NHALF / 4); i += 256) {
+        const int r = i >> 5, c4 = i & 31;
+        if (r < rows_here)
+          *reinterpret_cast<float4*>(dst + (int64_t)r * NCOL + c4 * 4) =
+              *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+      }
+    } else {
+      // packed output [N, 144]: this CTA owns packed columns [col_base, col_base + ncols)
+#pragma unroll
+      for (int q = 0; q < SYM_FOLD / 4; ++q) {
+        float4 o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int pc = col_base + grp * SYM_FOLD + q * 4 + e;      // packed index
+          // diagonal entries of the packed upper triangle: p(i,i) = 16 i - i (i-1)/2
+          bool diag = false;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
+          op[e] = omain[q * 4 + e] + (diag ? lambda : 0.f);
+        }
+        *reinterpret_cast<float4*>(stage + prow * SYM_OUT_LD + grp * SYM_FOLD + q * 4) = o;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* dst = out + row0 * SYM_COLS + col_base;
+      const int c4n = ncols / 4;                                      // 20 or 16 float4 per row
+      for (int i = t; i < TILE_M * c4n; i += 256) {
+        const int r = i / c4n, c4 = i - r * c4n;
+        if (r < rows_here)
+          *reinterpret_cast<float4*>(dst + (int64_t)r * SYM_COLS + c4 * 4) =
+              *reinterpret_cast<const float4*>(stage + r * SYM_OUT_LD + c4 * 4);
+      }
     }
   }
 
@@ -895,6 +963,41 @@ int tc_build_descriptors(rlvae_tables* t) {
   return 0;
 }
 
+int tc_build_sym_descriptors(rlvae_tables* t) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  RLVAE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+  PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(fn);
+  const uint64_t Kpad = (uint64_t)t->Kpad;
+  // packed-transposed tables [144, Kpad]; a box is one 32-centroid atom x 80 packed rows (rows past
+  // 144 are out of bounds and arrive as zeros)
+  if (int rc = make_map_2d(enc, &t->tm_mts_hi, t->Mts_hi, Kpad, tc::SYM_COLS, 32, tc::SYM_H0)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mts_lo, t->Mts_lo, Kpad, tc::SYM_COLS, 32, tc::SYM_H0)) return rc;
+  return 0;
+}
+
+int launch_inverse_metric_tc_sym(const rlvae_tables* t, const float* z, int64_t n, float* packed,
+                                 cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mts_hi != nullptr,
+                "symmetric tensor path needs latent_dim == 16 and symmetric tables");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
+                "tensor path needs 16-byte aligned z and output");
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), 2);
+  const float alpha = 1.4426950408889634f / t->T2;
+  tc::inverse_metric_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
+      t->tm_cstack, t->tm_mts_hi, t->tm_mts_lo, z, t->cbias, n, t->Kpad / tc::BK, alpha, t->lambda, packed);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
                              cudaStream_t s) {
   if (n == 0) return 0;
@@ -903,13 +1006,13 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
                 "tensor path needs 16-byte aligned z and output");
   static bool attr_set = false;
   if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel,
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     attr_set = true;
   }
   const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), tc::NCOL / tc::NHALF);
   const float alpha = 1.4426950408889634f / t->T2;
-  tc::inverse_metric_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
+  tc::inverse_metric_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
       t->tm_cstack, t->tm_mt_hi, t->tm_mt_lo, z, t->cbias, n, t->Kpad / tc::BK, alpha, t->lambda, ginv);
   RLVAE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(h, name), name
     assert h.rlvae_abi_version() == 1
     # argument validation happens before any CUDA call: safe without a GPU
-    assert h.rlvae_inverse_metric(None, None, 4, None, 0, None) != 0
+    assert h.rlvae_inverse_metric(None, None, 4, None, None, 0, None) != 0
     assert b'not loaded' in h.rlvae_last_error()
     assert h.rlvae_metric_eval_workspace(10, 16) == 4 * (3 * 10 * 256 + 10)
 
