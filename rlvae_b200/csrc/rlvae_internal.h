@@ -59,6 +59,8 @@ struct rlvae_tables {
   float* Mts_hi = nullptr;  // [144, Kpad]
   float* Mts_lo = nullptr;  // [144, Kpad]
   CUtensorMap tm_cstack, tm_mt_hi, tm_mt_lo, tm_mn_hi, tm_mn_lo, tm_mts_hi, tm_mts_lo;
+  // CTA-pair variants: each CTA of a pair fetches half of the B-tile rows (smaller boxes)
+  CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
 };
 
 namespace rlvae {

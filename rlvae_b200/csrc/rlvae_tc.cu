@@ -33,10 +33,17 @@
 // [N,K] never exists outside TMEM; the tables stream L2 -> smem once per 128 points.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "rlvae_internal.h"
 
 // -DRLVAE_TC_PROFILE: CTA (0,0) prints where its MMA thread and exp group A spend their cycles
+#ifdef RLVAE_TC_PROFILE
+__device__ long long g_trace[4][16][8];
+#define TRACE(role, j, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (j) >= 40 && (j) < 56 && lane == 0) g_trace[role][(j) - 40][slot] = clock64(); } while (0)
+#else
+#define TRACE(role, j, slot) do {} while (0)
+#endif
 #ifdef RLVAE_TC_PROFILE
 #define PROF_T0() long long _pt = clock64()
 #define PROF_ADD(acc) do { long long _n = clock64(); (acc) += _n - _pt; _pt = _n; } while (0)
@@ -71,7 +78,7 @@ constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;                      // C ring
 constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;       // M ring
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;    // bias ring
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;    // mbarriers
-constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + 1;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + 1 + 2;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;         // + alignment slack
 constexpr int OUT_LD = 132;                                       // epilogue staging row (floats)
@@ -164,6 +171,52 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants.  The pair = two CTAs of a cluster on one TPC: the MMA
+// spans M = 256 (128 TMEM lanes in each CTA) and each CTA supplies HALF of the B tile from its own
+// shared memory, so per-SM TMA ingest and B-operand smem reads are halved.  The leader (even rank)
+// issues; barriers the leader waits on are signalled from the peer through shared::cluster.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // works from either CTA of the pair
+  // default semantics (.release.cta): what is published lives in this SM's TMEM and is ordered by
+  // tcgen05.wait/fence; a cluster-scope release here cost ~900 cycles per arrive (measured)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                                 int c1) {           // completes on the LEADER's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {       // arrives on both CTAs' barrier
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, 128-byte swizzle, 128-byte rows, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
@@ -266,16 +319,24 @@ __device__ __forceinline__ float write_z_tiles(uint8_t* gbase, const float* __re
 }
 
 // GEMM1: S[128 x 32] = (z_hi|z_hi).(c_hi|c_lo) + z_lo.c_hi   (6 tcgen05.mma, K = 8 each)
+template <bool PAIR = false>
 __device__ __forceinline__ void issue_gemm1(uint32_t d_tmem, uint64_t a1_desc, uint64_t a2_desc,
                                             uint64_t b_desc) {
+  constexpr uint32_t id = make_idesc(PAIR ? 256 : 128, BK);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) mma_ss(d_tmem, a1_desc + 2 * k, b_desc + 2 * k, IDESC_G1, k > 0);
+  for (int k = 0; k < 4; ++k) {
+    if (PAIR) mma_ss_pair(d_tmem, a1_desc + 2 * k, b_desc + 2 * k, id, k > 0);
+    else mma_ss(d_tmem, a1_desc + 2 * k, b_desc + 2 * k, id, k > 0);
+  }
 #pragma unroll
-  for (int k = 0; k < 2; ++k) mma_ss(d_tmem, a2_desc + 2 * k, b_desc + 2 * k, IDESC_G1, 1);
+  for (int k = 0; k < 2; ++k) {
+    if (PAIR) mma_ss_pair(d_tmem, a2_desc + 2 * k, b_desc + 2 * k, id, 1);
+    else mma_ss(d_tmem, a2_desc + 2 * k, b_desc + 2 * k, id, 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
-template <bool SYM>
+template <bool SYM, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                          const __grid_constant__ CUtensorMap tm_mt_hi,
@@ -296,24 +357,34 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
   auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
   const uint32_t BAR_O_FULL = bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2);
+  auto BAR_BIAS_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 3 + s); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 3 + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
   const int half = blockIdx.y;         // which 128 of the 256 output columns (SYM: 80 + 64 of 144)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair
+  const bool leader = rank == 0;
   const int ncols = SYM ? (half == 0 ? SYM_H0 : SYM_COLS - SYM_H0) : NHALF;   // MMA N of GEMM2
   const int col_base = SYM ? half * SYM_H0 : half * NHALF;
-  constexpr uint32_t ATOM_BYTES = SYM ? SYM_ATOM_BYTES : M_ATOM_BYTES;
-  constexpr uint32_t TILE_BYTES = 2 * ATOM_BYTES;                             // bytes TMA delivers per stage
+  // rows of the B tile this CTA holds per 32-centroid atom (a pair splits N between its CTAs)
+  constexpr int ROWS_BOX = (SYM ? SYM_H0 : NHALF) / (PAIR ? 2 : 1);
+  constexpr uint32_t ATOM_BYTES = ROWS_BOX * 128;
+  constexpr uint32_t TILE_BYTES = 2 * ATOM_BYTES;                             // bytes TMA delivers per stage per CTA
   constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
-  const uint32_t idesc_g2 = make_idesc(128, ncols);
+  const int row_cta = col_base + (PAIR ? (int)rank * (ncols / 2) : 0);
+  const uint32_t idesc_g2 = make_idesc(PAIR ? 256 : 128, ncols);
+  constexpr int NPAIR = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 1 + 4); }
-    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4); }
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_BIAS_FULL(s), 1);
+    }
+    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) mbar_init(BAR_CH_FREE(b), 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FREE(b), 8 * NPAIR); mbar_init(BAR_CH_FULL(b), 1); }
     mbar_init(BAR_O_FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
@@ -321,9 +392,15 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mt_lo) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
 
   // exp-thread identity: TMEM lane quarter = warp % 4, point = quarter*32 + lane, group = even/odd blocks
@@ -351,23 +428,31 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers initialised in BOTH CTAs before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // =========================================================== TMA producer (warp-converged)
+    // In a pair every CTA fetches only ITS half of each B tile (rows row_cta.. of the table slice,
+    // 32 of the 64 centroid rows); all transaction bytes complete on the leader's FULL barrier.
     auto load_m = [&](int jm) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int it = 2 * jm + h, ms = it % M_STAGES;
         mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        TRACE(0, jm, 1 + h);
         if (elect_one()) {
-          mbar_expect_tx(BAR_M_FULL(ms), TILE_BYTES);
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
           const CUtensorMap* map = (h == 0) ? &tm_mt_hi : &tm_mt_lo;
           const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
-          tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, col_base);
-          tma_load_2d(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, col_base);
+          if (PAIR) {
+            tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d_pair(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
+          } else {
+            tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
+          }
         }
         __syncwarp();
       }
@@ -375,10 +460,18 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     for (int j = 0; j < num_blocks; ++j) {
       const int cs = j % C_STAGES;
       mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      TRACE(0, j, 0);
       if (elect_one()) {
-        mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + BIAS_BYTES);
-        tma_load_2d(base + OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
-        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
+        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+        const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
+        if (PAIR) {           // 32 of the 64 centroid rows per CTA (box = 32 rows)
+          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+        } else {
+          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+        }
+        mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
       }
       __syncwarp();
       // the M tiles trail the centroid tiles by two super-blocks, like GEMM2 trails GEMM1
@@ -386,26 +479,28 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
     for (int jm = (num_blocks >= 2 ? num_blocks - 2 : 0); jm < num_blocks; ++jm) load_m(jm);
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (warp-converged)
-    {
+    // =========================================================== MMA issuer (warp-converged; pair: leader only)
+    if (leader) {
       const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
       const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
       // GEMM1 for super-block j; `waited` = its C_FULL wait already happened
       auto gemm1 = [&](int j, bool waited) {
         const int cs = j % C_STAGES;
         if (!waited) mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_gemm1(tmem_base + TM_SP + (j & 1) * 128, a1_desc, a2_desc,
-                      make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
-          tc_commit(BAR_S_FULL(j & 1));
-          tc_commit(BAR_C_EMPTY(cs));
+          issue_gemm1<PAIR>(tmem_base + TM_SP + (j & 1) * 128, a1_desc, a2_desc,
+                             make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
+          if (PAIR) tc_commit_pair(BAR_S_FULL(j & 1)); else tc_commit(BAR_S_FULL(j & 1));
+          // the C stage is released by the exp warps: their arrival follows S_FULL, i.e. GEMM1's completion
         }
         __syncwarp();
       };
       auto wait_m = [&](int it) { mbar_wait(BAR_M_FULL(it % M_STAGES), (it / M_STAGES) & 1); };
-      long long pw_g1 = 0, pw_w = 0, pw_p = 0, pw_issue = 0;
-      (void)pw_g1; (void)pw_w; (void)pw_p; (void)pw_issue;
+      long long pw_g1 = 0, pw_w = 0, pw_p = 0, pw_issue = 0, pw_wc = 0, pw_wf = 0;
+      (void)pw_g1; (void)pw_w; (void)pw_p; (void)pw_issue; (void)pw_wc; (void)pw_wf;
       gemm1(0, false);
       if (num_blocks > 1) gemm1(1, false);
       wait_m(0);
@@ -418,6 +513,7 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       // a group of 8 queued MMAs so that its ~60-90 cycle latency never drains the tensor pipe.
       for (int j = 0; j < num_blocks; ++j) {
         PROF_T0();
+        TRACE(1, j, 0);
         const int chunk = j / CHUNK_BLOCKS;
         const int first = (j % CHUNK_BLOCKS) == 0;   // a new chunk overwrites its accumulator
         const int sb = j & 1;
@@ -432,49 +528,60 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_hi + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, !(first && kk == 0));
+            MMA_TS(acc, p_hi + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, !(first && kk == 0));
         }
         __syncwarp();
         PROF_ADD(pw_issue);
+        TRACE(1, j, 1);
         if (j + 1 < num_blocks) wait_m(2 * j + 2);
-        if (j + 2 < num_blocks) mbar_wait(BAR_C_FULL((j + 2) % C_STAGES), ((j + 2) / C_STAGES) & 1);
         PROF_ADD(pw_w);
+        TRACE(1, j, 2);
+        if (j + 2 < num_blocks) mbar_wait(BAR_C_FULL((j + 2) % C_STAGES), ((j + 2) / C_STAGES) & 1);
+        PROF_ADD(pw_wc);
+        TRACE(1, j, 3);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_lo + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
-          tc_commit(BAR_M_EMPTY(ms_hi));
+            MMA_TS(acc, p_lo + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
+          COMMIT(BAR_M_EMPTY(ms_hi));
         }
         __syncwarp();
         PROF_ADD(pw_issue);
+        TRACE(1, j, 4);
         if (j + 1 < num_blocks) {
           wait_m(2 * j + 3);
+          PROF_ADD(pw_w);
+          TRACE(1, j, 5);
           const int nchunk = (j + 1) / CHUNK_BLOCKS;   // chunk buffer of the next super-block
           if (((j + 1) % CHUNK_BLOCKS) == 0 && nchunk >= 2)   // both exp groups folded chunk-2
             mbar_wait(BAR_CH_FREE(nchunk & 1), ((nchunk >> 1) - 1) & 1);
         }
-        PROF_ADD(pw_w);
+        PROF_ADD(pw_wf);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts(acc, p_hi + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
-          tc_commit(BAR_M_EMPTY(ms_lo));
+            MMA_TS(acc, p_hi + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
+          COMMIT(BAR_M_EMPTY(ms_lo));
+          if ((j % CHUNK_BLOCKS) == CHUNK_BLOCKS - 1 || j == num_blocks - 1)
+            COMMIT(BAR_CH_FULL(chunk & 1));          // chunk complete: the exp groups may fold it
         }
         __syncwarp();
         PROF_ADD(pw_issue);
         // GEMM1 two super-blocks ahead re-uses this S/P buffer: ordered behind GEMM2(j) in the pipe
+        TRACE(1, j, 6);
         if (j + 2 < num_blocks) gemm1(j + 2, true);
         PROF_ADD(pw_g1);
         if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) & 1), ((j + 1) >> 1) & 1);
         PROF_ADD(pw_p);
+        TRACE(1, j, 7);
       }
-      if (elect_one()) tc_commit(BAR_O_FULL);
+      if (elect_one()) COMMIT(BAR_O_FULL);
       __syncwarp();
 #ifdef RLVAE_TC_PROFILE
       if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-        printf("[tc prof] MMA warp per super-block: total %lld | gemm1 issue %lld  hidden waits %lld  p_full %lld  gemm2 issue %lld\n",
-               (clock64() - loop_t0) / num_blocks, pw_g1 / num_blocks, pw_w / num_blocks, pw_p / num_blocks,
-               pw_issue / num_blocks);
+        printf("[tc prof] MMA warp per super-block: total %lld | gemm1 issue %lld  wait M %lld  wait C %lld  wait CH_FREE %lld  p_full %lld  gemm2 issue %lld\n",
+               (clock64() - loop_t0) / num_blocks, pw_g1 / num_blocks, pw_w / num_blocks, pw_wc / num_blocks,
+               pw_wf / num_blocks, pw_p / num_blocks, pw_issue / num_blocks);
 #endif
     }
   } else {
@@ -512,20 +619,23 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (signal) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR_CH_FREE(c & 1));
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
       }
     };
     int folded = 0;                         // chunks already folded by this group
+    const int num_chunks_total = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
     long long pe_wait = 0, pe_work = 0, pe_fold = 0;
     (void)pe_wait; (void)pe_work; (void)pe_fold;
     for (int j = grp; j < num_blocks; j += 2) {
       PROF_T0();
       const int cs = j % C_STAGES;
       const uint32_t sp = tmem_base + lane_addr + TM_SP + (j & 1) * 128;
-      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);   // bias bytes visible to this thread
+      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 0);
+      mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);   // bias bytes visible to this thread
       mbar_wait(BAR_S_FULL(j & 1), (j >> 1) & 1);
       tc_fence_after();
       PROF_ADD(pe_wait);
+      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 1);
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t s[32], l[32];
@@ -552,14 +662,22 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR_P_FULL(j & 1));
+        if (PAIR) mbar_arrive_leader(BAR_P_FULL(j & 1)); else mbar_arrive(BAR_P_FULL(j & 1));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
       PROF_ADD(pe_work);
-      // S(j) came from GEMM1(j), issued after GEMM2(j-2): every chunk ending at a super-block
-      // <= j-2 is complete.  CH_FREE tells the MMA thread when both groups have drained a buffer.
-      while ((folded + 1) * CHUNK_BLOCKS - 1 <= j - 2) { fold_chunk(folded, true); ++folded; }
+      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 2);
+      // Fold every chunk whose last super-block is <= j as soon as the tensor core has finished it
+      // (CH_FULL); CH_FREE then tells the MMA warp that both groups have drained that buffer.  The
+      // wait costs nothing useful: this group's next S tile is only issued after GEMM2(j) anyway.
+      while (folded < num_chunks_total && min((folded + 1) * CHUNK_BLOCKS - 1, num_blocks - 1) <= j) {
+        mbar_wait(BAR_CH_FULL(folded & 1), (folded >> 1) & 1);
+        tc_fence_after();
+        fold_chunk(folded, true);
+        ++folded;
+      }
       PROF_ADD(pe_fold);
+      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 3);
     }
 #ifdef RLVAE_TC_PROFILE
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64)
@@ -569,8 +687,7 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     // ---------------------------------------------------------- epilogue
     mbar_wait(BAR_O_FULL, 0);
     tc_fence_after();
-    const int num_chunks = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
-    while (folded < num_chunks) { fold_chunk(folded, false); ++folded; }
+    while (folded < num_chunks_total) { fold_chunk(folded, false); ++folded; }
     float* stage = reinterpret_cast<float*>(gbase + OFF_M);
     const int t = threadIdx.x - 64;
     const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
@@ -624,11 +741,30 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
   }
 
+#undef MMA_TS
+#undef COMMIT
   tc_fence_before();
+#ifdef RLVAE_TC_PROFILE
   __syncthreads();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const long long t0 = g_trace[1][0][0];
+    for (int jj = 0; jj < 8; ++jj) {
+      printf("[trace j=%d] prod: C %lld Mhi(j) %lld Mlo(j) %lld | mma: start %lld g1done %lld wMhi %lld wC %lld g2 %lld wMlo %lld g3 %lld pfull %lld | expA/B: top %lld S %lld P %lld fold %lld\n",
+             40 + jj, g_trace[0][jj][0] - t0, g_trace[0][jj][1] - t0, g_trace[0][jj][2] - t0,
+             g_trace[1][jj][0] - t0, g_trace[1][jj][1] - t0, g_trace[1][jj][2] - t0, g_trace[1][jj][3] - t0,
+             g_trace[1][jj][4] - t0, g_trace[1][jj][5] - t0, g_trace[1][jj][6] - t0, g_trace[1][jj][7] - t0,
+             g_trace[2 + (jj & 1)][jj][0] - t0, g_trace[2 + (jj & 1)][jj][1] - t0, g_trace[2 + (jj & 1)][jj][2] - t0,
+             g_trace[2 + (jj & 1)][jj][3] - t0);
+    }
+  }
+#endif
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // no CTA of a pair exits while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -779,6 +915,8 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (elect_one()) {
         mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + CN_BYTES + BIAS_BYTES);
         tma_load_2d(base + grad::OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+        tma_load_2d(base + grad::OFF_C + cs * C_TILE_BYTES + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0,
+                    j * BK + 32);
         bulk_load_1d(base + OFF_CN + cs * CN_BYTES, cnat + (int64_t)j * BK * 16, CN_BYTES, BAR_C_FULL(cs));
         bulk_load_1d(base + grad::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
       }
@@ -954,10 +1092,12 @@ int tc_build_descriptors(rlvae_tables* t) {
   RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
   PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(fn);
   const uint64_t Kpad = (uint64_t)t->Kpad;
-  if (int rc = make_map_2d(enc, &t->tm_cstack, t->cstack, 32, Kpad, 32, tc::BK)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_cstack, t->cstack, 32, Kpad, 32, 32)) return rc;   // 32 centroid rows per box
   // M^T tiles are fetched one 32-centroid swizzle atom (128 B rows) at a time
   if (int rc = make_map_2d(enc, &t->tm_mt_hi, t->Mt_hi, Kpad, tc::NCOL, 32, tc::NHALF)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_mt_lo, t->Mt_lo, Kpad, tc::NCOL, 32, tc::NHALF)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mt2_hi, t->Mt_hi, Kpad, tc::NCOL, 32, tc::NHALF / 2)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mt2_lo, t->Mt_lo, Kpad, tc::NCOL, 32, tc::NHALF / 2)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn_hi, t->Mn_hi, Kpad)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn_lo, t->Mn_lo, Kpad)) return rc;
   return 0;
@@ -974,6 +1114,49 @@ int tc_build_sym_descriptors(rlvae_tables* t) {
   // 144 are out of bounds and arrive as zeros)
   if (int rc = make_map_2d(enc, &t->tm_mts_hi, t->Mts_hi, Kpad, tc::SYM_COLS, 32, tc::SYM_H0)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_mts_lo, t->Mts_lo, Kpad, tc::SYM_COLS, 32, tc::SYM_H0)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mts2_hi, t->Mts_hi, Kpad, tc::SYM_COLS, 32, tc::SYM_H0 / 2)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_mts2_lo, t->Mts_lo, Kpad, tc::SYM_COLS, 32, tc::SYM_H0 / 2)) return rc;
+  return 0;
+}
+
+// CTA pairs (cta_group::2) are the default; RLVAE_TC_PAIR=0 selects the single-CTA kernels.
+static bool use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RLVAE_TC_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool SYM, bool PAIR>
+static int launch_fwd(const CUtensorMap& c, const CUtensorMap& hi, const CUtensorMap& lo, const rlvae_tables* t,
+                      const float* z, int64_t n, float* out, cudaStream_t s) {
+  auto kern = tc::inverse_metric_tc_kernel<SYM, PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;               // clusters of two point tiles
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 2, 1);
+  cfg.blockDim = dim3(tc::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  const float lambda = t->lambda;
+  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, cbias, n, nb, alpha, lambda, out));
   return 0;
 }
 
@@ -984,18 +1167,8 @@ int launch_inverse_metric_tc_sym(const rlvae_tables* t, const float* z, int64_t 
                 "symmetric tensor path needs latent_dim == 16 and symmetric tables");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
                 "tensor path needs 16-byte aligned z and output");
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    attr_set = true;
-  }
-  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), 2);
-  const float alpha = 1.4426950408889634f / t->T2;
-  tc::inverse_metric_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
-      t->tm_cstack, t->tm_mts_hi, t->tm_mts_lo, z, t->cbias, n, t->Kpad / tc::BK, alpha, t->lambda, packed);
-  RLVAE_CUDA_OK(cudaGetLastError());
-  return 0;
+  return use_pairs() ? launch_fwd<true, true>(t->tm_cstack, t->tm_mts2_hi, t->tm_mts2_lo, t, z, n, packed, s)
+                     : launch_fwd<true, false>(t->tm_cstack, t->tm_mts_hi, t->tm_mts_lo, t, z, n, packed, s);
 }
 
 int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
@@ -1004,18 +1177,8 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(ginv) & 15) == 0,
                 "tensor path needs 16-byte aligned z and output");
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::inverse_metric_tc_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    attr_set = true;
-  }
-  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), tc::NCOL / tc::NHALF);
-  const float alpha = 1.4426950408889634f / t->T2;
-  tc::inverse_metric_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
-      t->tm_cstack, t->tm_mt_hi, t->tm_mt_lo, z, t->cbias, n, t->Kpad / tc::BK, alpha, t->lambda, ginv);
-  RLVAE_CUDA_OK(cudaGetLastError());
-  return 0;
+  return use_pairs() ? launch_fwd<false, true>(t->tm_cstack, t->tm_mt2_hi, t->tm_mt2_lo, t, z, n, ginv, s)
+                     : launch_fwd<false, false>(t->tm_cstack, t->tm_mt_hi, t->tm_mt_lo, t, z, n, ginv, s);
 }
 
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
