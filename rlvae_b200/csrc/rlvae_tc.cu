@@ -336,33 +336,68 @@ __device__ __forceinline__ void issue_gemm1(uint32_t d_tmem, uint64_t a1_desc, u
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
+// Warp-specialised, 512 threads = 4 warpgroups:
+//   WG0  warp 0 TMA producer, warp 1 MMA issuer (warps 2,3 idle)          -> 40 registers
+//   WG1  exp group A (even super-blocks), WG2 exp group B (odd)            -> 112 registers
+//   WG3  fold group: owns the fp32 running total, folds every finished chunk, writes the output -> 232
+// Pipeline per 64-centroid super-block j (all MMAs execute in issue order):
+//   GEMM1(j+3) is issued right after GEMM2(j), so S(j+3) is ready ~2 iterations before P(j+3) is
+//   needed: the exp stage (MUFU-bound, ~1.2-1.5k cycles of latency) is off the critical path.
+//   Three S/P buffers + ONE chunk accumulator = 512 TMEM columns; the accumulator is handed to the
+//   fold group at every chunk end (CH_FULL) and taken back (CH_FREE) while GEMM1(j+3) keeps the
+//   tensor pipe busy.
+namespace fwd {
+constexpr int THREADS = 512;
+constexpr int C_STAGES = 4;
+constexpr int SP_BUFS = 3;
+constexpr int M_STAGES = 5;
+constexpr int AHEAD = 3;             // GEMM1 runs this many super-blocks ahead of GEMM2
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
+constexpr uint32_t TM_ACC = 0;       // chunk accumulator (<= 128 columns)
+constexpr uint32_t TM_SP = 128;      // + buf*128 : S/P_hi (64) ; + 64 : P_lo (64)
+}  // namespace fwd
+
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
 template <bool SYM, bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(fwd::THREADS, 1)
 inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                          const __grid_constant__ CUtensorMap tm_mt_hi,
                          const __grid_constant__ CUtensorMap tm_mt_lo,
                          const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
-                         int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
+                         int num_blocks, int chunk_blocks, float alpha /* log2(e)/T^2 */, float lambda,
                          float* __restrict__ out) {
+  constexpr int C_STAGES = fwd::C_STAGES, SP_BUFS = fwd::SP_BUFS, M_STAGES = fwd::M_STAGES, AHEAD = fwd::AHEAD;
+  constexpr uint32_t OFF_C = fwd::OFF_C, OFF_M = fwd::OFF_M, OFF_BIAS = fwd::OFF_BIAS, TM_ACC = fwd::TM_ACC,
+                     TM_SP = fwd::TM_SP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
 
-  const uint32_t bar0 = base + OFF_BAR;
+  const uint32_t bar0 = base + fwd::OFF_BAR;
   auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
   auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
-  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
-  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (2 * C_STAGES + M_STAGES + s); };
-  auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + b); };
-  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
-  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
-  const uint32_t BAR_O_FULL = bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2);
-  auto BAR_BIAS_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 3 + s); };
-  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 3 + b); };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + OFF_TMEM_PTR);
+  auto BAR_BIAS_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (3 * C_STAGES + M_STAGES + s); };
+  auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
+  const uint32_t BAR_CH_FULL = bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS);
+  const uint32_t BAR_CH_FREE = BAR_CH_FULL + 8u;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + fwd::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
   const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
   const int half = blockIdx.y;         // which 128 of the 256 output columns (SYM: 80 + 64 of 144)
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair
@@ -372,11 +407,12 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   // rows of the B tile this CTA holds per 32-centroid atom (a pair splits N between its CTAs)
   constexpr int ROWS_BOX = (SYM ? SYM_H0 : NHALF) / (PAIR ? 2 : 1);
   constexpr uint32_t ATOM_BYTES = ROWS_BOX * 128;
-  constexpr uint32_t TILE_BYTES = 2 * ATOM_BYTES;                             // bytes TMA delivers per stage per CTA
+  constexpr uint32_t TILE_BYTES = 2 * ATOM_BYTES;        // bytes TMA delivers per stage per CTA
   constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
   const int row_cta = col_base + (PAIR ? (int)rank * (ncols / 2) : 0);
   const uint32_t idesc_g2 = make_idesc(PAIR ? 256 : 128, ncols);
   constexpr int NPAIR = PAIR ? 2 : 1;
+  const int num_chunks = (num_blocks + chunk_blocks - 1) / chunk_blocks;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) {
@@ -384,8 +420,8 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
     for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FREE(b), 8 * NPAIR); mbar_init(BAR_CH_FULL(b), 1); }
-    mbar_init(BAR_O_FULL, 1);
+    mbar_init(BAR_CH_FULL, 1);
+    mbar_init(BAR_CH_FREE, 4 * NPAIR);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mt_hi) : "memory");
@@ -394,134 +430,121 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   if (warp == 1) {
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
-                   ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+                   ::"r"(base + fwd::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                   ::"r"(base + OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+                   ::"r"(base + fwd::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
 
-  // exp-thread identity: TMEM lane quarter = warp % 4, point = quarter*32 + lane, group = even/odd blocks
+  // row identity of the exp / fold threads: TMEM lane quarter = warp % 4, point = quarter*32 + lane
   const int quarter = warp & 3;
   const int prow = quarter * 32 + lane;
-  const int grp = (warp >= 6) ? 1 : 0;
   float zb = 0.f;
-  if (warp >= 2) {
-    // both groups need zb; group A also writes the operand tiles
-    if (grp == 0) {
-      zb = write_z_tiles(gbase, z, row0 + prow, n, prow, alpha);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
-    } else {
-      const int64_t r = row0 + prow;
-      float nrm = 0.f;
-      if (r < n) {
-        const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+  if (wg == 1) {          // exp group A writes the GEMM1 operand tiles
+    zb = write_z_tiles(gbase, z, row0 + prow, n, prow, alpha);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
+  } else if (wg == 2) {
+    const int64_t r = row0 + prow;
+    float nrm = 0.f;
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 v = __ldg(src + q);
-          nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
-        }
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
       }
-      zb = -nrm * alpha;
     }
+    zb = -nrm * alpha;
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers initialised in BOTH CTAs before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
-    // =========================================================== TMA producer (warp-converged)
-    // In a pair every CTA fetches only ITS half of each B tile (rows row_cta.. of the table slice,
-    // 32 of the 64 centroid rows); all transaction bytes complete on the leader's FULL barrier.
-    auto load_m = [&](int jm) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int it = 2 * jm + h, ms = it % M_STAGES;
-        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
-        TRACE(0, jm, 1 + h);
-        if (elect_one()) {
-          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
-          const CUtensorMap* map = (h == 0) ? &tm_mt_hi : &tm_mt_lo;
-          const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
-          if (PAIR) {
-            tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
-            tma_load_2d_pair(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
-          } else {
-            tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
-            tma_load_2d(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
-          }
-        }
-        __syncwarp();
-      }
-    };
-    for (int j = 0; j < num_blocks; ++j) {
-      const int cs = j % C_STAGES;
-      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
-      TRACE(0, j, 0);
-      if (elect_one()) {
-        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
-        const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
-        if (PAIR) {           // 32 of the 64 centroid rows per CTA (box = 32 rows)
-          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
-        } else {
-          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
-          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
-        }
-        mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
-        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
-      }
-      __syncwarp();
-      // the M tiles trail the centroid tiles by two super-blocks, like GEMM2 trails GEMM1
-      if (j >= 2) load_m(j - 2);
-    }
-    for (int jm = (num_blocks >= 2 ? num_blocks - 2 : 0); jm < num_blocks; ++jm) load_m(jm);
-  } else if (warp == 1) {
-    // =========================================================== MMA issuer (warp-converged; pair: leader only)
-    if (leader) {
-      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
-      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
 #define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
-      // GEMM1 for super-block j; `waited` = its C_FULL wait already happened
-      auto gemm1 = [&](int j, bool waited) {
+
+  if (wg == 0) {
+    reg_dec<40>();
+    if (warp == 0) {
+      // =========================================================== TMA producer (warp-converged)
+      // In a pair every CTA fetches only ITS half of each B tile; all transaction bytes complete on
+      // the leader's FULL barrier.
+      auto load_m = [&](int jm) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int it = 2 * jm + h, ms = it % M_STAGES;
+          mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+            const CUtensorMap* map = (h == 0) ? &tm_mt_hi : &tm_mt_lo;
+            const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
+            if (PAIR) {
+              tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+              tma_load_2d_pair(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
+            } else {
+              tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+              tma_load_2d(dst + ATOM_BYTES, map, BAR_M_FULL(ms), jm * BK + 32, row_cta);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      for (int j = 0; j < num_blocks; ++j) {
         const int cs = j % C_STAGES;
+        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+          const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
+          if (PAIR) {           // 32 of the 64 centroid rows per CTA (box = 32 rows)
+            tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+          } else {
+            tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+            tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+          }
+          mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+          bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
+        }
+        __syncwarp();
+        // the M tiles trail the centroid tiles like GEMM2 trails GEMM1
+        if (j >= AHEAD) load_m(j - AHEAD);
+      }
+      for (int jm = (num_blocks >= AHEAD ? num_blocks - AHEAD : 0); jm < num_blocks; ++jm) load_m(jm);
+    } else if (warp == 1 && leader) {
+      // =========================================================== MMA issuer (warp-converged; pair: leader only)
+      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+      auto gemm1 = [&](int j, bool waited) {
+        const int cs = j % C_STAGES, sb = j % SP_BUFS;
         if (!waited) mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_gemm1<PAIR>(tmem_base + TM_SP + (j & 1) * 128, a1_desc, a2_desc,
+          issue_gemm1<PAIR>(tmem_base + TM_SP + sb * 128, a1_desc, a2_desc,
                              make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
-          if (PAIR) tc_commit_pair(BAR_S_FULL(j & 1)); else tc_commit(BAR_S_FULL(j & 1));
-          // the C stage is released by the exp warps: their arrival follows S_FULL, i.e. GEMM1's completion
+          COMMIT(BAR_S_FULL(sb));   // the C stage itself is released by the exp warps (after S_FULL)
         }
         __syncwarp();
       };
       auto wait_m = [&](int it) { mbar_wait(BAR_M_FULL(it % M_STAGES), (it / M_STAGES) & 1); };
-      long long pw_g1 = 0, pw_w = 0, pw_p = 0, pw_issue = 0, pw_wc = 0, pw_wf = 0;
-      (void)pw_g1; (void)pw_w; (void)pw_p; (void)pw_issue; (void)pw_wc; (void)pw_wf;
-      gemm1(0, false);
-      if (num_blocks > 1) gemm1(1, false);
+      for (int j = 0; j < AHEAD && j < num_blocks; ++j) gemm1(j, false);
       wait_m(0);
       wait_m(1);
       mbar_wait(BAR_P_FULL(0), 0);
-#ifdef RLVAE_TC_PROFILE
-      const long long loop_t0 = clock64();
-#endif
-      // Every wait below is for something that is (normally) long complete; each is placed behind
-      // a group of 8 queued MMAs so that its ~60-90 cycle latency never drains the tensor pipe.
+      // Every wait below is for something that is normally long complete; each sits behind a
+      // group of 8 queued MMAs so that its latency never drains the tensor pipe.
       for (int j = 0; j < num_blocks; ++j) {
-        PROF_T0();
-        TRACE(1, j, 0);
-        const int chunk = j / CHUNK_BLOCKS;
-        const int first = (j % CHUNK_BLOCKS) == 0;   // a new chunk overwrites its accumulator
-        const int sb = j & 1;
+        const int chunk = j / chunk_blocks;
+        const int first = (j % chunk_blocks) == 0;     // a new chunk overwrites the accumulator ...
+        if (first && chunk >= 1) mbar_wait(BAR_CH_FREE, (chunk - 1) & 1);   // ... once the fold group has drained it
         tc_fence_after();
+        const int sb = j % SP_BUFS;
         const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
         const uint32_t p_hi = tmem_base + TM_SP + sb * 128;
         const uint32_t p_lo = p_hi + 64;
-        const uint32_t acc = tmem_base + TM_CH + (chunk & 1) * 128;
+        const uint32_t acc = tmem_base + TM_ACC;
         const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
         const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
         // K index kk = 8 centroids; atom = kk / 4 (ATOM_BYTES apart)
@@ -531,14 +554,8 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             MMA_TS(acc, p_hi + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, !(first && kk == 0));
         }
         __syncwarp();
-        PROF_ADD(pw_issue);
-        TRACE(1, j, 1);
         if (j + 1 < num_blocks) wait_m(2 * j + 2);
-        PROF_ADD(pw_w);
-        TRACE(1, j, 2);
-        if (j + 2 < num_blocks) mbar_wait(BAR_C_FULL((j + 2) % C_STAGES), ((j + 2) / C_STAGES) & 1);
-        PROF_ADD(pw_wc);
-        TRACE(1, j, 3);
+        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((j + AHEAD) % C_STAGES), ((j + AHEAD) / C_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
@@ -546,96 +563,34 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           COMMIT(BAR_M_EMPTY(ms_hi));
         }
         __syncwarp();
-        PROF_ADD(pw_issue);
-        TRACE(1, j, 4);
-        if (j + 1 < num_blocks) {
-          wait_m(2 * j + 3);
-          PROF_ADD(pw_w);
-          TRACE(1, j, 5);
-          const int nchunk = (j + 1) / CHUNK_BLOCKS;   // chunk buffer of the next super-block
-          if (((j + 1) % CHUNK_BLOCKS) == 0 && nchunk >= 2)   // both exp groups folded chunk-2
-            mbar_wait(BAR_CH_FREE(nchunk & 1), ((nchunk >> 1) - 1) & 1);
-        }
-        PROF_ADD(pw_wf);
+        if (j + 1 < num_blocks) wait_m(2 * j + 3);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             MMA_TS(acc, p_hi + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), idesc_g2, 1);
           COMMIT(BAR_M_EMPTY(ms_lo));
-          if ((j % CHUNK_BLOCKS) == CHUNK_BLOCKS - 1 || j == num_blocks - 1)
-            COMMIT(BAR_CH_FULL(chunk & 1));          // chunk complete: the exp groups may fold it
+          if ((j % chunk_blocks) == chunk_blocks - 1 || j == num_blocks - 1)
+            COMMIT(BAR_CH_FULL);                      // chunk complete: hand the accumulator to the fold group
         }
         __syncwarp();
-        PROF_ADD(pw_issue);
-        // GEMM1 two super-blocks ahead re-uses this S/P buffer: ordered behind GEMM2(j) in the pipe
-        TRACE(1, j, 6);
-        if (j + 2 < num_blocks) gemm1(j + 2, true);
-        PROF_ADD(pw_g1);
-        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) & 1), ((j + 1) >> 1) & 1);
-        PROF_ADD(pw_p);
-        TRACE(1, j, 7);
+        // GEMM1 AHEAD super-blocks ahead re-uses this S/P buffer: ordered behind GEMM2(j) in the pipe,
+        // and keeps the pipe busy while the fold group drains the accumulator at a chunk boundary
+        if (j + AHEAD < num_blocks) gemm1(j + AHEAD, true);
+        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) % SP_BUFS), ((j + 1) / SP_BUFS) & 1);
       }
-      if (elect_one()) COMMIT(BAR_O_FULL);
-      __syncwarp();
-#ifdef RLVAE_TC_PROFILE
-      if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-        printf("[tc prof] MMA warp per super-block: total %lld | gemm1 issue %lld  wait M %lld  wait C %lld  wait CH_FREE %lld  p_full %lld  gemm2 issue %lld\n",
-               (clock64() - loop_t0) / num_blocks, pw_g1 / num_blocks, pw_w / num_blocks, pw_wc / num_blocks,
-               pw_wf / num_blocks, pw_p / num_blocks, pw_issue / num_blocks);
-#endif
     }
-  } else {
+  } else if (wg == 1 || wg == 2) {
     // =========================================================== exp groups (one thread per point)
+    reg_dec<112>();
+    const int grp = wg - 1;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float two_alpha = 2.f * alpha;
-    // running total: FOLD columns of this row per thread (dense 2x64 = 128, packed 2x48 >= 80)
-    constexpr int FOLD = SYM ? SYM_FOLD : 64;
-    float omain[FOLD];
-#pragma unroll
-    for (int i = 0; i < FOLD; ++i) omain[i] = 0.f;
-    // fold chunk c (finished on the tensor core) into the running total with RN fp32 adds
-    auto fold_chunk = [&](int c, bool signal) {
-      const uint32_t src = tmem_base + lane_addr + TM_CH + (c & 1) * 128 + grp * FOLD;
-      {
-        uint32_t a[32];
-        TMEM_LD32(src, a);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) omain[i] += __uint_as_float(a[i]);
-      }
-      if (SYM) {     // columns 32..47 of this group's range (beyond ncols: never-written TMEM, unused)
-        uint32_t a[16];
-        TMEM_LD16(src + 32, a);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) omain[32 + i] += __uint_as_float(a[i]);
-      } else {
-        uint32_t a[32];
-        TMEM_LD32(src + 32, a);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) omain[32 + i] += __uint_as_float(a[i]);
-      }
-      if (signal) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
-      }
-    };
-    int folded = 0;                         // chunks already folded by this group
-    const int num_chunks_total = (num_blocks + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
-    long long pe_wait = 0, pe_work = 0, pe_fold = 0;
-    (void)pe_wait; (void)pe_work; (void)pe_fold;
     for (int j = grp; j < num_blocks; j += 2) {
-      PROF_T0();
-      const int cs = j % C_STAGES;
-      const uint32_t sp = tmem_base + lane_addr + TM_SP + (j & 1) * 128;
-      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 0);
+      const int cs = j % C_STAGES, sb = j % SP_BUFS;
+      const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 128;
       mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);   // bias bytes visible to this thread
-      mbar_wait(BAR_S_FULL(j & 1), (j >> 1) & 1);
+      mbar_wait(BAR_S_FULL(sb), (j / SP_BUFS) & 1);
       tc_fence_after();
-      PROF_ADD(pe_wait);
-      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 1);
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t s[32], l[32];
@@ -662,51 +617,63 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_leader(BAR_P_FULL(j & 1)); else mbar_arrive(BAR_P_FULL(j & 1));
+        if (PAIR) mbar_arrive_leader(BAR_P_FULL(sb)); else mbar_arrive(BAR_P_FULL(sb));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
-      PROF_ADD(pe_work);
-      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 2);
-      // Fold every chunk whose last super-block is <= j as soon as the tensor core has finished it
-      // (CH_FULL); CH_FREE then tells the MMA warp that both groups have drained that buffer.  The
-      // wait costs nothing useful: this group's next S tile is only issued after GEMM2(j) anyway.
-      while (folded < num_chunks_total && min((folded + 1) * CHUNK_BLOCKS - 1, num_blocks - 1) <= j) {
-        mbar_wait(BAR_CH_FULL(folded & 1), (folded >> 1) & 1);
-        tc_fence_after();
-        fold_chunk(folded, true);
-        ++folded;
-      }
-      PROF_ADD(pe_fold);
-      if (warp == 2 || warp == 6) TRACE(2 + grp, j, 3);
     }
-#ifdef RLVAE_TC_PROFILE
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64)
-      printf("[tc prof] exp group A per own block: wait %lld  work %lld  fold %lld\n",
-             pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2), pe_fold / (num_blocks / 2));
-#endif
-    // ---------------------------------------------------------- epilogue
-    mbar_wait(BAR_O_FULL, 0);
-    tc_fence_after();
-    while (folded < num_chunks_total) { fold_chunk(folded, false); ++folded; }
+  } else {
+    // =========================================================== fold group: fp32 running total + output
+    reg_inc<232>();
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    constexpr int NTOT = SYM ? SYM_H0 : NHALF;          // columns kept per row (80 packed / 128 dense)
+    float total[NTOT];
+#pragma unroll
+    for (int i = 0; i < NTOT; ++i) total[i] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      mbar_wait(BAR_CH_FULL, c & 1);
+      tc_fence_after();
+      const uint32_t src = tmem_base + lane_addr + TM_ACC;
+#pragma unroll
+      for (int cb = 0; cb < NTOT / 32; ++cb) {
+        uint32_t a[32];
+        TMEM_LD32(src + cb * 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) total[cb * 32 + i] += __uint_as_float(a[i]);
+      }
+      if (SYM) {      // columns 64..79 (half 1 only fills 64: the rest is never-written TMEM, never stored)
+        uint32_t a[16];
+        TMEM_LD16(src + 64, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) total[64 + i] += __uint_as_float(a[i]);
+      }
+      if (c + 1 < num_chunks) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE); else mbar_arrive(BAR_CH_FREE); }
+      }
+    }
+    // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
     float* stage = reinterpret_cast<float*>(gbase + OFF_M);
-    const int t = threadIdx.x - 64;
+    const int t = threadIdx.x - 384;
     const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
     if (!SYM) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
+      for (int q = 0; q < NHALF / 4; ++q) {
         float4 o;
         float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int col = half * NHALF + grp * 64 + q * 4 + e;
-          op[e] = omain[q * 4 + e] + ((col % 17 == 0) ? lambda : 0.f);
+          const int col = half * NHALF + q * 4 + e;
+          op[e] = total[q * 4 + e] + ((col % 17 == 0) ? lambda : 0.f);
         }
-        *reinterpret_cast<float4*>(stage + prow * OUT_LD + grp * 64 + q * 4) = o;
+        *reinterpret_cast<float4*>(stage + prow * OUT_LD + q * 4) = o;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight exp warps only
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four fold warps only
       float* dst = out + row0 * NCOL + half * NHALF;
 #pragma unroll 4
-      for (int i = t; i < TILE_M * (NHALF / 4); i += 256) {
+      for (int i = t; i < TILE_M * (NHALF / 4); i += 128) {
         const int r = i >> 5, c4 = i & 31;
         if (r < rows_here)
           *reinterpret_cast<float4*>(dst + (int64_t)r * NCOL + c4 * 4) =
@@ -715,24 +682,23 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     } else {
       // packed output [N, 144]: this CTA owns packed columns [col_base, col_base + ncols)
 #pragma unroll
-      for (int q = 0; q < SYM_FOLD / 4; ++q) {
+      for (int q = 0; q < SYM_H0 / 4; ++q) {
         float4 o;
         float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int pc = col_base + grp * SYM_FOLD + q * 4 + e;      // packed index
-          // diagonal entries of the packed upper triangle: p(i,i) = 16 i - i (i-1)/2
-          bool diag = false;
+          const int pc = col_base + q * 4 + e;      // packed index
+          bool diag = false;                        // p(i,i) = 16 i - i (i-1)/2
 #pragma unroll
           for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
-          op[e] = omain[q * 4 + e] + (diag ? lambda : 0.f);
+          op[e] = total[q * 4 + e] + (diag ? lambda : 0.f);
         }
-        *reinterpret_cast<float4*>(stage + prow * SYM_OUT_LD + grp * SYM_FOLD + q * 4) = o;
+        *reinterpret_cast<float4*>(stage + prow * SYM_OUT_LD + q * 4) = o;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = out + row0 * SYM_COLS + col_base;
       const int c4n = ncols / 4;                                      // 20 or 16 float4 per row
-      for (int i = t; i < TILE_M * c4n; i += 256) {
+      for (int i = t; i < TILE_M * c4n; i += 128) {
         const int r = i / c4n, c4 = i - r * c4n;
         if (r < rows_here)
           *reinterpret_cast<float4*>(dst + (int64_t)r * SYM_COLS + c4 * 4) =
@@ -740,24 +706,10 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
     }
   }
-
 #undef MMA_TS
 #undef COMMIT
+
   tc_fence_before();
-#ifdef RLVAE_TC_PROFILE
-  __syncthreads();
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-    const long long t0 = g_trace[1][0][0];
-    for (int jj = 0; jj < 8; ++jj) {
-      printf("[trace j=%d] prod: C %lld Mhi(j) %lld Mlo(j) %lld | mma: start %lld g1done %lld wMhi %lld wC %lld g2 %lld wMlo %lld g3 %lld pfull %lld | expA/B: top %lld S %lld P %lld fold %lld\n",
-             40 + jj, g_trace[0][jj][0] - t0, g_trace[0][jj][1] - t0, g_trace[0][jj][2] - t0,
-             g_trace[1][jj][0] - t0, g_trace[1][jj][1] - t0, g_trace[1][jj][2] - t0, g_trace[1][jj][3] - t0,
-             g_trace[1][jj][4] - t0, g_trace[1][jj][5] - t0, g_trace[1][jj][6] - t0, g_trace[1][jj][7] - t0,
-             g_trace[2 + (jj & 1)][jj][0] - t0, g_trace[2 + (jj & 1)][jj][1] - t0, g_trace[2 + (jj & 1)][jj][2] - t0,
-             g_trace[2 + (jj & 1)][jj][3] - t0);
-    }
-  }
-#endif
   if (PAIR) cluster_sync_all(); else __syncthreads();   // no CTA of a pair exits while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
@@ -767,7 +719,6 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
-
 
 // ==========================================================================================
 // Gradient / backward kernel:  out[n,:] += scale * sum_k w_nk <U_n, M_k> (c_k - z_n)
@@ -1135,15 +1086,16 @@ static int launch_fwd(const CUtensorMap& c, const CUtensorMap& hi, const CUtenso
   auto kern = tc::inverse_metric_tc_kernel<SYM, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::fwd::SMEM_BYTES));
     attr_set = true;
   }
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;               // clusters of two point tiles
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles, 2, 1);
-  cfg.blockDim = dim3(tc::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.blockDim = dim3(tc::fwd::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::fwd::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1156,7 +1108,13 @@ static int launch_fwd(const CUtensorMap& c, const CUtensorMap& hi, const CUtenso
   const float* cbias = t->cbias;
   const int nb = t->Kpad / tc::BK;
   const float lambda = t->lambda;
-  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, cbias, n, nb, alpha, lambda, out));
+  static int chunk_blocks = 0;       // super-blocks per tensor-core accumulation chunk (RLVAE_TC_CHUNK)
+  if (chunk_blocks == 0) {
+    const char* e = getenv("RLVAE_TC_CHUNK");
+    chunk_blocks = (e != nullptr && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : tc::CHUNK_BLOCKS;
+  }
+  const int cb = chunk_blocks;
+  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, cbias, n, nb, cb, alpha, lambda, out));
   return 0;
 }
 
