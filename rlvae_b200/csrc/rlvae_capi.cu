@@ -93,6 +93,26 @@ __global__ void pack_sym_kernel(const float* __restrict__ M, int Kpad, float* __
   }
 }
 
+// packed natural layout [Kpad, 160] for the gradient kernel (row = centroid, 136 packed columns + 0s)
+__global__ void pack_sym_nat_kernel(const float* __restrict__ M, int Kpad, float* __restrict__ hi_n,
+                                    float* __restrict__ lo_n) {
+  const int64_t total = (int64_t)Kpad * kSymNatCols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / kSymNatCols), p = (int)(idx - (int64_t)k * kSymNatCols);
+    float v = 0.f;
+    if (p < 136) {
+      int i = 0, base = 0;
+      while (p >= base + (16 - i)) { base += 16 - i; ++i; }
+      const int j = i + (p - base);
+      v = M[(int64_t)k * 256 + i * 16 + j];
+    }
+    const float hi = tf32_hi(v);
+    hi_n[idx] = hi;
+    lo_n[idx] = v - hi;
+  }
+}
+
 __global__ void symmetry_kernel(const float* __restrict__ m_in, int K, int d, int* __restrict__ asym) {
   const int64_t total = (int64_t)K * d * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -116,7 +136,7 @@ static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
 static void free_tables(rlvae_tables* t) {
   pythae_cache_release(t);
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
-                    &t->Mn_hi, &t->Mn_lo, &t->caug, &t->Mts_hi, &t->Mts_lo};
+                    &t->Mn_hi, &t->Mn_lo, &t->caug, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -216,11 +236,15 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     if (t->symmetric) {   // 136 instead of 256 accumulated columns
       cudaError_t e1 = cudaMalloc(&t->Mts_hi, sizeof(float) * (size_t)kSymCols * Kpad);
       cudaError_t e2 = cudaMalloc(&t->Mts_lo, sizeof(float) * (size_t)kSymCols * Kpad);
+      if (e1 == cudaSuccess) e1 = cudaMalloc(&t->Mns_hi, sizeof(float) * (size_t)kSymNatCols * Kpad);
+      if (e2 == cudaSuccess) e2 = cudaMalloc(&t->Mns_lo, sizeof(float) * (size_t)kSymNatCols * Kpad);
       if (e1 != cudaSuccess || e2 != cudaSuccess) {
         set_error("tables_create: cudaMalloc (packed tables) failed");
         return fail(1);
       }
       pack_sym_kernel<<<592, 256, 0, s>>>(t->M, Kpad, t->Mts_hi, t->Mts_lo);
+      OK_OR_FAIL(cudaGetLastError());
+      pack_sym_nat_kernel<<<592, 256, 0, s>>>(t->M, Kpad, t->Mns_hi, t->Mns_lo);
       OK_OR_FAIL(cudaGetLastError());
       OK_OR_FAIL(cudaStreamSynchronize(s));
       rc = tc_build_sym_descriptors(t);

@@ -58,9 +58,12 @@ struct rlvae_tables {
   // symmetric tables only: packed upper triangle (136 -> 144 rows), transposed, hi/lo
   float* Mts_hi = nullptr;  // [144, Kpad]
   float* Mts_lo = nullptr;  // [144, Kpad]
+  float* Mns_hi = nullptr;  // [Kpad, 160] packed natural (gradient kernel B operand)
+  float* Mns_lo = nullptr;  // [Kpad, 160]
   CUtensorMap tm_cstack, tm_mt_hi, tm_mt_lo, tm_mn_hi, tm_mn_lo, tm_mts_hi, tm_mts_lo;
   // CTA-pair variants: each CTA of a pair fetches half of the B-tile rows (smaller boxes)
   CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
+  CUtensorMap tm_mn2_hi, tm_mn2_lo, tm_mns_hi, tm_mns_lo, tm_mns2_hi, tm_mns2_lo;
 };
 
 namespace rlvae {
@@ -79,6 +82,7 @@ int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv
                                     float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s);
 constexpr int kSymCols = 144;
+constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
                       int32_t* status, cudaStream_t s);
 int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist,

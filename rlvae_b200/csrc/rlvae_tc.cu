@@ -197,6 +197,12 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                                 int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {       // arrives on both CTAs' barrier
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -248,6 +254,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
         "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),      \
         "=r"(r[14]), "=r"(r[15])                                                                     \
       : "r"(taddr) : "memory")
+#define TMEM_ST8(taddr, r)                                                                           \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"               \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), \
+                 "r"(r[7]) : "memory")
 #define TMEM_ST32(taddr, r)                                                                          \
   asm volatile(                                                                                      \
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                \
@@ -727,12 +737,17 @@ inverse_metric_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 //
 // Same skeleton as the forward kernel.  Per 64-centroid super-block the tensor core produces
 //   S[128 x 64] = Z.C^T                      (GEMM1, as in the forward kernel)
-//   T[128 x 64] = U_hi.Mhi^T + U_lo.Mhi^T + U_hi.Mlo^T      (3xTF32, 48 MMAs of N = 64, K = 8)
-// with U (this CTA's 128 of the 256 (i,j) columns, hi/lo split) resident in TMEM as the A operand
-// and the natural-layout table tile [64 centroids x 128] as the K-major B operand.  The exp groups
-// then form w = exp2(..), u = w*t and accumulate g += u*c_k, su += u in fp32 registers; the two
-// column halves (blockIdx.y) add their partial results into `out` (zeroed by the launcher).
-// T is re-started every super-block, so the accumulator-truncation drift is bounded by 48 MMAs.
+//   T[128 x 64] = U_hi.Mhi^T + U_lo.Mhi^T + U_hi.Mlo^T      (3xTF32, N = 64, K = 8 per MMA)
+// with U (this CTA's share of the (i,j) columns, hi/lo split) resident in TMEM as the A operand
+// and the natural-layout table tile [64 centroids x cols] as the K-major B operand.  The exp groups
+// then form w = exp2(..), u = w*t and accumulate g += u*c_k, su += u in fp32 registers (packed
+// fma.rn.f32x2); the two column halves (blockIdx.y) add their partial results into `out` (zeroed by
+// the launcher; exactly two addends per element).  T is re-started every super-block, so the
+// accumulator-truncation drift is bounded by <= 51 MMAs.
+//   SYM : symmetric tables contract only the 136 packed columns: <U,M> = sum_{i<=j} Ut_p M_p with
+//         Ut_p = U_ij + U_ji (i<j), U_ii -- valid for ANY U.  Half 0 takes packed columns [0,72),
+//         half 1 [72,136) (9 / 8 K-steps instead of 16).
+//   PAIR: CTA pair (cta_group::2): each CTA supplies 32 of the 64 centroid rows of every B tile.
 // TMEM columns: [0,128) U_hi, [128,256) U_lo, [256,512) two (S 64 | T 64) buffers.
 // ==========================================================================================
 namespace grad {
@@ -741,7 +756,7 @@ constexpr int M_STAGES = 4;
 constexpr uint32_t C_TILE_BYTES = BK * 128;        // [hi|lo] rows for GEMM1
 constexpr uint32_t CN_BYTES = BK * 64;             // natural fp32 centroid rows for the FMA stage
 constexpr uint32_t BIAS_BYTES = BK * 4;
-constexpr uint32_t M_ATOM_BYTES = BK * 128;        // 64 centroid rows x 32 fp32
+constexpr uint32_t M_ATOM_BYTES = BK * 128;        // 64 centroid rows x 32 fp32 (pair: 32 rows used)
 constexpr uint32_t M_TILE_BYTES = 4 * M_ATOM_BYTES;
 constexpr uint32_t OFF_A1 = 0;
 constexpr uint32_t OFF_A2 = OFF_A1 + A_BYTES;
@@ -750,15 +765,22 @@ constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_CN = OFF_M + M_STAGES * M_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_CN + C_STAGES * CN_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
-constexpr int NUM_BARS = 2 * C_STAGES + 2 * M_STAGES + 4;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 4;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 constexpr int RED_LD = 20;                          // group-B partials staged in the M ring
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 128, TM_ST = 256;   // ST + buf*128 : S (64) | T (64)
-constexpr uint32_t IDESC_T = make_idesc(128, BK);
+constexpr int SYM_SPLIT = 72;                       // packed columns of half 0 (9 K-steps); half 1: 64
+constexpr int SYM_NAT_COLS = 160;                   // packed natural row length (5 atoms of 32)
 }  // namespace grad
 
+__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {   // acc += a * b, two lanes
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&acc))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+}
+
+template <bool SYM, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                       const __grid_constant__ CUtensorMap tm_mn_hi,
@@ -771,37 +793,58 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   constexpr uint32_t C_TILE_BYTES = grad::C_TILE_BYTES, CN_BYTES = grad::CN_BYTES,
                      BIAS_BYTES = grad::BIAS_BYTES, M_TILE_BYTES = grad::M_TILE_BYTES,
                      OFF_CN = grad::OFF_CN, TM_UHI = grad::TM_UHI, TM_ULO = grad::TM_ULO,
-                     TM_ST = grad::TM_ST, IDESC_T = grad::IDESC_T;
+                     TM_ST = grad::TM_ST;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar0 = base + grad::OFF_BAR;
   auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
   auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
-  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
-  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (2 * C_STAGES + M_STAGES + s); };
-  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + b); };
-  auto BAR_ST_FREE = [&](int b) { return bar0 + 8u * (2 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  auto BAR_CB_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };   // natural c rows + bias (local)
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (3 * C_STAGES + M_STAGES + s); };
+  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_ST_FREE = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + grad::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
   const int half = blockIdx.y;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  // contraction (K) extent of this half, in 8-column K-steps, and where it starts inside the TMA box
+  const int ksteps = SYM ? (half == 0 ? grad::SYM_SPLIT / 8 : (136 - grad::SYM_SPLIT) / 8) : 16;
+  const int kstep0 = SYM ? (half == 0 ? 0 : (grad::SYM_SPLIT - 64) / 8) : 0;   // half 1 box starts at column 64
+  constexpr int BOX_ATOMS = SYM ? 3 : 4;
+  constexpr uint32_t ROWS_CTA = PAIR ? BK / 2 : BK;                  // centroid rows of a B tile held here
+  constexpr uint32_t ATOM_BYTES = ROWS_CTA * 128;
+  constexpr uint32_t TILE_BYTES = BOX_ATOMS * ATOM_BYTES;
+  constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
+  constexpr uint32_t IDESC_T = make_idesc(PAIR ? 256 : 128, BK);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C_STAGES; ++s) { mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); }
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_CB_FULL(s), 1);
+    }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_ST_FREE(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_ST_FREE(b), 4 * NPAIR); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_lo) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(base + grad::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + grad::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + grad::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();            // TMEM base published before the exp threads store U into it
@@ -819,7 +862,7 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   if (warp >= 2) {
     const int64_t r = row0 + prow;
     if (grp == 0) {
-      zb = write_z_tiles(gbase, z, r, n, prow, alpha);   // uses the forward kernel's A1/A2 offsets
+      zb = write_z_tiles(gbase, z, r, n, prow, alpha);   // A1/A2 offsets are the forward kernel's
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (r < n) {
@@ -833,30 +876,64 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
       if (grp == 1) zb = -nrm * alpha;
     }
-    // this thread's 64 columns of U (hi/lo split) -> TMEM, the A operand of the T GEMM
-    const float* usrc = u + r * NCOL + half * NHALF + grp * 64;
+    // this thread's share of U (hi/lo split) -> TMEM, the A operand of the T GEMM.
+    // dense: 64 of this half's 128 columns; packed: up to 40 of this half's 72 / 64 columns.
+    const float* urow = u + r * NCOL;
+    if (!SYM) {
+      const float* usrc = urow + half * NHALF + grp * 64;
 #pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      uint32_t h[32], l[32];
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t h[32], l[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 v = (r < n) ? __ldg(reinterpret_cast<const float4*>(usrc + cb * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int q = 0; q < 8; ++q) {
+          float4 v = (r < n) ? __ldg(reinterpret_cast<const float4*>(usrc + cb * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float hi = tf32_rna(vv[e]);
-          h[4 * q + e] = __float_as_uint(hi);
-          l[4 * q + e] = __float_as_uint(vv[e] - hi);
+          for (int e = 0; e < 4; ++e) {
+            const float hi = tf32_rna(vv[e]);
+            h[4 * q + e] = __float_as_uint(hi);
+            l[4 * q + e] = __float_as_uint(vv[e] - hi);
+          }
         }
+        TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 64 + cb * 32, h);
+        TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 64 + cb * 32, l);
       }
-      TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 64 + cb * 32, h);
-      TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 64 + cb * 32, l);
+    } else {
+      // packed column p = pbase + grp*40 + i  (i < 40); columns past the half's extent are zero
+      const int pbase = half == 0 ? 0 : grad::SYM_SPLIT;
+      const int pend = half == 0 ? grad::SYM_SPLIT : 136;
+      uint32_t h[32], l[32], h2[8], l2[8];
+      // (i,j) of packed index p by walking the upper-triangle rows
+      int p = pbase + grp * 40;
+      int ri = 0, rb = 0;
+      while (ri < 15 && p >= rb + (16 - ri)) { rb += 16 - ri; ++ri; }
+      int cj = ri + (p - rb);
+#pragma unroll
+      for (int i = 0; i < 40; ++i) {
+        float v = 0.f;
+        if (r < n && p < pend) {
+          v = __ldg(urow + ri * 16 + cj);
+          if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+        }
+        const float hi = tf32_rna(v);
+        if (i < 32) { h[i] = __float_as_uint(hi); l[i] = __float_as_uint(v - hi); }
+        else { h2[i - 32] = __float_as_uint(hi); l2[i - 32] = __float_as_uint(v - hi); }
+        ++p; ++cj;
+        if (cj == 16) { ++ri; cj = ri; }
+      }
+      TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 40, h);
+      TMEM_ST8(tmem_base + lane_addr + TM_UHI + grp * 40 + 32, h2);
+      TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 40, l);
+      TMEM_ST8(tmem_base + lane_addr + TM_ULO + grp * 40 + 32, l2);
     }
     tmem_wait_st();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
   if (warp == 0) {
     // =========================================================== TMA producer (warp-converged)
@@ -864,12 +941,17 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       const int cs = j % C_STAGES;
       mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES + CN_BYTES + BIAS_BYTES);
-        tma_load_2d(base + grad::OFF_C + cs * C_TILE_BYTES, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
-        tma_load_2d(base + grad::OFF_C + cs * C_TILE_BYTES + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0,
-                    j * BK + 32);
-        bulk_load_1d(base + OFF_CN + cs * CN_BYTES, cnat + (int64_t)j * BK * 16, CN_BYTES, BAR_C_FULL(cs));
-        bulk_load_1d(base + grad::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_C_FULL(cs));
+        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+        const uint32_t dst = base + grad::OFF_C + cs * C_TILE_BYTES;
+        if (PAIR) {
+          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+        } else {
+          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+        }
+        mbar_expect_tx(BAR_CB_FULL(cs), CN_BYTES + BIAS_BYTES);
+        bulk_load_1d(base + OFF_CN + cs * CN_BYTES, cnat + (int64_t)j * BK * 16, CN_BYTES, BAR_CB_FULL(cs));
+        bulk_load_1d(base + grad::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_CB_FULL(cs));
       }
       __syncwarp();
 #pragma unroll
@@ -877,61 +959,71 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const int it = 2 * j + h, ms = it % M_STAGES;
         mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(BAR_M_FULL(ms), M_TILE_BYTES);
-          tma_load_3d(base + grad::OFF_M + ms * M_TILE_BYTES, h == 0 ? &tm_mn_hi : &tm_mn_lo, BAR_M_FULL(ms), 0,
-                      j * BK, half * 4);
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+          const CUtensorMap* map = h == 0 ? &tm_mn_hi : &tm_mn_lo;
+          const uint32_t dst = base + grad::OFF_M + ms * M_TILE_BYTES;
+          const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
+          const int atom0 = SYM ? half * 2 : half * 4;
+          if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, atom0);
+          else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, atom0);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (warp-converged)
-    const uint64_t a1_desc = make_desc_sw128(base + grad::OFF_A1);
-    const uint64_t a2_desc = make_desc_sw128(base + grad::OFF_A2);
-    for (int j = 0; j < num_blocks; ++j) {
-      const int cs = j % C_STAGES, sb = j & 1;
-      const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
-      mbar_wait(BAR_ST_FREE(sb), ((j >> 1) & 1) ^ 1);       // exp groups done with super-block j-2
-      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
-      mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
-      tc_fence_after();
-      const uint32_t s_t = tmem_base + TM_ST + sb * 128;
-      const uint32_t t_t = s_t + 64;
-      const uint64_t bh = make_desc_sw128(base + grad::OFF_M + ms_hi * M_TILE_BYTES);
-      const uint64_t bl = make_desc_sw128(base + grad::OFF_M + ms_lo * M_TILE_BYTES);
-      if (elect_one()) {
-        issue_gemm1(s_t, a1_desc, a2_desc, make_desc_sw128(base + grad::OFF_C + cs * C_TILE_BYTES));
-        // K index kk = 8 of this half's 128 (i,j) columns; atom = kk / 4 (8 KB apart = +512)
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          mma_ts(t_t, tmem_base + TM_UHI + 8 * kk, bh + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          mma_ts(t_t, tmem_base + TM_ULO + 8 * kk, bh + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, 1);
-        tc_commit(BAR_M_EMPTY(ms_hi));
+    // =========================================================== MMA issuer (warp-converged; pair: leader only)
+    if (leader) {
+      const uint64_t a1_desc = make_desc_sw128(base + grad::OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + grad::OFF_A2);
+      for (int j = 0; j < num_blocks; ++j) {
+        const int cs = j % C_STAGES, sb = j & 1;
+        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+        mbar_wait(BAR_ST_FREE(sb), ((j >> 1) & 1) ^ 1);       // exp groups done with super-block j-2
+        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t s_t = tmem_base + TM_ST + sb * 128;
+        const uint32_t t_t = s_t + 64;
+        const uint64_t bh = make_desc_sw128(base + grad::OFF_M + ms_hi * M_TILE_BYTES);
+        const uint64_t bl = make_desc_sw128(base + grad::OFF_M + ms_lo * M_TILE_BYTES);
+        if (elect_one()) {
+          issue_gemm1<PAIR>(s_t, a1_desc, a2_desc, make_desc_sw128(base + grad::OFF_C + cs * C_TILE_BYTES));
+          // K-step kk = 8 (i,j) columns; box step s = kstep0 + kk; atom = s / 4 (ATOM_BYTES apart)
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_UHI + 8 * kk, bh + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, kk > 0);
+          }
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_ULO + 8 * kk, bh + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, 1);
+          }
+          COMMIT(BAR_M_EMPTY(ms_hi));
+        }
+        __syncwarp();
+        mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_UHI + 8 * kk, bl + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, 1);
+          }
+          COMMIT(BAR_M_EMPTY(ms_lo));
+          COMMIT(BAR_ST_FULL(sb));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          mma_ts(t_t, tmem_base + TM_UHI + 8 * kk, bl + (kk >> 2) * 512 + 2 * (kk & 3), IDESC_T, 1);
-        tc_commit(BAR_M_EMPTY(ms_lo));
-        tc_commit(BAR_ST_FULL(sb));
-      }
-      __syncwarp();
     }
   } else {
     // =========================================================== exp groups (one thread per point)
     const float two_alpha = 2.f * alpha;
-    float g[16], su = 0.f;
+    float2 g2[8];
+    float su = 0.f;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) g[e] = 0.f;
+    for (int e = 0; e < 8; ++e) g2[e] = make_float2(0.f, 0.f);
     for (int j = grp; j < num_blocks; j += 2) {
       const int cs = j % C_STAGES, sb = j & 1;
       const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
-      mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_CB_FULL(cs), (j / C_STAGES) & 1);
       mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -947,31 +1039,30 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, bias[i] + zb));
           const float uv = w * __uint_as_float(tv[i]);
           su += uv;
+          const float2 uu = make_float2(uv, uv);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 c4 = crow[i * 4 + q];
-            g[4 * q] = fmaf(uv, c4.x, g[4 * q]);
-            g[4 * q + 1] = fmaf(uv, c4.y, g[4 * q + 1]);
-            g[4 * q + 2] = fmaf(uv, c4.z, g[4 * q + 2]);
-            g[4 * q + 3] = fmaf(uv, c4.w, g[4 * q + 3]);
+            ffma2(g2[2 * q], uu, make_float2(c4.x, c4.y));
+            ffma2(g2[2 * q + 1], uu, make_float2(c4.z, c4.w));
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR_ST_FREE(sb));
+        if (PAIR) mbar_arrive_leader(BAR_ST_FREE(sb)); else mbar_arrive(BAR_ST_FREE(sb));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
     }
     // ---------------------------------------------------------- combine the two groups, then the halves
-    // All TMA/MMA traffic of this CTA is complete once both groups have consumed their last
-    // super-block, so the M ring can be reused as scratch.
+    // Every TMA / MMA of this CTA has been consumed once both groups leave their loops, so the M
+    // ring can be reused as scratch.  (In a pair the peer may still be streaming into ITS smem only.)
     asm volatile("bar.sync 1, 256;" ::: "memory");
     float* red = reinterpret_cast<float*>(gbase + grad::OFF_M);
     if (grp == 1) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) red[prow * RED_LD + e] = g[e];
+      for (int e = 0; e < 8; ++e) { red[prow * RED_LD + 2 * e] = g2[e].x; red[prow * RED_LD + 2 * e + 1] = g2[e].y; }
       red[prow * RED_LD + 16] = su;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -981,18 +1072,23 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (r < n) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float ge = g[e] + red[prow * RED_LD + e];
+          const float ge = ((e & 1) ? g2[e >> 1].y : g2[e >> 1].x) + red[prow * RED_LD + e];
           atomicAdd(out + r * 16 + e, scale * (ge - zrow[e] * su));   // exactly two addends per element
         }
       }
     }
   }
+#undef MMA_TS
+#undef COMMIT
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -1021,10 +1117,11 @@ static int make_map_2d(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64
 }
 
 // natural table [Kpad, 256] viewed as [8 column atoms][Kpad][32]: one box = 4 atoms x 64 rows
-static int make_map_atoms(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64_t Kpad) {
-  cuuint64_t dims[3] = {32, Kpad, 8};
-  cuuint64_t strides[2] = {256 * sizeof(float), 32 * sizeof(float)};
-  cuuint32_t box[3] = {32, (cuuint32_t)tc::BK, 4};
+static int make_map_atoms(PFN_encodeTiled enc, CUtensorMap* map, float* ptr, uint64_t Kpad, uint32_t row_len = 256,
+                          uint32_t box_rows = tc::BK, uint32_t box_atoms = 4) {
+  cuuint64_t dims[3] = {32, Kpad, row_len / 32};
+  cuuint64_t strides[2] = {row_len * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, box_atoms};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1051,6 +1148,8 @@ int tc_build_descriptors(rlvae_tables* t) {
   if (int rc = make_map_2d(enc, &t->tm_mt2_lo, t->Mt_lo, Kpad, tc::NCOL, 32, tc::NHALF / 2)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn_hi, t->Mn_hi, Kpad)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn_lo, t->Mn_lo, Kpad)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mn2_hi, t->Mn_hi, Kpad, 256, tc::BK / 2, 4)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mn2_lo, t->Mn_lo, Kpad, 256, tc::BK / 2, 4)) return rc;
   return 0;
 }
 
@@ -1067,6 +1166,11 @@ int tc_build_sym_descriptors(rlvae_tables* t) {
   if (int rc = make_map_2d(enc, &t->tm_mts_lo, t->Mts_lo, Kpad, tc::SYM_COLS, 32, tc::SYM_H0)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_mts2_hi, t->Mts_hi, Kpad, tc::SYM_COLS, 32, tc::SYM_H0 / 2)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_mts2_lo, t->Mts_lo, Kpad, tc::SYM_COLS, 32, tc::SYM_H0 / 2)) return rc;
+  // packed natural tables [Kpad, 160] of the gradient kernel: boxes of 3 column atoms
+  if (int rc = make_map_atoms(enc, &t->tm_mns_hi, t->Mns_hi, Kpad, kSymNatCols, tc::BK, 3)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mns_lo, t->Mns_lo, Kpad, kSymNatCols, tc::BK, 3)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mns2_hi, t->Mns_hi, Kpad, kSymNatCols, tc::BK / 2, 3)) return rc;
+  if (int rc = make_map_atoms(enc, &t->tm_mns2_lo, t->Mns_lo, Kpad, kSymNatCols, tc::BK / 2, 3)) return rc;
   return 0;
 }
 
@@ -1139,25 +1243,52 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
                      : launch_fwd<false, false>(t->tm_cstack, t->tm_mt_hi, t->tm_mt_lo, t, z, n, ginv, s);
 }
 
+template <bool SYM, bool PAIR>
+static int launch_grad(const CUtensorMap& c, const CUtensorMap& hi, const CUtensorMap& lo, const rlvae_tables* t,
+                       const float* z, const float* u, int64_t n, float scale, float* out, cudaStream_t s) {
+  auto kern = tc::metric_grad_tc_kernel<SYM, PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::grad::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 2, 1);
+  cfg.blockDim = dim3(tc::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::grad::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cnat = t->c;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, u, cnat, cbias, n, nb, alpha, scale, out));
+  return 0;
+}
+
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                           float* out, cudaStream_t s) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0,
                 "tensor path needs 16-byte aligned z and u");
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(tc::metric_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::grad::SMEM_BYTES));
-    attr_set = true;
-  }
   RLVAE_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 16, s));   // the two column halves add
-  const dim3 grid((unsigned)((n + tc::TILE_M - 1) / tc::TILE_M), tc::NCOL / tc::NHALF);
-  const float alpha = 1.4426950408889634f / t->T2;
-  tc::metric_grad_tc_kernel<<<grid, tc::THREADS, tc::grad::SMEM_BYTES, s>>>(
-      t->tm_cstack, t->tm_mn_hi, t->tm_mn_lo, z, u, t->c, t->cbias, n, t->Kpad / tc::BK, alpha, scale, out);
-  RLVAE_CUDA_OK(cudaGetLastError());
-  return 0;
+  const bool sym = t->symmetric && t->Mns_hi != nullptr;
+  if (sym) {
+    return use_pairs() ? launch_grad<true, true>(t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t, z, u, n, scale, out, s)
+                       : launch_grad<true, false>(t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t, z, u, n, scale, out, s);
+  }
+  return use_pairs() ? launch_grad<false, true>(t->tm_cstack, t->tm_mn2_hi, t->tm_mn2_lo, t, z, u, n, scale, out, s)
+                     : launch_grad<false, false>(t->tm_cstack, t->tm_mn_hi, t->tm_mn_lo, t, z, u, n, scale, out, s);
 }
 
 }  // namespace rlvae
