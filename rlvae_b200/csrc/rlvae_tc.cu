@@ -975,12 +975,21 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     if (leader) {
       const uint64_t a1_desc = make_desc_sw128(base + grad::OFF_A1);
       const uint64_t a2_desc = make_desc_sw128(base + grad::OFF_A2);
+      long long gw_free = 0, gw_c = 0, gw_m = 0, gw_issue = 0;
+      (void)gw_free; (void)gw_c; (void)gw_m; (void)gw_issue;
+#ifdef RLVAE_TC_PROFILE
+      const long long gl0 = clock64();
+#endif
       for (int j = 0; j < num_blocks; ++j) {
+        PROF_T0();
         const int cs = j % C_STAGES, sb = j & 1;
         const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
         mbar_wait(BAR_ST_FREE(sb), ((j >> 1) & 1) ^ 1);       // exp groups done with super-block j-2
+        PROF_ADD(gw_free);
         mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        PROF_ADD(gw_c);
         mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+        PROF_ADD(gw_m);
         tc_fence_after();
         const uint32_t s_t = tmem_base + TM_ST + sb * 128;
         const uint32_t t_t = s_t + 64;
@@ -1000,7 +1009,9 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           COMMIT(BAR_M_EMPTY(ms_hi));
         }
         __syncwarp();
+        PROF_ADD(gw_issue);
         mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
+        PROF_ADD(gw_m);
         tc_fence_after();
         if (elect_one()) {
           for (int kk = 0; kk < ksteps; ++kk) {
@@ -1011,7 +1022,14 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           COMMIT(BAR_ST_FULL(sb));
         }
         __syncwarp();
+        PROF_ADD(gw_issue);
       }
+#ifdef RLVAE_TC_PROFILE
+      if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+        printf("[grad prof] MMA warp per super-block: total %lld | wait ST_FREE %lld  wait C %lld  wait M %lld  issue %lld\n",
+               (clock64() - gl0) / num_blocks, gw_free / num_blocks, gw_c / num_blocks, gw_m / num_blocks,
+               gw_issue / num_blocks);
+#endif
     }
   } else {
     // =========================================================== exp groups (one thread per point)
@@ -1020,12 +1038,16 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float su = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) g2[e] = make_float2(0.f, 0.f);
+    long long ge_wait = 0, ge_work = 0;
+    (void)ge_wait; (void)ge_work;
     for (int j = grp; j < num_blocks; j += 2) {
+      PROF_T0();
       const int cs = j % C_STAGES, sb = j & 1;
       const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
       mbar_wait(BAR_CB_FULL(cs), (j / C_STAGES) & 1);
       mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
       tc_fence_after();
+      PROF_ADD(ge_wait);
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t sv[32], tv[32];
@@ -1054,7 +1076,13 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (PAIR) mbar_arrive_leader(BAR_ST_FREE(sb)); else mbar_arrive(BAR_ST_FREE(sb));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
+      PROF_ADD(ge_work);
     }
+#ifdef RLVAE_TC_PROFILE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64)
+      printf("[grad prof] exp group A per own super-block: wait %lld  work %lld\n", ge_wait / (num_blocks / 2),
+             ge_work / (num_blocks / 2));
+#endif
     // ---------------------------------------------------------- combine the two groups, then the halves
     // Every TMA / MMA of this CTA has been consumed once both groups leave their loops, so the M
     // ring can be reused as scratch.  (In a pair the peer may still be streaming into ITS smem only.)
@@ -1073,6 +1101,416 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float ge = ((e & 1) ? g2[e >> 1].y : g2[e >> 1].x) + red[prow * RED_LD + e];
+          atomicAdd(out + r * 16 + e, scale * (ge - zrow[e] * su));   // exactly two addends per element
+        }
+      }
+    }
+  }
+#undef MMA_TS
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ==========================================================================================
+// Gradient kernel for SYMMETRIC tables with the final contraction on the tensor core as well
+// (the FMA contraction of metric_grad_tc_kernel costs ~25 issue slots per (point, centroid) and is
+// SM-issue bound at ~2.7k cycles per super-block; measured).  Per 64-centroid super-block j:
+//   [GEMM1, T-GEMM](j)  ->  S | T in TMEM buffer j&1                     (as in metric_grad_tc_kernel)
+//   exp group           ->  u = exp2(..) * t, split u_hi | u_lo, written over S | T
+//   GEMM3(j)            ->  OUT[128 x 32] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo     (3xTF32, N = 32)
+// where Ct = [c_k (16 rows) ; 1 ; 0 ...] so that OUT[:, :16] = sum_k u c_k and OUT[:, 16] = sum_k u.
+// OUT is accumulated in two alternating 32-column chunk accumulators (2 super-blocks each) that the
+// exp groups fold into fp32 registers -- the same remedy for the accumulator truncation as in the
+// forward kernel.  TMEM: [0,80) U_hi, [80,160) U_lo, [160,416) two (S|u_hi 64, T|u_lo 64) buffers,
+// [416,480) two OUT chunk accumulators.
+// ==========================================================================================
+namespace gsym {
+constexpr int C_STAGES = 3;
+constexpr int M_STAGES = 4;
+constexpr uint32_t C_TILE_BYTES = BK * 128;
+constexpr uint32_t CT_TILE_BYTES = 2 * 32 * 128;   // [32 rows x 64 centroids] = 2 atoms of 4 KB (pair: 2 KB used each)
+constexpr uint32_t BIAS_BYTES = BK * 4;
+constexpr uint32_t M_TILE_BYTES = 3 * BK * 128;    // 3 column atoms x 64 centroid rows
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE_BYTES;            // hi then lo per stage
+constexpr uint32_t OFF_M = OFF_CT + C_STAGES * 2 * CT_TILE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 2 + 2 + 2 + 2 + 1;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TM_UHI = 0, TM_ULO = 80, TM_ST = 160, TM_OUT = 416;
+constexpr int RED_LD = 36;
+}  // namespace gsym
+
+template <bool PAIR>
+__global__ void __launch_bounds__(THREADS, 1)
+metric_grad_sym_kernel(const __grid_constant__ CUtensorMap tm_cstack,
+                       const __grid_constant__ CUtensorMap tm_mn_hi,
+                       const __grid_constant__ CUtensorMap tm_mn_lo,
+                       const __grid_constant__ CUtensorMap tm_ct_hi,
+                       const __grid_constant__ CUtensorMap tm_ct_lo,
+                       const float* __restrict__ z, const float* __restrict__ u,
+                       const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha, float scale,
+                       float* __restrict__ out) {
+  constexpr int C_STAGES = gsym::C_STAGES, M_STAGES = gsym::M_STAGES, RED_LD = gsym::RED_LD;
+  constexpr uint32_t C_TILE_BYTES = gsym::C_TILE_BYTES, CT_TILE_BYTES = gsym::CT_TILE_BYTES,
+                     BIAS_BYTES = gsym::BIAS_BYTES, M_TILE_BYTES = gsym::M_TILE_BYTES, OFF_C = gsym::OFF_C,
+                     OFF_CT = gsym::OFF_CT, OFF_M = gsym::OFF_M, OFF_BIAS = gsym::OFF_BIAS,
+                     TM_UHI = gsym::TM_UHI, TM_ULO = gsym::TM_ULO, TM_ST = gsym::TM_ST, TM_OUT = gsym::TM_OUT;
+  constexpr int CHUNK = 2;             // super-blocks per OUT chunk accumulator
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + gsym::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_B_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };     // bias (local)
+  auto BAR_CT_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_CT_EMPTY = [&](int s) { return bar0 + 8u * (4 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (5 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (5 * C_STAGES + M_STAGES + s); };
+  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_U_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 4 + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 6 + b); };
+  const uint32_t BAR_DONE = bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 8);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + gsym::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const int half = blockIdx.y;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  const int ksteps = half == 0 ? grad::SYM_SPLIT / 8 : (136 - grad::SYM_SPLIT) / 8;    // 9 / 8
+  const int kstep0 = half == 0 ? 0 : (grad::SYM_SPLIT - 64) / 8;                       // box of half 1 starts at column 64
+  constexpr uint32_t ROWS_CTA = PAIR ? BK / 2 : BK;
+  constexpr uint32_t ATOM_BYTES = ROWS_CTA * 128;                   // M tile atom held by this CTA
+  constexpr uint32_t TILE_BYTES = 3 * ATOM_BYTES;
+  constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
+  constexpr uint32_t CT_ROWS = PAIR ? 16 : 32;
+  constexpr uint32_t CT_ATOM_BYTES = CT_ROWS * 128;
+  constexpr uint32_t CT_BYTES = 2 * CT_ATOM_BYTES;                  // per hi / lo tile per CTA
+  constexpr uint32_t CT_ATOM_DESC = CT_ATOM_BYTES >> 4;
+  constexpr uint32_t IDESC_T = make_idesc(PAIR ? 256 : 128, BK);
+  constexpr uint32_t IDESC_3 = make_idesc(PAIR ? 256 : 128, 32);
+  const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_B_FULL(s), 1);
+      mbar_init(BAR_CT_FULL(s), 1); mbar_init(BAR_CT_EMPTY(s), 1);
+    }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), 4 * NPAIR);
+      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
+    }
+    mbar_init(BAR_DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_lo) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + gsym::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + gsym::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();            // TMEM base published before the exp threads store U into it
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  float zb = 0.f;
+  float zrow[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
+  if (warp >= 2) {
+    const int64_t r = row0 + prow;
+    if (grp == 0) {
+      zb = write_z_tiles(gbase, z, r, n, prow, alpha);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+      float nrm = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+      }
+      if (grp == 1) zb = -nrm * alpha;
+    }
+    // packed symmetric U: Ut_p = U_ij + U_ji (i<j), U_ii; this thread converts 40 packed columns
+    const float* urow = u + r * NCOL;
+    const int pbase = half == 0 ? 0 : grad::SYM_SPLIT;
+    const int pend = half == 0 ? grad::SYM_SPLIT : 136;
+    uint32_t h[32], l[32], h2[8], l2[8];
+    int p = pbase + grp * 40;
+    int ri = 0, rb = 0;
+    while (ri < 15 && p >= rb + (16 - ri)) { rb += 16 - ri; ++ri; }
+    int cj = ri + (p - rb);
+#pragma unroll
+    for (int i = 0; i < 40; ++i) {
+      float v = 0.f;
+      if (r < n && p < pend) {
+        v = __ldg(urow + ri * 16 + cj);
+        if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+      }
+      const float hi = tf32_rna(v);
+      if (i < 32) { h[i] = __float_as_uint(hi); l[i] = __float_as_uint(v - hi); }
+      else { h2[i - 32] = __float_as_uint(hi); l2[i - 32] = __float_as_uint(v - hi); }
+      ++p; ++cj;
+      if (cj == 16) { ++ri; cj = ri; }
+    }
+    TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 40, h);
+    TMEM_ST8(tmem_base + lane_addr + TM_UHI + grp * 40 + 32, h2);
+    TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 40, l);
+    TMEM_ST8(tmem_base + lane_addr + TM_ULO + grp * 40 + 32, l2);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (warp-converged)
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+        const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
+        if (PAIR) {
+          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+        } else {
+          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+        }
+        mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
+        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int it = 2 * j + h, ms = it % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+          const CUtensorMap* map = h == 0 ? &tm_mn_hi : &tm_mn_lo;
+          const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
+          const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
+          if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, half * 2);
+          else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, half * 2);
+        }
+        __syncwarp();
+      }
+      // Ct tiles (hi, lo): [32 (pair: 16) rows x 64 centroids] as two 32-centroid atoms each
+      mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
+        const uint32_t dst = base + OFF_CT + cs * 2 * CT_TILE_BYTES;
+        const int row = PAIR ? 16 * (int)rank : 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (PAIR) {
+            tma_load_2d_pair(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d_pair(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          } else {
+            tma_load_2d(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (warp-converged; pair: leader only)
+    if (leader) {
+      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+      // [GEMM1, T-GEMM] of super-block j into S|T buffer j&1
+      auto issue_st = [&](int j) {
+        const int cs = j % C_STAGES, sb = j & 1;
+        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t s_t = tmem_base + TM_ST + sb * 128;
+        const uint32_t t_t = s_t + 64;
+        const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
+        const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
+        if (elect_one()) {
+          issue_gemm1<PAIR>(s_t, a1_desc, a2_desc, make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_UHI + 8 * kk, bh + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, kk > 0);
+          }
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_ULO + 8 * kk, bh + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, 1);
+          }
+          COMMIT(BAR_M_EMPTY(ms_hi));
+        }
+        __syncwarp();
+        mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int st = kstep0 + kk;
+            MMA_TS(t_t, tmem_base + TM_UHI + 8 * kk, bl + (st >> 2) * ATOM_DESC + 2 * (st & 3), IDESC_T, 1);
+          }
+          COMMIT(BAR_M_EMPTY(ms_lo));
+          COMMIT(BAR_ST_FULL(sb));
+        }
+        __syncwarp();
+      };
+      issue_st(0);
+      for (int j = 0; j < num_blocks; ++j) {
+        // S|T(j+1) first: its buffer was released by GEMM3(j-1), already queued ahead in the pipe
+        if (j + 1 < num_blocks) issue_st(j + 1);
+        const int cs = j % C_STAGES, sb = j & 1;
+        const int chunk = j / CHUNK;
+        const int first = (j % CHUNK) == 0;
+        if (first && chunk >= 2) mbar_wait(BAR_CH_FREE(chunk & 1), ((chunk >> 1) - 1) & 1);
+        mbar_wait(BAR_CT_FULL(cs), (j / C_STAGES) & 1);
+        mbar_wait(BAR_U_FULL(sb), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t u_hi = tmem_base + TM_ST + sb * 128;
+        const uint32_t u_lo = u_hi + 64;
+        const uint32_t acc = tmem_base + TM_OUT + (chunk & 1) * 32;
+        const uint64_t ch = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES);
+        const uint64_t cl = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES + CT_TILE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, !(first && kk == 0));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_lo + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, cl + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
+          COMMIT(BAR_CT_EMPTY(cs));
+          if ((j % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(chunk & 1));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) COMMIT(BAR_DONE);
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== exp groups (one thread per point)
+    const float two_alpha = 2.f * alpha;
+    float tot[32];                       // this group's share of OUT: chunks of parity grp
+#pragma unroll
+    for (int e = 0; e < 32; ++e) tot[e] = 0.f;
+    auto fold_chunk = [&](int c, bool signal) {
+      uint32_t a[32];
+      TMEM_LD32(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tot[i] += __uint_as_float(a[i]);
+      if (signal) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
+      }
+    };
+    int next_chunk = grp;                // chunks c with (c & 1) == grp belong to this group
+    for (int j = grp; j < num_blocks; j += 2) {
+      const int cs = j % C_STAGES, sb = j & 1;
+      const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
+      mbar_wait(BAR_B_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t sv[32], tv[32];
+        TMEM_LD32(st + rnd * 32, sv);
+        TMEM_LD32(st + 64 + rnd * 32, tv);
+        const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = bias4[q];
+          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * q + e;
+            const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
+            const float uv = w * __uint_as_float(tv[i]);
+            const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
+            sv[i] = uh;
+            tv[i] = __float_as_uint(uv - __uint_as_float(uh));
+          }
+        }
+        TMEM_ST32(st + rnd * 32, sv);
+        TMEM_ST32(st + 64 + rnd * 32, tv);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+      // fold this group's chunks whose last super-block is <= j-1 (their GEMM3 is queued ahead of
+      // everything this group waits for next, so the wait is short)
+      while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
+        mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
+        tc_fence_after();
+        fold_chunk(next_chunk, true);
+        next_chunk += 2;
+      }
+    }
+    mbar_wait(BAR_DONE, 0);
+    tc_fence_after();
+    while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
+    // ---------------------------------------------------------- combine the two groups, then the halves
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* red = reinterpret_cast<float*>(gbase + OFF_M);
+    if (grp == 1) {
+#pragma unroll
+      for (int e = 0; e < 17; ++e) red[prow * RED_LD + e] = tot[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const int64_t r = row0 + prow;
+      const float su = tot[16] + red[prow * RED_LD + 16];
+      if (r < n) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float ge = tot[e] + red[prow * RED_LD + e];
           atomicAdd(out + r * 16 + e, scale * (ge - zrow[e] * su));   // exactly two addends per element
         }
       }
