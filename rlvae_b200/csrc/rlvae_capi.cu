@@ -22,7 +22,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
 __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int Kpad, int d,
                                       float inv_T2_log2e, float* __restrict__ c, float* __restrict__ cn,
                                       float* __restrict__ cstack, float* __restrict__ cbias,
-                                      float* __restrict__ caug, float* __restrict__ stats) {
+                                      float* __restrict__ ct_hi, float* __restrict__ ct_lo,
+                                      float* __restrict__ stats) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   float nrm = 0.f;
@@ -42,10 +43,12 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
       const float hi = tf32_hi(v);
       cstack[(int64_t)k * 32 + j] = hi;
       cstack[(int64_t)k * 32 + 16 + j] = v - hi;
-      // gradient-pass B operand: row = [hi(c) (16) | lo(c) (16)], same as cstack (kept separate
-      // so either pass can change its layout independently)
-      caug[(int64_t)k * 32 + j] = hi;
-      caug[(int64_t)k * 32 + 16 + j] = v - hi;
+      // B operand of the gradient kernel's final contraction: transposed [32, Kpad] (centroid index
+      // contiguous), rows 0..15 = c, row 16 = 1 (so that the same GEMM also yields sum_k u), rest 0
+      ct_hi[(int64_t)j * Kpad + k] = hi;
+      ct_lo[(int64_t)j * Kpad + k] = v - hi;
+      ct_hi[(int64_t)(16 + j) * Kpad + k] = (j == 0) ? 1.f : 0.f;
+      ct_lo[(int64_t)(16 + j) * Kpad + k] = 0.f;
     }
     cbias[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
   }
@@ -136,7 +139,7 @@ static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
 static void free_tables(rlvae_tables* t) {
   pythae_cache_release(t);
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
-                    &t->Mn_hi, &t->Mn_lo, &t->caug, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
+                    &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -187,7 +190,8 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   ALLOC(t->M, (size_t)Kpad * dd);
   if (tc) {
     ALLOC(t->cstack, (size_t)Kpad * 32);
-    ALLOC(t->caug, (size_t)Kpad * 32);
+    ALLOC(t->ct_hi, (size_t)Kpad * 32);
+    ALLOC(t->ct_lo, (size_t)Kpad * 32);
     ALLOC(t->cbias, Kpad);
     ALLOC(t->Mt_hi, (size_t)Kpad * dd);
     ALLOC(t->Mt_lo, (size_t)Kpad * dd);
@@ -207,7 +211,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   OK_OR_FAIL(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
   const float inv_T2_log2e = 1.4426950408889634f / t->T2;
   pack_centroids_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(centroids, K, Kpad, d, inv_T2_log2e, t->c,
-                                                           t->cn, t->cstack, t->cbias, t->caug, stats);
+                                                           t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, stats);
   OK_OR_FAIL(cudaGetLastError());
   pack_matrices_kernel<<<592, 256, 0, s>>>(matrices, K, Kpad, dd, t->M, t->Mt_hi, t->Mt_lo, t->Mn_hi,
                                            t->Mn_lo);
@@ -329,12 +333,6 @@ static int inverse_metric_internal(const rlvae_tables* t, const float* z, int64_
   return launch_inverse_metric_tc(t, z, n, buf, s);
 }
 
-static int inverse_from(const float* a, int packed, int64_t n, int d, float* inv, float* lad, float* sgn,
-                        float* diag, int transpose, cudaStream_t s) {
-  return packed ? launch_batched_inverse_packed16(a, n, inv, lad, sgn, diag, transpose, s)
-                : launch_batched_inverse(a, n, d, inv, lad, sgn, diag, transpose, s);
-}
-
 int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet, float* sign,
                           float* diag_inv, int flags, void* stream) {
   RLVAE_REQUIRE(n >= 0, "batched_inverse: negative batch");
@@ -391,17 +389,32 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     if (packed) { if (int rc = launch_unpack_sym16(a_buf, n, ginv, s)) return rc; }
     else RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
   }
+  if (packed) {
+    // symmetric tables on the tensor path: G^{-1} arrives packed [N,144]; one per-thread Cholesky
+    // kernel produces packed G and -log|det G^{-1}| = log|det G|, and the gradient kernel contracts
+    // the packed G directly (G^T == G).  The spare tail of a_buf holds the fallback list.
+    float* g_packed = (g != nullptr || grad_logdet_g != nullptr) ? (w + mat) : nullptr;
+    int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
+    if (g_packed != nullptr || logdet_g != nullptr) {
+      if (int rc = launch_sym16_inverse(a_buf, n, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s))
+        return rc;
+    }
+    if (g != nullptr) { if (int rc = launch_unpack_sym16(g_packed, n, g, s)) return rc; }
+    if (grad_logdet_g != nullptr)
+      return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
+    return 0;
+  }
   // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
   // G^T == G up to rounding, otherwise a transposed copy is produced.
   const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
   const bool plain_g = (g != nullptr) || ((grad_logdet_g != nullptr) && t->symmetric);
   if (plain_g || logdet_g != nullptr) {
-    if (int rc = inverse_from(a_buf, packed, n, d, plain_g ? g_buf : nullptr, logdet_g ? lad_buf : nullptr,
-                              nullptr, nullptr, 0, s))
+    if (int rc = launch_batched_inverse(a_buf, n, d, plain_g ? g_buf : nullptr, logdet_g ? lad_buf : nullptr,
+                                        nullptr, nullptr, 0, s))
       return rc;
   }
   if (need_gt) {
-    if (int rc = inverse_from(a_buf, packed, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
+    if (int rc = launch_batched_inverse(a_buf, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
   }
   if (logdet_g != nullptr) {
     // log|det G| = -log|det G^{-1}|
@@ -450,8 +463,15 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   auto eval = [&](const float* zz) -> int {
     int packed = 0;
     if (int rc = inverse_metric_internal(t, zz, n, ginv, path, s, &packed)) return rc;
+    if (packed) {   // per-thread Cholesky on the packed layout; the gradient contracts packed G
+      int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
+      if (int rc = launch_sym16_inverse(ginv, n, exact ? gfull : nullptr, lad, 1.f, sgn, diag, fail_ws, s))
+        return rc;
+      if (exact) return launch_metric_grad_tc(t, zz, gfull, n, 1.f / t->T2, gex, s, 1);
+      return 0;
+    }
     // exact mode wants G^T for the contraction (see rlvae_metric_eval)
-    if (int rc = inverse_from(ginv, packed, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
+    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
       if (int rc = rlvae_metric_grad(t, zz, gfull, n, 1.f / t->T2, gex, path, stream)) return rc;
     return 0;
@@ -488,7 +508,10 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
   for (int i = 0; i < n_steps; ++i) {
     int packed = 0;
     if (int rc = inverse_metric_internal(t, z, n, ginv, path, s, &packed)) return rc;
-    if (int rc = inverse_from(ginv, packed, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
+    if (packed) {
+      int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
+      if (int rc = launch_sym16_inverse(ginv, n, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s)) return rc;
+    } else if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
     if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;
   }
   return 0;

@@ -54,7 +54,8 @@ struct rlvae_tables {
   float* Mt_lo = nullptr;   // [256, Kpad]  M - hi
   float* Mn_hi = nullptr;   // [Kpad, 256]  natural, for the gradient pass
   float* Mn_lo = nullptr;   // [Kpad, 256]
-  float* caug = nullptr;    // [Kpad, 32] (reserved)
+  float* ct_hi = nullptr;   // [32, Kpad]  rows 0..15 tf32_hi(c)^T, row 16 = 1, rest 0 (gradient contraction)
+  float* ct_lo = nullptr;   // [32, Kpad]  rows 0..15 (c - hi)^T, rest 0
   // symmetric tables only: packed upper triangle (136 -> 144 rows), transposed, hi/lo
   float* Mts_hi = nullptr;  // [144, Kpad]
   float* Mts_lo = nullptr;  // [144, Kpad]
@@ -64,6 +65,7 @@ struct rlvae_tables {
   // CTA-pair variants: each CTA of a pair fetches half of the B-tile rows (smaller boxes)
   CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
   CUtensorMap tm_mn2_hi, tm_mn2_lo, tm_mns_hi, tm_mns_lo, tm_mns2_hi, tm_mns2_lo;
+  CUtensorMap tm_ct_hi, tm_ct_lo, tm_ct2_hi, tm_ct2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
 };
 
 namespace rlvae {
@@ -81,6 +83,10 @@ int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* 
 int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv, float* logabsdet,
                                     float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s);
+// d == 16, symmetric packed input: per-thread Cholesky with a pivoting fallback for the matrices that
+// are not positive definite.  fail_ws: 1 + n ints.  logabsdet receives lad_scale * log|det A|.
+int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
+                         float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
@@ -96,8 +102,9 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
 int launch_inverse_metric_tc_sym(const rlvae_tables* t, const float* z, int64_t n, float* packed,
                                  cudaStream_t s);
 int tc_build_sym_descriptors(rlvae_tables* t);
+// u_packed != 0 (symmetric tables only): u is a SYMMETRIC matrix in the packed [N,144] layout
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n,
-                          float scale, float* out, cudaStream_t s);
+                          float scale, float* out, cudaStream_t s, int u_packed = 0);
 
 // HMC elementwise stages (rlvae_hmc.cu)
 struct HmcBeginArgs;

@@ -35,20 +35,27 @@ __host__ __device__ constexpr int sym16_index(int i, int j) {   // packed upper 
 }
 
 // PACKED (D == 16 only): the input is the symmetric packed layout [N, 144] of the tensor kernel
+// `list` / `count` (optional): process only the matrices list[0 .. *count) -- the fallback pass behind
+// sym16_cholesky_kernel -- with a grid-stride loop; otherwise matrix = blockIdx.x * MATS + group.
+// `packed_out` (PACKED only): the inverse in the packed symmetric layout (upper triangle).
 template <int D, bool PACKED = false>
 __global__ void __launch_bounds__(PP<D>::THREADS)
 batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv,
                        float* __restrict__ logabsdet, float* __restrict__ sign,
-                       float* __restrict__ diag_inv, int transpose_inv) {
+                       float* __restrict__ diag_inv, int transpose_inv,
+                       const int* __restrict__ list = nullptr, const int* __restrict__ count = nullptr,
+                       float* __restrict__ packed_out = nullptr, float lad_scale = 1.f) {
   using P = PP<D>;
   constexpr int LANES = P::LANES, RPL = P::RPL, LD = P::LD;
   __shared__ float stage[P::MATS * D * LD];
 
   const int lane = threadIdx.x % LANES;
   const int grp = threadIdx.x / LANES;
-  const int64_t mat = (int64_t)blockIdx.x * P::MATS + grp;
-  const bool live = mat < n;
-  const int64_t msafe = live ? mat : (n - 1);
+  const int64_t limit = (list != nullptr) ? (int64_t)*count : n;
+  for (int64_t slot = (int64_t)blockIdx.x * P::MATS + grp; slot < limit; slot += (int64_t)gridDim.x * P::MATS) {
+  const int64_t mat = (list != nullptr) ? (int64_t)list[slot] : slot;
+  const bool live = true;
+  const int64_t msafe = mat;
   float* sm = stage + grp * D * LD;
   // lanes of one matrix always sit inside one warp
   const unsigned gmask = (LANES == 32) ? 0xffffffffu
@@ -166,10 +173,19 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
     }
     if (diag_inv != nullptr)
       for (int i = lane; i < D; i += LANES) diag_inv[mat * D + i] = sm[i * LD + i];
+    if (PACKED && packed_out != nullptr) {
+      float* dst = packed_out + mat * kSymCols;
+      for (int i = lane; i < D * D; i += LANES) {
+        const int rr = i / D, cc = i % D;
+        if (rr <= cc) dst[sym16_index(rr, cc)] = sm[rr * LD + cc];
+      }
+    }
     if (lane == 0) {
-      if (logabsdet != nullptr) logabsdet[mat] = singular ? -INFINITY : lad;
+      if (logabsdet != nullptr) logabsdet[mat] = lad_scale * (singular ? -INFINITY : lad);
       if (sign != nullptr) sign[mat] = singular ? 0.f : (parity ? -sgn : sgn);
     }
+  }
+  __syncwarp(gmask);    // the staging rows are reused by the next slot of this group
   }
 }
 
@@ -183,9 +199,9 @@ int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* 
     batched_inverse_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, n, inv, logabsdet, sign,  \
                                                                diag_inv, transpose_inv);    \
   } break;
-    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
 #undef CASE
-    default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be 1,2,4,8,16 or 32");
+    default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be a power of two <= 64");
   }
   RLVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -197,6 +213,156 @@ int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv
   unsigned grid = (unsigned)((n + PP<16>::MATS - 1) / PP<16>::MATS);
   batched_inverse_kernel<16, true><<<grid, PP<16>::THREADS, 0, s>>>(a_packed, n, inv, logabsdet, sign,
                                                                      diag_inv, transpose_inv);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric positive-definite fast path (d == 16, packed [N,144] input from the symmetric tensor
+// kernel): ONE THREAD PER MATRIX, the 136 packed entries in registers, everything statically indexed.
+//   Cholesky A = L L^T  ->  L^{-1} in place  ->  G = L^{-T} L^{-1} in place (LAPACK potrf/trtri/lauum)
+// ~2.2k FMAs per matrix and no shuffles (the 16-lane Gauss-Jordan above spends ~27k lane-instructions
+// per matrix), so the kernel is bound by its HBM traffic: 576 B in + up to 576 + 64 + 8 B out per point.
+// Global traffic is staged through shared memory (row stride 148 floats: 16-byte aligned and
+// conflict-free for 128-bit accesses) so that every global access is a coalesced float4.
+// A matrix whose Cholesky pivot is not > 0 (not positive definite -- the loader only warns about
+// that, ref src/models/components/metric_loader.py:211-214) is appended to `fail_list`; the pivoting
+// Gauss-Jordan kernel then redoes exactly those matrices (launch_sym16_inverse), which keeps the
+// torch.linalg.inv / slogdet semantics for every input.
+// ------------------------------------------------------------------------------------------------
+namespace sym16 {
+constexpr int THREADS = 64;
+constexpr int LD = 148;
+}
+#define SYM_L(r, c) a[sym16_index((c), (r))]   /* lower-triangular entry (r >= c) */
+
+__global__ void __launch_bounds__(sym16::THREADS)
+sym16_cholesky_kernel(const float* __restrict__ a_packed, int64_t n, float* __restrict__ g_packed,
+                      float* __restrict__ logabsdet, float lad_scale, float* __restrict__ sign,
+                      float* __restrict__ diag_g, int* __restrict__ fail_count,
+                      int* __restrict__ fail_list) {
+  constexpr int LD = sym16::LD, TH = sym16::THREADS;
+  __shared__ __align__(16) float stage[TH * LD];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * TH;
+  const int rows = (int)((n - m0 < TH) ? (n - m0) : TH);
+  {
+    const float4* src = reinterpret_cast<const float4*>(a_packed + m0 * kSymCols);
+    for (int i = tid; i < rows * 36; i += TH) {
+      const int r = i / 36, c = i - r * 36;
+      *reinterpret_cast<float4*>(stage + r * LD + 4 * c) = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  const bool live = tid < rows;
+  float a[136];
+#pragma unroll
+  for (int q = 0; q < 34; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(stage + tid * LD + 4 * q);
+    a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+  }
+  if (!live) {          // keep the idle lanes finite
+#pragma unroll
+    for (int i = 0; i < 136; ++i) a[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[sym16_index(i, i)] = 1.f;
+  }
+  // ---- Cholesky (left-looking, column by column); rd[j] = 1 / L_jj
+  float rd[16];
+  float lad = 0.f;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float d = SYM_L(j, j);
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fmaf(-SYM_L(j, k), SYM_L(j, k), d);
+    ok = ok && (d > 0.f);
+    lad += logf(d);
+    const float ljj = sqrtf(d);
+    const float inv = 1.f / ljj;
+    rd[j] = inv;
+    SYM_L(j, j) = ljj;
+#pragma unroll
+    for (int i = j + 1; i < 16; ++i) {
+      float sacc = SYM_L(i, j);
+#pragma unroll
+      for (int k = 0; k < j; ++k) sacc = fmaf(-SYM_L(i, k), SYM_L(j, k), sacc);
+      SYM_L(i, j) = sacc * inv;
+    }
+  }
+  // ---- L^{-1} in place, column by column (columns > j still hold L)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    SYM_L(j, j) = rd[j];
+#pragma unroll
+    for (int i = j + 1; i < 16; ++i) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = j; k < i; ++k) sacc = fmaf(SYM_L(i, k), SYM_L(k, j), sacc);
+      SYM_L(i, j) = -sacc * rd[i];
+    }
+  }
+  if (diag_g != nullptr && live) {
+    float dg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = i; k < 16; ++k) sacc = fmaf(SYM_L(k, i), SYM_L(k, i), sacc);
+      dg[i] = sacc;
+    }
+    float4* dst = reinterpret_cast<float4*>(diag_g + (m0 + tid) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
+  }
+  if (live) {
+    if (logabsdet != nullptr) logabsdet[m0 + tid] = lad_scale * lad;
+    if (sign != nullptr) sign[m0 + tid] = 1.f;
+    if (!ok) fail_list[atomicAdd(fail_count, 1)] = (int)(m0 + tid);
+  }
+  if (g_packed == nullptr) return;
+  // ---- G = L^{-T} L^{-1} in place, row by row (row i is dead once G_i. is formed)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = i; k < 16; ++k) sacc = fmaf(SYM_L(k, i), SYM_L(k, j), sacc);
+      SYM_L(i, j) = sacc;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 34; ++q)
+    *reinterpret_cast<float4*>(stage + tid * LD + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+  *reinterpret_cast<float4*>(stage + tid * LD + 136) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(stage + tid * LD + 140) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(g_packed + m0 * kSymCols);
+  for (int i = tid; i < rows * 36; i += TH) {
+    const int r = i / 36, c = i - r * 36;
+    dst[i] = *reinterpret_cast<const float4*>(stage + r * LD + 4 * c);
+  }
+}
+#undef SYM_L
+
+// Packed symmetric G^{-1} [N,144] -> any of { packed G [N,144], lad_scale * log|det G^{-1}|, sign,
+// diag(G) }.  `fail_ws` holds 1 + n ints (counter, then the list of non-positive-definite matrices).
+int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
+                         float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(fail_ws != nullptr, "sym16_inverse: workspace required");
+  RLVAE_REQUIRE(n < (int64_t)1 << 31, "sym16_inverse: batch too large for the 32-bit fallback list");
+  RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
+  const unsigned grid = (unsigned)((n + sym16::THREADS - 1) / sym16::THREADS);
+  sym16_cholesky_kernel<<<grid, sym16::THREADS, 0, s>>>(a_packed, n, g_packed, logabsdet, lad_scale, sign,
+                                                         diag_g, fail_ws, fail_ws + 1);
+  RLVAE_CUDA_OK(cudaGetLastError());
+  // fallback for the matrices Cholesky rejected (usually none: the kernel reads the counter and exits)
+  const int64_t groups = (n + PP<16>::MATS - 1) / PP<16>::MATS;
+  const unsigned fgrid = (unsigned)(groups < 1184 ? groups : 1184);
+  batched_inverse_kernel<16, true><<<fgrid, PP<16>::THREADS, 0, s>>>(
+      a_packed, n, nullptr, logabsdet, sign, diag_g, 0, fail_ws + 1, fail_ws, g_packed, lad_scale);
   RLVAE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -294,9 +460,9 @@ int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float 
     unsigned grid = (unsigned)((n + PP<D>::MATS - 1) / PP<D>::MATS);                        \
     chol_apply_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, eps, n, jitter, out, status);  \
   } break;
-    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
 #undef CASE
-    default: RLVAE_REQUIRE(false, "chol_apply: latent_dim must be 1,2,4,8,16 or 32");
+    default: RLVAE_REQUIRE(false, "chol_apply: latent_dim must be a power of two <= 64");
   }
   RLVAE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -787,7 +787,7 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                       const __grid_constant__ CUtensorMap tm_mn_lo,
                       const float* __restrict__ z, const float* __restrict__ u,
                       const float* __restrict__ cnat, const float* __restrict__ cbias, int64_t n,
-                      int num_blocks, float alpha, float scale, float* __restrict__ out) {
+                      int num_blocks, float alpha, float scale, float* __restrict__ out, int u_packed) {
   // local names shadow the forward kernel's constants of the same name
   constexpr int C_STAGES = grad::C_STAGES, M_STAGES = grad::M_STAGES, RED_LD = grad::RED_LD;
   constexpr uint32_t C_TILE_BYTES = grad::C_TILE_BYTES, CN_BYTES = grad::CN_BYTES,
@@ -878,7 +878,7 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
     // this thread's share of U (hi/lo split) -> TMEM, the A operand of the T GEMM.
     // dense: 64 of this half's 128 columns; packed: up to 40 of this half's 72 / 64 columns.
-    const float* urow = u + r * NCOL;
+    const float* urow = u + r * (u_packed ? SYM_COLS : NCOL);   // packed: a symmetric U, [N,144]
     if (!SYM) {
       const float* usrc = urow + half * NHALF + grp * 64;
 #pragma unroll
@@ -912,8 +912,13 @@ metric_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       for (int i = 0; i < 40; ++i) {
         float v = 0.f;
         if (r < n && p < pend) {
-          v = __ldg(urow + ri * 16 + cj);
-          if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+          if (u_packed) {
+            v = __ldg(urow + p);
+            if (cj != ri) v += v;
+          } else {
+            v = __ldg(urow + ri * 16 + cj);
+            if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+          }
         }
         const float hi = tf32_rna(v);
         if (i < 32) { h[i] = __float_as_uint(hi); l[i] = __float_as_uint(v - hi); }
@@ -1162,7 +1167,7 @@ metric_grad_sym_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const __grid_constant__ CUtensorMap tm_ct_lo,
                        const float* __restrict__ z, const float* __restrict__ u,
                        const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha, float scale,
-                       float* __restrict__ out) {
+                       float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = gsym::C_STAGES, M_STAGES = gsym::M_STAGES, RED_LD = gsym::RED_LD;
   constexpr uint32_t C_TILE_BYTES = gsym::C_TILE_BYTES, CT_TILE_BYTES = gsym::CT_TILE_BYTES,
                      BIAS_BYTES = gsym::BIAS_BYTES, M_TILE_BYTES = gsym::M_TILE_BYTES, OFF_C = gsym::OFF_C,
@@ -1268,7 +1273,7 @@ metric_grad_sym_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (grp == 1) zb = -nrm * alpha;
     }
     // packed symmetric U: Ut_p = U_ij + U_ji (i<j), U_ii; this thread converts 40 packed columns
-    const float* urow = u + r * NCOL;
+    const float* urow = u + r * (u_packed ? SYM_COLS : NCOL);   // packed: a symmetric U, [N,144]
     const int pbase = half == 0 ? 0 : grad::SYM_SPLIT;
     const int pend = half == 0 ? grad::SYM_SPLIT : 136;
     uint32_t h[32], l[32], h2[8], l2[8];
@@ -1280,8 +1285,13 @@ metric_grad_sym_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     for (int i = 0; i < 40; ++i) {
       float v = 0.f;
       if (r < n && p < pend) {
-        v = __ldg(urow + ri * 16 + cj);
-        if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+        if (u_packed) {
+          v = __ldg(urow + p);
+          if (cj != ri) v += v;
+        } else {
+          v = __ldg(urow + ri * 16 + cj);
+          if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+        }
       }
       const float hi = tf32_rna(v);
       if (i < 32) { h[i] = __float_as_uint(hi); l[i] = __float_as_uint(v - hi); }
@@ -1588,6 +1598,10 @@ int tc_build_descriptors(rlvae_tables* t) {
   if (int rc = make_map_atoms(enc, &t->tm_mn_lo, t->Mn_lo, Kpad)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn2_hi, t->Mn_hi, Kpad, 256, tc::BK / 2, 4)) return rc;
   if (int rc = make_map_atoms(enc, &t->tm_mn2_lo, t->Mn_lo, Kpad, 256, tc::BK / 2, 4)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct_hi, t->ct_hi, Kpad, 32, 32, 32)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct_lo, t->ct_lo, Kpad, 32, 32, 32)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct2_hi, t->ct_hi, Kpad, 32, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct2_lo, t->ct_lo, Kpad, 32, 32, 16)) return rc;
   return 0;
 }
 
@@ -1683,7 +1697,8 @@ int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, f
 
 template <bool SYM, bool PAIR>
 static int launch_grad(const CUtensorMap& c, const CUtensorMap& hi, const CUtensorMap& lo, const rlvae_tables* t,
-                       const float* z, const float* u, int64_t n, float scale, float* out, cudaStream_t s) {
+                       const float* z, const float* u, int64_t n, float scale, float* out, cudaStream_t s,
+                       int u_packed) {
   auto kern = tc::metric_grad_tc_kernel<SYM, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1709,24 +1724,76 @@ static int launch_grad(const CUtensorMap& c, const CUtensorMap& hi, const CUtens
   const float* cnat = t->c;
   const float* cbias = t->cbias;
   const int nb = t->Kpad / tc::BK;
-  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, u, cnat, cbias, n, nb, alpha, scale, out));
+  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, u, cnat, cbias, n, nb, alpha, scale, out, u_packed));
   return 0;
 }
 
+template <bool PAIR>
+static int launch_grad_sym(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
+                           float* out, cudaStream_t s, int u_packed) {
+  auto kern = tc::metric_grad_sym_kernel<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::gsym::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 2, 1);
+  cfg.blockDim = dim3(tc::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::gsym::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  if (PAIR) {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t->tm_ct2_hi,
+                                     t->tm_ct2_lo, z, u, cbias, n, nb, alpha, scale, out, u_packed));
+  } else {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t->tm_ct_hi,
+                                     t->tm_ct_lo, z, u, cbias, n, nb, alpha, scale, out, u_packed));
+  }
+  return 0;
+}
+
+// RLVAE_TC_GRAD=fma selects the older kernel whose final contraction runs on the FMA pipe
+static bool use_grad_sym() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RLVAE_TC_GRAD");
+    v = (e != nullptr && e[0] == 'f') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
-                          float* out, cudaStream_t s) {
+                          float* out, cudaStream_t s, int u_packed) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0,
                 "tensor path needs 16-byte aligned z and u");
   RLVAE_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 16, s));   // the two column halves add
   const bool sym = t->symmetric && t->Mns_hi != nullptr;
-  if (sym) {
-    return use_pairs() ? launch_grad<true, true>(t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t, z, u, n, scale, out, s)
-                       : launch_grad<true, false>(t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t, z, u, n, scale, out, s);
+  RLVAE_REQUIRE(sym || !u_packed, "packed U needs symmetric tables");
+  if (sym && use_grad_sym()) {
+    return use_pairs() ? launch_grad_sym<true>(t, z, u, n, scale, out, s, u_packed)
+                       : launch_grad_sym<false>(t, z, u, n, scale, out, s, u_packed);
   }
-  return use_pairs() ? launch_grad<false, true>(t->tm_cstack, t->tm_mn2_hi, t->tm_mn2_lo, t, z, u, n, scale, out, s)
-                     : launch_grad<false, false>(t->tm_cstack, t->tm_mn_hi, t->tm_mn_lo, t, z, u, n, scale, out, s);
+  if (sym) {
+    return use_pairs() ? launch_grad<true, true>(t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t, z, u, n, scale, out, s, u_packed)
+                       : launch_grad<true, false>(t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t, z, u, n, scale, out, s, u_packed);
+  }
+  return use_pairs() ? launch_grad<false, true>(t->tm_cstack, t->tm_mn2_hi, t->tm_mn2_lo, t, z, u, n, scale, out, s, 0)
+                     : launch_grad<false, false>(t->tm_cstack, t->tm_mn_hi, t->tm_mn_lo, t, z, u, n, scale, out, s, 0);
 }
 
 }  // namespace rlvae

@@ -186,6 +186,11 @@ class MetricTensor(nn.Module):
     def compute_metric(self, z: torch.Tensor) -> torch.Tensor:
         """G(z) = inv(G^{-1}(z)) [N,d,d]  (ref metric_tensor.py:139-160).  A singular G^{-1}
         is retried once with +1e-6 I, like the reference's LinAlgError handler."""
+        if not (torch.is_grad_enabled() and z.requires_grad):
+            # no graph to build: one fused evaluation (packed Cholesky for symmetric tables)
+            g = self.evaluate(z, want_ginv=False, want_g=True, want_logdet=False)['g']
+            if not self.check_singular or bool(torch.isfinite(g).all()):
+                return g
         g_inv = self.compute_inverse_metric(z)
         g, sgn = _InverseFn.apply(g_inv)
         if self.check_singular and bool((sgn == 0).any()):   # exact zero pivot == LinAlgError
@@ -196,6 +201,8 @@ class MetricTensor(nn.Module):
 
     def compute_log_det_metric(self, z: torch.Tensor) -> torch.Tensor:
         """log|det G(z)| [N]  (ref metric_tensor.py:162-182) = -log|det G^{-1}(z)|."""
+        if not (torch.is_grad_enabled() and z.requires_grad):
+            return self.evaluate(z, want_ginv=False, want_g=False, want_logdet=True)['logdet_g']
         return -_LogAbsDetFn.apply(self.compute_inverse_metric(z))
 
     def compute_riemannian_distance_squared(self, z1: torch.Tensor, z2: torch.Tensor) -> torch.Tensor:

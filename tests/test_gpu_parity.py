@@ -248,7 +248,7 @@ def test_batched_inverse_general_matrices():
     """pivoting / sign / singular handling of rlvae_batched_inverse vs torch.linalg on CPU."""
     from rlvae_b200 import _capi
     g = torch.Generator().manual_seed(12)
-    for d in (1, 2, 4, 8, 16, 32):
+    for d in (1, 2, 4, 8, 16, 32, 64):
         a = torch.randn(300, d, d, generator=g)           # general, both determinant signs
         a[0] = torch.eye(d)[torch.randperm(d, generator=g)]   # a pure permutation
         inv, lad, sgn, diag = _capi.batched_inverse(a.to(dev()), True, True, True, True)
@@ -264,6 +264,62 @@ def test_batched_inverse_general_matrices():
     _, lad, sgn, _ = _capi.batched_inverse(sing.to(dev()), False, True, True, False)
     assert sgn.cpu().tolist() == [0.0, 1.0, 0.0]
     assert lad[1].item() == 0.0 and lad[0].item() == -math.inf
+
+
+def test_symmetric_indefinite_tables_take_the_pivoting_fallback():
+    """Symmetric but indefinite M_k (the loader only warns, ref metric_loader.py:211-214): the packed
+    per-thread Cholesky rejects every matrix and the pivoting Gauss-Jordan pass redoes them, so the
+    results keep torch.linalg.inv / slogdet semantics.  A mixed batch (some points positive definite,
+    some not) exercises the fallback list itself."""
+    from rlvae_b200 import _capi
+    gen = torch.Generator().manual_seed(21)
+    K, d = 200, 16
+    q, _ = torch.linalg.qr(torch.randn(d, d, generator=gen))
+    c = torch.randn(K, d, generator=gen)
+    sign = torch.ones(d); sign[d // 2:] = -1.0
+    # centroids in the half-space c_0 > 0 carry indefinite M_k, the others positive definite ones
+    dk = 0.05 * (0.5 + torch.rand(K, d, generator=gen))
+    dk = torch.where((c[:, :1] > 0), dk * sign, dk)
+    M = torch.einsum('ij,kj,lj->kil', q, dk, q)
+    M = 0.5 * (M + M.transpose(1, 2))
+    t = (c, M, 3.0, 0.01)
+    z = torch.randn(777, d, generator=gen)
+    z[:300, 0] += 6.0       # dominated by indefinite centroids
+    z[300:600, 0] -= 6.0    # dominated by positive definite centroids
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=128)
+    ev_min = torch.linalg.eigvalsh(ref_ginv.double())[:, 0]
+    assert (ev_min < 0).any() and (ev_min > 0).any()
+    ref_g = torch.linalg.inv(ref_ginv)
+    sl = torch.linalg.slogdet(ref_g.double())
+    ref_grad = O.chunked(O.grad_log_sqrt_det_ginv_exact, z, *t, chunk=128) * -2.0
+    good = torch.linalg.cond(ref_ginv.double()) < 50       # fp32 inverse error ~ cond * eps
+    assert good.sum() > 500
+    for path in paths_for(t):
+        mt = make_mt(t, path)
+        ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+        assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT, path
+        assert rel_fro(ev['g'].cpu()[good], ref_g[good]) < 1e-4, path
+        close_ld(ev['logdet_g'].cpu()[good], sl.logabsdet[good].float())
+        assert rel_fro(ev['grad_logdet_g'].cpu()[good], ref_grad[good]) < 5e-4, path
+
+
+def test_latent_dim_64_direct_path():
+    """BASELINE.json configs[4] shape family (d = 64): the direct kernels and the d = 64 per-point
+    inverse against the CPU oracle (small K, N so the oracle's [n,K,d,d] stays small)."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(96, 64, seed=3)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    z = make_points(130, 64, seed=4)
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=32)
+    ref_g = torch.linalg.inv(ref_ginv)
+    ref_ld = torch.linalg.slogdet(ref_g).logabsdet
+    ref_grad = O.chunked(O.grad_log_sqrt_det_ginv_exact, z, *t, chunk=32) * -2.0
+    mt = make_mt(t, 'auto')
+    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT
+    assert rel_fro(ev['g'].cpu(), ref_g) < 5e-5
+    close_ld(ev['logdet_g'], ref_ld)
+    assert rel_fro(ev['grad_logdet_g'].cpu(), ref_grad) < TOL_LD
 
 
 @pytest.mark.parametrize('case', ['hmc_d16_k300', 'hmc_d16_k300_beta03'])
