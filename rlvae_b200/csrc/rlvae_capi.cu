@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <cuda_fp16.h>
+
 #include "rlvae_internal.h"
 
 namespace rlvae {
@@ -59,13 +61,15 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
 __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int Kpad, int dd,
                                      float* __restrict__ M, float* __restrict__ mt_hi,
                                      float* __restrict__ mt_lo, float* __restrict__ mn_hi,
-                                     float* __restrict__ mn_lo) {
+                                     float* __restrict__ mn_lo, float* __restrict__ stats) {
   const int64_t total = (int64_t)Kpad * dd;
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / dd), q = (int)(i - (int64_t)k * dd);
     const float v = (k < K) ? m_in[i] : 0.f;
     M[i] = v;
+    amax = fmaxf(amax, fabsf(v));
     if (mt_hi != nullptr) {
       const float hi = tf32_hi(v);
       mn_hi[i] = hi;
@@ -73,6 +77,27 @@ __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int 
       mt_hi[(int64_t)q * Kpad + k] = hi;
       mt_lo[(int64_t)q * Kpad + k] = v - hi;
     }
+  }
+  if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[3]), __float_as_int(amax));
+}
+
+// split-fp16 packed-transposed tables [144, Kpad]: hi = fp16(scale * M), lo = fp16(scale * M - hi)
+__global__ void pack_sym_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_t,
+                                  __half* __restrict__ lo_t) {
+  const int64_t total = (int64_t)kSymCols * Kpad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / Kpad), k = (int)(idx - (int64_t)p * Kpad);
+    float v = 0.f;
+    if (p < 136) {
+      int i = 0, base = 0;
+      while (p >= base + (16 - i)) { base += 16 - i; ++i; }
+      const int j = i + (p - base);
+      v = scale * M[(int64_t)k * 256 + i * 16 + j];
+    }
+    const __half h = __float2half_rn(v);
+    hi_t[idx] = h;
+    lo_t[idx] = __float2half_rn(v - __half2float(h));
   }
 }
 
@@ -138,6 +163,9 @@ static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
 
 static void free_tables(rlvae_tables* t) {
   pythae_cache_release(t);
+  if (t->Mh_hi) cudaFree(t->Mh_hi);
+  if (t->Mh_lo) cudaFree(t->Mh_lo);
+  t->Mh_hi = t->Mh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
                     &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
@@ -214,7 +242,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
                                                            t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, stats);
   OK_OR_FAIL(cudaGetLastError());
   pack_matrices_kernel<<<592, 256, 0, s>>>(matrices, K, Kpad, dd, t->M, t->Mt_hi, t->Mt_lo, t->Mn_hi,
-                                           t->Mn_lo);
+                                           t->Mn_lo, stats);
   OK_OR_FAIL(cudaGetLastError());
   symmetry_kernel<<<592, 256, 0, s>>>(matrices, K, d, reinterpret_cast<int*>(stats + 2));
   OK_OR_FAIL(cudaGetLastError());
@@ -227,6 +255,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   std::memcpy(&asym, &h_stats[2], sizeof(int));
   t->symmetric = asym ? 0 : 1;
   t->r2max = h_stats[1];
+  t->m_absmax = h_stats[3];
   const float r2mean = h_stats[0] / (float)K;
   // Accuracy gate of the expanded form ||z||^2+||c||^2-2 z.c (DESIGN.md "precision"): its
   // absolute error ~2.5e-7*mean||c||^2 becomes a relative error /T^2 in every weight.
@@ -253,6 +282,27 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
       OK_OR_FAIL(cudaStreamSynchronize(s));
       rc = tc_build_sym_descriptors(t);
       if (rc != 0) return fail(rc);
+      // split-fp16 tables: M' = 2^e M with max|M'| in (2^13, 2^14]
+      if (t->m_absmax > 0.f) {
+        int ex = 0;
+        frexpf(t->m_absmax, &ex);                    // m_absmax = f * 2^ex, f in [0.5, 1)
+        const int e = 14 - ex;
+        if (e > -100 && e < 100) {
+          cudaError_t e3 = cudaMalloc(&t->Mh_hi, sizeof(__half) * (size_t)kSymCols * Kpad);
+          cudaError_t e4 = cudaMalloc(&t->Mh_lo, sizeof(__half) * (size_t)kSymCols * Kpad);
+          if (e3 != cudaSuccess || e4 != cudaSuccess) {
+            set_error("tables_create: cudaMalloc (fp16 tables) failed");
+            return fail(1);
+          }
+          pack_sym_h_kernel<<<592, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, e), static_cast<__half*>(t->Mh_hi),
+                                                static_cast<__half*>(t->Mh_lo));
+          OK_OR_FAIL(cudaGetLastError());
+          OK_OR_FAIL(cudaStreamSynchronize(s));
+          t->h16_out_scale = ldexpf(1.f, -(14 + e));
+          rc = tc_build_h16_descriptors(t);
+          if (rc != 0) return fail(rc);
+        }
+      }
     }
   }
   *out = t;
@@ -284,6 +334,36 @@ static int resolve_path(const rlvae_tables* t, int path, bool* use_tc) {
   return 0;
 }
 
+// RLVAE_TC_FWD=tf32 selects the 3xTF32 forward kernel for symmetric tables (default: split fp16)
+static bool use_h16(const rlvae_tables* t) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RLVAE_TC_FWD");
+    v = (e != nullptr && e[0] == 't') ? 0 : 1;
+  }
+  return v == 1 && t->Mh_hi != nullptr;
+}
+
+// Symmetric tables on the tensor path: packed G^{-1} [N,144] into a_packed plus any of
+// { packed G, lad_scale * log|det G^{-1}|, sign, diag(G) }.  fail_ws: 1 + n ints.
+static int sym_forward(const rlvae_tables* t, const float* z, int64_t n, float* a_packed, float* g_packed,
+                       float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s) {
+  if (use_h16(t))
+    return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s);
+  if (int rc = launch_inverse_metric_tc_sym(t, z, n, a_packed, s)) return rc;
+  if (g_packed || lad || sgn || diag)
+    return launch_sym16_inverse(a_packed, n, g_packed, lad, lad_scale, sgn, diag, fail_ws, s);
+  return 0;
+}
+
+// does this (tables, path selector) pair run the packed symmetric tensor kernels?
+static int sym_tensor_path(const rlvae_tables* t, int path, bool* yes) {
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  *yes = use_tc && t->symmetric && t->Mts_hi != nullptr;
+  return 0;
+}
+
 int64_t rlvae_inverse_metric_workspace(int64_t n, int d) {
   return d == 16 ? (int64_t)sizeof(float) * n * kSymCols : 0;
 }
@@ -301,7 +381,7 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
   if (t->symmetric && t->Mts_hi != nullptr && work != nullptr) {
     // symmetric tables: accumulate the 136 packed entries, then expand to [N,16,16]
     float* packed = static_cast<float*>(work);
-    if (int rc = launch_inverse_metric_tc_sym(t, z, n, packed, s)) return rc;
+    if (int rc = sym_forward(t, z, n, packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr, s)) return rc;
     return launch_unpack_sym16(packed, n, ginv, s);
   }
   return launch_inverse_metric_tc(t, z, n, ginv, s);
@@ -315,21 +395,16 @@ int rlvae_inverse_metric_packed(const rlvae_tables_t* t, const float* z, int64_t
   RLVAE_REQUIRE(z != nullptr && packed != nullptr, "inverse_metric_packed: NULL pointer");
   RLVAE_REQUIRE(t->tensor_capable && t->symmetric && t->Mts_hi != nullptr,
                 "inverse_metric_packed: needs latent_dim == 16 and symmetric metric matrices");
-  return launch_inverse_metric_tc_sym(t, z, n, packed, static_cast<cudaStream_t>(stream));
+  return sym_forward(t, z, n, packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr,
+                     static_cast<cudaStream_t>(stream));
 }
 
-// G^{-1} in whichever layout is cheapest for the consumers inside this library:
-// *packed = 1 -> `buf` holds the symmetric packed [N,144] layout, else the full [N,d,d].
-static int inverse_metric_internal(const rlvae_tables* t, const float* z, int64_t n, float* buf, int path,
-                                   cudaStream_t s, int* packed) {
+// full [N,d,d] G^{-1} for the non-symmetric / non-tensor cases
+static int inverse_metric_full(const rlvae_tables* t, const float* z, int64_t n, float* buf, int path,
+                               cudaStream_t s) {
   bool use_tc;
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
-  *packed = 0;
   if (!use_tc) return launch_inverse_metric_direct(t, z, n, buf, s);
-  if (t->symmetric && t->Mts_hi != nullptr) {
-    *packed = 1;
-    return launch_inverse_metric_tc_sym(t, z, n, buf, s);
-  }
   return launch_inverse_metric_tc(t, z, n, buf, s);
 }
 
@@ -383,27 +458,24 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   float* lad_buf = w + 2 * mat;
   float* gt_buf = w + 2 * mat + n;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int packed = 0;
-  if (int rc = inverse_metric_internal(t, z, n, a_buf, path, s, &packed)) return rc;
-  if (ginv != nullptr) {
-    if (packed) { if (int rc = launch_unpack_sym16(a_buf, n, ginv, s)) return rc; }
-    else RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
-  }
+  bool packed = false;
+  if (int rc = sym_tensor_path(t, path, &packed)) return rc;
   if (packed) {
-    // symmetric tables on the tensor path: G^{-1} arrives packed [N,144]; one per-thread Cholesky
-    // kernel produces packed G and -log|det G^{-1}| = log|det G|, and the gradient kernel contracts
-    // the packed G directly (G^T == G).  The spare tail of a_buf holds the fallback list.
+    // symmetric tables on the tensor path: ONE kernel produces packed G^{-1} [N,144], packed G and
+    // -log|det G^{-1}| = log|det G| (per-thread Cholesky fused into its epilogue); the gradient
+    // kernel contracts the packed G directly (G^T == G).  The spare tail of a_buf is the fallback list.
     float* g_packed = (g != nullptr || grad_logdet_g != nullptr) ? (w + mat) : nullptr;
     int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
-    if (g_packed != nullptr || logdet_g != nullptr) {
-      if (int rc = launch_sym16_inverse(a_buf, n, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s))
-        return rc;
-    }
+    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s)) return rc;
+    if (ginv != nullptr) { if (int rc = launch_unpack_sym16(a_buf, n, ginv, s)) return rc; }
     if (g != nullptr) { if (int rc = launch_unpack_sym16(g_packed, n, g, s)) return rc; }
     if (grad_logdet_g != nullptr)
       return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
     return 0;
   }
+  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s)) return rc;
+  if (ginv != nullptr)
+    RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
   // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
   // G^T == G up to rounding, otherwise a transposed copy is produced.
   const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
@@ -459,17 +531,18 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   const bool exact = grad_mode == RLVAE_GRAD_EXACT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
+  bool packed = false;
+  if (int rc = sym_tensor_path(t, path, &packed)) return rc;
   // one metric evaluation at the chain's current position: G^{-1}, then diag(G)/log|det|
   auto eval = [&](const float* zz) -> int {
-    int packed = 0;
-    if (int rc = inverse_metric_internal(t, zz, n, ginv, path, s, &packed)) return rc;
-    if (packed) {   // per-thread Cholesky on the packed layout; the gradient contracts packed G
+    if (packed) {   // fused forward + per-thread Cholesky; the gradient contracts packed G
       int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
-      if (int rc = launch_sym16_inverse(ginv, n, exact ? gfull : nullptr, lad, 1.f, sgn, diag, fail_ws, s))
+      if (int rc = sym_forward(t, zz, n, ginv, exact ? gfull : nullptr, lad, 1.f, sgn, diag, fail_ws, s))
         return rc;
       if (exact) return launch_metric_grad_tc(t, zz, gfull, n, 1.f / t->T2, gex, s, 1);
       return 0;
     }
+    if (int rc = inverse_metric_full(t, zz, n, ginv, path, s)) return rc;
     // exact mode wants G^T for the contraction (see rlvae_metric_eval)
     if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
@@ -505,13 +578,16 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
   float* ginv = w;
   float* diag = w + 2 * n * d * d;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bool packed = false;
+  if (int rc = sym_tensor_path(t, path, &packed)) return rc;
   for (int i = 0; i < n_steps; ++i) {
-    int packed = 0;
-    if (int rc = inverse_metric_internal(t, z, n, ginv, path, s, &packed)) return rc;
     if (packed) {
       int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
-      if (int rc = launch_sym16_inverse(ginv, n, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s)) return rc;
-    } else if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
+      if (int rc = sym_forward(t, z, n, ginv, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s)) return rc;
+    } else {
+      if (int rc = inverse_metric_full(t, z, n, ginv, path, s)) return rc;
+      if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
+    }
     if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;
   }
   return 0;

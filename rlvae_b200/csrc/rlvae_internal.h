@@ -65,7 +65,13 @@ struct rlvae_tables {
   // CTA-pair variants: each CTA of a pair fetches half of the B-tile rows (smaller boxes)
   CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
   CUtensorMap tm_mn2_hi, tm_mn2_lo, tm_mns_hi, tm_mns_lo, tm_mns2_hi, tm_mns2_lo;
-  CUtensorMap tm_ct_hi, tm_ct_lo, tm_ct2_hi, tm_ct2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
+  CUtensorMap tm_ct_hi, tm_ct_lo, tm_ct2_hi, tm_ct2_lo;
+  // split-fp16 tables (symmetric, d == 16): fp16(2^e M) and fp16 residual, packed-transposed [144, Kpad]
+  void* Mh_hi = nullptr;
+  void* Mh_lo = nullptr;
+  float h16_out_scale = 0.f;   // 2^-(14+e)
+  float m_absmax = 0.f;
+  CUtensorMap tm_mh_hi, tm_mh_lo, tm_mh2_hi, tm_mh2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
 };
 
 namespace rlvae {
@@ -87,6 +93,13 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
 // are not positive definite.  fail_ws: 1 + n ints.  logabsdet receives lad_scale * log|det A|.
 int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
+int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
+                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
+// split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
+int tc_build_h16_descriptors(rlvae_tables* t);
+int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
+                              float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
+                              int* fail_ws, cudaStream_t s);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,

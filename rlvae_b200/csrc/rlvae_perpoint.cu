@@ -358,7 +358,14 @@ int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, floa
   sym16_cholesky_kernel<<<grid, sym16::THREADS, 0, s>>>(a_packed, n, g_packed, logabsdet, lad_scale, sign,
                                                          diag_g, fail_ws, fail_ws + 1);
   RLVAE_CUDA_OK(cudaGetLastError());
-  // fallback for the matrices Cholesky rejected (usually none: the kernel reads the counter and exits)
+  return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
+}
+
+// The pivoting pass over the matrices a Cholesky kernel rejected (fail_ws = counter + list); usually
+// the list is empty and every CTA exits after reading the counter.
+int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
+                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s) {
+  if (n == 0) return 0;
   const int64_t groups = (n + PP<16>::MATS - 1) / PP<16>::MATS;
   const unsigned fgrid = (unsigned)(groups < 1184 ? groups : 1184);
   batched_inverse_kernel<16, true><<<fgrid, PP<16>::THREADS, 0, s>>>(

@@ -1,0 +1,622 @@
+// Split-fp16 tcgen05 kernels for SYMMETRIC metric tables, latent_dim == 16 (sm_100a).
+//
+// Same mathematics as rlvae_tc.cu (G^{-1}[n] = sum_k exp(-||z_n-c_k||^2/T^2) M_k + lambda I,
+// ref src/models/components/metric_tensor.py:115-135), but the weighted-sum GEMM runs on
+// kind::f16 at twice the kind::tf32 rate with the same ~2^-22 relative accuracy:
+//
+//   P' = 2^14 exp(..)        in (0, 2^14]          P_hi = fp16(P'),  P_lo = fp16(P' - P_hi)
+//   M' = 2^e M, max|M'| <= 2^14 (e per table)       M_hi = fp16(M'),  M_lo = fp16(M' - M_hi)
+//   O  = P_hi.M_hi + P_lo.M_hi + P_hi.M_lo          (fp32 accumulate in TMEM; the dropped P_lo.M_lo
+//                                                    term is 2^-24 relative)
+// Both operands are exact sums of two fp16 numbers down to an ABSOLUTE floor of 2^-25 in the scaled
+// units (fp16 subnormal spacing), i.e. 2^-39 relative to the largest weight / table entry, which is
+// why the power-of-two pre-scaling matters and why it is exact.  The result is un-scaled by
+// 2^-(14+e) in the epilogue.  The distance GEMM (GEMM1) stays 3xTF32: its absolute error feeds the
+// exponent.
+//
+// Because P is half as wide in TMEM (two fp16 per 32-bit column) one CTA now owns ALL 144 packed
+// columns of its 128 points (no column halves -> GEMM1 and the exp stage are not duplicated) and
+// there is room for TWO chunk accumulators, so the fp32 folding of a finished chunk overlaps the
+// accumulation of the next one.
+//
+//   TMEM columns: [0,192) three S/P buffers (64 each: S fp32, overwritten in place by
+//                 P_hi[0:32) | P_lo[0:32) | P_hi[32:64) | P_lo[32:64) as packed fp16),
+//                 [192,336) and [352,496) the two chunk accumulators (N = 144).
+//   Warp roles  : as in rlvae_tc.cu (TMA warp, MMA warp, two exp warpgroups, one fold warpgroup).
+//   FUSED       : the fold warpgroup keeps the finished 136 entries of its point in registers and
+//                 runs the per-thread Cholesky of rlvae_perpoint.cu on them, so log det G and
+//                 diag(G) (and packed G) leave the kernel directly -- the "fused metric + log-det"
+//                 kernel of the north star.  Points that are not positive definite go to the same
+//                 fallback list.
+#include <cuda_fp16.h>
+
+#include "rlvae_tc_common.cuh"
+
+namespace rlvae {
+namespace tc {
+namespace h16 {
+
+constexpr int THREADS = 512;
+constexpr int C_STAGES = 4;
+constexpr int SP_BUFS = 3;
+constexpr int M_STAGES = 6;
+constexpr int AHEAD = 3;
+constexpr int NCOLS = 144;                               // packed columns = MMA N of GEMM2
+constexpr uint32_t M_TILE_BYTES = NCOLS * 128;           // [144 rows x 64 centroids] fp16 (pair: 72 rows used)
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+constexpr int OUT_LD = 148;                               // staging row: 16-byte aligned, conflict-free for 128-bit
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
+constexpr uint32_t TM_SP = 0;        // + buf*64
+constexpr uint32_t TM_ACC = 192;     // + buf*160
+constexpr float P_SHIFT = 14.f;      // P' = 2^14 P
+
+}  // namespace h16
+
+// instruction descriptor for kind::f16: c = f32, a = b = f16, K-major both
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#define TMEM_ST16(taddr, r)                                                                          \
+  asm volatile(                                                                                      \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                \
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                    \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),     \
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), \
+        "r"(r[15]) : "memory")
+
+// (a, b) -> packed fp16 pair {hi half = a, lo half = b} and the fp32 residuals of both
+__device__ __forceinline__ void split_pair(float even, float odd, uint32_t& hi2, uint32_t& lo2) {
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(odd), "f"(even));   // .hi = odd, .lo = even element
+  float he, ho;
+  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}"
+      : "=f"(he), "=f"(ho) : "r"(h));
+  uint32_t l;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(odd - ho), "f"(even - he));
+  hi2 = h;
+  lo2 = l;
+}
+
+#define SYM_L(r, c) a[sym_index((c), (r))]   /* lower-triangular entry (r >= c) of the packed array */
+
+// Per-thread Cholesky / inverse on the 136 packed entries (same algorithm as sym16_cholesky_kernel
+// in rlvae_perpoint.cu).  a[] holds A on entry and packed G = A^{-1} on exit (when want_g).
+__device__ __forceinline__ bool sym16_factor(float (&a)[144], float& lad, float (&dg)[16], bool want_g) {
+  float rd[16];
+  bool ok = true;
+  lad = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float d = SYM_L(j, j);
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fmaf(-SYM_L(j, k), SYM_L(j, k), d);
+    ok = ok && (d > 0.f);
+    lad += logf(d);
+    const float ljj = sqrtf(d);
+    const float inv = 1.f / ljj;
+    rd[j] = inv;
+    SYM_L(j, j) = ljj;
+#pragma unroll
+    for (int i = j + 1; i < 16; ++i) {
+      float s = SYM_L(i, j);
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fmaf(-SYM_L(i, k), SYM_L(j, k), s);
+      SYM_L(i, j) = s * inv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    SYM_L(j, j) = rd[j];
+#pragma unroll
+    for (int i = j + 1; i < 16; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = j; k < i; ++k) s = fmaf(SYM_L(i, k), SYM_L(k, j), s);
+      SYM_L(i, j) = -s * rd[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = i; k < 16; ++k) s = fmaf(SYM_L(k, i), SYM_L(k, i), s);
+    dg[i] = s;
+  }
+  if (want_g) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = i; k < 16; ++k) s = fmaf(SYM_L(k, i), SYM_L(k, j), s);
+        SYM_L(i, j) = s;
+      }
+    }
+  }
+  return ok;
+}
+#undef SYM_L
+
+struct FusedOut {
+  float* a_packed;     // [N,144] G^{-1} (lambda on the diagonal) or NULL
+  float* g_packed;     // [N,144] G or NULL
+  float* logabsdet;    // [N] lad_scale * log det G^{-1} or NULL
+  float* sign;         // [N] or NULL
+  float* diag_g;       // [N,16] or NULL
+  int* fail_ws;        // counter + list (needed when any of g_packed / logabsdet / sign / diag_g is set)
+  float lad_scale;
+};
+
+template <bool PAIR>
+__global__ void __launch_bounds__(h16::THREADS, 1)
+inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
+                          const __grid_constant__ CUtensorMap tm_mh_hi,
+                          const __grid_constant__ CUtensorMap tm_mh_lo,
+                          const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
+                          int num_blocks, int chunk_blocks, float alpha /* log2(e)/T^2 */, float lambda,
+                          float out_scale /* 2^-(14+e) */, FusedOut fo) {
+  // local names shadow the tc:: constants of the 3xTF32 kernels
+  constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
+                M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS, OUT_LD = h16::OUT_LD;
+  constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, TM_SP = h16::TM_SP, TM_ACC = h16::TM_ACC;
+  constexpr float P_SHIFT = h16::P_SHIFT;
+  (void)THREADS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+  const uint32_t bar0 = base + h16::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_BIAS_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (3 * C_STAGES + M_STAGES + s); };
+  auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + h16::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  constexpr int ROWS_BOX = NCOLS / NPAIR;                 // B-tile rows held by this CTA (144 / 72)
+  constexpr uint32_t TILE_BYTES = ROWS_BOX * 128;
+  constexpr uint32_t IDESC_G2 = make_idesc_f16(PAIR ? 256 : 128, NCOLS);
+  const int row_cta = PAIR ? (int)rank * ROWS_BOX : 0;
+  const int num_chunks = (num_blocks + chunk_blocks - 1) / chunk_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_BIAS_FULL(s), 1);
+    }
+    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_lo) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + h16::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + h16::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  float zb = 0.f;
+  if (wg == 1) {          // exp group A writes the GEMM1 operand tiles
+    zb = write_z_tiles(gbase, z, row0 + prow, n, prow, alpha);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  } else if (wg == 2) {
+    const int64_t r = row0 + prow;
+    float nrm = 0.f;
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+      }
+    }
+    zb = -nrm * alpha;
+  }
+  zb += P_SHIFT;           // P' = 2^14 P, folded into the exponent
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+#define MMA_H(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_G2, acc); else mma_ts_f16(d, a, b, IDESC_G2, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (wg == 0) {
+    reg_dec<40>();
+    if (warp == 0) {
+      // =========================================================== TMA producer (warp-converged)
+      auto load_m = [&](int jm) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int it = 2 * jm + h, ms = it % M_STAGES;
+          mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+            const CUtensorMap* map = (h == 0) ? &tm_mh_hi : &tm_mh_lo;
+            const uint32_t dst = base + h16::OFF_M + ms * M_TILE_BYTES;
+            if (PAIR) tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+            else tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+          }
+          __syncwarp();
+        }
+      };
+      for (int j = 0; j < num_blocks; ++j) {
+        const int cs = j % C_STAGES;
+        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+          const uint32_t dst = base + h16::OFF_C + cs * C_TILE_BYTES;
+          if (PAIR) {
+            tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+          } else {
+            tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+            tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+          }
+          mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+          bulk_load_1d(base + h16::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
+        }
+        __syncwarp();
+        if (j >= AHEAD) load_m(j - AHEAD);
+      }
+      for (int jm = (num_blocks >= AHEAD ? num_blocks - AHEAD : 0); jm < num_blocks; ++jm) load_m(jm);
+    } else if (warp == 1 && leader) {
+      // =========================================================== MMA issuer (warp-converged; pair: leader only)
+      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+      auto gemm1 = [&](int j, bool waited) {
+        const int cs = j % C_STAGES, sb = j % SP_BUFS;
+        if (!waited) mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_gemm1<PAIR>(tmem_base + TM_SP + sb * 64, a1_desc, a2_desc,
+                             make_desc_sw128(base + h16::OFF_C + cs * C_TILE_BYTES));
+          COMMIT(BAR_S_FULL(sb));
+        }
+        __syncwarp();
+      };
+      auto wait_m = [&](int it) { mbar_wait(BAR_M_FULL(it % M_STAGES), (it / M_STAGES) & 1); };
+      for (int j = 0; j < AHEAD && j < num_blocks; ++j) gemm1(j, false);
+      wait_m(0);
+      wait_m(1);
+      mbar_wait(BAR_P_FULL(0), 0);
+      for (int j = 0; j < num_blocks; ++j) {
+        const int chunk = j / chunk_blocks;
+        const int first = (j % chunk_blocks) == 0;
+        const int ab = chunk & 1;
+        if (first && chunk >= 2) mbar_wait(BAR_CH_FREE(ab), ((chunk >> 1) - 1) & 1);   // fold group drained it
+        tc_fence_after();
+        const int sb = j % SP_BUFS;
+        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+        const uint32_t p = tmem_base + TM_SP + sb * 64;     // k-step kk: P_hi at (kk>>1)*32 + (kk&1)*8, P_lo 16 further
+        const uint32_t acc = tmem_base + TM_ACC + ab * 160;
+        const uint64_t bh = make_desc_sw128(base + h16::OFF_M + ms_hi * M_TILE_BYTES);
+        const uint64_t bl = make_desc_sw128(base + h16::OFF_M + ms_lo * M_TILE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bh + 2 * kk, !(first && kk == 0));
+        }
+        __syncwarp();
+        if (j + 1 < num_blocks) wait_m(2 * j + 2);
+        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((j + AHEAD) % C_STAGES), ((j + AHEAD) / C_STAGES) & 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + 16 + (kk & 1) * 8, bh + 2 * kk, 1);
+          COMMIT(BAR_M_EMPTY(ms_hi));
+        }
+        __syncwarp();
+        if (j + 1 < num_blocks) wait_m(2 * j + 3);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bl + 2 * kk, 1);
+          COMMIT(BAR_M_EMPTY(ms_lo));
+          if ((j % chunk_blocks) == chunk_blocks - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(ab));
+        }
+        __syncwarp();
+        if (j + AHEAD < num_blocks) gemm1(j + AHEAD, true);
+        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) % SP_BUFS), ((j + 1) / SP_BUFS) & 1);
+      }
+    }
+  } else if (wg == 1 || wg == 2) {
+    // =========================================================== exp groups (one thread per point)
+    reg_dec<112>();
+    const int grp = wg - 1;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float two_alpha = 2.f * alpha;
+    for (int j = grp; j < num_blocks; j += 2) {
+      const int cs = j % C_STAGES, sb = j % SP_BUFS;
+      const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 64;
+      mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_S_FULL(sb), (j / SP_BUFS) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t s[32], ph[16], pl[16];
+        TMEM_LD32(sp + rnd * 32, s);
+        const float4* bias4 = reinterpret_cast<const float4*>(gbase + h16::OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = bias4[q];
+          const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), two_alpha, bv.x + zb));
+          const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), two_alpha, bv.y + zb));
+          const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), two_alpha, bv.z + zb));
+          const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), two_alpha, bv.w + zb));
+          split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+          split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+        }
+        TMEM_ST16(sp + rnd * 32, ph);
+        TMEM_ST16(sp + rnd * 32 + 16, pl);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_P_FULL(sb)); else mbar_arrive(BAR_P_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+    }
+  } else {
+    // =========================================================== fold group: fp32 running total + output
+    reg_inc<232>();
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float total[NCOLS];
+#pragma unroll
+    for (int i = 0; i < NCOLS; ++i) total[i] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int ab = c & 1;
+      mbar_wait(BAR_CH_FULL(ab), (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t src = tmem_base + lane_addr + TM_ACC + ab * 160;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t a[32];
+        TMEM_LD32(src + cb * 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) total[cb * 32 + i] += __uint_as_float(a[i]);
+      }
+      {
+        uint32_t a[16];
+        TMEM_LD16(src + 128, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) total[128 + i] += __uint_as_float(a[i]);
+      }
+      if (c + 2 < num_chunks) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(ab)); else mbar_arrive(BAR_CH_FREE(ab)); }
+      }
+    }
+    // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
+    float* stage = reinterpret_cast<float*>(gbase + h16::OFF_M);
+    const int t = threadIdx.x - 384;
+    const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
+    const bool live = prow < rows_here;
+#pragma unroll
+    for (int pc = 0; pc < NCOLS; ++pc) {
+      bool diag = false;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
+      total[pc] = (pc < 136) ? fmaf(total[pc], out_scale, diag ? lambda : 0.f) : 0.f;
+    }
+    auto store_rows = [&](float* dst_base) {      // total[] -> [rows, 144] coalesced through smem
+#pragma unroll
+      for (int q = 0; q < NCOLS / 4; ++q)
+        *reinterpret_cast<float4*>(stage + prow * OUT_LD + q * 4) =
+            make_float4(total[4 * q], total[4 * q + 1], total[4 * q + 2], total[4 * q + 3]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float4* dst = reinterpret_cast<float4*>(dst_base + row0 * NCOLS);
+      for (int i = t; i < (int)rows_here * 36; i += 128) {
+        const int r = i / 36, c4 = i - r * 36;
+        dst[i] = *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    if (fo.a_packed != nullptr) store_rows(fo.a_packed);
+    const bool fused = fo.g_packed != nullptr || fo.logabsdet != nullptr || fo.sign != nullptr || fo.diag_g != nullptr;
+    if (fused) {
+      if (!live) {
+#pragma unroll
+        for (int i = 0; i < 136; ++i) total[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) total[sym_index(i, i)] = 1.f;
+      }
+      float lad, dg[16];
+      const bool ok = sym16_factor(total, lad, dg, fo.g_packed != nullptr);
+      if (live) {
+        const int64_t r = row0 + prow;
+        if (fo.logabsdet != nullptr) fo.logabsdet[r] = fo.lad_scale * lad;
+        if (fo.sign != nullptr) fo.sign[r] = 1.f;
+        if (fo.diag_g != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(fo.diag_g + r * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
+        }
+        if (!ok) fo.fail_ws[1 + atomicAdd(fo.fail_ws, 1)] = (int)r;
+      }
+      if (fo.g_packed != nullptr) {
+#pragma unroll
+        for (int i = 136; i < NCOLS; ++i) total[i] = 0.f;
+        store_rows(fo.g_packed);
+      }
+    }
+  }
+#undef MMA_H
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled16)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+
+static int make_map_h(PFN_encodeTiled16 enc, CUtensorMap* map, void* ptr, uint64_t inner, uint64_t outer,
+                      uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(__half)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp16) failed with CUresult " + std::to_string((int)r));
+    return 4;
+  }
+  return 0;
+}
+
+int tc_build_h16_descriptors(rlvae_tables* t) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  RLVAE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+  PFN_encodeTiled16 enc = reinterpret_cast<PFN_encodeTiled16>(fn);
+  const uint64_t Kpad = (uint64_t)t->Kpad;
+  // packed-transposed fp16 tables [144, Kpad]: one box = 64 centroids (128 B) x 144 (pair: 72) rows
+  if (int rc = make_map_h(enc, &t->tm_mh_hi, t->Mh_hi, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS)) return rc;
+  if (int rc = make_map_h(enc, &t->tm_mh_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS)) return rc;
+  if (int rc = make_map_h(enc, &t->tm_mh2_hi, t->Mh_hi, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
+  if (int rc = make_map_h(enc, &t->tm_mh2_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
+  return 0;
+}
+
+static bool h16_use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RLVAE_TC_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool PAIR>
+static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s) {
+  auto kern = tc::inverse_metric_h16_kernel<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::h16::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 1, 1);
+  cfg.blockDim = dim3(tc::h16::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::h16::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  const float lambda = t->lambda;
+  const float out_scale = t->h16_out_scale;
+  static int chunk_blocks = 0;
+  if (chunk_blocks == 0) {
+    const char* e = getenv("RLVAE_TC_CHUNK");
+    chunk_blocks = (e != nullptr && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : tc::CHUNK_BLOCKS;
+  }
+  const int cb = chunk_blocks;
+  if (PAIR) {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, cb,
+                                     alpha, lambda, out_scale, fo));
+  } else {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, cb,
+                                     alpha, lambda, out_scale, fo));
+  }
+  return 0;
+}
+
+// Symmetric tables, d == 16: any of { packed G^{-1}, packed G, lad_scale * log|det G^{-1}|, sign,
+// diag(G) } from ONE kernel (+ the pivoting fallback pass for points that are not positive definite,
+// which needs packed G^{-1}: a_packed must be given whenever a factor output is requested).
+int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
+                              float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
+                              int* fail_ws, cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr,
+                "split-fp16 tensor path needs latent_dim == 16 and symmetric tables");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0, "tensor path needs 16-byte aligned z");
+  const bool fused = g_packed || logabsdet || sign || diag_g;
+  RLVAE_REQUIRE(!fused || (fail_ws != nullptr && a_packed != nullptr),
+                "fused factor outputs need the packed G^{-1} buffer and the fallback workspace");
+  RLVAE_REQUIRE(n < (int64_t)1 << 31, "batch too large for the 32-bit fallback list");
+  if (fused) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
+  tc::FusedOut fo{a_packed, g_packed, logabsdet, sign, diag_g, fail_ws, lad_scale};
+  if (int rc = h16_use_pairs() ? launch_h16<true>(t, z, n, fo, s) : launch_h16<false>(t, z, n, fo, s)) return rc;
+  if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
+  return 0;
+}
+
+}  // namespace rlvae

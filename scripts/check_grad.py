@@ -22,6 +22,7 @@ b = mk('tensor').evaluate(z, want_g=True, want_grad=True)
 torch.cuda.synchronize()
 rel = lambda x, y: ((x - y).flatten(1).norm(dim=1) / y.flatten(1).norm(dim=1)).max().item()
 print('grad rel err tensor vs direct', rel(b['grad_logdet_g'], a['grad_logdet_g']))
+print('ginv rel', rel(b['ginv'], a['ginv']))
 print('g rel', rel(b['g'], a['g']), 'logdet abs', (b['logdet_g'] - a['logdet_g']).abs().max().item())
 # arbitrary (non-symmetric) U through the autograd backward
 U = torch.randn(z.shape[0], 16, 16, device=dev)
