@@ -81,6 +81,26 @@ __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int 
   if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[3]), __float_as_int(amax));
 }
 
+// split-fp16 natural tables [Kpad, 192] (136 packed columns + zeros) for the gradient kernel
+__global__ void pack_sym_nat_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_n,
+                                      __half* __restrict__ lo_n) {
+  const int64_t total = (int64_t)Kpad * 192;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / 192), p = (int)(idx - (int64_t)k * 192);
+    float v = 0.f;
+    if (p < 136) {
+      int i = 0, base = 0;
+      while (p >= base + (16 - i)) { base += 16 - i; ++i; }
+      const int j = i + (p - base);
+      v = scale * M[(int64_t)k * 256 + i * 16 + j];
+    }
+    const __half h = __float2half_rn(v);
+    hi_n[idx] = h;
+    lo_n[idx] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // split-fp16 packed-transposed tables [144, Kpad]: hi = fp16(scale * M), lo = fp16(scale * M - hi)
 __global__ void pack_sym_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_t,
                                   __half* __restrict__ lo_t) {
@@ -165,7 +185,9 @@ static void free_tables(rlvae_tables* t) {
   pythae_cache_release(t);
   if (t->Mh_hi) cudaFree(t->Mh_hi);
   if (t->Mh_lo) cudaFree(t->Mh_lo);
-  t->Mh_hi = t->Mh_lo = nullptr;
+  if (t->Mnh_hi) cudaFree(t->Mnh_hi);
+  if (t->Mnh_lo) cudaFree(t->Mnh_lo);
+  t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
                     &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
@@ -287,9 +309,11 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
         int ex = 0;
         frexpf(t->m_absmax, &ex);                    // m_absmax = f * 2^ex, f in [0.5, 1)
         const int e = 14 - ex;
-        if (e > -100 && e < 100) {
+        if (e > -60 && e < 60) {
           cudaError_t e3 = cudaMalloc(&t->Mh_hi, sizeof(__half) * (size_t)kSymCols * Kpad);
           cudaError_t e4 = cudaMalloc(&t->Mh_lo, sizeof(__half) * (size_t)kSymCols * Kpad);
+          if (e3 == cudaSuccess) e3 = cudaMalloc(&t->Mnh_hi, sizeof(__half) * (size_t)192 * Kpad);
+          if (e4 == cudaSuccess) e4 = cudaMalloc(&t->Mnh_lo, sizeof(__half) * (size_t)192 * Kpad);
           if (e3 != cudaSuccess || e4 != cudaSuccess) {
             set_error("tables_create: cudaMalloc (fp16 tables) failed");
             return fail(1);
@@ -297,8 +321,12 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           pack_sym_h_kernel<<<592, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, e), static_cast<__half*>(t->Mh_hi),
                                                 static_cast<__half*>(t->Mh_lo));
           OK_OR_FAIL(cudaGetLastError());
+          pack_sym_nat_h_kernel<<<592, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, e), static_cast<__half*>(t->Mnh_hi),
+                                                    static_cast<__half*>(t->Mnh_lo));
+          OK_OR_FAIL(cudaGetLastError());
           OK_OR_FAIL(cudaStreamSynchronize(s));
           t->h16_out_scale = ldexpf(1.f, -(14 + e));
+          t->h16_m_unscale = ldexpf(1.f, -e);
           rc = tc_build_h16_descriptors(t);
           if (rc != 0) return fail(rc);
         }

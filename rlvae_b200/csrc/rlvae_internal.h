@@ -69,9 +69,13 @@ struct rlvae_tables {
   // split-fp16 tables (symmetric, d == 16): fp16(2^e M) and fp16 residual, packed-transposed [144, Kpad]
   void* Mh_hi = nullptr;
   void* Mh_lo = nullptr;
+  void* Mnh_hi = nullptr;      // natural [Kpad, 192] (136 packed columns + zeros), gradient kernel B operand
+  void* Mnh_lo = nullptr;
   float h16_out_scale = 0.f;   // 2^-(14+e)
+  float h16_m_unscale = 0.f;   // 2^-e
   float m_absmax = 0.f;
-  CUtensorMap tm_mh_hi, tm_mh_lo, tm_mh2_hi, tm_mh2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
+  CUtensorMap tm_mh_hi, tm_mh_lo, tm_mh2_hi, tm_mh2_lo;
+  CUtensorMap tm_mnh_hi, tm_mnh_lo, tm_mnh2_hi, tm_mnh2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
 };
 
 namespace rlvae {
@@ -97,6 +101,8 @@ int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, flo
                           float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
 int tc_build_h16_descriptors(rlvae_tables* t);
+int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
+                           float* out, cudaStream_t s, int u_packed);
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
                               int* fail_ws, cudaStream_t s);

@@ -1469,14 +1469,15 @@ static int launch_grad_sym(const rlvae_tables* t, const float* z, const float* u
   return 0;
 }
 
-// RLVAE_TC_GRAD=fma selects the older kernel whose final contraction runs on the FMA pipe
-static bool use_grad_sym() {
+// RLVAE_TC_GRAD = h16 (default: split-fp16 T GEMM, one CTA per 128 points) | tf32 (3xTF32, tensor-core
+// final contraction) | fma (3xTF32, final contraction on the FMA pipe)
+static int grad_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RLVAE_TC_GRAD");
-    v = (e != nullptr && e[0] == 'f') ? 0 : 1;
+    v = (e == nullptr) ? 2 : (e[0] == 'f' ? 0 : (e[0] == 't' ? 1 : 2));
   }
-  return v == 1;
+  return v;
 }
 
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
@@ -1485,10 +1486,12 @@ int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u,
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable, "tensor path needs latent_dim == 16");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0,
                 "tensor path needs 16-byte aligned z and u");
-  RLVAE_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 16, s));   // the two column halves add
   const bool sym = t->symmetric && t->Mns_hi != nullptr;
   RLVAE_REQUIRE(sym || !u_packed, "packed U needs symmetric tables");
-  if (sym && use_grad_sym()) {
+  if (sym && grad_variant() == 2 && t->Mnh_hi != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    return launch_metric_grad_h16(t, z, u, n, scale, out, s, u_packed);
+  RLVAE_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 16, s));   // the two column halves add
+  if (sym && grad_variant() >= 1) {
     return use_pairs() ? launch_grad_sym<true>(t, z, u, n, scale, out, s, u_packed)
                        : launch_grad_sym<false>(t, z, u, n, scale, out, s, u_packed);
   }

@@ -32,6 +32,15 @@
 
 #include "rlvae_tc_common.cuh"
 
+// -DRLVAE_TC_PROFILE: CTA 0 prints where its MMA warp and exp group A spend their cycles
+#ifdef RLVAE_TC_PROFILE
+#define PROF_T0() long long _pt = clock64()
+#define PROF_ADD(acc) do { long long _n = clock64(); (acc) += _n - _pt; _pt = _n; } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(acc) do {} while (0)
+#endif
+
 namespace rlvae {
 namespace tc {
 namespace h16 {
@@ -506,6 +515,483 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   }
 }
 
+
+// ==========================================================================================
+// Gradient / backward kernel, split-fp16 version (symmetric tables, d == 16):
+//   out[n,:] = scale * sum_k w_nk <U_n, M_k> (c_k - z_n)
+// Per 64-centroid super-block j (ONE CTA contracts all 136 packed columns, so nothing is duplicated):
+//   GEMM1   S[128 x 64]  = Z.C^T                                   (3xTF32, as everywhere)
+//   T-GEMM  T[128 x 64]  = U'_hi.M'_hi^T + U'_lo.M'_hi^T + U'_hi.M'_lo^T   (kind::f16, K = 144 = 9 steps)
+//           U' = 2^eU Ut (per point, max|U'| in [2^13, 2^14)), Ut_p = U_ij + U_ji (i<j), U_ii: valid for
+//           ANY U; M' = 2^eM M as in the forward kernel.  U' (hi|lo fp16) is resident in TMEM.
+//   exp     u = exp2(..) * t, split u_hi | u_lo (fp32 / TF32), written over S | T
+//   GEMM3   OUT[128 x 32] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo   (3xTF32; Ct = [c^T ; 1 ; 0])
+// OUT accumulates in two alternating chunk accumulators (2 super-blocks each) that the exp groups
+// fold into fp32 registers.  out = scale 2^-(eU+eM) (OUT[:, :16] - z OUT[:, 16]).
+// TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2.
+// ==========================================================================================
+namespace g16 {
+constexpr int THREADS = 320;
+constexpr int C_STAGES = 3;
+constexpr int M_STAGES = 4;
+constexpr int KSTEPS = 9;                           // 144 packed columns / 16
+constexpr uint32_t CT_TILE_BYTES = 2 * 32 * 128;    // [32 rows x 64 centroids] fp32 = 2 atoms of 32 centroids
+constexpr uint32_t M_TILE_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
+constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE_BYTES;
+constexpr uint32_t OFF_M = OFF_CT + C_STAGES * 2 * CT_TILE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 9;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400;
+constexpr int RED_LD = 36;
+}  // namespace g16
+
+__device__ __forceinline__ void split_pair_scaled(float even, float odd, float sc, uint32_t& hi2, uint32_t& lo2) {
+  split_pair(even * sc, odd * sc, hi2, lo2);
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(g16::THREADS, 1)
+metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
+                       const __grid_constant__ CUtensorMap tm_mn_hi,
+                       const __grid_constant__ CUtensorMap tm_mn_lo,
+                       const __grid_constant__ CUtensorMap tm_ct_hi,
+                       const __grid_constant__ CUtensorMap tm_ct_lo,
+                       const float* __restrict__ z, const float* __restrict__ u,
+                       const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
+                       float scale /* includes 2^-eM */, float* __restrict__ out, int u_packed) {
+  constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
+  constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES, OFF_C = g16::OFF_C,
+                     OFF_CT = g16::OFF_CT, OFF_M = g16::OFF_M, OFF_BIAS = g16::OFF_BIAS,
+                     TM_UHI = g16::TM_UHI, TM_ULO = g16::TM_ULO, TM_ST = g16::TM_ST, TM_OUT = g16::TM_OUT;
+  constexpr int CHUNK = 2;             // super-blocks per OUT chunk accumulator
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + g16::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_B_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };     // bias (local)
+  auto BAR_CT_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_CT_EMPTY = [&](int s) { return bar0 + 8u * (4 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (5 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (5 * C_STAGES + M_STAGES + s); };
+  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_U_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 4 + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 6 + b); };
+  const uint32_t BAR_DONE = bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 8);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + g16::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  constexpr uint32_t ROWS_CTA = PAIR ? BK / 2 : BK;
+  constexpr uint32_t ATOM_BYTES = ROWS_CTA * 128;                   // M tile atom held by this CTA
+  constexpr uint32_t TILE_BYTES = 3 * ATOM_BYTES;
+  constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
+  constexpr uint32_t CT_ROWS = PAIR ? 16 : 32;
+  constexpr uint32_t CT_ATOM_BYTES = CT_ROWS * 128;
+  constexpr uint32_t CT_BYTES = 2 * CT_ATOM_BYTES;                  // per hi / lo tile per CTA
+  constexpr uint32_t CT_ATOM_DESC = CT_ATOM_BYTES >> 4;
+  constexpr uint32_t IDESC_T = make_idesc_f16(PAIR ? 256 : 128, BK);
+  constexpr uint32_t IDESC_3 = make_idesc(PAIR ? 256 : 128, 32);
+  const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_B_FULL(s), 1);
+      mbar_init(BAR_CT_FULL(s), 1); mbar_init(BAR_CT_EMPTY(s), 1);
+    }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), 4 * NPAIR);
+      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
+    }
+    mbar_init(BAR_DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_lo) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + g16::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + g16::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();            // TMEM base published before the exp threads store U into it
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  float zb = 0.f;
+  float u_unscale = 1.f;      // 2^-eU
+  float zrow[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
+  if (warp >= 2) {
+    const int64_t r = row0 + prow;
+    if (grp == 0) {
+      zb = write_z_tiles(gbase, z, r, n, prow, alpha);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+      float nrm = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = __ldg(src + q);
+        zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+      }
+      if (grp == 1) zb = -nrm * alpha;
+    }
+    // ---- U' = 2^eU Ut, split into fp16 hi | lo, resident in TMEM as the A operand of the T GEMM.
+    // group 0 converts packed columns [0,64), group 1 [64,144); both scan the whole row for the scale.
+    const int row_len = u_packed ? SYM_COLS : NCOL;
+    const float* urow = u + r * row_len;
+    float m = 0.f;
+    if (r < n) {
+      const float4* u4 = reinterpret_cast<const float4*>(urow);
+      const int nq = u_packed ? 34 : 64;
+      for (int q = 0; q < nq; ++q) {
+        const float4 v = __ldg(u4 + q);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+      m *= 2.f;                                     // |Ut_p| <= 2 max|U|
+    }
+    int eu = 0;
+    if (m > 0.f && m < 3.0e38f) {
+      const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;    // m = f 2^ex, f in [0.5, 1)
+      eu = 14 - ex;
+      eu = eu > 50 ? 50 : (eu < -50 ? -50 : eu);
+    }
+    const float usc = __uint_as_float((uint32_t)(eu + 127) << 23);
+    u_unscale = __uint_as_float((uint32_t)(127 - eu) << 23);
+    {
+      uint32_t h[32], l[32], h2[8], l2[8];
+      int p = grp * 64;
+      int ri = 0, rb = 0;
+      while (ri < 15 && p >= rb + (16 - ri)) { rb += 16 - ri; ++ri; }
+      int cj = ri + (p - rb);
+      auto next = [&]() -> float {      // Ut at packed index p, then advance
+        float v = 0.f;
+        if (r < n && p < 136) {
+          if (u_packed) {
+            v = __ldg(urow + p);
+            if (cj != ri) v += v;
+          } else {
+            v = __ldg(urow + ri * 16 + cj);
+            if (cj != ri) v += __ldg(urow + cj * 16 + ri);
+          }
+        }
+        ++p; ++cj;
+        if (cj == 16) { ++ri; cj = ri; }
+        return v;
+      };
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = next();
+        const float e1 = next();
+        split_pair_scaled(e0, e1, usc, h[i], l[i]);
+      }
+      TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 32, h);
+      TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 32, l);
+      if (grp == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float e0 = next();
+          const float e1 = next();
+          split_pair_scaled(e0, e1, usc, h2[i], l2[i]);
+        }
+        TMEM_ST8(tmem_base + lane_addr + TM_UHI + 64, h2);
+        TMEM_ST8(tmem_base + lane_addr + TM_ULO + 64, l2);
+      }
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+#define MMA_T16(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_T, acc); else mma_ts_f16(d, a, b, IDESC_T, acc); } while (0)
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (warp-converged)
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+        const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
+        if (PAIR) {
+          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+        } else {
+          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+        }
+        mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
+        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int it = 2 * j + h, ms = it % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+          const CUtensorMap* map = h == 0 ? &tm_mn_hi : &tm_mn_lo;
+          const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
+          const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
+          if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, 0);
+          else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, 0);
+        }
+        __syncwarp();
+      }
+      // Ct tiles (hi, lo): [32 (pair: 16) rows x 64 centroids] as two 32-centroid atoms each
+      mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
+        const uint32_t dst = base + OFF_CT + cs * 2 * CT_TILE_BYTES;
+        const int row = PAIR ? 16 * (int)rank : 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (PAIR) {
+            tma_load_2d_pair(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d_pair(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          } else {
+            tma_load_2d(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (warp-converged; pair: leader only)
+    if (leader) {
+      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
+      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
+      // [GEMM1, T-GEMM] of super-block j into S|T buffer j&1
+      auto issue_st = [&](int j) {
+        const int cs = j % C_STAGES, sb = j & 1;
+        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
+        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
+        mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t s_t = tmem_base + TM_ST + sb * 128;
+        const uint32_t t_t = s_t + 64;
+        const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
+        const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
+        if (elect_one()) {
+          issue_gemm1<PAIR>(s_t, a1_desc, a2_desc, make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_T16(t_t, tmem_base + TM_UHI + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_T16(t_t, tmem_base + TM_ULO + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), 1);
+          COMMIT(BAR_M_EMPTY(ms_hi));
+        }
+        __syncwarp();
+        mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_T16(t_t, tmem_base + TM_UHI + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), 1);
+          COMMIT(BAR_M_EMPTY(ms_lo));
+          COMMIT(BAR_ST_FULL(sb));
+        }
+        __syncwarp();
+      };
+      long long pw_st = 0, pw_chfree = 0, pw_u = 0, pw_g3 = 0;
+      (void)pw_st; (void)pw_chfree; (void)pw_u; (void)pw_g3;
+#ifdef RLVAE_TC_PROFILE
+      const long long pl0 = clock64();
+#endif
+      issue_st(0);
+      for (int j = 0; j < num_blocks; ++j) {
+        PROF_T0();
+        // S|T(j+1) first: its buffer was released by GEMM3(j-1), already queued ahead in the pipe
+        if (j + 1 < num_blocks) issue_st(j + 1);
+        PROF_ADD(pw_st);
+        const int cs = j % C_STAGES, sb = j & 1;
+        const int chunk = j / CHUNK;
+        const int first = (j % CHUNK) == 0;
+        if (first && chunk >= 2) mbar_wait(BAR_CH_FREE(chunk & 1), ((chunk >> 1) - 1) & 1);
+        mbar_wait(BAR_CT_FULL(cs), (j / C_STAGES) & 1);
+        PROF_ADD(pw_chfree);
+        mbar_wait(BAR_U_FULL(sb), (j >> 1) & 1);
+        PROF_ADD(pw_u);
+        tc_fence_after();
+        const uint32_t u_hi = tmem_base + TM_ST + sb * 128;
+        const uint32_t u_lo = u_hi + 64;
+        const uint32_t acc = tmem_base + TM_OUT + (chunk & 1) * 32;
+        const uint64_t ch = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES);
+        const uint64_t cl = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES + CT_TILE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, !(first && kk == 0));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_lo + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, cl + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
+          COMMIT(BAR_CT_EMPTY(cs));
+          if ((j % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(chunk & 1));
+        }
+        __syncwarp();
+        PROF_ADD(pw_g3);
+      }
+#ifdef RLVAE_TC_PROFILE
+      if (blockIdx.x == 0 && lane == 0)
+        printf("[g16 prof] MMA warp per super-block: total %lld | issue_st(j+1) %lld  wait CH_FREE/CT %lld  wait U_FULL %lld  issue G3 %lld\n",
+               (clock64() - pl0) / num_blocks, pw_st / num_blocks, pw_chfree / num_blocks, pw_u / num_blocks,
+               pw_g3 / num_blocks);
+#endif
+      if (elect_one()) COMMIT(BAR_DONE);
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== exp groups (one thread per point)
+    const float two_alpha = 2.f * alpha;
+    float tot[32];                       // this group's share of OUT: chunks of parity grp
+#pragma unroll
+    for (int e = 0; e < 32; ++e) tot[e] = 0.f;
+    auto fold_chunk = [&](int c, bool signal) {
+      uint32_t a[32];
+      TMEM_LD32(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tot[i] += __uint_as_float(a[i]);
+      if (signal) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
+      }
+    };
+    int next_chunk = grp;                // chunks c with (c & 1) == grp belong to this group
+    long long pe_wait = 0, pe_work = 0, pe_fold = 0;
+    (void)pe_wait; (void)pe_work; (void)pe_fold;
+    for (int j = grp; j < num_blocks; j += 2) {
+      PROF_T0();
+      const int cs = j % C_STAGES, sb = j & 1;
+      const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
+      mbar_wait(BAR_B_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
+      tc_fence_after();
+      PROF_ADD(pe_wait);
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t sv[32], tv[32];
+        TMEM_LD32(st + rnd * 32, sv);
+        TMEM_LD32(st + 64 + rnd * 32, tv);
+        const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = bias4[q];
+          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * q + e;
+            const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
+            const float uv = w * __uint_as_float(tv[i]);
+            const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
+            sv[i] = uh;
+            tv[i] = __float_as_uint(uv - __uint_as_float(uh));
+          }
+        }
+        TMEM_ST32(st + rnd * 32, sv);
+        TMEM_ST32(st + 64 + rnd * 32, tv);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+      PROF_ADD(pe_work);
+      while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
+        mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
+        tc_fence_after();
+        fold_chunk(next_chunk, true);
+        next_chunk += 2;
+      }
+      PROF_ADD(pe_fold);
+    }
+#ifdef RLVAE_TC_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 64)
+      printf("[g16 prof] exp group A per own super-block: wait S|T %lld  work %lld  fold %lld\n",
+             pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2), pe_fold / (num_blocks / 2));
+#endif
+    mbar_wait(BAR_DONE, 0);
+    tc_fence_after();
+    while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
+    // ---------------------------------------------------------- combine the two groups
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* red = reinterpret_cast<float*>(gbase + OFF_M);
+    if (grp == 1) {
+#pragma unroll
+      for (int e = 0; e < 17; ++e) red[prow * RED_LD + e] = tot[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const int64_t r = row0 + prow;
+      const float su = tot[16] + red[prow * RED_LD + 16];
+      if (r < n) {
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float ge = tot[e] + red[prow * RED_LD + e];
+          o[e] = (ge - zrow[e] * su) * u_unscale * scale;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + r * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+  }
+#undef MMA_T16
+#undef MMA_TS
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ host
@@ -530,6 +1016,23 @@ static int make_map_h(PFN_encodeTiled16 enc, CUtensorMap* map, void* ptr, uint64
   return 0;
 }
 
+
+// natural fp16 table [Kpad, 192] viewed as [3 column atoms][Kpad][64]: one box = 3 atoms x 64 (pair: 32) rows
+static int make_map_h_atoms(PFN_encodeTiled16 enc, CUtensorMap* map, void* ptr, uint64_t Kpad, uint32_t box_rows) {
+  cuuint64_t dims[3] = {64, Kpad, 3};
+  cuuint64_t strides[2] = {192 * sizeof(__half), 64 * sizeof(__half)};
+  cuuint32_t box[3] = {64, box_rows, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp16, 3d) failed with CUresult " + std::to_string((int)r));
+    return 4;
+  }
+  return 0;
+}
+
 int tc_build_h16_descriptors(rlvae_tables* t) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -542,6 +1045,10 @@ int tc_build_h16_descriptors(rlvae_tables* t) {
   if (int rc = make_map_h(enc, &t->tm_mh_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS)) return rc;
   if (int rc = make_map_h(enc, &t->tm_mh2_hi, t->Mh_hi, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
   if (int rc = make_map_h(enc, &t->tm_mh2_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
+  if (int rc = make_map_h_atoms(enc, &t->tm_mnh_hi, t->Mnh_hi, Kpad, tc::BK)) return rc;
+  if (int rc = make_map_h_atoms(enc, &t->tm_mnh_lo, t->Mnh_lo, Kpad, tc::BK)) return rc;
+  if (int rc = make_map_h_atoms(enc, &t->tm_mnh2_hi, t->Mnh_hi, Kpad, tc::BK / 2)) return rc;
+  if (int rc = make_map_h_atoms(enc, &t->tm_mnh2_lo, t->Mnh_lo, Kpad, tc::BK / 2)) return rc;
   return 0;
 }
 
@@ -617,6 +1124,57 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   if (int rc = h16_use_pairs() ? launch_h16<true>(t, z, n, fo, s) : launch_h16<false>(t, z, n, fo, s)) return rc;
   if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
   return 0;
+}
+
+template <bool PAIR>
+static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
+                      cudaStream_t s, int u_packed) {
+  auto kern = tc::metric_grad_h16_kernel<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::g16::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 1, 1);
+  cfg.blockDim = dim3(tc::g16::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::g16::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
+  if (PAIR) {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct2_hi,
+                                     t->tm_ct2_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+  } else {
+    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct_hi,
+                                     t->tm_ct_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+  }
+  return 0;
+}
+
+// (scale) * sum_k w_k <U, M_k> (c_k - z) for symmetric tables; u is [N,256] (any U) or, with
+// u_packed, a symmetric U in the packed [N,144] layout.
+int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
+                           float* out, cudaStream_t s, int u_packed) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mnh_hi != nullptr,
+                "split-fp16 gradient path needs latent_dim == 16 and symmetric tables");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
+  return h16_use_pairs() ? launch_g16<true>(t, z, u, n, scale, out, s, u_packed)
+                         : launch_g16<false>(t, z, u, n, scale, out, s, u_packed);
 }
 
 }  // namespace rlvae
