@@ -30,6 +30,8 @@
 //                 fallback list.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "rlvae_tc_common.cuh"
 
 // -DRLVAE_TC_PROFILE: CTA 0 prints where its MMA warp and exp group A spend their cycles
@@ -41,12 +43,19 @@
 #define PROF_ADD(acc) do {} while (0)
 #endif
 
+#ifdef RLVAE_TC_PROFILE
+__device__ long long g_h16_trace[8][16];   // [event][block - 40]
+#define HTRACE(ev, j) do { if (blockIdx.x == 0 && (j) >= 40 && (j) < 56 && lane == 0) g_h16_trace[ev][(j) - 40] = clock64(); } while (0)
+#else
+#define HTRACE(ev, j) do {} while (0)
+#endif
+
 namespace rlvae {
 namespace tc {
 namespace h16 {
 
 constexpr int THREADS = 512;
-constexpr int C_STAGES = 4;
+constexpr int C_STAGES = 3;
 constexpr int SP_BUFS = 3;
 constexpr int M_STAGES = 6;
 constexpr int AHEAD = 3;
@@ -56,7 +65,7 @@ constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
 constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
-constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + 3;   // + 3 pipe-trace barriers (profiling builds)
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 constexpr int OUT_LD = 148;                               // staging row: 16-byte aligned, conflict-free for 128-bit
@@ -195,7 +204,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS, OUT_LD = h16::OUT_LD;
   constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, TM_SP = h16::TM_SP, TM_ACC = h16::TM_ACC;
   constexpr float P_SHIFT = h16::P_SHIFT;
-  (void)THREADS;
+  constexpr int CB = 2;     // super-blocks per tensor-core accumulation chunk (compile-time: see the MMA issuer)
+  (void)THREADS; (void)chunk_blocks;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -210,6 +220,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
   auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
   auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + b); };
+  auto BAR_MON = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + b); };
+  (void)BAR_MON;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + h16::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -223,7 +235,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   constexpr uint32_t TILE_BYTES = ROWS_BOX * 128;
   constexpr uint32_t IDESC_G2 = make_idesc_f16(PAIR ? 256 : 128, NCOLS);
   const int row_cta = PAIR ? (int)rank * ROWS_BOX : 0;
-  const int num_chunks = (num_blocks + chunk_blocks - 1) / chunk_blocks;
+  const int num_chunks = (num_blocks + CB - 1) / CB;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) {
@@ -232,6 +244,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR); }
+    for (int b = 0; b < 3; ++b) mbar_init(BAR_MON(b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_hi) : "memory");
@@ -278,24 +291,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
   if (wg == 0) {
-    reg_dec<40>();
+    reg_dec<72>();
     if (warp == 0) {
-      // =========================================================== TMA producer (warp-converged)
-      auto load_m = [&](int jm) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int it = 2 * jm + h, ms = it % M_STAGES;
-          mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
-            const CUtensorMap* map = (h == 0) ? &tm_mh_hi : &tm_mh_lo;
-            const uint32_t dst = base + h16::OFF_M + ms * M_TILE_BYTES;
-            if (PAIR) tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
-            else tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
-          }
-          __syncwarp();
-        }
-      };
+      // =========================================================== TMA producer 1: centroid tiles + bias
       for (int j = 0; j < num_blocks; ++j) {
         const int cs = j % C_STAGES;
         mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
@@ -312,49 +310,64 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           bulk_load_1d(base + h16::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
         }
         __syncwarp();
-        if (j >= AHEAD) load_m(j - AHEAD);
       }
-      for (int jm = (num_blocks >= AHEAD ? num_blocks - AHEAD : 0); jm < num_blocks; ++jm) load_m(jm);
+    } else if (warp == 2) {
+      // =========================================================== TMA producer 2: M tiles, as far ahead
+      // as the ring allows (its own warp: a stalled centroid stage must not delay the table stream)
+      for (int it = 0; it < 2 * num_blocks; ++it) {
+        const int ms = it % M_STAGES, jm = it >> 1;
+        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+          const CUtensorMap* map = (it & 1) == 0 ? &tm_mh_hi : &tm_mh_lo;
+          const uint32_t dst = base + h16::OFF_M + ms * M_TILE_BYTES;
+          if (PAIR) tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+          else tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+        }
+        __syncwarp();
+      }
     } else if (warp == 1 && leader) {
       // =========================================================== MMA issuer (warp-converged; pair: leader only)
+      // The issue loop is unrolled 6x (lcm of the chunk, S/P-buffer, C-stage and M-stage periods) so
+      // that every stage index, TMEM address and almost every barrier parity is a compile-time
+      // constant: the tensor pipe idles whenever this warp's own instruction stream is slower than
+      // the MMAs it feeds (measured: 1.7k cycles per super-block with runtime div/mod vs 1.15k of MMA).
       const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
       const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
-      auto gemm1 = [&](int j, bool waited) {
-        const int cs = j % C_STAGES, sb = j % SP_BUFS;
-        if (!waited) mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
-        tc_fence_after();
+      const uint64_t c_desc0 = make_desc_sw128(base + h16::OFF_C);
+      const uint64_t m_desc0 = make_desc_sw128(base + h16::OFF_M);
+      auto gemm1 = [&](auto CSc, auto SBc) {
+        constexpr int cs = decltype(CSc)::value, sb = decltype(SBc)::value;
         if (elect_one()) {
-          issue_gemm1<PAIR>(tmem_base + TM_SP + sb * 64, a1_desc, a2_desc,
-                             make_desc_sw128(base + h16::OFF_C + cs * C_TILE_BYTES));
+          issue_gemm1<PAIR>(tmem_base + TM_SP + sb * 64, a1_desc, a2_desc, c_desc0 + ((cs * C_TILE_BYTES) >> 4));
           COMMIT(BAR_S_FULL(sb));
         }
         __syncwarp();
       };
-      auto wait_m = [&](int it) { mbar_wait(BAR_M_FULL(it % M_STAGES), (it / M_STAGES) & 1); };
-      for (int j = 0; j < AHEAD && j < num_blocks; ++j) gemm1(j, false);
-      wait_m(0);
-      wait_m(1);
-      mbar_wait(BAR_P_FULL(0), 0);
-      for (int j = 0; j < num_blocks; ++j) {
-        const int chunk = j / chunk_blocks;
-        const int first = (j % chunk_blocks) == 0;
-        const int ab = chunk & 1;
-        if (first && chunk >= 2) mbar_wait(BAR_CH_FREE(ab), ((chunk >> 1) - 1) & 1);   // fold group drained it
+      uint32_t free_phase = 0;     // bit ab: parity of the next CH_FREE(ab) completion to wait for
+      auto block = [&](auto Jc, const int j, const uint32_t qodd /* (j / 6) & 1 */) {
+        constexpr int J = decltype(Jc)::value;
+        constexpr int first = (J % CB) == 0, sb = J % SP_BUFS;
+        const uint32_t ab = ((J / CB) & 1) ^ qodd;          // 6 blocks = 3 chunks: the accumulator parity flips every pass
+        constexpr int ms_hi = (2 * J) % M_STAGES, ms_lo = (2 * J + 1) % M_STAGES;
+        if (first && j >= 2 * CB) {                       // fold group drained this accumulator
+          mbar_wait(BAR_CH_FREE(ab), (free_phase >> ab) & 1u);
+          free_phase ^= 1u << ab;
+        }
         tc_fence_after();
-        const int sb = j % SP_BUFS;
-        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
         const uint32_t p = tmem_base + TM_SP + sb * 64;     // k-step kk: P_hi at (kk>>1)*32 + (kk&1)*8, P_lo 16 further
         const uint32_t acc = tmem_base + TM_ACC + ab * 160;
-        const uint64_t bh = make_desc_sw128(base + h16::OFF_M + ms_hi * M_TILE_BYTES);
-        const uint64_t bl = make_desc_sw128(base + h16::OFF_M + ms_lo * M_TILE_BYTES);
+        const uint64_t bh = m_desc0 + ((ms_hi * M_TILE_BYTES) >> 4);
+        const uint64_t bl = m_desc0 + ((ms_lo * M_TILE_BYTES) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bh + 2 * kk, !(first && kk == 0));
         }
         __syncwarp();
-        if (j + 1 < num_blocks) wait_m(2 * j + 2);
-        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((j + AHEAD) % C_STAGES), ((j + AHEAD) / C_STAGES) & 1);
+        // inputs of the NEXT steps, waited for behind queued MMAs (normally long complete)
+        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((2 * J + 2) % M_STAGES), ((2 * J + 2) / M_STAGES) & 1);
+        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -362,31 +375,54 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           COMMIT(BAR_M_EMPTY(ms_hi));
         }
         __syncwarp();
-        if (j + 1 < num_blocks) wait_m(2 * j + 3);
+        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((2 * J + 3) % M_STAGES), ((2 * J + 3) / M_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bl + 2 * kk, 1);
           COMMIT(BAR_M_EMPTY(ms_lo));
-          if ((j % chunk_blocks) == chunk_blocks - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(ab));
+          if ((J % CB) == CB - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(ab));
         }
         __syncwarp();
-        if (j + AHEAD < num_blocks) gemm1(j + AHEAD, true);
-        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((j + 1) % SP_BUFS), ((j + 1) / SP_BUFS) & 1);
+        if (j + AHEAD < num_blocks) {
+          tc_fence_after();
+          gemm1(std::integral_constant<int, (J + AHEAD) % C_STAGES>{}, std::integral_constant<int, (J + AHEAD) % SP_BUFS>{});
+        }
+        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((J + 1) % SP_BUFS), ((J + 1) / SP_BUFS) & 1);
+      };
+      // prologue: GEMM1 of the first AHEAD (= 3) blocks
+      if (0 < num_blocks) { mbar_wait(BAR_C_FULL(0), 0); tc_fence_after(); gemm1(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{}); }
+      if (1 < num_blocks) { mbar_wait(BAR_C_FULL(1), 0); tc_fence_after(); gemm1(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}); }
+      if (2 < num_blocks) { mbar_wait(BAR_C_FULL(2), 0); tc_fence_after(); gemm1(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
+      mbar_wait(BAR_M_FULL(0), 0);
+      mbar_wait(BAR_M_FULL(1), 0);
+      mbar_wait(BAR_P_FULL(0), 0);
+      static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 12 % M_STAGES == 0 && AHEAD == 3,
+                    "the 6x unrolled issue loop assumes these periods");
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 6, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3) RLVAE_BLK(4) RLVAE_BLK(5)
+#undef RLVAE_BLK
       }
     }
   } else if (wg == 1 || wg == 2) {
     // =========================================================== exp groups (one thread per point)
-    reg_dec<112>();
+    reg_dec<104>();
     const int grp = wg - 1;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float two_alpha = 2.f * alpha;
+    long long pe_wait = 0, pe_work = 0;
+    (void)pe_wait; (void)pe_work;
     for (int j = grp; j < num_blocks; j += 2) {
+      PROF_T0();
       const int cs = j % C_STAGES, sb = j % SP_BUFS;
       const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 64;
       mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);
       mbar_wait(BAR_S_FULL(sb), (j / SP_BUFS) & 1);
       tc_fence_after();
+      if (quarter == 0) HTRACE(3, j);
+      PROF_ADD(pe_wait);
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t s[32], ph[16], pl[16];
@@ -413,7 +449,14 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (PAIR) mbar_arrive_leader(BAR_P_FULL(sb)); else mbar_arrive(BAR_P_FULL(sb));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
+      if (quarter == 0) HTRACE(4, j);
+      PROF_ADD(pe_work);
     }
+#ifdef RLVAE_TC_PROFILE
+    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 128)
+      printf("[h16 prof %d] exp group A per own super-block: wait S %lld  work %lld\n", (int)blockIdx.x,
+             pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2));
+#endif
   } else {
     // =========================================================== fold group: fp32 running total + output
     reg_inc<232>();
@@ -421,10 +464,18 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float total[NCOLS];
 #pragma unroll
     for (int i = 0; i < NCOLS; ++i) total[i] = 0.f;
+    long long pf_wait = 0, pf_work = 0;
+    (void)pf_wait; (void)pf_work;
+#ifdef RLVAE_TC_PROFILE
+    const long long pf0 = clock64();
+#endif
     for (int c = 0; c < num_chunks; ++c) {
+      PROF_T0();
       const int ab = c & 1;
       mbar_wait(BAR_CH_FULL(ab), (c >> 1) & 1);
       tc_fence_after();
+      if (quarter == 0) HTRACE(5, c * CB);
+      PROF_ADD(pf_wait);
       const uint32_t src = tmem_base + lane_addr + TM_ACC + ab * 160;
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
@@ -446,7 +497,15 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(ab)); else mbar_arrive(BAR_CH_FREE(ab)); }
       }
+      if (quarter == 0) HTRACE(6, c * CB);
+      PROF_ADD(pf_work);
     }
+#ifdef RLVAE_TC_PROFILE
+    const long long pf1 = clock64();
+    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
+      printf("[h16 prof %d] fold group per chunk: wait CH_FULL %lld  fold %lld | mainloop total %lld cycles\n",
+             (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf1 - pf0);
+#endif
     // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
     float* stage = reinterpret_cast<float*>(gbase + h16::OFF_M);
     const int t = threadIdx.x - 384;
@@ -500,6 +559,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         store_rows(fo.g_packed);
       }
     }
+#ifdef RLVAE_TC_PROFILE
+    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
+      printf("[h16 prof %d] epilogue %lld cycles\n", (int)blockIdx.x, clock64() - pf1);
+#endif
   }
 #undef MMA_H
 #undef COMMIT
@@ -531,7 +594,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 // TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2.
 // ==========================================================================================
 namespace g16 {
-constexpr int THREADS = 320;
+constexpr int THREADS = 384;        // TMA warp (C), MMA warp, 2 exp groups of 4 warps, TMA warps (M, Ct)
 constexpr int C_STAGES = 3;
 constexpr int M_STAGES = 4;
 constexpr int KSTEPS = 9;                           // 144 packed columns / 16
@@ -648,7 +711,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   float zrow[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     const int64_t r = row0 + prow;
     if (grp == 0) {
       zb = write_z_tiles(gbase, z, r, n, prow, alpha);
@@ -738,7 +801,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
   if (warp == 0) {
-    // =========================================================== TMA producer (warp-converged)
+    // =========================================================== TMA producer 1: centroid tiles + bias
     for (int j = 0; j < num_blocks; ++j) {
       const int cs = j % C_STAGES;
       mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
@@ -755,21 +818,27 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
       }
       __syncwarp();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int it = 2 * j + h, ms = it % M_STAGES;
-        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
-        if (elect_one()) {
-          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
-          const CUtensorMap* map = h == 0 ? &tm_mn_hi : &tm_mn_lo;
-          const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
-          const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
-          if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, 0);
-          else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, 0);
-        }
-        __syncwarp();
+    }
+  } else if (warp == 10) {
+    // =========================================================== TMA producer 2: M tiles (hi, lo alternate)
+    for (int it = 0; it < 2 * num_blocks; ++it) {
+      const int ms = it % M_STAGES, j = it >> 1;
+      mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
+        const CUtensorMap* map = (it & 1) == 0 ? &tm_mn_hi : &tm_mn_lo;
+        const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
+        const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
+        if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, 0);
+        else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, 0);
       }
-      // Ct tiles (hi, lo): [32 (pair: 16) rows x 64 centroids] as two 32-centroid atoms each
+      __syncwarp();
+    }
+  } else if (warp == 11) {
+    // =========================================================== TMA producer 3: Ct tiles (hi, lo):
+    // [32 (pair: 16) rows x 64 centroids] as two 32-centroid atoms each
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
       mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
       if (elect_one()) {
         if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
@@ -868,7 +937,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         PROF_ADD(pw_g3);
       }
 #ifdef RLVAE_TC_PROFILE
-      if (blockIdx.x == 0 && lane == 0)
+      if ((blockIdx.x == 0 || blockIdx.x == 4096) && lane == 0)
         printf("[g16 prof] MMA warp per super-block: total %lld | issue_st(j+1) %lld  wait CH_FREE/CT %lld  wait U_FULL %lld  issue G3 %lld\n",
                (clock64() - pl0) / num_blocks, pw_st / num_blocks, pw_chfree / num_blocks, pw_u / num_blocks,
                pw_g3 / num_blocks);
@@ -946,7 +1015,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       PROF_ADD(pe_fold);
     }
 #ifdef RLVAE_TC_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 64)
+    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 64)
       printf("[g16 prof] exp group A per own super-block: wait S|T %lld  work %lld  fold %lld\n",
              pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2), pe_fold / (num_blocks / 2));
 #endif

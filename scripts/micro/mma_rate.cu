@@ -108,31 +108,19 @@ void run(const char* name, int grid) {
 
 int main() {
   for (int grid : {148}) {
-    run<0, false, 256, 1>("tf32 SS N=256 1 acc", grid);
-    run<0, false, 128, 1>("tf32 SS N=128 1 acc", grid);
-    run<0, false, 128, 2>("tf32 SS N=128 2 acc", grid);
-    run<0, true, 128, 1>("tf32 TS N=128 1 acc", grid);
-    run<0, true, 128, 2>("tf32 TS N=128 2 acc", grid);
-    run<0, true, 256, 1>("tf32 TS N=256 1 acc", grid);
-    run<0, false, 32, 1>("tf32 SS N=32 1 acc", grid);
-    run<0, false, 32, 4>("tf32 SS N=32 4 acc", grid);
-    run<0, true, 32, 4>("tf32 TS N=32 4 acc", grid);
-    run<0, true, 16, 4>("tf32 TS N=16 4 acc", grid);
-    run<0, true, 48, 4>("tf32 TS N=48 4 acc", grid);
-    run<0, true, 64, 2>("tf32 TS N=64 2 acc", grid);
-    run<0, false, 64, 2>("tf32 SS N=64 2 acc", grid);
-    run<0, true, 80, 2>("tf32 TS N=80 2 acc", grid);
-    run<0, true, 96, 2>("tf32 TS N=96 2 acc", grid);
-    run<0, true, 112, 2>("tf32 TS N=112 2 acc", grid);
-    run<0, true, 144, 1>("tf32 TS N=144 1 acc", grid);
-    run<0, true, 192, 1>("tf32 TS N=192 1 acc", grid);
-    run<0, true, 32, 4, true>("tf32 TS N=32 4 acc ELECT", grid);
-    run<0, true, 64, 2, true>("tf32 TS N=64 2 acc ELECT", grid);
+    run<1, true, 144, 1, true>("f16 TS N=144 1 acc ELECT", grid);
+    run<1, true, 144, 2, true>("f16 TS N=144 2 acc ELECT", grid);
+    run<1, true, 128, 2, true>("f16 TS N=128 2 acc ELECT", grid);
+    run<1, true, 64, 2, true>("f16 TS N=64 2 acc ELECT", grid);
+    run<1, true, 32, 4, true>("f16 TS N=32 4 acc ELECT", grid);
+    run<1, false, 64, 2, true>("f16 SS N=64 2 acc ELECT", grid);
+    run<1, false, 144, 2, true>("f16 SS N=144 2 acc ELECT", grid);
     run<0, false, 64, 2, true>("tf32 SS N=64 2 acc ELECT", grid);
-    run<0, true, 128, 2, true>("tf32 TS N=128 2 acc ELECT", grid);
-    run<1, false, 256, 1>("bf16 SS N=256 1 acc", grid);
-    run<1, false, 128, 1>("bf16 SS N=128 1 acc", grid);
-    run<1, true, 128, 1>("bf16 TS N=128 1 acc", grid);
+    run<0, true, 64, 2, true>("tf32 TS N=64 2 acc ELECT", grid);
+    run<0, true, 32, 4, true>("tf32 TS N=32 4 acc ELECT", grid);
+    run<0, true, 32, 1, true>("tf32 TS N=32 1 acc ELECT", grid);
+    run<0, true, 144, 1, true>("tf32 TS N=144 1 acc ELECT", grid);
+    run<0, true, 80, 2, true>("tf32 TS N=80 2 acc ELECT", grid);
   }
   return 0;
 }
