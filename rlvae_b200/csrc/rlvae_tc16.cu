@@ -57,10 +57,11 @@ namespace h16 {
 constexpr int THREADS = 512;
 constexpr int C_STAGES = 3;
 constexpr int SP_BUFS = 3;
-constexpr int M_STAGES = 6;
+constexpr int M_STAGES = 3;                             // one stage = the hi AND the lo tile of a super-block
 constexpr int AHEAD = 3;
 constexpr int NCOLS = 144;                               // packed columns = MMA N of GEMM2
-constexpr uint32_t M_TILE_BYTES = NCOLS * 128;           // [144 rows x 64 centroids] fp16 (pair: 72 rows used)
+constexpr uint32_t M_HALF_BYTES = NCOLS * 128;           // [144 rows x 64 centroids] fp16 (pair: 72 rows used)
+constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;      // hi tile, then lo tile
 constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
 constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
@@ -73,6 +74,8 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
 constexpr uint32_t TM_SP = 0;        // + buf*64
 constexpr uint32_t TM_ACC = 192;     // + buf*160
+constexpr uint32_t TM_ZHI = 336;     // z (tf32 hi) 16 columns: A operand of GEMM1, in the hole between the accumulators
+constexpr uint32_t TM_ZLO = 496;     // z - hi, 16 columns
 constexpr float P_SHIFT = 14.f;      // P' = 2^14 P
 
 }  // namespace h16
@@ -202,7 +205,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS, OUT_LD = h16::OUT_LD;
-  constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, TM_SP = h16::TM_SP, TM_ACC = h16::TM_ACC;
+  constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, M_HALF_BYTES = h16::M_HALF_BYTES, TM_SP = h16::TM_SP,
+                     TM_ACC = h16::TM_ACC, TM_ZHI = h16::TM_ZHI, TM_ZLO = h16::TM_ZLO;
   constexpr float P_SHIFT = h16::P_SHIFT;
   constexpr int CB = 2;     // super-blocks per tensor-core accumulation chunk (compile-time: see the MMA issuer)
   (void)THREADS; (void)chunk_blocks;
@@ -264,29 +268,47 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 
   const int quarter = warp & 3;
   const int prow = quarter * 32 + lane;
+  tc_fence_before();
+  __syncthreads();            // TMEM base published (the exp threads store z into TMEM below)
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
   float zb = 0.f;
-  if (wg == 1) {          // exp group A writes the GEMM1 operand tiles
-    zb = write_z_tiles(gbase, z, row0 + prow, n, prow, alpha);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  } else if (wg == 2) {
+  if (wg == 1 || wg == 2) {
     const int64_t r = row0 + prow;
-    float nrm = 0.f;
+    float zv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zv[j] = 0.f;
     if (r < n) {
       const float4* src = reinterpret_cast<const float4*>(z + r * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 v = __ldg(src + q);
-        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+        const float4 v = __ldg(src + q);
+        zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
       }
     }
-    zb = -nrm * alpha;
+    float nrm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nrm = fmaf(zv[j], zv[j], nrm);
+    zb = -nrm * alpha + P_SHIFT;     // P' = 2^14 P, folded into the exponent
+    if (wg == 1) {                   // exp group A writes the A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float h = tf32_rna(zv[j]);
+        hi[j] = __float_as_uint(h);
+        lo[j] = __float_as_uint(zv[j] - h);
+      }
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      TMEM_ST16(tmem_base + lane_addr + TM_ZHI, hi);
+      TMEM_ST16(tmem_base + lane_addr + TM_ZLO, lo);
+      tmem_wait_st();
+    }
   }
-  zb += P_SHIFT;           // P' = 2^14 P, folded into the exponent
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
 
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
 #define MMA_H(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_G2, acc); else mma_ts_f16(d, a, b, IDESC_G2, acc); } while (0)
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
@@ -314,15 +336,19 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     } else if (warp == 2) {
       // =========================================================== TMA producer 2: M tiles, as far ahead
       // as the ring allows (its own warp: a stalled centroid stage must not delay the table stream)
-      for (int it = 0; it < 2 * num_blocks; ++it) {
-        const int ms = it % M_STAGES, jm = it >> 1;
-        mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+      for (int jm = 0; jm < num_blocks; ++jm) {
+        const int ms = jm % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((jm / M_STAGES) & 1) ^ 1);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
-          const CUtensorMap* map = (it & 1) == 0 ? &tm_mh_hi : &tm_mh_lo;
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * 2 * TILE_BYTES);
           const uint32_t dst = base + h16::OFF_M + ms * M_TILE_BYTES;
-          if (PAIR) tma_load_2d_pair(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
-          else tma_load_2d(dst, map, BAR_M_FULL(ms), jm * BK, row_cta);
+          if (PAIR) {
+            tma_load_2d_pair(dst, &tm_mh_hi, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d_pair(dst + M_HALF_BYTES, &tm_mh_lo, BAR_M_FULL(ms), jm * BK, row_cta);
+          } else {
+            tma_load_2d(dst, &tm_mh_hi, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d(dst + M_HALF_BYTES, &tm_mh_lo, BAR_M_FULL(ms), jm * BK, row_cta);
+          }
         }
         __syncwarp();
       }
@@ -332,14 +358,22 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       // that every stage index, TMEM address and almost every barrier parity is a compile-time
       // constant: the tensor pipe idles whenever this warp's own instruction stream is slower than
       // the MMAs it feeds (measured: 1.7k cycles per super-block with runtime div/mod vs 1.15k of MMA).
-      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
-      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
       const uint64_t c_desc0 = make_desc_sw128(base + h16::OFF_C);
       const uint64_t m_desc0 = make_desc_sw128(base + h16::OFF_M);
       auto gemm1 = [&](auto CSc, auto SBc) {
         constexpr int cs = decltype(CSc)::value, sb = decltype(SBc)::value;
         if (elect_one()) {
-          issue_gemm1<PAIR>(tmem_base + TM_SP + sb * 64, a1_desc, a2_desc, c_desc0 + ((cs * C_TILE_BYTES) >> 4));
+          // S = z_hi.c_hi + z_hi.c_lo + z_lo.c_hi (3xTF32), A operand from TMEM: N/2 = 32 cycles per MMA
+          // (the shared-memory A tile costs 48); a centroid row is [c_hi (16) | c_lo (16)] = 4 K-steps
+          constexpr uint32_t id1 = make_idesc(PAIR ? 256 : 128, BK);
+          const uint32_t d = tmem_base + TM_SP + sb * 64;
+          const uint64_t bc = c_desc0 + ((cs * C_TILE_BYTES) >> 4);
+          MMA_TS(d, tmem_base + TM_ZHI, bc, id1, 0);
+          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 2, id1, 1);
+          MMA_TS(d, tmem_base + TM_ZHI, bc + 4, id1, 1);
+          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 6, id1, 1);
+          MMA_TS(d, tmem_base + TM_ZLO, bc, id1, 1);
+          MMA_TS(d, tmem_base + TM_ZLO + 8, bc + 2, id1, 1);
           COMMIT(BAR_S_FULL(sb));
         }
         __syncwarp();
@@ -349,7 +383,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         constexpr int J = decltype(Jc)::value;
         constexpr int first = (J % CB) == 0, sb = J % SP_BUFS;
         const uint32_t ab = ((J / CB) & 1) ^ qodd;          // 6 blocks = 3 chunks: the accumulator parity flips every pass
-        constexpr int ms_hi = (2 * J) % M_STAGES, ms_lo = (2 * J + 1) % M_STAGES;
+        constexpr int ms = J % M_STAGES;
         if (first && j >= 2 * CB) {                       // fold group drained this accumulator
           mbar_wait(BAR_CH_FREE(ab), (free_phase >> ab) & 1u);
           free_phase ^= 1u << ab;
@@ -357,8 +391,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         tc_fence_after();
         const uint32_t p = tmem_base + TM_SP + sb * 64;     // k-step kk: P_hi at (kk>>1)*32 + (kk&1)*8, P_lo 16 further
         const uint32_t acc = tmem_base + TM_ACC + ab * 160;
-        const uint64_t bh = m_desc0 + ((ms_hi * M_TILE_BYTES) >> 4);
-        const uint64_t bl = m_desc0 + ((ms_lo * M_TILE_BYTES) >> 4);
+        const uint64_t bh = m_desc0 + ((ms * M_TILE_BYTES) >> 4);
+        const uint64_t bl = bh + (M_HALF_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -366,21 +400,16 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         }
         __syncwarp();
         // inputs of the NEXT steps, waited for behind queued MMAs (normally long complete)
-        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((2 * J + 2) % M_STAGES), ((2 * J + 2) / M_STAGES) & 1);
+        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((J + 1) % M_STAGES), ((J + 1) / M_STAGES) & 1);
         if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             MMA_H(acc, p + (kk >> 1) * 32 + 16 + (kk & 1) * 8, bh + 2 * kk, 1);
-          COMMIT(BAR_M_EMPTY(ms_hi));
-        }
-        __syncwarp();
-        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((2 * J + 3) % M_STAGES), ((2 * J + 3) / M_STAGES) & 1);
-        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bl + 2 * kk, 1);
-          COMMIT(BAR_M_EMPTY(ms_lo));
+          COMMIT(BAR_M_EMPTY(ms));
           if ((J % CB) == CB - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(ab));
         }
         __syncwarp();
@@ -395,9 +424,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (1 < num_blocks) { mbar_wait(BAR_C_FULL(1), 0); tc_fence_after(); gemm1(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}); }
       if (2 < num_blocks) { mbar_wait(BAR_C_FULL(2), 0); tc_fence_after(); gemm1(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
       mbar_wait(BAR_M_FULL(0), 0);
-      mbar_wait(BAR_M_FULL(1), 0);
       mbar_wait(BAR_P_FULL(0), 0);
-      static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 12 % M_STAGES == 0 && AHEAD == 3,
+      static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 6 % M_STAGES == 0 && AHEAD == 3,
                     "the 6x unrolled issue loop assumes these periods");
       uint32_t qodd = 0;
       for (int j0 = 0; j0 < num_blocks; j0 += 6, qodd ^= 1u) {
@@ -565,6 +593,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #endif
   }
 #undef MMA_H
+#undef MMA_TS
 #undef COMMIT
 
   tc_fence_before();
