@@ -620,16 +620,18 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 //   GEMM3   OUT[128 x 32] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo   (3xTF32; Ct = [c^T ; 1 ; 0])
 // OUT accumulates in two alternating chunk accumulators (2 super-blocks each) that the exp groups
 // fold into fp32 registers.  out = scale 2^-(eU+eM) (OUT[:, :16] - z OUT[:, 16]).
-// TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2.
+// TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2,
+//       [464,496) z_hi | z_lo (TF32 split, A operand of GEMM1).
 // ==========================================================================================
 namespace g16 {
 constexpr int THREADS = 384;        // TMA warp (C), MMA warp, 2 exp groups of 4 warps, TMA warps (M, Ct)
-constexpr int C_STAGES = 3;
-constexpr int M_STAGES = 4;
+constexpr int C_STAGES = 4;
+constexpr int M_STAGES = 2;                          // one stage = hi AND lo tile of a super-block
 constexpr int KSTEPS = 9;                           // 144 packed columns / 16
 constexpr uint32_t CT_TILE_BYTES = 2 * 32 * 128;    // [32 rows x 64 centroids] fp32 = 2 atoms of 32 centroids
-constexpr uint32_t M_TILE_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
-constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
+constexpr uint32_t M_HALF_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
+constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;
+constexpr uint32_t OFF_C = 0;                       // (z lives in TMEM: no A tiles in shared memory)
 constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_M = OFF_CT + C_STAGES * 2 * CT_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
@@ -638,7 +640,7 @@ constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 9;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400;
+constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400, TM_ZHI = 464, TM_ZLO = 480;
 constexpr int RED_LD = 36;
 }  // namespace g16
 
@@ -657,9 +659,11 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
                        float scale /* includes 2^-eM */, float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
-  constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES, OFF_C = g16::OFF_C,
+  constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
+                     M_HALF_BYTES = g16::M_HALF_BYTES, OFF_C = g16::OFF_C,
                      OFF_CT = g16::OFF_CT, OFF_M = g16::OFF_M, OFF_BIAS = g16::OFF_BIAS,
-                     TM_UHI = g16::TM_UHI, TM_ULO = g16::TM_ULO, TM_ST = g16::TM_ST, TM_OUT = g16::TM_OUT;
+                     TM_UHI = g16::TM_UHI, TM_ULO = g16::TM_ULO, TM_ST = g16::TM_ST, TM_OUT = g16::TM_OUT,
+                     TM_ZHI = g16::TM_ZHI, TM_ZLO = g16::TM_ZLO;
   constexpr int CHUNK = 2;             // super-blocks per OUT chunk accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -742,10 +746,6 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
   if (warp >= 2 && warp < 10) {
     const int64_t r = row0 + prow;
-    if (grp == 0) {
-      zb = write_z_tiles(gbase, z, r, n, prow, alpha);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     if (r < n) {
       const float4* src = reinterpret_cast<const float4*>(z + r * 16);
       float nrm = 0.f;
@@ -755,7 +755,18 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
         nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
       }
-      if (grp == 1) zb = -nrm * alpha;
+      zb = -nrm * alpha;
+    }
+    if (grp == 0) {             // A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
+      uint32_t zh[16], zl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float hh = tf32_rna(zrow[j]);
+        zh[j] = __float_as_uint(hh);
+        zl[j] = __float_as_uint(zrow[j] - hh);
+      }
+      TMEM_ST16(tmem_base + lane_addr + TM_ZHI, zh);
+      TMEM_ST16(tmem_base + lane_addr + TM_ZLO, zl);
     }
     // ---- U' = 2^eU Ut, split into fp16 hi | lo, resident in TMEM as the A operand of the T GEMM.
     // group 0 converts packed columns [0,64), group 1 [64,144); both scan the whole row for the scale.
@@ -850,16 +861,20 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
   } else if (warp == 10) {
     // =========================================================== TMA producer 2: M tiles (hi, lo alternate)
-    for (int it = 0; it < 2 * num_blocks; ++it) {
-      const int ms = it % M_STAGES, j = it >> 1;
-      mbar_wait(BAR_M_EMPTY(ms), ((it / M_STAGES) & 1) ^ 1);
+    for (int j = 0; j < num_blocks; ++j) {
+      const int ms = j % M_STAGES;
+      mbar_wait(BAR_M_EMPTY(ms), ((j / M_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * TILE_BYTES);
-        const CUtensorMap* map = (it & 1) == 0 ? &tm_mn_hi : &tm_mn_lo;
+        if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * 2 * TILE_BYTES);
         const uint32_t dst = base + OFF_M + ms * M_TILE_BYTES;
         const int row = j * BK + (PAIR ? 32 * (int)rank : 0);
-        if (PAIR) tma_load_3d_pair(dst, map, BAR_M_FULL(ms), 0, row, 0);
-        else tma_load_3d(dst, map, BAR_M_FULL(ms), 0, row, 0);
+        if (PAIR) {
+          tma_load_3d_pair(dst, &tm_mn_hi, BAR_M_FULL(ms), 0, row, 0);
+          tma_load_3d_pair(dst + M_HALF_BYTES, &tm_mn_lo, BAR_M_FULL(ms), 0, row, 0);
+        } else {
+          tma_load_3d(dst, &tm_mn_hi, BAR_M_FULL(ms), 0, row, 0);
+          tma_load_3d(dst + M_HALF_BYTES, &tm_mn_lo, BAR_M_FULL(ms), 0, row, 0);
+        }
       }
       __syncwarp();
     }
@@ -889,66 +904,65 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   } else if (warp == 1) {
     // =========================================================== MMA issuer (warp-converged; pair: leader only)
     if (leader) {
-      const uint64_t a1_desc = make_desc_sw128(base + OFF_A1);
-      const uint64_t a2_desc = make_desc_sw128(base + OFF_A2);
-      // [GEMM1, T-GEMM] of super-block j into S|T buffer j&1
-      auto issue_st = [&](int j) {
-        const int cs = j % C_STAGES, sb = j & 1;
-        const int ms_hi = (2 * j) % M_STAGES, ms_lo = (2 * j + 1) % M_STAGES;
-        mbar_wait(BAR_C_FULL(cs), (j / C_STAGES) & 1);
-        mbar_wait(BAR_M_FULL(ms_hi), ((2 * j) / M_STAGES) & 1);
+      // Unrolled 4x (2 S|T buffers, 2 OUT chunks of 2 blocks, 4 C stages, 2 M stages): stage indices,
+      // TMEM addresses and most barrier parities are compile-time constants (see the forward kernel).
+      static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loop assumes these periods");
+      const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
+      const uint64_t m_desc0 = make_desc_sw128(base + OFF_M);
+      const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
+      constexpr uint32_t ID1 = make_idesc(PAIR ? 256 : 128, BK);
+      // [GEMM1, T-GEMM] of the block with residue JJ = j mod 4 into S|T buffer j&1
+      auto issue_st = [&](auto Jc, const uint32_t c_parity) {
+        constexpr int JJ = decltype(Jc)::value;
+        constexpr int cs = JJ % C_STAGES, sb = JJ & 1, ms = JJ % M_STAGES;
+        mbar_wait(BAR_C_FULL(cs), c_parity);
+        mbar_wait(BAR_M_FULL(ms), (JJ / M_STAGES) & 1);
         tc_fence_after();
         const uint32_t s_t = tmem_base + TM_ST + sb * 128;
         const uint32_t t_t = s_t + 64;
-        const uint64_t bh = make_desc_sw128(base + OFF_M + ms_hi * M_TILE_BYTES);
-        const uint64_t bl = make_desc_sw128(base + OFF_M + ms_lo * M_TILE_BYTES);
+        const uint64_t bc = c_desc0 + ((cs * C_TILE_BYTES) >> 4);
+        const uint64_t bh = m_desc0 + ((ms * M_TILE_BYTES) >> 4);
+        const uint64_t bl = bh + (M_HALF_BYTES >> 4);
         if (elect_one()) {
-          issue_gemm1<PAIR>(s_t, a1_desc, a2_desc, make_desc_sw128(base + OFF_C + cs * C_TILE_BYTES));
+          MMA_TS(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
+          MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 2, ID1, 1);
+          MMA_TS(s_t, tmem_base + TM_ZHI, bc + 4, ID1, 1);
+          MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 6, ID1, 1);
+          MMA_TS(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
+          MMA_TS(s_t, tmem_base + TM_ZLO + 8, bc + 2, ID1, 1);
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
             MMA_T16(t_t, tmem_base + TM_UHI + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), kk > 0);
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
             MMA_T16(t_t, tmem_base + TM_ULO + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), 1);
-          COMMIT(BAR_M_EMPTY(ms_hi));
-        }
-        __syncwarp();
-        mbar_wait(BAR_M_FULL(ms_lo), ((2 * j + 1) / M_STAGES) & 1);
-        tc_fence_after();
-        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
             MMA_T16(t_t, tmem_base + TM_UHI + 8 * kk, bl + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), 1);
-          COMMIT(BAR_M_EMPTY(ms_lo));
+          COMMIT(BAR_M_EMPTY(ms));
           COMMIT(BAR_ST_FULL(sb));
         }
         __syncwarp();
       };
-      long long pw_st = 0, pw_chfree = 0, pw_u = 0, pw_g3 = 0;
-      (void)pw_st; (void)pw_chfree; (void)pw_u; (void)pw_g3;
-#ifdef RLVAE_TC_PROFILE
-      const long long pl0 = clock64();
-#endif
-      issue_st(0);
-      for (int j = 0; j < num_blocks; ++j) {
-        PROF_T0();
+      uint32_t free_phase = 0;     // bit b: parity of the next CH_FREE(b) completion to wait for
+      auto block = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
+        constexpr int J = decltype(Jc)::value;
         // S|T(j+1) first: its buffer was released by GEMM3(j-1), already queued ahead in the pipe
-        if (j + 1 < num_blocks) issue_st(j + 1);
-        PROF_ADD(pw_st);
-        const int cs = j % C_STAGES, sb = j & 1;
-        const int chunk = j / CHUNK;
-        const int first = (j % CHUNK) == 0;
-        if (first && chunk >= 2) mbar_wait(BAR_CH_FREE(chunk & 1), ((chunk >> 1) - 1) & 1);
-        mbar_wait(BAR_CT_FULL(cs), (j / C_STAGES) & 1);
-        PROF_ADD(pw_chfree);
-        mbar_wait(BAR_U_FULL(sb), (j >> 1) & 1);
-        PROF_ADD(pw_u);
+        if (j + 1 < num_blocks) issue_st(std::integral_constant<int, (J + 1) % 4>{}, (qodd + (J + 1) / 4) & 1u);
+        constexpr int cs = J % C_STAGES, sb = J & 1, cb = (J >> 1) & 1;
+        constexpr int first = (J % CHUNK) == 0;
+        if (first && j >= 2 * CHUNK) {
+          mbar_wait(BAR_CH_FREE(cb), (free_phase >> cb) & 1u);
+          free_phase ^= 1u << cb;
+        }
+        mbar_wait(BAR_CT_FULL(cs), qodd);
+        mbar_wait(BAR_U_FULL(sb), (J >> 1) & 1);
         tc_fence_after();
         const uint32_t u_hi = tmem_base + TM_ST + sb * 128;
         const uint32_t u_lo = u_hi + 64;
-        const uint32_t acc = tmem_base + TM_OUT + (chunk & 1) * 32;
-        const uint64_t ch = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES);
-        const uint64_t cl = make_desc_sw128(base + OFF_CT + cs * 2 * CT_TILE_BYTES + CT_TILE_BYTES);
+        const uint32_t acc = tmem_base + TM_OUT + cb * 32;
+        const uint64_t ch = ct_desc0 + ((cs * 2 * CT_TILE_BYTES) >> 4);
+        const uint64_t cl = ch + (CT_TILE_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
@@ -960,17 +974,17 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           for (int kk = 0; kk < 8; ++kk)
             MMA_TS(acc, u_hi + 8 * kk, cl + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
           COMMIT(BAR_CT_EMPTY(cs));
-          if ((j % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(chunk & 1));
+          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(cb));
         }
         __syncwarp();
-        PROF_ADD(pw_g3);
+      };
+      issue_st(std::integral_constant<int, 0>{}, 0u);
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 4, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3)
+#undef RLVAE_BLK
       }
-#ifdef RLVAE_TC_PROFILE
-      if ((blockIdx.x == 0 || blockIdx.x == 4096) && lane == 0)
-        printf("[g16 prof] MMA warp per super-block: total %lld | issue_st(j+1) %lld  wait CH_FREE/CT %lld  wait U_FULL %lld  issue G3 %lld\n",
-               (clock64() - pl0) / num_blocks, pw_st / num_blocks, pw_chfree / num_blocks, pw_u / num_blocks,
-               pw_g3 / num_blocks);
-#endif
       if (elect_one()) COMMIT(BAR_DONE);
       __syncwarp();
     }
