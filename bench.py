@@ -9,7 +9,8 @@ one pass of the hot path over one batch of N synthetic points.  Under torchrun e
 evaluates its own N points against replicated tables (weak scaling, no data-path collective,
 SURVEY.md §8e); `value` is total evals over all ranks / max-over-ranks device time.
 
-Extra keys: `roofline` (dominant kernel = the tcgen05 weighted-sum kernel, tensor bound),
+Extra keys: `roofline` (the fused metric + log-det tcgen05 kernel, tensor bound, timed alone against
+MEASURED_PEAKS.json's bf16 burst rate; `roofline_gradient_kernel` is the same for the gradient kernel),
 `cpu_baseline` (the CPU oracle port on a bounded sample, rank 0 / N=1 only), `e2e` (host-buffer
 API: pinned H2D of z, evaluation, D2H of log det + grad, per step), `hmc` (config[2]: chain
 leapfrog steps/s, 2^20 chains x 20 leapfrog), `clocks`, `gpu_launches`.
@@ -122,6 +123,30 @@ def measure_tf32_peak(dev):
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
+def measure_bf16_rate(dev):
+    """cuBLAS bf16 dense GEMM in THIS run (8192^3, best of 8): same-conditions cross-check of the
+    MEASURED_PEAKS.json burst figure."""
+    a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+    best = 1e9
+    for i in range(11):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); a @ b; e1.record(); e1.synchronize()
+        if i >= 3:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed `ncu --set full` capture (profiles/r1_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
 def cpu_reference_rate(sm, budget_s=12.0, chunk=128, max_points=4096, threads=None):
     """The reference algorithm (CPU oracle port: [n,K,d,d] materialisation + LU inverse + slogdet +
     autograd) on the host cores: evals/s over a bounded sample of the same workload."""
@@ -220,6 +245,7 @@ def run_ours(args):
     for _ in range(W):
         step()
     barrier()
+    _capi.lib().rlvae_launch_count(1)        # reset: count the kernels launched inside the timed region
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -232,6 +258,7 @@ def run_ours(args):
         step()
         ev[i][1].record()
     barrier()
+    launches_timed = int(_capi.lib().rlvae_launch_count(0))
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -239,50 +266,76 @@ def run_ours(args):
     ms_per_step = dev_ms / S
     value = world * n / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel alone (tcgen05 weighted sum): CUDA events around the launch
-    ginv = out['ginv']
-    packed_path = path_name == 'tensor' and tab.symmetric
-    kev = []
-    for i in range(3 + 5):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        if packed_path:     # the tcgen05 kernel alone: symmetric tables -> packed [N,144] output
-            _capi.lib().rlvae_inverse_metric_packed(tab.handle, _capi._ptr(z), n, _capi._ptr(ginv),
-                                                    _capi._stream(z))
-        else:
-            _capi.lib().rlvae_inverse_metric(tab.handle, _capi._ptr(z), n, _capi._ptr(ginv), None,
-                                             _capi.PATH_AUTO, _capi._stream(z))
-        e1.record(); e1.synchronize()
-        if i >= 3:
-            kev.append(e0.elapsed_time(e1))
-    k_ms = sum(kev) / len(kev)
+    # ---- the two tensor kernels of the step, each timed alone (CUDA events around the launch, L2 flushed)
+    lib = _capi.lib()
+    sym_tensor = path_name == 'tensor' and tab.symmetric
+    work = torch.empty(int(lib.rlvae_metric_eval_workspace(n, D)) // 4, device=dev, dtype=torch.float32)
+    ld_buf = torch.empty(n, device=dev)
+    gr_buf = torch.empty(n, D, device=dev)
+
+    def time_launch(fn, reps=5):
+        ts = []
+        for i in range(3 + reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    st = _capi._stream(z)
+    # fused metric + log-det kernel: z -> packed G^-1, packed G, log det G (what rlvae_metric_eval runs first)
+    def _ok(rc):
+        assert rc == 0, lib.rlvae_last_error()
+
+    fwd_ms = time_launch(lambda: _ok(lib.rlvae_metric_eval(tab.handle, _capi._ptr(z), n, None, None,
+                                                           _capi._ptr(ld_buf), None, _capi._ptr(work),
+                                                           _capi.PATH_AUTO, st)))
+    # gradient kernel alone: contraction with the packed G the fused kernel left in the workspace
+    g_src = out['g'] if 'g' in out and out['g'] is not None else None
+    if g_src is None:
+        g_src = mt.evaluate(z[: 1 << 16], want_ginv=False, want_g=True, want_logdet=False)['g'].repeat(n >> 16, 1, 1)
+    grad_ms = time_launch(lambda: _ok(lib.rlvae_metric_grad(tab.handle, _capi._ptr(z), _capi._ptr(g_src), n,
+                                                            -2.0 / float(tab.temperature) ** 2,
+                                                            _capi._ptr(gr_buf), _capi.PATH_AUTO, st)))
+    del g_src
     peaks, peak_src = measured_peaks()
     line = {}
-    roof = None
+    roof = roof_grad = None
     if rank == 0:
-        f_alg = n * 2 * K * D * (D + 1)                       # per launch, forward only
-        if path_name == 'tensor':
-            tf32_peak = measure_tf32_peak(dev)
-            ach = 3 * f_alg / (k_ms * 1e-3) / 1e12            # 3xTF32: three tensor MACs per fp32 MAC
-            # tensor work actually issued: GEMM2 columns (144 packed / 256 dense) + GEMM1 (N=64, K=48)
-            cols = 2 * (80 + 64) / 2 if packed_path else 256
-            kp = tab.Kpad
-            issued = n * 2 * kp * (3 * cols + 2 * 48) / (k_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'inverse_metric_tc_kernel', 'achieved': ach,
-                    'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak, 'traffic': None,
-                    'tensor_issued_tflops': issued, 'tensor_issued_frac': issued / tf32_peak,
-                    'achieved_fp32_equiv_tflops': f_alg / (k_ms * 1e-3) / 1e12, 'kernel_ms': k_ms,
-                    'note': ('algorithmic flops count dense M (2Kd(d+1) per point, SURVEY.md 8d); the '
-                             'tables are symmetric, so the kernel accumulates 136 of the 256 columns '
-                             '(144/256 of the dense tensor work is issued)') if packed_path else
-                            'dense 256-column kernel',
-                    'peak_source': 'cuBLAS TF32 8192^3 best-of-8 measured in this run (MEASURED_PEAKS.json '
-                                   f'({peak_src}) holds bf16 only: {peaks.get("bf16_tflops")} TF/s burst)'}
+        tf32_rate = measure_tf32_peak(dev)
+        bf16_rate = measure_bf16_rate(dev)
+        peak = float(peaks['bf16_tflops'])          # burst figure: each kernel is timed alone
+        if sym_tensor:
+            # Tensor work in fp16-equivalent flops: a TF32 MAC costs two fp16 MACs of pipe time (the
+            # measured TF32 GEMM rate is half the bf16 one).  ALGORITHMIC = symmetric tables, no padding:
+            #   forward : 3 passes x 2K x (136 weighted-sum columns [fp16] + 2 x 16 distance dims [TF32])
+            #   gradient: 3 passes x 2K x (136 [fp16] + 2 x 16 [TF32] + 2 x 17 final contraction [TF32])
+            f_fwd = n * 3 * 2 * K * (136 + 2 * 16)
+            f_grad = n * 3 * 2 * K * (136 + 2 * 16 + 2 * 17)
+            issued_fwd = n * 3 * 2 * tab.Kpad * (144 + 2 * 16)
+            issued_grad = n * 3 * 2 * tab.Kpad * (144 + 2 * 16 + 2 * 32)
+            note = ('fp16-equivalent tensor flops (TF32 MACs weighted x2: measured TF32 GEMM rate %.0f TF/s vs '
+                    'bf16 %.0f TF/s in this run); symmetric tables -> 136 packed columns; dense-M definition '
+                    'of SURVEY.md 8d would read %.0f TF/s fp32-equivalent' )
+            ach = f_fwd / (fwd_ms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': 'inverse_metric_h16_kernel (fused G^-1 + Cholesky log det)',
+                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                    'traffic': ncu_traffic('inverse_metric_h16_kernel'), 'kernel_ms': fwd_ms,
+                    'issued': issued_fwd / (fwd_ms * 1e-3) / 1e12,
+                    'peak_source': f'MEASURED_PEAKS.json bf16_tflops burst ({peak_src})',
+                    'same_run_cublas': {'bf16_tflops': bf16_rate, 'tf32_tflops': tf32_rate},
+                    'note': note % (tf32_rate, bf16_rate, n * 2 * K * D * (D + 1) / (fwd_ms * 1e-3) / 1e12)}
+            achg = f_grad / (grad_ms * 1e-3) / 1e12
+            roof_grad = {'bound': 'tensor', 'kernel': 'metric_grad_h16_kernel', 'achieved': achg, 'peak': peak,
+                         'unit': 'TFLOP/s', 'frac': achg / peak, 'traffic': ncu_traffic('metric_grad_h16_kernel'),
+                         'kernel_ms': grad_ms, 'issued': issued_grad / (grad_ms * 1e-3) / 1e12}
         else:
-            ach = f_alg / (k_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'inverse_metric_direct_kernel', 'achieved': ach,
-                    'peak': None, 'unit': 'TFLOP/s', 'frac': None, 'traffic': None, 'kernel_ms': k_ms}
+            f_alg = n * 2 * K * D * (D + 1)
+            ach = (3 if path_name == 'tensor' else 1) * f_alg / (fwd_ms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': 'inverse_metric_tc_kernel' if path_name == 'tensor'
+                    else 'inverse_metric_direct_kernel', 'achieved': ach, 'peak': tf32_rate, 'unit': 'TFLOP/s',
+                    'frac': ach / tf32_rate, 'traffic': None, 'kernel_ms': fwd_ms}
 
     # ---- end to end through the host-buffer API (pinned H2D of z, D2H of log det + grad)
     he = HostEvaluator(mt, chunk=1 << 17, want_grad=True)
@@ -331,18 +384,17 @@ def run_ours(args):
                    'sample': f'{npts} points of the same workload in 128-point chunks, {dt:.1f} s; CPU oracle '
                              'port of the reference eager PyTorch path (G^-1, log det via inv+slogdet, '
                              'grad by autograd)'}
-        launches = 4 if path_name == 'tensor' or True else 4   # metric + batched_inverse + negate + grad
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': S, 'warmup': W,
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32 (3xTF32 tensor products, fp32 accumulate)' if path_name == 'tensor' else 'f32',
+                'dtype': 'f32 (split-fp16 / 3xTF32 tensor products with fp32 accumulate: fp32-level accuracy)' if path_name == 'tensor' else 'f32',
                 'data': 'synthetic',
                 'config': {'workload': f'G^-1 + log det G + grad_z log det G, d={D}, K={K}, N=2^20 per GPU '
                                        '(BASELINE.json configs[1])', 'points_per_gpu': n, 'path': path_name,
                            'parallelism': f'points sharded over {world} GPU(s), tables replicated',
                            'l2': 'L2 flushed (256 MB write) before every timed step; each step also '
                                  'writes >2 GB of outputs'},
-                'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'hmc': hmc, 'clocks': clocks,
-                'gpu_launches': launches * S,
+                'roofline': roof, 'roofline_gradient_kernel': roof_grad, 'cpu_baseline': cpu, 'e2e': e2e, 'hmc': hmc, 'clocks': clocks,
+                'gpu_launches': launches_timed,
                 'tflops_fp32_equiv': value * flops_per_eval(True) / 1e12}
         print(json.dumps(line))
     if world > 1:

@@ -45,6 +45,9 @@ enum {
 
 const char* rlvae_last_error(void);
 int         rlvae_abi_version(void);
+/* number of CUDA kernels this library has launched since load (or since the last reset != 0);
+ * bench.py's gpu_launches */
+long long   rlvae_launch_count(int reset);
 
 /* ---- tables: replaces MetricTensor.load_pretrained's buffers --------------------------------
  * ref: src/models/components/metric_tensor.py:59-96 (centroids [K,d], metric_matrices [K,d,d],

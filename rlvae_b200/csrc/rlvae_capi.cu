@@ -1,5 +1,6 @@
 // extern "C" entry points of librlvae_b200.so (declared in include/rlvae_b200.h) plus the
 // table-packing kernels behind rlvae_tables_create.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -12,6 +13,8 @@ namespace rlvae {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launch_count{0};
+void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 void pythae_cache_release(const rlvae_tables* t);
 
 __device__ __forceinline__ float tf32_hi(float x) {
@@ -177,7 +180,7 @@ __global__ void negate_copy_kernel(const float* __restrict__ x, float* __restric
 }
 static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
   negate_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, n);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -204,6 +207,9 @@ extern "C" {
 
 const char* rlvae_last_error(void) { return g_last_error.c_str(); }
 int rlvae_abi_version(void) { return 1; }
+long long rlvae_launch_count(int reset) {
+  return reset ? g_launch_count.exchange(0) : g_launch_count.load();
+}
 
 int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const float* matrices,
                         int n_centroids, int latent_dim, float temperature, float regularization,

@@ -127,7 +127,7 @@ int launch_inverse_metric_direct(const rlvae_tables* t, const float* z, int64_t 
   }
   inverse_metric_direct_kernel<<<grid, DM_THREADS, smem, s>>>(z, t->c, t->M, n, t->K, t->d, ncols,
                                                              t->T2, t->lambda, ginv);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -260,7 +260,7 @@ int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float
   dim3 grid((unsigned)((n + DG_BM - 1) / DG_BM));
   metric_grad_direct_kernel<<<grid, DG_THREADS, dg_smem_bytes(t->d), s>>>(
       z, u, t->c, t->M, n, t->K, t->d, t->T2, scale, out);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -326,7 +326,7 @@ int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float
     if (g_pythae.aug) cudaFree(g_pythae.aug);
     RLVAE_CUDA_OK(cudaMalloc(&g_pythae.aug, sizeof(float) * (size_t)t->K * ncols));
     build_aug_table_kernel<<<t->K, 128, 0, s>>>(t->c, t->M, t->K, d, g_pythae.aug);
-    RLVAE_CUDA_OK(cudaGetLastError());
+    RLVAE_LAUNCH_OK();
     g_pythae.owner = t;
   }
   if (g_pythae.scratch_elems < n * ncols) {
@@ -347,11 +347,11 @@ int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float
   }
   inverse_metric_direct_kernel<<<grid, DM_THREADS, dm_smem_bytes(d), s>>>(
       z, t->c, g_pythae.aug, n, t->K, d, ncols, t->T2, t->lambda, g_pythae.scratch);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   const int64_t total = n * d;
   pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_pythae.scratch, z, g, n, d,
                                                                        t->lambda, t->T2, out);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -412,7 +412,7 @@ int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* 
 #undef CASE
     default: RLVAE_REQUIRE(false, "nearest2: unsupported latent_dim (1,2,3,4,8,16,32,64)");
   }
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 

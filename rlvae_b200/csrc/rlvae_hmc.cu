@@ -107,7 +107,7 @@ int launch_hmc_begin(const float* z, const float* gamma, const float* diag_g, co
   hmc_begin_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(z, gamma, diag_g, logabsdet, sign,
                                                                grad_exact, n, d, b0, eps, lambda, T2,
                                                                grad_mode, rho_half, z_new, h0);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -120,7 +120,7 @@ int launch_hmc_step(const float* diag_g, const float* logabsdet, const float* si
   hmc_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(
       diag_g, logabsdet, sign, grad_exact, n, d, eps, lambda, T2, grad_mode, scale, last, rho_half,
       z_cur, z_prev, acc, h0, h1, alpha, moves, z_out);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -130,7 +130,7 @@ int launch_axpy_grad_modular(float* z, const float* diag_g, int64_t n, int d, fl
   if (total == 0) return 0;
   axpy_grad_modular_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, diag_g, total, step,
                                                                            lambda, T2);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 

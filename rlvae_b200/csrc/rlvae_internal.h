@@ -28,6 +28,19 @@ void set_error(const std::string& msg);
     }                                                                                    \
   } while (0)
 
+// every kernel launch of the hot path goes through one of these two (rlvae_launch_count reports the total)
+void count_launch();
+#define RLVAE_LAUNCH_OK()                    \
+  do {                                       \
+    ::rlvae::count_launch();                 \
+    RLVAE_CUDA_OK(cudaGetLastError());       \
+  } while (0)
+#define RLVAE_LAUNCH_EX(expr)                \
+  do {                                       \
+    ::rlvae::count_launch();                 \
+    RLVAE_CUDA_OK(expr);                     \
+  } while (0)
+
 constexpr int kMaxLatentDim = 64;
 constexpr int kKPad = 128;  // centroid tables are zero-padded to a multiple of this
 

@@ -203,7 +203,7 @@ int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* 
 #undef CASE
     default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be a power of two <= 64");
   }
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -213,7 +213,7 @@ int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv
   unsigned grid = (unsigned)((n + PP<16>::MATS - 1) / PP<16>::MATS);
   batched_inverse_kernel<16, true><<<grid, PP<16>::THREADS, 0, s>>>(a_packed, n, inv, logabsdet, sign,
                                                                      diag_inv, transpose_inv);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -357,7 +357,7 @@ int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, floa
   const unsigned grid = (unsigned)((n + sym16::THREADS - 1) / sym16::THREADS);
   sym16_cholesky_kernel<<<grid, sym16::THREADS, 0, s>>>(a_packed, n, g_packed, logabsdet, lad_scale, sign,
                                                          diag_g, fail_ws, fail_ws + 1);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
 }
 
@@ -370,7 +370,7 @@ int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, flo
   const unsigned fgrid = (unsigned)(groups < 1184 ? groups : 1184);
   batched_inverse_kernel<16, true><<<fgrid, PP<16>::THREADS, 0, s>>>(
       a_packed, n, nullptr, logabsdet, sign, diag_g, 0, fail_ws + 1, fail_ws, g_packed, lad_scale);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -386,7 +386,7 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
   if (n == 0) return 0;
   const int64_t total = n * 256;
   unpack_sym16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a_packed, n, full);
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 
@@ -471,7 +471,7 @@ int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float 
 #undef CASE
     default: RLVAE_REQUIRE(false, "chol_apply: latent_dim must be a power of two <= 64");
   }
-  RLVAE_CUDA_OK(cudaGetLastError());
+  RLVAE_LAUNCH_OK();
   return 0;
 }
 

@@ -1374,7 +1374,7 @@ static int launch_fwd(const CUtensorMap& c, const CUtensorMap& hi, const CUtenso
     chunk_blocks = (e != nullptr && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : tc::CHUNK_BLOCKS;
   }
   const int cb = chunk_blocks;
-  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, cbias, n, nb, cb, alpha, lambda, out));
+  RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, cbias, n, nb, cb, alpha, lambda, out));
   return 0;
 }
 
@@ -1428,7 +1428,7 @@ static int launch_grad(const CUtensorMap& c, const CUtensorMap& hi, const CUtens
   const float* cnat = t->c;
   const float* cbias = t->cbias;
   const int nb = t->Kpad / tc::BK;
-  RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, u, cnat, cbias, n, nb, alpha, scale, out, u_packed));
+  RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, c, hi, lo, z, u, cnat, cbias, n, nb, alpha, scale, out, u_packed));
   return 0;
 }
 
@@ -1460,10 +1460,10 @@ static int launch_grad_sym(const rlvae_tables* t, const float* z, const float* u
   const float* cbias = t->cbias;
   const int nb = t->Kpad / tc::BK;
   if (PAIR) {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t->tm_ct2_hi,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns2_hi, t->tm_mns2_lo, t->tm_ct2_hi,
                                      t->tm_ct2_lo, z, u, cbias, n, nb, alpha, scale, out, u_packed));
   } else {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t->tm_ct_hi,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mns_hi, t->tm_mns_lo, t->tm_ct_hi,
                                      t->tm_ct_lo, z, u, cbias, n, nb, alpha, scale, out, u_packed));
   }
   return 0;

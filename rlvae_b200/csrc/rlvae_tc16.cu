@@ -1208,10 +1208,10 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   }
   const int cb = chunk_blocks;
   if (PAIR) {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, cb,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, cb,
                                      alpha, lambda, out_scale, fo));
   } else {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, cb,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, cb,
                                      alpha, lambda, out_scale, fo));
   }
   return 0;
@@ -1267,10 +1267,10 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const int nb = t->Kpad / tc::BK;
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   if (PAIR) {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct2_hi,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct2_hi,
                                      t->tm_ct2_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
   } else {
-    RLVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct_hi,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct_hi,
                                      t->tm_ct_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
   }
   return 0;
