@@ -24,3 +24,11 @@ for _ in range(steps):
     out = mt.evaluate(z, want_ginv=True, want_logdet=True, want_grad=True, out=out)
 torch.cuda.synchronize()
 print('ok', float(out['logdet_g'][:8].sum()))
+if len(sys.argv) > 3 and sys.argv[3] == 'hmc':     # plus one short HMC iteration (2 leapfrog steps)
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    from rlvae_b200.synthetic import make_hmc_streams
+    z0, gam, acc = make_hmc_streams(n, 16, 1, seed=2)
+    s = RiemannianHMCSampler(MetricModel(mt), mcmc_steps_nbr=1, n_lf=2, eps_lf=0.03)
+    zf = s.sample_with_streams(z0.to(dev), gam.to(dev), acc.to(dev))
+    torch.cuda.synchronize()
+    print('hmc ok', float(zf[:4].sum()))

@@ -9,10 +9,10 @@ launches, rep, prefix = sys.argv[1:4]
 rows = list(csv.reader(open(launches)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 h = rows[hdr]
-ki, vi, ui = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
+ki, vi, ui, mi = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit'), h.index('Metric Name')
 tot, cnt = defaultdict(float), defaultdict(int)
 for r in rows[hdr + 1:]:
-    if len(r) <= vi:
+    if len(r) <= vi or r[mi] != 'gpu__time_duration.sum':
         continue
     v = float(r[vi].replace(',', ''))
     u = r[ui]
