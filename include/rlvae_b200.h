@@ -104,6 +104,19 @@ int64_t rlvae_metric_eval_workspace(int64_t n, int d);   /* bytes */
 int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
                       float* logdet_g, float* grad_logdet_g, void* work, int path, void* stream);
 
+/* ---- A19: spectrum of the metric for the per-flow-step analysis consumers ---------------------
+ * ref: src/visualizations/flow_analysis.py:104-126, src/visualizations/manifold.py:79-101,
+ * src/models/modular_rlvae.py:434-457 (torch.linalg.eigvals / det of G^{-1}(z_t), G(z_t) per step).
+ * rlvae_sym_eigvalsh: eigenvalues (ascending, like torch.linalg.eigvalsh) of n symmetric d x d
+ * matrices, d == 16: a = [N,16,16] (upper triangle read) or, packed != 0, the packed [N,144]
+ * layout of rlvae_inverse_metric_packed.  eig [N,16].  Per-thread cyclic Jacobi in registers.
+ * rlvae_metric_spectrum: z -> eig(G^{-1}(z)) [N,16] ascending (eig(G) = 1/eig(G^{-1})) and,
+ * optionally, log|det G| [N], in one pass over the tables (symmetric tables, d == 16);
+ * work: rlvae_metric_eval_workspace(n, d) bytes.                                              */
+int rlvae_sym_eigvalsh(const float* a, int64_t n, int d, int packed, float* eig, void* stream);
+int rlvae_metric_spectrum(const rlvae_tables_t* t, const float* z, int64_t n, float* eig_ginv,
+                          float* logdet_g, void* work, int path, void* stream);
+
 /* ---- A11: one MCMC iteration of RiemannianHMCSampler.sample ----------------------------------
  * ref: src/models/samplers/hmc_sampler.py:120-163.  In/out: z [N,d] (chain state, replaced by
  * the accepted state).  gamma [N,d] and acc [N] are the random draws of lines 122 and 158.

@@ -35,6 +35,8 @@ _SIGNATURES = [
     ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_metric_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ('rlvae_sym_eigvalsh', c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    ('rlvae_metric_spectrum', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_hmc_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_hmc_iteration', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float,
                                     POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -218,6 +220,32 @@ def metric_eval(tab: Tables, z: torch.Tensor, want_ginv=True, want_g=False, want
         _check(lib().rlvae_metric_eval(tab.handle, _ptr(z), n, _ptr(ginv), _ptr(g), _ptr(ld), _ptr(gr),
                                        _ptr(work), path, _stream(z)), 'rlvae_metric_eval')
     return dict(ginv=ginv, g=g, logdet_g=ld, grad_logdet_g=gr, work=work)
+
+
+def sym_eigvalsh(a: torch.Tensor) -> torch.Tensor:
+    """Eigenvalues (ascending) of symmetric matrices a [N,d,d].  d == 16 runs the per-thread Jacobi
+    kernel; other sizes use torch.linalg.eigvalsh on the device (a library call, not a CPU path)."""
+    a = _req(a, 'a')
+    n, d = a.shape[0], a.shape[-1]
+    if d != 16:
+        return torch.linalg.eigvalsh(a)
+    out = torch.empty((n, d), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _check(lib().rlvae_sym_eigvalsh(_ptr(a), n, d, 0, _ptr(out), _stream(a)), 'rlvae_sym_eigvalsh')
+    return out
+
+
+def metric_spectrum(tab: Tables, z: torch.Tensor, want_logdet: bool = True, path: int = PATH_AUTO):
+    """-> (eig(G^{-1}(z)) [N,16] ascending, log|det G| [N] or None); symmetric tables, d == 16."""
+    z = _req(z, 'z')
+    n, d = z.shape
+    eig = torch.empty((n, d), device=z.device, dtype=torch.float32)
+    ld = torch.empty(n, device=z.device, dtype=torch.float32) if want_logdet else None
+    work = torch.empty(max(int(lib().rlvae_metric_eval_workspace(n, d)), 1), device=z.device, dtype=torch.uint8)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_metric_spectrum(tab.handle, _ptr(z), n, _ptr(eig), _ptr(ld), _ptr(work), path,
+                                           _stream(z)), 'rlvae_metric_spectrum')
+    return eig, ld
 
 
 def hmc_workspace(n: int, d: int, device) -> torch.Tensor:

@@ -535,6 +535,41 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   return 0;
 }
 
+int rlvae_sym_eigvalsh(const float* a, int64_t n, int d, int packed, float* eig, void* stream) {
+  RLVAE_REQUIRE(n >= 0, "sym_eigvalsh: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(a != nullptr && eig != nullptr, "sym_eigvalsh: NULL pointer");
+  RLVAE_REQUIRE(d == 16, "sym_eigvalsh: latent_dim must be 16 (other sizes: use the framework's eigvalsh)");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(eig) & 15) == 0,
+                "sym_eigvalsh: pointers must be 16-byte aligned");
+  return launch_sym16_eigvalsh(a, n, packed ? 1 : 0, eig, static_cast<cudaStream_t>(stream));
+}
+
+int rlvae_metric_spectrum(const rlvae_tables_t* t, const float* z, int64_t n, float* eig_ginv,
+                          float* logdet_g, void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "metric_spectrum: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "metric_spectrum: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && eig_ginv != nullptr && work != nullptr, "metric_spectrum: NULL pointer");
+  RLVAE_REQUIRE(t->d == 16 && t->symmetric, "metric_spectrum: needs latent_dim == 16 and symmetric metric matrices");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* a_buf = static_cast<float*>(work);
+  bool packed = false;
+  if (int rc = sym_tensor_path(t, path, &packed)) return rc;
+  if (packed) {
+    int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
+    if (int rc = sym_forward(t, z, n, a_buf, nullptr, logdet_g, -1.f, nullptr, nullptr, fail_ws, s)) return rc;
+    return launch_sym16_eigvalsh(a_buf, n, 1, eig_ginv, s);
+  }
+  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s)) return rc;
+  if (logdet_g != nullptr) {
+    float* lad = a_buf + n * 256;
+    if (int rc = launch_batched_inverse(a_buf, n, 16, nullptr, lad, nullptr, nullptr, 0, s)) return rc;
+    if (int rc = negate_copy(lad, logdet_g, n, s)) return rc;
+  }
+  return launch_sym16_eigvalsh(a_buf, n, 0, eig_ginv, s);
+}
+
 int64_t rlvae_hmc_workspace(int64_t n, int d) {
   // ginv, g (exact mode), diag, rho_half, z_prev, grad, logabsdet, sign, h0
   return (int64_t)sizeof(float) * (2 * n * d * d + 4 * n * d + 3 * n);

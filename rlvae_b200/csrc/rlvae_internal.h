@@ -110,6 +110,8 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
 // are not positive definite.  fail_ws: 1 + n ints.  logabsdet receives lad_scale * log|det A|.
 int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
+// eigenvalues (ascending) of symmetric 16x16 matrices: a = packed [N,144] or full [N,16,16] (upper triangle read)
+int launch_sym16_eigvalsh(const float* a, int64_t n, int packed, float* eig, cudaStream_t s);
 int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
                           float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs

@@ -374,6 +374,140 @@ int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, flo
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Eigenvalues of symmetric 16 x 16 matrices (per-step spectrum / condition number of G^{-1}, G for
+// the flow-analysis consumers: ref src/visualizations/flow_analysis.py:104-126,
+// src/visualizations/manifold.py:79-101, src/models/modular_rlvae.py:434-457, which call
+// torch.linalg.eigvals / det per batch).  ONE THREAD PER MATRIX: cyclic Jacobi on the 136 packed
+// entries held in registers (every index static), sweeps until the whole warp has converged, then a
+// sorting network; ascending order like torch.linalg.eigvalsh.  Input: packed [N,144] (PACKED) or
+// the upper triangle of a full [N,16,16].  HBM-bound target: 576 (or 1024) B in, 64 B out per matrix.
+// ------------------------------------------------------------------------------------------------
+#define SYM_U(r, c) a[sym16_index((r), (c))]   /* r <= c */
+
+// One Jacobi rotation (P, Q), P < Q, on the packed upper triangle; every index is a template constant.
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rotate(float (&a)[136]) {
+  constexpr int ipq = sym16_index(P, Q), ipp = sym16_index(P, P), iqq = sym16_index(Q, Q);
+  const float apq = a[ipq], app = a[ipp], aqq = a[iqq];
+  // rotation angle (Rutishauser); a negligible a_pq gives the identity rotation
+  const bool skip = fabsf(apq) <= 1e-30f || apq * apq <= 1e-18f * fabsf(app * aqq);
+  const float theta = 0.5f * (aqq - app) / (skip ? 1.f : apq);
+  float t = 1.f / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
+  t = theta < 0.f ? -t : t;
+  t = skip ? 0.f : t;
+  const float c = rsqrtf(fmaf(t, t, 1.f));
+  const float sn = t * c;
+  a[ipp] = fmaf(-t, apq, app);
+  a[iqq] = fmaf(t, apq, aqq);
+  a[ipq] = skip ? apq : 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k != P && k != Q) {
+      const int ikp = (k < P) ? sym16_index(k, P) : sym16_index(P, k);
+      const int ikq = (k < Q) ? sym16_index(k, Q) : sym16_index(Q, k);
+      const float x = a[ikp], y = a[ikq];
+      a[ikp] = fmaf(c, x, -sn * y);
+      a[ikq] = fmaf(sn, x, c * y);
+    }
+  }
+}
+template <int P, int Q>
+struct JacobiSweep {
+  static __device__ __forceinline__ void run(float (&a)[136]) {
+    jacobi_rotate<P, Q>(a);
+    if constexpr (Q + 1 < 16) JacobiSweep<P, Q + 1>::run(a);
+    else if constexpr (P + 2 < 16) JacobiSweep<P + 1, P + 2>::run(a);
+  }
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(sym16::THREADS)
+sym16_eigvalsh_kernel(const float* __restrict__ src_all, int64_t n, float* __restrict__ eig) {
+  constexpr int LD = sym16::LD, TH = sym16::THREADS;
+  __shared__ __align__(16) float stage[TH * LD];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * TH;
+  const int rows = (int)((n - m0 < TH) ? (n - m0) : TH);
+  float a[136];
+  if (PACKED) {
+    const float4* src = reinterpret_cast<const float4*>(src_all + m0 * kSymCols);
+    for (int i = tid; i < rows * 36; i += TH) {
+      const int r = i / 36, c = i - r * 36;
+      *reinterpret_cast<float4*>(stage + r * LD + 4 * c) = __ldg(src + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 34; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(stage + tid * LD + 4 * q);
+      a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+  } else {
+    // full [N,16,16]: stage 256 floats per matrix in four 64-column passes, keep the upper triangle
+    const float4* src = reinterpret_cast<const float4*>(src_all + m0 * 256);
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {            // rows 4*pass .. 4*pass+3 of every matrix
+      __syncthreads();
+      for (int i = tid; i < rows * 16; i += TH) {
+        const int r = i >> 4, c = i & 15;
+        *reinterpret_cast<float4*>(stage + r * LD + 4 * c) = __ldg(src + (int64_t)r * 64 + pass * 16 + c);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc)
+          if (cc >= 4 * pass + rr) SYM_U(4 * pass + rr, cc) = stage[tid * LD + rr * 16 + cc];
+    }
+  }
+  const bool live = tid < rows;
+  if (!live) {
+#pragma unroll
+    for (int i = 0; i < 136; ++i) a[i] = 0.f;
+  }
+  float fro = 0.f;
+#pragma unroll
+  for (int i = 0; i < 136; ++i) fro = fmaf(a[i], a[i], fro);
+  const float tol = 1e-14f * fro;          // off-diagonal sum of squares target (relative 1e-7 in norm)
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    float off = 0.f;
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 16; ++q) off = fmaf(SYM_U(p, q), SYM_U(p, q), off);
+    if (__all_sync(0xffffffffu, !(off > tol))) break;
+    JacobiSweep<0, 1>::run(a);
+  }
+  float ev[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ev[i] = SYM_U(i, i);
+  // odd-even transposition sort, ascending
+#pragma unroll
+  for (int round = 0; round < 16; ++round) {
+#pragma unroll
+    for (int i = (round & 1); i + 1 < 16; i += 2) {
+      const float lo = fminf(ev[i], ev[i + 1]), hi = fmaxf(ev[i], ev[i + 1]);
+      ev[i] = lo; ev[i + 1] = hi;
+    }
+  }
+  if (live) {
+    float4* dst = reinterpret_cast<float4*>(eig + (m0 + tid) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(ev[4 * q], ev[4 * q + 1], ev[4 * q + 2], ev[4 * q + 3]);
+  }
+}
+#undef SYM_U
+
+int launch_sym16_eigvalsh(const float* a, int64_t n, int packed, float* eig, cudaStream_t s) {
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)((n + sym16::THREADS - 1) / sym16::THREADS);
+  if (packed) sym16_eigvalsh_kernel<true><<<grid, sym16::THREADS, 0, s>>>(a, n, eig);
+  else sym16_eigvalsh_kernel<false><<<grid, sym16::THREADS, 0, s>>>(a, n, eig);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
 __global__ void unpack_sym16_kernel(const float* __restrict__ packed, int64_t n, float* __restrict__ full) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n * 256) return;

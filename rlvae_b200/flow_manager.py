@@ -137,7 +137,8 @@ class FlowManager(nn.Module):
 
     # ------------------------------------------------------------------ hot-path consumer (A19)
     @torch.no_grad()
-    def metric_along_flow(self, metric_tensor, z0: torch.Tensor, n_obs: int, want_g: bool = False):
+    def metric_along_flow(self, metric_tensor, z0: torch.Tensor, n_obs: int, want_g: bool = False,
+                          want_spectrum: bool = False):
         """Roll ``z0`` [B,d] through the flows and evaluate the metric at every step in one
         fused call: returns dict(z [B,T,d], log_det_jacobians [B,T-1], logdet_G [B,T],
         det_G [B,T], optionally G [B,T,d,d]) -- what flow_analysis.py:104-126 computes per t."""
@@ -151,4 +152,10 @@ class FlowManager(nn.Module):
                'logdet_G': ld, 'det_G': torch.exp(ld)}
         if want_g:
             out['G'] = ev['g'].reshape(b, t, d, d)
+        if want_spectrum:   # eigenvalues / condition number / traces per (B, T) (manifold.py:86-93)
+            sp = metric_tensor.compute_metric_spectrum(z.reshape(b * t, d).contiguous())
+            for k in ('eigenvals_G_inv', 'eigenvals_G'):
+                out[k] = sp[k].reshape(b, t, d)
+            for k in ('condition_number', 'trace_G', 'trace_G_inv'):
+                out[k] = sp[k].reshape(b, t)
         return out

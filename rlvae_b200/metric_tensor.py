@@ -221,6 +221,30 @@ class MetricTensor(nn.Module):
             return _capi.metric_eval(self._tables(z.device), z.float(), want_ginv, want_g, want_logdet,
                                      want_grad, self._path(), out)
 
+    def compute_metric_spectrum(self, z: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Per-point spectrum of the metric, what the flow-analysis consumers compute per step with
+        torch.linalg.eigvals / det (ref flow_analysis.py:104-126, manifold.py:79-101,
+        modular_rlvae.py:434-457): eigenvalues of G^{-1} and G (ascending), condition number, traces,
+        log det.  Symmetric tables with d == 16 run one fused pass (forward kernel + per-thread Jacobi);
+        anything else composes compute_inverse_metric with torch.linalg on the device."""
+        self._check_ready(z)
+        with torch.no_grad():
+            tab = self._tables(z.device)
+            if tab.d == 16 and tab.symmetric:
+                eig_inv, ld = _capi.metric_spectrum(tab, z.float(), True, self._path())
+            else:
+                g_inv = self.compute_inverse_metric(z)
+                if tab.symmetric:
+                    eig_inv = torch.linalg.eigvalsh(g_inv)
+                else:
+                    eig_inv = torch.sort(torch.linalg.eigvals(g_inv).real, dim=-1).values
+                ld = -torch.linalg.slogdet(g_inv).logabsdet
+            eig_g = torch.flip(1.0 / eig_inv, dims=[-1])
+            return {'eigenvals_G_inv': eig_inv, 'eigenvals_G': eig_g,
+                    'condition_number': eig_inv[:, -1] / eig_inv[:, 0],
+                    'trace_G_inv': eig_inv.sum(-1), 'trace_G': eig_g.sum(-1),
+                    'logdet_G': ld, 'det_G': torch.exp(ld), 'det_G_inv': torch.exp(-ld)}
+
     def compute_grad_log_det_metric(self, z: torch.Tensor) -> torch.Tensor:
         """Analytic grad_z log det G(z) [N,d] (north_star)."""
         return self.evaluate(z, want_ginv=False, want_logdet=False, want_grad=True)['grad_logdet_g']

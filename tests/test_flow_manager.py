@@ -60,8 +60,13 @@ def test_metric_along_flow_fused_equals_per_step_loop():
     mt = MetricTensor(16, device=dev)
     with contextlib.redirect_stdout(io.StringIO()):
         mt.load_pretrained(**sm.as_load_kwargs())
-    out = fm.metric_along_flow(mt, g['z0'].to(dev), n_obs=6, want_g=True)
+    out = fm.metric_along_flow(mt, g['z0'].to(dev), n_obs=6, want_g=True, want_spectrum=True)
     assert out['z'].shape == (6, 6, 16) and out['logdet_G'].shape == (6, 6) and out['G'].shape == (6, 6, 16, 16)
+    assert out['eigenvals_G'].shape == (6, 6, 16) and out['condition_number'].shape == (6, 6)
+    ev_ref = torch.linalg.eigvalsh(out['G'].double().cpu())            # flow_analysis.py:120-124 per step
+    torch.testing.assert_close(out['eigenvals_G'].double().cpu(), ev_ref, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out['trace_G'].cpu(), torch.diagonal(out['G'], dim1=-2, dim2=-1).sum(-1).cpu(),
+                               rtol=1e-4, atol=1e-6)
     # the flows are stock torch; GPU vs CPU fp32 matmul rounding is amplified by 6 x 2 x 16 sequential
     # MADE passes, so this is a sanity bound only (CPU parity is exact in the test above)
     torch.testing.assert_close(out['z'].cpu(), g['z_seq'].transpose(0, 1), rtol=2e-2, atol=2e-2)

@@ -303,6 +303,40 @@ def test_symmetric_indefinite_tables_take_the_pivoting_fallback():
         assert rel_fro(ev['grad_logdet_g'].cpu()[good], ref_grad[good]) < 5e-4, path
 
 
+def test_metric_spectrum_matches_reference_eigvals():
+    """A19: what manifold.py:86-93 / modular_rlvae.py:440-447 compute per step with
+    torch.linalg.eigvals(G_inv).real and det -- here from the fused forward + per-thread Jacobi pass."""
+    from rlvae_b200 import _capi
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(300, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    z = make_points(1000, 16, seed=7)
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=200)
+    ref_ev = torch.sort(torch.linalg.eigvals(ref_ginv).real, dim=-1).values        # the reference's call
+    ref_ld = -torch.linalg.slogdet(ref_ginv.double()).logabsdet
+    for path in paths_for(t):
+        sp = make_mt(t, path).compute_metric_spectrum(z.to(dev()))
+        ev = sp['eigenvals_G_inv'].cpu()
+        assert ((ev - ref_ev).abs().max(dim=1).values / ref_ev.abs().max(dim=1).values).max() < 1e-5, path
+        torch.testing.assert_close(sp['condition_number'].cpu(), ref_ev[:, -1] / ref_ev[:, 0], rtol=2e-4, atol=0)
+        close_ld(sp['logdet_G'], ref_ld.float())
+        torch.testing.assert_close(sp['eigenvals_G'].cpu(), torch.flip(1.0 / ref_ev, dims=[-1]), rtol=2e-4, atol=0)
+        torch.testing.assert_close(sp['trace_G_inv'].cpu(), torch.diagonal(ref_ginv, dim1=1, dim2=2).sum(-1),
+                                   rtol=1e-5, atol=0)
+    # the stand-alone kernel on general symmetric (indefinite, clustered, diagonal) matrices
+    gen = torch.Generator().manual_seed(3)
+    a = torch.randn(777, 16, 16, generator=gen)
+    a = a + a.transpose(1, 2)
+    a[0] = torch.diag(torch.arange(16.0) - 5.0)
+    a[1] = torch.eye(16) * 3.0
+    a[2] = 0.0
+    a[3] = torch.ones(16, 16)
+    got = _capi.sym_eigvalsh(a.to(dev())).cpu()
+    ref = torch.linalg.eigvalsh(a.double())
+    scale = ref.abs().max(dim=1).values.clamp_min(1e-30)
+    assert ((got.double() - ref).abs().max(dim=1).values / scale).max() < 2e-6
+
+
 def test_latent_dim_64_direct_path():
     """BASELINE.json configs[4] shape family (d = 64): the direct kernels and the d = 64 per-point
     inverse against the CPU oracle (small K, N so the oracle's [n,K,d,d] stays small)."""
