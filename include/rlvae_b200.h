@@ -117,6 +117,14 @@ int rlvae_sym_eigvalsh(const float* a, int64_t n, int d, int packed, float* eig,
 int rlvae_metric_spectrum(const rlvae_tables_t* t, const float* z, int64_t n, float* eig_ginv,
                           float* logdet_g, void* work, int path, void* stream);
 
+/* ---- metric construction (the step before the path) ----------------------
+ * ref: scripts/train_and_extract_vanilla_vae.py:199-221.  For every centroid c_i the covariance of
+ * the encoded latents under the normalised Gaussian weights exp(-||mu_n - c_i||^2 / T^2):
+ * latents [N,d], centroids [K,d] -> cov [K,d,d].  (M_i = cov_i + reg I and the minimum-eigenvalue
+ * lift of lines 213-218 are composed by the host mirror, rlvae_b200.metric_builder.)            */
+int rlvae_local_covariance(const float* latents, int64_t n, const float* centroids, int n_centroids,
+                           int latent_dim, float temperature, float* cov, void* stream);
+
 /* ---- A11: one MCMC iteration of RiemannianHMCSampler.sample ----------------------------------
  * ref: src/models/samplers/hmc_sampler.py:120-163.  In/out: z [N,d] (chain state, replaced by
  * the accepted state).  gamma [N,d] and acc [N] are the random draws of lines 122 and 158.

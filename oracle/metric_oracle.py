@@ -309,3 +309,25 @@ def eval_ginv_logdet_grad(z, centroids, matrices, temperature, regularization):
     ld = log_det_metric(zz, centroids, matrices, temperature, regularization)
     grad = torch.autograd.grad(ld.sum(), zz)[0]
     return ginv, ld.detach(), grad
+
+
+# ---------------------------------------------------------------------------------------------
+# Metric construction
+def build_local_metrics(all_mus, centroids, temperature, regularization):
+    """ref scripts/train_and_extract_vanilla_vae.py:204-226: per centroid, normalised Gaussian
+    weights over all encoded latents, weighted mean, weighted covariance + reg I, then the
+    minimum-eigenvalue lift to 1e-6.  Same op order as the reference loop."""
+    d = all_mus.shape[1]
+    out = []
+    for c in centroids:
+        dists = torch.norm(all_mus - c, dim=1)
+        weights = torch.exp(-dists ** 2 / (temperature ** 2))
+        weights = weights / (weights.sum() + 1e-8)
+        mean = (weights.unsqueeze(1) * all_mus).sum(dim=0)
+        diffs = all_mus - mean.unsqueeze(0)
+        metric = torch.einsum('n,ni,nj->ij', weights, diffs, diffs) + regularization * torch.eye(d, dtype=all_mus.dtype)
+        min_eig = torch.linalg.eigvals(metric).real.min().item()
+        if min_eig < 1e-6:
+            metric = metric + (1e-6 - min_eig) * torch.eye(d, dtype=all_mus.dtype)
+        out.append(metric)
+    return torch.stack(out, dim=0)

@@ -37,6 +37,7 @@ _SIGNATURES = [
     ('rlvae_metric_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_sym_eigvalsh', c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     ('rlvae_metric_spectrum', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ('rlvae_local_covariance', c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     ('rlvae_hmc_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_hmc_iteration', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float,
                                     POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -246,6 +247,20 @@ def metric_spectrum(tab: Tables, z: torch.Tensor, want_logdet: bool = True, path
         _check(lib().rlvae_metric_spectrum(tab.handle, _ptr(z), n, _ptr(eig), _ptr(ld), _ptr(work), path,
                                            _stream(z)), 'rlvae_metric_spectrum')
     return eig, ld
+
+
+def local_covariance(latents: torch.Tensor, centroids: torch.Tensor, temperature: float) -> torch.Tensor:
+    """cov [K,d,d]: weighted covariance of the latents around every centroid (metric construction)."""
+    x = _req(latents, 'latents')
+    c = _req(centroids, 'centroids')
+    if x.dim() != 2 or c.dim() != 2 or x.shape[1] != c.shape[1]:
+        raise ValueError(f'inconsistent shapes: latents {tuple(x.shape)}, centroids {tuple(c.shape)}')
+    k, d = c.shape
+    out = torch.empty((k, d, d), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _check(lib().rlvae_local_covariance(_ptr(x), x.shape[0], _ptr(c), k, d, c_float(temperature), _ptr(out),
+                                            _stream(x)), 'rlvae_local_covariance')
+    return out
 
 
 def hmc_workspace(n: int, d: int, device) -> torch.Tensor:

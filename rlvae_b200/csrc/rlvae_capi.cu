@@ -570,6 +570,18 @@ int rlvae_metric_spectrum(const rlvae_tables_t* t, const float* z, int64_t n, fl
   return launch_sym16_eigvalsh(a_buf, n, 0, eig_ginv, s);
 }
 
+int rlvae_local_covariance(const float* latents, int64_t n, const float* centroids, int n_centroids,
+                           int latent_dim, float temperature, float* cov, void* stream) {
+  RLVAE_REQUIRE(n >= 0 && n_centroids >= 0, "local_covariance: negative size");
+  RLVAE_REQUIRE(latent_dim >= 1 && latent_dim <= kMaxLatentDim, "local_covariance: latent_dim must be in [1,64]");
+  RLVAE_REQUIRE(temperature != 0.f, "local_covariance: temperature must be non-zero");
+  if (n_centroids == 0) return 0;
+  RLVAE_REQUIRE(centroids != nullptr && cov != nullptr && (latents != nullptr || n == 0),
+                "local_covariance: NULL pointer");
+  return launch_local_covariance(latents, n, centroids, n_centroids, latent_dim, temperature, cov,
+                                 static_cast<cudaStream_t>(stream));
+}
+
 int64_t rlvae_hmc_workspace(int64_t n, int d) {
   // ginv, g (exact mode), diag, rho_half, z_prev, grad, logabsdet, sign, h0
   return (int64_t)sizeof(float) * (2 * n * d * d + 4 * n * d + 3 * n);

@@ -140,6 +140,10 @@ int tc_build_sym_descriptors(rlvae_tables* t);
 int launch_metric_grad_tc(const rlvae_tables* t, const float* z, const float* u, int64_t n,
                           float scale, float* out, cudaStream_t s, int u_packed = 0);
 
+// metric construction (rlvae_build.cu)
+int launch_local_covariance(const float* mus, int64_t n, const float* centroids, int k, int d, float temperature,
+                            float* cov, cudaStream_t s);
+
 // HMC elementwise stages (rlvae_hmc.cu)
 struct HmcBeginArgs;
 int launch_hmc_begin(const float* z, const float* gamma, const float* diag_g, const float* logabsdet,

@@ -337,6 +337,32 @@ def test_metric_spectrum_matches_reference_eigvals():
     assert ((got.double() - ref).abs().max(dim=1).values / scale).max() < 2e-6
 
 
+@pytest.mark.parametrize('case', ['builder_d16_T01', 'builder_d16_T05', 'builder_d2_T03', 'builder_d32_T10'])
+def test_metric_construction_matches_reference(case):
+    """8f rank 4: M_i from rlvae_local_covariance (+ reg I, eigenvalue lift) vs the reference's loop."""
+    from rlvae_b200 import MetricTensor, metric_builder
+    g = load_golden(case)
+    T, reg = float(g['temperature']), float(g['regularization'])
+    m = metric_builder.build_local_metrics(g['latents'].to(dev()), g['centroids'].to(dev()), T, reg)
+    assert rel_fro(m.cpu(), g['M']) < 2e-5
+    data = metric_builder.build_metric_data(g['latents'].to(dev()), centroids=g['centroids'].to(dev()),
+                                            temperature=T, regularization=reg)
+    assert set(data) == {'centroids', 'M_matrices', 'temperature', 'regularization', 'latent_dim', 'n_centroids'}
+    st = metric_builder.metric_statistics(m)
+    ev = torch.linalg.eigvalsh(g['M'].double())
+    assert abs(st['min_eigenvalue'] - ev.min().item()) < 1e-5 * ev.max().item()
+    # the product loads into the hot path unchanged
+    import contextlib, io
+    mt = MetricTensor(latent_dim=g['latents'].shape[1], device=dev())
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt.load_pretrained(data['centroids'], data['M_matrices'], temperature=0.7, regularization=reg)
+    z = g['centroids'][:5].to(dev())
+    ref = O.inverse_metric(g['centroids'][:5], g['centroids'], g['M'], 0.7, reg)
+    assert rel_fro(mt.compute_inverse_metric(z).cpu(), ref) < 5e-5
+    lf = torch.tril(torch.randn(7, 4, 4, generator=torch.Generator().manual_seed(1))).to(dev())
+    torch.testing.assert_close(metric_builder.matrices_from_cholesky_factors(lf), lf @ lf.transpose(1, 2))
+
+
 def test_latent_dim_64_direct_path():
     """BASELINE.json configs[4] shape family (d = 64): the direct kernels and the d = 64 per-point
     inverse against the CPU oracle (small K, N so the oracle's [n,K,d,d] stays small)."""

@@ -99,3 +99,12 @@ def test_oracle_vs_live_reference_fresh_inputs():
     assert rel_fro(O.inverse_metric(z, *t), mt.compute_inverse_metric(z)) < 1e-6
     assert rel_fro(O.metric(z, *t), mt.compute_metric(z)) < 1e-6
     torch.testing.assert_close(O.log_det_metric(z, *t), mt.compute_log_det_metric(z), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize('case', ['builder_d16_T01', 'builder_d16_T05', 'builder_d2_T03', 'builder_d32_T10'])
+def test_metric_construction_oracle_matches_reference_lines(case):
+    """oracle.build_local_metrics vs the output of the reference's own loop
+    (scripts/train_and_extract_vanilla_vae.py:204-226, executed by oracle/make_golden_builder.py)."""
+    g = load_golden(case)
+    got = O.build_local_metrics(g['latents'], g['centroids'], float(g['temperature']), float(g['regularization']))
+    torch.testing.assert_close(got, g['M'], rtol=1e-6, atol=1e-7)
