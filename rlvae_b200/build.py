@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'librlvae_b200.so')
-SOURCES = ['rlvae_capi.cu', 'rlvae_direct.cu', 'rlvae_perpoint.cu', 'rlvae_hmc.cu', 'rlvae_tc.cu', 'rlvae_tc16.cu', 'rlvae_build.cu']
+SOURCES = ['rlvae_capi.cu', 'rlvae_direct.cu', 'rlvae_perpoint.cu', 'rlvae_hmc.cu', 'rlvae_tc.cu', 'rlvae_tc16.cu', 'rlvae_tc64.cu', 'rlvae_build.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static']
 

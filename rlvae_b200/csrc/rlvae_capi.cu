@@ -190,6 +190,8 @@ static void free_tables(rlvae_tables* t) {
   if (t->Mh_lo) cudaFree(t->Mh_lo);
   if (t->Mnh_hi) cudaFree(t->Mnh_hi);
   if (t->Mnh_lo) cudaFree(t->Mnh_lo);
+  if (t->c64h) cudaFree(t->c64h);
+  t->c64h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
                     &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
@@ -339,6 +341,15 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
       }
     }
   }
+  if (d == 64 && t->symmetric) {   // split-fp16 forward path for the large-metric configuration
+    int rc = tc_build_h64_tables(t, s);
+    if (rc != 0) return fail(rc);
+    if (t->c64h != nullptr) {
+      t->tensor_capable = 1;
+      const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
+      t->tensor_auto = (rel < 2.0e-6f) ? 1 : 0;
+    }
+  }
   *out = t;
   return 0;
 }
@@ -398,8 +409,11 @@ static int sym_tensor_path(const rlvae_tables* t, int path, bool* yes) {
   return 0;
 }
 
+static int inverse_metric_full(const rlvae_tables* t, const float* z, int64_t n, float* buf, int path,
+                               cudaStream_t s, float* scratch);
+
 int64_t rlvae_inverse_metric_workspace(int64_t n, int d) {
-  return d == 16 ? (int64_t)sizeof(float) * n * kSymCols : 0;
+  return d == 16 ? (int64_t)sizeof(float) * n * kSymCols : (d == 64 ? (int64_t)sizeof(float) * n * kSym64Cols : 0);
 }
 
 int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, void* work,
@@ -412,6 +426,7 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!use_tc) return launch_inverse_metric_direct(t, z, n, ginv, s);
+  if (t->d == 64) return inverse_metric_full(t, z, n, ginv, path, s, static_cast<float*>(work));
   if (t->symmetric && t->Mts_hi != nullptr && work != nullptr) {
     // symmetric tables: accumulate the 136 packed entries, then expand to [N,16,16]
     float* packed = static_cast<float*>(work);
@@ -434,10 +449,17 @@ int rlvae_inverse_metric_packed(const rlvae_tables_t* t, const float* z, int64_t
 }
 
 // full [N,d,d] G^{-1} for the non-symmetric / non-tensor cases
+// `scratch` (d == 64 only): n * kSym64Cols floats for the packed tiles of the tensor kernel; without
+// it AUTO falls back to the direct kernel (an explicit TENSOR request then fails).
 static int inverse_metric_full(const rlvae_tables* t, const float* z, int64_t n, float* buf, int path,
-                               cudaStream_t s) {
+                               cudaStream_t s, float* scratch) {
   bool use_tc;
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  if (use_tc && t->d == 64) {
+    if (scratch != nullptr) return launch_inverse_metric_h64(t, z, n, buf, scratch, s);
+    RLVAE_REQUIRE(path != RLVAE_PATH_TENSOR, "d = 64 tensor path needs a workspace");
+    use_tc = false;
+  }
   if (!use_tc) return launch_inverse_metric_direct(t, z, n, buf, s);
   return launch_inverse_metric_tc(t, z, n, buf, s);
 }
@@ -460,8 +482,8 @@ int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, i
   bool use_tc;
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return use_tc ? launch_metric_grad_tc(t, z, u, n, scale, out, s)
-                : launch_metric_grad_direct(t, z, u, n, scale, out, s);
+  return (use_tc && t->d == 16) ? launch_metric_grad_tc(t, z, u, n, scale, out, s)
+                                : launch_metric_grad_direct(t, z, u, n, scale, out, s);   // d = 64: forward only
 }
 
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
@@ -474,7 +496,7 @@ int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const floa
 }
 
 int64_t rlvae_metric_eval_workspace(int64_t n, int d) {
-  return (int64_t)sizeof(float) * (3 * n * d * d + n);
+  return (int64_t)sizeof(float) * (3 * n * d * d + n + 4);
 }
 
 int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* ginv, float* g,
@@ -490,7 +512,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   float* a_buf = w;                    // G^{-1}, full or packed (both fit in n*d*d floats)
   float* g_buf = g ? g : (w + mat);
   float* lad_buf = w + 2 * mat;
-  float* gt_buf = w + 2 * mat + n;
+  float* gt_buf = w + 2 * mat + ((n + 3) & ~(int64_t)3);   // 16-byte aligned (also the d = 64 packed scratch)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bool packed = false;
   if (int rc = sym_tensor_path(t, path, &packed)) return rc;
@@ -507,7 +529,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
       return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
     return 0;
   }
-  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s)) return rc;
+  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s, gt_buf)) return rc;
   if (ginv != nullptr)
     RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
   // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
@@ -561,7 +583,7 @@ int rlvae_metric_spectrum(const rlvae_tables_t* t, const float* z, int64_t n, fl
     if (int rc = sym_forward(t, z, n, a_buf, nullptr, logdet_g, -1.f, nullptr, nullptr, fail_ws, s)) return rc;
     return launch_sym16_eigvalsh(a_buf, n, 1, eig_ginv, s);
   }
-  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s)) return rc;
+  if (int rc = inverse_metric_full(t, z, n, a_buf, path, s, nullptr)) return rc;
   if (logdet_g != nullptr) {
     float* lad = a_buf + n * 256;
     if (int rc = launch_batched_inverse(a_buf, n, 16, nullptr, lad, nullptr, nullptr, 0, s)) return rc;
@@ -623,7 +645,7 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
       if (exact) return launch_metric_grad_tc(t, zz, gfull, n, 1.f / t->T2, gex, s, 1);
       return 0;
     }
-    if (int rc = inverse_metric_full(t, zz, n, ginv, path, s)) return rc;
+    if (int rc = inverse_metric_full(t, zz, n, ginv, path, s, gfull)) return rc;   // gfull doubles as the d = 64 scratch
     // exact mode wants G^T for the contraction (see rlvae_metric_eval)
     if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
@@ -666,7 +688,7 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
       int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
       if (int rc = sym_forward(t, z, n, ginv, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s)) return rc;
     } else {
-      if (int rc = inverse_metric_full(t, z, n, ginv, path, s)) return rc;
+      if (int rc = inverse_metric_full(t, z, n, ginv, path, s, w + n * d * d)) return rc;
       if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;
     }
     if (int rc = launch_axpy_grad_modular(z, diag, n, d, step_size, t->lambda, t->T2, s)) return rc;

@@ -88,7 +88,12 @@ struct rlvae_tables {
   float h16_m_unscale = 0.f;   // 2^-e
   float m_absmax = 0.f;
   CUtensorMap tm_mh_hi, tm_mh_lo, tm_mh2_hi, tm_mh2_lo;
-  CUtensorMap tm_mnh_hi, tm_mnh_lo, tm_mnh2_hi, tm_mnh2_lo;   // boxes of 32 centroids x 32 (pair: 16) rows
+  CUtensorMap tm_mnh_hi, tm_mnh_lo, tm_mnh2_hi, tm_mnh2_lo;
+  // d == 64 split-fp16 forward path (rlvae_tc64.cu): centroid rows [Kpad,128] fp16 = [hi | lo] of 2^ec c;
+  // Mh_hi / Mh_lo then hold the packed-transposed [2176, Kpad] tables
+  void* c64h = nullptr;
+  float c64_unscale = 0.f;     // 2^-ec
+  CUtensorMap tm_c64, tm_c64_2;   // boxes of 32 centroids x 32 (pair: 16) rows
 };
 
 namespace rlvae {
@@ -116,6 +121,11 @@ int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, flo
                           float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
 int tc_build_h16_descriptors(rlvae_tables* t);
+// d == 64 (symmetric tables): tables + forward through a packed [N,2176] scratch
+int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s);
+int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, float* ginv, float* packed_scratch,
+                              cudaStream_t s);
+constexpr int kSym64Cols = 2176;
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,

@@ -80,49 +80,6 @@ constexpr float P_SHIFT = 14.f;      // P' = 2^14 P
 
 }  // namespace h16
 
-// instruction descriptor for kind::f16: c = f32, a = b = f16, K-major both
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_ts_f16_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                                uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-#define TMEM_ST16(taddr, r)                                                                          \
-  asm volatile(                                                                                      \
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                \
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                    \
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),     \
-        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), \
-        "r"(r[15]) : "memory")
-
-// (a, b) -> packed fp16 pair {hi half = a, lo half = b} and the fp32 residuals of both
-__device__ __forceinline__ void split_pair(float even, float odd, uint32_t& hi2, uint32_t& lo2) {
-  uint32_t h;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(odd), "f"(even));   // .hi = odd, .lo = even element
-  float he, ho;
-  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}"
-      : "=f"(he), "=f"(ho) : "r"(h));
-  uint32_t l;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(odd - ho), "f"(even - he));
-  hi2 = h;
-  lo2 = l;
-}
-
 #define SYM_L(r, c) a[sym_index((c), (r))]   /* lower-triangular entry (r >= c) of the packed array */
 
 // Per-thread Cholesky / inverse on the 136 packed entries (same algorithm as sym16_cholesky_kernel

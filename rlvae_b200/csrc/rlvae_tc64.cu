@@ -1,0 +1,590 @@
+// Split-fp16 tcgen05 forward kernel for latent_dim == 64, symmetric tables (sm_100a):
+// BASELINE.json configs[4] ("large-metric stress": d = 64, K = 50k, tables streamed via TMA).
+//
+//   G^{-1}[n] = sum_k exp(-||z_n - c_k||^2 / T^2) M_k + lambda I      ref src/models/components/metric_tensor.py:115-135
+//
+// Same skeleton as inverse_metric_h16_kernel (rlvae_tc16.cu), with the two changes d = 64 forces:
+//  * the 64 x 65 / 2 = 2080 packed columns do not fit one CTA's TMEM, so blockIdx.y selects a tile
+//    of 128 packed columns (17 tiles, 2176 padded columns); every column tile recomputes the
+//    distance GEMM and the exp stage for its 128 points;
+//  * that makes the distance GEMM a third of the work, so it runs on kind::f16 as well:
+//    z' = 2^ez z (per point), c' = 2^ec c (per table), both split hi + lo in fp16,
+//    S' = z'_hi.c'_hi + z'_hi.c'_lo + z'_lo.c'_hi  (12 MMAs, K = 16 each, A operand = z' in TMEM),
+//    S = 2^-(ez+ec) S' is folded into the exponent's FFMA.  Error class: 2^-22 relative to
+//    |z||c|, the same as the 3xTF32 split of the d = 16 kernels.
+// Per 64-centroid super-block and column tile: GEMM1 12 x 32 + GEMM2 12 x 64 = 1152 tensor cycles.
+// The per-point 64 x 64 inverse / log det stays a separate kernel (batched_inverse_kernel<64>):
+// a 2080-entry matrix does not fit one thread's registers.
+//
+//   TMEM: [0,192) three S/P buffers, [192,320) / [320,448) chunk accumulators (N = 128),
+//         [448,480) z'_hi, [480,512) z'_lo (64 dims as packed fp16).
+//   Output: packed [N, 2176] fp32 (entry 64 i - i (i-1)/2 + (j - i) = element (i <= j), WITHOUT lambda;
+//           unpack_sym64_kernel expands to [N,64,64] and adds lambda on the diagonal).
+#include <type_traits>
+
+#include "rlvae_tc_common.cuh"
+
+namespace rlvae {
+namespace tc {
+namespace h64 {
+
+constexpr int D = 64;
+constexpr int THREADS = 512;
+constexpr int C_STAGES = 3;
+constexpr int SP_BUFS = 3;
+constexpr int M_STAGES = 3;
+constexpr int AHEAD = 3;
+constexpr int NT = 128;                                   // packed columns per CTA = MMA N of GEMM2
+constexpr int NPACK = 2080;                               // 64 * 65 / 2
+constexpr int NPAD = 2176;                                // 17 tiles of 128
+constexpr uint32_t C_TILE64 = 2 * BK * 128;               // [64 centroids x (hi atom | lo atom)] fp16
+constexpr uint32_t M_HALF_BYTES = NT * 128;               // [128 rows x 64 centroids] fp16 (pair: 64 rows used)
+constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;       // hi tile, then lo tile
+constexpr uint32_t OFF_C = 0;
+constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE64;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+constexpr int OUT_LD = 132;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
+constexpr uint32_t TM_SP = 0, TM_ACC = 192, TM_ZHI = 448, TM_ZLO = 480;
+constexpr float P_SHIFT = 14.f;
+
+}  // namespace h64
+
+template <bool PAIR>
+__global__ void __launch_bounds__(h64::THREADS, 1)
+inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
+                          const __grid_constant__ CUtensorMap tm_mh_hi,
+                          const __grid_constant__ CUtensorMap tm_mh_lo,
+                          const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
+                          int num_blocks, float alpha /* log2(e)/T^2 */, float c_unscale /* 2^-ec */,
+                          float out_scale /* 2^-(14+e) */, float* __restrict__ out /* [N, 2176] */) {
+  constexpr int C_STAGES = h64::C_STAGES, SP_BUFS = h64::SP_BUFS, M_STAGES = h64::M_STAGES, AHEAD = h64::AHEAD,
+                NT = h64::NT, OUT_LD = h64::OUT_LD, D = h64::D;
+  constexpr uint32_t M_TILE_BYTES = h64::M_TILE_BYTES, M_HALF_BYTES = h64::M_HALF_BYTES, C_TILE64 = h64::C_TILE64,
+                     TM_SP = h64::TM_SP, TM_ACC = h64::TM_ACC, TM_ZHI = h64::TM_ZHI, TM_ZLO = h64::TM_ZLO;
+  constexpr float P_SHIFT = h64::P_SHIFT;
+  constexpr int CB = 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+  const uint32_t bar0 = base + h64::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_BIAS_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (3 * C_STAGES + M_STAGES + s); };
+  auto BAR_S_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_P_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + SP_BUFS + b); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + h64::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const int col_tile = blockIdx.y;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  constexpr int ROWS_BOX = NT / NPAIR;                    // B-tile rows held by this CTA
+  constexpr uint32_t TILE_BYTES = ROWS_BOX * 128;
+  constexpr int C_ROWS = BK / NPAIR;                      // centroid rows of a C tile held by this CTA
+  constexpr uint32_t C_ATOM_BYTES = C_ROWS * 128;
+  constexpr uint32_t C_ATOM_DESC = C_ATOM_BYTES >> 4;
+  constexpr uint32_t IDESC_G1 = make_idesc_f16(PAIR ? 256 : 128, BK);
+  constexpr uint32_t IDESC_G2 = make_idesc_f16(PAIR ? 256 : 128, NT);
+  const int row_cta = col_tile * NT + (PAIR ? (int)rank * ROWS_BOX : 0);
+  const int num_chunks = (num_blocks + CB - 1) / CB;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_BIAS_FULL(s), 1);
+    }
+    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_lo) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + h64::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + h64::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  tc_fence_before();
+  __syncthreads();            // TMEM base published (the exp threads store z into TMEM below)
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  float zb = 0.f, s_scale = 0.f;   // exponent = S' * s_scale + bias_k + zb
+  if (wg == 1 || wg == 2) {
+    const int64_t r = row0 + prow;
+    float nrm = 0.f, zmax = 0.f;
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * D);
+#pragma unroll 4
+      for (int q = 0; q < D / 4; ++q) {
+        const float4 v = __ldg(src + q);
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+        zmax = fmaxf(zmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+    }
+    // z' = 2^ez z with max|z'| in [2^13, 2^14)
+    int ez = 0;
+    if (zmax > 0.f && zmax < 3.0e38f) {
+      const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;    // zmax = f 2^ex, f in [0.5, 1)
+      ez = 14 - ex;
+      ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
+    }
+    const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
+    zb = -nrm * alpha + P_SHIFT;
+    s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
+    if (wg == 1) {                   // exp group A writes the A operand of GEMM1 (split fp16) into TMEM
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      uint32_t hi[32], lo[32];
+      const float4* src = reinterpret_cast<const float4*>(z + r * D);
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q) {
+        const float4 v = (r < n) ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        split_pair(v.x * zsc, v.y * zsc, hi[2 * q], lo[2 * q]);
+        split_pair(v.z * zsc, v.w * zsc, hi[2 * q + 1], lo[2 * q + 1]);
+      }
+      TMEM_ST32(tmem_base + lane_addr + TM_ZHI, hi);
+      TMEM_ST32(tmem_base + lane_addr + TM_ZLO, lo);
+      tmem_wait_st();
+    }
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+#define MMA_G1(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_G1, acc); else mma_ts_f16(d, a, b, IDESC_G1, acc); } while (0)
+#define MMA_H(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_G2, acc); else mma_ts_f16(d, a, b, IDESC_G2, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (wg == 0) {
+    reg_dec<72>();
+    if (warp == 0) {
+      // =========================================================== TMA producer 1: centroid tiles + bias
+      for (int j = 0; j < num_blocks; ++j) {
+        const int cs = j % C_STAGES;
+        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE64);
+          const uint32_t dst = base + h64::OFF_C + cs * C_TILE64;
+          // box = [64 fp16] x [C_ROWS centroid rows] x [2 atoms: hi, lo]
+          if (PAIR) tma_load_3d_pair(dst, &tm_c64, BAR_C_FULL(cs), 0, j * BK + C_ROWS * (int)rank, 0);
+          else tma_load_3d(dst, &tm_c64, BAR_C_FULL(cs), 0, j * BK, 0);
+          mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+          bulk_load_1d(base + h64::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 2) {
+      // =========================================================== TMA producer 2: table tiles of this column tile
+      for (int jm = 0; jm < num_blocks; ++jm) {
+        const int ms = jm % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((jm / M_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * 2 * TILE_BYTES);
+          const uint32_t dst = base + h64::OFF_M + ms * M_TILE_BYTES;
+          if (PAIR) {
+            tma_load_2d_pair(dst, &tm_mh_hi, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d_pair(dst + M_HALF_BYTES, &tm_mh_lo, BAR_M_FULL(ms), jm * BK, row_cta);
+          } else {
+            tma_load_2d(dst, &tm_mh_hi, BAR_M_FULL(ms), jm * BK, row_cta);
+            tma_load_2d(dst + M_HALF_BYTES, &tm_mh_lo, BAR_M_FULL(ms), jm * BK, row_cta);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 && leader) {
+      // =========================================================== MMA issuer (6x unrolled, see rlvae_tc16.cu)
+      const uint64_t c_desc0 = make_desc_sw128(base + h64::OFF_C);
+      const uint64_t m_desc0 = make_desc_sw128(base + h64::OFF_M);
+      auto gemm1 = [&](auto CSc, auto SBc) {
+        constexpr int cs = decltype(CSc)::value, sb = decltype(SBc)::value;
+        if (elect_one()) {
+          const uint32_t d = tmem_base + TM_SP + sb * 64;
+          const uint64_t bh = c_desc0 + ((cs * C_TILE64) >> 4);       // hi atom; lo atom C_ATOM_DESC further
+          const uint64_t bl = bh + C_ATOM_DESC;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_G1(d, tmem_base + TM_ZHI + 8 * kk, bh + 2 * kk, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_G1(d, tmem_base + TM_ZHI + 8 * kk, bl + 2 * kk, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_G1(d, tmem_base + TM_ZLO + 8 * kk, bh + 2 * kk, 1);
+          COMMIT(BAR_S_FULL(sb));
+        }
+        __syncwarp();
+      };
+      uint32_t free_phase = 0;
+      auto block = [&](auto Jc, const int j, const uint32_t qodd /* (j / 6) & 1 */) {
+        constexpr int J = decltype(Jc)::value;
+        constexpr int first = (J % CB) == 0, sb = J % SP_BUFS;
+        const uint32_t ab = ((J / CB) & 1) ^ qodd;
+        constexpr int ms = J % M_STAGES;
+        if (first && j >= 2 * CB) {
+          mbar_wait(BAR_CH_FREE(ab), (free_phase >> ab) & 1u);
+          free_phase ^= 1u << ab;
+        }
+        tc_fence_after();
+        const uint32_t p = tmem_base + TM_SP + sb * 64;
+        const uint32_t acc = tmem_base + TM_ACC + ab * NT;
+        const uint64_t bh = m_desc0 + ((ms * M_TILE_BYTES) >> 4);
+        const uint64_t bl = bh + (M_HALF_BYTES >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bh + 2 * kk, !(first && kk == 0));
+        }
+        __syncwarp();
+        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((J + 1) % M_STAGES), ((J + 1) / M_STAGES) & 1);
+        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + 16 + (kk & 1) * 8, bh + 2 * kk, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_H(acc, p + (kk >> 1) * 32 + (kk & 1) * 8, bl + 2 * kk, 1);
+          COMMIT(BAR_M_EMPTY(ms));
+          if ((J % CB) == CB - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(ab));
+        }
+        __syncwarp();
+        if (j + AHEAD < num_blocks) {
+          tc_fence_after();
+          gemm1(std::integral_constant<int, (J + AHEAD) % C_STAGES>{}, std::integral_constant<int, (J + AHEAD) % SP_BUFS>{});
+        }
+        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((J + 1) % SP_BUFS), ((J + 1) / SP_BUFS) & 1);
+      };
+      if (0 < num_blocks) { mbar_wait(BAR_C_FULL(0), 0); tc_fence_after(); gemm1(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{}); }
+      if (1 < num_blocks) { mbar_wait(BAR_C_FULL(1), 0); tc_fence_after(); gemm1(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}); }
+      if (2 < num_blocks) { mbar_wait(BAR_C_FULL(2), 0); tc_fence_after(); gemm1(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
+      mbar_wait(BAR_M_FULL(0), 0);
+      mbar_wait(BAR_P_FULL(0), 0);
+      static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 6 % M_STAGES == 0 && AHEAD == 3,
+                    "the 6x unrolled issue loop assumes these periods");
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 6, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3) RLVAE_BLK(4) RLVAE_BLK(5)
+#undef RLVAE_BLK
+      }
+    }
+  } else if (wg == 1 || wg == 2) {
+    // =========================================================== exp groups (one thread per point)
+    reg_dec<104>();
+    const int grp = wg - 1;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int j = grp; j < num_blocks; j += 2) {
+      const int cs = j % C_STAGES, sb = j % SP_BUFS;
+      const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 64;
+      mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_S_FULL(sb), (j / SP_BUFS) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t s[32], ph[16], pl[16];
+        TMEM_LD32(sp + rnd * 32, s);
+        const float4* bias4 = reinterpret_cast<const float4*>(gbase + h64::OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = bias4[q];
+          const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), s_scale, bv.x + zb));
+          const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), s_scale, bv.y + zb));
+          const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), s_scale, bv.z + zb));
+          const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), s_scale, bv.w + zb));
+          split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+          split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+        }
+        TMEM_ST16(sp + rnd * 32, ph);
+        TMEM_ST16(sp + rnd * 32 + 16, pl);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_P_FULL(sb)); else mbar_arrive(BAR_P_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+    }
+  } else {
+    // =========================================================== fold group: fp32 running total + output
+    reg_inc<232>();
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float total[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) total[i] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int ab = c & 1;
+      mbar_wait(BAR_CH_FULL(ab), (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t src = tmem_base + lane_addr + TM_ACC + ab * NT;
+#pragma unroll
+      for (int cb = 0; cb < NT / 32; ++cb) {
+        uint32_t a[32];
+        TMEM_LD32(src + cb * 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) total[cb * 32 + i] += __uint_as_float(a[i]);
+      }
+      if (c + 2 < num_chunks) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(ab)); else mbar_arrive(BAR_CH_FREE(ab)); }
+      }
+    }
+    // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
+    float* stage = reinterpret_cast<float*>(gbase + h64::OFF_M);
+    const int t = threadIdx.x - 384;
+    const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
+#pragma unroll
+    for (int q = 0; q < NT / 4; ++q)
+      *reinterpret_cast<float4*>(stage + prow * OUT_LD + q * 4) =
+          make_float4(total[4 * q] * out_scale, total[4 * q + 1] * out_scale, total[4 * q + 2] * out_scale,
+                      total[4 * q + 3] * out_scale);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* dst = out + row0 * h64::NPAD + col_tile * NT;
+    for (int i = t; i < (int)rows_here * (NT / 4); i += 128) {
+      const int r = i / (NT / 4), c4 = i - r * (NT / 4);
+      *reinterpret_cast<float4*>(dst + (int64_t)r * h64::NPAD + c4 * 4) =
+          *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+    }
+  }
+#undef MMA_G1
+#undef MMA_H
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------ tables
+__host__ __device__ constexpr int sym64_index(int i, int j) {   // i <= j
+  return i * 64 - (i * (i - 1)) / 2 + (j - i);
+}
+
+// [Kpad, 128] fp16: row k = [fp16(2^ec c_k) (64) | fp16(2^ec c_k - hi) (64)], plus the exp2 bias
+__global__ void pack_c64_kernel(const float* __restrict__ c, int K, int Kpad, float scale, float inv_T2_log2e,
+                                __half* __restrict__ c64, float* __restrict__ cbias) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  float nrm = 0.f;
+  for (int j = 0; j < 64; ++j) {
+    const float v = (k < K) ? c[(int64_t)k * 64 + j] : 0.f;
+    nrm = fmaf(v, v, nrm);
+    const float sv = v * scale;
+    const __half h = __float2half_rn(sv);
+    c64[(int64_t)k * 128 + j] = h;
+    c64[(int64_t)k * 128 + 64 + j] = __float2half_rn(sv - __half2float(h));
+  }
+  cbias[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
+}
+
+// packed-transposed fp16 tables [2176, Kpad]: hi = fp16(scale * M), lo = fp16(scale * M - hi)
+__global__ void pack_sym64_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_t,
+                                    __half* __restrict__ lo_t) {
+  const int64_t total = (int64_t)tc::h64::NPAD * Kpad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / Kpad), k = (int)(idx - (int64_t)p * Kpad);
+    float v = 0.f;
+    if (p < tc::h64::NPACK) {
+      int i = 0, base = 0;
+      while (p >= base + (64 - i)) { base += 64 - i; ++i; }
+      const int j = i + (p - base);
+      v = scale * M[(int64_t)k * 4096 + i * 64 + j];
+    }
+    const __half h = __float2half_rn(v);
+    hi_t[idx] = h;
+    lo_t[idx] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  if (m > 0.f && isfinite(m)) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// packed [N, 2176] -> full symmetric [N, 64, 64], + lambda on the diagonal
+__global__ void unpack_sym64_kernel(const float* __restrict__ packed, int64_t n, float lambda,
+                                    float* __restrict__ full) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * 4096) return;
+  const int64_t p = gid >> 12;
+  const int e = (int)(gid & 4095), i = e >> 6, j = e & 63;
+  const float v = packed[p * tc::h64::NPAD + (i <= j ? sym64_index(i, j) : sym64_index(j, i))];
+  full[gid] = v + (i == j ? lambda : 0.f);
+}
+
+typedef CUresult (*PFN_encodeTiled64)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+
+static int encode(PFN_encodeTiled64 enc, CUtensorMap* map, void* ptr, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box) {
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (d = 64 tables) failed with CUresult " + std::to_string((int)r));
+    return 4;
+  }
+  return 0;
+}
+
+// Build the d = 64 split-fp16 tables and descriptors (symmetric tables only).  Synchronises `s`.
+int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
+  const int Kpad = t->Kpad, K = t->K;
+  float* stat = nullptr;
+  RLVAE_CUDA_OK(cudaMalloc(&stat, sizeof(float)));
+  RLVAE_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(float), s));
+  absmax_kernel<<<256, 256, 0, s>>>(t->c, (int64_t)Kpad * 64, stat);
+  float cmax = 0.f;
+  RLVAE_CUDA_OK(cudaMemcpyAsync(&cmax, stat, sizeof(float), cudaMemcpyDeviceToHost, s));
+  RLVAE_CUDA_OK(cudaStreamSynchronize(s));
+  cudaFree(stat);
+  if (!(t->m_absmax > 0.f) || !(cmax > 0.f)) return 0;      // degenerate tables: direct path only
+  int ex = 0;
+  frexpf(t->m_absmax, &ex);
+  const int em = 14 - ex;
+  frexpf(cmax, &ex);
+  const int ec = 14 - ex;
+  if (em <= -60 || em >= 60 || ec <= -60 || ec >= 60) return 0;
+  RLVAE_CUDA_OK(cudaMalloc(&t->c64h, sizeof(__half) * (size_t)Kpad * 128));
+  RLVAE_CUDA_OK(cudaMalloc(&t->cbias, sizeof(float) * (size_t)Kpad));
+  RLVAE_CUDA_OK(cudaMalloc(&t->Mh_hi, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad));
+  RLVAE_CUDA_OK(cudaMalloc(&t->Mh_lo, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad));
+  pack_c64_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, K, Kpad, ldexpf(1.f, ec), 1.4426950408889634f / t->T2,
+                                                     static_cast<__half*>(t->c64h), t->cbias);
+  RLVAE_LAUNCH_OK();
+  pack_sym64_h_kernel<<<1184, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, em), static_cast<__half*>(t->Mh_hi),
+                                           static_cast<__half*>(t->Mh_lo));
+  RLVAE_LAUNCH_OK();
+  RLVAE_CUDA_OK(cudaStreamSynchronize(s));
+  t->h16_out_scale = ldexpf(1.f, -(14 + em));
+  t->h16_m_unscale = ldexpf(1.f, -em);
+  t->c64_unscale = ldexpf(1.f, -ec);
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  RLVAE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+  PFN_encodeTiled64 enc = reinterpret_cast<PFN_encodeTiled64>(fn);
+  {   // centroid rows [Kpad, 128] fp16 viewed as [2 atoms][Kpad][64]
+    cuuint64_t dims[3] = {64, (cuuint64_t)Kpad, 2};
+    cuuint64_t strides[2] = {128 * sizeof(__half), 64 * sizeof(__half)};
+    cuuint32_t box[3] = {64, tc::BK, 2};
+    if (int rc = encode(enc, &t->tm_c64, t->c64h, 3, dims, strides, box)) return rc;
+    cuuint32_t box2[3] = {64, tc::BK / 2, 2};
+    if (int rc = encode(enc, &t->tm_c64_2, t->c64h, 3, dims, strides, box2)) return rc;
+  }
+  {   // table tiles [2176, Kpad] fp16: box = 64 centroids x 128 (pair: 64) rows
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)tc::h64::NPAD};
+    cuuint64_t strides[1] = {(cuuint64_t)Kpad * sizeof(__half)};
+    cuuint32_t box[2] = {tc::BK, tc::h64::NT};
+    if (int rc = encode(enc, &t->tm_mh_hi, t->Mh_hi, 2, dims, strides, box)) return rc;
+    if (int rc = encode(enc, &t->tm_mh_lo, t->Mh_lo, 2, dims, strides, box)) return rc;
+    cuuint32_t box2[2] = {tc::BK, tc::h64::NT / 2};
+    if (int rc = encode(enc, &t->tm_mh2_hi, t->Mh_hi, 2, dims, strides, box2)) return rc;
+    if (int rc = encode(enc, &t->tm_mh2_lo, t->Mh_lo, 2, dims, strides, box2)) return rc;
+  }
+  return 0;
+}
+
+static bool h64_use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RLVAE_TC_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool PAIR>
+static int launch_h64(const rlvae_tables* t, const float* z, int64_t n, float* packed, cudaStream_t s) {
+  auto kern = tc::inverse_metric_h64_kernel<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::h64::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, tc::h64::NPAD / tc::h64::NT, 1);
+  cfg.blockDim = dim3(tc::h64::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::h64::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  const float cu = t->c64_unscale, os = t->h16_out_scale;
+  if (PAIR) {
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64_2, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, alpha,
+                                       cu, os, packed));
+  } else {
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, alpha,
+                                       cu, os, packed));
+  }
+  return 0;
+}
+
+// d = 64, symmetric tables: z -> full G^{-1} [N,64,64] through the packed [N,2176] scratch
+int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, float* ginv, float* packed_scratch,
+                              cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 64 && t->symmetric && t->c64h != nullptr, "d = 64 tensor path needs symmetric tables");
+  RLVAE_REQUIRE(packed_scratch != nullptr, "d = 64 tensor path needs the packed scratch buffer");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_scratch) & 15) == 0,
+                "tensor path needs 16-byte aligned z and scratch");
+  if (int rc = h64_use_pairs() ? launch_h64<true>(t, z, n, packed_scratch, s)
+                               : launch_h64<false>(t, z, n, packed_scratch, s))
+    return rc;
+  const int64_t total = n * 4096;
+  unpack_sym64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(packed_scratch, n, t->lambda, ginv);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace rlvae

@@ -363,23 +363,47 @@ def test_metric_construction_matches_reference(case):
     torch.testing.assert_close(metric_builder.matrices_from_cholesky_factors(lf), lf @ lf.transpose(1, 2))
 
 
-def test_latent_dim_64_direct_path():
-    """BASELINE.json configs[4] shape family (d = 64): the direct kernels and the d = 64 per-point
-    inverse against the CPU oracle (small K, N so the oracle's [n,K,d,d] stays small)."""
+def test_latent_dim_64_paths():
+    """BASELINE.json configs[4] shape family (d = 64): the direct kernels AND the split-fp16 tensor
+    kernel (column-tiled, fp16 distance GEMM) + the d = 64 per-point inverse against the CPU oracle
+    (small K, N so the oracle's [n,K,d,d] stays small)."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
-    sm = make_synthetic_metric(96, 64, seed=3)
+    sm = make_synthetic_metric(200, 64, seed=3)
     t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
-    z = make_points(130, 64, seed=4)
-    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=32)
+    z = make_points(300, 64, seed=4)
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=20)
     ref_g = torch.linalg.inv(ref_ginv)
     ref_ld = torch.linalg.slogdet(ref_g).logabsdet
-    ref_grad = O.chunked(O.grad_log_sqrt_det_ginv_exact, z, *t, chunk=32) * -2.0
-    mt = make_mt(t, 'auto')
-    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
-    assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT
-    assert rel_fro(ev['g'].cpu(), ref_g) < 5e-5
-    close_ld(ev['logdet_g'], ref_ld)
-    assert rel_fro(ev['grad_logdet_g'].cpu(), ref_grad) < TOL_LD
+    ref_grad = O.chunked(O.grad_log_sqrt_det_ginv_exact, z[:64], *t, chunk=16) * -2.0
+    paths = paths_for(t)
+    assert 'tensor' in paths, 'the d = 64 tensor path should be selected for these tables'
+    for path in paths:
+        mt = make_mt(t, path)
+        ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+        assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT, path
+        assert rel_fro(ev['g'].cpu(), ref_g) < 5e-5, path
+        close_ld(ev['logdet_g'], ref_ld)
+        assert rel_fro(ev['grad_logdet_g'].cpu()[:64], ref_grad) < TOL_LD, path
+        assert rel_fro(mt.compute_inverse_metric(z.to(dev())).cpu(), ref_ginv) < TOL_MAT, path
+    # ragged batches around the tile sizes on the tensor path
+    mt = make_mt(t, 'tensor')
+    for n in (1, 127, 129, 257):
+        got = mt.compute_inverse_metric(z[:n].to(dev()))
+        assert rel_fro(got.cpu(), ref_ginv[:n]) < TOL_MAT, n
+
+
+def test_latent_dim_64_large_k_tensor_vs_direct():
+    """d = 64 with K = 5,000 centroids: the tensor kernel against the direct kernel on 512 points."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(5000, 64, seed=5)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    if 'tensor' not in paths_for(t):
+        pytest.skip('tensor path not selected for these tables')
+    z = make_points(512, 64, seed=6).to(dev())
+    a = make_mt(t, 'direct').evaluate(z, want_ginv=True, want_logdet=True)
+    b = make_mt(t, 'tensor').evaluate(z, want_ginv=True, want_logdet=True)
+    assert rel_fro(b['ginv'].cpu(), a['ginv'].cpu()) < TOL_MAT
+    close_ld(b['logdet_g'], a['logdet_g'])
 
 
 @pytest.mark.parametrize('case', ['hmc_d16_k300', 'hmc_d16_k300_beta03'])
