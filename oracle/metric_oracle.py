@@ -331,3 +331,44 @@ def build_local_metrics(all_mus, centroids, temperature, regularization):
             metric = metric + (1e-6 - min_eig) * torch.eye(d, dtype=all_mus.dtype)
         out.append(metric)
     return torch.stack(out, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# A8: pythae RHVAESampler.hmc_sampling (variant C), what OfficialRHVAESampler.sample_prior runs
+def rhvae_log_pi(z, c, M, T, lam):
+    """rhvae_sampler.py:157-158: log(sqrt(det G^{-1}) + 1e-10)."""
+    return torch.log(torch.sqrt(torch.det(inverse_metric(z, c, M, T, lam))) + 1e-10)
+
+
+def rhvae_hmc_sample(tables, idx0, gammas, accs, n_lf, eps_lf, beta_zero=1.0, record=None):
+    """src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:98-148 with the RNG draws
+    injected: ``idx0`` replaces the randint of line 100 (z0 = centroids[idx0]), ``gammas[i]`` the
+    randn_like of line 107, ``accs[i]`` the rand of line 141.  alpha is NOT clamped and has no
+    epsilon (line 140); the tempering state is not reset between MCMC iterations (line 104)."""
+    c, M, T, lam = tables
+    b0 = float(beta_zero) ** 0.5
+    beta_old = b0
+    z0 = c[idx0]
+    z = z0
+    n, d = z.shape
+    for i in range(gammas.shape[0]):
+        rho = gammas[i] / b0
+        H0 = -rhvae_log_pi(z, c, M, T, lam) + 0.5 * torch.norm(rho, dim=1) ** 2
+        for k in range(n_lf):
+            g = -grad_pythae(z, c, M, T, lam).reshape(n, d)
+            rho_ = rho - (eps_lf / 2) * g
+            z = z + eps_lf * rho_
+            g = -grad_pythae(z, c, M, T, lam).reshape(n, d)
+            rho__ = rho_ - (eps_lf / 2) * g
+            beta_new = 1.0 / (((1 - 1 / b0) * ((k + 1) / n_lf) ** 2) + 1 / b0)
+            rho = (beta_old / beta_new) * rho__
+            beta_old = beta_new
+        H = -rhvae_log_pi(z, c, M, T, lam) + 0.5 * torch.norm(rho, dim=1) ** 2
+        alpha = torch.exp(-H) / torch.exp(-H0)
+        moves = (accs[i] < alpha).to(torch.int).reshape(n, 1)
+        z = z * moves + (1 - moves) * z0
+        z0 = z
+        if record is not None:
+            for name, val in (('H0', H0), ('H', H), ('alpha', alpha), ('moves', moves.reshape(-1)), ('z', z.clone())):
+                record.setdefault(name, []).append(val)
+    return z

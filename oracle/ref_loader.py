@@ -41,7 +41,7 @@ _cache = {}
 
 def modules():
     """-> dict(metric_tensor, metric_loader, base_sampler, hmc_sampler, riemannian_sampler)."""
-    if _cache:
+    if 'metric_tensor' in _cache:
         return _cache
     if not available():
         raise RuntimeError(f'reference checkout not found under {REF_ROOT}')

@@ -7,9 +7,9 @@ Drop-in names for the reference's hot-path API: ``MetricTensor`
 from .flow_manager import FlowManager
 from .metric_loader import MetricLoader
 from .metric_tensor import MetricTensor
-from .samplers import (BaseRiemannianSampler, MetricModel, RiemannianHMCSampler,
+from .samplers import (BaseRiemannianSampler, MetricModel, RHVAEStyleHMCSampler, RiemannianHMCSampler,
                        WorkingRiemannianSampler)
 
 __all__ = ['MetricTensor', 'MetricLoader', 'BaseRiemannianSampler', 'MetricModel',
-           'RiemannianHMCSampler', 'WorkingRiemannianSampler', 'FlowManager']
+           'RiemannianHMCSampler', 'RHVAEStyleHMCSampler', 'WorkingRiemannianSampler', 'FlowManager']
 __version__ = '0.1.0'

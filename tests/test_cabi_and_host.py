@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     # argument validation happens before any CUDA call: safe without a GPU
     assert h.rlvae_inverse_metric(None, None, 4, None, None, 0, None) != 0
     assert b'not loaded' in h.rlvae_last_error()
-    assert h.rlvae_metric_eval_workspace(10, 16) == 4 * (3 * 10 * 256 + 10)
+    assert h.rlvae_metric_eval_workspace(10, 16) == 4 * (3 * 10 * 256 + 10 + 4)
 
 
 def test_no_product_module_imports_the_oracle():

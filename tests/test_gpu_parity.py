@@ -441,6 +441,31 @@ def test_hmc_matches_reference_chain(case):
         assert mism == 0, f'{mism} accept decisions differ'
 
 
+@pytest.mark.parametrize('case', ['rhvae_hmc_d16_k120', 'rhvae_hmc_d16_k120_beta03'])
+def test_pythae_variant_hmc_matches_reference_chain(case):
+    """A8: RHVAESampler.hmc_sampling (what OfficialRHVAESampler.sample_prior runs): same RNG stream ->
+    same accept decisions and final state as the real pythae code; per-iteration values vs the oracle."""
+    from rlvae_b200 import MetricModel, RHVAEStyleHMCSampler
+    g = load_golden(case)
+    t = tables_of(g)
+    rec = {}
+    O.rhvae_hmc_sample(t, g['idx0'], g['gamma'], g['acc'], int(g['n_lf']), float(g['eps_lf']),
+                       float(g['beta_zero']), record=rec)
+    for path in paths_for(t):
+        s = RHVAEStyleHMCSampler(MetricModel(make_mt(t, path)), mcmc_steps_nbr=g['gamma'].shape[0],
+                                 n_lf=int(g['n_lf']), eps_lf=float(g['eps_lf']), beta_zero=float(g['beta_zero']))
+        got = {}
+        zf = s.hmc_sampling_with_streams(g['idx0'].to(dev()), g['gamma'].to(dev()), g['acc'].to(dev()), record=got)
+        for i in range(g['gamma'].shape[0]):
+            flip = got['moves'][i].cpu() != rec['moves'][i]
+            assert torch.all((g['acc'][i][flip] - rec['alpha'][i][flip]).abs() < 1e-4 * (1 + rec['alpha'][i][flip].abs()))
+            assert int(flip.sum()) == 0
+            close_ld(got['H0'][i], rec['H0'][i], 1e-4)
+        torch.testing.assert_close(zf.cpu(), g['z_final'], rtol=2e-4, atol=2e-4)
+        assert s.sample_prior(5).shape == (5, 16)
+        assert s.get_sampler_info()['n_lf'] == int(g['n_lf'])
+
+
 @pytest.mark.parametrize('case', ['samplers_metricpt_T07', 'samplers_synth_d16_k300'])
 def test_samplers_match_reference(case):
     from rlvae_b200 import MetricModel, RiemannianHMCSampler, WorkingRiemannianSampler, _capi

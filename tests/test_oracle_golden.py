@@ -108,3 +108,14 @@ def test_metric_construction_oracle_matches_reference_lines(case):
     g = load_golden(case)
     got = O.build_local_metrics(g['latents'], g['centroids'], float(g['temperature']), float(g['regularization']))
     torch.testing.assert_close(got, g['M'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('case', ['rhvae_hmc_d16_k120', 'rhvae_hmc_d16_k120_beta03'])
+def test_pythae_hmc_oracle_matches_reference_chain(case):
+    """oracle.rhvae_hmc_sample vs the final state of the real RHVAESampler.hmc_sampling
+    (oracle/make_golden_rhvae.py) under the recorded RNG stream."""
+    g = load_golden(case)
+    t = tables_of(g)
+    z = O.rhvae_hmc_sample(t, g['idx0'], g['gamma'], g['acc'], int(g['n_lf']), float(g['eps_lf']),
+                           float(g['beta_zero']))
+    torch.testing.assert_close(z, g['z_final'], rtol=1e-5, atol=1e-5)
