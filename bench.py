@@ -13,7 +13,8 @@ Extra keys: `roofline` (the fused metric + log-det tcgen05 kernel, tensor bound,
 MEASURED_PEAKS.json's bf16 burst rate; `roofline_gradient_kernel` is the same for the gradient kernel),
 `cpu_baseline` (the CPU oracle port on a bounded sample, rank 0 / N=1 only), `e2e` (host-buffer
 API: pinned H2D of z, evaluation, D2H of log det + grad, per step), `hmc` (config[2]: chain
-leapfrog steps/s, 2^20 chains x 20 leapfrog), `clocks`, `gpu_launches`.
+leapfrog steps/s, 2^20 chains x 20 leapfrog), `flow` (config[3]: 65,536 sequences x 10 flow steps, metric
+spectrum per step), `clocks`, `gpu_launches`.
 
 `--impl reference` times the reference's own algorithm on the host cores (the CPU oracle port of
 its eager PyTorch code -- the reference is Python and is not present on the GPU box).
@@ -376,6 +377,32 @@ def run_ours(args):
     except Exception as e:   # never lose the headline because of the secondary measurement
         hmc = {'error': str(e)[:200]}
 
+    # ---- FlowManager temporal flow (BASELINE.json configs[3]): B = 65,536 sequences x 10 timesteps,
+    # flows in stock torch, then ONE fused metric evaluation (log det G + spectrum) over [B*T, d]
+    flow = None
+    try:
+        from rlvae_b200 import FlowManager
+        torch.manual_seed(7)
+        fm = FlowManager(latent_dim=D, n_flows=8, device=dev).to(dev).eval()
+        zf0 = torch.randn(65536, D, device=dev)
+        with torch.no_grad():
+            fm.metric_along_flow(mt, zf0, n_obs=10, want_spectrum=True)      # warm-up
+            barrier()
+            e0, e1, e2 = torch.cuda.Event(True), torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            z_seq, _ = fm.apply_flows([zf0], n_obs=10)
+            e1.record()
+            zz = torch.stack(z_seq, dim=1).reshape(-1, D).contiguous()
+            sp = mt.compute_metric_spectrum(zz)
+            e2.record(); e2.synchronize()
+        f_ms, m_ms = max_over_ranks(e0.elapsed_time(e1)), max_over_ranks(e1.elapsed_time(e2))
+        flow = {'sequences_per_gpu': 65536, 'timesteps': 10, 'apply_flows_ms': f_ms,
+                'metric_spectrum_ms': m_ms, 'metric_evals_per_sec': world * 655360 / (m_ms * 1e-3),
+                'finite': bool(torch.isfinite(sp['logdet_G']).all().item())}
+        del fm, zf0, z_seq, zz, sp
+    except Exception as e:
+        flow = {'error': str(e)[:200]}
+
     if rank == 0:
         cpu = None
         if world == 1:
@@ -393,7 +420,7 @@ def run_ours(args):
                            'parallelism': f'points sharded over {world} GPU(s), tables replicated',
                            'l2': 'L2 flushed (256 MB write) before every timed step; each step also '
                                  'writes >2 GB of outputs'},
-                'roofline': roof, 'roofline_gradient_kernel': roof_grad, 'cpu_baseline': cpu, 'e2e': e2e, 'hmc': hmc, 'clocks': clocks,
+                'roofline': roof, 'roofline_gradient_kernel': roof_grad, 'cpu_baseline': cpu, 'e2e': e2e, 'hmc': hmc, 'flow': flow, 'clocks': clocks,
                 'gpu_launches': launches_timed,
                 'tflops_fp32_equiv': value * flops_per_eval(True) / 1e12}
         print(json.dumps(line))

@@ -391,11 +391,15 @@ static bool use_h16(const rlvae_tables* t) {
 
 // Symmetric tables on the tensor path: packed G^{-1} [N,144] into a_packed plus any of
 // { packed G, lad_scale * log|det G^{-1}|, sign, diag(G) }.  fail_ws: 1 + n ints.
+// a_full (optional): the expanded [N,16,16] G^{-1} as well (same kernel on the split-fp16 path).
 static int sym_forward(const rlvae_tables* t, const float* z, int64_t n, float* a_packed, float* g_packed,
-                       float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s) {
+                       float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s,
+                       float* a_full = nullptr) {
   if (use_h16(t))
-    return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s);
+    return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s, a_full);
+  RLVAE_REQUIRE(a_packed != nullptr, "symmetric 3xTF32 path needs the packed buffer");
   if (int rc = launch_inverse_metric_tc_sym(t, z, n, a_packed, s)) return rc;
+  if (a_full != nullptr) { if (int rc = launch_unpack_sym16(a_packed, n, a_full, s)) return rc; }
   if (g_packed || lad || sgn || diag)
     return launch_sym16_inverse(a_packed, n, g_packed, lad, lad_scale, sgn, diag, fail_ws, s);
   return 0;
@@ -427,11 +431,11 @@ int rlvae_inverse_metric(const rlvae_tables_t* t, const float* z, int64_t n, flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!use_tc) return launch_inverse_metric_direct(t, z, n, ginv, s);
   if (t->d == 64) return inverse_metric_full(t, z, n, ginv, path, s, static_cast<float*>(work));
-  if (t->symmetric && t->Mts_hi != nullptr && work != nullptr) {
-    // symmetric tables: accumulate the 136 packed entries, then expand to [N,16,16]
-    float* packed = static_cast<float*>(work);
-    if (int rc = sym_forward(t, z, n, packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr, s)) return rc;
-    return launch_unpack_sym16(packed, n, ginv, s);
+  if (t->symmetric && t->Mts_hi != nullptr && (work != nullptr || use_h16(t))) {
+    // symmetric tables: accumulate the 136 packed entries; the split-fp16 kernel expands them to
+    // [N,16,16] in its epilogue, the 3xTF32 kernel goes through the packed workspace
+    float* packed = use_h16(t) ? nullptr : static_cast<float*>(work);
+    return sym_forward(t, z, n, packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr, s, ginv);
   }
   return launch_inverse_metric_tc(t, z, n, ginv, s);
 }
@@ -522,8 +526,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     // kernel contracts the packed G directly (G^T == G).  The spare tail of a_buf is the fallback list.
     float* g_packed = (g != nullptr || grad_logdet_g != nullptr) ? (w + mat) : nullptr;
     int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
-    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s)) return rc;
-    if (ginv != nullptr) { if (int rc = launch_unpack_sym16(a_buf, n, ginv, s)) return rc; }
+    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv)) return rc;
     if (g != nullptr) { if (int rc = launch_unpack_sym16(g_packed, n, g, s)) return rc; }
     if (grad_logdet_g != nullptr)
       return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);

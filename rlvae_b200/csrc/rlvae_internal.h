@@ -128,9 +128,10 @@ int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, 
 constexpr int kSym64Cols = 2176;
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);
+// a_full (optional): the expanded [N,16,16] G^{-1}, written by the same kernel
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s);
+                              int* fail_ws, cudaStream_t s, float* a_full = nullptr);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,

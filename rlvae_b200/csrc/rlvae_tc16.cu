@@ -142,6 +142,7 @@ __device__ __forceinline__ bool sym16_factor(float (&a)[144], float& lad, float 
 #undef SYM_L
 
 struct FusedOut {
+  float* a_full;       // [N,16,16] G^{-1} expanded (what the reference API returns) or NULL
   float* a_packed;     // [N,144] G^{-1} (lambda on the diagonal) or NULL
   float* g_packed;     // [N,144] G or NULL
   float* logabsdet;    // [N] lad_scale * log det G^{-1} or NULL
@@ -517,6 +518,33 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     if (fo.a_packed != nullptr) store_rows(fo.a_packed);
+    if (fo.a_full != nullptr) {
+      // full symmetric [rows, 256] through smem (row stride 260 floats: conflict-free 128-bit accesses);
+      // the staging area spans the centroid ring and the table ring, both idle by now
+      constexpr int FLD = 260;
+      static_assert(TILE_M * FLD * 4 <= h16::OFF_BIAS, "full-matrix staging must fit the C + M rings");
+      float* fstage = reinterpret_cast<float*>(gbase + h16::OFF_C);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            v[e] = total[i <= j ? sym_index(i, j) : sym_index(j, i)];
+          }
+          *reinterpret_cast<float4*>(fstage + prow * FLD + i * 16 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float4* dst = reinterpret_cast<float4*>(fo.a_full + row0 * 256);
+      for (int i = t; i < (int)rows_here * 64; i += 128) {
+        const int r = i >> 6, c4 = i & 63;
+        dst[i] = *reinterpret_cast<const float4*>(fstage + r * FLD + c4 * 4);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     const bool fused = fo.g_packed != nullptr || fo.logabsdet != nullptr || fo.sign != nullptr || fo.diag_g != nullptr;
     if (fused) {
       if (!live) {
@@ -1179,7 +1207,7 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
 // which needs packed G^{-1}: a_packed must be given whenever a factor output is requested).
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s) {
+                              int* fail_ws, cudaStream_t s, float* a_full) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr,
                 "split-fp16 tensor path needs latent_dim == 16 and symmetric tables");
@@ -1189,7 +1217,8 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
                 "fused factor outputs need the packed G^{-1} buffer and the fallback workspace");
   RLVAE_REQUIRE(n < (int64_t)1 << 31, "batch too large for the 32-bit fallback list");
   if (fused) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
-  tc::FusedOut fo{a_packed, g_packed, logabsdet, sign, diag_g, fail_ws, lad_scale};
+  RLVAE_REQUIRE(a_full == nullptr || (reinterpret_cast<uintptr_t>(a_full) & 15) == 0, "G^-1 output must be 16-byte aligned");
+  tc::FusedOut fo{a_full, a_packed, g_packed, logabsdet, sign, diag_g, fail_ws, lad_scale};
   if (int rc = h16_use_pairs() ? launch_h16<true>(t, z, n, fo, s) : launch_h16<false>(t, z, n, fo, s)) return rc;
   if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
   return 0;

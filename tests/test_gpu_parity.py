@@ -194,6 +194,30 @@ def test_full_size_properties_config2():
     assert (fd - an).abs().max().item() < 5e-3 * (1 + an.abs().max().item())
 
 
+def test_hmc_full_size_properties_config3():
+    """BASELINE.json configs[2] size (2^20 chains, d = 16, K = 10k; 3 leapfrog steps to stay short):
+    finite, deterministic, accept mask consistent with the returned state, and slicing-invariant."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    from rlvae_b200.synthetic import make_hmc_streams, make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    n = 1 << 20
+    z0, gam, acc = make_hmc_streams(n, 16, 1, seed=2)
+    z0, gam, acc = z0.to(dev()), gam.to(dev()), acc.to(dev())
+    s = RiemannianHMCSampler(MetricModel(make_mt(t, 'auto')), mcmc_steps_nbr=1, n_lf=3, eps_lf=0.03)
+    rec = {}
+    z1 = s.sample_with_streams(z0, gam, acc, record=rec)
+    z2 = s.sample_with_streams(z0, gam, acc)
+    assert torch.isfinite(z1).all() and torch.equal(z1, z2)
+    moves = rec['moves'][0].bool()
+    assert 0.5 < moves.float().mean().item() <= 1.0
+    assert torch.equal(z1[~moves], z0[~moves])                      # rejected chains stay where they were
+    assert (z1[moves] != z0[moves]).any(dim=1).all()
+    lo, hi = 4321, 4321 + 5003                                        # a ragged slice reproduces the same chains
+    zp = s.sample_with_streams(z0[lo:hi].contiguous(), gam[:, lo:hi].contiguous(), acc[:, lo:hi].contiguous())
+    torch.testing.assert_close(zp, z1[lo:hi], rtol=1e-5, atol=1e-6)
+
+
 def test_linearity_in_tables():
     """G^{-1} - lambda I is linear in M: eval(M1 + M2) == eval(M1) + eval(M2) - lambda I."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
