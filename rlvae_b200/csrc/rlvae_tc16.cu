@@ -21,7 +21,8 @@
 //
 //   TMEM columns: [0,192) three S/P buffers (64 each: S fp32, overwritten in place by
 //                 P_hi[0:32) | P_lo[0:32) | P_hi[32:64) | P_lo[32:64) as packed fp16),
-//                 [192,336) and [352,496) the two chunk accumulators (N = 144).
+//                 [192,336) and [352,496) the two chunk accumulators (N = 144),
+//                 [336,352) z_hi and [496,512) z_lo (TF32 split of z: the A operand of GEMM1).
 //   Warp roles  : as in rlvae_tc.cu (TMA warp, MMA warp, two exp warpgroups, one fold warpgroup).
 //   FUSED       : the fold warpgroup keeps the finished 136 entries of its point in registers and
 //                 runs the per-thread Cholesky of rlvae_perpoint.cu on them, so log det G and
@@ -158,7 +159,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const __grid_constant__ CUtensorMap tm_mh_hi,
                           const __grid_constant__ CUtensorMap tm_mh_lo,
                           const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
-                          int num_blocks, int chunk_blocks, float alpha /* log2(e)/T^2 */, float lambda,
+                          int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
                           float out_scale /* 2^-(14+e) */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
@@ -167,7 +168,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                      TM_ACC = h16::TM_ACC, TM_ZHI = h16::TM_ZHI, TM_ZLO = h16::TM_ZLO;
   constexpr float P_SHIFT = h16::P_SHIFT;
   constexpr int CB = 2;     // super-blocks per tensor-core accumulation chunk (compile-time: see the MMA issuer)
-  (void)THREADS; (void)chunk_blocks;
+  (void)THREADS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -1186,17 +1187,11 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   const int nb = t->Kpad / tc::BK;
   const float lambda = t->lambda;
   const float out_scale = t->h16_out_scale;
-  static int chunk_blocks = 0;
-  if (chunk_blocks == 0) {
-    const char* e = getenv("RLVAE_TC_CHUNK");
-    chunk_blocks = (e != nullptr && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : tc::CHUNK_BLOCKS;
-  }
-  const int cb = chunk_blocks;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, cb,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb,
                                      alpha, lambda, out_scale, fo));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, cb,
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb,
                                      alpha, lambda, out_scale, fo));
   }
   return 0;
