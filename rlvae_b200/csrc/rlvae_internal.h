@@ -79,6 +79,7 @@ struct rlvae_tables {
   CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
   CUtensorMap tm_mn2_hi, tm_mn2_lo, tm_mns_hi, tm_mns_lo, tm_mns2_hi, tm_mns2_lo;
   CUtensorMap tm_ct_hi, tm_ct_lo, tm_ct2_hi, tm_ct2_lo;
+  CUtensorMap tm_ct16_hi, tm_ct16_lo, tm_ct8_hi, tm_ct8_lo;   // boxes of 32 centroids x 16 (pair: 8) rows
   // split-fp16 tables (symmetric, d == 16): fp16(2^e M) and fp16 residual, packed-transposed [144, Kpad]
   void* Mh_hi = nullptr;
   void* Mh_lo = nullptr;

@@ -1306,6 +1306,11 @@ int tc_build_descriptors(rlvae_tables* t) {
   if (int rc = make_map_2d(enc, &t->tm_ct_lo, t->ct_lo, Kpad, 32, 32, 32)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct2_hi, t->ct_hi, Kpad, 32, 32, 16)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct2_lo, t->ct_lo, Kpad, 32, 32, 16)) return rc;
+  // split-fp16 gradient kernel: only the 16 c^T rows (N = 16), pair: 8 rows per CTA
+  if (int rc = make_map_2d(enc, &t->tm_ct16_hi, t->ct_hi, Kpad, 32, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct16_lo, t->ct_lo, Kpad, 32, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_hi, t->ct_hi, Kpad, 32, 32, 8)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_lo, t->ct_lo, Kpad, 32, 32, 8)) return rc;
   return 0;
 }
 

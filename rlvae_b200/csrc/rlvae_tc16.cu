@@ -603,9 +603,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 //           U' = 2^eU Ut (per point, max|U'| in [2^13, 2^14)), Ut_p = U_ij + U_ji (i<j), U_ii: valid for
 //           ANY U; M' = 2^eM M as in the forward kernel.  U' (hi|lo fp16) is resident in TMEM.
 //   exp     u = exp2(..) * t, split u_hi | u_lo (fp32 / TF32), written over S | T
-//   GEMM3   OUT[128 x 32] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo   (3xTF32; Ct = [c^T ; 1 ; 0])
+//   GEMM3   OUT[128 x 16] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo   (3xTF32, N = 16; Ct = c^T; sum_k u is
+//           accumulated by the exp threads themselves: one FADD per element instead of 16 more columns)
 // OUT accumulates in two alternating chunk accumulators (2 super-blocks each) that the exp groups
-// fold into fp32 registers.  out = scale 2^-(eU+eM) (OUT[:, :16] - z OUT[:, 16]).
+// fold into fp32 registers.  out = scale 2^-(eU+eM) (OUT - z sum_k u).
 // TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2,
 //       [464,496) z_hi | z_lo (TF32 split, A operand of GEMM1).
 // ==========================================================================================
@@ -614,7 +615,7 @@ constexpr int THREADS = 384;        // TMA warp (C), MMA warp, 2 exp groups of 4
 constexpr int C_STAGES = 4;
 constexpr int M_STAGES = 2;                          // one stage = hi AND lo tile of a super-block
 constexpr int KSTEPS = 9;                           // 144 packed columns / 16
-constexpr uint32_t CT_TILE_BYTES = 2 * 32 * 128;    // [32 rows x 64 centroids] fp32 = 2 atoms of 32 centroids
+constexpr uint32_t CT_TILE_BYTES = 2 * 16 * 128;    // [16 rows (c^T) x 64 centroids] fp32 = 2 atoms of 32 centroids
 constexpr uint32_t M_HALF_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
 constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;
 constexpr uint32_t OFF_C = 0;                       // (z lives in TMEM: no A tiles in shared memory)
@@ -622,12 +623,12 @@ constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_M = OFF_CT + C_STAGES * 2 * CT_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
-constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 9;
+constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400, TM_ZHI = 464, TM_ZLO = 480;
-constexpr int RED_LD = 36;
+constexpr int RED_LD = 20;
 }  // namespace g16
 
 __device__ __forceinline__ void split_pair_scaled(float even, float odd, float sc, uint32_t& hi2, uint32_t& lo2) {
@@ -667,6 +668,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 4 + b); };
   auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 6 + b); };
   const uint32_t BAR_DONE = bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 8);
+  auto BAR_G3_DONE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 9 + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + g16::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -679,12 +681,12 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   constexpr uint32_t ATOM_BYTES = ROWS_CTA * 128;                   // M tile atom held by this CTA
   constexpr uint32_t TILE_BYTES = 3 * ATOM_BYTES;
   constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
-  constexpr uint32_t CT_ROWS = PAIR ? 16 : 32;
+  constexpr uint32_t CT_ROWS = PAIR ? 8 : 16;
   constexpr uint32_t CT_ATOM_BYTES = CT_ROWS * 128;
   constexpr uint32_t CT_BYTES = 2 * CT_ATOM_BYTES;                  // per hi / lo tile per CTA
   constexpr uint32_t CT_ATOM_DESC = CT_ATOM_BYTES >> 4;
   constexpr uint32_t IDESC_T = make_idesc_f16(PAIR ? 256 : 128, BK);
-  constexpr uint32_t IDESC_3 = make_idesc(PAIR ? 256 : 128, 32);
+  constexpr uint32_t IDESC_3 = make_idesc(PAIR ? 256 : 128, 16);   // N = 16: the 16 components of sum_k u c_k
   const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
 
   if (warp == 0 && lane == 0) {
@@ -698,6 +700,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
     }
     mbar_init(BAR_DONE, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(BAR_G3_DONE(b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
@@ -827,7 +830,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
   if (warp == 0) {
-    // =========================================================== TMA producer 1: centroid tiles + bias
+    // =========================================================== TMA producer 1: centroid tiles + bias,
+    // then the Ct tiles (hi, lo) of the same block: [32 (pair: 16) rows x 64 centroids] as two
+    // 32-centroid atoms each
     for (int j = 0; j < num_blocks; ++j) {
       const int cs = j % C_STAGES;
       mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
@@ -842,6 +847,23 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         }
         mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
+      }
+      __syncwarp();
+      mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
+        const uint32_t dst = base + OFF_CT + cs * 2 * CT_TILE_BYTES;
+        const int row = PAIR ? 8 * (int)rank : 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (PAIR) {
+            tma_load_2d_pair(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d_pair(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          } else {
+            tma_load_2d(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          }
+        }
       }
       __syncwarp();
     }
@@ -864,45 +886,24 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
       __syncwarp();
     }
-  } else if (warp == 11) {
-    // =========================================================== TMA producer 3: Ct tiles (hi, lo):
-    // [32 (pair: 16) rows x 64 centroids] as two 32-centroid atoms each
-    for (int j = 0; j < num_blocks; ++j) {
-      const int cs = j % C_STAGES;
-      mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
-      if (elect_one()) {
-        if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
-        const uint32_t dst = base + OFF_CT + cs * 2 * CT_TILE_BYTES;
-        const int row = PAIR ? 16 * (int)rank : 0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          if (PAIR) {
-            tma_load_2d_pair(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
-            tma_load_2d_pair(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
-          } else {
-            tma_load_2d(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
-            tma_load_2d(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
-          }
-        }
-      }
-      __syncwarp();
-    }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (warp-converged; pair: leader only)
+    // =========================================================== MMA issuer 1 (pair: leader only):
+    // [GEMM1, T-GEMM] of every super-block.  The final contraction (GEMM3) is issued by a SECOND warp
+    // (warp 11): with one issuer the 57 MMAs per super-block made the kernel issue-bound (measured:
+    // ~26 cycles of issue per MMA against 1.44k cycles of tensor time).  The two streams touch disjoint
+    // TMEM regions; their only ordering constraint -- S|T(j+2) overwrites the buffer GEMM3(j) reads --
+    // is the G3_DONE barrier.  Unrolled 4x: stage indices and parities are compile-time constants.
     if (leader) {
-      // Unrolled 4x (2 S|T buffers, 2 OUT chunks of 2 blocks, 4 C stages, 2 M stages): stage indices,
-      // TMEM addresses and most barrier parities are compile-time constants (see the forward kernel).
-      static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loop assumes these periods");
+      static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loops assume these periods");
       const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
       const uint64_t m_desc0 = make_desc_sw128(base + OFF_M);
-      const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
       constexpr uint32_t ID1 = make_idesc(PAIR ? 256 : 128, BK);
-      // [GEMM1, T-GEMM] of the block with residue JJ = j mod 4 into S|T buffer j&1
-      auto issue_st = [&](auto Jc, const uint32_t c_parity) {
-        constexpr int JJ = decltype(Jc)::value;
-        constexpr int cs = JJ % C_STAGES, sb = JJ & 1, ms = JJ % M_STAGES;
-        mbar_wait(BAR_C_FULL(cs), c_parity);
-        mbar_wait(BAR_M_FULL(ms), (JJ / M_STAGES) & 1);
+      auto issue_st = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
+        constexpr int J = decltype(Jc)::value;
+        constexpr int cs = J % C_STAGES, sb = J & 1, ms = J % M_STAGES;
+        mbar_wait(BAR_C_FULL(cs), qodd);
+        mbar_wait(BAR_M_FULL(ms), (J / M_STAGES) & 1);
+        if (j >= 2) mbar_wait(BAR_G3_DONE(sb), ((J >> 1) + 1) & 1);     // GEMM3(j-2) has consumed this buffer
         tc_fence_after();
         const uint32_t s_t = tmem_base + TM_ST + sb * 128;
         const uint32_t t_t = s_t + 64;
@@ -930,11 +931,20 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         }
         __syncwarp();
       };
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 4, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) issue_st(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3)
+#undef RLVAE_BLK
+      }
+    }
+  } else if (warp == 11) {
+    // =========================================================== MMA issuer 2 (pair: leader only): GEMM3
+    if (leader) {
+      const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
       uint32_t free_phase = 0;     // bit b: parity of the next CH_FREE(b) completion to wait for
-      auto block = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
+      auto issue_g3 = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
         constexpr int J = decltype(Jc)::value;
-        // S|T(j+1) first: its buffer was released by GEMM3(j-1), already queued ahead in the pipe
-        if (j + 1 < num_blocks) issue_st(std::integral_constant<int, (J + 1) % 4>{}, (qodd + (J + 1) / 4) & 1u);
         constexpr int cs = J % C_STAGES, sb = J & 1, cb = (J >> 1) & 1;
         constexpr int first = (J % CHUNK) == 0;
         if (first && j >= 2 * CHUNK) {
@@ -960,14 +970,14 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           for (int kk = 0; kk < 8; ++kk)
             MMA_TS(acc, u_hi + 8 * kk, cl + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
           COMMIT(BAR_CT_EMPTY(cs));
+          COMMIT(BAR_G3_DONE(sb));
           if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(cb));
         }
         __syncwarp();
       };
-      issue_st(std::integral_constant<int, 0>{}, 0u);
       uint32_t qodd = 0;
       for (int j0 = 0; j0 < num_blocks; j0 += 4, qodd ^= 1u) {
-#define RLVAE_BLK(J) if (j0 + J < num_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) issue_g3(std::integral_constant<int, J>{}, j0 + J, qodd);
         RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3)
 #undef RLVAE_BLK
       }
@@ -977,15 +987,15 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   } else {
     // =========================================================== exp groups (one thread per point)
     const float two_alpha = 2.f * alpha;
-    float tot[32];                       // this group's share of OUT: chunks of parity grp
+    float tot[17];                       // this group's share of OUT (chunks of parity grp) and of sum_k u
 #pragma unroll
-    for (int e = 0; e < 32; ++e) tot[e] = 0.f;
+    for (int e = 0; e < 17; ++e) tot[e] = 0.f;
     auto fold_chunk = [&](int c, bool signal) {
-      uint32_t a[32];
-      TMEM_LD32(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
+      uint32_t a[16];
+      TMEM_LD16(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) tot[i] += __uint_as_float(a[i]);
+      for (int i = 0; i < 16; ++i) tot[i] += __uint_as_float(a[i]);
       if (signal) {
         tc_fence_before();
         __syncwarp();
@@ -1003,6 +1013,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
       tc_fence_after();
       PROF_ADD(pe_wait);
+      float su_blk = 0.f;                // sum of u over this super-block (two-level fp32 summation)
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t sv[32], tv[32];
@@ -1019,6 +1030,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             const int i = 4 * q + e;
             const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
             const float uv = w * __uint_as_float(tv[i]);
+            su_blk += uv;
             const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
             sv[i] = uh;
             tv[i] = __float_as_uint(uv - __uint_as_float(uh));
@@ -1027,6 +1039,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         TMEM_ST32(st + rnd * 32, sv);
         TMEM_ST32(st + 64 + rnd * 32, tv);
       }
+      tot[16] += su_blk;
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -1248,11 +1261,11 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const int nb = t->Kpad / tc::BK;
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct2_hi,
-                                     t->tm_ct2_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
+                                     t->tm_ct8_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct_hi,
-                                     t->tm_ct_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
+                                     t->tm_ct16_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
   }
   return 0;
 }
