@@ -28,7 +28,7 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
                                       float inv_T2_log2e, float* __restrict__ c, float* __restrict__ cn,
                                       float* __restrict__ cstack, float* __restrict__ cbias,
                                       float* __restrict__ ct_hi, float* __restrict__ ct_lo,
-                                      float* __restrict__ stats) {
+                                      float* __restrict__ cn_inf, float* __restrict__ stats) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   float nrm = 0.f;
@@ -56,6 +56,7 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
       ct_lo[(int64_t)(16 + j) * Kpad + k] = 0.f;
     }
     cbias[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
+    cn_inf[k] = (k < K) ? nrm : 3.0e38f;
   }
 }
 
@@ -194,7 +195,7 @@ static void free_tables(rlvae_tables* t) {
   t->c64h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
-                    &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
+                    &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->cn_inf, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -251,6 +252,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     ALLOC(t->ct_hi, (size_t)Kpad * 32);
     ALLOC(t->ct_lo, (size_t)Kpad * 32);
     ALLOC(t->cbias, Kpad);
+    ALLOC(t->cn_inf, Kpad);
     ALLOC(t->Mt_hi, (size_t)Kpad * dd);
     ALLOC(t->Mt_lo, (size_t)Kpad * dd);
     ALLOC(t->Mn_hi, (size_t)Kpad * dd);
@@ -269,7 +271,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   OK_OR_FAIL(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
   const float inv_T2_log2e = 1.4426950408889634f / t->T2;
   pack_centroids_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(centroids, K, Kpad, d, inv_T2_log2e, t->c,
-                                                           t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, stats);
+                                                           t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, t->cn_inf, stats);
   OK_OR_FAIL(cudaGetLastError());
   pack_matrices_kernel<<<592, 256, 0, s>>>(matrices, K, Kpad, dd, t->M, t->Mt_hi, t->Mt_lo, t->Mn_hi,
                                            t->Mn_lo, stats);
@@ -705,6 +707,15 @@ int rlvae_nearest2(const rlvae_tables_t* t, const float* mu, int64_t n, int64_t*
   RLVAE_REQUIRE(n >= 0, "nearest2: negative batch");
   if (n == 0) return 0;
   RLVAE_REQUIRE(mu && idx && dist, "nearest2: NULL pointer");
+  // d == 16: distance GEMM on the tensor core as a pre-filter, exact decision among 8 candidates
+  // (same indices and distances as the direct kernel); RLVAE_NEAREST=direct keeps the scalar scan
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("RLVAE_NEAREST");
+    use_tc = (e != nullptr && e[0] == 'd') ? 0 : 1;
+  }
+  if (use_tc && t->d == 16 && t->cn_inf != nullptr && t->K >= 2 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0)
+    return launch_nearest2_tc(t, mu, n, idx, dist, static_cast<cudaStream_t>(stream));
   return launch_nearest2(t, mu, n, idx, dist, static_cast<cudaStream_t>(stream));
 }
 

@@ -63,6 +63,7 @@ struct rlvae_tables {
   // tensor path (d == 16)
   float* cstack = nullptr;  // [Kpad, 32] = [tf32_hi(c) | c - hi]
   float* cbias = nullptr;   // [Kpad]  -||c||^2 * log2(e)/T^2  (padding rows: -1e30)
+  float* cn_inf = nullptr;  // [Kpad]  ||c||^2 with 3e38 on the padding rows (tensor nearest2)
   float* Mt_hi = nullptr;   // [256, Kpad]  tf32_hi(M) transposed (centroid index contiguous)
   float* Mt_lo = nullptr;   // [256, Kpad]  M - hi
   float* Mn_hi = nullptr;   // [Kpad, 256]  natural, for the gradient pass
@@ -127,6 +128,7 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s);
 int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, float* ginv, float* packed_scratch,
                               cudaStream_t s);
 constexpr int kSym64Cols = 2176;
+int launch_nearest2_tc(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s);
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);
 // a_full (optional): the expanded [N,16,16] G^{-1}, written by the same kernel

@@ -1103,6 +1103,280 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   }
 }
 
+
+// ==========================================================================================
+// Two nearest centroids on the tensor core (d == 16).
+//   ref src/models/samplers/riemannian_sampler.py:58-67,125-131: dist = norm(mu - c) [N,K], topk(2, smallest)
+// The [N,K] distance matrix is GEMM1 of the kernels above (S = Z.C^T, 3xTF32, z resident in TMEM);
+// the scan groups turn S into keys ||c_k||^2 - 2 S_k (same order as the distances) and keep the FOUR
+// smallest per point.  The expanded form is only a pre-filter: its ~1e-6 |z||c| absolute error could
+// swap near-ties, so the final two are chosen among the 8 candidates (4 per scan group) by the
+// EXACT differences sum_j (mu_j - c_kj)^2, accumulated exactly like nearest2_kernel (same value, same
+// lowest-index tie rule) -- indices are bit-identical to the direct kernel / the reference's topk.
+// One stage index for everything: C tile + ||c||^2 slice (TMA) -> S buffer (TMEM) -> scan -> FREE.
+// ==========================================================================================
+namespace n2 {
+constexpr int THREADS = 320;         // TMA warp, MMA warp, two scan groups of 4 warps
+constexpr int STAGES = 4;
+constexpr uint32_t CN_BYTES = BK * 4;
+constexpr uint32_t OFF_C = 0;
+constexpr uint32_t OFF_CN = OFF_C + STAGES * C_TILE_BYTES;
+constexpr uint32_t OFF_MERGE = OFF_CN + STAGES * CN_BYTES;         // [128 rows][8] (key, idx) of group B
+constexpr uint32_t OFF_BAR = OFF_MERGE + TILE_M * 8 * 4;
+constexpr int NUM_BARS = 4 * STAGES;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+constexpr uint32_t TM_S = 0;         // + stage*64
+constexpr uint32_t TM_ZHI = 256, TM_ZLO = 272;
+}  // namespace n2
+
+
+// order-preserving float -> int map (so that keys can be ranked with integer min / max)
+__device__ __forceinline__ int ordered_int(float x) {
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+// sorted insertion into the four smallest (key, index) pairs; strict '<' keeps the earlier entry on ties
+__device__ __forceinline__ void top4_insert(int key, int id, int& k0, int& k1, int& k2, int& k3, int& i0, int& i1,
+                                            int& i2, int& i3) {
+  if (key < k1) {
+    if (key < k0) { k3 = k2; i3 = i2; k2 = k1; i2 = i1; k1 = k0; i1 = i0; k0 = key; i0 = id; }
+    else { k3 = k2; i3 = i2; k2 = k1; i2 = i1; k1 = key; i1 = id; }
+  } else {
+    if (key < k2) { k3 = k2; i3 = i2; k2 = key; i2 = id; }
+    else { k3 = key; i3 = id; }
+  }
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(n2::THREADS, 1)
+nearest2_tc_kernel(const __grid_constant__ CUtensorMap tm_cstack, const float* __restrict__ mu,
+                   const float* __restrict__ cn_inf /* ||c||^2, +huge on padding rows */,
+                   const float* __restrict__ cnat /* [Kpad,16] */, int64_t n, int num_blocks, int n_centroids,
+                   int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  constexpr int STAGES = n2::STAGES;
+  constexpr uint32_t OFF_C = n2::OFF_C, OFF_CN = n2::OFF_CN, CN_BYTES = n2::CN_BYTES, TM_S = n2::TM_S,
+                     TM_ZHI = n2::TM_ZHI, TM_ZLO = n2::TM_ZLO;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + n2::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_CN_FULL = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto BAR_S_FULL = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto BAR_FREE = [&](int s) { return bar0 + 8u * (3 * STAGES + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + n2::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_CN_FULL(s), 1); mbar_init(BAR_S_FULL(s), 1);
+      mbar_init(BAR_FREE(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + n2::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + n2::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  float zrow[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) zrow[j] = 0.f;
+  if (warp >= 2) {
+    const int64_t r = row0 + prow;
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(mu + r * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(src + q);
+        zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
+      }
+    }
+    if (grp == 0) {
+      uint32_t zh[16], zl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float hh = tf32_rna(zrow[j]);
+        zh[j] = __float_as_uint(hh);
+        zl[j] = __float_as_uint(zrow[j] - hh);
+      }
+      TMEM_ST16(tmem_base + lane_addr + TM_ZHI, zh);
+      TMEM_ST16(tmem_base + lane_addr + TM_ZLO, zl);
+      tmem_wait_st();
+    }
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+#define MMA_TS(d, a, b, id, acc) do { if (PAIR) mma_ts_pair(d, a, b, id, acc); else mma_ts(d, a, b, id, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (warp == 0) {
+    // =========================================================== TMA producer: centroid tile + ||c||^2 slice
+    for (int j = 0; j < num_blocks; ++j) {
+      const int st = j % STAGES;
+      mbar_wait(BAR_FREE(st), ((j / STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_C_FULL(st), C_TILE_BYTES);
+        const uint32_t dst = base + OFF_C + st * C_TILE_BYTES;
+        if (PAIR) {
+          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(st), 0, j * BK + 32 * (int)rank);
+        } else {
+          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(st), 0, j * BK);
+          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(st), 0, j * BK + 32);
+        }
+        mbar_expect_tx(BAR_CN_FULL(st), CN_BYTES);
+        bulk_load_1d(base + OFF_CN + st * CN_BYTES, cn_inf + (int64_t)j * BK, CN_BYTES, BAR_CN_FULL(st));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer: the distance GEMM only
+    if (leader) {
+      const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
+      constexpr uint32_t ID1 = make_idesc(PAIR ? 256 : 128, BK);
+      for (int j = 0; j < num_blocks; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(BAR_C_FULL(st), (j / STAGES) & 1);     // implies the scan groups of both CTAs freed S(st)
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_base + TM_S + st * 64;
+          const uint64_t bc = c_desc0 + ((st * C_TILE_BYTES) >> 4);
+          MMA_TS(d, tmem_base + TM_ZHI, bc, ID1, 0);
+          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 2, ID1, 1);
+          MMA_TS(d, tmem_base + TM_ZHI, bc + 4, ID1, 1);
+          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 6, ID1, 1);
+          MMA_TS(d, tmem_base + TM_ZLO, bc, ID1, 1);
+          MMA_TS(d, tmem_base + TM_ZLO + 8, bc + 2, ID1, 1);
+          COMMIT(BAR_S_FULL(st));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================================================== scan groups: four smallest keys per point.
+    // Per super-block and thread: 64 keys -> ordered ints with the in-block index in the low 6 bits ->
+    // the three smallest of the even and of the odd elements by a branch-free min/max insertion network
+    // (two independent chains for ILP; ~9 instructions per element).  Only those 6 block candidates go
+    // through the branchy top-4 insertion (a per-element insertion is if-converted by ptxas into ~35
+    // instructions for EVERY element, or -- as a real branch -- pays ~150 cycles of divergence 12% of
+    // the time: both measured at 10-15 ms per 2^20 x 10k, no better than the scalar kernel).
+    constexpr int IMAX = 0x7fffffff;
+    int k0 = IMAX, k1 = IMAX, k2 = IMAX, k3 = IMAX;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    for (int j = grp; j < num_blocks; j += 2) {
+      const int st = j % STAGES;
+      mbar_wait(BAR_CN_FULL(st), (j / STAGES) & 1);
+      mbar_wait(BAR_S_FULL(st), (j / STAGES) & 1);
+      tc_fence_after();
+      int a0 = IMAX, a1 = IMAX, a2 = IMAX, b0 = IMAX, b1 = IMAX, b2 = IMAX;
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        uint32_t sv[32];
+        TMEM_LD32(tmem_base + lane_addr + TM_S + st * 64 + rnd * 32, sv);
+        const float4* cn4 = reinterpret_cast<const float4*>(gbase + OFF_CN + st * CN_BYTES) + rnd * 8;
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 cv = cn4[q];
+          const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = rnd * 32 + 4 * q + e;
+            const int v = (ordered_int(fmaf(-2.f, __uint_as_float(sv[4 * q + e]), c4[e])) & ~63) | i;
+            if (e & 1) {
+              const int x = max(b0, v); b0 = min(b0, v);
+              const int y = max(b1, x); b1 = min(b1, x);
+              b2 = min(b2, y);
+            } else {
+              const int x = max(a0, v); a0 = min(a0, v);
+              const int y = max(a1, x); a1 = min(a1, x);
+              a2 = min(a2, y);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_FREE(st));
+      const int cand[6] = {a0, a1, a2, b0, b1, b2};
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+        if (cand[q] < k3) top4_insert(cand[q], j * BK + (cand[q] & 63), k0, k1, k2, k3, i0, i1, i2, i3);
+    }
+    // ---- merge the two groups' candidates, then decide by exact differences
+    int* merge = reinterpret_cast<int*>(gbase + n2::OFF_MERGE);
+    if (grp == 1) {
+      merge[prow * 8 + 0] = i0; merge[prow * 8 + 1] = i1; merge[prow * 8 + 2] = i2; merge[prow * 8 + 3] = i3;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const int64_t r = row0 + prow;
+      if (r < n) {
+        int cand[8] = {i0, i1, i2, i3, merge[prow * 8 + 0], merge[prow * 8 + 1], merge[prow * 8 + 2],
+                       merge[prow * 8 + 3]};
+        float b0 = 3.4e38f, b1 = 3.4e38f;
+        int j0 = 0x7fffffff, j1 = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int id = cand[q];
+          if (id < 0 || id >= n_centroids) continue;      // empty slot or a padding row
+          const float4* crow = reinterpret_cast<const float4*>(cnat + (int64_t)id * 16);
+          float sq = 0.f;
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const float4 cv = __ldg(crow + v4);
+            float df = zrow[4 * v4] - cv.x; sq = fmaf(df, df, sq);
+            df = zrow[4 * v4 + 1] - cv.y; sq = fmaf(df, df, sq);
+            df = zrow[4 * v4 + 2] - cv.z; sq = fmaf(df, df, sq);
+            df = zrow[4 * v4 + 3] - cv.w; sq = fmaf(df, df, sq);
+          }
+          // (sq, index) lexicographic: the index-ordered strict-less scan of nearest2_kernel
+          if (sq < b0 || (sq == b0 && id < j0)) { b1 = b0; j1 = j0; b0 = sq; j0 = id; }
+          else if (sq < b1 || (sq == b1 && id < j1)) { b1 = sq; j1 = id; }
+        }
+        idx_out[r * 2 + 0] = j0; idx_out[r * 2 + 1] = j1;
+        dist_out[r * 2 + 0] = sqrtf(b0); dist_out[r * 2 + 1] = sqrtf(b1);
+      }
+    }
+  }
+#undef MMA_TS
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ host
@@ -1281,6 +1555,44 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
   return h16_use_pairs() ? launch_g16<true>(t, z, u, n, scale, out, s, u_packed)
                          : launch_g16<false>(t, z, u, n, scale, out, s, u_packed);
+}
+
+template <bool PAIR>
+static int launch_n2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s) {
+  auto kern = tc::nearest2_tc_kernel<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::n2::SMEM_BYTES));
+    attr_set = true;
+  }
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, 1, 1);
+  cfg.blockDim = dim3(tc::n2::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::n2::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float* cn = t->cn_inf;
+  const float* cnat = t->c;
+  const int nb = t->Kpad / tc::BK;
+  const int K = t->K;
+  RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, mu, cn, cnat, n, nb, K, idx, dist));
+  return 0;
+}
+
+// two nearest centroids, d == 16: tensor-core pre-filter + exact decision (bit-identical to the direct kernel)
+int launch_nearest2_tc(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(t->d == 16 && t->cstack != nullptr && t->cn_inf != nullptr, "tensor nearest2 needs latent_dim == 16");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(mu) & 15) == 0, "tensor nearest2 needs 16-byte aligned mu");
+  return h16_use_pairs() ? launch_n2<true>(t, mu, n, idx, dist, s) : launch_n2<false>(t, mu, n, idx, dist, s);
 }
 
 }  // namespace rlvae

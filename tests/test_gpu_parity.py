@@ -218,6 +218,33 @@ def test_hmc_full_size_properties_config3():
     torch.testing.assert_close(zp, z1[lo:hi], rtol=1e-5, atol=1e-6)
 
 
+def test_nearest2_tensor_prefilter_is_exact_at_k10k():
+    """A14/A15 at config size: the tensor-core pre-filter + exact decision against the reference's
+    expression (norm of differences, topk smallest) on 16k points x 10k centroids, plus ragged tails."""
+    from rlvae_b200 import _capi
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    mt = make_mt((sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization))
+    tab = mt._tables(dev())
+    mu = make_points(16384 + 77, 16, seed=9).to(dev())
+    mu[:64] = sm.centroids[:64].to(dev())                       # points sitting exactly on centroids
+    idx, dist = _capi.nearest2(tab, mu)
+    c = sm.centroids.to(dev())
+    for lo in range(0, mu.shape[0], 2048):
+        m = mu[lo:lo + 2048]
+        d = torch.norm(m[:, None] - c[None], dim=-1)            # riemannian_sampler.py:61
+        rd, ri = torch.topk(d, k=2, dim=-1, largest=False)      # :64
+        same = idx[lo:lo + 2048] == ri
+        # a differing index is only acceptable for an exact-to-rounding tie
+        gd = torch.gather(d, 1, idx[lo:lo + 2048])
+        assert torch.all(same | ((gd - rd).abs() <= 1e-6 * rd.abs() + 1e-12)), lo
+        torch.testing.assert_close(dist[lo:lo + 2048], rd, rtol=1e-5, atol=1e-7)
+    assert (dist[:64, 0] == 0).all() and torch.equal(idx[:64, 0].cpu(), torch.arange(64))
+    for n in (1, 127, 129):
+        i2, d2 = _capi.nearest2(tab, mu[:n].contiguous())
+        assert torch.equal(i2, idx[:n]) and torch.equal(d2, dist[:n])
+
+
 def test_linearity_in_tables():
     """G^{-1} - lambda I is linear in M: eval(M1 + M2) == eval(M1) + eval(M2) - lambda I."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
