@@ -32,3 +32,8 @@ if len(sys.argv) > 3 and sys.argv[3] == 'hmc':     # plus one short HMC iteratio
     zf = s.sample_with_streams(z0.to(dev), gam.to(dev), acc.to(dev))
     torch.cuda.synchronize()
     print('hmc ok', float(zf[:4].sum()))
+    from rlvae_b200 import _capi
+    idx, dist = _capi.nearest2(mt._tables(dev), z)             # A14/A15: tensor-core nearest2
+    sp = mt.compute_metric_spectrum(z)                          # A19: forward + per-thread Jacobi
+    torch.cuda.synchronize()
+    print('nearest2 / spectrum ok', int(idx[0, 0]), float(sp['condition_number'][:4].mean()))
