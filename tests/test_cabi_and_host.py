@@ -105,3 +105,20 @@ def test_synthetic_metric_is_calibrated_and_deterministic():
     assert abs(ld.mean().item()) < 1.0          # det G^{-1} has geometric mean ~1
     z0, g, acc = make_hmc_streams(10, 16, 3, seed=2)
     assert z0.shape == (10, 16) and g.shape == (3, 10, 16) and acc.shape == (3, 10)
+
+
+def test_new_host_modules_refuse_cpu_tensors_and_keep_reference_surfaces():
+    """metric_builder / RHVAE-style sampler: no CPU fallback, reference-compatible surfaces."""
+    import inspect
+    from rlvae_b200 import RHVAEStyleHMCSampler, metric_builder
+    x = torch.randn(20, 4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        metric_builder.build_local_metrics(x, x[:3], 0.1, 0.01)
+    with pytest.raises(ValueError):
+        metric_builder.build_metric_data(x.cuda() if torch.cuda.is_available() else x)
+    lf = torch.tril(torch.randn(3, 4, 4))
+    assert torch.allclose(metric_builder.matrices_from_cholesky_factors(lf), lf @ lf.transpose(1, 2))
+    sig = inspect.signature(RHVAEStyleHMCSampler.__init__)
+    assert list(sig.parameters)[1:] == ['model', 'mcmc_steps_nbr', 'n_lf', 'eps_lf', 'beta_zero']
+    assert sig.parameters['mcmc_steps_nbr'].default == 100 and sig.parameters['n_lf'].default == 15
+    assert RHVAEStyleHMCSampler.tempering(5, 10, 0.5) == pytest.approx(1.0 / ((1 - 2.0) * 0.25 + 2.0))
