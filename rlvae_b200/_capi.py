@@ -115,6 +115,7 @@ class Tables:
         _check(lib().rlvae_tables_info(self._h, info), 'rlvae_tables_info')
         self.Kpad, self.symmetric = int(info[2]), bool(info[3])
         self.tensor_capable, self.tensor_auto = bool(info[4]), bool(info[5])
+        self.expanded_ok = bool(info[6])     # False -> the d = 16 symmetric kernels run in exact-distance mode
 
     @property
     def handle(self):

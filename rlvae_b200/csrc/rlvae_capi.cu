@@ -28,7 +28,8 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
                                       float inv_T2_log2e, float* __restrict__ c, float* __restrict__ cn,
                                       float* __restrict__ cstack, float* __restrict__ cbias,
                                       float* __restrict__ ct_hi, float* __restrict__ ct_lo,
-                                      float* __restrict__ cn_inf, float* __restrict__ stats) {
+                                      float* __restrict__ cn_inf, float* __restrict__ cmask,
+                                      float* __restrict__ stats) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   float nrm = 0.f;
@@ -57,6 +58,7 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
     }
     cbias[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
     cn_inf[k] = (k < K) ? nrm : 3.0e38f;
+    cmask[k] = (k < K) ? 0.f : -1.0e30f;
   }
 }
 
@@ -195,7 +197,7 @@ static void free_tables(rlvae_tables* t) {
   t->c64h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
-                    &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->cn_inf, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
+                    &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->cn_inf, &t->cmask, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
   for (float** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -253,6 +255,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     ALLOC(t->ct_lo, (size_t)Kpad * 32);
     ALLOC(t->cbias, Kpad);
     ALLOC(t->cn_inf, Kpad);
+    ALLOC(t->cmask, Kpad);
     ALLOC(t->Mt_hi, (size_t)Kpad * dd);
     ALLOC(t->Mt_lo, (size_t)Kpad * dd);
     ALLOC(t->Mn_hi, (size_t)Kpad * dd);
@@ -271,7 +274,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   OK_OR_FAIL(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
   const float inv_T2_log2e = 1.4426950408889634f / t->T2;
   pack_centroids_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(centroids, K, Kpad, d, inv_T2_log2e, t->c,
-                                                           t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, t->cn_inf, stats);
+                                                           t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, t->cn_inf, t->cmask, stats);
   OK_OR_FAIL(cudaGetLastError());
   pack_matrices_kernel<<<592, 256, 0, s>>>(matrices, K, Kpad, dd, t->M, t->Mt_hi, t->Mt_lo, t->Mn_hi,
                                            t->Mn_lo, stats);
@@ -297,7 +300,8 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     if (rc != 0) return fail(rc);
     t->tensor_capable = 1;
     const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
-    t->tensor_auto = (rel < 2.0e-6f) ? 1 : 0;
+    t->expanded_ok = (rel < 2.0e-6f) ? 1 : 0;
+    t->tensor_auto = t->expanded_ok;
     if (t->symmetric) {   // 136 instead of 256 accumulated columns
       cudaError_t e1 = cudaMalloc(&t->Mts_hi, sizeof(float) * (size_t)kSymCols * Kpad);
       cudaError_t e2 = cudaMalloc(&t->Mts_lo, sizeof(float) * (size_t)kSymCols * Kpad);
@@ -337,6 +341,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           OK_OR_FAIL(cudaStreamSynchronize(s));
           t->h16_out_scale = ldexpf(1.f, -(14 + e));
           t->h16_m_unscale = ldexpf(1.f, -e);
+          t->tensor_auto = 1;    // the split-fp16 kernels have an exact-distance mode: no restriction on T
           rc = tc_build_h16_descriptors(t);
           if (rc != 0) return fail(rc);
         }
@@ -349,7 +354,8 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     if (t->c64h != nullptr) {
       t->tensor_capable = 1;
       const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
-      t->tensor_auto = (rel < 2.0e-6f) ? 1 : 0;
+      t->expanded_ok = (rel < 2.0e-6f) ? 1 : 0;
+      t->tensor_auto = t->expanded_ok;
     }
   }
   *out = t;
@@ -366,7 +372,7 @@ int rlvae_tables_destroy(rlvae_tables_t* t) {
 int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]) {
   RLVAE_REQUIRE(t != nullptr && info != nullptr, "tables_info: NULL argument");
   info[0] = t->K; info[1] = t->d; info[2] = t->Kpad; info[3] = t->symmetric;
-  info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = 0; info[7] = 0;
+  info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = t->expanded_ok; info[7] = 0;
   return 0;
 }
 

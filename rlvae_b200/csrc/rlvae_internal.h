@@ -52,7 +52,8 @@ struct rlvae_tables {
   float T = 0.f, T2 = 0.f, lambda = 0.f;
   int symmetric = 0;       // every M_k bitwise symmetric
   int tensor_capable = 0;  // d == 16 and TMA descriptors built
-  int tensor_auto = 0;     // accuracy criterion for the expanded-distance form holds
+  int tensor_auto = 0;     // AUTO picks a tensor path (expanded form accurate enough, or exact-distance mode available)
+  int expanded_ok = 0;     // accuracy criterion for the expanded-distance form ||z||^2+||c||^2-2z.c holds
   float r2max = 0.f;       // max_k ||c_k||^2
 
   // natural layouts, zero padded to Kpad rows
@@ -64,6 +65,7 @@ struct rlvae_tables {
   float* cstack = nullptr;  // [Kpad, 32] = [tf32_hi(c) | c - hi]
   float* cbias = nullptr;   // [Kpad]  -||c||^2 * log2(e)/T^2  (padding rows: -1e30)
   float* cn_inf = nullptr;  // [Kpad]  ||c||^2 with 3e38 on the padding rows (tensor nearest2)
+  float* cmask = nullptr;   // [Kpad]  0 on real rows, -1e30 on padding rows (exact-distance tensor mode)
   float* Mt_hi = nullptr;   // [256, Kpad]  tf32_hi(M) transposed (centroid index contiguous)
   float* Mt_lo = nullptr;   // [256, Kpad]  M - hi
   float* Mn_hi = nullptr;   // [Kpad, 256]  natural, for the gradient pass

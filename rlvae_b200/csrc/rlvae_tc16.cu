@@ -153,12 +153,18 @@ struct FusedOut {
   float lad_scale;
 };
 
-template <bool PAIR>
+// EXACT: the weights come from exact differences sum_j (z_j - c_kj)^2 formed by the exp threads on the
+// FMA pipe (packed fp32x2, natural centroid rows broadcast from shared memory) instead of the
+// expanded form on the tensor core.  No GEMM1, no accuracy gate on T: this is the mode for small
+// temperatures (the reference's T = 0.7 configuration), ~28 instead of ~7 instructions per
+// (point, centroid) in the exp stage, which then bounds the kernel instead of the tensor pipe.
+template <bool PAIR, bool EXACT>
 __global__ void __launch_bounds__(h16::THREADS, 1)
 inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const __grid_constant__ CUtensorMap tm_mh_hi,
                           const __grid_constant__ CUtensorMap tm_mh_lo,
-                          const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
+                          const float* __restrict__ z, const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
+                          const float* __restrict__ cnat /* EXACT: natural centroid rows [Kpad,16] */, int64_t n,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
                           float out_scale /* 2^-(14+e) */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
@@ -232,6 +238,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   float zb = 0.f;
+  float2 nz[8];                       // EXACT: the negated point
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nz[j] = make_float2(0.f, 0.f);
   if (wg == 1 || wg == 2) {
     const int64_t r = row0 + prow;
     float zv[16];
@@ -248,8 +257,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float nrm = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) nrm = fmaf(zv[j], zv[j], nrm);
-    zb = -nrm * alpha + P_SHIFT;     // P' = 2^14 P, folded into the exponent
-    if (wg == 1) {                   // exp group A writes the A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
+    zb = EXACT ? P_SHIFT : (-nrm * alpha + P_SHIFT);     // P' = 2^14 P, folded into the exponent
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nz[j] = make_float2(-zv[2 * j], -zv[2 * j + 1]);
+    if (wg == 1 && !EXACT) {         // exp group A writes the A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -279,15 +290,20 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const int cs = j % C_STAGES;
         mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
           const uint32_t dst = base + h16::OFF_C + cs * C_TILE_BYTES;
-          if (PAIR) {
-            tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+          if (EXACT) {      // natural rows of the 64 centroids (4 KB) + mask, both for this CTA's exp groups
+            mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES + BK * 64);
+            bulk_load_1d(dst, cnat + (int64_t)j * BK * 16, BK * 64, BAR_BIAS_FULL(cs));
           } else {
-            tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
-            tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+            if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+            if (PAIR) {
+              tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+            } else {
+              tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+              tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+            }
+            mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
           }
-          mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
           bulk_load_1d(base + h16::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
         }
         __syncwarp();
@@ -322,17 +338,20 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       auto gemm1 = [&](auto CSc, auto SBc) {
         constexpr int cs = decltype(CSc)::value, sb = decltype(SBc)::value;
         if (elect_one()) {
-          // S = z_hi.c_hi + z_hi.c_lo + z_lo.c_hi (3xTF32), A operand from TMEM: N/2 = 32 cycles per MMA
-          // (the shared-memory A tile costs 48); a centroid row is [c_hi (16) | c_lo (16)] = 4 K-steps
-          constexpr uint32_t id1 = make_idesc(PAIR ? 256 : 128, BK);
-          const uint32_t d = tmem_base + TM_SP + sb * 64;
-          const uint64_t bc = c_desc0 + ((cs * C_TILE_BYTES) >> 4);
-          MMA_TS(d, tmem_base + TM_ZHI, bc, id1, 0);
-          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 2, id1, 1);
-          MMA_TS(d, tmem_base + TM_ZHI, bc + 4, id1, 1);
-          MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 6, id1, 1);
-          MMA_TS(d, tmem_base + TM_ZLO, bc, id1, 1);
-          MMA_TS(d, tmem_base + TM_ZLO + 8, bc + 2, id1, 1);
+          if (!EXACT) {
+            // S = z_hi.c_hi + z_hi.c_lo + z_lo.c_hi (3xTF32), A operand from TMEM: N/2 = 32 cycles per MMA
+            // (the shared-memory A tile costs 48); a centroid row is [c_hi (16) | c_lo (16)] = 4 K-steps
+            constexpr uint32_t id1 = make_idesc(PAIR ? 256 : 128, BK);
+            const uint32_t d = tmem_base + TM_SP + sb * 64;
+            const uint64_t bc = c_desc0 + ((cs * C_TILE_BYTES) >> 4);
+            MMA_TS(d, tmem_base + TM_ZHI, bc, id1, 0);
+            MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 2, id1, 1);
+            MMA_TS(d, tmem_base + TM_ZHI, bc + 4, id1, 1);
+            MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 6, id1, 1);
+            MMA_TS(d, tmem_base + TM_ZLO, bc, id1, 1);
+            MMA_TS(d, tmem_base + TM_ZLO + 8, bc + 2, id1, 1);
+          }
+          // EXACT: no distance GEMM; S_FULL then only says "GEMM2 has finished reading this P buffer"
           COMMIT(BAR_S_FULL(sb));
         }
         __syncwarp();
@@ -360,7 +379,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         __syncwarp();
         // inputs of the NEXT steps, waited for behind queued MMAs (normally long complete)
         if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((J + 1) % M_STAGES), ((J + 1) / M_STAGES) & 1);
-        if (j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
+        if (!EXACT && j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -379,9 +398,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((J + 1) % SP_BUFS), ((J + 1) / SP_BUFS) & 1);
       };
       // prologue: GEMM1 of the first AHEAD (= 3) blocks
-      if (0 < num_blocks) { mbar_wait(BAR_C_FULL(0), 0); tc_fence_after(); gemm1(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{}); }
-      if (1 < num_blocks) { mbar_wait(BAR_C_FULL(1), 0); tc_fence_after(); gemm1(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}); }
-      if (2 < num_blocks) { mbar_wait(BAR_C_FULL(2), 0); tc_fence_after(); gemm1(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
+      if (0 < num_blocks) { if (!EXACT) mbar_wait(BAR_C_FULL(0), 0); tc_fence_after(); gemm1(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{}); }
+      if (1 < num_blocks) { if (!EXACT) mbar_wait(BAR_C_FULL(1), 0); tc_fence_after(); gemm1(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}); }
+      if (2 < num_blocks) { if (!EXACT) mbar_wait(BAR_C_FULL(2), 0); tc_fence_after(); gemm1(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
       mbar_wait(BAR_M_FULL(0), 0);
       mbar_wait(BAR_P_FULL(0), 0);
       static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 6 % M_STAGES == 0 && AHEAD == 3,
@@ -412,19 +431,34 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       PROF_ADD(pe_wait);
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
-        uint32_t s[32], ph[16], pl[16];
-        TMEM_LD32(sp + rnd * 32, s);
+        uint32_t ph[16], pl[16];
         const float4* bias4 = reinterpret_cast<const float4*>(gbase + h16::OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
-        tmem_wait_ld();
+        if (EXACT) {
+          const float4* crow = reinterpret_cast<const float4*>(gbase + h16::OFF_C + cs * C_TILE_BYTES) + rnd * 32 * 4;
+#pragma unroll 2
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = bias4[q];
+            const float w0 = ex2_approx(fmaf(dist2_row16(crow + (4 * q) * 4, nz), -alpha, bv.x + zb));
+            const float w1 = ex2_approx(fmaf(dist2_row16(crow + (4 * q + 1) * 4, nz), -alpha, bv.y + zb));
+            const float w2 = ex2_approx(fmaf(dist2_row16(crow + (4 * q + 2) * 4, nz), -alpha, bv.z + zb));
+            const float w3 = ex2_approx(fmaf(dist2_row16(crow + (4 * q + 3) * 4, nz), -alpha, bv.w + zb));
+            split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+            split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+          }
+        } else {
+          uint32_t s[32];
+          TMEM_LD32(sp + rnd * 32, s);
+          tmem_wait_ld();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bv = bias4[q];
-          const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), two_alpha, bv.x + zb));
-          const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), two_alpha, bv.y + zb));
-          const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), two_alpha, bv.z + zb));
-          const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), two_alpha, bv.w + zb));
-          split_pair(w0, w1, ph[2 * q], pl[2 * q]);
-          split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = bias4[q];
+            const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), two_alpha, bv.x + zb));
+            const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), two_alpha, bv.y + zb));
+            const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), two_alpha, bv.z + zb));
+            const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), two_alpha, bv.w + zb));
+            split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+            split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+          }
         }
         TMEM_ST16(sp + rnd * 32, ph);
         TMEM_ST16(sp + rnd * 32 + 16, pl);
@@ -635,7 +669,8 @@ __device__ __forceinline__ void split_pair_scaled(float even, float odd, float s
   split_pair(even * sc, odd * sc, hi2, lo2);
 }
 
-template <bool PAIR>
+// EXACT: weights from exact differences on the FMA pipe (see inverse_metric_h16_kernel); no GEMM1.
+template <bool PAIR, bool EXACT>
 __global__ void __launch_bounds__(g16::THREADS, 1)
 metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const __grid_constant__ CUtensorMap tm_mn_hi,
@@ -643,8 +678,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const __grid_constant__ CUtensorMap tm_ct_hi,
                        const __grid_constant__ CUtensorMap tm_ct_lo,
                        const float* __restrict__ z, const float* __restrict__ u,
-                       const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
-                       float scale /* includes 2^-eM */, float* __restrict__ out, int u_packed) {
+                       const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
+                       const float* __restrict__ cnat /* EXACT: natural centroid rows */, int64_t n, int num_blocks,
+                       float alpha, float scale /* includes 2^-eM */, float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
   constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
                      M_HALF_BYTES = g16::M_HALF_BYTES, OFF_C = g16::OFF_C,
@@ -744,9 +780,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
         nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
       }
-      zb = -nrm * alpha;
+      zb = EXACT ? 0.f : -nrm * alpha;
     }
-    if (grp == 0) {             // A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
+    if (grp == 0 && !EXACT) {   // A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
       uint32_t zh[16], zl[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -837,15 +873,20 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       const int cs = j % C_STAGES;
       mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
         const uint32_t dst = base + OFF_C + cs * C_TILE_BYTES;
-        if (PAIR) {
-          tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+        if (EXACT) {        // natural rows of the 64 centroids (4 KB) + mask for this CTA's exp groups
+          mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES + BK * 64);
+          bulk_load_1d(dst, cnat + (int64_t)j * BK * 16, BK * 64, BAR_B_FULL(cs));
         } else {
-          tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
-          tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+          if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE_BYTES);
+          if (PAIR) {
+            tma_load_2d_pair(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32 * (int)rank);
+          } else {
+            tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
+            tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
+          }
+          mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
         }
-        mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
       }
       __syncwarp();
@@ -901,7 +942,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       auto issue_st = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
         constexpr int J = decltype(Jc)::value;
         constexpr int cs = J % C_STAGES, sb = J & 1, ms = J % M_STAGES;
-        mbar_wait(BAR_C_FULL(cs), qodd);
+        if (!EXACT) mbar_wait(BAR_C_FULL(cs), qodd);
         mbar_wait(BAR_M_FULL(ms), (J / M_STAGES) & 1);
         if (j >= 2) mbar_wait(BAR_G3_DONE(sb), ((J >> 1) + 1) & 1);     // GEMM3(j-2) has consumed this buffer
         tc_fence_after();
@@ -911,12 +952,14 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const uint64_t bh = m_desc0 + ((ms * M_TILE_BYTES) >> 4);
         const uint64_t bl = bh + (M_HALF_BYTES >> 4);
         if (elect_one()) {
-          MMA_TS(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
-          MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 2, ID1, 1);
-          MMA_TS(s_t, tmem_base + TM_ZHI, bc + 4, ID1, 1);
-          MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 6, ID1, 1);
-          MMA_TS(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
-          MMA_TS(s_t, tmem_base + TM_ZLO + 8, bc + 2, ID1, 1);
+          if (!EXACT) {
+            MMA_TS(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
+            MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 2, ID1, 1);
+            MMA_TS(s_t, tmem_base + TM_ZHI, bc + 4, ID1, 1);
+            MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 6, ID1, 1);
+            MMA_TS(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
+            MMA_TS(s_t, tmem_base + TM_ZLO + 8, bc + 2, ID1, 1);
+          }
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
             MMA_T16(t_t, tmem_base + TM_UHI + 8 * kk, bh + (kk >> 2) * ATOM_DESC + 2 * (kk & 3), kk > 0);
@@ -987,6 +1030,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   } else {
     // =========================================================== exp groups (one thread per point)
     const float two_alpha = 2.f * alpha;
+    float2 nz[8];                        // EXACT: the negated point
+#pragma unroll
+    for (int q = 0; q < 8; ++q) nz[q] = make_float2(-zrow[2 * q], -zrow[2 * q + 1]);
     float tot[17];                       // this group's share of OUT (chunks of parity grp) and of sum_k u
 #pragma unroll
     for (int e = 0; e < 17; ++e) tot[e] = 0.f;
@@ -1017,9 +1063,11 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {
         uint32_t sv[32], tv[32];
-        TMEM_LD32(st + rnd * 32, sv);
+        if (!EXACT) TMEM_LD32(st + rnd * 32, sv);
         TMEM_LD32(st + 64 + rnd * 32, tv);
         const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
+        const float4* crow = reinterpret_cast<const float4*>(gbase + OFF_C + cs * C_TILE_BYTES) + rnd * 32 * 4;
+        (void)crow;
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1028,7 +1076,8 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = 4 * q + e;
-            const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
+            const float w = EXACT ? ex2_approx(fmaf(dist2_row16(crow + i * 4, nz), -alpha, b4[e]))
+                                  : ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
             const float uv = w * __uint_as_float(tv[i]);
             su_blk += uv;
             const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
@@ -1446,9 +1495,9 @@ static bool h16_use_pairs() {
   return v == 1;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool EXACT>
 static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s) {
-  auto kern = tc::inverse_metric_h16_kernel<PAIR>;
+  auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT>;
   static bool attr_set = false;
   if (!attr_set) {
     RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1470,18 +1519,30 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float alpha = 1.4426950408889634f / t->T2;
-  const float* cbias = t->cbias;
+  const float* cbias = EXACT ? t->cmask : t->cbias;
+  const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
   const float lambda = t->lambda;
   const float out_scale = t->h16_out_scale;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb,
-                                     alpha, lambda, out_scale, fo));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
+                                       alpha, lambda, out_scale, fo));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb,
-                                     alpha, lambda, out_scale, fo));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
+                                       alpha, lambda, out_scale, fo));
   }
   return 0;
+}
+
+// exact-distance mode: whenever the expanded form would be too inaccurate for these tables (small T),
+// or on request (RLVAE_TC_EXACT=1)
+static bool h16_exact(const rlvae_tables* t) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RLVAE_TC_EXACT");
+    forced = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return forced == 1 || !t->expanded_ok;
 }
 
 // Symmetric tables, d == 16: any of { packed G^{-1}, packed G, lad_scale * log|det G^{-1}|, sign,
@@ -1501,15 +1562,18 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   if (fused) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
   RLVAE_REQUIRE(a_full == nullptr || (reinterpret_cast<uintptr_t>(a_full) & 15) == 0, "G^-1 output must be 16-byte aligned");
   tc::FusedOut fo{a_full, a_packed, g_packed, logabsdet, sign, diag_g, fail_ws, lad_scale};
-  if (int rc = h16_use_pairs() ? launch_h16<true>(t, z, n, fo, s) : launch_h16<false>(t, z, n, fo, s)) return rc;
+  int rc;
+  if (h16_exact(t)) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
+  else rc = h16_use_pairs() ? launch_h16<true, false>(t, z, n, fo, s) : launch_h16<false, false>(t, z, n, fo, s);
+  if (rc) return rc;
   if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
   return 0;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool EXACT>
 static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
                       cudaStream_t s, int u_packed) {
-  auto kern = tc::metric_grad_h16_kernel<PAIR>;
+  auto kern = tc::metric_grad_h16_kernel<PAIR, EXACT>;
   static bool attr_set = false;
   if (!attr_set) {
     RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1531,15 +1595,16 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float alpha = 1.4426950408889634f / t->T2;
-  const float* cbias = t->cbias;
+  const float* cbias = EXACT ? t->cmask : t->cbias;
+  const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
-                                     t->tm_ct8_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, out, u_packed));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
-                                     t->tm_ct16_lo, z, u, cbias, n, nb, alpha, sc, out, u_packed));
+                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, out, u_packed));
   }
   return 0;
 }
@@ -1553,8 +1618,11 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
                 "split-fp16 gradient path needs latent_dim == 16 and symmetric tables");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
-  return h16_use_pairs() ? launch_g16<true>(t, z, u, n, scale, out, s, u_packed)
-                         : launch_g16<false>(t, z, u, n, scale, out, s, u_packed);
+  if (h16_exact(t))
+    return h16_use_pairs() ? launch_g16<true, true>(t, z, u, n, scale, out, s, u_packed)
+                           : launch_g16<false, true>(t, z, u, n, scale, out, s, u_packed);
+  return h16_use_pairs() ? launch_g16<true, false>(t, z, u, n, scale, out, s, u_packed)
+                         : launch_g16<false, false>(t, z, u, n, scale, out, s, u_packed);
 }
 
 template <bool PAIR>

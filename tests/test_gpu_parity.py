@@ -245,6 +245,28 @@ def test_nearest2_tensor_prefilter_is_exact_at_k10k():
         assert torch.equal(i2, idx[:n]) and torch.equal(d2, dist[:n])
 
 
+def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
+    """The reference's own configuration T = 0.7 (conf/model/hybrid_rlvae.yaml:41) at config size: the
+    expanded-distance form is too inaccurate there, so the d = 16 symmetric kernels switch to exact
+    differences on the FMA pipe (weighted sum and gradient contraction stay on the tensor core)."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    t = (sm.centroids, sm.metric_matrices, 0.7, sm.regularization)
+    mt = make_mt(t, 'auto')
+    tab = mt._tables(dev())
+    assert tab.tensor_auto and not tab.expanded_ok
+    z = torch.cat([make_points(3000, 16, seed=1), sm.centroids[:1000] + 0.05 * make_points(1000, 16, seed=2)]).to(dev())
+    a = make_mt(t, 'direct').evaluate(z, want_g=True, want_grad=True)
+    b = mt.evaluate(z, want_g=True, want_grad=True)
+    assert rel_fro(b['ginv'].cpu(), a['ginv'].cpu()) < TOL_MAT
+    assert rel_fro(b['g'].cpu(), a['g'].cpu()) < TOL_MAT
+    close_ld(b['logdet_g'], a['logdet_g'])
+    live = a['grad_logdet_g'].norm(dim=1) > 1e-6 * a['grad_logdet_g'].norm(dim=1).max()
+    assert rel_fro(b['grad_logdet_g'][live].cpu(), a['grad_logdet_g'][live].cpu()) < TOL_LD
+    ref = O.chunked(O.inverse_metric, z[3000:3064].cpu(), *t, chunk=32)
+    assert rel_fro(b['ginv'][3000:3064].cpu(), ref) < TOL_MAT
+
+
 def test_linearity_in_tables():
     """G^{-1} - lambda I is linear in M: eval(M1 + M2) == eval(M1) + eval(M2) - lambda I."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
