@@ -411,6 +411,23 @@ def run_ours(args):
                    'sample': f'{npts} points of the same workload in 128-point chunks, {dt:.1f} s; CPU oracle '
                              'port of the reference eager PyTorch path (G^-1, log det via inv+slogdet, '
                              'grad by autograd)'}
+            # the same for the sampler: RiemannianHMCSampler.sample on the host cores
+            try:
+                from oracle import metric_oracle as O
+                nch = 16
+                hz0, hgam, hacc = make_hmc_streams(nch, D, 1, seed=2)
+                tt = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+                t0 = time.perf_counter()
+                O.hmc_sample(tt, hz0, hgam, hacc, HMC_STEPS, 0.03)
+                hdt = time.perf_counter() - t0
+                if isinstance(hmc, dict):
+                    hmc['cpu_baseline'] = {'value': nch * HMC_STEPS / hdt, 'unit': 'chain-leapfrog-steps/s',
+                                           'cores': th, 'kind': 'port',
+                                           'sample': f'{nch} chains x {HMC_STEPS} leapfrog x 1 MCMC iteration, K={K}, '
+                                                     f'{hdt:.1f} s (the reference evaluates the metric 2*n_lf+2 times)'}
+            except Exception as e:
+                if isinstance(hmc, dict):
+                    hmc['cpu_baseline'] = {'error': str(e)[:200]}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': S, 'warmup': W,
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32 (split-fp16 / 3xTF32 tensor products with fp32 accumulate: fp32-level accuracy)' if path_name == 'tensor' else 'f32',
