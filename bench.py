@@ -310,12 +310,12 @@ def run_ours(args):
         if sym_tensor:
             # Tensor work in fp16-equivalent flops: a TF32 MAC costs two fp16 MACs of pipe time (the
             # measured TF32 GEMM rate is half the bf16 one).  ALGORITHMIC = symmetric tables, no padding:
-            #   forward : 3 passes x 2K x (136 weighted-sum columns [fp16] + 2 x 16 distance dims [TF32])
-            #   gradient: 3 passes x 2K x (136 [fp16] + 2 x 16 [TF32] + 2 x 16 final contraction [TF32])
-            f_fwd = n * 3 * 2 * K * (136 + 2 * 16)
-            f_grad = n * 3 * 2 * K * (136 + 2 * 16 + 2 * 16)
-            issued_fwd = n * 3 * 2 * tab.Kpad * (144 + 2 * 16)
-            issued_grad = n * 3 * 2 * tab.Kpad * (144 + 2 * 16 + 2 * 16)
+            #   forward : 3 passes x 2K x (136 weighted-sum columns + 16 distance dims) [all fp16]
+            #   gradient: 3 passes x 2K x (136 [fp16] + 16 [fp16] + 2 x 16 final contraction [TF32])
+            f_fwd = n * 3 * 2 * K * (136 + 16)
+            f_grad = n * 3 * 2 * K * (136 + 16 + 2 * 16)
+            issued_fwd = n * 3 * 2 * tab.Kpad * (144 + 16)
+            issued_grad = n * 3 * 2 * tab.Kpad * (144 + 16 + 2 * 16)
             note = ('fp16-equivalent tensor flops (TF32 MACs weighted x2: measured TF32 GEMM rate %.0f TF/s vs '
                     'bf16 %.0f TF/s in this run); symmetric tables -> 136 packed columns; dense-M definition '
                     'of SURVEY.md 8d would read %.0f TF/s fp32-equivalent' )

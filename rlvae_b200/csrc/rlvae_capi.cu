@@ -32,16 +32,18 @@ __global__ void pack_centroids_kernel(const float* __restrict__ c_in, int K, int
                                       float* __restrict__ stats) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
-  float nrm = 0.f;
+  float nrm = 0.f, amax = 0.f;
   for (int j = 0; j < d; ++j) {
     const float v = (k < K) ? c_in[(int64_t)k * d + j] : 0.f;
     c[(int64_t)k * d + j] = v;
     nrm = fmaf(v, v, nrm);
+    amax = fmaxf(amax, fabsf(v));
   }
   cn[k] = nrm;
   if (k < K) {
     atomicAdd(&stats[0], nrm);                                  // sum ||c||^2
     atomicMax(reinterpret_cast<int*>(&stats[1]), __float_as_int(nrm));  // max (nrm >= 0)
+    if (isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[4]), __float_as_int(amax));  // max |c_kj|
   }
   if (cstack != nullptr) {  // d == 16
     for (int j = 0; j < 16; ++j) {
@@ -85,6 +87,20 @@ __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int 
     }
   }
   if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[3]), __float_as_int(amax));
+}
+
+// split-fp16 centroid rows for GEMM1 (d == 16): [Kpad, 64] fp16 = [fp16(2^ec c) (16) | residual (16) | 0 (32)]
+// (one 128-byte swizzle row per centroid, like cstack)
+__global__ void pack_c16h_kernel(const float* __restrict__ c, int K, int Kpad, float scale, __half* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  for (int j = 0; j < 16; ++j) {
+    const float v = (k < K) ? scale * c[(int64_t)k * 16 + j] : 0.f;
+    const __half h = __float2half_rn(v);
+    out[(int64_t)k * 64 + j] = h;
+    out[(int64_t)k * 64 + 16 + j] = __float2half_rn(v - __half2float(h));
+  }
+  for (int j = 32; j < 64; ++j) out[(int64_t)k * 64 + j] = __float2half_rn(0.f);
 }
 
 // split-fp16 natural tables [Kpad, 192] (136 packed columns + zeros) for the gradient kernel
@@ -194,7 +210,8 @@ static void free_tables(rlvae_tables* t) {
   if (t->Mnh_hi) cudaFree(t->Mnh_hi);
   if (t->Mnh_lo) cudaFree(t->Mnh_lo);
   if (t->c64h) cudaFree(t->c64h);
-  t->c64h = nullptr;
+  if (t->c16h) cudaFree(t->c16h);
+  t->c64h = t->c16h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
                     &t->Mn_hi, &t->Mn_lo, &t->ct_hi, &t->ct_lo, &t->cn_inf, &t->cmask, &t->Mts_hi, &t->Mts_lo, &t->Mns_hi, &t->Mns_lo};
@@ -235,7 +252,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   t->T = temperature; t->T2 = temperature * temperature; t->lambda = regularization;
   const bool tc = (d == 16);
 
-  float* stats = nullptr;  // [0] sum ||c||^2, [1] max ||c||^2, [2] (int) asymmetric flag
+  float* stats = nullptr;  // [0] sum ||c||^2, [1] max ||c||^2, [2] (int) asymmetric flag, [3] max |M|, [4] max |c|
 #define ALLOC(ptr, elems)                                                          \
   do {                                                                             \
     cudaError_t _e = cudaMalloc(&(ptr), sizeof(float) * (size_t)(elems));          \
@@ -245,7 +262,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
       return 1;                                                                    \
     }                                                                              \
   } while (0)
-  ALLOC(stats, 4);
+  ALLOC(stats, 8);
   ALLOC(t->c, (size_t)Kpad * d);
   ALLOC(t->cn, Kpad);
   ALLOC(t->M, (size_t)Kpad * dd);
@@ -271,7 +288,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
       return fail(1);                                                              \
     }                                                                              \
   } while (0)
-  OK_OR_FAIL(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
+  OK_OR_FAIL(cudaMemsetAsync(stats, 0, 8 * sizeof(float), s));
   const float inv_T2_log2e = 1.4426950408889634f / t->T2;
   pack_centroids_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(centroids, K, Kpad, d, inv_T2_log2e, t->c,
                                                            t->cn, t->cstack, t->cbias, t->ct_hi, t->ct_lo, t->cn_inf, t->cmask, stats);
@@ -281,7 +298,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   OK_OR_FAIL(cudaGetLastError());
   symmetry_kernel<<<592, 256, 0, s>>>(matrices, K, d, reinterpret_cast<int*>(stats + 2));
   OK_OR_FAIL(cudaGetLastError());
-  float h_stats[4];
+  float h_stats[8];
   OK_OR_FAIL(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
   OK_OR_FAIL(cudaStreamSynchronize(s));
   cudaFree(stats);
@@ -291,6 +308,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
   t->symmetric = asym ? 0 : 1;
   t->r2max = h_stats[1];
   t->m_absmax = h_stats[3];
+  t->c_absmax = h_stats[4];
   const float r2mean = h_stats[0] / (float)K;
   // Accuracy gate of the expanded form ||z||^2+||c||^2-2 z.c (DESIGN.md "precision"): its
   // absolute error ~2.5e-7*mean||c||^2 becomes a relative error /T^2 in every weight.
@@ -338,6 +356,19 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           pack_sym_nat_h_kernel<<<592, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, e), static_cast<__half*>(t->Mnh_hi),
                                                     static_cast<__half*>(t->Mnh_lo));
           OK_OR_FAIL(cudaGetLastError());
+          // split-fp16 centroid rows for GEMM1: c' = 2^ec c with max|c'| in [2^13, 2^14)
+          int exc = 0;
+          frexpf(t->c_absmax > 0.f ? t->c_absmax : 1.f, &exc);
+          int ec = 14 - exc;
+          ec = ec > 50 ? 50 : (ec < -50 ? -50 : ec);
+          if (cudaMalloc(&t->c16h, sizeof(__half) * (size_t)Kpad * 64) != cudaSuccess) {
+            set_error("tables_create: cudaMalloc (fp16 centroid rows) failed");
+            return fail(1);
+          }
+          pack_c16h_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, K, Kpad, ldexpf(1.f, ec),
+                                                              static_cast<__half*>(t->c16h));
+          OK_OR_FAIL(cudaGetLastError());
+          t->c16_unscale = ldexpf(1.f, -ec);
           OK_OR_FAIL(cudaStreamSynchronize(s));
           t->h16_out_scale = ldexpf(1.f, -(14 + e));
           t->h16_m_unscale = ldexpf(1.f, -e);

@@ -95,6 +95,10 @@ struct rlvae_tables {
   CUtensorMap tm_mnh_hi, tm_mnh_lo, tm_mnh2_hi, tm_mnh2_lo;
   // d == 64 split-fp16 forward path (rlvae_tc64.cu): centroid rows [Kpad,128] fp16 = [hi | lo] of 2^ec c;
   // Mh_hi / Mh_lo then hold the packed-transposed [2176, Kpad] tables
+  void* c16h = nullptr;        // d == 16: [Kpad,64] fp16 = [hi (16) | lo (16) | 0] of 2^ec c (GEMM1 of the fp16 kernels)
+  float c16_unscale = 0.f;     // 2^-ec
+  float c_absmax = 0.f;
+  CUtensorMap tm_c16h;
   void* c64h = nullptr;
   float c64_unscale = 0.f;     // 2^-ec
   CUtensorMap tm_c64, tm_c64_2;   // boxes of 32 centroids x 32 (pair: 16) rows

@@ -166,7 +166,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const float* __restrict__ z, const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
                           const float* __restrict__ cnat /* EXACT: natural centroid rows [Kpad,16] */, int64_t n,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
-                          float out_scale /* 2^-(14+e) */, FusedOut fo) {
+                          float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS, OUT_LD = h16::OUT_LD;
@@ -237,7 +237,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   __syncthreads();            // TMEM base published (the exp threads store z into TMEM below)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  float zb = 0.f;
+  float zb = 0.f, s_scale = 0.f;      // exponent = S' * s_scale + bias_k + zb
   float2 nz[8];                       // EXACT: the negated point
 #pragma unroll
   for (int j = 0; j < 8; ++j) nz[j] = make_float2(0.f, 0.f);
@@ -254,23 +254,28 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
       }
     }
-    float nrm = 0.f;
+    float nrm = 0.f, zmax = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) nrm = fmaf(zv[j], zv[j], nrm);
+    for (int j = 0; j < 16; ++j) { nrm = fmaf(zv[j], zv[j], nrm); zmax = fmaxf(zmax, fabsf(zv[j])); }
     zb = EXACT ? P_SHIFT : (-nrm * alpha + P_SHIFT);     // P' = 2^14 P, folded into the exponent
 #pragma unroll
     for (int j = 0; j < 8; ++j) nz[j] = make_float2(-zv[2 * j], -zv[2 * j + 1]);
-    if (wg == 1 && !EXACT) {         // exp group A writes the A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
-      uint32_t hi[16], lo[16];
+    // GEMM1 on kind::f16: z' = 2^ez z (per point, max|z'| in [2^13, 2^14)), split hi + lo; S = 2^-(ez+ec) S'
+    int ez = 0;
+    if (zmax > 0.f && zmax < 3.0e38f) {
+      const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+      ez = 14 - ex;
+      ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
+    }
+    s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
+    if (wg == 1 && !EXACT) {         // exp group A writes the A operand of GEMM1 into TMEM
+      const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float h = tf32_rna(zv[j]);
-        hi[j] = __float_as_uint(h);
-        lo[j] = __float_as_uint(zv[j] - h);
-      }
+      for (int j = 0; j < 8; ++j) split_pair(zv[2 * j] * zsc, zv[2 * j + 1] * zsc, hi[j], lo[j]);
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      TMEM_ST16(tmem_base + lane_addr + TM_ZHI, hi);
-      TMEM_ST16(tmem_base + lane_addr + TM_ZLO, lo);
+      TMEM_ST8(tmem_base + lane_addr + TM_ZHI, hi);
+      TMEM_ST8(tmem_base + lane_addr + TM_ZLO, lo);
       tmem_wait_st();
     }
   }
@@ -339,17 +344,21 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         constexpr int cs = decltype(CSc)::value, sb = decltype(SBc)::value;
         if (elect_one()) {
           if (!EXACT) {
-            // S = z_hi.c_hi + z_hi.c_lo + z_lo.c_hi (3xTF32), A operand from TMEM: N/2 = 32 cycles per MMA
-            // (the shared-memory A tile costs 48); a centroid row is [c_hi (16) | c_lo (16)] = 4 K-steps
-            constexpr uint32_t id1 = make_idesc(PAIR ? 256 : 128, BK);
+            // S' = z'_hi.c'_hi + z'_hi.c'_lo + z'_lo.c'_hi on kind::f16 (K = 16 = all latent dims per MMA),
+            // A operand from TMEM: 3 MMAs of 32 cycles (3xTF32 needed 6); a centroid row is
+            // [c'_hi (16) | c'_lo (16) | 0] fp16 = 2 K-steps of one 128-byte swizzle row
+            constexpr uint32_t id1 = make_idesc_f16(PAIR ? 256 : 128, BK);
             const uint32_t d = tmem_base + TM_SP + sb * 64;
             const uint64_t bc = c_desc0 + ((cs * C_TILE_BYTES) >> 4);
-            MMA_TS(d, tmem_base + TM_ZHI, bc, id1, 0);
-            MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 2, id1, 1);
-            MMA_TS(d, tmem_base + TM_ZHI, bc + 4, id1, 1);
-            MMA_TS(d, tmem_base + TM_ZHI + 8, bc + 6, id1, 1);
-            MMA_TS(d, tmem_base + TM_ZLO, bc, id1, 1);
-            MMA_TS(d, tmem_base + TM_ZLO + 8, bc + 2, id1, 1);
+            if (PAIR) {
+              mma_ts_f16_pair(d, tmem_base + TM_ZHI, bc, id1, 0);
+              mma_ts_f16_pair(d, tmem_base + TM_ZHI, bc + 2, id1, 1);
+              mma_ts_f16_pair(d, tmem_base + TM_ZLO, bc, id1, 1);
+            } else {
+              mma_ts_f16(d, tmem_base + TM_ZHI, bc, id1, 0);
+              mma_ts_f16(d, tmem_base + TM_ZHI, bc + 2, id1, 1);
+              mma_ts_f16(d, tmem_base + TM_ZLO, bc, id1, 1);
+            }
           }
           // EXACT: no distance GEMM; S_FULL then only says "GEMM2 has finished reading this P buffer"
           COMMIT(BAR_S_FULL(sb));
@@ -417,7 +426,6 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     reg_dec<104>();
     const int grp = wg - 1;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const float two_alpha = 2.f * alpha;
     long long pe_wait = 0, pe_work = 0;
     (void)pe_wait; (void)pe_work;
     for (int j = grp; j < num_blocks; j += 2) {
@@ -452,10 +460,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bv = bias4[q];
-            const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), two_alpha, bv.x + zb));
-            const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), two_alpha, bv.y + zb));
-            const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), two_alpha, bv.z + zb));
-            const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), two_alpha, bv.w + zb));
+            const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), s_scale, bv.x + zb));
+            const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), s_scale, bv.y + zb));
+            const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), s_scale, bv.z + zb));
+            const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), s_scale, bv.w + zb));
             split_pair(w0, w1, ph[2 * q], pl[2 * q]);
             split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
           }
@@ -680,7 +688,8 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const float* __restrict__ z, const float* __restrict__ u,
                        const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
                        const float* __restrict__ cnat /* EXACT: natural centroid rows */, int64_t n, int num_blocks,
-                       float alpha, float scale /* includes 2^-eM */, float* __restrict__ out, int u_packed) {
+                       float alpha, float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
+                       float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
   constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
                      M_HALF_BYTES = g16::M_HALF_BYTES, OFF_C = g16::OFF_C,
@@ -764,7 +773,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   const int prow = quarter * 32 + lane;
   const int grp = (warp >= 6) ? 1 : 0;
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-  float zb = 0.f;
+  float zb = 0.f, s_scale = 0.f;   // exponent = S' * s_scale + bias_k + zb
   float u_unscale = 1.f;      // 2^-eU
   float zrow[16];
 #pragma unroll
@@ -782,16 +791,25 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
       zb = EXACT ? 0.f : -nrm * alpha;
     }
-    if (grp == 0 && !EXACT) {   // A operand of GEMM1: z = hi + lo (TF32 split) in TMEM
-      uint32_t zh[16], zl[16];
+    {   // GEMM1 on kind::f16: z' = 2^ez z (max|z'| in [2^13, 2^14)), split hi + lo; S = 2^-(ez+ec) S'
+      float zmax = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float hh = tf32_rna(zrow[j]);
-        zh[j] = __float_as_uint(hh);
-        zl[j] = __float_as_uint(zrow[j] - hh);
+      for (int j = 0; j < 16; ++j) zmax = fmaxf(zmax, fabsf(zrow[j]));
+      int ez = 0;
+      if (zmax > 0.f && zmax < 3.0e38f) {
+        const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+        ez = 14 - ex;
+        ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
       }
-      TMEM_ST16(tmem_base + lane_addr + TM_ZHI, zh);
-      TMEM_ST16(tmem_base + lane_addr + TM_ZLO, zl);
+      s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
+      if (grp == 0 && !EXACT) {
+        const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
+        uint32_t zh[8], zl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_pair(zrow[2 * j] * zsc, zrow[2 * j + 1] * zsc, zh[j], zl[j]);
+        TMEM_ST8(tmem_base + lane_addr + TM_ZHI, zh);
+        TMEM_ST8(tmem_base + lane_addr + TM_ZLO, zl);
+      }
     }
     // ---- U' = 2^eU Ut, split into fp16 hi | lo, resident in TMEM as the A operand of the T GEMM.
     // group 0 converts packed columns [0,64), group 1 [64,144); both scan the whole row for the scale.
@@ -938,7 +956,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loops assume these periods");
       const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
       const uint64_t m_desc0 = make_desc_sw128(base + OFF_M);
-      constexpr uint32_t ID1 = make_idesc(PAIR ? 256 : 128, BK);
+      constexpr uint32_t ID1 = make_idesc_f16(PAIR ? 256 : 128, BK);
       auto issue_st = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
         constexpr int J = decltype(Jc)::value;
         constexpr int cs = J % C_STAGES, sb = J & 1, ms = J % M_STAGES;
@@ -952,13 +970,16 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const uint64_t bh = m_desc0 + ((ms * M_TILE_BYTES) >> 4);
         const uint64_t bl = bh + (M_HALF_BYTES >> 4);
         if (elect_one()) {
-          if (!EXACT) {
-            MMA_TS(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
-            MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 2, ID1, 1);
-            MMA_TS(s_t, tmem_base + TM_ZHI, bc + 4, ID1, 1);
-            MMA_TS(s_t, tmem_base + TM_ZHI + 8, bc + 6, ID1, 1);
-            MMA_TS(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
-            MMA_TS(s_t, tmem_base + TM_ZLO + 8, bc + 2, ID1, 1);
+          if (!EXACT) {     // S' = z'_hi.c'_hi + z'_hi.c'_lo + z'_lo.c'_hi (kind::f16, K = 16: one MMA each)
+            if (PAIR) {
+              mma_ts_f16_pair(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
+              mma_ts_f16_pair(s_t, tmem_base + TM_ZHI, bc + 2, ID1, 1);
+              mma_ts_f16_pair(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
+            } else {
+              mma_ts_f16(s_t, tmem_base + TM_ZHI, bc, ID1, 0);
+              mma_ts_f16(s_t, tmem_base + TM_ZHI, bc + 2, ID1, 1);
+              mma_ts_f16(s_t, tmem_base + TM_ZLO, bc, ID1, 1);
+            }
           }
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
@@ -1029,7 +1050,6 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
   } else {
     // =========================================================== exp groups (one thread per point)
-    const float two_alpha = 2.f * alpha;
     float2 nz[8];                        // EXACT: the negated point
 #pragma unroll
     for (int q = 0; q < 8; ++q) nz[q] = make_float2(-zrow[2 * q], -zrow[2 * q + 1]);
@@ -1077,7 +1097,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           for (int e = 0; e < 4; ++e) {
             const int i = 4 * q + e;
             const float w = EXACT ? ex2_approx(fmaf(dist2_row16(crow + i * 4, nz), -alpha, b4[e]))
-                                  : ex2_approx(fmaf(__uint_as_float(sv[i]), two_alpha, b4[e] + zb));
+                                  : ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
             const float uv = w * __uint_as_float(tv[i]);
             su_blk += uv;
             const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
@@ -1479,6 +1499,7 @@ int tc_build_h16_descriptors(rlvae_tables* t) {
   if (int rc = make_map_h(enc, &t->tm_mh_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS)) return rc;
   if (int rc = make_map_h(enc, &t->tm_mh2_hi, t->Mh_hi, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
   if (int rc = make_map_h(enc, &t->tm_mh2_lo, t->Mh_lo, Kpad, tc::h16::NCOLS, tc::BK, tc::h16::NCOLS / 2)) return rc;
+  if (int rc = make_map_h(enc, &t->tm_c16h, t->c16h, 64, Kpad, 64, 32)) return rc;   // 32 centroid rows (128 B each) per box
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh_hi, t->Mnh_hi, Kpad, tc::BK)) return rc;
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh_lo, t->Mnh_lo, Kpad, tc::BK)) return rc;
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh2_hi, t->Mnh_hi, Kpad, tc::BK / 2)) return rc;
@@ -1524,12 +1545,13 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   const int nb = t->Kpad / tc::BK;
   const float lambda = t->lambda;
   const float out_scale = t->h16_out_scale;
+  const float cu = t->c16_unscale;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, fo));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
+                                       alpha, lambda, out_scale, cu, fo));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, fo));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
+                                       alpha, lambda, out_scale, cu, fo));
   }
   return 0;
 }
@@ -1599,12 +1621,13 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
+  const float cu = t->c16_unscale;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
-                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
+                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, out, u_packed));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_cstack, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
-                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
+                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, out, u_packed));
   }
   return 0;
 }
