@@ -70,9 +70,7 @@ constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
 constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + 3;   // + 3 pipe-trace barriers (profiling builds)
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
-constexpr int OUT_LD = 148;                               // staging row: 16-byte aligned, conflict-free for 128-bit
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(TILE_M * OUT_LD * 4 <= M_STAGES * M_TILE_BYTES, "epilogue staging must fit the M ring");
 constexpr uint32_t TM_SP = 0;        // + buf*64
 constexpr uint32_t TM_ACC = 192;     // + buf*160
 constexpr uint32_t TM_ZHI = 336;     // z (tf32 hi) 16 columns: A operand of GEMM1, in the hole between the accumulators
@@ -96,8 +94,11 @@ __device__ __forceinline__ bool sym16_factor(float (&a)[144], float& lad, float 
     for (int k = 0; k < j; ++k) d = fmaf(-SYM_L(j, k), SYM_L(j, k), d);
     ok = ok && (d > 0.f);
     lad += logf(d);
-    const float ljj = sqrtf(d);
-    const float inv = 1.f / ljj;
+    // 1/sqrt(d) by MUFU.RSQ + one Newton step (< 1 ulp), L_jj = d / sqrt(d): this is the serial part of
+    // the factorisation (16 dependent columns), sqrtf + an IEEE division were a third of its latency
+    float inv = rsqrtf(d);
+    inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);
+    const float ljj = d * inv;
     rd[j] = inv;
     SYM_L(j, j) = ljj;
 #pragma unroll
@@ -169,7 +170,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
-                M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS, OUT_LD = h16::OUT_LD;
+                M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
   constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, M_HALF_BYTES = h16::M_HALF_BYTES, TM_SP = h16::TM_SP,
                      TM_ACC = h16::TM_ACC, TM_ZHI = h16::TM_ZHI, TM_ZLO = h16::TM_ZLO;
   constexpr float P_SHIFT = h16::P_SHIFT;
@@ -536,9 +537,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
              (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf1 - pf0);
 #endif
     // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
-    float* stage = reinterpret_cast<float*>(gbase + h16::OFF_M);
     const int t = threadIdx.x - 384;
-    const int64_t rows_here = (n - row0 < TILE_M) ? (n - row0) : TILE_M;
+    const int64_t rows_here = (n - row0 < TILE_M) ? ((n - row0 > 0) ? (n - row0) : 0) : TILE_M;   // 0 for a pair's padding tile
     const bool live = prow < rows_here;
 #pragma unroll
     for (int pc = 0; pc < NCOLS; ++pc) {
@@ -547,26 +547,35 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
       total[pc] = (pc < 136) ? fmaf(total[pc], out_scale, diag ? lambda : 0.f) : 0.f;
     }
-    auto store_rows = [&](float* dst_base) {      // total[] -> [rows, 144] coalesced through smem
-#pragma unroll
-      for (int q = 0; q < NCOLS / 4; ++q)
-        *reinterpret_cast<float4*>(stage + prow * OUT_LD + q * 4) =
-            make_float4(total[4 * q], total[4 * q + 1], total[4 * q + 2], total[4 * q + 3]);
+    // Output tiles leave through shared memory and ONE bulk async copy each (cp.async.bulk, issued by a
+    // single thread): the CTA's 128 rows are contiguous in global memory, so the staging is unpadded
+    // (bank conflicts on the staging writes cost ~1k cycles; a cooperative copy by the 128 fold threads
+    // cost ~0.9 ms per 2^20 points for the expanded G^-1).  The staging area spans the centroid ring and
+    // the table ring, both idle by now.
+    float* fstage = reinterpret_cast<float*>(gbase + h16::OFF_C);
+    static_assert(TILE_M * 256 * 4 <= h16::OFF_BIAS, "full-matrix staging must fit the C + M rings");
+    auto bulk_store = [&](float* gdst, uint32_t bytes) {       // staged tile -> global, asynchronous
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic smem writes -> async proxy
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float4* dst = reinterpret_cast<float4*>(dst_base + row0 * NCOLS);
-      for (int i = t; i < (int)rows_here * 36; i += 128) {
-        const int r = i / 36, c4 = i - r * 36;
-        dst[i] = *reinterpret_cast<const float4*>(stage + r * OUT_LD + c4 * 4);
+      if (t == 0 && bytes > 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(gdst), "r"(smem_u32(fstage)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+    };
+    auto bulk_wait = [&]() {                                    // staging area reusable again
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
-    if (fo.a_packed != nullptr) store_rows(fo.a_packed);
+    auto store_rows = [&](float* dst_base) {                    // total[] -> packed [rows, 144]
+#pragma unroll
+      for (int q = 0; q < NCOLS / 4; ++q)
+        *reinterpret_cast<float4*>(fstage + prow * NCOLS + q * 4) =
+            make_float4(total[4 * q], total[4 * q + 1], total[4 * q + 2], total[4 * q + 3]);
+      bulk_store(dst_base + row0 * NCOLS, (uint32_t)rows_here * NCOLS * 4);
+    };
+    if (fo.a_packed != nullptr) { store_rows(fo.a_packed); bulk_wait(); }
     if (fo.a_full != nullptr) {
-      // full symmetric [rows, 256] through smem (row stride 260 floats: conflict-free 128-bit accesses);
-      // the staging area spans the centroid ring and the table ring, both idle by now
-      constexpr int FLD = 260;
-      static_assert(TILE_M * FLD * 4 <= h16::OFF_BIAS, "full-matrix staging must fit the C + M rings");
-      float* fstage = reinterpret_cast<float*>(gbase + h16::OFF_C);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
 #pragma unroll
@@ -577,16 +586,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             const int j = 4 * q + e;
             v[e] = total[i <= j ? sym_index(i, j) : sym_index(j, i)];
           }
-          *reinterpret_cast<float4*>(fstage + prow * FLD + i * 16 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(fstage + prow * 256 + i * 16 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float4* dst = reinterpret_cast<float4*>(fo.a_full + row0 * 256);
-      for (int i = t; i < (int)rows_here * 64; i += 128) {
-        const int r = i >> 6, c4 = i & 63;
-        dst[i] = *reinterpret_cast<const float4*>(fstage + r * FLD + c4 * 4);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bulk_store(fo.a_full + row0 * 256, (uint32_t)rows_here * 1024);   // the Cholesky below overlaps this copy
     }
     const bool fused = fo.g_packed != nullptr || fo.logabsdet != nullptr || fo.sign != nullptr || fo.diag_g != nullptr;
     if (fused) {
@@ -612,9 +615,11 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (fo.g_packed != nullptr) {
 #pragma unroll
         for (int i = 136; i < NCOLS; ++i) total[i] = 0.f;
+        if (fo.a_full != nullptr) bulk_wait();
         store_rows(fo.g_packed);
       }
     }
+    bulk_wait();      // no bulk copy may still read this CTA's shared memory when it exits
 #ifdef RLVAE_TC_PROFILE
     if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
       printf("[h16 prof %d] epilogue %lld cycles\n", (int)blockIdx.x, clock64() - pf1);
