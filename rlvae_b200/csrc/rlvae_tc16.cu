@@ -537,7 +537,6 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
              (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf1 - pf0);
 #endif
     // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
-    const int t = threadIdx.x - 384;
     const int64_t rows_here = (n - row0 < TILE_M) ? ((n - row0 > 0) ? (n - row0) : 0) : TILE_M;   // 0 for a pair's padding tile
     const bool live = prow < rows_here;
 #pragma unroll
@@ -547,35 +546,22 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
       total[pc] = (pc < 136) ? fmaf(total[pc], out_scale, diag ? lambda : 0.f) : 0.f;
     }
-    // Output tiles leave through shared memory and ONE bulk async copy each (cp.async.bulk, issued by a
-    // single thread): the CTA's 128 rows are contiguous in global memory, so the staging is unpadded
-    // (bank conflicts on the staging writes cost ~1k cycles; a cooperative copy by the 128 fold threads
-    // cost ~0.9 ms per 2^20 points for the expanded G^-1).  The staging area spans the centroid ring and
-    // the table ring, both idle by now.
-    float* fstage = reinterpret_cast<float*>(gbase + h16::OFF_C);
-    static_assert(TILE_M * 256 * 4 <= h16::OFF_BIAS, "full-matrix staging must fit the C + M rings");
-    auto bulk_store = [&](float* gdst, uint32_t bytes) {       // staged tile -> global, asynchronous
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic smem writes -> async proxy
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (t == 0 && bytes > 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(gdst), "r"(smem_u32(fstage)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    // Outputs are stored straight from the registers of the thread that owns the point: 36 (packed) or 64
+    // (expanded) fire-and-forget 128-bit stores per row, each row a contiguous 576 B / 1 KB run, so every
+    // 32-byte sector is written completely (by two consecutive stores) and the stores drain while the
+    // thread goes on with the Cholesky.  (Staging through shared memory + a cooperative or bulk copy
+    // serialised ~10k cycles per CTA behind barriers: measured +0.9 / +0.65 ms per 2^20 points.)
+    auto store_rows = [&](float* dst_base) {                    // total[] -> packed [rows, 144]
+      if (live) {
+        float4* dst = reinterpret_cast<float4*>(dst_base + (row0 + prow) * NCOLS);
+#pragma unroll
+        for (int q = 0; q < NCOLS / 4; ++q)
+          dst[q] = make_float4(total[4 * q], total[4 * q + 1], total[4 * q + 2], total[4 * q + 3]);
       }
     };
-    auto bulk_wait = [&]() {                                    // staging area reusable again
-      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    };
-    auto store_rows = [&](float* dst_base) {                    // total[] -> packed [rows, 144]
-#pragma unroll
-      for (int q = 0; q < NCOLS / 4; ++q)
-        *reinterpret_cast<float4*>(fstage + prow * NCOLS + q * 4) =
-            make_float4(total[4 * q], total[4 * q + 1], total[4 * q + 2], total[4 * q + 3]);
-      bulk_store(dst_base + row0 * NCOLS, (uint32_t)rows_here * NCOLS * 4);
-    };
-    if (fo.a_packed != nullptr) { store_rows(fo.a_packed); bulk_wait(); }
-    if (fo.a_full != nullptr) {
+    if (fo.a_packed != nullptr) store_rows(fo.a_packed);
+    if (fo.a_full != nullptr && live) {
+      float4* dst = reinterpret_cast<float4*>(fo.a_full + (row0 + prow) * 256);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
 #pragma unroll
@@ -586,10 +572,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             const int j = 4 * q + e;
             v[e] = total[i <= j ? sym_index(i, j) : sym_index(j, i)];
           }
-          *reinterpret_cast<float4*>(fstage + prow * 256 + i * 16 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          dst[i * 4 + q] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
-      bulk_store(fo.a_full + row0 * 256, (uint32_t)rows_here * 1024);   // the Cholesky below overlaps this copy
     }
     const bool fused = fo.g_packed != nullptr || fo.logabsdet != nullptr || fo.sign != nullptr || fo.diag_g != nullptr;
     if (fused) {
@@ -615,11 +600,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (fo.g_packed != nullptr) {
 #pragma unroll
         for (int i = 136; i < NCOLS; ++i) total[i] = 0.f;
-        if (fo.a_full != nullptr) bulk_wait();
         store_rows(fo.g_packed);
       }
     }
-    bulk_wait();      // no bulk copy may still read this CTA's shared memory when it exits
 #ifdef RLVAE_TC_PROFILE
     if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
       printf("[h16 prof %d] epilogue %lld cycles\n", (int)blockIdx.x, clock64() - pf1);
