@@ -433,14 +433,20 @@ static bool use_h16(const rlvae_tables* t) {
 // a_full (optional): the expanded [N,16,16] G^{-1} as well (same kernel on the split-fp16 path).
 static int sym_forward(const rlvae_tables* t, const float* z, int64_t n, float* a_packed, float* g_packed,
                        float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s,
-                       float* a_full = nullptr) {
-  if (use_h16(t))
-    return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s, a_full);
+                       float* a_full = nullptr, float* g_full = nullptr) {
+  if (use_h16(t)) {
+    // a pivoting fallback can only write the packed G: expand it afterwards for the (rare) failures by
+    // keeping g_packed alongside g_full
+    return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s, a_full,
+                                     g_full);
+  }
   RLVAE_REQUIRE(a_packed != nullptr, "symmetric 3xTF32 path needs the packed buffer");
   if (int rc = launch_inverse_metric_tc_sym(t, z, n, a_packed, s)) return rc;
   if (a_full != nullptr) { if (int rc = launch_unpack_sym16(a_packed, n, a_full, s)) return rc; }
-  if (g_packed || lad || sgn || diag)
-    return launch_sym16_inverse(a_packed, n, g_packed, lad, lad_scale, sgn, diag, fail_ws, s);
+  if (g_packed || lad || sgn || diag) {
+    if (int rc = launch_sym16_inverse(a_packed, n, g_packed, lad, lad_scale, sgn, diag, fail_ws, s)) return rc;
+  }
+  if (g_full != nullptr) return launch_unpack_sym16(g_packed, n, g_full, s);
   return 0;
 }
 
@@ -565,8 +571,8 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     // kernel contracts the packed G directly (G^T == G).  The spare tail of a_buf is the fallback list.
     float* g_packed = (g != nullptr || grad_logdet_g != nullptr) ? (w + mat) : nullptr;
     int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
-    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv)) return rc;
-    if (g != nullptr) { if (int rc = launch_unpack_sym16(g_packed, n, g, s)) return rc; }
+    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv, g))
+      return rc;
     if (grad_logdet_g != nullptr)
       return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
     return 0;

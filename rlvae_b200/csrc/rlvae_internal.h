@@ -126,7 +126,8 @@ int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, floa
 // eigenvalues (ascending) of symmetric 16x16 matrices: a = packed [N,144] or full [N,16,16] (upper triangle read)
 int launch_sym16_eigvalsh(const float* a, int64_t n, int packed, float* eig, cudaStream_t s);
 int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
-                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s);
+                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s,
+                          float* g_full = nullptr);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
 int tc_build_h16_descriptors(rlvae_tables* t);
 // d == 64 (symmetric tables): tables + forward through a packed [N,2176] scratch
@@ -140,7 +141,7 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
 // a_full (optional): the expanded [N,16,16] G^{-1}, written by the same kernel
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s, float* a_full = nullptr);
+                              int* fail_ws, cudaStream_t s, float* a_full = nullptr, float* g_full = nullptr);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,

@@ -366,14 +366,30 @@ int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, floa
 
 // The pivoting pass over the matrices a Cholesky kernel rejected (fail_ws = counter + list); usually
 // the list is empty and every CTA exits after reading the counter.
+// expanded [N,16,16] rows of the listed matrices from their packed rows (after the pivoting pass)
+__global__ void unpack_sym16_list_kernel(const float* __restrict__ packed, const int* __restrict__ list,
+                                         const int* __restrict__ count, float* __restrict__ full) {
+  const int cnt = *count;
+  for (int slot = blockIdx.x; slot < cnt; slot += gridDim.x) {
+    const int64_t p = list[slot];
+    const int e = threadIdx.x, i = e >> 4, j = e & 15;
+    full[p * 256 + e] = packed[p * kSymCols + (i <= j ? sym16_index(i, j) : sym16_index(j, i))];
+  }
+}
+
 int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
-                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s) {
+                          float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s,
+                          float* g_full) {
   if (n == 0) return 0;
   const int64_t groups = (n + PP<16>::MATS - 1) / PP<16>::MATS;
   const unsigned fgrid = (unsigned)(groups < 1184 ? groups : 1184);
   batched_inverse_kernel<16, true><<<fgrid, PP<16>::THREADS, 0, s>>>(
       a_packed, n, nullptr, logabsdet, sign, diag_g, 0, fail_ws + 1, fail_ws, g_packed, lad_scale);
   RLVAE_LAUNCH_OK();
+  if (g_full != nullptr && g_packed != nullptr) {
+    unpack_sym16_list_kernel<<<296, 256, 0, s>>>(g_packed, fail_ws + 1, fail_ws, g_full);
+    RLVAE_LAUNCH_OK();
+  }
   return 0;
 }
 

@@ -147,6 +147,7 @@ struct FusedOut {
   float* a_full;       // [N,16,16] G^{-1} expanded (what the reference API returns) or NULL
   float* a_packed;     // [N,144] G^{-1} (lambda on the diagonal) or NULL
   float* g_packed;     // [N,144] G or NULL
+  float* g_full;       // [N,16,16] G expanded or NULL
   float* logabsdet;    // [N] lad_scale * log det G^{-1} or NULL
   float* sign;         // [N] or NULL
   float* diag_g;       // [N,16] or NULL
@@ -576,7 +577,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         }
       }
     }
-    const bool fused = fo.g_packed != nullptr || fo.logabsdet != nullptr || fo.sign != nullptr || fo.diag_g != nullptr;
+    const bool fused = fo.g_packed != nullptr || fo.g_full != nullptr || fo.logabsdet != nullptr ||
+                       fo.sign != nullptr || fo.diag_g != nullptr;
     if (fused) {
       if (!live) {
 #pragma unroll
@@ -585,7 +587,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         for (int i = 0; i < 16; ++i) total[sym_index(i, i)] = 1.f;
       }
       float lad, dg[16];
-      const bool ok = sym16_factor(total, lad, dg, fo.g_packed != nullptr);
+      const bool ok = sym16_factor(total, lad, dg, fo.g_packed != nullptr || fo.g_full != nullptr);
       if (live) {
         const int64_t r = row0 + prow;
         if (fo.logabsdet != nullptr) fo.logabsdet[r] = fo.lad_scale * lad;
@@ -601,6 +603,22 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int i = 136; i < NCOLS; ++i) total[i] = 0.f;
         store_rows(fo.g_packed);
+      }
+      if (fo.g_full != nullptr && live) {
+        float4* dst = reinterpret_cast<float4*>(fo.g_full + (row0 + prow) * 256);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q + e;
+              v[e] = total[i <= j ? sym_index(i, j) : sym_index(j, i)];
+            }
+            dst[i * 4 + q] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
       }
     }
 #ifdef RLVAE_TC_PROFILE
@@ -1560,23 +1578,25 @@ static bool h16_exact(const rlvae_tables* t) {
 // which needs packed G^{-1}: a_packed must be given whenever a factor output is requested).
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s, float* a_full) {
+                              int* fail_ws, cudaStream_t s, float* a_full, float* g_full) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr,
                 "split-fp16 tensor path needs latent_dim == 16 and symmetric tables");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0, "tensor path needs 16-byte aligned z");
-  const bool fused = g_packed || logabsdet || sign || diag_g;
+  const bool fused = g_packed || g_full || logabsdet || sign || diag_g;
   RLVAE_REQUIRE(!fused || (fail_ws != nullptr && a_packed != nullptr),
                 "fused factor outputs need the packed G^{-1} buffer and the fallback workspace");
   RLVAE_REQUIRE(n < (int64_t)1 << 31, "batch too large for the 32-bit fallback list");
   if (fused) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
   RLVAE_REQUIRE(a_full == nullptr || (reinterpret_cast<uintptr_t>(a_full) & 15) == 0, "G^-1 output must be 16-byte aligned");
-  tc::FusedOut fo{a_full, a_packed, g_packed, logabsdet, sign, diag_g, fail_ws, lad_scale};
+  RLVAE_REQUIRE(g_full == nullptr || (reinterpret_cast<uintptr_t>(g_full) & 15) == 0, "G output must be 16-byte aligned");
+  tc::FusedOut fo{a_full, a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
   int rc;
   if (h16_exact(t)) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
   else rc = h16_use_pairs() ? launch_h16<true, false>(t, z, n, fo, s) : launch_h16<false, false>(t, z, n, fo, s);
   if (rc) return rc;
-  if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s);
+  RLVAE_REQUIRE(g_full == nullptr || g_packed != nullptr, "the expanded G output needs the packed G buffer too");
+  if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s, g_full);
   return 0;
 }
 
