@@ -11,8 +11,10 @@
 // Both operands are exact sums of two fp16 numbers down to an ABSOLUTE floor of 2^-25 in the scaled
 // units (fp16 subnormal spacing), i.e. 2^-39 relative to the largest weight / table entry, which is
 // why the power-of-two pre-scaling matters and why it is exact.  The result is un-scaled by
-// 2^-(14+e) in the epilogue.  The distance GEMM (GEMM1) stays 3xTF32: its absolute error feeds the
-// exponent.
+// 2^-(14+e) in the epilogue.  The distance GEMM (GEMM1) is split the same way (z' = 2^ez z per point,
+// c' = 2^ec c per table, S = 2^-(ez+ec) (z'_hi.c'_hi + z'_hi.c'_lo + z'_lo.c'_hi), K = 16 = one MMA per
+// term), or -- EXACT mode, for temperatures where the expanded distance form is too inaccurate --
+// replaced by exact differences on the FMA pipe.
 //
 // Because P is half as wide in TMEM (two fp16 per 32-bit column) one CTA now owns ALL 144 packed
 // columns of its 128 points (no column halves -> GEMM1 and the exp stage are not duplicated) and
@@ -22,12 +24,14 @@
 //   TMEM columns: [0,192) three S/P buffers (64 each: S fp32, overwritten in place by
 //                 P_hi[0:32) | P_lo[0:32) | P_hi[32:64) | P_lo[32:64) as packed fp16),
 //                 [192,336) and [352,496) the two chunk accumulators (N = 144),
-//                 [336,352) z_hi and [496,512) z_lo (TF32 split of z: the A operand of GEMM1).
-//   Warp roles  : as in rlvae_tc.cu (TMA warp, MMA warp, two exp warpgroups, one fold warpgroup).
+//                 [336,344) z'_hi and [496,504) z'_lo (fp16 split of z: the A operand of GEMM1).
+//   Warps       : 0 TMA (centroid tiles + bias), 1 MMA issuer, 2 TMA (table tiles), 3 idle;
+//                 4-7 / 8-11 exp groups (even / odd super-blocks), 12-15 fold group.
 //   FUSED       : the fold warpgroup keeps the finished 136 entries of its point in registers and
 //                 runs the per-thread Cholesky of rlvae_perpoint.cu on them, so log det G and
-//                 diag(G) (and packed G) leave the kernel directly -- the "fused metric + log-det"
-//                 kernel of the north star.  Points that are not positive definite go to the same
+//                 diag(G) (and packed / expanded G, expanded G^{-1}) leave the kernel directly, stored
+//                 from the registers of the owning thread -- the "fused metric + log-det" kernel of
+//                 the north star.  Points that are not positive definite go to the same
 //                 fallback list.
 #include <cuda_fp16.h>
 
