@@ -267,6 +267,30 @@ def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
     assert rel_fro(b['ginv'][3000:3064].cpu(), ref) < TOL_MAT
 
 
+@pytest.mark.parametrize('sc,smul', [(1e-3, 1e-6), (1e3, 1e6), (37.0, 1e-3), (1.0, 3e4)])
+def test_scale_covariance_of_the_split_fp16_path(sc, smul):
+    """G^{-1}(s z; s c, m M, s T, m lambda) = m G^{-1}(z; c, M, T, lambda): exercises the power-of-two
+    pre-scalings of the split-fp16 kernels (tables far from unit scale must not lose accuracy), for
+    G^{-1}, log det, the gradient and the spectrum, against the unit-scale direct kernels."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(700, 16, seed=11)
+    z = make_points(600, 16, seed=12)
+    base = make_mt((sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization), 'direct')
+    ref = base.evaluate(z.to(dev()), want_ginv=True, want_logdet=True, want_grad=True)
+    t = (sm.centroids * sc, sm.metric_matrices * smul, sm.temperature * sc, sm.regularization * smul)
+    if 'tensor' not in paths_for(t):
+        pytest.skip('tensor path not selected')
+    mt = make_mt(t, 'tensor')
+    ev = mt.evaluate((z * sc).to(dev()), want_ginv=True, want_logdet=True, want_grad=True)
+    assert rel_fro(ev['ginv'].cpu() / smul, ref['ginv'].cpu()) < TOL_MAT
+    close_ld(ev['logdet_g'].cpu() + 16 * math.log(smul), ref['logdet_g'].cpu())
+    assert rel_fro(ev['grad_logdet_g'].cpu() * sc, ref['grad_logdet_g'].cpu()) < TOL_LD
+    sp = mt.compute_metric_spectrum((z * sc).to(dev()))
+    ref_ev = torch.linalg.eigvalsh(ref['ginv'].double().cpu())
+    assert ((sp['eigenvals_G_inv'].cpu().double() / smul - ref_ev).abs().max(dim=1).values
+            / ref_ev.abs().max(dim=1).values).max() < 1e-5
+
+
 def test_linearity_in_tables():
     """G^{-1} - lambda I is linear in M: eval(M1 + M2) == eval(M1) + eval(M2) - lambda I."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
