@@ -433,7 +433,7 @@ def run_ours(args):
                 'dtype': 'f32 (split-fp16 / 3xTF32 tensor products with fp32 accumulate: fp32-level accuracy)' if path_name == 'tensor' else 'f32',
                 'data': 'synthetic',
                 'config': {'workload': f'G^-1 + log det G + grad_z log det G, d={D}, K={K}, N=2^20 per GPU '
-                                       '(BASELINE.json configs[1])', 'points_per_gpu': n, 'path': path_name,
+                                       '(BASELINE.json configs[1])', 'points_per_gpu': n, 'path': path_name, 'implementation': mt.kernel_info().get('implementation'),
                            'parallelism': f'points sharded over {world} GPU(s), tables replicated',
                            'l2': 'L2 flushed (256 MB write) before every timed step; each step also '
                                  'writes >2 GB of outputs'},

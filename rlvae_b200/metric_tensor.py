@@ -284,6 +284,27 @@ class MetricTensor(nn.Module):
                 print(f"   Batch size: {d['batch_size']}, Centroids: {d['n_centroids']}")
             return d
 
+    def kernel_info(self) -> Dict[str, Any]:
+        """Which implementation `kernel_path='auto'` resolves to for the loaded tables."""
+        if not self._is_loaded or not self.centroids.is_cuda:
+            return {'loaded': self._is_loaded, 'device': str(self.centroids.device)}
+        tab = self._tables(self.centroids.device)
+        tensor = tab.tensor_capable and tab.tensor_auto and self.kernel_path != 'direct'
+        if self.kernel_path == 'tensor':
+            tensor = tab.tensor_capable
+        if not tensor:
+            kind = 'direct CUDA-core kernels'
+        elif tab.d == 64:
+            kind = 'split-fp16 tcgen05 forward kernel (column-tiled); gradient on the direct kernel'
+        elif tab.symmetric:
+            kind = ('split-fp16 tcgen05 kernels, ' +
+                    ('expanded-distance GEMM' if tab.expanded_ok else 'exact-distance mode (small temperature)'))
+        else:
+            kind = '3xTF32 tcgen05 kernels (non-symmetric tables)'
+        return {'loaded': True, 'device': str(self.centroids.device), 'latent_dim': tab.d, 'n_centroids': tab.K,
+                'symmetric_tables': tab.symmetric, 'tensor_path': bool(tensor), 'expanded_form_accurate': tab.expanded_ok,
+                'implementation': kind, 'kernel_path': self.kernel_path}
+
     def is_loaded(self) -> bool:
         return self._is_loaded
 

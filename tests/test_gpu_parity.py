@@ -255,6 +255,7 @@ def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
     mt = make_mt(t, 'auto')
     tab = mt._tables(dev())
     assert tab.tensor_auto and not tab.expanded_ok
+    assert 'exact-distance' in mt.kernel_info()['implementation']
     z = torch.cat([make_points(3000, 16, seed=1), sm.centroids[:1000] + 0.05 * make_points(1000, 16, seed=2)]).to(dev())
     a = make_mt(t, 'direct').evaluate(z, want_g=True, want_grad=True)
     b = mt.evaluate(z, want_g=True, want_grad=True)
