@@ -89,18 +89,63 @@ __global__ void pack_matrices_kernel(const float* __restrict__ m_in, int K, int 
   if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[3]), __float_as_int(amax));
 }
 
-// split-fp16 centroid rows for GEMM1 (d == 16): [Kpad, 64] fp16 = [fp16(2^ec c) (16) | residual (16) | 0 (32)]
-// (one 128-byte swizzle row per centroid, like cstack)
-__global__ void pack_c16h_kernel(const float* __restrict__ c, int K, int Kpad, float scale, __half* __restrict__ out) {
+// mean centroid (d == 16): the expanded distance form is evaluated about it (see pack_c16h_kernel)
+__global__ void centroid_mean_kernel(const float* __restrict__ c, int K, float* __restrict__ shift) {
+  __shared__ double part[256][17];
+  double acc[16];
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    for (int j = 0; j < 16; ++j) acc[j] += (double)c[(int64_t)k * 16 + j];
+  for (int j = 0; j < 16; ++j) part[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double tot = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) tot += part[i][threadIdx.x];
+    const float m = (float)(tot / (double)K);
+    shift[threadIdx.x] = isfinite(m) ? m : 0.f;
+  }
+}
+
+// split-fp16 centroid rows for GEMM1 (d == 16): [Kpad, 64] fp16 = [fp16(2^ec c~) (16) | residual (16) | 0 (32)]
+// (one 128-byte swizzle row per centroid, like cstack), with c~ = c - shift.  ||z-c||^2 is invariant
+// under a common translation, and the cancellation error of ||z~||^2+||c~||^2-2 z~.c~ scales with
+// ||c~||^2, so centring the table widens the range of temperatures the expanded form can serve.
+// bias_h[k] = -||c~_k||^2 log2(e)/T^2 (padding: -1e30); stats[5] accumulates sum ||c~||^2, [6] max |c~|.
+__global__ void pack_c16h_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K, int Kpad,
+                                 float scale, float inv_T2_log2e, __half* __restrict__ out,
+                                 float* __restrict__ bias_h, float* __restrict__ ctc_hi,
+                                 float* __restrict__ ctc_lo) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
+  float nrm = 0.f;
   for (int j = 0; j < 16; ++j) {
-    const float v = (k < K) ? scale * c[(int64_t)k * 16 + j] : 0.f;
+    const float cv = (k < K) ? c[(int64_t)k * 16 + j] - shift[j] : 0.f;
+    nrm = fmaf(cv, cv, nrm);
+    const float v = scale * cv;
     const __half h = __float2half_rn(v);
     out[(int64_t)k * 64 + j] = h;
     out[(int64_t)k * 64 + 16 + j] = __float2half_rn(v - __half2float(h));
+    const float thi = tf32_hi(cv);
+    ctc_hi[(int64_t)j * Kpad + k] = thi;
+    ctc_lo[(int64_t)j * Kpad + k] = cv - thi;
   }
   for (int j = 32; j < 64; ++j) out[(int64_t)k * 64 + j] = __float2half_rn(0.f);
+  bias_h[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
+}
+
+// sum and max over the centred centroids (for the accuracy gate and the fp16 scale)
+__global__ void centred_stats_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K,
+                                     float* __restrict__ out2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float nrm = 0.f, amax = 0.f;
+  for (int j = 0; j < 16; ++j) {
+    const float cv = c[(int64_t)k * 16 + j] - shift[j];
+    nrm = fmaf(cv, cv, nrm);
+    amax = fmaxf(amax, fabsf(cv));
+  }
+  if (isfinite(nrm)) atomicAdd(&out2[0], nrm);
+  if (isfinite(amax)) atomicMax(reinterpret_cast<int*>(&out2[1]), __float_as_int(amax));
 }
 
 // split-fp16 natural tables [Kpad, 192] (136 packed columns + zeros) for the gradient kernel
@@ -211,6 +256,11 @@ static void free_tables(rlvae_tables* t) {
   if (t->Mnh_lo) cudaFree(t->Mnh_lo);
   if (t->c64h) cudaFree(t->c64h);
   if (t->c16h) cudaFree(t->c16h);
+  if (t->cbias_h) cudaFree(t->cbias_h);
+  if (t->cshift) cudaFree(t->cshift);
+  if (t->ctc_hi) cudaFree(t->ctc_hi);
+  if (t->ctc_lo) cudaFree(t->ctc_lo);
+  t->cbias_h = t->cshift = t->ctc_hi = t->ctc_lo = nullptr;
   t->c64h = t->c16h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
@@ -356,24 +406,47 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           pack_sym_nat_h_kernel<<<592, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, e), static_cast<__half*>(t->Mnh_hi),
                                                     static_cast<__half*>(t->Mnh_lo));
           OK_OR_FAIL(cudaGetLastError());
-          // split-fp16 centroid rows for GEMM1: c' = 2^ec c with max|c'| in [2^13, 2^14)
-          int exc = 0;
-          frexpf(t->c_absmax > 0.f ? t->c_absmax : 1.f, &exc);
-          int ec = 14 - exc;
-          ec = ec > 50 ? 50 : (ec < -50 ? -50 : ec);
-          if (cudaMalloc(&t->c16h, sizeof(__half) * (size_t)Kpad * 64) != cudaSuccess) {
+          // split-fp16 centroid rows for GEMM1, centred on the mean centroid:
+          // c' = 2^ec (c - shift) with max|c'| in [2^13, 2^14)
+          if (cudaMalloc(&t->c16h, sizeof(__half) * (size_t)Kpad * 64) != cudaSuccess ||
+              cudaMalloc(&t->cbias_h, sizeof(float) * (size_t)Kpad) != cudaSuccess ||
+              cudaMalloc(&t->ctc_hi, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
+              cudaMalloc(&t->ctc_lo, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
+              cudaMalloc(&t->cshift, sizeof(float) * 18) != cudaSuccess) {
             set_error("tables_create: cudaMalloc (fp16 centroid rows) failed");
             return fail(1);
           }
-          pack_c16h_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, K, Kpad, ldexpf(1.f, ec),
-                                                              static_cast<__half*>(t->c16h));
+          OK_OR_FAIL(cudaMemsetAsync(t->cshift, 0, sizeof(float) * 18, s));
+          const char* ce = getenv("RLVAE_TC_CENTRE");   // "0": keep the table un-centred (A/B only)
+          if (ce == nullptr || ce[0] != '0') {
+            centroid_mean_kernel<<<1, 256, 0, s>>>(t->c, K, t->cshift);
+            OK_OR_FAIL(cudaGetLastError());
+          }
+          centred_stats_kernel<<<(K + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, t->cshift + 16);
+          OK_OR_FAIL(cudaGetLastError());
+          float h_cs[18];
+          OK_OR_FAIL(cudaMemcpyAsync(h_cs, t->cshift, sizeof(h_cs), cudaMemcpyDeviceToHost, s));
+          OK_OR_FAIL(cudaStreamSynchronize(s));
+          int exc = 0;
+          frexpf(h_cs[17] > 0.f ? h_cs[17] : 1.f, &exc);
+          int ec = 14 - exc;
+          ec = ec > 50 ? 50 : (ec < -50 ? -50 : ec);
+          pack_c16h_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, Kpad, ldexpf(1.f, ec), inv_T2_log2e,
+                                                              static_cast<__half*>(t->c16h), t->cbias_h, t->ctc_hi, t->ctc_lo);
           OK_OR_FAIL(cudaGetLastError());
           t->c16_unscale = ldexpf(1.f, -ec);
           OK_OR_FAIL(cudaStreamSynchronize(s));
+          {   // the gate of the expanded form now looks at the centred norms
+            const float r2c = h_cs[16] / (float)K;
+            const float relc = 2.5e-7f * fmaxf(r2c, 1.f) / t->T2;
+            t->expanded_ok = (relc < 2.0e-6f) ? 1 : 0;
+          }
           t->h16_out_scale = ldexpf(1.f, -(14 + e));
           t->h16_m_unscale = ldexpf(1.f, -e);
           t->tensor_auto = 1;    // the split-fp16 kernels have an exact-distance mode: no restriction on T
           rc = tc_build_h16_descriptors(t);
+          if (rc != 0) return fail(rc);
+          rc = tc_build_ct_centred_descriptors(t);
           if (rc != 0) return fail(rc);
         }
       }

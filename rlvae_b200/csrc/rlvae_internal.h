@@ -97,6 +97,10 @@ struct rlvae_tables {
   // Mh_hi / Mh_lo then hold the packed-transposed [2176, Kpad] tables
   void* c16h = nullptr;        // d == 16: [Kpad,64] fp16 = [hi (16) | lo (16) | 0] of 2^ec c (GEMM1 of the fp16 kernels)
   float c16_unscale = 0.f;     // 2^-ec
+  float* cshift = nullptr;     // d == 16: [16] mean centroid the fp16 GEMM1 operands are centred on (+2 scratch)
+  float* cbias_h = nullptr;    // [Kpad] -||c - shift||^2 * log2(e)/T^2 (padding rows: -1e30)
+  float* ctc_hi = nullptr;     // [16, Kpad] TF32 hi / lo of (c - shift)^T: B operand of the fp16 gradient
+  float* ctc_lo = nullptr;     //            kernel's final contraction (tm_ct16_*, tm_ct8_*)
   float c_absmax = 0.f;
   CUtensorMap tm_c16h;
   void* c64h = nullptr;
@@ -151,6 +155,7 @@ int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* 
 
 // tensor path (rlvae_tc.cu)
 int tc_build_descriptors(rlvae_tables* t);
+int tc_build_ct_centred_descriptors(rlvae_tables* t);
 int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
                              cudaStream_t s);
 // symmetric tables: packed [N,144] result (lambda already on the packed diagonal)

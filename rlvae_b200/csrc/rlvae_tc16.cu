@@ -172,7 +172,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const float* __restrict__ z, const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
                           const float* __restrict__ cnat /* EXACT: natural centroid rows [Kpad,16] */, int64_t n,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
-                          float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */, FusedOut fo) {
+                          float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */,
+                          const float* __restrict__ cshift /* [16] centre of the expanded form */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
@@ -260,12 +261,19 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nz[j] = make_float2(-zv[2 * j], -zv[2 * j + 1]);
+    if (!EXACT) {                    // the expanded form works on z~ = z - shift (tables hold c~ = c - shift)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+        zv[4 * q] -= sh.x; zv[4 * q + 1] -= sh.y; zv[4 * q + 2] -= sh.z; zv[4 * q + 3] -= sh.w;
+      }
+    }
     float nrm = 0.f, zmax = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) { nrm = fmaf(zv[j], zv[j], nrm); zmax = fmaxf(zmax, fabsf(zv[j])); }
     zb = EXACT ? P_SHIFT : (-nrm * alpha + P_SHIFT);     // P' = 2^14 P, folded into the exponent
-#pragma unroll
-    for (int j = 0; j < 8; ++j) nz[j] = make_float2(-zv[2 * j], -zv[2 * j + 1]);
     // GEMM1 on kind::f16: z' = 2^ez z (per point, max|z'| in [2^13, 2^14)), split hi + lo; S = 2^-(ez+ec) S'
     int ez = 0;
     if (zmax > 0.f && zmax < 3.0e38f) {
@@ -699,6 +707,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const float* __restrict__ cbias /* EXACT: 0 / -1e30 mask */,
                        const float* __restrict__ cnat /* EXACT: natural centroid rows */, int64_t n, int num_blocks,
                        float alpha, float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
+                       const float* __restrict__ cshift /* [16] centre of the expanded form */,
                        float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
   constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
@@ -792,19 +801,25 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     const int64_t r = row0 + prow;
     if (r < n) {
       const float4* src = reinterpret_cast<const float4*>(z + r * 16);
-      float nrm = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 v = __ldg(src + q);
         zrow[4 * q] = v.x; zrow[4 * q + 1] = v.y; zrow[4 * q + 2] = v.z; zrow[4 * q + 3] = v.w;
-        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
       }
-      zb = EXACT ? 0.f : -nrm * alpha;
     }
-    {   // GEMM1 on kind::f16: z' = 2^ez z (max|z'| in [2^13, 2^14)), split hi + lo; S = 2^-(ez+ec) S'
-      float zmax = 0.f;
+    if (!EXACT) {   // GEMM1 on kind::f16 about the table's centre: z~ = z - shift, z' = 2^ez z~ (max|z'| in
+                    // [2^13, 2^14)), split hi + lo; S = 2^-(ez+ec) S'
+      float zs[16];
+      float nrm = 0.f, zmax = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) zmax = fmaxf(zmax, fabsf(zrow[j]));
+      for (int q = 0; q < 4; ++q) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+        zs[4 * q] = zrow[4 * q] - sh.x; zs[4 * q + 1] = zrow[4 * q + 1] - sh.y;
+        zs[4 * q + 2] = zrow[4 * q + 2] - sh.z; zs[4 * q + 3] = zrow[4 * q + 3] - sh.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { nrm = fmaf(zs[j], zs[j], nrm); zmax = fmaxf(zmax, fabsf(zs[j])); }
+      zb = -nrm * alpha;
       int ez = 0;
       if (zmax > 0.f && zmax < 3.0e38f) {
         const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
@@ -812,11 +827,11 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
       }
       s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
-      if (grp == 0 && !EXACT) {
+      if (grp == 0) {
         const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
         uint32_t zh[8], zl[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split_pair(zrow[2 * j] * zsc, zrow[2 * j + 1] * zsc, zh[j], zl[j]);
+        for (int j = 0; j < 8; ++j) split_pair(zs[2 * j] * zsc, zs[2 * j + 1] * zsc, zh[j], zl[j]);
         TMEM_ST8(tmem_base + lane_addr + TM_ZHI, zh);
         TMEM_ST8(tmem_base + lane_addr + TM_ZLO, zl);
       }
@@ -1159,7 +1174,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float ge = tot[e] + red[prow * RED_LD + e];
-          o[e] = (ge - zrow[e] * su) * u_unscale * scale;
+          o[e] = (ge - (zrow[e] - __ldg(cshift + e)) * su) * u_unscale * scale;   // Ct holds c - shift
         }
         float4* dst = reinterpret_cast<float4*>(out + r * 16);
 #pragma unroll
@@ -1550,7 +1565,7 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float alpha = 1.4426950408889634f / t->T2;
-  const float* cbias = EXACT ? t->cmask : t->cbias;
+  const float* cbias = EXACT ? t->cmask : t->cbias_h;
   const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
   const float lambda = t->lambda;
@@ -1558,10 +1573,10 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   const float cu = t->c16_unscale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, fo));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, fo));
   }
   return 0;
 }
@@ -1629,17 +1644,17 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float alpha = 1.4426950408889634f / t->T2;
-  const float* cbias = EXACT ? t->cmask : t->cbias;
+  const float* cbias = EXACT ? t->cmask : t->cbias_h;
   const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   const float cu = t->c16_unscale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
-                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, out, u_packed));
+                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, out, u_packed));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
-                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, out, u_packed));
+                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, out, u_packed));
   }
   return 0;
 }

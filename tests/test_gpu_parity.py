@@ -268,6 +268,40 @@ def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
     assert rel_fro(b['ginv'][3000:3064].cpu(), ref) < TOL_MAT
 
 
+@pytest.mark.parametrize('temperature', [None, 0.7])
+def test_translated_tables(temperature):
+    """Translation invariance G^{-1}(z + o; c + o) = G^{-1}(z; c).  A latent cloud far from the origin
+    (||c||^2 ~ 6400 here) would fail the accuracy gate of ||z||^2+||c||^2-2 z.c, and its gradient
+    contraction sum_k coef_k c_k - z sum_k coef_k would cancel; the split-fp16 tables are centred on
+    the mean centroid, so the fast form keeps serving it (and the exact-distance mode at T = 0.7
+    keeps its gradient accuracy), matching the direct kernels on the same translated inputs."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(1500, 16, seed=21)
+    T = sm.temperature if temperature is None else temperature
+    z = make_points(1200, 16, seed=22)
+    if temperature is not None:
+        z = torch.cat([z[:600], sm.centroids[:600] + 0.05 * z[600:]])
+    base = make_mt((sm.centroids, sm.metric_matrices, T, sm.regularization), 'direct')
+    ref = base.evaluate(z.to(dev()), want_ginv=True, want_logdet=True, want_grad=True)
+    off = torch.linspace(-20.0, 20.0, 16)
+    off[off.abs() < 15] = 20.0
+    t = (sm.centroids + off, sm.metric_matrices, T, sm.regularization)
+    mt = make_mt(t, 'auto')
+    tab = mt._tables(dev())
+    assert tab.tensor_auto and bool(tab.expanded_ok) == (temperature is None)
+    assert ('exact-distance' in mt.kernel_info()['implementation']) == (temperature is not None)
+    zt = (z + off).to(dev())
+    ev = mt.evaluate(zt, want_ginv=True, want_logdet=True, want_grad=True)
+    same = make_mt(t, 'direct').evaluate(zt, want_ginv=True, want_logdet=True, want_grad=True)
+    assert rel_fro(ev['ginv'].cpu(), same['ginv'].cpu()) < TOL_MAT
+    close_ld(ev['logdet_g'].cpu(), same['logdet_g'].cpu())
+    gs = same['grad_logdet_g']
+    live = gs.norm(dim=1) > 1e-6 * gs.norm(dim=1).max()
+    assert rel_fro(ev['grad_logdet_g'][live].cpu(), gs[live].cpu()) < TOL_LD
+    # against the un-translated problem only the fp32 rounding of z + o and c + o remains
+    assert rel_fro(ev['ginv'].cpu(), ref['ginv'].cpu()) < (1e-4 if temperature is None else 1e-3)
+
+
 @pytest.mark.parametrize('sc,smul', [(1e-3, 1e-6), (1e3, 1e6), (37.0, 1e-3), (1.0, 3e4)])
 def test_scale_covariance_of_the_split_fp16_path(sc, smul):
     """G^{-1}(s z; s c, m M, s T, m lambda) = m G^{-1}(z; c, M, T, lambda): exercises the power-of-two
