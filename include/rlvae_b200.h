@@ -59,8 +59,10 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
 int rlvae_tables_destroy(rlvae_tables_t* t);
 /* info[0]=K, [1]=d, [2]=K padded, [3]=1 if every M_k is exactly symmetric,
  * [4]=1 if the tensor path exists for this d, [5]=1 if AUTO would pick the tensor path,
- * [6]=1 if the expanded-distance form is accurate enough for these tables (else the d = 16
- * symmetric kernels run in exact-distance mode; other tensor kernels are not used by AUTO) */
+ * [6]=1 if the expanded-distance form is accurate enough for these tables (other tensor kernels
+ * are not used by AUTO when it is not), [7]=how the d = 16 symmetric kernels form the weights:
+ * 0 expanded form, 1 exact differences, 2 hybrid (expanded form + exact refinement of the weights
+ * that can matter) */
 int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]);
 
 /* ---- A2: G^{-1}(z) = sum_k M_k exp(-||z-c_k||^2/T^2) + lambda I ------------------------------

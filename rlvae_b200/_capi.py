@@ -115,7 +115,8 @@ class Tables:
         _check(lib().rlvae_tables_info(self._h, info), 'rlvae_tables_info')
         self.Kpad, self.symmetric = int(info[2]), bool(info[3])
         self.tensor_capable, self.tensor_auto = bool(info[4]), bool(info[5])
-        self.expanded_ok = bool(info[6])     # False -> the d = 16 symmetric kernels run in exact-distance mode
+        self.expanded_ok = bool(info[6])     # accuracy gate of the expanded distance form
+        self.weight_mode = int(info[7])      # d = 16 symmetric: 0 expanded form, 1 exact differences, 2 hybrid
 
     @property
     def handle(self):

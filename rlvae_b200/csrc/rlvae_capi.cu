@@ -440,6 +440,16 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
             const float r2c = h_cs[16] / (float)K;
             const float relc = 2.5e-7f * fmaxf(r2c, 1.f) / t->T2;
             t->expanded_ok = (relc < 2.0e-6f) ? 1 : 0;
+            // Hybrid mode: the un-refined weights (each below 2^-bits, relative error relc) move G^{-1} by
+            // at most relc * K * 2^-bits * max||M_k||_F <= 1e-6 lambda, and G^{-1} >= lambda I.
+            const float mf = 16.f * t->m_absmax;
+            if (t->lambda > 0.f && isfinite(t->lambda) && mf > 0.f && isfinite(mf)) {
+              const float bits = log2f(relc * (float)K * mf / (1.0e-6f * t->lambda));
+              if (isfinite(bits) && bits < 48.f) {
+                t->hybrid_ok = 1;
+                t->hybrid_bits = fmaxf(bits, 8.f);
+              }
+            }
           }
           t->h16_out_scale = ldexpf(1.f, -(14 + e));
           t->h16_m_unscale = ldexpf(1.f, -e);
@@ -476,7 +486,8 @@ int rlvae_tables_destroy(rlvae_tables_t* t) {
 int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]) {
   RLVAE_REQUIRE(t != nullptr && info != nullptr, "tables_info: NULL argument");
   info[0] = t->K; info[1] = t->d; info[2] = t->Kpad; info[3] = t->symmetric;
-  info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = t->expanded_ok; info[7] = 0;
+  info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = t->expanded_ok;
+  info[7] = (t->d == 16 && t->symmetric && t->c16h != nullptr) ? h16_mode(t) : 0;
   return 0;
 }
 

@@ -97,6 +97,8 @@ struct rlvae_tables {
   // Mh_hi / Mh_lo then hold the packed-transposed [2176, Kpad] tables
   void* c16h = nullptr;        // d == 16: [Kpad,64] fp16 = [hi (16) | lo (16) | 0] of 2^ec c (GEMM1 of the fp16 kernels)
   float c16_unscale = 0.f;     // 2^-ec
+  int hybrid_ok = 0;           // d == 16 symmetric: the hybrid weight mode has a valid threshold
+  float hybrid_bits = 0.f;     //   weights below 2^-hybrid_bits cannot move G^{-1} by more than 1e-6 lambda
   float* cshift = nullptr;     // d == 16: [16] mean centroid the fp16 GEMM1 operands are centred on (+2 scratch)
   float* cbias_h = nullptr;    // [Kpad] -||c - shift||^2 * log2(e)/T^2 (padding rows: -1e30)
   float* ctc_hi = nullptr;     // [16, Kpad] TF32 hi / lo of (c - shift)^T: B operand of the fp16 gradient
@@ -134,6 +136,7 @@ int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, flo
                           float* g_full = nullptr);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
 int tc_build_h16_descriptors(rlvae_tables* t);
+int h16_mode(const rlvae_tables* t);   // 0 expanded, 1 exact differences, 2 hybrid
 // d == 64 (symmetric tables): tables + forward through a packed [N,2176] scratch
 int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s);
 int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, float* ginv, float* packed_scratch,

@@ -164,7 +164,11 @@ struct FusedOut {
 // expanded form on the tensor core.  No GEMM1, no accuracy gate on T: this is the mode for small
 // temperatures (the reference's T = 0.7 configuration), ~28 instead of ~7 instructions per
 // (point, centroid) in the exp stage, which then bounds the kernel instead of the tensor pipe.
-template <bool PAIR, bool EXACT>
+// HYBRID (only with !EXACT): the expanded form runs as usual, and every weight whose exponent is above
+// hyb_thr -- the only ones large enough for the expanded form's absolute exponent error to matter in
+// G^{-1} (see h16_mode) -- is recomputed from exact differences (natural centroid rows through L1).  At
+// small T almost every weight is far below the threshold, so this keeps most of the tensor-core speed.
+template <bool PAIR, bool EXACT, bool HYBRID>
 __global__ void __launch_bounds__(h16::THREADS, 1)
 inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const __grid_constant__ CUtensorMap tm_mh_hi,
@@ -173,7 +177,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const float* __restrict__ cnat /* EXACT: natural centroid rows [Kpad,16] */, int64_t n,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
                           float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */,
-                          const float* __restrict__ cshift /* [16] centre of the expanded form */, FusedOut fo) {
+                          const float* __restrict__ cshift /* [16] centre of the expanded form */,
+                          float hyb_thr /* HYBRID: refine weights with log2(2^14 w) above this */, FusedOut fo) {
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
@@ -471,15 +476,40 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           uint32_t s[32];
           TMEM_LD32(sp + rnd * 32, s);
           tmem_wait_ld();
+          if (HYBRID) {
+            uint32_t live = 0;             // weights of this thread that need exact differences
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bv = bias4[q];
-            const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), s_scale, bv.x + zb));
-            const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), s_scale, bv.y + zb));
-            const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), s_scale, bv.z + zb));
-            const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), s_scale, bv.w + zb));
-            split_pair(w0, w1, ph[2 * q], pl[2 * q]);
-            split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+            for (int q = 0; q < 8; ++q) {
+              const float4 bv = bias4[q];
+              const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * q + e;
+                const float ex = fmaf(__uint_as_float(s[i]), s_scale, b4[e] + zb);
+                s[i] = __float_as_uint(ex);
+                live |= (ex > hyb_thr ? 1u : 0u) << i;
+              }
+            }
+            refine_exponents(s, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
+                             -alpha, P_SHIFT);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float w0 = ex2_approx(__uint_as_float(s[4 * q])), w1 = ex2_approx(__uint_as_float(s[4 * q + 1]));
+              const float w2 = ex2_approx(__uint_as_float(s[4 * q + 2])), w3 = ex2_approx(__uint_as_float(s[4 * q + 3]));
+              split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+              split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 bv = bias4[q];
+              const float w0 = ex2_approx(fmaf(__uint_as_float(s[4 * q]), s_scale, bv.x + zb));
+              const float w1 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 1]), s_scale, bv.y + zb));
+              const float w2 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 2]), s_scale, bv.z + zb));
+              const float w3 = ex2_approx(fmaf(__uint_as_float(s[4 * q + 3]), s_scale, bv.w + zb));
+              split_pair(w0, w1, ph[2 * q], pl[2 * q]);
+              split_pair(w2, w3, ph[2 * q + 1], pl[2 * q + 1]);
+            }
           }
         }
         TMEM_ST16(sp + rnd * 32, ph);
@@ -696,7 +726,8 @@ __device__ __forceinline__ void split_pair_scaled(float even, float odd, float s
 }
 
 // EXACT: weights from exact differences on the FMA pipe (see inverse_metric_h16_kernel); no GEMM1.
-template <bool PAIR, bool EXACT>
+// HYBRID: as in the forward kernel -- weights above hyb_thr are recomputed from exact differences.
+template <bool PAIR, bool EXACT, bool HYBRID>
 __global__ void __launch_bounds__(g16::THREADS, 1)
 metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const __grid_constant__ CUtensorMap tm_mn_hi,
@@ -708,6 +739,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        const float* __restrict__ cnat /* EXACT: natural centroid rows */, int64_t n, int num_blocks,
                        float alpha, float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
                        const float* __restrict__ cshift /* [16] centre of the expanded form */,
+                       float hyb_thr /* HYBRID: refine weights with log2 w above this */,
                        float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
   constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
@@ -1114,20 +1146,46 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         const float4* crow = reinterpret_cast<const float4*>(gbase + OFF_C + cs * C_TILE_BYTES) + rnd * 32 * 4;
         (void)crow;
         tmem_wait_ld();
+        if (HYBRID) {
+          uint32_t live = 0;               // weights of this thread that need exact differences
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bv = bias4[q];
-          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = bias4[q];
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 4 * q + e;
-            const float w = EXACT ? ex2_approx(fmaf(dist2_row16(crow + i * 4, nz), -alpha, b4[e]))
-                                  : ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
-            const float uv = w * __uint_as_float(tv[i]);
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q + e;
+              const float ex = fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb);
+              live |= (ex > hyb_thr ? 1u : 0u) << i;
+              sv[i] = __float_as_uint(ex);
+            }
+          }
+          refine_exponents(sv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
+                           -alpha, 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
             su_blk += uv;
             const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
             sv[i] = uh;
             tv[i] = __float_as_uint(uv - __uint_as_float(uh));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = bias4[q];
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q + e;
+              const float w = EXACT ? ex2_approx(fmaf(dist2_row16(crow + i * 4, nz), -alpha, b4[e]))
+                                    : ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
+              const float uv = w * __uint_as_float(tv[i]);
+              su_blk += uv;
+              const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
+              sv[i] = uh;
+              tv[i] = __float_as_uint(uv - __uint_as_float(uh));
+            }
           }
         }
         TMEM_ST32(st + rnd * 32, sv);
@@ -1541,9 +1599,9 @@ static bool h16_use_pairs() {
   return v == 1;
 }
 
-template <bool PAIR, bool EXACT>
+template <bool PAIR, bool EXACT, bool HYBRID = false>
 static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s) {
-  auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT>;
+  auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT, HYBRID>;
   static bool attr_set = false;
   if (!attr_set) {
     RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1573,23 +1631,27 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   const float cu = t->c16_unscale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, t->cshift, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, t->cshift, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo));
   }
   return 0;
 }
 
-// exact-distance mode: whenever the expanded form would be too inaccurate for these tables (small T),
-// or on request (RLVAE_TC_EXACT=1)
-static bool h16_exact(const rlvae_tables* t) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("RLVAE_TC_EXACT");
-    forced = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return forced == 1 || !t->expanded_ok;
+// How the weights are formed (d == 16, symmetric tables):
+//   0  expanded form on the tensor core              -- when its accuracy gate passes (expanded_ok)
+//   2  hybrid: expanded form + exact refinement of   -- small T with lambda > 0: only weights above
+//      the weights that matter                          2^-hybrid_bits can move G^{-1} by more than 1e-6 lambda
+//   1  exact differences on the FMA pipe             -- everything else, or RLVAE_TC_EXACT=1
+// RLVAE_TC_EXACT=2 forces the hybrid mode where its threshold exists.
+int h16_mode(const rlvae_tables* t) {
+  const char* e = getenv("RLVAE_TC_EXACT");       // read per call: the tests switch modes within one process
+  const int forced = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+  if (forced == 1) return 1;
+  if (forced == 2 && t->hybrid_ok) return 2;
+  if (t->expanded_ok) return 0;
+  return t->hybrid_ok ? 2 : 1;
 }
 
 // Symmetric tables, d == 16: any of { packed G^{-1}, packed G, lad_scale * log|det G^{-1}|, sign,
@@ -1611,7 +1673,9 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   RLVAE_REQUIRE(g_full == nullptr || (reinterpret_cast<uintptr_t>(g_full) & 15) == 0, "G output must be 16-byte aligned");
   tc::FusedOut fo{a_full, a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
   int rc;
-  if (h16_exact(t)) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
+  const int mode = h16_mode(t);
+  if (mode == 1) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
+  else if (mode == 2) rc = h16_use_pairs() ? launch_h16<true, false, true>(t, z, n, fo, s) : launch_h16<false, false, true>(t, z, n, fo, s);
   else rc = h16_use_pairs() ? launch_h16<true, false>(t, z, n, fo, s) : launch_h16<false, false>(t, z, n, fo, s);
   if (rc) return rc;
   RLVAE_REQUIRE(g_full == nullptr || g_packed != nullptr, "the expanded G output needs the packed G buffer too");
@@ -1619,10 +1683,10 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   return 0;
 }
 
-template <bool PAIR, bool EXACT>
+template <bool PAIR, bool EXACT, bool HYBRID = false>
 static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
                       cudaStream_t s, int u_packed) {
-  auto kern = tc::metric_grad_h16_kernel<PAIR, EXACT>;
+  auto kern = tc::metric_grad_h16_kernel<PAIR, EXACT, HYBRID>;
   static bool attr_set = false;
   if (!attr_set) {
     RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1651,10 +1715,10 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const float cu = t->c16_unscale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
-                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, out, u_packed));
+                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
-                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, out, u_packed));
+                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   }
   return 0;
 }
@@ -1668,9 +1732,13 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
                 "split-fp16 gradient path needs latent_dim == 16 and symmetric tables");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
-  if (h16_exact(t))
+  const int mode = h16_mode(t);
+  if (mode == 1)
     return h16_use_pairs() ? launch_g16<true, true>(t, z, u, n, scale, out, s, u_packed)
                            : launch_g16<false, true>(t, z, u, n, scale, out, s, u_packed);
+  if (mode == 2)
+    return h16_use_pairs() ? launch_g16<true, false, true>(t, z, u, n, scale, out, s, u_packed)
+                           : launch_g16<false, false, true>(t, z, u, n, scale, out, s, u_packed);
   return h16_use_pairs() ? launch_g16<true, false>(t, z, u, n, scale, out, s, u_packed)
                          : launch_g16<false, false>(t, z, u, n, scale, out, s, u_packed);
 }

@@ -372,6 +372,49 @@ __device__ __forceinline__ float dist2_row16(const float4* __restrict__ crow, co
   return acc.x + acc.y;
 }
 
+// the same from global memory (read-only path; every lane of a warp asks for the same row)
+__device__ __forceinline__ float dist2_row16_ldg(const float4* __restrict__ crow, const float2 (&nz)[8]) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 c = __ldg(crow + q);
+    const float2 d0 = fadd2(make_float2(c.x, c.y), nz[2 * q]);
+    const float2 d1 = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
+    ffma2_acc(acc, d0, d0);
+    ffma2_acc(acc, d1, d1);
+  }
+  return acc.x + acc.y;
+}
+
+// HYBRID weight mode: ex[i] (i < 32, float bits) are this thread's exponents for 32 consecutive
+// centroids from the expanded form; the ones flagged in `live` are replaced by
+// neg_alpha * ||z - c_i||^2 + shift from exact differences.  Must be called by the whole warp.
+// Sparse case (the usual one at small T): every lane works on its own flagged centroid at the same
+// time, so a round costs one distance however many lanes need one.  Dense case: a uniform sweep with
+// broadcast loads, like the exact mode.
+__device__ __forceinline__ void refine_exponents(uint32_t (&ex)[32], uint32_t live, const float4* __restrict__ crows,
+                                                 const float2 (&nz)[8], float neg_alpha, float shift) {
+  if (!__any_sync(0xffffffffu, live != 0u)) return;
+  const int total = __reduce_add_sync(0xffffffffu, __popc(live));
+  if (total > 160) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = fmaf(dist2_row16_ldg(crows + i * 4, nz), neg_alpha, shift);
+      if ((live >> i) & 1u) ex[i] = __float_as_uint(v);
+    }
+    return;
+  }
+  while (__any_sync(0xffffffffu, live != 0u)) {
+    if (live != 0u) {
+      const int b = __ffs(live) - 1;
+      live &= live - 1u;
+      const uint32_t v = __float_as_uint(fmaf(dist2_row16_ldg(crows + b * 4, nz), neg_alpha, shift));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ex[i] = (i == b) ? v : ex[i];
+    }
+  }
+}
+
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 

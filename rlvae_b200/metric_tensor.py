@@ -298,7 +298,8 @@ class MetricTensor(nn.Module):
             kind = 'split-fp16 tcgen05 forward kernel (column-tiled); gradient on the direct kernel'
         elif tab.symmetric:
             kind = ('split-fp16 tcgen05 kernels, ' +
-                    ('expanded-distance GEMM' if tab.expanded_ok else 'exact-distance mode (small temperature)'))
+                    ('expanded-distance GEMM', 'exact-distance mode (small temperature)',
+                     'hybrid mode (small temperature: expanded-distance GEMM + exact refinement of the live weights)')[tab.weight_mode])
         else:
             kind = '3xTF32 tcgen05 kernels (non-symmetric tables)'
         return {'loaded': True, 'device': str(self.centroids.device), 'latent_dim': tab.d, 'n_centroids': tab.K,

@@ -245,17 +245,23 @@ def test_nearest2_tensor_prefilter_is_exact_at_k10k():
         assert torch.equal(i2, idx[:n]) and torch.equal(d2, dist[:n])
 
 
-def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
+@pytest.mark.parametrize('mode', ['auto', 'exact', 'hybrid'])
+def test_small_temperature_runs_on_the_tensor_path(mode, monkeypatch):
     """The reference's own configuration T = 0.7 (conf/model/hybrid_rlvae.yaml:41) at config size: the
-    expanded-distance form is too inaccurate there, so the d = 16 symmetric kernels switch to exact
-    differences on the FMA pipe (weighted sum and gradient contraction stay on the tensor core)."""
+    expanded-distance form alone is too inaccurate there, so the d = 16 symmetric kernels either refine
+    the weights that matter from exact differences (hybrid mode, the default when lambda > 0) or form
+    every distance by exact differences on the FMA pipe (exact mode); the weighted sum and the gradient
+    contraction stay on the tensor core."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    if mode != 'auto':
+        monkeypatch.setenv('RLVAE_TC_EXACT', {'exact': '1', 'hybrid': '2'}[mode])
     sm = make_synthetic_metric(10000, 16, seed=0)
     t = (sm.centroids, sm.metric_matrices, 0.7, sm.regularization)
     mt = make_mt(t, 'auto')
     tab = mt._tables(dev())
     assert tab.tensor_auto and not tab.expanded_ok
-    assert 'exact-distance' in mt.kernel_info()['implementation']
+    assert tab.weight_mode == {'auto': 2, 'exact': 1, 'hybrid': 2}[mode]
+    assert ('exact-distance' if tab.weight_mode == 1 else 'hybrid') in mt.kernel_info()['implementation']
     z = torch.cat([make_points(3000, 16, seed=1), sm.centroids[:1000] + 0.05 * make_points(1000, 16, seed=2)]).to(dev())
     a = make_mt(t, 'direct').evaluate(z, want_g=True, want_grad=True)
     b = mt.evaluate(z, want_g=True, want_grad=True)
@@ -266,6 +272,14 @@ def test_small_temperature_runs_on_the_tensor_path_in_exact_distance_mode():
     assert rel_fro(b['grad_logdet_g'][live].cpu(), a['grad_logdet_g'][live].cpu()) < TOL_LD
     ref = O.chunked(O.inverse_metric, z[3000:3064].cpu(), *t, chunk=32)
     assert rel_fro(b['ginv'][3000:3064].cpu(), ref) < TOL_MAT
+
+
+def test_hybrid_mode_needs_a_regularisation_floor():
+    """Without lambda > 0 there is no absolute scale to neglect small weights against: exact mode."""
+    from rlvae_b200.synthetic import make_synthetic_metric
+    sm = make_synthetic_metric(300, 16, seed=3)
+    mt = make_mt((sm.centroids, sm.metric_matrices, 0.5, 0.0), 'auto')
+    assert mt._tables(dev()).weight_mode == 1
 
 
 @pytest.mark.parametrize('temperature', [None, 0.7])
@@ -289,7 +303,7 @@ def test_translated_tables(temperature):
     mt = make_mt(t, 'auto')
     tab = mt._tables(dev())
     assert tab.tensor_auto and bool(tab.expanded_ok) == (temperature is None)
-    assert ('exact-distance' in mt.kernel_info()['implementation']) == (temperature is not None)
+    assert (tab.weight_mode != 0) == (temperature is not None)
     zt = (z + off).to(dev())
     ev = mt.evaluate(zt, want_ginv=True, want_logdet=True, want_grad=True)
     same = make_mt(t, 'direct').evaluate(zt, want_ginv=True, want_logdet=True, want_grad=True)
