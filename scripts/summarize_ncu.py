@@ -36,7 +36,8 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum', 'launch__shared_mem_per_block_dynamic']
-idx = [(w, names.index(w)) for w in want if w in names]
+idx = [(w, [k for k, nm in enumerate(names) if nm == w or nm.endswith('.' + w)][0]) for w in want
+       if any(nm == w or nm.endswith('.' + w) for nm in names)]
 with open(prefix + '_kernels.md', 'w') as f:
     for row in rr[2:]:
         f.write('\n'.join(f'- {w}: {row[i]} {units[i]}' for w, i in idx) + '\n\n')
