@@ -705,6 +705,7 @@ constexpr int THREADS = 384;        // TMA warp (C), MMA warp, 2 exp groups of 4
 constexpr int C_STAGES = 4;
 constexpr int M_STAGES = 2;                          // one stage = hi AND lo tile of a super-block
 constexpr int KSTEPS = 9;                           // 144 packed columns / 16
+constexpr bool COLSPLIT = true;                     // exp groups split every super-block by columns (see the exp loop)
 constexpr uint32_t CT_TILE_BYTES = 2 * 16 * 128;    // [16 rows (c^T) x 64 centroids] fp32 = 2 atoms of 32 centroids
 constexpr uint32_t M_HALF_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
 constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;
@@ -742,6 +743,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                        float hyb_thr /* HYBRID: refine weights with log2 w above this */,
                        float* __restrict__ out, int u_packed) {
   constexpr int C_STAGES = g16::C_STAGES, M_STAGES = g16::M_STAGES, RED_LD = g16::RED_LD, KSTEPS = g16::KSTEPS;
+  constexpr bool COLSPLIT = g16::COLSPLIT;
   constexpr uint32_t CT_TILE_BYTES = g16::CT_TILE_BYTES, M_TILE_BYTES = g16::M_TILE_BYTES,
                      M_HALF_BYTES = g16::M_HALF_BYTES, OFF_C = g16::OFF_C,
                      OFF_CT = g16::OFF_CT, OFF_M = g16::OFF_M, OFF_BIAS = g16::OFF_BIAS,
@@ -787,12 +789,12 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) {
-      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_B_FULL(s), 1);
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), COLSPLIT ? 8 : 4); mbar_init(BAR_B_FULL(s), 1);
       mbar_init(BAR_CT_FULL(s), 1); mbar_init(BAR_CT_EMPTY(s), 1);
     }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), 4 * NPAIR);
+      mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), (COLSPLIT ? 8 : 4) * NPAIR);
       mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
     }
     mbar_init(BAR_DONE, 1);
@@ -1128,7 +1130,10 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     int next_chunk = grp;                // chunks c with (c & 1) == grp belong to this group
     long long pe_wait = 0, pe_work = 0, pe_fold = 0;
     (void)pe_wait; (void)pe_work; (void)pe_fold;
-    for (int j = grp; j < num_blocks; j += 2) {
+    // COLSPLIT: both groups work on EVERY super-block, 32 centroids each, instead of alternating whole
+    // super-blocks.  The tensor pipe runs in order (T(j+1), GEMM3(j), T(j+2), ...), so u(j) has to be
+    // ready within the ~960 cycles of T(j+1): halving the exp latency per super-block removes that stall.
+    for (int j = COLSPLIT ? 0 : grp; j < num_blocks; j += COLSPLIT ? 1 : 2) {
       PROF_T0();
       const int cs = j % C_STAGES, sb = j & 1;
       const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
@@ -1138,7 +1143,8 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       PROF_ADD(pe_wait);
       float su_blk = 0.f;                // sum of u over this super-block (two-level fp32 summation)
 #pragma unroll
-      for (int rnd = 0; rnd < 2; ++rnd) {
+      for (int rr = 0; rr < (COLSPLIT ? 1 : 2); ++rr) {
+        const int rnd = COLSPLIT ? grp : rr;
         uint32_t sv[32], tv[32];
         if (!EXACT) TMEM_LD32(st + rnd * 32, sv);
         TMEM_LD32(st + 64 + rnd * 32, tv);
