@@ -133,6 +133,19 @@ __global__ void pack_c16h_kernel(const float* __restrict__ c, const float* __res
   bias_h[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
 }
 
+// sum_k ||M_k||_F into out[0] (bound on what the un-refined weights of the hybrid mode can add up to)
+__global__ void matrix_norm_sum_kernel(const float* __restrict__ M, int K, int dd, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float nrm = 0.f;
+  if (k < K) {
+    float s = 0.f;
+    for (int i = 0; i < dd; ++i) { const float v = M[(int64_t)k * dd + i]; s = fmaf(v, v, s); }
+    nrm = sqrtf(s);
+  }
+  for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+  if ((threadIdx.x & 31) == 0 && isfinite(nrm)) atomicAdd(out, nrm);
+}
+
 // sum and max over the centred centroids (for the accuracy gate and the fp16 scale)
 __global__ void centred_stats_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K,
                                      float* __restrict__ out2) {
@@ -412,11 +425,11 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
               cudaMalloc(&t->cbias_h, sizeof(float) * (size_t)Kpad) != cudaSuccess ||
               cudaMalloc(&t->ctc_hi, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
               cudaMalloc(&t->ctc_lo, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
-              cudaMalloc(&t->cshift, sizeof(float) * 18) != cudaSuccess) {
+              cudaMalloc(&t->cshift, sizeof(float) * 20) != cudaSuccess) {
             set_error("tables_create: cudaMalloc (fp16 centroid rows) failed");
             return fail(1);
           }
-          OK_OR_FAIL(cudaMemsetAsync(t->cshift, 0, sizeof(float) * 18, s));
+          OK_OR_FAIL(cudaMemsetAsync(t->cshift, 0, sizeof(float) * 20, s));
           const char* ce = getenv("RLVAE_TC_CENTRE");   // "0": keep the table un-centred (A/B only)
           if (ce == nullptr || ce[0] != '0') {
             centroid_mean_kernel<<<1, 256, 0, s>>>(t->c, K, t->cshift);
@@ -424,7 +437,9 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           }
           centred_stats_kernel<<<(K + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, t->cshift + 16);
           OK_OR_FAIL(cudaGetLastError());
-          float h_cs[18];
+          matrix_norm_sum_kernel<<<(K + 127) / 128, 128, 0, s>>>(t->M, K, dd, t->cshift + 18);
+          OK_OR_FAIL(cudaGetLastError());
+          float h_cs[20];
           OK_OR_FAIL(cudaMemcpyAsync(h_cs, t->cshift, sizeof(h_cs), cudaMemcpyDeviceToHost, s));
           OK_OR_FAIL(cudaStreamSynchronize(s));
           int exc = 0;
@@ -441,10 +456,10 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
             const float relc = 2.5e-7f * fmaxf(r2c, 1.f) / t->T2;
             t->expanded_ok = (relc < 2.0e-6f) ? 1 : 0;
             // Hybrid mode: the un-refined weights (each below 2^-bits, relative error relc) move G^{-1} by
-            // at most relc * K * 2^-bits * max||M_k||_F <= 1e-6 lambda, and G^{-1} >= lambda I.
-            const float mf = 16.f * t->m_absmax;
+            // at most relc * 2^-bits * sum_k ||M_k||_F <= 1e-6 lambda, and G^{-1} >= lambda I.
+            const float mf = h_cs[18];
             if (t->lambda > 0.f && isfinite(t->lambda) && mf > 0.f && isfinite(mf)) {
-              const float bits = log2f(relc * (float)K * mf / (1.0e-6f * t->lambda));
+              const float bits = log2f(relc * mf / (1.0e-6f * t->lambda));
               if (isfinite(bits) && bits < 48.f) {
                 t->hybrid_ok = 1;
                 t->hybrid_bits = fmaxf(bits, 8.f);

@@ -64,6 +64,8 @@ constexpr int C_STAGES = 3;
 constexpr int SP_BUFS = 3;
 constexpr int M_STAGES = 3;                             // one stage = the hi AND the lo tile of a super-block
 constexpr int AHEAD = 3;
+constexpr bool COLSPLIT = false;                         // exp groups split every super-block by columns: measured slower here
+                                                         // (7.31 vs 6.75 ms; three S|P buffers already hide the exp latency)
 constexpr int NCOLS = 144;                               // packed columns = MMA N of GEMM2
 constexpr uint32_t M_HALF_BYTES = NCOLS * 128;           // [144 rows x 64 centroids] fp16 (pair: 72 rows used)
 constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;      // hi tile, then lo tile
@@ -182,6 +184,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
+  constexpr bool COLSPLIT = h16::COLSPLIT;
   constexpr uint32_t M_TILE_BYTES = h16::M_TILE_BYTES, M_HALF_BYTES = h16::M_HALF_BYTES, TM_SP = h16::TM_SP,
                      TM_ACC = h16::TM_ACC, TM_ZHI = h16::TM_ZHI, TM_ZLO = h16::TM_ZLO;
   constexpr float P_SHIFT = h16::P_SHIFT;
@@ -220,9 +223,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) {
-      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 4); mbar_init(BAR_BIAS_FULL(s), 1);
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), COLSPLIT ? 8 : 4); mbar_init(BAR_BIAS_FULL(s), 1);
     }
-    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), 4 * NPAIR); }
+    for (int s = 0; s < SP_BUFS; ++s) { mbar_init(BAR_S_FULL(s), 1); mbar_init(BAR_P_FULL(s), (COLSPLIT ? 8 : 4) * NPAIR); }
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR); }
     for (int b = 0; b < 3; ++b) mbar_init(BAR_MON(b), 1);
@@ -447,7 +450,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     long long pe_wait = 0, pe_work = 0;
     (void)pe_wait; (void)pe_work;
-    for (int j = grp; j < num_blocks; j += 2) {
+    // COLSPLIT: both groups work on every super-block, 32 centroids each (halves the latency between
+    // GEMM1(j) and GEMM2(j)); otherwise the groups alternate whole super-blocks
+    for (int j = COLSPLIT ? 0 : grp; j < num_blocks; j += COLSPLIT ? 1 : 2) {
       PROF_T0();
       const int cs = j % C_STAGES, sb = j % SP_BUFS;
       const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 64;
@@ -457,7 +462,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       if (quarter == 0) HTRACE(3, j);
       PROF_ADD(pe_wait);
 #pragma unroll
-      for (int rnd = 0; rnd < 2; ++rnd) {
+      for (int rr = 0; rr < (COLSPLIT ? 1 : 2); ++rr) {
+        const int rnd = COLSPLIT ? grp : rr;
         uint32_t ph[16], pl[16];
         const float4* bias4 = reinterpret_cast<const float4*>(gbase + h16::OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
         if (EXACT) {
