@@ -482,7 +482,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
     if (rc != 0) return fail(rc);
     if (t->c64h != nullptr) {
       t->tensor_capable = 1;
-      const float rel = 2.5e-7f * fmaxf(r2mean, 1.f) / t->T2;
+      const float rel = 2.5e-7f * fmaxf(t->r2mean_centred, 1.f) / t->T2;     // centred table, as for d = 16
       t->expanded_ok = (rel < 2.0e-6f) ? 1 : 0;
       t->tensor_auto = t->expanded_ok;
     }

@@ -99,7 +99,7 @@ struct rlvae_tables {
   float c16_unscale = 0.f;     // 2^-ec
   int hybrid_ok = 0;           // d == 16 symmetric: the hybrid weight mode has a valid threshold
   float hybrid_bits = 0.f;     //   weights below 2^-hybrid_bits cannot move G^{-1} by more than 1e-6 lambda
-  float* cshift = nullptr;     // d == 16: [16] mean centroid the fp16 GEMM1 operands are centred on (+4 scratch)
+  float* cshift = nullptr;     // [d] mean centroid the fp16 GEMM1 operands are centred on (+ scratch; d == 16 or 64)
   float* cbias_h = nullptr;    // [Kpad] -||c - shift||^2 * log2(e)/T^2 (padding rows: -1e30)
   float* ctc_hi = nullptr;     // [16, Kpad] TF32 hi / lo of (c - shift)^T: B operand of the fp16 gradient
   float* ctc_lo = nullptr;     //            kernel's final contraction (tm_ct16_*, tm_ct8_*)
@@ -107,6 +107,7 @@ struct rlvae_tables {
   CUtensorMap tm_c16h;
   void* c64h = nullptr;
   float c64_unscale = 0.f;     // 2^-ec
+  float r2mean_centred = 0.f;  // mean ||c - cshift||^2 (d == 64: set by tc_build_h64_tables)
   CUtensorMap tm_c64, tm_c64_2;   // boxes of 32 centroids x 32 (pair: 16) rows
 };
 

@@ -62,7 +62,8 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
                           const __grid_constant__ CUtensorMap tm_mh_lo,
                           const float* __restrict__ z, const float* __restrict__ cbias, int64_t n,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float c_unscale /* 2^-ec */,
-                          float out_scale /* 2^-(14+e) */, float* __restrict__ out /* [N, 2176] */) {
+                          float out_scale /* 2^-(14+e) */, const float* __restrict__ cshift /* [64] table centre */,
+                          float* __restrict__ out /* [N, 2176] */) {
   constexpr int C_STAGES = h64::C_STAGES, SP_BUFS = h64::SP_BUFS, M_STAGES = h64::M_STAGES, AHEAD = h64::AHEAD,
                 NT = h64::NT, OUT_LD = h64::OUT_LD, D = h64::D;
   constexpr uint32_t M_TILE_BYTES = h64::M_TILE_BYTES, M_HALF_BYTES = h64::M_HALF_BYTES, C_TILE64 = h64::C_TILE64,
@@ -141,7 +142,9 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
       const float4* src = reinterpret_cast<const float4*>(z + r * D);
 #pragma unroll 4
       for (int q = 0; q < D / 4; ++q) {
-        const float4 v = __ldg(src + q);
+        float4 v = __ldg(src + q);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);   // expanded form about the table centre
+        v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
         nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
         zmax = fmaxf(zmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
       }
@@ -162,7 +165,12 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
       const float4* src = reinterpret_cast<const float4*>(z + r * D);
 #pragma unroll
       for (int q = 0; q < D / 4; ++q) {
-        const float4 v = (r < n) ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) {
+          v = __ldg(src + q);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+          v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
+        }
         split_pair(v.x * zsc, v.y * zsc, hi[2 * q], lo[2 * q]);
         split_pair(v.z * zsc, v.w * zsc, hi[2 * q + 1], lo[2 * q + 1]);
       }
@@ -393,13 +401,42 @@ __host__ __device__ constexpr int sym64_index(int i, int j) {   // i <= j
 }
 
 // [Kpad, 128] fp16: row k = [fp16(2^ec c_k) (64) | fp16(2^ec c_k - hi) (64)], plus the exp2 bias
-__global__ void pack_c64_kernel(const float* __restrict__ c, int K, int Kpad, float scale, float inv_T2_log2e,
-                                __half* __restrict__ c64, float* __restrict__ cbias) {
+// mean centroid [64] (the expanded distance form is evaluated about it, as for d = 16)
+__global__ void centroid_mean64_kernel(const float* __restrict__ c, int K, float* __restrict__ shift) {
+  __shared__ double part[4][64];
+  const int j = threadIdx.x & 63, slice = threadIdx.x >> 6;       // 256 threads: 4 slices of the K range
+  double acc = 0.0;
+  for (int k = slice; k < K; k += 4) acc += (double)c[(int64_t)k * 64 + j];
+  part[slice][j] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    const float m = (float)((part[0][j] + part[1][j] + part[2][j] + part[3][j]) / (double)K);
+    shift[j] = isfinite(m) ? m : 0.f;
+  }
+}
+
+// stats[0] += sum_k ||c_k - shift||^2, stats[1] = max |c - shift|
+__global__ void centred_stats64_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K,
+                                       float* __restrict__ stats) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float nrm = 0.f, amax = 0.f;
+  for (int j = 0; j < 64; ++j) {
+    const float v = c[(int64_t)k * 64 + j] - shift[j];
+    nrm = fmaf(v, v, nrm);
+    amax = fmaxf(amax, fabsf(v));
+  }
+  if (isfinite(nrm)) atomicAdd(&stats[0], nrm);
+  if (isfinite(amax)) atomicMax(reinterpret_cast<int*>(&stats[1]), __float_as_int(amax));
+}
+
+__global__ void pack_c64_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K, int Kpad,
+                                float scale, float inv_T2_log2e, __half* __restrict__ c64, float* __restrict__ cbias) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   float nrm = 0.f;
   for (int j = 0; j < 64; ++j) {
-    const float v = (k < K) ? c[(int64_t)k * 64 + j] : 0.f;
+    const float v = (k < K) ? c[(int64_t)k * 64 + j] - shift[j] : 0.f;
     nrm = fmaf(v, v, nrm);
     const float sv = v * scale;
     const __half h = __float2half_rn(sv);
@@ -427,13 +464,6 @@ __global__ void pack_sym64_h_kernel(const float* __restrict__ M, int Kpad, float
     hi_t[idx] = h;
     lo_t[idx] = __float2half_rn(v - __half2float(h));
   }
-}
-
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
-  float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(x[i]));
-  if (m > 0.f && isfinite(m)) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
 
 // packed [N, 2176] -> full symmetric [N, 64, 64], + lambda on the diagonal
@@ -468,14 +498,23 @@ static int encode(PFN_encodeTiled64 enc, CUtensorMap* map, void* ptr, int rank, 
 // Build the d = 64 split-fp16 tables and descriptors (symmetric tables only).  Synchronises `s`.
 int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
   const int Kpad = t->Kpad, K = t->K;
-  float* stat = nullptr;
-  RLVAE_CUDA_OK(cudaMalloc(&stat, sizeof(float)));
-  RLVAE_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(float), s));
-  absmax_kernel<<<256, 256, 0, s>>>(t->c, (int64_t)Kpad * 64, stat);
-  float cmax = 0.f;
-  RLVAE_CUDA_OK(cudaMemcpyAsync(&cmax, stat, sizeof(float), cudaMemcpyDeviceToHost, s));
+  // centre of the expanded distance form (mean centroid) + statistics of the centred table
+  RLVAE_CUDA_OK(cudaMalloc(&t->cshift, sizeof(float) * 66));
+  RLVAE_CUDA_OK(cudaMemsetAsync(t->cshift, 0, sizeof(float) * 66, s));
+  {
+    const char* ce = getenv("RLVAE_TC_CENTRE");
+    if (ce == nullptr || ce[0] != '0') {
+      centroid_mean64_kernel<<<1, 256, 0, s>>>(t->c, K, t->cshift);
+      RLVAE_LAUNCH_OK();
+    }
+  }
+  centred_stats64_kernel<<<(K + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, t->cshift + 64);
+  RLVAE_LAUNCH_OK();
+  float h_st[2] = {0.f, 0.f};
+  RLVAE_CUDA_OK(cudaMemcpyAsync(h_st, t->cshift + 64, sizeof(h_st), cudaMemcpyDeviceToHost, s));
   RLVAE_CUDA_OK(cudaStreamSynchronize(s));
-  cudaFree(stat);
+  const float cmax = h_st[1];
+  t->r2mean_centred = h_st[0] / (float)K;
   if (!(t->m_absmax > 0.f) || !(cmax > 0.f)) return 0;      // degenerate tables: direct path only
   int ex = 0;
   frexpf(t->m_absmax, &ex);
@@ -487,7 +526,7 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
   RLVAE_CUDA_OK(cudaMalloc(&t->cbias, sizeof(float) * (size_t)Kpad));
   RLVAE_CUDA_OK(cudaMalloc(&t->Mh_hi, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad));
   RLVAE_CUDA_OK(cudaMalloc(&t->Mh_lo, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad));
-  pack_c64_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, K, Kpad, ldexpf(1.f, ec), 1.4426950408889634f / t->T2,
+  pack_c64_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, Kpad, ldexpf(1.f, ec), 1.4426950408889634f / t->T2,
                                                      static_cast<__half*>(t->c64h), t->cbias);
   RLVAE_LAUNCH_OK();
   pack_sym64_h_kernel<<<1184, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, em), static_cast<__half*>(t->Mh_hi),
@@ -562,10 +601,10 @@ static int launch_h64(const rlvae_tables* t, const float* z, int64_t n, float* p
   const float cu = t->c64_unscale, os = t->h16_out_scale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64_2, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, n, nb, alpha,
-                                       cu, os, packed));
+                                       cu, os, t->cshift, packed));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64, t->tm_mh_hi, t->tm_mh_lo, z, cbias, n, nb, alpha,
-                                       cu, os, packed));
+                                       cu, os, t->cshift, packed));
   }
   return 0;
 }

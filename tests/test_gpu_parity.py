@@ -552,6 +552,22 @@ def test_latent_dim_64_large_k_tensor_vs_direct():
     close_ld(b['logdet_g'], a['logdet_g'])
 
 
+def test_latent_dim_64_translated_tables():
+    """d = 64: the tensor kernel evaluates the expanded form about the mean centroid too, so a latent
+    cloud far from the origin still passes the accuracy gate and matches the direct kernel."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(1000, 64, seed=7)
+    off = torch.full((64,), 12.0)
+    off[::2] = -9.0
+    t = (sm.centroids + off, sm.metric_matrices, sm.temperature, sm.regularization)
+    assert 'tensor' in paths_for(t)
+    z = (make_points(400, 64, seed=8) + off).to(dev())
+    a = make_mt(t, 'direct').evaluate(z, want_ginv=True, want_logdet=True)
+    b = make_mt(t, 'tensor').evaluate(z, want_ginv=True, want_logdet=True)
+    assert rel_fro(b['ginv'].cpu(), a['ginv'].cpu()) < TOL_MAT
+    close_ld(b['logdet_g'], a['logdet_g'])
+
+
 @pytest.mark.parametrize('case', ['hmc_d16_k300', 'hmc_d16_k300_beta03'])
 def test_hmc_matches_reference_chain(case):
     """A11: same RNG stream -> same accept decisions and the same final state as the reference;
