@@ -57,7 +57,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
                         int n_centroids, int latent_dim, float temperature, float regularization,
                         void* stream);
 int rlvae_tables_destroy(rlvae_tables_t* t);
-/* info[0]=K, [1]=d, [2]=K padded, [3]=1 if every M_k is exactly symmetric,
+/* info[0]=K, [1]=d, [2]=K padded, [3]=1 if every M_k is symmetric (to 2^-22 of its largest entry),
  * [4]=1 if the tensor path exists for this d, [5]=1 if AUTO would pick the tensor path,
  * [6]=1 if the expanded-distance form is accurate enough for these tables (other tensor kernels
  * are not used by AUTO when it is not), [7]=how the d = 16 symmetric kernels form the weights:

@@ -50,7 +50,7 @@ constexpr int kKPad = 128;  // centroid tables are zero-padded to a multiple of 
 struct rlvae_tables {
   int K = 0, d = 0, Kpad = 0;
   float T = 0.f, T2 = 0.f, lambda = 0.f;
-  int symmetric = 0;       // every M_k bitwise symmetric
+  int symmetric = 0;       // every M_k symmetric to 2^-22 of its largest entry (packed tables hold (M + M^T)/2)
   int tensor_capable = 0;  // d == 16 and TMA descriptors built
   int tensor_auto = 0;     // AUTO picks a tensor path (expanded form accurate enough, or exact-distance mode available)
   int expanded_ok = 0;     // accuracy criterion for the expanded-distance form ||z||^2+||c||^2-2z.c holds

@@ -458,7 +458,7 @@ __global__ void pack_sym64_h_kernel(const float* __restrict__ M, int Kpad, float
       int i = 0, base = 0;
       while (p >= base + (64 - i)) { base += 64 - i; ++i; }
       const int j = i + (p - base);
-      v = scale * M[(int64_t)k * 4096 + i * 64 + j];
+      v = scale * 0.5f * (M[(int64_t)k * 4096 + i * 64 + j] + M[(int64_t)k * 4096 + j * 64 + i]);
     }
     const __half h = __float2half_rn(v);
     hi_t[idx] = h;
