@@ -37,3 +37,49 @@ for T in (0.7, 3.0):
         torch.cuda.synchronize()
         hmc_us = (time.perf_counter() - t0) / 5 / 3 * 1e6
         print(f'  n={n:6d}: evaluate (G^-1 + log det + grad) {ev_us:8.1f} us   HMC iteration (10 leapfrog) {hmc_us:8.1f} us')
+
+# the reference-facing entry points at one small batch (wall clock per call, Python overhead included)
+from rlvae_b200 import WorkingRiemannianSampler, _capi
+mt = MetricTensor(16, device=dev)
+with contextlib.redirect_stdout(io.StringIO()):
+    mt.load_pretrained(sm.centroids.clone(), sm.metric_matrices.clone(), temperature=0.7,
+                       regularization=sm.regularization)
+model = MetricModel(mt)
+ws, hs = WorkingRiemannianSampler(model), RiemannianHMCSampler(model)
+mu = make_points(1024, 16, seed=3).to(dev)
+lv = torch.full_like(mu, -2.0)
+
+
+def wall(name, fn, reps=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    print(f'  {name:46s} {(time.perf_counter() - t0) / reps * 1e6:8.1f} us')
+
+
+print('entry points at n = 1024, K = 200, T = 0.7:')
+with torch.no_grad():
+    wall('nearest2', lambda: _capi.nearest2(mt._tables(dev), mu))
+    for m in ('enhanced', 'geodesic', 'basic'):
+        wall(f'WorkingRiemannianSampler {m}', lambda m=m: ws.sample_riemannian_latents(mu, lv, method=m))
+    wall("RiemannianHMCSampler 'hmc' refine", lambda: hs.sample_riemannian_latents(mu, lv, method='hmc'))
+    wall('compute_inverse_metric', lambda: mt.compute_inverse_metric(mu))
+    wall('compute_metric', lambda: mt.compute_metric(mu))
+    wall('compute_log_det_metric', lambda: mt.compute_log_det_metric(mu))
+    wall('compute_metric_spectrum', lambda: mt.compute_metric_spectrum(mu))
+    wall('riemannian_distance_squared', lambda: mt.compute_riemannian_distance_squared(mu, mu.roll(1, 0)))
+    wall('log_pi', lambda: hs.log_pi(mu))
+    wall('grad_func', lambda: hs.grad_func(mu))
+mug = mu.clone().requires_grad_(True)
+
+
+def bwd():
+    mug.grad = None
+    mt.compute_log_det_metric(mug).sum().backward()
+
+
+wall('log det + autograd backward', bwd)
