@@ -624,6 +624,45 @@ def test_hmc_matches_reference_chain(case):
         assert mism == 0, f'{mism} accept decisions differ'
 
 
+def test_hmc_small_temperature_matches_the_oracle_chain():
+    """The reference's T = 0.7 with its HMC sampler: the hybrid weight mode (tensor path) and the direct
+    kernels against the CPU oracle chain, teacher-forced per iteration -- Hamiltonians to 1e-4 and
+    identical accept decisions (a flip only where acc sits within rounding of alpha).  The exact-gradient
+    drift (not in the reference, so not in the oracle) is checked hybrid-vs-direct the same way."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    from rlvae_b200.synthetic import make_hmc_streams, make_synthetic_metric
+    sm = make_synthetic_metric(300, 16, seed=31)
+    t = (sm.centroids, sm.metric_matrices, 0.7, sm.regularization)
+    n, iters, n_lf, eps = 192, 3, 5, 0.03
+    z0, gam, acc = make_hmc_streams(n, 16, iters, seed=32)
+    z0[: n // 2] = sm.centroids[: n // 2] + 0.1 * z0[: n // 2]        # chains that start next to centroids
+    rec = {}
+    O.hmc_sample(t, z0, gam, acc, n_lf, eps, 1.0, record=rec)
+    paths = paths_for(t)
+    assert 'tensor' in paths and make_mt(t)._tables(dev()).weight_mode == 2
+    forced = [z0] + rec['z'][:-1]
+
+    def run(path, grad_mode):
+        s = RiemannianHMCSampler(MetricModel(make_mt(t, path)), mcmc_steps_nbr=iters, n_lf=n_lf, eps_lf=eps,
+                                 beta_zero=1.0, grad_mode=grad_mode)
+        got = {}
+        s.sample_with_streams(z0.to(dev()), gam.to(dev()), acc.to(dev()),
+                              z_forced=[f.to(dev()) for f in forced], record=got)
+        return got
+
+    def same_chain(got, ref, tag):
+        for i in range(iters):
+            close_ld(got['H0'][i], ref['H0'][i], 1e-4)
+            close_ld(got['H'][i], ref['H'][i], 1e-4)
+            flip = got['moves'][i].cpu() != ref['moves'][i].cpu()
+            assert torch.all((acc[i][flip] - ref['alpha'][i].cpu()[flip]).abs() < 1e-5), tag
+            assert int(flip.sum()) == 0, tag
+
+    for path in paths:
+        same_chain(run(path, 'modular'), rec, path)
+    same_chain(run('tensor', 'exact'), run('direct', 'exact'), 'exact drift')
+
+
 @pytest.mark.parametrize('case', ['rhvae_hmc_d16_k120', 'rhvae_hmc_d16_k120_beta03'])
 def test_pythae_variant_hmc_matches_reference_chain(case):
     """A8: RHVAESampler.hmc_sampling (what OfficialRHVAESampler.sample_prior runs): same RNG stream ->
