@@ -83,3 +83,16 @@ def bwd():
 
 
 wall('log det + autograd backward', bwd)
+
+# RiemannianHMCSampler.sample at the reference's default schedule (100 MCMC steps x 15 leapfrog).
+# (Replaying each MCMC iteration as one CUDA graph was tried and changed nothing -- 49.3 vs 48.7 ms: at
+# these sizes the loop is bound by the ~30 us of GPU-side kernel latency per metric evaluation, not by
+# the host's launches.)
+hs_full = RiemannianHMCSampler(model, mcmc_steps_nbr=100, n_lf=15, eps_lf=0.03)
+for nn in (64, 1024):
+    hs_full.sample(nn)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hs_full.sample(nn)
+    torch.cuda.synchronize()
+    print(f'  sample({nn}), 100 x 15 leapfrog: {(time.perf_counter() - t0) * 1e3:7.1f} ms')
