@@ -181,6 +181,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */,
                           const float* __restrict__ cshift /* [16] centre of the expanded form */,
                           float hyb_thr /* HYBRID: refine weights with log2(2^14 w) above this */, FusedOut fo) {
+#ifdef RLVAE_TC_PROFILE
+  const long long pk0 = clock64();
+#endif
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
@@ -580,10 +583,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       PROF_ADD(pf_work);
     }
 #ifdef RLVAE_TC_PROFILE
-    const long long pf1 = clock64();
-    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
-      printf("[h16 prof %d] fold group per chunk: wait CH_FULL %lld  fold %lld | mainloop total %lld cycles\n",
-             (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf1 - pf0);
+    const long long pf1 = clock64();     // (printed after the epilogue: a printf here would be timed as epilogue)
 #endif
     // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
     const int64_t rows_here = (n - row0 < TILE_M) ? ((n - row0 > 0) ? (n - row0) : 0) : TILE_M;   // 0 for a pair's padding tile
@@ -671,7 +671,11 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
 #ifdef RLVAE_TC_PROFILE
     if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
-      printf("[h16 prof %d] epilogue %lld cycles\n", (int)blockIdx.x, clock64() - pf1);
+    {
+      const long long pf2 = clock64();
+      printf("[h16 prof %d] fold group per chunk: wait CH_FULL %lld  fold %lld | prologue %lld  mainloop %lld  epilogue %lld cycles\n",
+             (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf0 - pk0, pf1 - pf0, pf2 - pf1);
+    }
 #endif
   }
 #undef MMA_H
