@@ -34,7 +34,8 @@ typedef struct rlvae_tables rlvae_tables_t;
 enum {
   RLVAE_PATH_AUTO   = 0, /* tensor path when eligible (d==16, accuracy criterion), else direct */
   RLVAE_PATH_DIRECT = 1, /* fp32 CUDA-core kernel, direct ||z-c||^2 differences (any d <= 64)   */
-  RLVAE_PATH_TENSOR = 2  /* tcgen05/TMEM 3xTF32 kernel (d == 16 only); error if not available   */
+  RLVAE_PATH_TENSOR = 2  /* tcgen05/TMEM kernels: split-fp16 (symmetric tables, d == 16 or 64) or 3xTF32
+                            (any d == 16 table); error if no tensor kernel exists for these tables */
 };
 
 /* log_pi / gradient flavours of the HMC sampler */
@@ -62,8 +63,11 @@ int rlvae_tables_destroy(rlvae_tables_t* t);
  * [6]=1 if the expanded-distance form is accurate enough for these tables (other tensor kernels
  * are not used by AUTO when it is not), [7]=how the d = 16 symmetric kernels form the weights:
  * 0 expanded form, 1 exact differences, 2 hybrid (expanded form + exact refinement of the weights
- * that can matter) */
-int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]);
+ * that can matter), [8]=1 if every M_k was certified positive semi-definite and
+ * lambda > 0 (G^{-1}(z) is then positive definite everywhere: the fused kernels skip the packed
+ * G^{-1} store that only feeds the pivoting fallback, and the single-launch HMC trajectory kernel is
+ * eligible), [9..11] reserved (0) */
+int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[12]);
 
 /* ---- A2: G^{-1}(z) = sum_k M_k exp(-||z-c_k||^2/T^2) + lambda I ------------------------------
  * ref: src/models/components/metric_tensor.py:98-137.   z [N,d] -> ginv [N,d,d]
@@ -96,9 +100,11 @@ int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, i
 
 /* ---- variant C (pythae): (1/T^2) G^T sum_k w_k M_k^T (c_k - z) -------------------------------
  * ref: src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187.
- * g [N,d,d] (the metric at z) -> out [N,d].  Direct path only.                                */
+ * g [N,d,d] (the metric at z) -> out [N,d].  CUDA-core path.  `work` must hold
+ * rlvae_metric_grad_pythae_workspace(n, d) bytes.                                             */
+int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d);   /* bytes */
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
-                             float* out, void* stream);
+                             float* out, void* work, void* stream);
 
 /* ---- fused metric evaluation -----------------------------------------------------------------
  * z -> any subset of { ginv [N,d,d], g [N,d,d], logdet_g [N] (= log|det G|, ref

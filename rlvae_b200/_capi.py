@@ -32,7 +32,8 @@ _SIGNATURES = [
     ('rlvae_inverse_metric_packed', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p]),
-    ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    ('rlvae_metric_grad_pythae_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_metric_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_sym_eigvalsh', c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
@@ -93,6 +94,30 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32):
     return t.contiguous()
 
 
+def _req_z(tab: 'Tables', z: torch.Tensor, name: str = 'z') -> torch.Tensor:
+    """A latent batch for tables ``tab``: contiguous fp32 [N, tab.d] on the tables' device.  Everything
+    below this line is raw pointers, so a wrong latent_dim or device must fail HERE, not in a kernel."""
+    z = _req(z, name)
+    if z.dim() != 2 or z.shape[1] != tab.d:
+        raise ValueError(f'{name} must be [batch, {tab.d}], got {tuple(z.shape)}')
+    if z.device != tab.device:
+        raise RuntimeError(f'{name} is on {z.device} but the metric tables live on {tab.device}')
+    return z
+
+
+def _req_out(t, name: str, shape, device, dtype=torch.float32):
+    """A caller-supplied output buffer: exact shape, dtype, device, contiguous (kernels write through
+    the raw pointer).  None passes through."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != device:
+        raise RuntimeError(f'{name}: output buffer must be a CUDA tensor on {device}')
+    if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f'{name}: output buffer must be contiguous {dtype} of shape {tuple(shape)}, '
+                         f'got {t.dtype} {tuple(t.shape)} (contiguous={t.is_contiguous()})')
+    return t
+
+
 class Tables:
     """Owner of a ``rlvae_tables_t`` handle (packed device copies of the metric tables)."""
 
@@ -111,12 +136,13 @@ class Tables:
                                              c_float(self.temperature), c_float(self.regularization),
                                              _stream(c)), 'rlvae_tables_create')
         self._h = h
-        info = (c_int64 * 8)()
+        info = (c_int64 * 12)()
         _check(lib().rlvae_tables_info(self._h, info), 'rlvae_tables_info')
         self.Kpad, self.symmetric = int(info[2]), bool(info[3])
         self.tensor_capable, self.tensor_auto = bool(info[4]), bool(info[5])
         self.expanded_ok = bool(info[6])     # accuracy gate of the expanded distance form
         self.weight_mode = int(info[7])      # d = 16 symmetric: 0 expanded form, 1 exact differences, 2 hybrid
+        self.psd_certified = bool(info[8])   # every M_k PSD and lambda > 0: G^{-1}(z) positive definite everywhere
 
     @property
     def handle(self):
@@ -138,7 +164,7 @@ class Tables:
 
 # ----------------------------------------------------------------------------- thin call wrappers
 def inverse_metric(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO) -> torch.Tensor:
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     n, d = z.shape
     out = torch.empty((n, d, d), device=z.device, dtype=torch.float32)
     need = int(lib().rlvae_inverse_metric_workspace(n, d))
@@ -151,10 +177,11 @@ def inverse_metric(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO) -> torch
 
 def inverse_metric_packed(tab: Tables, z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """G^{-1} in the packed symmetric [N,144] layout (symmetric tables, d == 16)."""
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     n = z.shape[0]
     if out is None:
         out = torch.empty((n, 144), device=z.device, dtype=torch.float32)
+    _req_out(out, 'out', (n, 144), z.device)
     with torch.cuda.device(z.device):
         _check(lib().rlvae_inverse_metric_packed(tab.handle, _ptr(z), n, _ptr(out), _stream(z)),
                'rlvae_inverse_metric_packed')
@@ -164,6 +191,8 @@ def inverse_metric_packed(tab: Tables, z: torch.Tensor, out: torch.Tensor | None
 def batched_inverse(a: torch.Tensor, want_inv=True, want_logabsdet=False, want_sign=False,
                     want_diag=False, transpose=False):
     a = _req(a, 'a')
+    if a.dim() != 3 or a.shape[1] != a.shape[2]:
+        raise ValueError(f'a must be [batch, d, d], got {tuple(a.shape)}')
     n, d = a.shape[0], a.shape[-1]
     dev = a.device
     inv = torch.empty_like(a) if want_inv else None
@@ -177,8 +206,10 @@ def batched_inverse(a: torch.Tensor, want_inv=True, want_logabsdet=False, want_s
 
 
 def metric_grad(tab: Tables, z: torch.Tensor, u: torch.Tensor, scale: float, path: int = PATH_AUTO):
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     u = _req(u, 'u')
+    if tuple(u.shape) != (z.shape[0], tab.d, tab.d) or u.device != z.device:
+        raise ValueError(f'u must be [{z.shape[0]}, {tab.d}, {tab.d}] on {z.device}, got {tuple(u.shape)} on {u.device}')
     out = torch.empty_like(z)
     with torch.cuda.device(z.device):
         _check(lib().rlvae_metric_grad(tab.handle, _ptr(z), _ptr(u), z.shape[0], c_float(scale), _ptr(out),
@@ -187,36 +218,43 @@ def metric_grad(tab: Tables, z: torch.Tensor, u: torch.Tensor, scale: float, pat
 
 
 def metric_grad_pythae(tab: Tables, z: torch.Tensor, g: torch.Tensor):
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     g = _req(g, 'g')
+    if tuple(g.shape) != (z.shape[0], tab.d, tab.d) or g.device != z.device:
+        raise ValueError(f'g must be [{z.shape[0]}, {tab.d}, {tab.d}] on {z.device}, got {tuple(g.shape)} on {g.device}')
     out = torch.empty_like(z)
+    need = int(lib().rlvae_metric_grad_pythae_workspace(z.shape[0], tab.d))
+    work = torch.empty(max(need, 1), device=z.device, dtype=torch.uint8)
     with torch.cuda.device(z.device):
-        _check(lib().rlvae_metric_grad_pythae(tab.handle, _ptr(z), _ptr(g), z.shape[0], _ptr(out), _stream(z)),
-               'rlvae_metric_grad_pythae')
+        _check(lib().rlvae_metric_grad_pythae(tab.handle, _ptr(z), _ptr(g), z.shape[0], _ptr(out), _ptr(work),
+                                              _stream(z)), 'rlvae_metric_grad_pythae')
     return out
 
 
 def metric_eval(tab: Tables, z: torch.Tensor, want_ginv=True, want_g=False, want_logdet=True,
                 want_grad=False, path: int = PATH_AUTO, out=None):
     """-> dict(ginv, g, logdet_g, grad_logdet_g) (missing keys are None)."""
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     n, d = z.shape
     dev = z.device
     out = out or {}
-    ginv = out.get('ginv') if want_ginv else None
+    ginv = _req_out(out.get('ginv'), 'out[ginv]', (n, d, d), dev) if want_ginv else None
     if want_ginv and ginv is None:
         ginv = torch.empty((n, d, d), device=dev)
-    g = out.get('g') if want_g else None
+    g = _req_out(out.get('g'), 'out[g]', (n, d, d), dev) if want_g else None
     if want_g and g is None:
         g = torch.empty((n, d, d), device=dev)
-    ld = out.get('logdet_g') if want_logdet else None
+    ld = _req_out(out.get('logdet_g'), 'out[logdet_g]', (n,), dev) if want_logdet else None
     if want_logdet and ld is None:
         ld = torch.empty(n, device=dev)
-    gr = out.get('grad_logdet_g') if want_grad else None
+    gr = _req_out(out.get('grad_logdet_g'), 'out[grad_logdet_g]', (n, d), dev) if want_grad else None
     if want_grad and gr is None:
         gr = torch.empty((n, d), device=dev)
     work = out.get('work')
     need = int(lib().rlvae_metric_eval_workspace(n, d))
+    if work is not None and (not work.is_cuda or work.device != dev or work.dtype != torch.uint8
+                             or not work.is_contiguous()):
+        work = None
     if work is None or work.numel() < need:
         work = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
@@ -240,7 +278,7 @@ def sym_eigvalsh(a: torch.Tensor) -> torch.Tensor:
 
 def metric_spectrum(tab: Tables, z: torch.Tensor, want_logdet: bool = True, path: int = PATH_AUTO):
     """-> (eig(G^{-1}(z)) [N,16] ascending, log|det G| [N] or None); symmetric tables, d == 16."""
-    z = _req(z, 'z')
+    z = _req_z(tab, z)
     n, d = z.shape
     eig = torch.empty((n, d), device=z.device, dtype=torch.float32)
     ld = torch.empty(n, device=z.device, dtype=torch.float32) if want_logdet else None
@@ -275,9 +313,14 @@ def hmc_iteration(tab: Tables, z: torch.Tensor, gamma: torch.Tensor, acc: torch.
     """One MCMC iteration, in place on ``z``.  Returns (h0, h1, alpha, moves) if want_stats."""
     if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
         raise RuntimeError('hmc_iteration: z must be a contiguous fp32 CUDA tensor (updated in place)')
-    gamma = _req(gamma, 'gamma')
+    _req_z(tab, z)
+    gamma = _req_z(tab, gamma, 'gamma')
     acc = _req(acc, 'acc')
     n, d = z.shape
+    if gamma.shape[0] != n or tuple(acc.shape) != (n,) or acc.device != z.device:
+        raise ValueError(f'hmc_iteration: gamma must be [{n}, {d}] and acc [{n}] on {z.device}')
+    if len(scales) != n_lf:
+        raise ValueError(f'hmc_iteration: need {n_lf} tempering scales, got {len(scales)}')
     if work is None:
         work = hmc_workspace(n, d, z.device)
     sc = (c_float * n_lf)(*[float(s) for s in scales])
@@ -293,6 +336,7 @@ def hmc_iteration(tab: Tables, z: torch.Tensor, gamma: torch.Tensor, acc: torch.
 def hmc_refine(tab: Tables, z: torch.Tensor, n_steps: int, step_size: float, path: int = PATH_AUTO):
     if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
         raise RuntimeError('hmc_refine: z must be a contiguous fp32 CUDA tensor (updated in place)')
+    _req_z(tab, z)
     n, d = z.shape
     work = hmc_workspace(n, d, z.device)
     with torch.cuda.device(z.device):
@@ -302,7 +346,7 @@ def hmc_refine(tab: Tables, z: torch.Tensor, n_steps: int, step_size: float, pat
 
 
 def nearest2(tab: Tables, mu: torch.Tensor):
-    mu = _req(mu, 'mu')
+    mu = _req_z(tab, mu, 'mu')
     n = mu.shape[0]
     idx = torch.empty((n, 2), device=mu.device, dtype=torch.int64)
     dist = torch.empty((n, 2), device=mu.device)
@@ -315,6 +359,8 @@ def chol_apply(a: torch.Tensor, eps: torch.Tensor, jitter: float = 1e-6):
     a = _req(a, 'a')
     eps = _req(eps, 'eps')
     n, d = eps.shape
+    if tuple(a.shape) != (n, d, d) or a.device != eps.device:
+        raise ValueError(f'chol_apply: a must be [{n}, {d}, {d}] on {eps.device}, got {tuple(a.shape)} on {a.device}')
     out = torch.empty_like(eps)
     status = torch.empty(n, device=a.device, dtype=torch.int32)
     with torch.cuda.device(a.device):

@@ -2,6 +2,7 @@
 // table-packing kernels behind rlvae_tables_create.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -302,7 +303,7 @@ using namespace rlvae;
 extern "C" {
 
 const char* rlvae_last_error(void) { return g_last_error.c_str(); }
-int rlvae_abi_version(void) { return 1; }
+int rlvae_abi_version(void) { return 2; }
 long long rlvae_launch_count(int reset) {
   return reset ? g_launch_count.exchange(0) : g_launch_count.load();
 }
@@ -484,6 +485,29 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           if (rc != 0) return fail(rc);
           rc = tc_build_ct_centred_descriptors(t);
           if (rc != 0) return fail(rc);
+          // Positive semi-definiteness certificate: eigenvalues of every (symmetrised) M_k by the batched
+          // Jacobi kernel.  With all M_k >= 0 and lambda > 0, G^{-1}(z) = sum_k w_k M_k + lambda I is
+          // positive definite for every z, so the fused kernels' Cholesky cannot fail except by rounding.
+          if (t->lambda > 0.f && isfinite(t->lambda)) {
+            float* eig = nullptr;
+            if (cudaMalloc(&eig, sizeof(float) * (size_t)K * 16) == cudaSuccess) {
+              bool okc = launch_sym16_eigvalsh(t->M, K, 0, eig, s) == 0;
+              float* h_eig = okc ? static_cast<float*>(malloc(sizeof(float) * (size_t)K * 16)) : nullptr;
+              if (h_eig != nullptr &&
+                  cudaMemcpyAsync(h_eig, eig, sizeof(float) * (size_t)K * 16, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                  cudaStreamSynchronize(s) == cudaSuccess) {
+                float emin = 0.f;
+                bool finite = true;
+                for (int64_t i = 0; i < (int64_t)K * 16; i += 16) {     // ascending: entry 0 is the smallest
+                  if (!std::isfinite(h_eig[i])) finite = false;
+                  emin = fminf(emin, h_eig[i]);
+                }
+                t->psd_certified = (finite && emin >= -1.0e-6f * t->m_absmax) ? 1 : 0;
+              }
+              free(h_eig);
+              cudaFree(eig);
+            }
+          }
         }
       }
     }
@@ -509,11 +533,13 @@ int rlvae_tables_destroy(rlvae_tables_t* t) {
   return 0;
 }
 
-int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[8]) {
+int rlvae_tables_info(const rlvae_tables_t* t, int64_t info[12]) {
   RLVAE_REQUIRE(t != nullptr && info != nullptr, "tables_info: NULL argument");
   info[0] = t->K; info[1] = t->d; info[2] = t->Kpad; info[3] = t->symmetric;
   info[4] = t->tensor_capable; info[5] = t->tensor_auto; info[6] = t->expanded_ok;
   info[7] = (t->d == 16 && t->symmetric && t->c16h != nullptr) ? h16_mode(t) : 0;
+  info[8] = t->psd_certified;
+  info[9] = info[10] = info[11] = 0;
   return 0;
 }
 
@@ -543,12 +569,12 @@ static bool use_h16(const rlvae_tables* t) {
 // a_full (optional): the expanded [N,16,16] G^{-1} as well (same kernel on the split-fp16 path).
 static int sym_forward(const rlvae_tables* t, const float* z, int64_t n, float* a_packed, float* g_packed,
                        float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s,
-                       float* a_full = nullptr, float* g_full = nullptr) {
+                       float* a_full = nullptr, float* g_full = nullptr, int a_packed_wanted = 1) {
   if (use_h16(t)) {
     // a pivoting fallback can only write the packed G: expand it afterwards for the (rare) failures by
     // keeping g_packed alongside g_full
     return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s, a_full,
-                                     g_full);
+                                     g_full, a_packed_wanted);
   }
   RLVAE_REQUIRE(a_packed != nullptr, "symmetric 3xTF32 path needs the packed buffer");
   if (int rc = launch_inverse_metric_tc_sym(t, z, n, a_packed, s)) return rc;
@@ -645,13 +671,18 @@ int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, i
                                 : launch_metric_grad_direct(t, z, u, n, scale, out, s);   // d = 64: forward only
 }
 
+int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d) {
+  return (int64_t)sizeof(float) * n * (d * d + d);
+}
+
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
-                             float* out, void* stream) {
+                             float* out, void* work, void* stream) {
   RLVAE_REQUIRE(t != nullptr, "metric_grad_pythae: tables handle is NULL");
   RLVAE_REQUIRE(n >= 0, "metric_grad_pythae: negative batch");
   if (n == 0) return 0;
   RLVAE_REQUIRE(z != nullptr && g != nullptr && out != nullptr, "metric_grad_pythae: NULL pointer");
-  return launch_metric_grad_pythae(t, z, g, n, out, static_cast<cudaStream_t>(stream));
+  RLVAE_REQUIRE(work != nullptr, "metric_grad_pythae: workspace required");
+  return launch_metric_grad_pythae(t, z, g, n, out, static_cast<float*>(work), static_cast<cudaStream_t>(stream));
 }
 
 int64_t rlvae_metric_eval_workspace(int64_t n, int d) {
@@ -681,7 +712,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     // kernel contracts the packed G directly (G^T == G).  The spare tail of a_buf is the fallback list.
     float* g_packed = (g != nullptr || grad_logdet_g != nullptr) ? (w + mat) : nullptr;
     int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
-    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv, g))
+    if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv, g, 0))
       return rc;
     if (grad_logdet_g != nullptr)
       return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
@@ -798,7 +829,8 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   auto eval = [&](const float* zz) -> int {
     if (packed) {   // fused forward + per-thread Cholesky; the gradient contracts packed G
       int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
-      if (int rc = sym_forward(t, zz, n, ginv, exact ? gfull : nullptr, lad, 1.f, sgn, diag, fail_ws, s))
+      if (int rc = sym_forward(t, zz, n, ginv, exact ? gfull : nullptr, lad, 1.f, sgn, diag, fail_ws, s, nullptr,
+                               nullptr, 0))
         return rc;
       if (exact) return launch_metric_grad_tc(t, zz, gfull, n, 1.f / t->T2, gex, s, 1);
       return 0;
@@ -844,7 +876,8 @@ int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, 
   for (int i = 0; i < n_steps; ++i) {
     if (packed) {
       int* fail_ws = reinterpret_cast<int*>(ginv + n * kSymCols);
-      if (int rc = sym_forward(t, z, n, ginv, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s)) return rc;
+      if (int rc = sym_forward(t, z, n, ginv, nullptr, nullptr, 1.f, nullptr, diag, fail_ws, s, nullptr, nullptr, 0))
+        return rc;
     } else {
       if (int rc = inverse_metric_full(t, z, n, ginv, path, s, w + n * d * d)) return rc;
       if (int rc = launch_batched_inverse(ginv, n, d, nullptr, nullptr, nullptr, diag, 0, s)) return rc;

@@ -118,13 +118,7 @@ int launch_inverse_metric_direct(const rlvae_tables* t, const float* z, int64_t 
   const int ncols = t->d * t->d;
   dim3 grid((unsigned)((n + DM_BM - 1) / DM_BM), (unsigned)((ncols + DM_BN - 1) / DM_BN));
   size_t smem = dm_smem_bytes(t->d);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(inverse_metric_direct_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)dm_smem_bytes(kMaxLatentDim)));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(inverse_metric_direct_kernel, (int)dm_smem_bytes(kMaxLatentDim));
   inverse_metric_direct_kernel<<<grid, DM_THREADS, smem, s>>>(z, t->c, t->M, n, t->K, t->d, ncols,
                                                              t->T2, t->lambda, ginv);
   RLVAE_LAUNCH_OK();
@@ -250,13 +244,7 @@ static size_t dg_smem_bytes(int d) {
 int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float* u, int64_t n,
                               float scale, float* out, cudaStream_t s) {
   if (n == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(metric_grad_direct_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)dg_smem_bytes(kMaxLatentDim)));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(metric_grad_direct_kernel, (int)dg_smem_bytes(kMaxLatentDim));
   dim3 grid((unsigned)((n + DG_BM - 1) / DG_BM));
   metric_grad_direct_kernel<<<grid, DG_THREADS, dg_smem_bytes(t->d), s>>>(
       z, u, t->c, t->M, n, t->K, t->d, t->T2, scale, out);
@@ -308,59 +296,37 @@ __global__ void build_aug_table_kernel(const float* __restrict__ c, const float*
   }
 }
 
-// workspace-free contract: the caller passes nothing, so the augmented table and the
-// [N, d*d+d] scratch are cached on the tables handle / a grow-only device buffer.
-struct PythaeCache {
-  const rlvae_tables* owner = nullptr;
-  float* aug = nullptr;
-  float* scratch = nullptr;
-  int64_t scratch_elems = 0;
-};
-static PythaeCache g_pythae;
-
+// The augmented table [K, d*d+d] is a derived cache on the tables handle (built on first use, freed
+// with the handle); the [N, d*d+d] scratch comes from the caller (rlvae_metric_grad_pythae_workspace),
+// so nothing here is shared between devices, handles or streams.
 int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
-                              float* out, cudaStream_t s) {
+                              float* out, float* scratch, cudaStream_t s) {
   if (n == 0) return 0;
   const int d = t->d, ncols = d * d + d;
-  if (g_pythae.owner != t) {
-    if (g_pythae.aug) cudaFree(g_pythae.aug);
-    RLVAE_CUDA_OK(cudaMalloc(&g_pythae.aug, sizeof(float) * (size_t)t->K * ncols));
-    build_aug_table_kernel<<<t->K, 128, 0, s>>>(t->c, t->M, t->K, d, g_pythae.aug);
+  RLVAE_REQUIRE(scratch != nullptr, "metric_grad_pythae: workspace required");
+  if (t->pythae_aug == nullptr) {
+    float* aug = nullptr;
+    RLVAE_CUDA_OK(cudaMalloc(&aug, sizeof(float) * (size_t)t->K * ncols));
+    build_aug_table_kernel<<<t->K, 128, 0, s>>>(t->c, t->M, t->K, d, aug);
     RLVAE_LAUNCH_OK();
-    g_pythae.owner = t;
-  }
-  if (g_pythae.scratch_elems < n * ncols) {
-    if (g_pythae.scratch) {
-      RLVAE_CUDA_OK(cudaStreamSynchronize(s));
-      cudaFree(g_pythae.scratch);
-    }
-    RLVAE_CUDA_OK(cudaMalloc(&g_pythae.scratch, sizeof(float) * (size_t)n * ncols));
-    g_pythae.scratch_elems = n * ncols;
+    RLVAE_CUDA_OK(cudaStreamSynchronize(s));      // other streams may use the cached table next
+    t->pythae_aug = aug;
   }
   dim3 grid((unsigned)((n + DM_BM - 1) / DM_BM), (unsigned)((ncols + DM_BN - 1) / DM_BN));
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(inverse_metric_direct_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)dm_smem_bytes(kMaxLatentDim)));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(inverse_metric_direct_kernel, (int)dm_smem_bytes(kMaxLatentDim));
   inverse_metric_direct_kernel<<<grid, DM_THREADS, dm_smem_bytes(d), s>>>(
-      z, t->c, g_pythae.aug, n, t->K, d, ncols, t->T2, t->lambda, g_pythae.scratch);
+      z, t->c, t->pythae_aug, n, t->K, d, ncols, t->T2, t->lambda, scratch);
   RLVAE_LAUNCH_OK();
   const int64_t total = n * d;
-  pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_pythae.scratch, z, g, n, d,
+  pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(scratch, z, g, n, d,
                                                                        t->lambda, t->T2, out);
   RLVAE_LAUNCH_OK();
   return 0;
 }
 
 void pythae_cache_release(const rlvae_tables* t) {
-  if (g_pythae.owner == t) {
-    if (g_pythae.aug) cudaFree(g_pythae.aug);
-    g_pythae.aug = nullptr;
-    g_pythae.owner = nullptr;
-  }
+  if (t->pythae_aug) cudaFree(t->pythae_aug);
+  t->pythae_aug = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -369,19 +335,22 @@ void pythae_cache_release(const rlvae_tables* t) {
 template <int D>
 __global__ void __launch_bounds__(128)
 nearest2_kernel(const float* __restrict__ mu, const float* __restrict__ c, int64_t n, int K,
-                int64_t* __restrict__ idx, float* __restrict__ dist) {
+                int64_t* __restrict__ idx, float* __restrict__ dist, int dr) {
+  // dr <= D: real latent_dim (rows of mu and c are dr floats); the extra coordinates are zero on both sides
   constexpr int KC = 64;
   __shared__ float cs[KC * D];
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float zr[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) zr[j] = (p < n) ? mu[p * D + j] : 0.f;
+  for (int j = 0; j < D; ++j) zr[j] = (p < n && j < dr) ? mu[p * dr + j] : 0.f;
   float b0 = FLT_MAX, b1 = FLT_MAX;
   int i0 = 0, i1 = 0;
   for (int k0 = 0; k0 < K; k0 += KC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < KC * D; i += blockDim.x)
-      cs[i] = (k0 + i / D < K) ? c[(int64_t)k0 * D + i] : 0.f;
+    for (int i = threadIdx.x; i < KC * D; i += blockDim.x) {
+      const int kk = i / D, j = i - kk * D;
+      cs[i] = (k0 + kk < K && j < dr) ? c[(int64_t)(k0 + kk) * dr + j] : 0.f;
+    }
     __syncthreads();
     const int kmax = min(KC, K - k0);
     for (int kk = 0; kk < kmax; ++kk) {
@@ -406,11 +375,13 @@ int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* 
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->K >= 2, "nearest2 needs at least two centroids");
   unsigned grid = (unsigned)((n + 127) / 128);
-  switch (t->d) {
-#define CASE(D) case D: nearest2_kernel<D><<<grid, 128, 0, s>>>(mu, t->c, n, t->K, idx, dist); break;
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
+  int dp = 1;                      // any latent_dim <= 64: zero-padded to the next power of two
+  while (dp < t->d) dp <<= 1;
+  switch (dp) {
+#define CASE(D) case D: nearest2_kernel<D><<<grid, 128, 0, s>>>(mu, t->c, n, t->K, idx, dist, t->d); break;
+    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
 #undef CASE
-    default: RLVAE_REQUIRE(false, "nearest2: unsupported latent_dim (1,2,3,4,8,16,32,64)");
+    default: RLVAE_REQUIRE(false, "nearest2: latent_dim must be in [1,64]");
   }
   RLVAE_LAUNCH_OK();
   return 0;

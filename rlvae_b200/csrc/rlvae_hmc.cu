@@ -52,10 +52,10 @@ __global__ void hmc_step_kernel(const float* __restrict__ diag_g, const float* _
                                 const float* __restrict__ sgn, const float* __restrict__ gex,
                                 int64_t n, int d, float eps, float lambda, float T2, int mode,
                                 float scale, int last, float* __restrict__ rho_half,
-                                float* __restrict__ z_cur, const float* __restrict__ z_prev,
+                                float* z_cur /* may alias z_out */, const float* __restrict__ z_prev,
                                 const float* __restrict__ acc, const float* __restrict__ h0,
                                 float* __restrict__ h1, float* __restrict__ alpha_out,
-                                float* __restrict__ moves, float* __restrict__ z_out) {
+                                float* __restrict__ moves, float* z_out /* may alias z_cur */) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const float half_eps = eps / 2.f;

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/rlvae_b200.h"
@@ -39,6 +40,22 @@ void count_launch();
   do {                                       \
     ::rlvae::count_launch();                 \
     RLVAE_CUDA_OK(expr);                     \
+  } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (context),
+// and one process may drive several GPUs (the Python wrappers switch with torch.cuda.device(z.device)),
+// so the "already done" flag is one bit per device ordinal, not one per process.
+#define RLVAE_OPT_IN_SMEM(kern, bytes)                                                          \
+  do {                                                                                          \
+    static std::atomic<unsigned long long> _done{0};                                            \
+    int _dev = 0;                                                                               \
+    RLVAE_CUDA_OK(cudaGetDevice(&_dev));                                                        \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                        \
+    if (!(_done.load(std::memory_order_acquire) & _bit)) {                                      \
+      RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         (int)(bytes)));                                        \
+      _done.fetch_or(_bit, std::memory_order_release);                                          \
+    }                                                                                           \
   } while (0)
 
 constexpr int kMaxLatentDim = 64;
@@ -97,6 +114,8 @@ struct rlvae_tables {
   // Mh_hi / Mh_lo then hold the packed-transposed [2176, Kpad] tables
   void* c16h = nullptr;        // d == 16: [Kpad,64] fp16 = [hi (16) | lo (16) | 0] of 2^ec c (GEMM1 of the fp16 kernels)
   float c16_unscale = 0.f;     // 2^-ec
+  int psd_certified = 0;       // d == 16 symmetric: every M_k positive semi-definite (to rounding) and lambda > 0, so
+                               //   G^{-1}(z) is positive definite and the Cholesky fallback list stays empty
   int hybrid_ok = 0;           // d == 16 symmetric: the hybrid weight mode has a valid threshold
   float hybrid_bits = 0.f;     //   weights below 2^-hybrid_bits cannot move G^{-1} by more than 1e-6 lambda
   float* cshift = nullptr;     // [d] mean centroid the fp16 GEMM1 operands are centred on (+ scratch; d == 16 or 64)
@@ -109,6 +128,8 @@ struct rlvae_tables {
   float c64_unscale = 0.f;     // 2^-ec
   float r2mean_centred = 0.f;  // mean ||c - cshift||^2 (d == 64: set by tc_build_h64_tables)
   CUtensorMap tm_c64, tm_c64_2;   // boxes of 32 centroids x 32 (pair: 16) rows
+  // pythae-variant gradient (A8): [K, d*d+d] = [M_k | M_k^T c_k], built on first use (derived cache)
+  mutable float* pythae_aug = nullptr;
 };
 
 namespace rlvae {
@@ -119,7 +140,7 @@ int launch_inverse_metric_direct(const rlvae_tables* t, const float* z, int64_t 
 int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float* u, int64_t n,
                               float scale, float* out, cudaStream_t s);
 int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
-                              float* out, cudaStream_t s);
+                              float* out, float* scratch, cudaStream_t s);
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
                            float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 // d == 16 only: `a` is the packed symmetric layout [N,144] written by the symmetric tensor kernel
@@ -134,7 +155,8 @@ int launch_sym16_inverse(const float* a_packed, int64_t n, float* g_packed, floa
 int launch_sym16_eigvalsh(const float* a, int64_t n, int packed, float* eig, cudaStream_t s);
 int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
                           float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s,
-                          float* g_full = nullptr);
+                          float* g_full = nullptr, const rlvae_tables* recompute_from = nullptr,
+                          const float* z = nullptr);
 // split-fp16 tensor kernel (rlvae_tc16.cu): forward + fused per-point Cholesky outputs
 int tc_build_h16_descriptors(rlvae_tables* t);
 int h16_mode(const rlvae_tables* t);   // 0 expanded, 1 exact differences, 2 hybrid
@@ -147,9 +169,12 @@ int launch_nearest2_tc(const rlvae_tables* t, const float* mu, int64_t n, int64_
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);
 // a_full (optional): the expanded [N,16,16] G^{-1}, written by the same kernel
+// a_packed_wanted == 0: a_packed is only the fallback's scratch -- for certified tables the kernel then
+// skips the 576 B/point store and the (normally empty) fallback list is recomputed instead
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s, float* a_full = nullptr, float* g_full = nullptr);
+                              int* fail_ws, cudaStream_t s, float* a_full = nullptr, float* g_full = nullptr,
+                              int a_packed_wanted = 1);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,

@@ -44,7 +44,10 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
                        float* __restrict__ logabsdet, float* __restrict__ sign,
                        float* __restrict__ diag_inv, int transpose_inv,
                        const int* __restrict__ list = nullptr, const int* __restrict__ count = nullptr,
-                       float* __restrict__ packed_out = nullptr, float lad_scale = 1.f) {
+                       float* __restrict__ packed_out = nullptr, float lad_scale = 1.f, int dr = D) {
+  // dr <= D: the real matrices are dr x dr (any latent_dim, e.g. 10, 12, 20); they are embedded as
+  // diag(A, I_{D-dr}), which leaves the inverse block, log|det| and the sign unchanged (the identity
+  // rows are only ever chosen as pivots for their own columns, with pivot 1).
   using P = PP<D>;
   constexpr int LANES = P::LANES, RPL = P::RPL, LD = P::LD;
   __shared__ float stage[P::MATS * D * LD];
@@ -68,8 +71,11 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
       sm[rr * LD + cc] = src[rr <= cc ? sym16_index(rr, cc) : sym16_index(cc, rr)];
     }
   } else {
-    const float* src = a + msafe * D * D;
-    for (int i = lane; i < D * D; i += LANES) sm[(i / D) * LD + (i % D)] = src[i];
+    const float* src = a + msafe * dr * dr;
+    for (int i = lane; i < D * D; i += LANES) {
+      const int rr = i / D, cc = i % D;
+      sm[rr * LD + cc] = (rr < dr && cc < dr) ? src[rr * dr + cc] : (rr == cc ? 1.f : 0.f);
+    }
   }
   __syncwarp(gmask);
 
@@ -168,11 +174,11 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
   __syncwarp(gmask);
   if (live) {
     if (inv != nullptr) {
-      float* dst = inv + mat * D * D;
-      for (int i = lane; i < D * D; i += LANES) dst[i] = sm[(i / D) * LD + (i % D)];
+      float* dst = inv + mat * dr * dr;
+      for (int i = lane; i < dr * dr; i += LANES) dst[i] = sm[(i / dr) * LD + (i % dr)];
     }
     if (diag_inv != nullptr)
-      for (int i = lane; i < D; i += LANES) diag_inv[mat * D + i] = sm[i * LD + i];
+      for (int i = lane; i < dr; i += LANES) diag_inv[mat * dr + i] = sm[i * LD + i];
     if (PACKED && packed_out != nullptr) {
       float* dst = packed_out + mat * kSymCols;
       for (int i = lane; i < D * D; i += LANES) {
@@ -192,16 +198,21 @@ batched_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
                            float* sign, float* diag_inv, int transpose_inv, cudaStream_t s) {
   if (n == 0) return 0;
-  switch (d) {
+  RLVAE_REQUIRE(d >= 1 && d <= kMaxLatentDim, "batched_inverse: latent_dim must be in [1,64]");
+  int dp = 1;                       // next power of two: the kernel embeds A as diag(A, I)
+  while (dp < d) dp <<= 1;
+  switch (dp) {
 #define CASE(D)                                                                             \
   case D: {                                                                                 \
     unsigned grid = (unsigned)((n + PP<D>::MATS - 1) / PP<D>::MATS);                        \
     batched_inverse_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, n, inv, logabsdet, sign,  \
-                                                               diag_inv, transpose_inv);    \
+                                                               diag_inv, transpose_inv,     \
+                                                               nullptr, nullptr, nullptr,   \
+                                                               1.f, d);                     \
   } break;
     CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
 #undef CASE
-    default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be a power of two <= 64");
+    default: RLVAE_REQUIRE(false, "batched_inverse: latent_dim must be in [1,64]");
   }
   RLVAE_LAUNCH_OK();
   return 0;
@@ -377,12 +388,72 @@ __global__ void unpack_sym16_list_kernel(const float* __restrict__ packed, const
   }
 }
 
+// Packed G^{-1} rows of the LISTED points recomputed from the natural fp32 tables with exact
+// differences (the arithmetic of the direct kernel).  Used when the fused tensor kernel was told not
+// to store packed G^{-1} (tables certified positive semi-definite: a Cholesky failure can then only
+// come from rounding, so paying 576 B per point for the fallback's input is waste); one CTA per
+// listed point, thread p < 136 owns packed entry p.
+__global__ void __launch_bounds__(160)
+recompute_packed_rows_kernel(const float* __restrict__ z, const float* __restrict__ c,
+                             const float* __restrict__ M, int K, float inv_T2, float lambda,
+                             const int* __restrict__ list, const int* __restrict__ count,
+                             float* __restrict__ a_packed) {
+  __shared__ float w[160];
+  __shared__ float zs[16];
+  const int cnt = *count;
+  const int tid = threadIdx.x;
+  int pi = 0, pj = 0;                         // packed entry tid = (pi <= pj)
+  if (tid < 136) {
+    int base = 0;
+    while (tid >= base + (16 - pi)) { base += 16 - pi; ++pi; }
+    pj = pi + (tid - base);
+  }
+  for (int slot = blockIdx.x; slot < cnt; slot += gridDim.x) {
+    const int64_t p = list[slot];
+    __syncthreads();
+    if (tid < 16) zs[tid] = z[p * 16 + tid];
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 160) {
+      __syncthreads();
+      float wk = 0.f;
+      if (k0 + tid < K) {
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float df = c[(int64_t)(k0 + tid) * 16 + j] - zs[j];
+          sq = fmaf(df, df, sq);
+        }
+        wk = expf(-sq * inv_T2);
+      }
+      w[tid] = wk;
+      __syncthreads();
+      if (tid < 136) {
+        const int kmax = min(160, K - k0);
+        for (int kk = 0; kk < kmax; ++kk) {
+          const float* m = M + (int64_t)(k0 + kk) * 256;
+          acc = fmaf(w[kk], 0.5f * (m[pi * 16 + pj] + m[pj * 16 + pi]), acc);
+        }
+      }
+    }
+    if (tid < 136) a_packed[p * kSymCols + tid] = acc + (pi == pj ? lambda : 0.f);
+    else if (tid < 144) a_packed[p * kSymCols + tid] = 0.f;
+  }
+}
+
+// `recompute_from` (optional): the producer did not store packed G^{-1}; the rows of the listed points
+// are first recomputed into a_packed (which must still be a valid [N,144] scratch) from these tables.
 int launch_sym16_fallback(const float* a_packed, int64_t n, float* g_packed, float* logabsdet,
                           float lad_scale, float* sign, float* diag_g, int* fail_ws, cudaStream_t s,
-                          float* g_full) {
+                          float* g_full, const rlvae_tables* recompute_from, const float* z) {
   if (n == 0) return 0;
   const int64_t groups = (n + PP<16>::MATS - 1) / PP<16>::MATS;
   const unsigned fgrid = (unsigned)(groups < 1184 ? groups : 1184);
+  if (recompute_from != nullptr) {
+    const rlvae_tables* t = recompute_from;
+    recompute_packed_rows_kernel<<<(unsigned)(n < 592 ? n : 592), 160, 0, s>>>(
+        z, t->c, t->M, t->K, 1.f / t->T2, t->lambda, fail_ws + 1, fail_ws, const_cast<float*>(a_packed));
+    RLVAE_LAUNCH_OK();
+  }
   batched_inverse_kernel<16, true><<<fgrid, PP<16>::THREADS, 0, s>>>(
       a_packed, n, nullptr, logabsdet, sign, diag_g, 0, fail_ws + 1, fail_ws, g_packed, lad_scale);
   RLVAE_LAUNCH_OK();
@@ -548,7 +619,8 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
 template <int D>
 __global__ void __launch_bounds__(PP<D>::THREADS)
 chol_apply_kernel(const float* __restrict__ a, const float* __restrict__ eps, int64_t n,
-                  float jitter, float* __restrict__ out, int32_t* __restrict__ status) {
+                  float jitter, float* __restrict__ out, int32_t* __restrict__ status, int dr) {
+  // dr <= D: real dimension; A is embedded as diag(A, I), eps padded with zeros
   using P = PP<D>;
   constexpr int LANES = P::LANES, RPL = P::RPL, LD = P::LD;
   __shared__ float stage[P::MATS * D * LD];
@@ -564,9 +636,12 @@ chol_apply_kernel(const float* __restrict__ a, const float* __restrict__ eps, in
   const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                        : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
 
-  const float* src = a + msafe * D * D;
-  for (int i = lane; i < D * D; i += LANES) sm[(i / D) * LD + (i % D)] = src[i];
-  for (int i = lane; i < D; i += LANES) es[i] = eps[msafe * D + i];
+  const float* src = a + msafe * dr * dr;
+  for (int i = lane; i < D * D; i += LANES) {
+    const int rr = i / D, cc = i % D;
+    sm[rr * LD + cc] = (rr < dr && cc < dr) ? src[rr * dr + cc] : (rr == cc ? 1.f : 0.f);
+  }
+  for (int i = lane; i < D; i += LANES) es[i] = (i < dr) ? eps[msafe * dr + i] : 0.f;
   __syncwarp(gmask);
 
   float r[RPL][D];
@@ -575,7 +650,7 @@ chol_apply_kernel(const float* __restrict__ a, const float* __restrict__ eps, in
 #pragma unroll
     for (int m = 0; m < D; ++m) {
       const int row = lane + LANES * i;
-      r[i][m] = sm[row * LD + m] + ((m == row) ? jitter : 0.f);
+      r[i][m] = sm[row * LD + m] + ((m == row && row < dr) ? jitter : 0.f);
     }
 
   bool bad = false;
@@ -605,7 +680,7 @@ chol_apply_kernel(const float* __restrict__ a, const float* __restrict__ eps, in
 #pragma unroll
       for (int m = 0; m < D; ++m)
         if (m <= row) y = fmaf(r[i][m], es[m], y);
-      out[mat * D + row] = bad ? __int_as_float(0x7fc00000) : y;
+      if (row < dr) out[mat * dr + row] = bad ? __int_as_float(0x7fc00000) : y;
     }
     if (status != nullptr && lane == 0) status[mat] = bad ? 1 : 0;
   }
@@ -614,15 +689,18 @@ chol_apply_kernel(const float* __restrict__ a, const float* __restrict__ eps, in
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
                       int32_t* status, cudaStream_t s) {
   if (n == 0) return 0;
-  switch (d) {
+  RLVAE_REQUIRE(d >= 1 && d <= kMaxLatentDim, "chol_apply: latent_dim must be in [1,64]");
+  int dp = 1;
+  while (dp < d) dp <<= 1;
+  switch (dp) {
 #define CASE(D)                                                                             \
   case D: {                                                                                 \
     unsigned grid = (unsigned)((n + PP<D>::MATS - 1) / PP<D>::MATS);                        \
-    chol_apply_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, eps, n, jitter, out, status);  \
+    chol_apply_kernel<D><<<grid, PP<D>::THREADS, 0, s>>>(a, eps, n, jitter, out, status, d); \
   } break;
     CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32) CASE(64)
 #undef CASE
-    default: RLVAE_REQUIRE(false, "chol_apply: latent_dim must be a power of two <= 64");
+    default: RLVAE_REQUIRE(false, "chol_apply: latent_dim must be in [1,64]");
   }
   RLVAE_LAUNCH_OK();
   return 0;

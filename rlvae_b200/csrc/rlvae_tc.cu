@@ -1366,12 +1366,7 @@ template <bool SYM, bool PAIR>
 static int launch_fwd(const CUtensorMap& c, const CUtensorMap& hi, const CUtensorMap& lo, const rlvae_tables* t,
                       const float* z, int64_t n, float* out, cudaStream_t s) {
   auto kern = tc::inverse_metric_tc_kernel<SYM, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::fwd::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::fwd::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;               // clusters of two point tiles
   cudaLaunchConfig_t cfg{};
@@ -1426,12 +1421,7 @@ static int launch_grad(const CUtensorMap& c, const CUtensorMap& hi, const CUtens
                        const float* z, const float* u, int64_t n, float scale, float* out, cudaStream_t s,
                        int u_packed) {
   auto kern = tc::metric_grad_tc_kernel<SYM, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::grad::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::grad::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};
@@ -1458,12 +1448,7 @@ template <bool PAIR>
 static int launch_grad_sym(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed) {
   auto kern = tc::metric_grad_sym_kernel<PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::gsym::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::gsym::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};

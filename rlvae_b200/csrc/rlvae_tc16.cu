@@ -1618,12 +1618,7 @@ static bool h16_use_pairs() {
 template <bool PAIR, bool EXACT, bool HYBRID = false>
 static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s) {
   auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT, HYBRID>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::h16::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::h16::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};
@@ -1675,7 +1670,7 @@ int h16_mode(const rlvae_tables* t) {
 // which needs packed G^{-1}: a_packed must be given whenever a factor output is requested).
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s, float* a_full, float* g_full) {
+                              int* fail_ws, cudaStream_t s, float* a_full, float* g_full, int a_packed_wanted) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr,
                 "split-fp16 tensor path needs latent_dim == 16 and symmetric tables");
@@ -1687,7 +1682,10 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   if (fused) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
   RLVAE_REQUIRE(a_full == nullptr || (reinterpret_cast<uintptr_t>(a_full) & 15) == 0, "G^-1 output must be 16-byte aligned");
   RLVAE_REQUIRE(g_full == nullptr || (reinterpret_cast<uintptr_t>(g_full) & 15) == 0, "G output must be 16-byte aligned");
-  tc::FusedOut fo{a_full, a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
+  // certified tables: nobody reads the packed G^{-1} unless the caller asked for it (the fallback list is
+  // recomputed from the tables in the rare rounding-level failure), so it is not stored
+  const bool skip_packed = !a_packed_wanted && t->psd_certified;
+  tc::FusedOut fo{a_full, skip_packed ? nullptr : a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
   int rc;
   const int mode = h16_mode(t);
   if (mode == 1) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
@@ -1695,7 +1693,9 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   else rc = h16_use_pairs() ? launch_h16<true, false>(t, z, n, fo, s) : launch_h16<false, false>(t, z, n, fo, s);
   if (rc) return rc;
   RLVAE_REQUIRE(g_full == nullptr || g_packed != nullptr, "the expanded G output needs the packed G buffer too");
-  if (fused) return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s, g_full);
+  if (fused)
+    return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s, g_full,
+                                 skip_packed ? t : nullptr, z);
   return 0;
 }
 
@@ -1703,12 +1703,7 @@ template <bool PAIR, bool EXACT, bool HYBRID = false>
 static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
                       cudaStream_t s, int u_packed) {
   auto kern = tc::metric_grad_h16_kernel<PAIR, EXACT, HYBRID>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::g16::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::g16::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};
@@ -1762,11 +1757,7 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
 template <bool PAIR>
 static int launch_n2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s) {
   auto kern = tc::nearest2_tc_kernel<PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::n2::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::n2::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};

@@ -575,12 +575,7 @@ static bool h64_use_pairs() {
 template <bool PAIR>
 static int launch_h64(const rlvae_tables* t, const float* z, int64_t n, float* packed, cudaStream_t s) {
   auto kern = tc::inverse_metric_h64_kernel<PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::h64::SMEM_BYTES));
-    attr_set = true;
-  }
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::h64::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};

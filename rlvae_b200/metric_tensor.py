@@ -6,10 +6,10 @@ meaning and error behaviour, so the models, samplers and losses of the
 reference (``modular_rlvae.py:239-261``, ``loss_manager.py:106-113``,
 ``base_sampler.py:60-68``) can use it unchanged.  What differs is underneath:
 
-* ``compute_inverse_metric``  -> ``rlvae_inverse_metric``  (tcgen05 3xTF32 kernel
+* ``compute_inverse_metric``  -> ``rlvae_inverse_metric``  (tcgen05 split-fp16 / 3xTF32 kernels
   or the fp32 direct kernel; never materialises [N,K] or [N,K,d,d]);
-* ``compute_metric`` / ``compute_log_det_metric`` -> ``rlvae_batched_inverse``
-  (register/shuffle Gauss-Jordan, one matrix per d lanes);
+* ``compute_metric`` / ``compute_log_det_metric`` -> ``rlvae_metric_eval`` (Cholesky fused into the
+  tensor kernel's epilogue) or ``rlvae_batched_inverse`` (register/shuffle Gauss-Jordan);
 * backward w.r.t. ``z`` -> ``rlvae_metric_grad`` (closed-form contraction), wired
   through ``torch.autograd.Function`` so ``loss_manager.py:110-142`` and
   ``riemannian_flow_vae.py:1030-1069`` can back-propagate through the metric.
@@ -141,8 +141,9 @@ class MetricTensor(nn.Module):
                self.regularization.data_ptr(), self.regularization._version)
         if self._tab is None or self._tab_key != key:
             if self._tab is not None:
-                torch.cuda.synchronize(device)   # kernels may still read the old packed copy
-                self._tab.close()
+                # kernels may still read the old packed copy; an autograd graph may still hold the old
+                # handle (ctx.tab), so it is NOT closed here -- the last reference frees it (__del__)
+                torch.cuda.synchronize(device)
             self._tab = _capi.Tables(c.float(), m.float(), float(self.temperature.item()),
                                      float(self.regularization.item()))
             self._tab_key = key
@@ -187,10 +188,12 @@ class MetricTensor(nn.Module):
         """G(z) = inv(G^{-1}(z)) [N,d,d]  (ref metric_tensor.py:139-160).  A singular G^{-1}
         is retried once with +1e-6 I, like the reference's LinAlgError handler."""
         if not (torch.is_grad_enabled() and z.requires_grad):
-            # no graph to build: one fused evaluation (packed Cholesky for symmetric tables)
-            g = self.evaluate(z, want_ginv=False, want_g=True, want_logdet=False)['g']
-            if not self.check_singular or bool(torch.isfinite(g).all()):
-                return g
+            # no graph to build: one fused evaluation (packed Cholesky for symmetric tables).  The
+            # singularity check reads the [N] log-determinants the same kernel produces (a zero pivot
+            # gives log|det G^{-1}| = -inf), not the [N,d,d] result.
+            ev = self.evaluate(z, want_ginv=False, want_g=True, want_logdet=self.check_singular)
+            if not self.check_singular or bool(torch.isfinite(ev['logdet_g']).all()):
+                return ev['g']
         g_inv = self.compute_inverse_metric(z)
         g, sgn = _InverseFn.apply(g_inv)
         if self.check_singular and bool((sgn == 0).any()):   # exact zero pivot == LinAlgError

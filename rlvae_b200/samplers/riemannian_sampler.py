@@ -6,8 +6,10 @@ CUDA ``MetricTensor`` evaluates it); ``cholesky(A + 1e-6 I) @ eps`` becomes
 ``rlvae_chol_apply``.  Each ``*_with_noise`` method takes the random draws as
 arguments (parity tests feed the reference's recorded stream); the public methods
 draw them in the reference's order and delegate.
-Like the reference, every failure falls back to standard reparameterisation
-with a printed warning (:99-101, :177-179, :216-218).
+Like the reference, a failed Cholesky factorisation falls back to the symmetric square root
+from ``eigh`` with eigenvalues clamped at 1e-6 for the WHOLE batch (:85-90, :158-164, :202-207,
+:273-278), and any other failure falls back to standard reparameterisation with a printed warning
+(:99-101, :177-179, :216-218).
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ class _CholApplyFn(torch.autograd.Function):
     def forward(ctx, a, eps, jitter):
         out, status = _capi.chol_apply(a.detach(), eps.detach(), jitter)
         if bool((status != 0).any()):
-            raise RuntimeError('cholesky: matrix not positive definite')
+            raise _NotPositiveDefinite('cholesky: matrix not positive definite')
         ctx.save_for_backward(a, eps)
         ctx.jitter = jitter
         return out
@@ -44,8 +46,22 @@ class _CholApplyFn(torch.autograd.Function):
         return ga, ge, None
 
 
+class _NotPositiveDefinite(RuntimeError):
+    pass
+
+
 def chol_apply(a, eps, jitter=1e-6):
-    return _CholApplyFn.apply(a, eps, jitter)
+    """cholesky(A + jitter I) @ eps; if ANY matrix of the batch is not positive definite, the
+    reference's ``except`` branch: sqrt(A) @ eps with sqrt from eigh(A) (no jitter), eigenvalues clamped
+    at 1e-6, for the whole batch (torch.linalg.eigh on the device, the same library call the reference
+    makes)."""
+    try:
+        return _CholApplyFn.apply(a, eps, jitter)
+    except _NotPositiveDefinite:
+        ev, evec = torch.linalg.eigh(a)
+        ev = torch.clamp(ev, min=1e-6)
+        root = evec @ torch.diag_embed(torch.sqrt(ev)) @ evec.transpose(-2, -1)
+        return torch.einsum('bij,bj->bi', root, eps)
 
 
 class WorkingRiemannianSampler(BaseRiemannianSampler):

@@ -19,7 +19,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(h, name), name
-    assert h.rlvae_abi_version() == 1
+    assert h.rlvae_abi_version() == 2
     # argument validation happens before any CUDA call: safe without a GPU
     assert h.rlvae_inverse_metric(None, None, 4, None, None, 0, None) != 0
     assert b'not loaded' in h.rlvae_last_error()

@@ -1,0 +1,132 @@
+"""GPU parity at the BENCHMARK's own table sizes (VERDICT r1 "weak 1"): the tensor-core product path
+against the CPU oracle -- not against the repo's own direct kernels -- on
+
+* BASELINE.json configs[1]: K = 10,000, d = 16: the first 4,096 points of the bench input in
+  <= 512-point chunks, every output of the step: G^{-1}, G, log det G, grad_z log det G;
+* the same tables at the reference's small temperature T = 0.7 (hybrid weight mode);
+* BASELINE.json configs[2]: HMC at K = 10,000, 256 chains x 2 MCMC iterations x 20 leapfrog steps against
+  the chain the REAL reference produced (tests/golden/hmc_d16_k10k.npz, oracle/make_golden_k10k.py),
+  free-running and teacher-forced, identical accept decisions;
+* BASELINE.json configs[4]: d = 64, K = 50,000: 32 points in chunks of 4 (3.3 GB oracle intermediate).
+
+Tolerances are north_star's: rel 1e-5 (per-matrix Frobenius) on G^{-1} and G, 1e-4 on log det and
+gradients, identical HMC accept decisions for a fixed RNG stream.
+"""
+import pytest
+import torch
+
+from conftest import load_golden, rel_fro
+from oracle import metric_oracle as O
+from test_gpu_parity import TOL_LD, TOL_MAT, close_ld, dev, make_mt
+
+pytestmark = pytest.mark.gpu
+
+
+def _bench_tables(temperature=None):
+    from rlvae_b200.synthetic import make_synthetic_metric
+    sm = make_synthetic_metric(10000, 16, seed=0)
+    T = sm.temperature if temperature is None else temperature
+    return (sm.centroids, sm.metric_matrices, T, sm.regularization)
+
+
+def _oracle_all(z, t, chunk):
+    """G^{-1}, G, log det G, grad_z log det G the way the reference computes them, chunked to bound
+    the [n,K,d,d] intermediate (metric_tensor.py:98-182; gradient = closed form of autograd, checked
+    against autograd in tests/test_oracle_golden.py)."""
+    ginv = O.chunked(O.inverse_metric, z, *t, chunk=chunk)
+    g = torch.linalg.inv(ginv)
+    ld = torch.linalg.slogdet(g).logabsdet
+    grad = -2.0 * O.chunked(O.grad_log_sqrt_det_ginv_exact, z, *t, chunk=chunk)
+    return ginv, g, ld, grad
+
+
+def test_k10k_tensor_path_against_oracle_4096_points():
+    from rlvae_b200.synthetic import make_points
+    t = _bench_tables()
+    z = make_points(1 << 20, 16, seed=1)[:4096].contiguous()      # the first 4,096 points of bench.py's input
+    mt = make_mt(t, 'tensor')
+    tab = mt._tables(dev())
+    assert tab.tensor_auto and tab.symmetric and tab.weight_mode == 0
+    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    ginv, g, ld, grad = _oracle_all(z, t, chunk=512)
+    assert rel_fro(ev['ginv'].cpu(), ginv) < TOL_MAT
+    assert rel_fro(ev['g'].cpu(), g) < TOL_MAT
+    close_ld(ev['logdet_g'], ld)
+    assert rel_fro(ev['grad_logdet_g'].cpu(), grad) < TOL_LD
+    # the public single-output entry points take the same kernels
+    assert rel_fro(mt.compute_inverse_metric(z[:512].to(dev())).cpu(), ginv[:512]) < TOL_MAT
+    assert rel_fro(mt.compute_metric(z[:512].to(dev())).cpu(), g[:512]) < TOL_MAT
+    close_ld(mt.compute_log_det_metric(z[:512].to(dev())), ld[:512])
+
+
+def test_k10k_small_temperature_hybrid_against_oracle():
+    """T = 0.7 (conf/model/hybrid_rlvae.yaml:41) at K = 10k: log det and gradient too, against the
+    oracle.  Half of the points sit next to centroids (otherwise every weight underflows and
+    G^{-1} = lambda I, which tests nothing)."""
+    from rlvae_b200.synthetic import make_points
+    t = _bench_tables(temperature=0.7)
+    c = t[0]
+    z = torch.cat([make_points(512, 16, seed=1), c[:512] + 0.05 * make_points(512, 16, seed=2)]).contiguous()
+    mt = make_mt(t, 'auto')
+    assert mt._tables(dev()).weight_mode == 2
+    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    ginv, g, ld, grad = _oracle_all(z, t, chunk=256)
+    assert rel_fro(ev['ginv'].cpu(), ginv) < TOL_MAT
+    assert rel_fro(ev['g'].cpu(), g) < TOL_MAT
+    close_ld(ev['logdet_g'], ld)
+    live = grad.norm(dim=1) > 1e-6 * grad.norm(dim=1).max()
+    assert live.sum() > 300
+    assert rel_fro(ev['grad_logdet_g'].cpu()[live], grad[live]) < TOL_LD
+
+
+def test_hmc_k10k_matches_the_reference_chain():
+    """256 chains x 2 MCMC iterations x n_lf = 20 at K = 10,000 against RiemannianHMCSampler.sample of
+    the real reference (golden): free-running final state, then per-iteration teacher forcing with
+    identical accept decisions (a flip only where acc sits within rounding of alpha; count must be 0)."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler
+    g = load_golden('hmc_d16_k10k')
+    t = _bench_tables()
+    assert int(g['n_centroids']) == t[0].shape[0]
+    iters, n_lf = g['gamma'].shape[0], int(g['n_lf'])
+    s = RiemannianHMCSampler(MetricModel(make_mt(t, 'auto')), mcmc_steps_nbr=iters, n_lf=n_lf,
+                             eps_lf=float(g['eps_lf']), beta_zero=float(g['beta_zero']))
+    D = lambda k: g[k].to(dev())
+    zf = s.sample_with_streams(D('z0'), D('gamma'), D('acc'))
+    # chains whose decisions all sat clear of alpha must end where the reference's ended
+    clear = ((g['acc'] - g['rec_alpha']).abs() > 1e-4).all(dim=0)
+    assert clear.float().mean() > 0.95
+    torch.testing.assert_close(zf.cpu()[clear], g['z_final'][clear], rtol=2e-4, atol=2e-4)
+    forced = [g['z0']] + [g['rec_z'][i] for i in range(iters - 1)]
+    got = {}
+    s.sample_with_streams(D('z0'), D('gamma'), D('acc'), z_forced=[f.to(dev()) for f in forced], record=got)
+    mism = 0
+    for i in range(iters):
+        close_ld(got['H0'][i], g['rec_H0'][i], 1e-4)
+        close_ld(got['H'][i], g['rec_H'][i], 1e-4)
+        flip = got['moves'][i].cpu() != g['rec_moves'][i]
+        assert torch.all((g['acc'][i][flip] - g['rec_alpha'][i][flip]).abs() < 1e-5)
+        mism += int(flip.sum())
+        torch.testing.assert_close(got['z'][i].cpu()[~flip], g['rec_z'][i][~flip], rtol=1e-4, atol=1e-4)
+    assert mism == 0, f'{mism} accept decisions differ'
+
+
+def test_d64_k50k_against_oracle():
+    """BASELINE.json configs[4] tables (d = 64, K = 50,000): G^{-1}, log det G and grad_z log det G on
+    32 points against the oracle in chunks of 4 (the reference's [n,K,d,d] intermediate is 3.3 GB per
+    chunk), plus a ragged 129-point batch for tile tails against the first rows."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(50000, 64, seed=5, n_probe=128)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    z = make_points(129, 64, seed=6)
+    mt = make_mt(t, 'tensor')
+    assert mt._tables(dev()).tensor_auto
+    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=False, want_logdet=True, want_grad=True)
+    zr = z[:32]
+    ginv = O.chunked(O.inverse_metric, zr, *t, chunk=4)
+    ld = -torch.linalg.slogdet(ginv).logabsdet
+    grad = -2.0 * O.chunked(O.grad_log_sqrt_det_ginv_exact, zr, *t, chunk=4)
+    assert rel_fro(ev['ginv'][:32].cpu(), ginv) < TOL_MAT
+    close_ld(ev['logdet_g'][:32], ld)
+    assert rel_fro(ev['grad_logdet_g'][:32].cpu(), grad) < TOL_LD
+    one = mt.evaluate(z[:32].to(dev()), want_ginv=True, want_logdet=True, want_grad=True)
+    assert rel_fro(one['ginv'].cpu(), ev['ginv'][:32].cpu()) < 1e-6
