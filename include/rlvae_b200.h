@@ -41,7 +41,8 @@ enum {
 /* log_pi / gradient flavours of the HMC sampler */
 enum {
   RLVAE_GRAD_MODULAR = 0, /* ref: src/models/samplers/hmc_sampler.py:33-68  == (1 - lambda*G_ii)/T^2 */
-  RLVAE_GRAD_EXACT   = 1  /* grad_z 1/2 log det G^{-1}  (autograd of hmc_sampler.py:26-30)           */
+  RLVAE_GRAD_EXACT   = 1, /* grad_z 1/2 log det G^{-1}  (autograd of hmc_sampler.py:26-30)           */
+  RLVAE_HMC_NO_FUSION = 256 /* flag, OR-ed into grad_mode: per-step launches instead of the fused trajectory */
 };
 
 const char* rlvae_last_error(void);
@@ -146,6 +147,27 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
                         int64_t n, int n_lf, float eps_lf, float beta_zero_sqrt,
                         const float* h_scales, int grad_mode, float* h0, float* h1, float* alpha,
                         float* moves, void* work, int path, void* stream);
+/* Fused trajectory (north_star "one leapfrog-step kernel advances many HMC chains per launch"): when
+ * rlvae_hmc_fused_available(t, grad_mode, path) != 0 (d == 16, symmetric tables certified positive
+ * semi-definite with lambda > 0, RLVAE_GRAD_MODULAR, n_lf <= 64 for rlvae_hmc_iteration) the whole
+ * iteration -- all n_lf + 1 metric evaluations, the momentum / position updates of lines 127-148 and
+ * the accept step of lines 153-162 -- is ONE kernel launch: a CTA pair keeps its 256 chains' z and
+ * rho_half on chip for the entire trajectory.  The int32 at byte offset
+ * rlvae_hmc_workspace(n,d) - 256 of `work` then counts chain-steps whose G^{-1} lost positive
+ * definiteness to rounding (cond(G^{-1}) beyond ~1e5; log_pi takes its clamp value there); callers
+ * that care re-run with RLVAE_HMC_FUSED=0 in the environment (per-step launches + pivoting fallback).
+ *
+ * rlvae_hmc_run: n_iters MCMC iterations (the loop of lines 120-163) in one call -- one launch on the
+ * fused path.  gammas [n_iters,N,d], accs [n_iters,N], h_scales [n_iters*n_lf] (HOST; the tempering
+ * state carries over between iterations like the reference's beta_sqrt_old, line 116).  Optional
+ * outputs h0/h1/alpha/moves [n_iters,N] and z_trace [n_iters,N,d] (the state after every iteration).
+ * work: rlvae_hmc_run_workspace(n, d, n_iters, n_lf) bytes.                                   */
+int     rlvae_hmc_fused_available(const rlvae_tables_t* t, int grad_mode, int path);
+int64_t rlvae_hmc_run_workspace(int64_t n, int d, int n_iters, int n_lf);
+int rlvae_hmc_run(const rlvae_tables_t* t, float* z, const float* gammas, const float* accs, int64_t n,
+                  int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* h_scales,
+                  int grad_mode, float* h0, float* h1, float* alpha, float* moves, float* z_trace,
+                  void* work, int path, void* stream);
 
 /* ---- A13: z <- z + step * (-grad_func(z)), n_steps times (variant A) -------------------------
  * ref: src/models/samplers/hmc_sampler.py:242-257.  In/out z [N,d].                           */

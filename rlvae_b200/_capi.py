@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'librlvae_b200.so')
 
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
 GRAD_MODULAR, GRAD_EXACT = 0, 1
+HMC_NO_FUSION = 256      # flag OR-ed into grad_mode: per-step launches instead of the fused trajectory kernel
 
 # every symbol include/rlvae_b200.h declares: (name, restype, argtypes)
 _SIGNATURES = [
@@ -43,6 +44,11 @@ _SIGNATURES = [
     ('rlvae_hmc_iteration', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float,
                                     POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_void_p]),
+    ('rlvae_hmc_fused_available', c_int, [c_void_p, c_int, c_int]),
+    ('rlvae_hmc_run_workspace', c_int64, [c_int64, c_int, c_int, c_int]),
+    ('rlvae_hmc_run', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float,
+                              POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_void_p]),
     ('rlvae_hmc_refine', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int, c_void_p]),
     ('rlvae_nearest2', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ('rlvae_chol_apply', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -331,6 +337,48 @@ def hmc_iteration(tab: Tables, z: torch.Tensor, gamma: torch.Tensor, acc: torch.
                                          _ptr(stats[2]), _ptr(stats[3]), _ptr(work), path, _stream(z)),
                'rlvae_hmc_iteration')
     return tuple(stats) if want_stats else None
+
+
+def hmc_fused_available(tab: Tables, grad_mode: int = GRAD_MODULAR, path: int = PATH_AUTO) -> bool:
+    """True when rlvae_hmc_iteration / rlvae_hmc_run take the single-launch trajectory kernel."""
+    return bool(lib().rlvae_hmc_fused_available(tab.handle, grad_mode, path))
+
+
+def hmc_fail_count(work: torch.Tensor, n: int, d: int) -> torch.Tensor:
+    """View of the fused kernel's rounding-failure counter inside an HMC workspace (0-dim int32)."""
+    off = int(lib().rlvae_hmc_workspace(n, d)) - 256
+    return work[off:off + 4].view(torch.int32)[0]
+
+
+def hmc_run(tab: Tables, z: torch.Tensor, gammas: torch.Tensor, accs: torch.Tensor, n_lf: int, eps_lf: float,
+            beta_zero_sqrt: float, scales, grad_mode: int = GRAD_MODULAR, path: int = PATH_AUTO,
+            want_stats: bool = False, want_trace: bool = False, work: torch.Tensor | None = None):
+    """n_iters = gammas.shape[0] MCMC iterations in place on ``z`` -- ONE launch on the fused path.
+    scales: n_iters * n_lf floats (host).  Returns dict(work, stats=(h0,h1,alpha,moves) each [I,n], trace [I,n,d])."""
+    if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
+        raise RuntimeError('hmc_run: z must be a contiguous fp32 CUDA tensor (updated in place)')
+    _req_z(tab, z)
+    n, d = z.shape
+    gammas = _req(gammas, 'gammas')
+    accs = _req(accs, 'accs')
+    iters = int(gammas.shape[0])
+    if tuple(gammas.shape) != (iters, n, d) or tuple(accs.shape) != (iters, n) or gammas.device != z.device \
+            or accs.device != z.device:
+        raise ValueError(f'hmc_run: gammas must be [I, {n}, {d}] and accs [I, {n}] on {z.device}')
+    if len(scales) != iters * n_lf:
+        raise ValueError(f'hmc_run: need {iters * n_lf} tempering scales, got {len(scales)}')
+    need = int(lib().rlvae_hmc_run_workspace(n, d, iters, n_lf))
+    if work is None or work.numel() < need or work.device != z.device:
+        work = torch.empty(max(need, 1), device=z.device, dtype=torch.uint8)
+    sc = (c_float * max(len(scales), 1))(*[float(x) for x in scales])
+    stats = [torch.empty((iters, n), device=z.device) for _ in range(4)] if want_stats else [None] * 4
+    trace = torch.empty((iters, n, d), device=z.device) if want_trace else None
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_hmc_run(tab.handle, _ptr(z), _ptr(gammas), _ptr(accs), n, iters, n_lf, c_float(eps_lf),
+                                   c_float(beta_zero_sqrt), sc, grad_mode, _ptr(stats[0]), _ptr(stats[1]),
+                                   _ptr(stats[2]), _ptr(stats[3]), _ptr(trace), _ptr(work), path, _stream(z)),
+               'rlvae_hmc_run')
+    return dict(work=work, stats=tuple(stats) if want_stats else None, trace=trace)
 
 
 def hmc_refine(tab: Tables, z: torch.Tensor, n_steps: int, step_size: float, path: int = PATH_AUTO):

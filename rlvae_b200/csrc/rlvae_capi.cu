@@ -793,9 +793,35 @@ int rlvae_local_covariance(const float* latents, int64_t n, const float* centroi
                                  static_cast<cudaStream_t>(stream));
 }
 
-int64_t rlvae_hmc_workspace(int64_t n, int d) {
+static int64_t hmc_core_floats(int64_t n, int d) {
   // ginv, g (exact mode), diag, rho_half, z_prev, grad, logabsdet, sign, h0
-  return (int64_t)sizeof(float) * (2 * n * d * d + 4 * n * d + 3 * n);
+  return 2 * n * d * d + 4 * n * d + 3 * n;
+}
+
+int64_t rlvae_hmc_workspace(int64_t n, int d) {
+  // + 64 ints: [0] = the fused trajectory kernel's rounding-failure counter (see rlvae_hmc_iteration)
+  return (int64_t)sizeof(float) * (hmc_core_floats(n, d) + 64);
+}
+
+int64_t rlvae_hmc_run_workspace(int64_t n, int d, int n_iters, int n_lf) {
+  return rlvae_hmc_workspace(n, d) + (int64_t)sizeof(float) * (((int64_t)n_iters * n_lf + 63) / 64 * 64);
+}
+
+// RLVAE_HMC_FUSED=0 keeps the per-step launches (A/B and debugging); read per call
+static bool hmc_fused_enabled() {
+  const char* e = getenv("RLVAE_HMC_FUSED");
+  return !(e != nullptr && e[0] == '0');
+}
+
+static bool hmc_use_fused(const rlvae_tables* t, int grad_mode, int path) {
+  if (grad_mode & RLVAE_HMC_NO_FUSION) return false;
+  bool packed = false;
+  if (sym_tensor_path(t, path, &packed) != 0 || !packed) return false;
+  return grad_mode == RLVAE_GRAD_MODULAR && use_h16(t) && h16_hmc_available(t) && hmc_fused_enabled();
+}
+
+int rlvae_hmc_fused_available(const rlvae_tables_t* t, int grad_mode, int path) {
+  return (t != nullptr && hmc_use_fused(t, grad_mode, path)) ? 1 : 0;
 }
 
 int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, const float* acc,
@@ -806,6 +832,8 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   RLVAE_REQUIRE(n >= 0 && n_lf >= 1, "hmc_iteration: need n >= 0 and n_lf >= 1");
   if (n == 0) return 0;
   RLVAE_REQUIRE(z && gamma && acc && h_scales && work, "hmc_iteration: NULL pointer");
+  const int grad_mode_flags = grad_mode;
+  grad_mode &= ~RLVAE_HMC_NO_FUSION;
   RLVAE_REQUIRE(grad_mode == RLVAE_GRAD_MODULAR || grad_mode == RLVAE_GRAD_EXACT,
                 "hmc_iteration: unknown grad_mode");
   const int d = t->d;
@@ -822,9 +850,16 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   float* h0 = sgn + n;
   const bool exact = grad_mode == RLVAE_GRAD_EXACT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* fused_fail = reinterpret_cast<int*>(w + hmc_core_floats(n, d));
+  RLVAE_CUDA_OK(cudaMemsetAsync(fused_fail, 0, sizeof(int), s));
 
   bool packed = false;
   if (int rc = sym_tensor_path(t, path, &packed)) return rc;
+  if (n_lf <= 64 && hmc_use_fused(t, grad_mode_flags, path)) {
+    // ONE launch: every CTA pair keeps its 256 chains on chip for the n_lf + 1 metric evaluations
+    return launch_hmc_trajectory_h16(t, z, gamma, acc, n, 1, n_lf, eps_lf, beta_zero_sqrt, nullptr, h_scales,
+                                     h0_out, h1, alpha, moves, nullptr, fused_fail, s);
+  }
   // one metric evaluation at the chain's current position: G^{-1}, then diag(G)/log|det|
   auto eval = [&](const float* zz) -> int {
     if (packed) {   // fused forward + per-thread Cholesky; the gradient contracts packed G
@@ -857,6 +892,40 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
   }
   if (h0_out != nullptr)
     RLVAE_CUDA_OK(cudaMemcpyAsync(h0_out, h0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int rlvae_hmc_run(const rlvae_tables_t* t, float* z, const float* gammas, const float* accs, int64_t n,
+                  int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* h_scales,
+                  int grad_mode, float* h0, float* h1, float* alpha, float* moves, float* z_trace,
+                  void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "hmc_run: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0 && n_lf >= 1 && n_iters >= 0, "hmc_run: need n >= 0, n_lf >= 1, n_iters >= 0");
+  if (n == 0 || n_iters == 0) return 0;
+  RLVAE_REQUIRE(z && gammas && accs && h_scales && work, "hmc_run: NULL pointer");
+  const int d = t->d;
+  float* w = static_cast<float*>(work);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (hmc_use_fused(t, grad_mode, path)) {
+    int* fused_fail = reinterpret_cast<int*>(w + hmc_core_floats(n, d));
+    float* scales_dev = w + hmc_core_floats(n, d) + 64;
+    RLVAE_CUDA_OK(cudaMemsetAsync(fused_fail, 0, sizeof(int), s));
+    RLVAE_CUDA_OK(cudaMemcpyAsync(scales_dev, h_scales, sizeof(float) * (size_t)n_iters * n_lf,
+                                  cudaMemcpyHostToDevice, s));
+    return launch_hmc_trajectory_h16(t, z, gammas, accs, n, n_iters, n_lf, eps_lf, beta_zero_sqrt, scales_dev,
+                                     nullptr, h0, h1, alpha, moves, z_trace, fused_fail, s);
+  }
+  for (int i = 0; i < n_iters; ++i) {
+    if (int rc = rlvae_hmc_iteration(t, z, gammas + (int64_t)i * n * d, accs + (int64_t)i * n, n, n_lf, eps_lf,
+                                     beta_zero_sqrt, h_scales + (int64_t)i * n_lf, grad_mode,
+                                     h0 ? h0 + (int64_t)i * n : nullptr, h1 ? h1 + (int64_t)i * n : nullptr,
+                                     alpha ? alpha + (int64_t)i * n : nullptr,
+                                     moves ? moves + (int64_t)i * n : nullptr, work, path, stream))
+      return rc;
+    if (z_trace != nullptr)
+      RLVAE_CUDA_OK(cudaMemcpyAsync(z_trace + (int64_t)i * n * d, z, sizeof(float) * (size_t)n * d,
+                                    cudaMemcpyDeviceToDevice, s));
+  }
   return 0;
 }
 

@@ -175,6 +175,13 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
                               int* fail_ws, cudaStream_t s, float* a_full = nullptr, float* g_full = nullptr,
                               int a_packed_wanted = 1);
+// single-launch HMC trajectory (variant-A drift): n_iters MCMC iterations, chain state on chip.
+// scales_dev [n_iters * n_lf] (device) or, for n_iters == 1 and n_lf <= 64, h_scales (host).
+int h16_hmc_available(const rlvae_tables* t);
+int launch_hmc_trajectory_h16(const rlvae_tables* t, float* z, const float* gamma, const float* acc, int64_t n,
+                              int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* scales_dev,
+                              const float* h_scales, float* h0, float* h1, float* alpha, float* moves,
+                              float* z_trace, int* fail_count, cudaStream_t s);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,

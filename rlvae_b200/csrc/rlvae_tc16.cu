@@ -73,7 +73,13 @@ constexpr uint32_t OFF_C = OFF_A2 + A_BYTES;
 constexpr uint32_t OFF_M = OFF_C + C_STAGES * C_TILE_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
-constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + 3;   // + 3 pipe-trace barriers (profiling builds)
+constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + 3 + 2;   // + 3 pipe-trace barriers (profiling builds)
+                                                                                   // + 2 "next position ready" barriers (HMC mode)
+// HMC mode: per-chain state rows in the (otherwise unused) A-tile region of shared memory:
+// [0,16) z, [16,32) rho_half, [32] zb, [33] s_scale
+constexpr int ST_LD = 36;
+constexpr uint32_t OFF_STATE = OFF_A1;
+static_assert(TILE_M * ST_LD * 4 <= 2 * A_BYTES, "HMC state rows must fit the A-tile region");
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -161,6 +167,37 @@ struct FusedOut {
   float lad_scale;
 };
 
+// HMC mode of the forward kernel: ONE launch runs n_iters MCMC iterations of
+// RiemannianHMCSampler.sample (ref src/models/samplers/hmc_sampler.py:120-163) for the 128 chains of
+// the CTA -- n_lf + 1 metric evaluations per iteration, the chain state (z, rho_half) in shared memory /
+// registers of the owning thread, the update / accept arithmetic in the fold group's epilogue, which
+// already holds diag(G) and log det.  Only the variant-A drift (1 - lambda G_ii)/T^2 is fusable (the
+// exact gradient needs the second contraction kernel).
+struct HmcArgs {
+  float* z;              // [N,16] in: chain state; out: accepted state (re-read as z_prev at every accept step)
+  const float* gamma;    // [n_iters, N, 16]  draws of hmc_sampler.py:122
+  const float* acc;      // [n_iters, N]      draws of hmc_sampler.py:158
+  const float* scales;   // [n_iters * n_lf] device, or NULL -> scales_inl (n_iters == 1)
+  float* h0;             // [n_iters, N] or NULL
+  float* h1;             // [n_iters, N] or NULL
+  float* alpha;          // [n_iters, N] or NULL
+  float* moves;          // [n_iters, N] or NULL
+  float* z_trace;        // [n_iters, N, 16] accepted state after every iteration, or NULL
+  int* fail_count;       // incremented when a Cholesky pivot is not positive (certified tables: rounding only)
+  int n_iters, n_lf;
+  float eps, b0, T2;
+  float scales_inl[64];
+};
+
+// 0.5*log(clamp(det G^{-1}, 1e-10)) from log det (the fused Cholesky only succeeds for det > 0);
+// same arithmetic as log_pi_from_slogdet in rlvae_hmc.cu -- ref hmc_sampler.py:26-30
+__device__ __forceinline__ float hmc_log_pi(float lad, bool pos) {
+  const float floor_lp = 0.5f * logf(1e-10f);
+  if (!pos) return floor_lp;
+  if (lad > 88.72283f) return INFINITY;
+  return fmaxf(0.5f * lad, floor_lp);
+}
+
 // EXACT: the weights come from exact differences sum_j (z_j - c_kj)^2 formed by the exp threads on the
 // FMA pipe (packed fp32x2, natural centroid rows broadcast from shared memory) instead of the
 // expanded form on the tensor core.  No GEMM1, no accuracy gate on T: this is the mode for small
@@ -170,7 +207,7 @@ struct FusedOut {
 // hyb_thr -- the only ones large enough for the expanded form's absolute exponent error to matter in
 // G^{-1} (see h16_mode) -- is recomputed from exact differences (natural centroid rows through L1).  At
 // small T almost every weight is far below the threshold, so this keeps most of the tensor-core speed.
-template <bool PAIR, bool EXACT, bool HYBRID>
+template <bool PAIR, bool EXACT, bool HYBRID, bool HMC = false>
 __global__ void __launch_bounds__(h16::THREADS, 1)
 inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           const __grid_constant__ CUtensorMap tm_mh_hi,
@@ -180,10 +217,15 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                           int num_blocks, float alpha /* log2(e)/T^2 */, float lambda,
                           float out_scale /* 2^-(14+e) */, float c_unscale /* 2^-ec */,
                           const float* __restrict__ cshift /* [16] centre of the expanded form */,
-                          float hyb_thr /* HYBRID: refine weights with log2(2^14 w) above this */, FusedOut fo) {
+                          float hyb_thr /* HYBRID: refine weights with log2(2^14 w) above this */, FusedOut fo,
+                          const __grid_constant__ HmcArgs hm) {
 #ifdef RLVAE_TC_PROFILE
   const long long pk0 = clock64();
 #endif
+  // HMC: the main loop runs over ALL evaluations of the trajectory as one long block sequence
+  // (num_blocks is even, so chunk / stage / buffer phases simply continue across evaluations)
+  const int n_evals = HMC ? hm.n_iters * (hm.n_lf + 1) : 1;
+  const int total_blocks = n_evals * num_blocks;
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
                 M_STAGES = h16::M_STAGES, AHEAD = h16::AHEAD, NCOLS = h16::NCOLS;
@@ -209,6 +251,12 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 2 + b); };
   auto BAR_MON = [&](int b) { return bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + b); };
   (void)BAR_MON;
+  // HMC: the fold group publishes the next position -- BAR_ZR: z' in TMEM, for the MMA issuer (leader's
+  // barrier, both CTAs of a pair arrive); BAR_ZL: zb / s_scale / z in shared memory, for this CTA's exp groups
+  const uint32_t BAR_ZR = bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 7);
+  const uint32_t BAR_ZL = bar0 + 8u * (3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 8);
+  float* const state = reinterpret_cast<float*>(gbase + h16::OFF_STATE);
+  constexpr int ST_LD = h16::ST_LD;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + h16::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -232,6 +280,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR); }
     for (int b = 0; b < 3; ++b) mbar_init(BAR_MON(b), 1);
+    mbar_init(BAR_ZR, 4 * NPAIR);
+    mbar_init(BAR_ZL, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cstack) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mh_hi) : "memory");
@@ -265,12 +315,18 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
     for (int j = 0; j < 16; ++j) zv[j] = 0.f;
     if (r < n) {
-      const float4* src = reinterpret_cast<const float4*>(z + r * 16);
+      const float4* src = reinterpret_cast<const float4*>((HMC ? hm.z : z) + r * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v = __ldg(src + q);
+        const float4 v = HMC ? src[q] : __ldg(src + q);      // HMC: z is rewritten by this kernel
         zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
       }
+    }
+    if (HMC && wg == 1) {            // the chain's position for the fold thread that owns it
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(state + prow * ST_LD + 4 * q) =
+            make_float4(zv[4 * q], zv[4 * q + 1], zv[4 * q + 2], zv[4 * q + 3]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) nz[j] = make_float2(-zv[2 * j], -zv[2 * j + 1]);
@@ -316,9 +372,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     reg_dec<72>();
     if (warp == 0) {
       // =========================================================== TMA producer 1: centroid tiles + bias
-      for (int j = 0; j < num_blocks; ++j) {
-        const int cs = j % C_STAGES;
-        mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      for (int jg = 0, j = 0; jg < total_blocks; ++jg, j = (j + 1 == num_blocks) ? 0 : j + 1) {   // j: block within the evaluation
+        const int cs = jg % C_STAGES;
+        mbar_wait(BAR_C_EMPTY(cs), ((jg / C_STAGES) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t dst = base + h16::OFF_C + cs * C_TILE_BYTES;
           if (EXACT) {      // natural rows of the 64 centroids (4 KB) + mask, both for this CTA's exp groups
@@ -341,9 +397,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     } else if (warp == 2) {
       // =========================================================== TMA producer 2: M tiles, as far ahead
       // as the ring allows (its own warp: a stalled centroid stage must not delay the table stream)
-      for (int jm = 0; jm < num_blocks; ++jm) {
-        const int ms = jm % M_STAGES;
-        mbar_wait(BAR_M_EMPTY(ms), ((jm / M_STAGES) & 1) ^ 1);
+      for (int jg = 0, jm = 0; jg < total_blocks; ++jg, jm = (jm + 1 == num_blocks) ? 0 : jm + 1) {
+        const int ms = jg % M_STAGES;
+        mbar_wait(BAR_M_EMPTY(ms), ((jg / M_STAGES) & 1) ^ 1);
         if (elect_one()) {
           if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * 2 * TILE_BYTES);
           const uint32_t dst = base + h16::OFF_M + ms * M_TILE_BYTES;
@@ -391,12 +447,16 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         __syncwarp();
       };
       uint32_t free_phase = 0;     // bit ab: parity of the next CH_FREE(ab) completion to wait for
-      auto block = [&](auto Jc, const int j, const uint32_t qodd /* (j / 6) & 1 */) {
+      int jl = 0, ev = 0;          // HMC: block index within the current evaluation, evaluation index
+      // jg: global block index (== block within the evaluation unless HMC); the unrolled position J only
+      // fixes stage / buffer indices and parities, which continue across evaluations
+      auto block = [&](auto Jc, const int jg, const uint32_t qodd /* (jg / 6) & 1 */) {
         constexpr int J = decltype(Jc)::value;
         constexpr int first = (J % CB) == 0, sb = J % SP_BUFS;
         const uint32_t ab = ((J / CB) & 1) ^ qodd;          // 6 blocks = 3 chunks: the accumulator parity flips every pass
         constexpr int ms = J % M_STAGES;
-        if (first && j >= 2 * CB) {                       // fold group drained this accumulator
+        const int j = HMC ? jl : jg;
+        if (first && jg >= 2 * CB) {                      // fold group drained this accumulator
           mbar_wait(BAR_CH_FREE(ab), (free_phase >> ab) & 1u);
           free_phase ^= 1u << ab;
         }
@@ -412,7 +472,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         }
         __syncwarp();
         // inputs of the NEXT steps, waited for behind queued MMAs (normally long complete)
-        if (j + 1 < num_blocks) mbar_wait(BAR_M_FULL((J + 1) % M_STAGES), ((J + 1) / M_STAGES) & 1);
+        if (jg + 1 < total_blocks) mbar_wait(BAR_M_FULL((J + 1) % M_STAGES), ((J + 1) / M_STAGES) & 1);
         if (!EXACT && j + AHEAD < num_blocks) mbar_wait(BAR_C_FULL((J + AHEAD) % C_STAGES), ((J + AHEAD) / C_STAGES) & 1);
         if (elect_one()) {
 #pragma unroll
@@ -429,7 +489,27 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           tc_fence_after();
           gemm1(std::integral_constant<int, (J + AHEAD) % C_STAGES>{}, std::integral_constant<int, (J + AHEAD) % SP_BUFS>{});
         }
-        if (j + 1 < num_blocks) mbar_wait(BAR_P_FULL((J + 1) % SP_BUFS), ((J + 1) / SP_BUFS) & 1);
+        if (HMC && j == num_blocks - 1 && jg + 1 < total_blocks) {
+          // last block of an evaluation: the distance GEMMs of the next one need the chains' new
+          // positions, which the fold group publishes after its epilogue (z' in TMEM of both CTAs)
+          mbar_wait(BAR_ZR, (uint32_t)ev & 1u);
+          tc_fence_after();
+          if (1 <= num_blocks) {
+            if (!EXACT) mbar_wait(BAR_C_FULL((J + 1) % C_STAGES), ((J + 1) / C_STAGES) & 1);
+            gemm1(std::integral_constant<int, (J + 1) % C_STAGES>{}, std::integral_constant<int, (J + 1) % SP_BUFS>{});
+          }
+          if (2 <= num_blocks) {
+            if (!EXACT) mbar_wait(BAR_C_FULL((J + 2) % C_STAGES), ((J + 2) / C_STAGES) & 1);
+            gemm1(std::integral_constant<int, (J + 2) % C_STAGES>{}, std::integral_constant<int, (J + 2) % SP_BUFS>{});
+          }
+          if (3 <= num_blocks) {
+            if (!EXACT) mbar_wait(BAR_C_FULL((J + 3) % C_STAGES), ((J + 3) / C_STAGES) & 1);
+            gemm1(std::integral_constant<int, (J + 3) % C_STAGES>{}, std::integral_constant<int, (J + 3) % SP_BUFS>{});
+          }
+        }
+        if (jg + 1 < total_blocks && (HMC || j + 1 < num_blocks))
+          mbar_wait(BAR_P_FULL((J + 1) % SP_BUFS), ((J + 1) / SP_BUFS) & 1);
+        if (HMC) { if (++jl == num_blocks) { jl = 0; ++ev; } }
       };
       // prologue: GEMM1 of the first AHEAD (= 3) blocks
       if (0 < num_blocks) { if (!EXACT) mbar_wait(BAR_C_FULL(0), 0); tc_fence_after(); gemm1(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{}); }
@@ -440,8 +520,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       static_assert(6 % CB == 0 && 6 % SP_BUFS == 0 && 6 % C_STAGES == 0 && 6 % M_STAGES == 0 && AHEAD == 3,
                     "the 6x unrolled issue loop assumes these periods");
       uint32_t qodd = 0;
-      for (int j0 = 0; j0 < num_blocks; j0 += 6, qodd ^= 1u) {
-#define RLVAE_BLK(J) if (j0 + J < num_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
+      for (int j0 = 0; j0 < total_blocks; j0 += 6, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < total_blocks) block(std::integral_constant<int, J>{}, j0 + J, qodd);
         RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3) RLVAE_BLK(4) RLVAE_BLK(5)
 #undef RLVAE_BLK
       }
@@ -455,12 +535,30 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     (void)pe_wait; (void)pe_work;
     // COLSPLIT: both groups work on every super-block, 32 centroids each (halves the latency between
     // GEMM1(j) and GEMM2(j)); otherwise the groups alternate whole super-blocks
-    for (int j = COLSPLIT ? 0 : grp; j < num_blocks; j += COLSPLIT ? 1 : 2) {
+    int ev_cur = 0;                 // HMC: evaluation whose per-point constants this thread holds
+    for (int jg = COLSPLIT ? 0 : grp; jg < total_blocks; jg += COLSPLIT ? 1 : 2) {
       PROF_T0();
-      const int cs = j % C_STAGES, sb = j % SP_BUFS;
+      int j = jg;                   // block within the evaluation (selects the table rows)
+      if (HMC) {
+        const int e = jg / num_blocks;
+        j = jg - e * num_blocks;
+        if (e != ev_cur) {          // first block of a new evaluation: the chain has moved
+          ev_cur = e;
+          mbar_wait(BAR_ZL, (uint32_t)(e - 1) & 1u);
+          const float* st = state + prow * ST_LD;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 v = *reinterpret_cast<const float2*>(st + 2 * q);
+            nz[q] = make_float2(-v.x, -v.y);
+          }
+          zb = st[32];
+          s_scale = st[33];
+        }
+      }
+      const int cs = jg % C_STAGES, sb = jg % SP_BUFS;
       const uint32_t sp = tmem_base + lane_addr + TM_SP + sb * 64;
-      mbar_wait(BAR_BIAS_FULL(cs), (j / C_STAGES) & 1);
-      mbar_wait(BAR_S_FULL(sb), (j / SP_BUFS) & 1);
+      mbar_wait(BAR_BIAS_FULL(cs), (jg / C_STAGES) & 1);
+      mbar_wait(BAR_S_FULL(sb), (jg / SP_BUFS) & 1);
       tc_fence_after();
       if (quarter == 0) HTRACE(3, j);
       PROF_ADD(pe_wait);
@@ -551,7 +649,13 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #ifdef RLVAE_TC_PROFILE
     const long long pf0 = clock64();
 #endif
-    for (int c = 0; c < num_chunks; ++c) {
+    const int total_chunks = n_evals * num_chunks;
+    const int64_t rows_here = (n - row0 < TILE_M) ? ((n - row0 > 0) ? (n - row0) : 0) : TILE_M;   // 0 for a pair's padding tile
+    const bool live = prow < rows_here;
+    float h0_keep = 0.f;             // HMC: H0 of the running MCMC iteration
+    for (int ev = 0, cg0 = 0; ev < n_evals; ++ev, cg0 += num_chunks) {
+    for (int cl = 0; cl < num_chunks; ++cl) {
+      const int c = cg0 + cl;        // global chunk index: accumulator / phase bookkeeping continues across evaluations
       PROF_T0();
       const int ab = c & 1;
       mbar_wait(BAR_CH_FULL(ab), (c >> 1) & 1);
@@ -574,7 +678,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int i = 0; i < 16; ++i) total[128 + i] += __uint_as_float(a[i]);
       }
-      if (c + 2 < num_chunks) {
+      if (c + 2 < total_chunks) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(ab)); else mbar_arrive(BAR_CH_FREE(ab)); }
@@ -585,15 +689,168 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #ifdef RLVAE_TC_PROFILE
     const long long pf1 = clock64();     // (printed after the epilogue: a printf here would be timed as epilogue)
 #endif
-    // ---------------------------------------------------------- epilogue (all TMA / MMA work is complete)
-    const int64_t rows_here = (n - row0 < TILE_M) ? ((n - row0 > 0) ? (n - row0) : 0) : TILE_M;   // 0 for a pair's padding tile
-    const bool live = prow < rows_here;
+    // ---------------------------------------------------------- epilogue (all TMA / MMA work of this evaluation is complete)
 #pragma unroll
     for (int pc = 0; pc < NCOLS; ++pc) {
       bool diag = false;
 #pragma unroll
       for (int i = 0; i < 16; ++i) diag |= (pc == sym_index(i, i));
       total[pc] = (pc < 136) ? fmaf(total[pc], out_scale, diag ? lambda : 0.f) : 0.f;
+    }
+    if (HMC) {
+      // ---- one leapfrog stage of ref hmc_sampler.py:120-163 for the chain this thread owns.
+      // Evaluation k of an iteration (k = 0 .. n_lf) is the metric at the chain's position after k
+      // position updates: one metric evaluation per leapfrog step (the reference re-evaluates the same
+      // gradient at the end of step k and the start of step k + 1).
+      const int per_it = hm.n_lf + 1;
+      const int it = ev / per_it, k = ev - it * per_it;
+      const int64_t r = row0 + prow;
+      if (!live) {
+#pragma unroll
+        for (int i = 0; i < 136; ++i) total[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) total[sym_index(i, i)] = 1.f;
+      }
+      float lad, dg[16];
+      const bool ok = sym16_factor(total, lad, dg, false);
+      if (!ok) {                       // certified tables: rounding only.  Counted; the host redoes the call unfused.
+        if (live) atomicAdd(hm.fail_count, 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dg[i] = 0.f;
+      }
+      float* st = state + prow * ST_LD;
+      float zc[16], rh[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(st + 4 * q);
+        zc[4 * q] = v.x; zc[4 * q + 1] = v.y; zc[4 * q + 2] = v.z; zc[4 * q + 3] = v.w;
+      }
+      const float half_eps = hm.eps / 2.f;
+      bool moved_on = true;            // false after the accept step of the LAST iteration (nothing left to evaluate)
+      if (k == 0) {
+        // rho = gamma / beta_zero_sqrt (:123), H0 (:127), first half step (:132-138)
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) gm = __ldg(reinterpret_cast<const float4*>(hm.gamma + ((int64_t)it * n + r) * 16) + q);
+          const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = 4 * q + e;
+            const float rho = g4[e] / hm.b0;
+            ss = fmaf(rho, rho, ss);
+            const float g = -((1.f - lambda * dg[jj]) / hm.T2);
+            rh[jj] = rho - half_eps * g;
+            zc[jj] = zc[jj] + hm.eps * rh[jj];
+          }
+        }
+        const float nrm = sqrtf(ss);
+        h0_keep = -hmc_log_pi(lad, ok) + 0.5f * (nrm * nrm);
+        if (live && hm.h0 != nullptr) hm.h0[(int64_t)it * n + r] = h0_keep;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(st + 16 + 4 * q);
+          rh[4 * q] = v.x; rh[4 * q + 1] = v.y; rh[4 * q + 2] = v.z; rh[4 * q + 3] = v.w;
+        }
+        const float scale = (hm.scales != nullptr) ? __ldg(hm.scales + it * hm.n_lf + (k - 1)) : hm.scales_inl[k - 1];
+        if (k < hm.n_lf) {
+          // second half step + tempering (:141-148), then the next step's first half (:132-138)
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float g = -((1.f - lambda * dg[jj]) / hm.T2);
+            const float rho = scale * (rh[jj] - half_eps * g);
+            rh[jj] = rho - half_eps * g;
+            zc[jj] = zc[jj] + hm.eps * rh[jj];
+          }
+        } else {
+          // end of the trajectory: H (:153), alpha (:156-157), accept / reject (:158-162)
+          float ss = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float g = -((1.f - lambda * dg[jj]) / hm.T2);
+            const float rho = scale * (rh[jj] - half_eps * g);
+            ss = fmaf(rho, rho, ss);
+          }
+          const float nrm = sqrtf(ss);
+          const float H = -hmc_log_pi(lad, ok) + 0.5f * (nrm * nrm);
+          float a = expf(-H) / (expf(-h0_keep) + 1e-10f);
+          a = fminf(fmaxf(a, 0.f), 1.f);
+          const float u = live ? __ldg(hm.acc + (int64_t)it * n + r) : 2.f;
+          const bool mv = u < a;
+          if (live) {
+            float4* zrow = reinterpret_cast<float4*>(hm.z + r * 16);
+            if (!mv) {                 // back to the state this iteration started from
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 v = zrow[q];
+                zc[4 * q] = v.x; zc[4 * q + 1] = v.y; zc[4 * q + 2] = v.z; zc[4 * q + 3] = v.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) zrow[q] = make_float4(zc[4 * q], zc[4 * q + 1], zc[4 * q + 2], zc[4 * q + 3]);
+            }
+            if (hm.z_trace != nullptr) {
+              float4* tr = reinterpret_cast<float4*>(hm.z_trace + ((int64_t)it * n + r) * 16);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tr[q] = make_float4(zc[4 * q], zc[4 * q + 1], zc[4 * q + 2], zc[4 * q + 3]);
+            }
+            if (hm.h1 != nullptr) hm.h1[(int64_t)it * n + r] = H;
+            if (hm.alpha != nullptr) hm.alpha[(int64_t)it * n + r] = a;
+            if (hm.moves != nullptr) hm.moves[(int64_t)it * n + r] = mv ? 1.f : 0.f;
+          }
+          moved_on = ev + 1 < n_evals;
+        }
+      }
+      if (moved_on) {
+        // publish the position of the next evaluation: state row (z, rho_half, exponent constants) for this
+        // CTA's exp groups, z' = 2^ez (z - shift) split in fp16 into TMEM for GEMM1
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(st + 4 * q) = make_float4(zc[4 * q], zc[4 * q + 1], zc[4 * q + 2], zc[4 * q + 3]);
+          *reinterpret_cast<float4*>(st + 16 + 4 * q) = make_float4(rh[4 * q], rh[4 * q + 1], rh[4 * q + 2], rh[4 * q + 3]);
+        }
+        float zs[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) zs[jj] = live ? zc[jj] : 0.f;
+        if (!EXACT) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+            zs[4 * q] -= sh.x; zs[4 * q + 1] -= sh.y; zs[4 * q + 2] -= sh.z; zs[4 * q + 3] -= sh.w;
+          }
+        }
+        float nrm2 = 0.f, zmax = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) { nrm2 = fmaf(zs[jj], zs[jj], nrm2); zmax = fmaxf(zmax, fabsf(zs[jj])); }
+        int ez = 0;
+        if (zmax > 0.f && zmax < 3.0e38f) {
+          const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+          ez = 14 - ex;
+          ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
+        }
+        st[32] = EXACT ? P_SHIFT : (-nrm2 * alpha + P_SHIFT);
+        st[33] = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
+        if (!EXACT) {
+          const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) split_pair(zs[2 * jj] * zsc, zs[2 * jj + 1] * zsc, hi[jj], lo[jj]);
+          TMEM_ST8(tmem_base + lane_addr + TM_ZHI, hi);
+          TMEM_ST8(tmem_base + lane_addr + TM_ZLO, lo);
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR_ZL);
+          if (PAIR) mbar_arrive_leader(BAR_ZR); else mbar_arrive(BAR_ZR);
+        }
+#pragma unroll
+        for (int i = 0; i < NCOLS; ++i) total[i] = 0.f;
+      }
+      continue;                        // next evaluation
     }
     // Outputs are stored straight from the registers of the thread that owns the point: 36 (packed) or 64
     // (expanded) fire-and-forget 128-bit stores per row, each row a contiguous 576 B / 1 KB run, so every
@@ -670,13 +927,14 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
     }
 #ifdef RLVAE_TC_PROFILE
-    if ((blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
+    if (!HMC && (blockIdx.x == 0 || blockIdx.x == 4096) && threadIdx.x == 384)
     {
       const long long pf2 = clock64();
       printf("[h16 prof %d] fold group per chunk: wait CH_FULL %lld  fold %lld | prologue %lld  mainloop %lld  epilogue %lld cycles\n",
              (int)blockIdx.x, pf_wait / num_chunks, pf_work / num_chunks, pf0 - pk0, pf1 - pf0, pf2 - pf1);
     }
 #endif
+    }   // evaluations (one, unless HMC)
   }
 #undef MMA_H
 #undef MMA_TS
@@ -1615,9 +1873,10 @@ static bool h16_use_pairs() {
   return v == 1;
 }
 
-template <bool PAIR, bool EXACT, bool HYBRID = false>
-static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s) {
-  auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT, HYBRID>;
+template <bool PAIR, bool EXACT, bool HYBRID = false, bool HMC = false>
+static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s,
+                      const tc::HmcArgs& hm = tc::HmcArgs{}) {
+  auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT, HYBRID, HMC>;
   RLVAE_OPT_IN_SMEM(kern, (int)tc::h16::SMEM_BYTES);
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
@@ -1642,10 +1901,10 @@ static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc
   const float cu = t->c16_unscale;
   if (PAIR) {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh2_hi, t->tm_mh2_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo, hm));
   } else {
     RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mh_hi, t->tm_mh_lo, z, cbias, cnat, n, nb,
-                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo));
+                                       alpha, lambda, out_scale, cu, t->cshift, 14.f - t->hybrid_bits, fo, hm));
   }
   return 0;
 }
@@ -1697,6 +1956,39 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
     return launch_sym16_fallback(a_packed, n, g_packed, logabsdet, lad_scale, sign, diag_g, fail_ws, s, g_full,
                                  skip_packed ? t : nullptr, z);
   return 0;
+}
+
+// The whole HMC trajectory in one launch (tables certified positive semi-definite, variant-A drift):
+// n_iters MCMC iterations x (n_lf + 1) metric evaluations per CTA pair, chain state on chip.
+int h16_hmc_available(const rlvae_tables* t) {
+  return t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr && t->psd_certified &&
+         h16_use_pairs() && (t->Kpad / tc::BK) % 2 == 0;
+}
+
+int launch_hmc_trajectory_h16(const rlvae_tables* t, float* z, const float* gamma, const float* acc, int64_t n,
+                              int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* scales_dev,
+                              const float* h_scales, float* h0, float* h1, float* alpha, float* moves,
+                              float* z_trace, int* fail_count, cudaStream_t s) {
+  if (n == 0 || n_iters == 0) return 0;
+  RLVAE_REQUIRE(h16_hmc_available(t), "fused HMC trajectory needs latent_dim == 16, symmetric certified tables");
+  RLVAE_REQUIRE(n_lf >= 1 && n_iters >= 1, "fused HMC trajectory: need n_lf >= 1 and n_iters >= 1");
+  RLVAE_REQUIRE(scales_dev != nullptr || (n_iters == 1 && n_lf <= 64 && h_scales != nullptr),
+                "fused HMC trajectory: tempering scales on the device are required for n_iters > 1 or n_lf > 64");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0,
+                "fused HMC trajectory needs 16-byte aligned z and gamma");
+  RLVAE_REQUIRE(z_trace == nullptr || (reinterpret_cast<uintptr_t>(z_trace) & 15) == 0, "z_trace must be 16-byte aligned");
+  RLVAE_REQUIRE((int64_t)n_iters * (n_lf + 1) * (t->Kpad / tc::BK) < ((int64_t)1 << 30), "trajectory too long for one launch");
+  tc::HmcArgs hm{};
+  hm.z = z; hm.gamma = gamma; hm.acc = acc; hm.scales = scales_dev;
+  hm.h0 = h0; hm.h1 = h1; hm.alpha = alpha; hm.moves = moves; hm.z_trace = z_trace; hm.fail_count = fail_count;
+  hm.n_iters = n_iters; hm.n_lf = n_lf; hm.eps = eps_lf; hm.b0 = beta_zero_sqrt; hm.T2 = t->T2;
+  if (scales_dev == nullptr)
+    for (int i = 0; i < n_lf; ++i) hm.scales_inl[i] = h_scales[i];
+  tc::FusedOut fo{};
+  const int mode = h16_mode(t);
+  if (mode == 1) return launch_h16<true, true, false, true>(t, z, n, fo, s, hm);
+  if (mode == 2) return launch_h16<true, false, true, true>(t, z, n, fo, s, hm);
+  return launch_h16<true, false, false, true>(t, z, n, fo, s, hm);
 }
 
 template <bool PAIR, bool EXACT, bool HYBRID = false>

@@ -3,8 +3,9 @@
 Same constructor, public attributes (``log_pi``, ``grad_func``, ``n_lf``, ``eps_lf``,
 ``beta_zero_sqrt``) and methods as the reference class (:13-296).  ``sample`` draws its
 random numbers in the reference's order (:114 z0, :122 gamma, :158 acc) and hands each
-MCMC iteration to ``rlvae_hmc_iteration`` -- one metric evaluation per leapfrog step
-instead of the reference's four [n,K,d,d] materialisations.
+chain to ``rlvae_hmc_run`` -- one metric evaluation per leapfrog step instead of the reference's four
+[n,K,d,d] materialisations, and ONE kernel launch for the whole trajectory (all MCMC
+iterations whose draws are in memory) when the fused trajectory kernel serves the tables.
 
 Reference quirks reproduced on purpose: the 'gradient' integrated is
 variant A == (1 - lambda*G_ii)/T^2; ``log_pi`` uses det + clamp(1e-10); the tempering
@@ -94,6 +95,36 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
         return out, beta_sqrt_old
 
     # ---- A11
+    _MAX_DRAW_BYTES = 1 << 30     # random draws generated ahead per launch of the fused trajectory kernel
+
+    def _all_scales(self, iters: int, n_lf: int, beta_old, b0_host):
+        out = []
+        for _ in range(iters):
+            sc, beta_old = self._scales(n_lf, beta_old, b0_host)
+            out.extend(sc)
+        return out, beta_old
+
+    def _run_chain(self, tab, path, z, gammas, accs, n_lf, eps, b0, mode, beta_old, b0_host, record=None):
+        """MCMC iterations gammas.shape[0] of the chain, in place on z: ONE kernel launch when the fused
+        trajectory kernel serves these tables (``rlvae_hmc_run``), else one C-ABI call per iteration inside
+        the library.  If the fused kernel reports a metric that lost positive definiteness to rounding, the
+        same iterations are redone from the same state with the per-step kernels + pivoting fallback."""
+        iters = gammas.shape[0]
+        scales, beta_new = self._all_scales(iters, n_lf, beta_old, b0_host)
+        fused = _capi.hmc_fused_available(tab, mode, path)
+        z_start = z.clone() if fused else None
+        want = record is not None
+        res = _capi.hmc_run(tab, z, gammas, accs, n_lf, eps, b0, scales, mode, path, want_stats=want, want_trace=want)
+        if fused and int(_capi.hmc_fail_count(res['work'], z.shape[0], z.shape[1]).item()) != 0:
+            z.copy_(z_start)
+            res = _capi.hmc_run(tab, z, gammas, accs, n_lf, eps, b0, scales, mode | _capi.HMC_NO_FUSION, path,
+                                want_stats=want, want_trace=want)
+        if want:
+            for name, val in zip(('H0', 'H', 'alpha', 'moves'), res['stats']):
+                record.setdefault(name, []).extend(list(val))
+            record.setdefault('z', []).extend(list(res['trace']))
+        return beta_new
+
     def sample_with_streams(self, z0, gammas, accs, z_forced=None, record=None):
         """``sample`` with the random draws supplied (z0 [n,d], gammas [I,n,d], accs [I,n]).
         ``z_forced[i]`` restarts iteration i from the given state (teacher forcing)."""
@@ -102,19 +133,17 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
         eps, b0 = float(self.eps_lf.item()), float(self.beta_zero_sqrt.item())
         mode = _capi.GRAD_EXACT if self.grad_mode == 'exact' else _capi.GRAD_MODULAR
         z = z0.detach().to(self.model.device, torch.float32).contiguous().clone()
-        work = _capi.hmc_workspace(z.shape[0], z.shape[1], z.device)
+        gammas = gammas.to(z.device, torch.float32).contiguous()
+        accs = accs.to(z.device, torch.float32).contiguous()
         b0_host = self.beta_zero_sqrt.detach().float().cpu()
         beta_old = b0_host
+        if z_forced is None:
+            self._run_chain(tab, path, z, gammas, accs, n_lf, eps, b0, mode, beta_old, b0_host, record)
+            return z
         for i in range(gammas.shape[0]):
-            if z_forced is not None:
-                z.copy_(z_forced[i])
-            scales, beta_old = self._scales(n_lf, beta_old, b0_host)
-            stats = _capi.hmc_iteration(tab, z, gammas[i], accs[i], n_lf, eps, b0, scales, mode, work, path,
-                                        want_stats=record is not None)
-            if record is not None:
-                for name, val in zip(('H0', 'H', 'alpha', 'moves'), stats):
-                    record.setdefault(name, []).append(val)
-                record.setdefault('z', []).append(z.clone())
+            z.copy_(z_forced[i])
+            beta_old = self._run_chain(tab, path, z, gammas[i:i + 1], accs[i:i + 1], n_lf, eps, b0, mode,
+                                       beta_old, b0_host, record)
         return z
 
     def sample(self, n_samples, t=0):
@@ -125,17 +154,25 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
         n_lf = int(self.n_lf.item())
         eps, b0 = float(self.eps_lf.item()), float(self.beta_zero_sqrt.item())
         mode = _capi.GRAD_EXACT if self.grad_mode == 'exact' else _capi.GRAD_MODULAR
-        z = torch.randn(n_samples, self.model.latent_dim, device=dev)
-        work = _capi.hmc_workspace(n_samples, self.model.latent_dim, dev)
+        d = self.model.latent_dim
+        z = torch.randn(n_samples, d, device=dev)
         b0_host = self.beta_zero_sqrt.detach().float().cpu()
         beta_old = b0_host
-        for _ in range(self.mcmc_steps_nbr):
-            gamma = torch.randn_like(z)
-            scales, beta_old = self._scales(n_lf, beta_old, b0_host)
-            # the reference draws acc after the trajectory; drawing it here consumes the same
-            # generator positions because nothing else draws in between
-            acc = torch.rand(n_samples, device=dev)
-            _capi.hmc_iteration(tab, z, gamma, acc, n_lf, eps, b0, scales, mode, work, path)
+        # The draws of several MCMC iterations are generated ahead, in the reference's call order (gamma
+        # :122 then acc :158 for every iteration -- nothing else draws in between), so that one launch of
+        # the fused trajectory kernel runs them all; bounded so a large batch does not hold all of them.
+        per_iter = 4 * n_samples * (d + 1)
+        ahead = max(1, min(self.mcmc_steps_nbr, self._MAX_DRAW_BYTES // max(per_iter, 1)))
+        done = 0
+        while done < self.mcmc_steps_nbr:
+            it = min(ahead, self.mcmc_steps_nbr - done)
+            gammas = torch.empty(it, n_samples, d, device=dev)
+            accs = torch.empty(it, n_samples, device=dev)
+            for i in range(it):
+                gammas[i] = torch.randn_like(z)
+                accs[i] = torch.rand(n_samples, device=dev)
+            beta_old = self._run_chain(tab, path, z, gammas, accs, n_lf, eps, b0, mode, beta_old, b0_host)
+            done += it
         return z.detach()
 
     # ---- A12
