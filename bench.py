@@ -9,12 +9,15 @@ one pass of the hot path over one batch of N synthetic points.  Under torchrun e
 evaluates its own N points against replicated tables (weak scaling, no data-path collective,
 SURVEY.md §8e); `value` is total evals over all ranks / max-over-ranks device time.
 
-Extra keys: `roofline` (the fused metric + log-det tcgen05 kernel, tensor bound, timed alone against
-MEASURED_PEAKS.json's bf16 burst rate; `roofline_gradient_kernel` is the same for the gradient kernel),
-`cpu_baseline` (the CPU oracle port on a bounded sample, rank 0 / N=1 only), `e2e` (host-buffer
-API: pinned H2D of z, evaluation, D2H of log det + grad, per step), `hmc` (config[2]: chain
-leapfrog steps/s, 2^20 chains x 20 leapfrog), `flow` (config[3]: 65,536 sequences x 10 flow steps, metric
-spectrum per step), `clocks`, `gpu_launches`.
+Extra keys: `roofline` (the DOMINANT kernel of the step -- the gradient kernel -- timed with CUDA events on
+the launching stream inside the timed steps, against MEASURED_PEAKS.json's sustained bf16 rate; three flop
+conventions side by side; `roofline_forward_kernel` is the same for the fused metric + log-det kernel),
+`cpu_baseline` (the CPU oracle port on a bounded sample, rank 0 / N=1 only), `e2e` (host-buffer API: pinned
+H2D of z, evaluation, D2H of log det + grad, per step), `e2e_with_ginv` (G^-1 copied out too), `hmc`
+(configs[2], weak: 2^20 chains per GPU x 20 leapfrog, one launch), `hmc_strong` (2^20 chains TOTAL over the
+ranks + NCCL all_gather / all_reduce in the timed region), `small_T` (the step at T = 0.7), `d64` (configs[4]:
+d = 64, K = 50k, 2^20 points per GPU), `flow` (configs[3]), `shard_check` (sharded == single-rank, bitwise),
+`clocks`, `gpu_launches`.
 
 `--impl reference` times the reference's own algorithm on the host cores (the CPU oracle port of
 its eager PyTorch code -- the reference is Python and is not present on the GPU box).
@@ -23,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import contextlib
+import ctypes
 import io
 import json
 import os
@@ -198,11 +202,28 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- our arm
+def committed_profile():
+    """Numbers that can only come from an ncu capture (taken once per change, committed under
+    profiles/): DRAM bytes per launch and tensor-pipe activity of the two kernels, for the SAME launches
+    the timed step runs (profiles/README.md says which command produced them)."""
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        p = os.path.join(ROOT, 'profiles', name)
+        if os.path.isfile(p):
+            try:
+                d = json.load(open(p))
+                d['_file'] = 'profiles/' + name
+                return d
+            except Exception:
+                pass
+    return {}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from rlvae_b200 import MetricModel, MetricTensor, RiemannianHMCSampler, _capi
+    from rlvae_b200.distributed import all_gather_rows, shard_bounds
     from rlvae_b200.host_pipeline import HostEvaluator
-    from rlvae_b200.synthetic import make_hmc_streams
+    from rlvae_b200.synthetic import make_hmc_streams, make_points
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -224,19 +245,24 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def quiet_load(mt, **kw):
+        with contextlib.redirect_stdout(io.StringIO()):
+            mt.load_pretrained(**kw)
+
     n = N_PER_GPU
     sm, z_cpu = tables_and_points(n, seed_offset=rank)
     mt = MetricTensor(D, device=dev)
-    with contextlib.redirect_stdout(io.StringIO()):
-        mt.load_pretrained(**sm.as_load_kwargs())
+    quiet_load(mt, **sm.as_load_kwargs())
     if world > 1:   # tables are replicated: one broadcast at load
         for b in (mt.centroids, mt.metric_matrices):
             dist.broadcast(b, src=0)
     tab = mt._tables(dev)
     path_name = 'tensor' if (tab.tensor_capable and tab.tensor_auto) else 'direct'
+    sym_tensor = path_name == 'tensor' and tab.symmetric
     z = z_cpu.to(dev)
     out = {}
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)   # > 126 MB L2
+    lib = _capi.lib()
 
     def step():
         nonlocal out
@@ -246,7 +272,8 @@ def run_ours(args):
     for _ in range(W):
         step()
     barrier()
-    _capi.lib().rlvae_launch_count(1)        # reset: count the kernels launched inside the timed region
+    lib.rlvae_launch_count(1)        # reset: count the kernels launched inside the timed region
+    lib.rlvae_profile_begin(S)       # CUDA events around each kernel of every timed step, on the launching stream
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -259,17 +286,26 @@ def run_ours(args):
         step()
         ev[i][1].record()
     barrier()
-    launches_timed = int(_capi.lib().rlvae_launch_count(0))
+    launches_timed = int(lib.rlvae_launch_count(0))
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     dev_ms = max_over_ranks(dev_ms)
     ms_per_step = dev_ms / S
     value = world * n / (ms_per_step * 1e-3)
+    # the kernels of the timed steps themselves (what the roofline block reports)
+    in_step = None
+    if int(lib.rlvae_profile_count()) == S:
+        acc3 = [0.0, 0.0, 0.0]
+        buf = (ctypes.c_float * 3)()
+        for i in range(S):
+            assert lib.rlvae_profile_read(i, buf) == 0, lib.rlvae_last_error()
+            for j in range(3):
+                acc3[j] += float(buf[j])
+        in_step = {'forward_ms': acc3[0] / S, 'fallback_pass_ms': acc3[1] / S, 'gradient_ms': acc3[2] / S}
+    lib.rlvae_profile_end()
 
-    # ---- the two tensor kernels of the step, each timed alone (CUDA events around the launch, L2 flushed)
-    lib = _capi.lib()
-    sym_tensor = path_name == 'tensor' and tab.symmetric
+    # ---- each tensor kernel also timed ALONE (L2 flushed, idle GPU before it: burst clocks)
     work = torch.empty(int(lib.rlvae_metric_eval_workspace(n, D)) // 4, device=dev, dtype=torch.float32)
     ld_buf = torch.empty(n, device=dev)
     gr_buf = torch.empty(n, D, device=dev)
@@ -285,58 +321,114 @@ def run_ours(args):
         return sum(ts) / len(ts)
 
     st = _capi._stream(z)
-    # fused metric + log-det kernel: z -> packed G^-1, packed G, log det G (what rlvae_metric_eval runs first)
+
     def _ok(rc):
         assert rc == 0, lib.rlvae_last_error()
 
-    fwd_ms = time_launch(lambda: _ok(lib.rlvae_metric_eval(tab.handle, _capi._ptr(z), n, None, None,
-                                                           _capi._ptr(ld_buf), None, _capi._ptr(work),
-                                                           _capi.PATH_AUTO, st)))
-    # gradient kernel alone: contraction with the packed G the fused kernel left in the workspace
-    g_src = out['g'] if 'g' in out and out['g'] is not None else None
-    if g_src is None:
-        g_src = mt.evaluate(z[: 1 << 16], want_ginv=False, want_g=True, want_logdet=False)['g'].repeat(n >> 16, 1, 1)
-    grad_ms = time_launch(lambda: _ok(lib.rlvae_metric_grad(tab.handle, _capi._ptr(z), _capi._ptr(g_src), n,
-                                                            -2.0 / float(tab.temperature) ** 2,
-                                                            _capi._ptr(gr_buf), _capi.PATH_AUTO, st)))
-    del g_src
+    # the SAME forward launch the step runs: expanded G^-1 + log det + packed G (for the gradient kernel);
+    # measured as (forward + gradient call) - (gradient alone) would mix kernels, so it is taken from the
+    # profile events of a call that also runs the gradient
+    fwd_alone_ms = grad_alone_ms = None
+    if sym_tensor:
+        lib.rlvae_profile_begin(8)
+        buf = (ctypes.c_float * 3)()
+        fa, ga = [], []
+        for i in range(8):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            _ok(lib.rlvae_metric_eval(tab.handle, _capi._ptr(z), n, _capi._ptr(out['ginv']), None, _capi._ptr(ld_buf),
+                                      _capi._ptr(gr_buf), _capi._ptr(work), _capi.PATH_AUTO, st))
+            _ok(lib.rlvae_profile_read(i, buf))
+            if i >= 3:
+                fa.append(float(buf[0])); ga.append(float(buf[2]))
+        lib.rlvae_profile_end()
+        fwd_alone_ms, grad_alone_ms = sum(fa) / len(fa), sum(ga) / len(ga)
+    else:
+        fwd_alone_ms = time_launch(lambda: _ok(lib.rlvae_metric_eval(tab.handle, _capi._ptr(z), n, _capi._ptr(out['ginv']),
+                                                                      None, _capi._ptr(ld_buf), None, _capi._ptr(work),
+                                                                      _capi.PATH_AUTO, st)))
     peaks, peak_src = measured_peaks()
     line = {}
-    roof = roof_grad = None
+    roof = roof_fwd = None
     if rank == 0:
         tf32_rate = measure_tf32_peak(dev)
         bf16_rate = measure_bf16_rate(dev)
-        peak = float(peaks['bf16_tflops'])          # burst figure: each kernel is timed alone
-        if sym_tensor:
-            # Tensor work in fp16-equivalent flops: a TF32 MAC costs two fp16 MACs of pipe time (the
-            # measured TF32 GEMM rate is half the bf16 one).  ALGORITHMIC = symmetric tables, no padding:
-            #   forward : 3 passes x 2K x (136 weighted-sum columns + 16 distance dims) [all fp16]
-            #   gradient: 3 passes x 2K x (136 [fp16] + 16 [fp16] + 2 x 16 final contraction [TF32])
-            f_fwd = n * 3 * 2 * K * (136 + 16)
-            f_grad = n * 3 * 2 * K * (136 + 16 + 2 * 16)
-            issued_fwd = n * 3 * 2 * tab.Kpad * (144 + 16)
-            issued_grad = n * 3 * 2 * tab.Kpad * (144 + 16 + 2 * 16)
-            note = ('fp16-equivalent tensor flops (TF32 MACs weighted x2: measured TF32 GEMM rate %.0f TF/s vs '
-                    'bf16 %.0f TF/s in this run); symmetric tables -> 136 packed columns; dense-M definition '
-                    'of SURVEY.md 8d would read %.0f TF/s fp32-equivalent' )
-            ach = f_fwd / (fwd_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'inverse_metric_h16_kernel (fused G^-1 + Cholesky log det)',
-                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    'traffic': ncu_traffic('inverse_metric_h16_kernel'), 'kernel_ms': fwd_ms,
-                    'issued': issued_fwd / (fwd_ms * 1e-3) / 1e12,
-                    'peak_source': f'MEASURED_PEAKS.json bf16_tflops burst ({peak_src})',
-                    'same_run_cublas': {'bf16_tflops': bf16_rate, 'tf32_tflops': tf32_rate},
-                    'note': note % (tf32_rate, bf16_rate, n * 2 * K * D * (D + 1) / (fwd_ms * 1e-3) / 1e12)}
-            achg = f_grad / (grad_ms * 1e-3) / 1e12
-            roof_grad = {'bound': 'tensor', 'kernel': 'metric_grad_h16_kernel', 'achieved': achg, 'peak': peak,
-                         'unit': 'TFLOP/s', 'frac': achg / peak, 'traffic': ncu_traffic('metric_grad_h16_kernel'),
-                         'kernel_ms': grad_ms, 'issued': issued_grad / (grad_ms * 1e-3) / 1e12}
+        prof = committed_profile()
+        burst, sustained = float(peaks['bf16_tflops']), float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
+        if sym_tensor and in_step is not None:
+            # Tensor work in fp16-equivalent flops: a TF32 MAC costs two fp16 MACs of pipe time (the measured
+            # TF32 GEMM rate is half the bf16 one).  Three conventions, printed side by side:
+            #   packed   ALGORITHMIC work of this design: symmetric tables -> 136 packed columns (+16 distance
+            #            dims), x3 split passes, no padding          
+            #   dense_8d SURVEY.md 8d's dense-M count 2Kd(d+1) per eval and kernel, x3 split passes
+            #            (exceeds the packed count by 272/152: symmetry is not credited)
+            #   fp32_eq  the same dense count with NO pass multiplier ("fp32-equivalent" flops)
+            dense = n * 2.0 * K * D * (D + 1)
+
+            def block(kernel, ms_step, ms_alone, packed_flops, issued_flops, key):
+                ach = packed_flops / (ms_step * 1e-3) / 1e12
+                pk = prof.get(key) if isinstance(prof.get(key), dict) else {}
+                return {'bound': 'tensor', 'kernel': kernel, 'achieved': ach, 'peak': burst, 'unit': 'TFLOP/s',
+                        'frac': ach / burst,
+                        'frac_of_sustained_peak': ach / sustained,
+                        'frac_dense_8d': 3 * dense / (ms_step * 1e-3) / 1e12 / burst,
+                        'frac_fp32_equiv': dense / (ms_step * 1e-3) / 1e12 / burst,
+                        'issued_tflops': issued_flops / (ms_step * 1e-3) / 1e12,
+                        'kernel_ms': ms_step, 'kernel_ms_after_idle': ms_alone,
+                        'tensor_pipe_active': pk.get('tensor_pipe_active_pct'),
+                        'traffic': pk.get('dram_bytes'), 'traffic_algorithmic': pk.get('algorithmic_bytes'),
+                        'ncu_source': prof.get('_file'),
+                        'timing': 'kernel_ms = CUDA events on the launching stream around this kernel inside the '
+                                  'timed steps (average over the steps).  peak = the BURST bf16 figure (the '
+                                  'conservative denominator: the steps are 16 ms long and run against the 1 kW power '
+                                  'cap, frac_of_sustained_peak uses the 4-second back-to-back figure); '
+                                  'kernel_ms_after_idle = the same launch right after a device synchronisation '
+                                  '(clocks still ramping: slower, reported for completeness)',
+                        'peak_source': f'MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained ({peak_src})'}
+
+            f_fwd = n * 3.0 * 2 * K * (136 + 16)
+            f_grad = n * 3.0 * 2 * K * (136 + 16 + 2 * 16)
+            issued_fwd = n * 3.0 * 2 * tab.Kpad * (144 + 16)
+            issued_grad = n * 3.0 * 2 * tab.Kpad * (144 + 16 + 2 * 16)
+            roof_g = block('metric_grad_h16_kernel', in_step['gradient_ms'], grad_alone_ms, f_grad, issued_grad,
+                           'metric_grad_h16_kernel')
+            roof_fwd = block('inverse_metric_h16_kernel (fused G^-1 + Cholesky log det + packed G)',
+                             in_step['forward_ms'], fwd_alone_ms, f_fwd, issued_fwd, 'inverse_metric_h16_kernel')
+            roof = roof_g if in_step['gradient_ms'] >= in_step['forward_ms'] else roof_fwd     # the DOMINANT kernel
+            roof = dict(roof)
+            roof['dominant'] = roof['kernel']
+            roof['step_share'] = {'forward_ms': in_step['forward_ms'], 'fallback_pass_ms': in_step['fallback_pass_ms'],
+                                  'gradient_ms': in_step['gradient_ms'], 'step_ms': ms_per_step}
+            roof['same_run_cublas'] = {'bf16_tflops': bf16_rate, 'tf32_tflops': tf32_rate}
+            roof['step_frac'] = (f_fwd + f_grad) / (ms_per_step * 1e-3) / 1e12 / burst
         else:
-            f_alg = n * 2 * K * D * (D + 1)
-            ach = (3 if path_name == 'tensor' else 1) * f_alg / (fwd_ms * 1e-3) / 1e12
+            f_alg = n * 2.0 * K * D * (D + 1)
+            ach = (3 if path_name == 'tensor' else 1) * f_alg / (fwd_alone_ms * 1e-3) / 1e12
             roof = {'bound': 'tensor', 'kernel': 'inverse_metric_tc_kernel' if path_name == 'tensor'
                     else 'inverse_metric_direct_kernel', 'achieved': ach, 'peak': tf32_rate, 'unit': 'TFLOP/s',
-                    'frac': ach / tf32_rate, 'traffic': None, 'kernel_ms': fwd_ms}
+                    'frac': ach / tf32_rate, 'traffic': None, 'kernel_ms': fwd_alone_ms}
+
+    # ---- shard check: the gathered sharded evaluation equals the single-rank evaluation (2^16 points)
+    shard_check = None
+    try:
+        nz = 1 << 16
+        zg = make_points(nz, D, seed=77).to(dev)
+        lo, hi = shard_bounds(nz, world, rank)
+        mine = mt.evaluate(zg[lo:hi].contiguous(), want_ginv=True, want_logdet=True, want_grad=True)
+        gath = {k: all_gather_rows(mine[k], nz) for k in ('ginv', 'logdet_g', 'grad_logdet_g')}
+        full = mt.evaluate(zg, want_ginv=True, want_logdet=True, want_grad=True)
+        diffs = {k: float((gath[k] - full[k]).abs().max().item()) for k in gath}
+        ok = all(torch.equal(gath[k], full[k]) for k in gath)
+        okt = torch.tensor([1.0 if ok else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        shard_check = {'points': nz, 'world': world, 'bitwise_equal': bool(okt.item() == 1.0), 'max_abs_diff': diffs}
+        assert shard_check['bitwise_equal'], f'sharded evaluation differs from the single-rank one: {diffs}'
+        del zg, mine, gath, full
+    except AssertionError:
+        raise
+    except Exception as e:
+        shard_check = {'error': str(e)[:200]}
 
     # ---- end to end through the host-buffer API (pinned H2D of z, D2H of log det + grad)
     he = HostEvaluator(mt, chunk=1 << 17, want_grad=True)
@@ -356,26 +448,100 @@ def run_ours(args):
            'd2h_bytes_per_step': io_bytes['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s,
            'api': 'rlvae_b200.host_pipeline.HostEvaluator (pinned host z in, log det + grad out; '
                   'G^-1 stays on device)'}
+    # the same with G^-1 copied out as well (1 KB per point: PCIe bound)
+    e2e_ginv = None
+    try:
+        gi_pin = torch.empty(n, D, D).pin_memory()
+        io2 = he(z_pin, ld_pin, gr_pin, ginv_host=gi_pin)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            io2 = he(z_pin, ld_pin, gr_pin, ginv_host=gi_pin)
+        barrier()
+        s2 = max_over_ranks(time.perf_counter() - t0) / 2
+        e2e_ginv = {'value': world * n / s2, 'unit': UNIT, 'h2d_bytes_per_step': io2['h2d_bytes'],
+                    'd2h_bytes_per_step': io2['d2h_bytes'], 'ms_per_step': 1e3 * s2,
+                    'd2h_gbs_per_gpu': io2['d2h_bytes'] / s2 / 1e9,
+                    'api': 'HostEvaluator(..., ginv_host=pinned [N,16,16]): every output of the metric copied to the host'}
+        del gi_pin
+    except Exception as e:
+        e2e_ginv = {'error': str(e)[:200]}
     del he
 
-    # ---- HMC (BASELINE.json configs[2]): 2^20 chains x 20 leapfrog, one MCMC iteration
-    hmc = None
-    try:
-        z0, gam, acc = make_hmc_streams(n, D, 1, seed=2 + rank)
+    # ---- HMC (BASELINE.json configs[2]): 20 leapfrog steps, one MCMC iteration = ONE kernel launch
+    def time_hmc(nch, seed, gather):
+        z0, gam, acc = make_hmc_streams(nch, D, 1, seed=seed)
+        if gather:      # strong scaling: rows of the GLOBAL draws that belong to this rank
+            lo, hi = shard_bounds(nch, world, rank)
+            z0, gam, acc = z0[lo:hi].contiguous(), gam[:, lo:hi].contiguous(), acc[:, lo:hi].contiguous()
         s = RiemannianHMCSampler(MetricModel(mt), mcmc_steps_nbr=1, n_lf=HMC_STEPS, eps_lf=0.03)
         z0, gam, acc = z0.to(dev), gam.to(dev), acc.to(dev)
-        s.sample_with_streams(z0, gam, acc)                   # warm-up
-        barrier()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        s.sample_with_streams(z0, gam, acc)
-        e1.record(); e1.synchronize()
-        h_ms = max_over_ranks(e0.elapsed_time(e1))
+        best = None
+        for rep in range(3):
+            barrier()
+            lib.rlvae_launch_count(1)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            rec = {}
+            zf = s.sample_with_streams(z0, gam, acc, record=rec if gather else None)
+            if gather:   # what north_star names: gather the samples, reduce the scalar (accept count)
+                zall = all_gather_rows(zf, nch)
+                cnt = rec['moves'][0].sum()
+                if world > 1:
+                    dist.all_reduce(cnt)
+            e1.record(); e1.synchronize()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            if rep and (best is None or ms < best[0]):
+                best = (ms, int(lib.rlvae_launch_count(0)), float(cnt.item()) / nch if gather else None,
+                        tuple(zall.shape) if gather else None)
+        return best
+
+    hmc = hmc_strong = None
+    try:
+        h_ms, h_launch, _, _ = time_hmc(n, 2 + rank, False)
         hmc = {'metric': 'hmc_chain_leapfrog_steps_per_sec', 'value': world * n * HMC_STEPS / (h_ms * 1e-3),
                'chains_per_gpu': n, 'n_lf': HMC_STEPS, 'mcmc_iterations': 1, 'ms': h_ms,
-               'metric_evals_per_iteration': HMC_STEPS + 1}
+               'metric_evals_per_iteration': HMC_STEPS + 1, 'kernel_launches_per_iteration': h_launch,
+               'fused_trajectory_kernel': bool(_capi.hmc_fused_available(tab)), 'scaling': 'weak'}
     except Exception as e:   # never lose the headline because of the secondary measurement
         hmc = {'error': str(e)[:200]}
+    try:
+        s_ms, s_launch, acc_rate, gshape = time_hmc(n, 2, True)
+        hmc_strong = {'metric': 'hmc_chain_leapfrog_steps_per_sec', 'value': n * HMC_STEPS / (s_ms * 1e-3),
+                      'chains_total': n, 'chains_per_gpu': n // world, 'n_lf': HMC_STEPS, 'ms': s_ms,
+                      'scaling': 'strong', 'accept_rate': acc_rate, 'gathered_shape': list(gshape),
+                      'collectives_in_timed_region': 'all_gather(z) + all_reduce(accept count) over NCCL'
+                      if world > 1 else 'none (1 rank)'}
+    except Exception as e:
+        hmc_strong = {'error': str(e)[:200]}
+
+    # ---- small temperature (the reference's T = 0.7, conf/model/hybrid_rlvae.yaml:41): the same step
+    small_t = None
+    try:
+        mt7 = MetricTensor(D, device=dev)
+        kw = sm.as_load_kwargs(); kw['temperature'] = 0.7
+        quiet_load(mt7, **kw)
+        # half of the points next to centroids (at T = 0.7 a random point sees no centroid at all)
+        z7 = torch.cat([z[: n // 2], mt7.centroids[torch.arange(n // 2, device=dev) % K] + 0.05 * z[n // 2:]]).contiguous()
+        o7 = {}
+        for _ in range(2):
+            o7 = mt7.evaluate(z7, want_ginv=True, want_logdet=True, want_grad=True, out=o7)
+        barrier()
+        ts = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            o7 = mt7.evaluate(z7, want_ginv=True, want_logdet=True, want_grad=True, out=o7)
+            e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t7 = max_over_ranks(sum(ts) / len(ts))
+        small_t = {'temperature': 0.7, 'ms_per_step': t7, 'value': world * n / (t7 * 1e-3), 'unit': UNIT,
+                   'implementation': mt7.kernel_info().get('implementation'),
+                   'finite': bool(torch.isfinite(o7['logdet_g']).all().item())}
+        del mt7, z7, o7
+    except Exception as e:
+        small_t = {'error': str(e)[:200]}
 
     # ---- FlowManager temporal flow (BASELINE.json configs[3]): B = 65,536 sequences x 10 timesteps,
     # flows in stock torch, then ONE fused metric evaluation (log det G + spectrum) over [B*T, d]
@@ -402,6 +568,16 @@ def run_ours(args):
         del fm, zf0, z_seq, zz, sp
     except Exception as e:
         flow = {'error': str(e)[:200]}
+
+    # ---- large-metric stress (BASELINE.json configs[4]): d = 64, K = 50,000, N = 2^20 points per GPU
+    # (8M over 8 GPUs), tables generated on the device from a fixed seed, evaluated in 2^17-point chunks
+    d64 = None
+    del out, work, ld_buf, gr_buf, z
+    torch.cuda.empty_cache()
+    try:
+        d64 = bench_d64(dev, world, rank, barrier, max_over_ranks)
+    except Exception as e:
+        d64 = {'error': str(e)[:300]}
 
     if rank == 0:
         cpu = None
@@ -436,13 +612,70 @@ def run_ours(args):
                                        '(BASELINE.json configs[1])', 'points_per_gpu': n, 'path': path_name, 'implementation': mt.kernel_info().get('implementation'),
                            'parallelism': f'points sharded over {world} GPU(s), tables replicated',
                            'l2': 'L2 flushed (256 MB write) before every timed step; each step also '
-                                 'writes >2 GB of outputs'},
-                'roofline': roof, 'roofline_gradient_kernel': roof_grad, 'cpu_baseline': cpu, 'e2e': e2e, 'hmc': hmc, 'flow': flow, 'clocks': clocks,
+                                 'writes >1.6 GB of outputs'},
+                'roofline': roof, 'roofline_forward_kernel': roof_fwd, 'cpu_baseline': cpu, 'e2e': e2e,
+                'e2e_with_ginv': e2e_ginv, 'hmc': hmc, 'hmc_strong': hmc_strong, 'small_T': small_t, 'd64': d64,
+                'flow': flow, 'shard_check': shard_check, 'clocks': clocks,
                 'gpu_launches': launches_timed,
                 'tflops_fp32_equiv': value * flops_per_eval(True) / 1e12}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_d64(dev, world, rank, barrier, max_over_ranks, n=1 << 20, K64=50000, chunk=1 << 17):
+    """BASELINE.json configs[4]: d = 64, K = 50,000 centroids, 2^20 points per GPU (8M over 8 GPUs).  Tables
+    and points from a fixed device seed (the recipe of scripts/stress_d64.py: M = L L^T, rescaled so that
+    G^-1 is O(1)); one step = G^-1 + log det G (+ grad_z log det G) for all points, in chunks."""
+    from rlvae_b200 import MetricTensor
+    d = 64
+    g = torch.Generator(device=dev).manual_seed(1234)
+    c = torch.randn(K64, d, device=dev, generator=g)
+    L = torch.tril(torch.randn(K64, d, d, device=dev, generator=g)) * d ** -0.5
+    M = L @ L.transpose(1, 2)
+    del L
+    M = 0.5 * (M + M.transpose(1, 2))
+    T, lam = 0.75 * d ** 0.5, 0.01
+    gz = torch.Generator(device=dev).manual_seed(4321 + rank)
+    z = torch.randn(n, d, device=dev, generator=gz)
+    w = torch.exp(-torch.cdist(z[:64].double(), c.double()) ** 2 / T ** 2).sum(1).mean().item()
+    M = (M / w).contiguous()
+    mt = MetricTensor(d, device=dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt.load_pretrained(c, M, temperature=T, regularization=lam)
+    del M
+    info = mt.kernel_info()
+    out = {}
+
+    def run(want_grad, npts):
+        nonlocal out
+        for lo in range(0, npts, chunk):
+            zz = z[lo:min(lo + chunk, npts)]
+            if out and out['ginv'].shape[0] != zz.shape[0]:
+                out = {}
+            out = mt.evaluate(zz, want_ginv=True, want_logdet=True, want_grad=want_grad, out=out)
+
+    res = {'latent_dim': d, 'n_centroids': K64, 'points_per_gpu': n, 'chunk_points': chunk,
+           'implementation': info.get('implementation'), 'tables_bytes_fp32': K64 * (d * d + d) * 4}
+    run(False, chunk)                       # warm-up (one chunk)
+    barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); run(False, n); e1.record(); e1.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    res['forward'] = {'what': 'G^-1 + log det G', 'ms': ms, 'value': world * n / (ms * 1e-3), 'unit': UNIT,
+                      'tflops_fp32_equiv_dense': world * n * 2.0 * K64 * d * (d + 1) / (ms * 1e-3) / 1e12}
+    res['finite'] = bool(torch.isfinite(out['logdet_g']).all().item())
+    # with the gradient: full size when the gradient runs on the tensor cores, a bounded sample otherwise
+    tensor_grad = 'gradient on the direct kernel' not in str(info.get('implementation'))
+    ng = n if tensor_grad else 4096
+    run(True, min(ng, chunk))
+    barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); run(True, ng); e1.record(); e1.synchronize()
+    msg = max_over_ranks(e0.elapsed_time(e1))
+    res['with_grad'] = {'what': 'G^-1 + log det G + grad_z log det G', 'points_per_gpu': ng, 'ms': msg,
+                        'value': world * ng / (msg * 1e-3), 'unit': UNIT, 'gradient_on_tensor_cores': tensor_grad}
+    return res
 
 
 def main():

@@ -51,6 +51,16 @@ int         rlvae_abi_version(void);
  * bench.py's gpu_launches */
 long long   rlvae_launch_count(int reset);
 
+/* Measurement aid (bench.py's roofline): while profiling is on, every rlvae_metric_eval call on the
+ * packed tensor path (d == 16, symmetric tables) records CUDA events on its stream around the
+ * fused forward launch, the fallback pass and the gradient launch.  rlvae_profile_read gives
+ * ms[0] = forward kernel, ms[1] = fallback pass, ms[2] = gradient kernel of call `record`
+ * (synchronises on that call's last event).  Not thread-safe.                                  */
+int rlvae_profile_begin(int max_records);
+int rlvae_profile_count(void);
+int rlvae_profile_read(int record, float ms[3]);
+int rlvae_profile_end(void);
+
 /* ---- tables: replaces MetricTensor.load_pretrained's buffers --------------------------------
  * ref: src/models/components/metric_tensor.py:59-96 (centroids [K,d], metric_matrices [K,d,d],
  * temperature, regularization).  Packs device-side derived copies: zero-padded tables,

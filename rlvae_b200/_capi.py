@@ -25,6 +25,10 @@ _SIGNATURES = [
     ('rlvae_last_error', c_char_p, []),
     ('rlvae_abi_version', c_int, []),
     ('rlvae_launch_count', ctypes.c_longlong, [c_int]),
+    ('rlvae_profile_begin', c_int, [c_int]),
+    ('rlvae_profile_count', c_int, []),
+    ('rlvae_profile_read', c_int, [c_int, POINTER(c_float)]),
+    ('rlvae_profile_end', c_int, []),
     ('rlvae_tables_create', c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     ('rlvae_tables_destroy', c_int, [c_void_p]),
     ('rlvae_tables_info', c_int, [c_void_p, POINTER(c_int64)]),

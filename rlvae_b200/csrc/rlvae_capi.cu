@@ -18,6 +18,21 @@ static std::atomic<long long> g_launch_count{0};
 void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 void pythae_cache_release(const rlvae_tables* t);
 
+// ---- per-kernel timing of rlvae_metric_eval on the packed tensor path (bench.py's roofline block):
+// CUDA events recorded on the launching stream around the forward launch, the fallback pass and the
+// gradient launch of every call while profiling is on.  Not thread-safe; a measurement aid.
+static struct {
+  bool on = false;
+  int cap = 0, n = 0;
+  cudaEvent_t* ev = nullptr;     // 4 per record
+} g_prof;
+void prof_mark(int slot, cudaStream_t s) {
+  if (g_prof.on && g_prof.n < g_prof.cap) cudaEventRecord(g_prof.ev[4 * g_prof.n + slot], s);
+}
+static void prof_next() {
+  if (g_prof.on && g_prof.n < g_prof.cap) ++g_prof.n;
+}
+
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -306,6 +321,40 @@ const char* rlvae_last_error(void) { return g_last_error.c_str(); }
 int rlvae_abi_version(void) { return 2; }
 long long rlvae_launch_count(int reset) {
   return reset ? g_launch_count.exchange(0) : g_launch_count.load();
+}
+
+int rlvae_profile_begin(int max_records) {
+  RLVAE_REQUIRE(max_records >= 1 && max_records <= 4096, "profile_begin: max_records must be in [1,4096]");
+  rlvae_profile_end();
+  g_prof.ev = static_cast<cudaEvent_t*>(malloc(sizeof(cudaEvent_t) * 4 * (size_t)max_records));
+  RLVAE_REQUIRE(g_prof.ev != nullptr, "profile_begin: out of host memory");
+  for (int i = 0; i < 4 * max_records; ++i) RLVAE_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
+  g_prof.cap = max_records;
+  g_prof.n = 0;
+  g_prof.on = true;
+  return 0;
+}
+
+int rlvae_profile_count(void) { return g_prof.n; }
+
+int rlvae_profile_read(int record, float ms[3]) {
+  RLVAE_REQUIRE(g_prof.ev != nullptr && record >= 0 && record < g_prof.n && ms != nullptr,
+                "profile_read: no such record");
+  cudaEvent_t* e = g_prof.ev + 4 * record;
+  RLVAE_CUDA_OK(cudaEventSynchronize(e[3]));
+  for (int i = 0; i < 3; ++i) RLVAE_CUDA_OK(cudaEventElapsedTime(&ms[i], e[i], e[i + 1]));
+  return 0;
+}
+
+int rlvae_profile_end(void) {
+  if (g_prof.ev != nullptr) {
+    for (int i = 0; i < 4 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
+    free(g_prof.ev);
+  }
+  g_prof.ev = nullptr;
+  g_prof.cap = g_prof.n = 0;
+  g_prof.on = false;
+  return 0;
 }
 
 int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const float* matrices,
@@ -714,9 +763,13 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     int* fail_ws = reinterpret_cast<int*>(a_buf + n * kSymCols);
     if (int rc = sym_forward(t, z, n, a_buf, g_packed, logdet_g, -1.f, nullptr, nullptr, fail_ws, s, ginv, g, 0))
       return rc;
+    prof_mark(2, s);       // (0, 1 bracket the forward launch inside launch_inverse_metric_h16)
+    int rc = 0;
     if (grad_logdet_g != nullptr)
-      return launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
-    return 0;
+      rc = launch_metric_grad_tc(t, z, g_packed, n, -2.f / t->T2, grad_logdet_g, s, 1);
+    prof_mark(3, s);
+    prof_next();
+    return rc;
   }
   if (int rc = inverse_metric_full(t, z, n, a_buf, path, s, gt_buf)) return rc;
   if (ginv != nullptr)

@@ -31,6 +31,7 @@ void set_error(const std::string& msg);
 
 // every kernel launch of the hot path goes through one of these two (rlvae_launch_count reports the total)
 void count_launch();
+void prof_mark(int slot, cudaStream_t s);   // rlvae_profile_*: event `slot` of the current record (no-op unless profiling)
 #define RLVAE_LAUNCH_OK()                    \
   do {                                       \
     ::rlvae::count_launch();                 \

@@ -1947,9 +1947,11 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   tc::FusedOut fo{a_full, skip_packed ? nullptr : a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
   int rc;
   const int mode = h16_mode(t);
+  prof_mark(0, s);
   if (mode == 1) rc = h16_use_pairs() ? launch_h16<true, true>(t, z, n, fo, s) : launch_h16<false, true>(t, z, n, fo, s);
   else if (mode == 2) rc = h16_use_pairs() ? launch_h16<true, false, true>(t, z, n, fo, s) : launch_h16<false, false, true>(t, z, n, fo, s);
   else rc = h16_use_pairs() ? launch_h16<true, false>(t, z, n, fo, s) : launch_h16<false, false>(t, z, n, fo, s);
+  prof_mark(1, s);
   if (rc) return rc;
   RLVAE_REQUIRE(g_full == nullptr || g_packed != nullptr, "the expanded G output needs the packed G buffer too");
   if (fused)

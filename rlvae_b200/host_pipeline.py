@@ -41,9 +41,14 @@ class HostEvaluator:
         self.d2h_bytes = 0
 
     def __call__(self, z_host: torch.Tensor, logdet_host: torch.Tensor,
-                 grad_host: Optional[torch.Tensor] = None, ginv_dev: Optional[torch.Tensor] = None) -> Dict:
-        """z_host [N,d] pinned fp32 -> fills logdet_host [N], grad_host [N,d] (pinned).  Returns
-        byte counts.  Synchronises before returning."""
+                 grad_host: Optional[torch.Tensor] = None, ginv_dev: Optional[torch.Tensor] = None,
+                 ginv_host: Optional[torch.Tensor] = None) -> Dict:
+        """z_host [N,d] pinned fp32 -> fills logdet_host [N], grad_host [N,d] and, if given, ginv_host
+        [N,d,d] (all pinned; G^{-1} is 4 d^2 bytes per point, so copying it out makes the call PCIe
+        bound).  Returns byte counts.  Synchronises before returning."""
+        for name, t in (('logdet_host', logdet_host), ('grad_host', grad_host), ('ginv_host', ginv_host)):
+            if t is not None and (t.is_cuda or not t.is_pinned() or not t.is_contiguous() or t.dtype != torch.float32):
+                raise RuntimeError(f'HostEvaluator: {name} must be a contiguous pinned fp32 host tensor')
         if z_host.is_cuda or not z_host.is_pinned():
             raise RuntimeError('HostEvaluator expects pinned host tensors')
         n = z_host.shape[0]
@@ -70,6 +75,9 @@ class HostEvaluator:
                 if self.want_grad and grad_host is not None:
                     grad_host[lo:hi].copy_(b['grad'][:m], non_blocking=True)
                     d2h += m * self.d * 4
+                if ginv_host is not None:
+                    ginv_host[lo:hi].copy_(ginv, non_blocking=True)
+                    d2h += m * self.d * self.d * 4
         for s in self.streams:
             cur.wait_stream(s)
         cur.synchronize()

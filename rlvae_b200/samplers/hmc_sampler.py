@@ -98,9 +98,18 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
     _MAX_DRAW_BYTES = 1 << 30     # random draws generated ahead per launch of the fused trajectory kernel
 
     def _all_scales(self, iters: int, n_lf: int, beta_old, b0_host):
+        """Tempering scales of ``iters`` consecutive MCMC iterations.  The schedule of one iteration only
+        depends on the state it starts from -- beta_zero_sqrt (first iteration) or tempering(n_lf) (carried
+        over, the reference never resets it) -- so each distinct schedule is computed once with the
+        reference's tensor arithmetic and cached (1,500 small tensor ops per ``sample`` call otherwise:
+        ~30 ms of host time, more than the fused kernel needs for the whole chain at small batches)."""
+        cache = self.__dict__.setdefault('_scale_cache', {})
         out = []
         for _ in range(iters):
-            sc, beta_old = self._scales(n_lf, beta_old, b0_host)
+            key = (n_lf, float(b0_host.item()), float(beta_old.item()))
+            if key not in cache:
+                cache[key] = self._scales(n_lf, beta_old, b0_host)
+            sc, beta_old = cache[key]
             out.extend(sc)
         return out, beta_old
 
@@ -168,9 +177,9 @@ class RiemannianHMCSampler(BaseRiemannianSampler):
             it = min(ahead, self.mcmc_steps_nbr - done)
             gammas = torch.empty(it, n_samples, d, device=dev)
             accs = torch.empty(it, n_samples, device=dev)
-            for i in range(it):
-                gammas[i] = torch.randn_like(z)
-                accs[i] = torch.rand(n_samples, device=dev)
+            for i in range(it):          # same generator calls as randn_like(z) / rand(n): normal_ / uniform_ on n*d / n elements
+                gammas[i].normal_()
+                accs[i].uniform_()
             beta_old = self._run_chain(tab, path, z, gammas, accs, n_lf, eps, b0, mode, beta_old, b0_host)
             done += it
         return z.detach()
