@@ -7,9 +7,10 @@ Drop-in names for the reference's hot-path API: ``MetricTensor`
 from .flow_manager import FlowManager
 from .metric_loader import MetricLoader
 from .metric_tensor import MetricTensor
-from .samplers import (BaseRiemannianSampler, MetricModel, RHVAEStyleHMCSampler, RiemannianHMCSampler,
-                       WorkingRiemannianSampler)
+from .samplers import (BaseRiemannianSampler, MetricModel, OfficialRHVAESampler, RHVAEStyleHMCSampler,
+                       RiemannianHMCSampler, WorkingRiemannianSampler)
 
 __all__ = ['MetricTensor', 'MetricLoader', 'BaseRiemannianSampler', 'MetricModel',
-           'RiemannianHMCSampler', 'RHVAEStyleHMCSampler', 'WorkingRiemannianSampler', 'FlowManager']
+           'RiemannianHMCSampler', 'RHVAEStyleHMCSampler', 'OfficialRHVAESampler', 'WorkingRiemannianSampler',
+           'FlowManager']
 __version__ = '0.1.0'

@@ -1,7 +1,7 @@
 from .base_sampler import BaseRiemannianSampler, MetricModel, tables_for
 from .hmc_sampler import RiemannianHMCSampler
-from .rhvae_sampler import RHVAEStyleHMCSampler
+from .rhvae_sampler import OfficialRHVAESampler, RHVAEStyleHMCSampler
 from .riemannian_sampler import WorkingRiemannianSampler
 
-__all__ = ['BaseRiemannianSampler', 'MetricModel', 'RiemannianHMCSampler', 'RHVAEStyleHMCSampler', 'WorkingRiemannianSampler',
+__all__ = ['BaseRiemannianSampler', 'MetricModel', 'RiemannianHMCSampler', 'RHVAEStyleHMCSampler', 'OfficialRHVAESampler', 'WorkingRiemannianSampler',
            'tables_for']

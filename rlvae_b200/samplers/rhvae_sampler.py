@@ -11,8 +11,14 @@ iterations, everything runs under ``no_grad``.  The wrapper class of the referen
 (``src/models/samplers/rhvae_sampler.py``) builds a full pythae ``RHVAE`` model around the
 encoder/decoder; that model object is out of scope, the sampling arithmetic is here.
 
-Per leapfrog step: two metric evaluations (fused forward kernel -> G) and two gradient
-contractions; the momentum / position updates are element-wise torch ops on the device.
+Per leapfrog step: ONE metric evaluation (fused forward kernel -> G) and one gradient contraction -- the
+reference evaluates the same gradient at the end of step k and at the start of step k + 1 (:110-131, z
+does not move in between), here it is carried over; the momentum / position updates are element-wise
+torch ops on the device.
+
+``OfficialRHVAESampler`` mirrors the reference's wrapper class (ref src/models/samplers/rhvae_sampler.py:
+13-255) -- same name, methods and quirks (temperature hard-coded to 0.1 at :62/:80, prior batches of at
+most 32 at :186, 100 x 15 leapfrog steps of 0.03 at :103-108) -- around that loop.
 """
 from __future__ import annotations
 
@@ -60,25 +66,27 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
         return 1 / beta_k
 
     # ------------------------------------------------------------------ the sampling loop (ref :98-148)
-    def hmc_sampling_with_streams(self, idx0: torch.Tensor, gammas: torch.Tensor, accs: torch.Tensor,
-                                  record: Optional[dict] = None) -> torch.Tensor:
+    def hmc_sampling_with_streams(self, idx0: Optional[torch.Tensor], gammas: torch.Tensor, accs: torch.Tensor,
+                                  record: Optional[dict] = None, z_start: Optional[torch.Tensor] = None,
+                                  state: Optional[dict] = None) -> torch.Tensor:
         """The loop with its random draws injected: ``idx0 [n]`` (line 100), ``gammas [steps,n,d]``
-        (line 107), ``accs [steps,n]`` (line 141)."""
+        (line 107), ``accs [steps,n]`` (line 141).  ``z_start`` / ``state`` continue a chain whose draws
+        arrive in several slabs (the tempering state is never reset, line 104)."""
         with torch.no_grad():
-            z0 = self.model.centroids_tens[idx0].float().contiguous()
+            z0 = (self.model.centroids_tens[idx0] if z_start is None else z_start).float().contiguous()
             n, d = z0.shape
             b0 = self.beta_zero_sqrt
-            beta_old = b0
+            beta_old = b0 if state is None else state['beta_old']
             z = z0
             eps = self.eps_lf
             for i in range(gammas.shape[0]):
                 rho = gammas[i] / b0
                 h0 = -self.log_sqrt_det_G_inv(z) + 0.5 * torch.norm(rho, dim=1) ** 2
+                g = -self.grad_log_sqrt_det_G_inv(z)
                 for k in range(self.n_lf):
-                    g = -self.grad_log_sqrt_det_G_inv(z)
                     rho_ = rho - (eps / 2) * g
                     z = (z + eps * rho_).contiguous()
-                    g = -self.grad_log_sqrt_det_G_inv(z)
+                    g = -self.grad_log_sqrt_det_G_inv(z)          # also the first gradient of step k + 1
                     rho__ = rho_ - (eps / 2) * g
                     beta_new = self.tempering(k + 1, self.n_lf, b0)
                     rho = (beta_old / beta_new) * rho__
@@ -92,15 +100,30 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
                     for name, val in (('H0', h0), ('H', h), ('alpha', alpha), ('moves', moves.reshape(-1)),
                                       ('z', z.clone())):
                         record.setdefault(name, []).append(val)
+            if state is not None:
+                state['beta_old'] = beta_old
             return z
 
     def hmc_sampling(self, n_samples: int) -> torch.Tensor:
         dev = self.device
         idx = torch.randint(len(self.model.centroids_tens), (n_samples,), device=dev)
         d = self.model.latent_dim
-        gammas = torch.randn(self.mcmc_steps_nbr, n_samples, d, device=dev)
-        accs = torch.rand(self.mcmc_steps_nbr, n_samples, device=dev)
-        return self.hmc_sampling_with_streams(idx, gammas, accs)
+        # drawn per iteration, in the reference's order (gamma :107, then acc :141), in slabs of at most
+        # ~256 MB so that a large batch does not hold mcmc_steps x n x d draws at once
+        z = None
+        step = max(1, min(self.mcmc_steps_nbr, (1 << 26) // max(n_samples * (d + 1), 1)))
+        done = 0
+        state = dict(beta_old=self.beta_zero_sqrt)
+        while done < self.mcmc_steps_nbr:
+            it = min(step, self.mcmc_steps_nbr - done)
+            gammas = torch.empty(it, n_samples, d, device=dev)
+            accs = torch.empty(it, n_samples, device=dev)
+            for i in range(it):
+                gammas[i].normal_()
+                accs[i].uniform_()
+            z = self.hmc_sampling_with_streams(idx if z is None else None, gammas, accs, z_start=z, state=state)
+            done += it
+        return z
 
     # ------------------------------------------------------------------ BaseRiemannianSampler surface
     def sample_prior(self, num_samples: int, method: str = 'official') -> torch.Tensor:
@@ -117,3 +140,116 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
         info.update({'mcmc_steps_nbr': self.mcmc_steps_nbr, 'n_lf': self.n_lf, 'eps_lf': self.eps_lf,
                      'beta_zero_sqrt': self.beta_zero_sqrt})
         return info
+
+
+class _FixedTemperatureModel:
+    """The sampler protocol of ``model`` with another temperature -- what setup_official_rhvae builds
+    (ref src/models/samplers/rhvae_sampler.py:83-101: same centroids / M / lambda, temperature.data = 0.1)."""
+
+    def __init__(self, model, temperature: float):
+        self._model = model
+        self.temperature = torch.as_tensor(float(temperature), device=model.centroids_tens.device)
+        self.latent_dim = model.latent_dim
+
+    centroids_tens = property(lambda self: self._model.centroids_tens)
+    M_tens = property(lambda self: self._model.M_tens)
+    lbd = property(lambda self: self._model.lbd)
+    device = property(lambda self: self._model.centroids_tens.device)
+
+    def parameters(self):
+        return self._model.parameters()
+
+    def G_inv(self, z):
+        from ..metric_tensor import _InverseMetricFn
+        from .hmc_sampler import _TabOwner
+        return _InverseMetricFn.apply(z.float(), _TabOwner(tables_for(self)), kernel_path_for(self._model))
+
+    def G(self, z):
+        return torch.linalg.inv(self.G_inv(z))
+
+
+class OfficialRHVAESampler(BaseRiemannianSampler):
+    """Drop-in for the reference's ``OfficialRHVAESampler`` (ref src/models/samplers/rhvae_sampler.py).
+
+    The reference builds a pythae ``RHVAE`` model object around the encoder / decoder (out of scope) only to
+    hand its sampler the metric with the temperature overwritten by 0.1 (:62, :80); what the two public
+    methods then compute is mirrored here on the CUDA kernels:
+
+    * ``sample_riemannian_latents(mu, log_var, 'official')`` (:108-167): G_inv(mu) at T = 0.1,
+      ``cholesky(G_inv + 1e-6 I) @ eps``, ``z = mu + 0.1 * (L eps) * sigma`` -- differentiable w.r.t. mu and
+      log_var like the reference; a failed factorisation or any other error falls back to standard
+      reparameterisation;
+    * ``sample_prior(n, 'official')`` (:169-191): pythae's manifold HMC (100 MCMC steps x 15 leapfrog steps of
+      0.03, beta_zero 1) in batches of ``min(32, n)`` (:186) -- the latent samples are returned (the
+      reference's pythae sampler goes on to decode them with the model's decoder, which is not part of
+      the metric path).
+    """
+
+    HARD_CODED_TEMPERATURE = 0.1      # ref :62 and :80 ("Same hardcoded value as test")
+    PRIOR_BATCH = 32                  # ref :186
+
+    def __init__(self, model):
+        super().__init__(model)
+        self._rhvae_model = None
+        self._rhvae_sampler = None
+
+    def setup_official_rhvae(self):
+        if not self.validate_metric_availability():
+            raise RuntimeError('Model must have loaded metric tensors first')
+        self._rhvae_model = _FixedTemperatureModel(self.model, self.HARD_CODED_TEMPERATURE)
+        self._rhvae_sampler = RHVAEStyleHMCSampler(self._rhvae_model, mcmc_steps_nbr=100, n_lf=15, eps_lf=0.03,
+                                                   beta_zero=1.0)
+
+    def official_with_noise(self, mu, log_var, eps):
+        """The main path of :121-152 with ``eps`` supplied."""
+        from .riemannian_sampler import _CholApplyFn
+        if self._rhvae_model is None:
+            self.setup_official_rhvae()
+        g_inv = self._rhvae_model.G_inv(mu)
+        eps_t = _CholApplyFn.apply(g_inv, eps, 1e-6)      # raises if not positive definite -> caller's fallback
+        return mu + eps_t * torch.exp(0.5 * log_var) * 0.1
+
+    def sample_riemannian_latents(self, mu, log_var, method: str = 'official'):
+        if method != 'official':
+            return mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
+        try:
+            if self._rhvae_model is None:
+                self.setup_official_rhvae()
+            eps = torch.randn_like(mu)
+            try:
+                return self.official_with_noise(mu, log_var, eps)
+            except Exception:           # ref :149-151: Cholesky failed -> standard sampling with the same eps
+                return mu + eps * torch.exp(0.5 * log_var)
+        except Exception as e:
+            print(f'⚠️ Official RHVAE sampling failed: {e}, using standard reparam')
+            return mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
+
+    def sample_prior(self, num_samples: int, method: str = 'official'):
+        if method != 'official':
+            return torch.randn(num_samples, self.model.latent_dim, device=self.device)
+        if self._rhvae_sampler is None:
+            self.setup_official_rhvae()
+        bs = min(self.PRIOR_BATCH, num_samples)
+        out = []
+        with torch.no_grad():
+            for _ in range(num_samples // bs):                       # pythae RHVAESampler.sample :61-67
+                out.append(self._rhvae_sampler.hmc_sampling(bs))
+            if num_samples % bs:
+                out.append(self._rhvae_sampler.hmc_sampling(num_samples % bs))
+        return torch.cat(out, dim=0)
+
+    def get_sampling_methods(self) -> Dict[str, str]:
+        return {'official': 'Official RHVAE sampling with HMC',
+                'standard': 'Standard reparameterization (fallback)'}
+
+    def get_rhvae_info(self) -> Dict[str, Any]:
+        info = {'rhvae_available': True, 'rhvae_model_created': self._rhvae_model is not None,
+                'rhvae_sampler_created': self._rhvae_sampler is not None}
+        if self._rhvae_model is not None:
+            info.update({'rhvae_temperature': float(self._rhvae_model.temperature.item()),
+                         'rhvae_regularization': float(self._rhvae_model.lbd),
+                         'rhvae_latent_dim': self._rhvae_model.latent_dim})
+        return info
+
+    def validate_metric_availability(self) -> bool:
+        return all(hasattr(self.model, a) for a in ('centroids_tens', 'M_tens', 'G', 'G_inv', 'temperature', 'lbd'))

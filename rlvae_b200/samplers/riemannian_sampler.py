@@ -180,23 +180,47 @@ class WorkingRiemannianSampler(BaseRiemannianSampler):
             print(f'⚠️ Geodesic prior sampling failed: {e}, using basic method')
             return self.sample_basic_prior(num_samples)
 
+    def centroid_aware_prior_with_noise(self, centroid_indices, noise):
+        """:290-311 with the randint (:303) and randn_like (:308) draws supplied."""
+        z_c = self.model.centroids_tens[centroid_indices]
+        return z_c + noise * 0.1
+
     def sample_centroid_aware_prior(self, num_samples: int):
         if not self.validate_metric_availability():
             return torch.randn(num_samples, self.model.latent_dim, device=self.device)
+        try:
+            cents = self.model.centroids_tens
+            pick = torch.randint(0, cents.shape[0], (num_samples,), device=self.device)
+            return self.centroid_aware_prior_with_noise(pick, torch.randn_like(cents[pick]))
+        except Exception as e:
+            print(f'⚠️ Centroid-aware prior sampling failed: {e}, using basic method')
+            return self.sample_basic_prior(num_samples)
+
+    def weighted_mixture_prior_with_noise(self, component_indices, noise_in_call_order):
+        """:319-349 with the draws supplied.  The reference loops over the K components and draws
+        ``randn(count_i, d)`` for every non-empty one (:337-343), writing the rows of component i in
+        increasing sample order; ``noise_in_call_order [n,d]`` is those draws concatenated in call order,
+        i.e. row r belongs to the r-th sample when the samples are stably sorted by component.  One
+        sort + one scatter instead of K masked writes."""
         cents = self.model.centroids_tens
-        pick = torch.randint(0, cents.shape[0], (num_samples,), device=self.device)
-        z_c = cents[pick]
-        return z_c + torch.randn_like(z_c) * 0.1
+        order = torch.argsort(component_indices, stable=True)
+        z = torch.empty(component_indices.shape[0], self.model.latent_dim, device=cents.device, dtype=cents.dtype)
+        z[order] = cents[component_indices[order]] + noise_in_call_order * 0.1
+        return z
 
     def sample_weighted_mixture_prior(self, num_samples: int):
-        """Mixture of N(c_k, 0.1^2 I) with uniform component choice.  Same distribution as the
-        reference's Python loop over K (:337-343), one gather instead of K masked writes (the
-        per-component draw order of the reference is not reproduced)."""
+        """Mixture of N(c_k, 0.1^2 I) with uniform component choice (one randn call for all components:
+        same distribution as the reference's per-component calls, not the same generator positions)."""
         if not self.validate_metric_availability():
             return torch.randn(num_samples, self.model.latent_dim, device=self.device)
-        cents = self.model.centroids_tens
-        comp = torch.randint(0, cents.shape[0], (num_samples,), device=self.device)
-        return cents[comp] + torch.randn(num_samples, self.model.latent_dim, device=self.device) * 0.1
+        try:
+            cents = self.model.centroids_tens
+            comp = torch.randint(0, cents.shape[0], (num_samples,), device=self.device)
+            noise = torch.randn(num_samples, self.model.latent_dim, device=self.device)
+            return self.weighted_mixture_prior_with_noise(comp, noise)
+        except Exception as e:
+            print(f'⚠️ Weighted mixture prior sampling failed: {e}, using basic method')
+            return self.sample_basic_prior(num_samples)
 
     def sample_basic_prior(self, num_samples: int):
         return torch.randn(num_samples, self.model.latent_dim, device=self.device)

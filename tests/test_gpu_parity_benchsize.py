@@ -183,3 +183,81 @@ def test_fused_hmc_trajectory_is_one_launch_and_matches_the_per_step_path():
         assert clear.float().mean() > 0.9
         torch.testing.assert_close(zf[clear], zu[clear], rtol=2e-4, atol=2e-4)
         assert torch.equal(rf['stats'][3][:, clear], ru['stats'][3][:, clear])
+
+
+@pytest.mark.parametrize('case', ['losses_d16_k300', 'losses_d16_k10k'])
+def test_losses_through_the_drop_in_match_the_reference(case):
+    """A21 (SURVEY.md 8f rank 1's purpose): the reference's loss arithmetic -- LossManager.
+    compute_riemannian_kl_loss (loss_manager.py:75-146) and the monolith KLs (riemannian_flow_vae.py:
+    1004-1077, 1328-1394), restated in oracle/losses_oracle.py and pinned against the real reference --
+    driven through the CUDA drop-in MetricTensor: loss value and the gradients w.r.t. mu and log_var
+    (autograd through rlvae_metric_grad / the batched inverse) against the reference's own numbers."""
+    from oracle import losses_oracle as LO
+    from rlvae_b200.synthetic import make_synthetic_metric
+    g = load_golden(case)
+    if 'centroids' in g:
+        t = (g['centroids'], g['matrices'], float(g['temperature']), float(g['regularization']))
+    else:
+        sm = make_synthetic_metric(int(g['n_centroids']), 16, seed=int(g['table_seed']))
+        t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    mt = make_mt(t, 'auto').to(dev())        # LossManager calls .to(device) on it (loss_manager.py:106-107)
+    fns = {'modular_kl': lambda m, lv, z: LO.modular_riemannian_kl(m, lv, z, mt),
+           'mono_metric_kl': lambda m, lv, z: LO.monolith_metric_kl(m, lv, z, mt.compute_metric),
+           'mono_kl': lambda m, lv, z: LO.monolith_riemannian_kl(m, lv, z, mt.compute_metric)}
+    for tag, fn in fns.items():
+        m = g['mu'].to(dev()).requires_grad_(True)
+        lv = g['log_var'].to(dev()).requires_grad_(True)
+        z = m + g['eps'].to(dev()) * torch.exp(0.5 * lv)
+        loss = fn(m, lv, z)
+        loss.backward()
+        ref = float(g[tag + '_loss'])
+        assert abs(float(loss.detach()) - ref) <= 1e-5 * (1 + abs(ref)), (tag, float(loss.detach()), ref)
+        for got, want in ((m.grad, g[tag + '_dmu']), (lv.grad, g[tag + '_dlogvar'])):
+            err = (got.cpu().double() - want.double()).norm() / want.double().norm().clamp_min(1e-30)
+            assert err < 1e-4, (tag, float(err))
+
+
+def test_prior_samplers_and_official_sampler_match_the_reference():
+    """A17 (riemannian_sampler.py:222-355) with the reference's recorded draws injected -- centroid_aware,
+    weighted_mixture (draws in the reference's per-component call order) and basic, next to the geodesic
+    prior of test_samplers_match_reference -- and the training-time path of OfficialRHVAESampler
+    (src/models/samplers/rhvae_sampler.py:108-167: temperature hard-coded to 0.1) against the outputs of the
+    real reference classes (oracle/make_golden_priors.py)."""
+    from rlvae_b200 import MetricModel, OfficialRHVAESampler, WorkingRiemannianSampler
+    from rlvae_b200.synthetic import make_synthetic_metric
+    g = load_golden('priors_synth_d16_k300')
+    sm = make_synthetic_metric(int(g['n_centroids']), 16, seed=int(g['table_seed']))
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    model = MetricModel(make_mt(t, 'auto'))
+    ws = WorkingRiemannianSampler(model)
+    D = lambda k: g[k].to(dev())
+    torch.testing.assert_close(ws.centroid_aware_prior_with_noise(D('ca_idx'), D('ca_noise')).cpu(), g['ca_z'],
+                               rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(ws.weighted_mixture_prior_with_noise(D('wm_idx'), D('wm_noise')).cpu(), g['wm_z'],
+                               rtol=1e-6, atol=1e-6)
+    assert torch.equal(g['basic_noise'], g['basic_z'])        # the reference's basic prior IS its randn draw
+    for m in ('geodesic', 'centroid_aware', 'weighted_mixture', 'basic'):
+        z = ws.sample_prior(33, method=m)
+        assert z.shape == (33, 16) and torch.isfinite(z).all()
+    # weighted mixture: every sample sits within a few noise standard deviations of ITS component's centroid
+    comp = torch.randint(0, 300, (500,), device=dev())
+    zz = ws.weighted_mixture_prior_with_noise(comp, torch.randn(500, 16, device=dev()))
+    assert ((zz - model.centroids_tens[comp]).norm(dim=1) < 0.1 * 16 ** 0.5 * 3).all()
+    # OfficialRHVAESampler: name, surface, hard-coded temperature, training-time path
+    off = OfficialRHVAESampler(model)
+    assert set(off.get_sampling_methods()) == {'official', 'standard'}
+    z = off.official_with_noise(D('off_mu'), D('off_log_var'), D('off_eps'))
+    assert abs(off.get_rhvae_info()['rhvae_temperature'] - 0.1) < 1e-7
+    torch.testing.assert_close(z.cpu(), g['off_z'], rtol=2e-5, atol=2e-5)
+    # differentiable w.r.t. mu and log_var like the reference's (:143-148)
+    mu = D('off_mu').clone().requires_grad_(True)
+    lv = D('off_log_var').clone().requires_grad_(True)
+    off.official_with_noise(mu, lv, D('off_eps')).sum().backward()
+    assert torch.isfinite(mu.grad).all() and torch.isfinite(lv.grad).all() and lv.grad.abs().sum() > 0
+    assert off.sample_riemannian_latents(D('off_mu'), D('off_log_var')).shape == (32, 16)
+    assert off.sample_riemannian_latents(D('off_mu'), D('off_log_var'), method='standard').shape == (32, 16)
+    # prior: batches of at most 32 (:186), 100 MCMC steps x 15 leapfrog; latents returned
+    off._rhvae_sampler.mcmc_steps_nbr = 3                      # keep the test short: the loop itself is pinned by
+    zp = off.sample_prior(40)                                  # test_pythae_variant_hmc_matches_reference_chain
+    assert zp.shape == (40, 16) and torch.isfinite(zp).all()
+    assert off.sample_prior(5, method='basic').shape == (5, 16)

@@ -119,3 +119,31 @@ def test_pythae_hmc_oracle_matches_reference_chain(case):
     z = O.rhvae_hmc_sample(t, g['idx0'], g['gamma'], g['acc'], int(g['n_lf']), float(g['eps_lf']),
                            float(g['beta_zero']))
     torch.testing.assert_close(z, g['z_final'], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('case', ['losses_d16_k300', 'losses_d16_k10k'])
+def test_loss_oracle_matches_reference_losses(case):
+    """A21: the restated loss arithmetic (oracle/losses_oracle.py) on the CPU oracle metric reproduces the
+    real reference's LossManager.compute_riemannian_kl_loss and the monolith KLs -- value and gradients
+    w.r.t. mu / log_var (goldens: oracle/make_golden_losses.py)."""
+    from oracle import losses_oracle as LO
+    from rlvae_b200.synthetic import make_synthetic_metric
+    g = load_golden(case)
+    if 'centroids' in g:
+        t = tables_of(g)
+    else:
+        sm = make_synthetic_metric(int(g['n_centroids']), 16, seed=int(g['table_seed']))
+        t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    metric = LO.OracleMetric(*t)
+    fns = {'modular_kl': lambda m, lv, z: LO.modular_riemannian_kl(m, lv, z, metric),
+           'mono_metric_kl': lambda m, lv, z: LO.monolith_metric_kl(m, lv, z, metric.compute_metric),
+           'mono_kl': lambda m, lv, z: LO.monolith_riemannian_kl(m, lv, z, metric.compute_metric)}
+    for tag, fn in fns.items():
+        m = g['mu'].clone().requires_grad_(True)
+        lv = g['log_var'].clone().requires_grad_(True)
+        z = m + g['eps'] * torch.exp(0.5 * lv)
+        loss = fn(m, lv, z)
+        loss.backward()
+        assert abs(float(loss) - float(g[tag + '_loss'])) <= 1e-6 * (1 + abs(float(g[tag + '_loss']))), tag
+        torch.testing.assert_close(m.grad, g[tag + '_dmu'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(lv.grad, g[tag + '_dlogvar'], rtol=1e-5, atol=1e-6)
