@@ -666,7 +666,7 @@ def bench_d64(dev, world, rank, barrier, max_over_ranks, n=1 << 20, K64=50000, c
                       'tflops_fp32_equiv_dense': world * n * 2.0 * K64 * d * (d + 1) / (ms * 1e-3) / 1e12}
     res['finite'] = bool(torch.isfinite(out['logdet_g']).all().item())
     # with the gradient: full size when the gradient runs on the tensor cores, a bounded sample otherwise
-    tensor_grad = 'gradient on the direct kernel' not in str(info.get('implementation'))
+    tensor_grad = 'gradient: partial tiles' in str(info.get('implementation'))
     ng = n if tensor_grad else 4096
     run(True, min(ng, chunk))
     barrier()

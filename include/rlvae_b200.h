@@ -108,6 +108,12 @@ int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* l
  * out [N,d].                                                                                  */
 int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, int64_t n,
                       float scale, float* out, int path, void* stream);
+/* The same with a workspace of rlvae_metric_grad_workspace(n, d) bytes (0 for d != 64): d = 64 symmetric
+ * tables then run the column-tiled tcgen05 gradient kernel (partial results per 128-column tile + a
+ * fixed-order reduction); without a workspace d = 64 uses the CUDA-core kernel.                 */
+int64_t rlvae_metric_grad_workspace(int64_t n, int d);   /* bytes */
+int rlvae_metric_grad_ws(const rlvae_tables_t* t, const float* z, const float* u, int64_t n,
+                         float scale, float* out, void* work, int path, void* stream);
 
 /* ---- variant C (pythae): (1/T^2) G^T sum_k w_k M_k^T (c_k - z) -------------------------------
  * ref: src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187.

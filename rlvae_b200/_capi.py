@@ -37,6 +37,8 @@ _SIGNATURES = [
     ('rlvae_inverse_metric_packed', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ('rlvae_batched_inverse', c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p]),
+    ('rlvae_metric_grad_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_metric_grad_ws', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad_pythae_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
@@ -221,9 +223,11 @@ def metric_grad(tab: Tables, z: torch.Tensor, u: torch.Tensor, scale: float, pat
     if tuple(u.shape) != (z.shape[0], tab.d, tab.d) or u.device != z.device:
         raise ValueError(f'u must be [{z.shape[0]}, {tab.d}, {tab.d}] on {z.device}, got {tuple(u.shape)} on {u.device}')
     out = torch.empty_like(z)
+    need = int(lib().rlvae_metric_grad_workspace(z.shape[0], tab.d))
+    work = torch.empty(need, device=z.device, dtype=torch.uint8) if need > 0 else None
     with torch.cuda.device(z.device):
-        _check(lib().rlvae_metric_grad(tab.handle, _ptr(z), _ptr(u), z.shape[0], c_float(scale), _ptr(out),
-                                       path, _stream(z)), 'rlvae_metric_grad')
+        _check(lib().rlvae_metric_grad_ws(tab.handle, _ptr(z), _ptr(u), z.shape[0], c_float(scale), _ptr(out),
+                                          _ptr(work), path, _stream(z)), 'rlvae_metric_grad')
     return out
 
 

@@ -295,6 +295,9 @@ static void free_tables(rlvae_tables* t) {
   if (t->Mnh_hi) cudaFree(t->Mnh_hi);
   if (t->Mnh_lo) cudaFree(t->Mnh_lo);
   if (t->c64h) cudaFree(t->c64h);
+  if (t->ct64_hi) cudaFree(t->ct64_hi);
+  if (t->ct64_lo) cudaFree(t->ct64_lo);
+  t->ct64_hi = t->ct64_lo = nullptr;
   if (t->c16h) cudaFree(t->c16h);
   if (t->cbias_h) cudaFree(t->cbias_h);
   if (t->cshift) cudaFree(t->cshift);
@@ -707,8 +710,12 @@ int rlvae_batched_inverse(const float* a, int64_t n, int d, float* inv, float* l
                                 static_cast<cudaStream_t>(stream));
 }
 
-int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, int64_t n, float scale,
-                      float* out, int path, void* stream) {
+int64_t rlvae_metric_grad_workspace(int64_t n, int d) {
+  return d == 64 ? (int64_t)sizeof(float) * metric_grad_h64_scratch_floats(n) : 0;
+}
+
+int rlvae_metric_grad_ws(const rlvae_tables_t* t, const float* z, const float* u, int64_t n, float scale,
+                         float* out, void* work, int path, void* stream) {
   RLVAE_REQUIRE(t != nullptr, "metric_grad: tables handle is NULL (metric not loaded)");
   RLVAE_REQUIRE(n >= 0, "metric_grad: negative batch");
   if (n == 0) return 0;
@@ -716,8 +723,15 @@ int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, i
   bool use_tc;
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return (use_tc && t->d == 16) ? launch_metric_grad_tc(t, z, u, n, scale, out, s)
-                                : launch_metric_grad_direct(t, z, u, n, scale, out, s);   // d = 64: forward only
+  if (use_tc && t->d == 16) return launch_metric_grad_tc(t, z, u, n, scale, out, s);
+  if (use_tc && t->d == 64 && work != nullptr && metric_grad_h64_available(t))
+    return launch_metric_grad_h64(t, z, u, n, scale, out, static_cast<float*>(work), s);
+  return launch_metric_grad_direct(t, z, u, n, scale, out, s);
+}
+
+int rlvae_metric_grad(const rlvae_tables_t* t, const float* z, const float* u, int64_t n, float scale,
+                      float* out, int path, void* stream) {
+  return rlvae_metric_grad_ws(t, z, u, n, scale, out, nullptr, path, stream);    // d = 64 without a workspace: direct kernel
 }
 
 int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d) {
@@ -792,8 +806,9 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   }
   if (grad_logdet_g != nullptr) {
     // grad_z log det G = -(2/T^2) sum_k w_k tr(G M_k) (c_k - z)
-    if (int rc = rlvae_metric_grad(t, z, need_gt ? gt_buf : g_buf, n, -2.f / t->T2, grad_logdet_g, path,
-                                   stream))
+    // (d = 64 tensor kernel: the G^T slot of the workspace is free for symmetric tables -- its partial tiles live there)
+    if (int rc = rlvae_metric_grad_ws(t, z, need_gt ? gt_buf : g_buf, n, -2.f / t->T2, grad_logdet_g,
+                                      need_gt ? nullptr : gt_buf, path, stream))
       return rc;
   }
   return 0;

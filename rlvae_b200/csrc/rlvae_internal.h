@@ -129,6 +129,11 @@ struct rlvae_tables {
   float c64_unscale = 0.f;     // 2^-ec
   float r2mean_centred = 0.f;  // mean ||c - cshift||^2 (d == 64: set by tc_build_h64_tables)
   CUtensorMap tm_c64, tm_c64_2;   // boxes of 32 centroids x 32 (pair: 16) rows
+  // d == 64 gradient kernel: (c - shift)^T scaled by 2^ec, split fp16 [64, Kpad]; Mnh_hi / Mnh_lo then hold the
+  // natural [Kpad, 2176] tables
+  void* ct64_hi = nullptr;
+  void* ct64_lo = nullptr;
+  CUtensorMap tm_ct64_hi, tm_ct64_lo, tm_ct64_2_hi, tm_ct64_2_lo;
   // pythae-variant gradient (A8): [K, d*d+d] = [M_k | M_k^T c_k], built on first use (derived cache)
   mutable float* pythae_aug = nullptr;
 };
@@ -166,6 +171,11 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s);
 int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, float* ginv, float* packed_scratch,
                               cudaStream_t s);
 constexpr int kSym64Cols = 2176;
+// d == 64 gradient on the tensor cores (column-tiled like the forward kernel; partial tiles + reduction)
+bool metric_grad_h64_available(const rlvae_tables* t);
+int64_t metric_grad_h64_scratch_floats(int64_t n);
+int launch_metric_grad_h64(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
+                           float* scratch, cudaStream_t s);
 int launch_nearest2_tc(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s);
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);

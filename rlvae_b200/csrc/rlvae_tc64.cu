@@ -393,6 +393,532 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
   }
 }
 
+// ==========================================================================================
+// Gradient / backward kernel for latent_dim == 64, symmetric tables (BASELINE.json configs[4]):
+//   out[n,:] = scale * sum_k w_nk <U_n, M_k> (c_k - z_n)            (rlvae_metric_grad, K4)
+// The 2080 packed columns of <U, M_k> are linear in the column range, so -- like the forward kernel --
+// blockIdx.y selects a tile of 128 packed columns and the CTA produces the PARTIAL result of its tile
+//   out^(c)[n,:] = scale * sum_k w_nk t^(c)_nk (c_k - z_n),   t^(c)_nk = sum_{p in tile c} Ut_np M_kp
+// into partial[c][n][:]; reduce_partials64_kernel adds the 17 tiles in a fixed order (deterministic).
+// Every column tile recomputes the distance GEMM and the exp stage for its 128 points (as the forward
+// kernel does).  Per 64-centroid super-block, all on kind::f16 with the split hi + lo operands:
+//   GEMM1  S[128 x 64]  = Z'.C'^T           12 MMAs, A = z' tiles in SHARED memory (TMEM is full)
+//   T-GEMM T[128 x 64]  = U'.M'^T           24 MMAs (K = 128 columns), A = U' (hi | lo) resident in TMEM,
+//                                           B = natural table tiles [64 centroids x 128 columns]
+//   exp    u' = 2^-21 w t, split hi | lo fp16, written over S (the layout of the forward kernel's P)
+//   GEMM3  OUT[128 x 64] += u'.C'            12 MMAs, B = (c - shift)^T tiles [64 dims x 64 centroids]
+// = 384 + 768 + 384 tensor cycles.  u' <= 2^14 because |t'| <= 128 * 2^28; both fp16 operands of GEMM3 are exact
+// hi + lo sums down to 2^-25 absolute (2^-39 of the largest u').
+// TMEM: [0,64) U'_hi, [64,128) U'_lo, [128,384) two (S | T) buffers, [384,512) two OUT chunk accumulators.
+// Warps: 0 TMA (C, bias, C^T), 1 MMA issuer (GEMM1 + T), 2-5 / 6-9 exp groups (32 centroids each of every
+// super-block), 10 TMA (table tiles), 11 MMA issuer (GEMM3).
+// ==========================================================================================
+namespace g64 {
+constexpr int D = 64;
+constexpr int THREADS = 384;
+constexpr int C_STAGES = 4;
+constexpr int M_STAGES = 2;
+constexpr int NT = 128;                                   // packed columns per CTA = K of the T GEMM
+constexpr int KSTEPS = NT / 16;
+constexpr int NTILES = h64::NPAD / NT;                    // 17
+constexpr uint32_t ZA_BYTES = TILE_M * 128;               // [128 points x 64 dims] fp16: one swizzle row per point
+constexpr uint32_t C_TILE64 = h64::C_TILE64;              // [64 centroids x (hi atom | lo atom)]
+constexpr uint32_t CT_HALF = D * 128;                     // [64 dims x 64 centroids] fp16 (pair: 32 rows used)
+constexpr uint32_t CT_TILE = 2 * CT_HALF;                 // hi, lo
+constexpr uint32_t M_HALF = 2 * BK * 128;                 // 2 column atoms (64 fp16 each) x 64 centroid rows
+constexpr uint32_t M_TILE = 2 * M_HALF;                   // hi, lo
+constexpr uint32_t OFF_ZA = 0;
+constexpr uint32_t OFF_C = OFF_ZA + 2 * ZA_BYTES;
+constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE64;
+constexpr uint32_t OFF_M = OFF_CT + C_STAGES * CT_TILE;
+constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE;
+constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
+constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TM_UHI = 0, TM_ULO = 64, TM_ST = 128, TM_OUT = 384;
+constexpr int RED_LD = 68;
+static_assert(TILE_M * RED_LD * 4 <= M_STAGES * M_TILE, "group-combine staging must fit the M ring");
+constexpr float U_DOWN = 4.76837158203125e-07f;           // 2^-21
+constexpr float U_UP = 2097152.f;                         // 2^21
+}  // namespace g64
+
+// per-point exponent eU with max|2^eU Ut| in [2^13, 2^14): Ut_p = U_ij + U_ji <= 2 max|U|
+__global__ void u_scale64_kernel(const float* __restrict__ u, int64_t n, int* __restrict__ eu) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t p = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); p < n; p += (int64_t)gridDim.x * warps) {
+    const float4* row = reinterpret_cast<const float4*>(u + p * 4096);
+    float m = 0.f;
+    for (int i = lane; i < 1024; i += 32) {
+      const float4 v = __ldg(row + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    m *= 2.f;
+    int e = 0;
+    if (m > 0.f && m < 3.0e38f) {
+      const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;    // m = f 2^ex, f in [0.5, 1)
+      e = 14 - ex;
+      e = e > 50 ? 50 : (e < -50 ? -50 : e);
+    }
+    if (lane == 0) eu[p] = e;
+  }
+}
+
+__global__ void reduce_partials64_kernel(const float* __restrict__ partial, int64_t n, int ntiles,
+                                         float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index into [n, 64]
+  if (i >= n * 16) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < ntiles; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)c * n * 64) + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = acc;
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(g64::THREADS, 1)
+metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
+                       const __grid_constant__ CUtensorMap tm_mn_hi,
+                       const __grid_constant__ CUtensorMap tm_mn_lo,
+                       const __grid_constant__ CUtensorMap tm_ct_hi,
+                       const __grid_constant__ CUtensorMap tm_ct_lo,
+                       const float* __restrict__ z, const float* __restrict__ u /* [N,64,64] */,
+                       const int* __restrict__ eu /* [N] per-point exponent of U' */,
+                       const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
+                       float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
+                       const float* __restrict__ cshift /* [64] */, float* __restrict__ partial /* [17, N, 64] */) {
+  constexpr int C_STAGES = g64::C_STAGES, M_STAGES = g64::M_STAGES, RED_LD = g64::RED_LD, KSTEPS = g64::KSTEPS,
+                D = g64::D, NT = g64::NT;
+  constexpr uint32_t C_TILE64 = g64::C_TILE64, CT_HALF = g64::CT_HALF, CT_TILE = g64::CT_TILE, M_HALF = g64::M_HALF,
+                     M_TILE = g64::M_TILE, OFF_ZA = g64::OFF_ZA, OFF_C = g64::OFF_C, OFF_CT = g64::OFF_CT,
+                     OFF_M = g64::OFF_M, OFF_BIAS = g64::OFF_BIAS, ZA_BYTES = g64::ZA_BYTES,
+                     TM_UHI = g64::TM_UHI, TM_ULO = g64::TM_ULO, TM_ST = g64::TM_ST, TM_OUT = g64::TM_OUT;
+  constexpr int CHUNK = 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + g64::OFF_BAR;
+  auto BAR_C_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_C_EMPTY = [&](int s) { return bar0 + 8u * (C_STAGES + s); };
+  auto BAR_B_FULL = [&](int s) { return bar0 + 8u * (2 * C_STAGES + s); };
+  auto BAR_CT_FULL = [&](int s) { return bar0 + 8u * (3 * C_STAGES + s); };
+  auto BAR_CT_EMPTY = [&](int s) { return bar0 + 8u * (4 * C_STAGES + s); };
+  auto BAR_M_FULL = [&](int s) { return bar0 + 8u * (5 * C_STAGES + s); };
+  auto BAR_M_EMPTY = [&](int s) { return bar0 + 8u * (5 * C_STAGES + M_STAGES + s); };
+  auto BAR_ST_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + b); };
+  auto BAR_U_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 2 + b); };
+  auto BAR_CH_FULL = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 4 + b); };
+  auto BAR_CH_FREE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 6 + b); };
+  const uint32_t BAR_DONE = bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 8);
+  auto BAR_G3_DONE = [&](int b) { return bar0 + 8u * (5 * C_STAGES + 2 * M_STAGES + 9 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + g64::OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+  const int col_tile = blockIdx.y;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NPAIR = PAIR ? 2 : 1;
+  constexpr int C_ROWS = BK / NPAIR;                        // centroid rows of a C / table tile held by this CTA
+  constexpr uint32_t C_ATOM_DESC = (C_ROWS * 128) >> 4;
+  constexpr uint32_t M_ATOM_BYTES = C_ROWS * 128;            // one column atom of the table tile in this CTA
+  constexpr uint32_t M_ATOM_DESC = M_ATOM_BYTES >> 4;
+  constexpr int CT_ROWS = D / NPAIR;                        // rows (latent dims) of a C^T tile held by this CTA
+  constexpr uint32_t IDESC_64 = make_idesc_f16(PAIR ? 256 : 128, BK);     // N = 64 for all three GEMMs
+  const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_STAGES; ++s) {
+      mbar_init(BAR_C_FULL(s), 1); mbar_init(BAR_C_EMPTY(s), 8); mbar_init(BAR_B_FULL(s), 1);
+      mbar_init(BAR_CT_FULL(s), 1); mbar_init(BAR_CT_EMPTY(s), 1);
+    }
+    for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), 8 * NPAIR);
+      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
+      mbar_init(BAR_G3_DONE(b), 1);
+    }
+    mbar_init(BAR_DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_mn_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ct_lo) : "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + g64::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(base + g64::OFF_TMEM_PTR), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp & 3;
+  const int prow = quarter * 32 + lane;
+  const int grp = (warp >= 6) ? 1 : 0;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  float zb = 0.f, s_scale = 0.f, u_unscale = 1.f;
+  if (warp >= 2 && warp < 10) {
+    const int64_t r = row0 + prow;
+    // ---- z~ = z - shift: exponent constants for both groups, z' = 2^ez z~ (hi | lo fp16) tiles by group 0
+    float nrm = 0.f, zmax = 0.f;
+    if (r < n) {
+      const float4* src = reinterpret_cast<const float4*>(z + r * D);
+#pragma unroll 4
+      for (int q = 0; q < D / 4; ++q) {
+        float4 v = __ldg(src + q);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+        v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
+        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm); nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+        zmax = fmaxf(zmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+    }
+    int ez = 0;
+    if (zmax > 0.f && zmax < 3.0e38f) {
+      const int ex = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+      ez = 14 - ex;
+      ez = ez > 50 ? 50 : (ez < -50 ? -50 : ez);
+    }
+    zb = -nrm * alpha;
+    s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
+    if (grp == 0) {
+      const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
+      const float4* src = reinterpret_cast<const float4*>(z + r * D);
+      uint8_t* ahi = gbase + OFF_ZA + prow * 128;
+      uint8_t* alo = ahi + ZA_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                       // 16-byte chunk c = dims [8c, 8c + 8)
+        uint32_t h4[4], l4[4];
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < n) {
+            v = __ldg(src + 2 * c + hq);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + 2 * c + hq);
+            v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
+          }
+          split_pair(v.x * zsc, v.y * zsc, h4[2 * hq], l4[2 * hq]);
+          split_pair(v.z * zsc, v.w * zsc, h4[2 * hq + 1], l4[2 * hq + 1]);
+        }
+        const int pc = (c ^ (prow & 7)) * 16;               // 128-byte swizzle
+        *reinterpret_cast<uint4*>(ahi + pc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+        *reinterpret_cast<uint4*>(alo + pc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> async proxy (UMMA)
+    }
+    // ---- U' = 2^eU Ut for this column tile: group g converts packed columns [64 g, 64 g + 64) of the tile
+    int e_u = 0;
+    if (r < n) e_u = __ldg(eu + r);
+    const float usc = __uint_as_float((uint32_t)(e_u + 127) << 23);
+    u_unscale = __uint_as_float((uint32_t)(127 - e_u) << 23);
+    {
+      const float* urow = u + r * 4096;
+      int p = col_tile * NT + grp * 64;
+      int ri = 0, rb = 0;
+      while (ri < 63 && p >= rb + (64 - ri)) { rb += 64 - ri; ++ri; }
+      int cj = ri + (p - rb);
+      auto next = [&]() -> float {
+        float v = 0.f;
+        if (r < n && p < h64::NPACK) {
+          v = __ldg(urow + ri * 64 + cj);
+          if (cj != ri) v += __ldg(urow + cj * 64 + ri);
+        }
+        ++p; ++cj;
+        if (cj == 64) { ++ri; cj = ri; }
+        return v;
+      };
+      uint32_t h[32], l[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = next();
+        const float e1 = next();
+        split_pair(e0 * usc, e1 * usc, h[i], l[i]);
+      }
+      TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 32, h);
+      TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 32, l);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+#define MMA_TS64(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_64, acc); else mma_ts_f16(d, a, b, IDESC_64, acc); } while (0)
+#define MMA_SS64(d, a, b, acc) do { if (PAIR) mma_ss_f16_pair(d, a, b, IDESC_64, acc); else mma_ss_f16(d, a, b, IDESC_64, acc); } while (0)
+#define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
+
+  if (warp == 0) {
+    // =========================================================== TMA producer 1: centroid tiles + bias, C^T tiles
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES;
+      mbar_wait(BAR_C_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_C_FULL(cs), C_TILE64);
+        const uint32_t dst = base + OFF_C + cs * C_TILE64;
+        if (PAIR) tma_load_3d_pair(dst, &tm_c64, BAR_C_FULL(cs), 0, j * BK + C_ROWS * (int)rank, 0);
+        else tma_load_3d(dst, &tm_c64, BAR_C_FULL(cs), 0, j * BK, 0);
+        mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
+        bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
+      }
+      __syncwarp();
+      mbar_wait(BAR_CT_EMPTY(cs), ((j / C_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_ROWS * 128);
+        const uint32_t dst = base + OFF_CT + cs * CT_TILE;
+        const int row = PAIR ? CT_ROWS * (int)rank : 0;
+        if (PAIR) {
+          tma_load_2d_pair(dst, &tm_ct_hi, BAR_CT_FULL(cs), j * BK, row);
+          tma_load_2d_pair(dst + CT_HALF, &tm_ct_lo, BAR_CT_FULL(cs), j * BK, row);
+        } else {
+          tma_load_2d(dst, &tm_ct_hi, BAR_CT_FULL(cs), j * BK, row);
+          tma_load_2d(dst + CT_HALF, &tm_ct_lo, BAR_CT_FULL(cs), j * BK, row);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    // =========================================================== TMA producer 2: natural table tiles of this column tile
+    for (int j = 0; j < num_blocks; ++j) {
+      const int ms = j % M_STAGES;
+      mbar_wait(BAR_M_EMPTY(ms), ((j / M_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(BAR_M_FULL(ms), NPAIR * 2 * 2 * M_ATOM_BYTES);
+        const uint32_t dst = base + OFF_M + ms * M_TILE;
+        const int row = j * BK + (PAIR ? C_ROWS * (int)rank : 0);
+        if (PAIR) {
+          tma_load_3d_pair(dst, &tm_mn_hi, BAR_M_FULL(ms), 0, row, 2 * col_tile);
+          tma_load_3d_pair(dst + M_HALF, &tm_mn_lo, BAR_M_FULL(ms), 0, row, 2 * col_tile);
+        } else {
+          tma_load_3d(dst, &tm_mn_hi, BAR_M_FULL(ms), 0, row, 2 * col_tile);
+          tma_load_3d(dst + M_HALF, &tm_mn_lo, BAR_M_FULL(ms), 0, row, 2 * col_tile);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer 1 (pair: leader only): GEMM1 + T-GEMM
+    if (leader) {
+      static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loops assume these periods");
+      const uint64_t za_hi = make_desc_sw128(base + OFF_ZA);
+      const uint64_t za_lo = make_desc_sw128(base + OFF_ZA + ZA_BYTES);
+      const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
+      const uint64_t m_desc0 = make_desc_sw128(base + OFF_M);
+      auto issue_st = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
+        constexpr int J = decltype(Jc)::value;
+        constexpr int cs = J % C_STAGES, sb = J & 1, ms = J % M_STAGES;
+        mbar_wait(BAR_C_FULL(cs), qodd);
+        mbar_wait(BAR_M_FULL(ms), (J / M_STAGES) & 1);
+        if (j >= 2) mbar_wait(BAR_G3_DONE(sb), ((J >> 1) + 1) & 1);     // GEMM3(j-2) has consumed this buffer
+        tc_fence_after();
+        const uint32_t s_t = tmem_base + TM_ST + sb * 128;
+        const uint32_t t_t = s_t + 64;
+        const uint64_t ch = c_desc0 + ((cs * C_TILE64) >> 4);         // hi atom; lo atom C_ATOM_DESC further
+        const uint64_t cl = ch + C_ATOM_DESC;
+        const uint64_t mh = m_desc0 + ((ms * M_TILE) >> 4);
+        const uint64_t ml = mh + (M_HALF >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_hi + 2 * kk, ch + 2 * kk, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_hi + 2 * kk, cl + 2 * kk, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_lo + 2 * kk, ch + 2 * kk, 1);
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_TS64(t_t, tmem_base + TM_UHI + 8 * kk, mh + (kk >> 2) * M_ATOM_DESC + 2 * (kk & 3), kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_TS64(t_t, tmem_base + TM_ULO + 8 * kk, mh + (kk >> 2) * M_ATOM_DESC + 2 * (kk & 3), 1);
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            MMA_TS64(t_t, tmem_base + TM_UHI + 8 * kk, ml + (kk >> 2) * M_ATOM_DESC + 2 * (kk & 3), 1);
+          COMMIT(BAR_M_EMPTY(ms));
+          COMMIT(BAR_ST_FULL(sb));
+        }
+        __syncwarp();
+      };
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 4, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) issue_st(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3)
+#undef RLVAE_BLK
+      }
+    }
+  } else if (warp == 11) {
+    // =========================================================== MMA issuer 2 (pair: leader only): GEMM3
+    if (leader) {
+      const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
+      uint32_t free_phase = 0;
+      auto issue_g3 = [&](auto Jc, const int j, const uint32_t qodd) {
+        constexpr int J = decltype(Jc)::value;
+        constexpr int cs = J % C_STAGES, sb = J & 1, cb = (J >> 1) & 1;
+        constexpr int first = (J % CHUNK) == 0;
+        if (first && j >= 2 * CHUNK) {
+          mbar_wait(BAR_CH_FREE(cb), (free_phase >> cb) & 1u);
+          free_phase ^= 1u << cb;
+        }
+        mbar_wait(BAR_CT_FULL(cs), qodd);
+        mbar_wait(BAR_U_FULL(sb), (J >> 1) & 1);
+        tc_fence_after();
+        const uint32_t up = tmem_base + TM_ST + sb * 128;     // k-step kk: u'_hi at (kk>>1)*32 + (kk&1)*8, u'_lo 16 further
+        const uint32_t acc = tmem_base + TM_OUT + cb * 64;
+        const uint64_t th = ct_desc0 + ((cs * CT_TILE) >> 4);
+        const uint64_t tl = th + (CT_HALF >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, th + 2 * kk, !(first && kk == 0));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_TS64(acc, up + (kk >> 1) * 32 + 16 + (kk & 1) * 8, th + 2 * kk, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, tl + 2 * kk, 1);
+          COMMIT(BAR_CT_EMPTY(cs));
+          COMMIT(BAR_G3_DONE(sb));
+          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(cb));
+        }
+        __syncwarp();
+      };
+      uint32_t qodd = 0;
+      for (int j0 = 0; j0 < num_blocks; j0 += 4, qodd ^= 1u) {
+#define RLVAE_BLK(J) if (j0 + J < num_blocks) issue_g3(std::integral_constant<int, J>{}, j0 + J, qodd);
+        RLVAE_BLK(0) RLVAE_BLK(1) RLVAE_BLK(2) RLVAE_BLK(3)
+#undef RLVAE_BLK
+      }
+      if (elect_one()) COMMIT(BAR_DONE);
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== exp groups (one thread per point, 32 centroids of every block)
+    float tot[D];                        // this group's share of OUT (chunks of parity grp)
+    float su = 0.f;                      // and of sum_k u'
+#pragma unroll
+    for (int e = 0; e < D; ++e) tot[e] = 0.f;
+    auto fold_chunk = [&](int c, bool signal) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t a[32];
+        TMEM_LD32(tmem_base + lane_addr + TM_OUT + (c & 1) * 64 + hh * 32, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tot[hh * 32 + i] += __uint_as_float(a[i]);
+      }
+      if (signal) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
+      }
+    };
+    int next_chunk = grp;
+    for (int j = 0; j < num_blocks; ++j) {
+      const int cs = j % C_STAGES, sb = j & 1;
+      const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
+      mbar_wait(BAR_B_FULL(cs), (j / C_STAGES) & 1);
+      mbar_wait(BAR_ST_FULL(sb), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[32], tv[32], ph[16], pl[16];
+      TMEM_LD32(st + grp * 32, sv);
+      TMEM_LD32(st + 64 + grp * 32, tv);
+      const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + grp * 8;
+      tmem_wait_ld();
+      float su_blk = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bv = bias4[q];
+        const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+        float uv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * q + e;
+          const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
+          uv[e] = w * (__uint_as_float(tv[i]) * g64::U_DOWN);
+          su_blk += uv[e];
+        }
+        split_pair(uv[0], uv[1], ph[2 * q], pl[2 * q]);
+        split_pair(uv[2], uv[3], ph[2 * q + 1], pl[2 * q + 1]);
+      }
+      su += su_blk;
+      TMEM_ST16(st + grp * 32, ph);
+      TMEM_ST16(st + grp * 32 + 16, pl);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
+      }
+      while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
+        mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
+        tc_fence_after();
+        fold_chunk(next_chunk, true);
+        next_chunk += 2;
+      }
+    }
+    mbar_wait(BAR_DONE, 0);
+    tc_fence_after();
+    while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
+    // ---------------------------------------------------------- combine the two groups, write the tile's partial result
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* red = reinterpret_cast<float*>(gbase + OFF_M);
+    if (grp == 1) {
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q)
+        *reinterpret_cast<float4*>(red + prow * RED_LD + 4 * q) = make_float4(tot[4 * q], tot[4 * q + 1], tot[4 * q + 2], tot[4 * q + 3]);
+      red[prow * RED_LD + D] = su;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const int64_t r = row0 + prow;
+      if (r < n) {
+        const float sut = su + red[prow * RED_LD + D];
+        const float f = g64::U_UP * u_unscale * scale;
+        float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)col_tile * n + r) * D);
+        const float4* zsrc = reinterpret_cast<const float4*>(z + r * D);
+#pragma unroll
+        for (int q = 0; q < D / 4; ++q) {
+          const float4 rv = *reinterpret_cast<const float4*>(red + prow * RED_LD + 4 * q);
+          float4 zv = __ldg(zsrc + q);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+          zv.x -= sh.x; zv.y -= sh.y; zv.z -= sh.z; zv.w -= sh.w;
+          float4 o;
+          o.x = ((tot[4 * q] + rv.x) * c_unscale - zv.x * sut) * f;          // C^T tiles hold 2^ec (c - shift)
+          o.y = ((tot[4 * q + 1] + rv.y) * c_unscale - zv.y * sut) * f;
+          o.z = ((tot[4 * q + 2] + rv.z) * c_unscale - zv.z * sut) * f;
+          o.w = ((tot[4 * q + 3] + rv.w) * c_unscale - zv.w * sut) * f;
+          dst[q] = o;
+        }
+      }
+    }
+  }
+#undef MMA_TS64
+#undef MMA_SS64
+#undef COMMIT
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ tables
@@ -466,6 +992,39 @@ __global__ void pack_sym64_h_kernel(const float* __restrict__ M, int Kpad, float
   }
 }
 
+// natural fp16 tables [Kpad, 2176] (row = centroid, 2080 packed columns + zeros): B operand of the T GEMM
+__global__ void pack_sym64_nat_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_n,
+                                        __half* __restrict__ lo_n) {
+  const int64_t total = (int64_t)Kpad * tc::h64::NPAD;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / tc::h64::NPAD), p = (int)(idx - (int64_t)k * tc::h64::NPAD);
+    float v = 0.f;
+    if (p < tc::h64::NPACK) {
+      int i = 0, base = 0;
+      while (p >= base + (64 - i)) { base += 64 - i; ++i; }
+      const int j = i + (p - base);
+      v = scale * 0.5f * (M[(int64_t)k * 4096 + i * 64 + j] + M[(int64_t)k * 4096 + j * 64 + i]);
+    }
+    const __half h = __float2half_rn(v);
+    hi_n[idx] = h;
+    lo_n[idx] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// (c - shift)^T scaled by 2^ec, split fp16 [64, Kpad] (centroid index contiguous): B operand of GEMM3
+__global__ void pack_ct64_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K, int Kpad,
+                                 float scale, __half* __restrict__ ct_hi, __half* __restrict__ ct_lo) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  for (int j = 0; j < 64; ++j) {
+    const float v = (k < K) ? (c[(int64_t)k * 64 + j] - shift[j]) * scale : 0.f;
+    const __half h = __float2half_rn(v);
+    ct_hi[(int64_t)j * Kpad + k] = h;
+    ct_lo[(int64_t)j * Kpad + k] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // packed [N, 2176] -> full symmetric [N, 64, 64], + lambda on the diagonal
 __global__ void unpack_sym64_kernel(const float* __restrict__ packed, int64_t n, float lambda,
                                     float* __restrict__ full) {
@@ -536,6 +1095,28 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
   t->h16_out_scale = ldexpf(1.f, -(14 + em));
   t->h16_m_unscale = ldexpf(1.f, -em);
   t->c64_unscale = ldexpf(1.f, -ec);
+  // gradient kernel tables: natural split-fp16 M [Kpad, 2176] and (c - shift)^T [64, Kpad]
+  const bool grad_tables =
+      cudaMalloc(&t->Mnh_hi, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad) == cudaSuccess &&
+      cudaMalloc(&t->Mnh_lo, sizeof(__half) * (size_t)tc::h64::NPAD * Kpad) == cudaSuccess &&
+      cudaMalloc(&t->ct64_hi, sizeof(__half) * (size_t)64 * Kpad) == cudaSuccess &&
+      cudaMalloc(&t->ct64_lo, sizeof(__half) * (size_t)64 * Kpad) == cudaSuccess;
+  if (grad_tables) {
+    pack_sym64_nat_h_kernel<<<1184, 256, 0, s>>>(t->M, Kpad, ldexpf(1.f, em), static_cast<__half*>(t->Mnh_hi),
+                                                 static_cast<__half*>(t->Mnh_lo));
+    RLVAE_LAUNCH_OK();
+    pack_ct64_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, Kpad, ldexpf(1.f, ec),
+                                                        static_cast<__half*>(t->ct64_hi), static_cast<__half*>(t->ct64_lo));
+    RLVAE_LAUNCH_OK();
+    RLVAE_CUDA_OK(cudaStreamSynchronize(s));
+  } else {
+    (void)cudaGetLastError();      // out of memory for the extra tables: the gradient stays on the direct kernel
+    if (t->Mnh_hi) cudaFree(t->Mnh_hi);
+    if (t->Mnh_lo) cudaFree(t->Mnh_lo);
+    if (t->ct64_hi) cudaFree(t->ct64_hi);
+    if (t->ct64_lo) cudaFree(t->ct64_lo);
+    t->Mnh_hi = t->Mnh_lo = t->ct64_hi = t->ct64_lo = nullptr;
+  }
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -559,6 +1140,28 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
     cuuint32_t box2[2] = {tc::BK, tc::h64::NT / 2};
     if (int rc = encode(enc, &t->tm_mh2_hi, t->Mh_hi, 2, dims, strides, box2)) return rc;
     if (int rc = encode(enc, &t->tm_mh2_lo, t->Mh_lo, 2, dims, strides, box2)) return rc;
+  }
+  if (t->Mnh_hi != nullptr) {
+    {   // natural tables [Kpad, 2176] fp16 viewed as [34 column atoms][Kpad][64]: box = 2 atoms x 64 (pair: 32) rows
+      cuuint64_t dims[3] = {64, (cuuint64_t)Kpad, (cuuint64_t)(tc::h64::NPAD / 64)};
+      cuuint64_t strides[2] = {(cuuint64_t)tc::h64::NPAD * sizeof(__half), 64 * sizeof(__half)};
+      cuuint32_t box[3] = {64, tc::BK, 2};
+      if (int rc = encode(enc, &t->tm_mnh_hi, t->Mnh_hi, 3, dims, strides, box)) return rc;
+      if (int rc = encode(enc, &t->tm_mnh_lo, t->Mnh_lo, 3, dims, strides, box)) return rc;
+      cuuint32_t box2[3] = {64, tc::BK / 2, 2};
+      if (int rc = encode(enc, &t->tm_mnh2_hi, t->Mnh_hi, 3, dims, strides, box2)) return rc;
+      if (int rc = encode(enc, &t->tm_mnh2_lo, t->Mnh_lo, 3, dims, strides, box2)) return rc;
+    }
+    {   // (c - shift)^T [64, Kpad] fp16: box = 64 centroids x 64 (pair: 32) rows
+      cuuint64_t dims[2] = {(cuuint64_t)Kpad, 64};
+      cuuint64_t strides[1] = {(cuuint64_t)Kpad * sizeof(__half)};
+      cuuint32_t box[2] = {tc::BK, 64};
+      if (int rc = encode(enc, &t->tm_ct64_hi, t->ct64_hi, 2, dims, strides, box)) return rc;
+      if (int rc = encode(enc, &t->tm_ct64_lo, t->ct64_lo, 2, dims, strides, box)) return rc;
+      cuuint32_t box2[2] = {tc::BK, 32};
+      if (int rc = encode(enc, &t->tm_ct64_2_hi, t->ct64_hi, 2, dims, strides, box2)) return rc;
+      if (int rc = encode(enc, &t->tm_ct64_2_lo, t->ct64_lo, 2, dims, strides, box2)) return rc;
+    }
   }
   return 0;
 }
@@ -617,6 +1220,72 @@ int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, 
     return rc;
   const int64_t total = n * 4096;
   unpack_sym64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(packed_scratch, n, t->lambda, ginv);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
+template <bool PAIR>
+static int launch_g64(const rlvae_tables* t, const float* z, const float* u, const int* eu, int64_t n, float scale,
+                      float* partial, cudaStream_t s) {
+  auto kern = tc::metric_grad_h64_kernel<PAIR>;
+  RLVAE_OPT_IN_SMEM(kern, (int)tc::g64::SMEM_BYTES);
+  unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
+  if (PAIR) tiles = (tiles + 1) & ~1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, tc::g64::NTILES, 1);
+  cfg.blockDim = dim3(tc::g64::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc::g64::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float alpha = 1.4426950408889634f / t->T2;
+  const float* cbias = t->cbias;
+  const int nb = t->Kpad / tc::BK;
+  const float sc = scale * t->h16_m_unscale;
+  const float cu = t->c64_unscale;
+  if (PAIR) {
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64_2, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct64_2_hi,
+                                       t->tm_ct64_2_lo, z, u, eu, cbias, n, nb, alpha, sc, cu, t->cshift, partial));
+  } else {
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c64, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct64_hi,
+                                       t->tm_ct64_lo, z, u, eu, cbias, n, nb, alpha, sc, cu, t->cshift, partial));
+  }
+  return 0;
+}
+
+int64_t metric_grad_h64_scratch_floats(int64_t n) {
+  return n * (int64_t)(tc::g64::NTILES * 64) + ((n + 3) & ~(int64_t)3);     // partial tiles + per-point exponents
+}
+
+bool metric_grad_h64_available(const rlvae_tables* t) {
+  return t->d == 64 && t->symmetric && t->c64h != nullptr && t->Mnh_hi != nullptr;
+}
+
+// d = 64, symmetric tables: (scale) * sum_k w_k <U, M_k> (c_k - z), u = [N,64,64] (any U);
+// scratch: metric_grad_h64_scratch_floats(n) floats (16-byte aligned)
+int launch_metric_grad_h64(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
+                           float* scratch, cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(metric_grad_h64_available(t), "d = 64 tensor gradient needs symmetric tables");
+  RLVAE_REQUIRE(scratch != nullptr, "d = 64 tensor gradient needs a workspace");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0,
+                "tensor path needs 16-byte aligned z, u, out and workspace");
+  float* partial = scratch;
+  int* eu = reinterpret_cast<int*>(scratch + n * (int64_t)(tc::g64::NTILES * 64));
+  const unsigned g1 = (unsigned)((n + 7) / 8 < 2368 ? (n + 7) / 8 : 2368);
+  tc::u_scale64_kernel<<<g1, 256, 0, s>>>(u, n, eu);
+  RLVAE_LAUNCH_OK();
+  if (int rc = h64_use_pairs() ? launch_g64<true>(t, z, u, eu, n, scale, partial, s)
+                               : launch_g64<false>(t, z, u, eu, n, scale, partial, s))
+    return rc;
+  const int64_t total4 = n * 16;
+  tc::reduce_partials64_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(partial, n, tc::g64::NTILES, out);
   RLVAE_LAUNCH_OK();
   return 0;
 }

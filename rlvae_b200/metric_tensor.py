@@ -298,7 +298,7 @@ class MetricTensor(nn.Module):
         if not tensor:
             kind = 'direct CUDA-core kernels'
         elif tab.d == 64:
-            kind = 'split-fp16 tcgen05 forward kernel (column-tiled); gradient on the direct kernel'
+            kind = 'split-fp16 tcgen05 kernels, column-tiled (forward: 17 tiles of 128 packed columns; gradient: partial tiles + reduction)'
         elif tab.symmetric:
             kind = ('split-fp16 tcgen05 kernels, ' +
                     ('expanded-distance GEMM', 'exact-distance mode (small temperature)',

@@ -261,3 +261,35 @@ def test_prior_samplers_and_official_sampler_match_the_reference():
     zp = off.sample_prior(40)                                  # test_pythae_variant_hmc_matches_reference_chain
     assert zp.shape == (40, 16) and torch.isfinite(zp).all()
     assert off.sample_prior(5, method='basic').shape == (5, 16)
+
+
+def test_d64_tensor_gradient_kernel_general_u_and_tile_tails():
+    """The column-tiled tcgen05 gradient kernel at d = 64 (rlvae_metric_grad_ws) with an ARBITRARY
+    (non-symmetric, badly scaled) U -- the autograd backward of compute_inverse_metric -- against the oracle
+    formula (2/T^2) sum_k w_k <U, M_k> (c_k - z), at ragged batch sizes, and against the CUDA-core kernel."""
+    from rlvae_b200 import _capi
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(700, 64, seed=9)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    mt = make_mt(t, 'tensor')
+    tab = mt._tables(dev())
+    assert 'gradient: partial tiles' in mt.kernel_info()['implementation']
+    gen = torch.Generator().manual_seed(10)
+    for n in (1, 127, 130, 300):
+        z = make_points(n, 64, seed=11 + n)
+        U = torch.randn(n, 64, 64, generator=gen) * torch.logspace(-6, 6, n)[:, None, None]
+        ref = O.chunked(lambda zz, uu: O.metric_backward(zz, *t[:3], uu), torch.arange(n), chunk=n) if False else \
+            torch.cat([O.metric_backward(z[i:i + 16], *t[:3], U[i:i + 16]) for i in range(0, n, 16)])
+        lib = _capi.lib()
+        lib.rlvae_launch_count(1)
+        got = _capi.metric_grad(tab, z.to(dev()), U.to(dev()), 2.0 / sm.temperature ** 2, _capi.PATH_TENSOR)
+        assert lib.rlvae_launch_count(0) == 3          # per-point scale, tensor kernel, tile reduction
+        assert rel_fro(got.cpu(), ref) < TOL_LD, n
+        direct = _capi.metric_grad(tab, z.to(dev()), U.to(dev()), 2.0 / sm.temperature ** 2, _capi.PATH_DIRECT)
+        assert rel_fro(got.cpu(), direct.cpu()) < TOL_LD, n
+    # through autograd
+    zg = make_points(64, 64, seed=3).to(dev()).requires_grad_(True)
+    w = torch.randn(64, 64, 64, generator=gen).to(dev())
+    (mt.compute_inverse_metric(zg) * w).sum().backward()
+    ref = O.metric_backward(zg.detach().cpu(), *t[:3], w.cpu())
+    assert rel_fro(zg.grad.cpu(), ref) < TOL_LD
