@@ -608,11 +608,10 @@ static int resolve_path(const rlvae_tables* t, int path, bool* use_tc) {
 
 // RLVAE_TC_FWD=tf32 selects the 3xTF32 forward kernel for symmetric tables (default: split fp16)
 static bool use_h16(const rlvae_tables* t) {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RLVAE_TC_FWD");
-    v = (e != nullptr && e[0] == 't') ? 0 : 1;
-  }
+    return (e != nullptr && e[0] == 't') ? 0 : 1;
+  }();   // initialised once, thread-safe (C++11 magic static)
   return v == 1 && t->Mh_hi != nullptr;
 }
 
@@ -1032,11 +1031,10 @@ int rlvae_nearest2(const rlvae_tables_t* t, const float* mu, int64_t n, int64_t*
   RLVAE_REQUIRE(mu && idx && dist, "nearest2: NULL pointer");
   // d == 16: distance GEMM on the tensor core as a pre-filter, exact decision among 8 candidates
   // (same indices and distances as the direct kernel); RLVAE_NEAREST=direct keeps the scalar scan
-  static int use_tc = -1;
-  if (use_tc < 0) {
+  static const int use_tc = [] {
     const char* e = getenv("RLVAE_NEAREST");
-    use_tc = (e != nullptr && e[0] == 'd') ? 0 : 1;
-  }
+    return (e != nullptr && e[0] == 'd') ? 0 : 1;
+  }();
   if (use_tc && t->d == 16 && t->cn_inf != nullptr && t->K >= 2 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0)
     return launch_nearest2_tc(t, mu, n, idx, dist, static_cast<cudaStream_t>(stream));
   return launch_nearest2(t, mu, n, idx, dist, static_cast<cudaStream_t>(stream));

@@ -4,7 +4,9 @@
 // leapfrog step is exactly ONE metric evaluation (the reference re-evaluates the same gradient
 // at the end of step k and the start of step k+1: SURVEY.md §3.2).
 //
-// One thread per chain; each thread touches a contiguous 4*d-byte row of every [N,d] array.
+// One thread per chain; each thread touches a contiguous 4*d-byte row of every [N,d] array, with 128-bit
+// loads / stores when d is a multiple of 4 (VEC).  This is the per-step path; certified d = 16 tables run the
+// whole trajectory inside the fused kernel instead (rlvae_tc16.cu, HMC mode).
 #include <cmath>
 
 #include "rlvae_internal.h"
@@ -91,6 +93,31 @@ __global__ void hmc_step_kernel(const float* __restrict__ diag_g, const float* _
   if (moves) moves[p] = mv ? 1.f : 0.f;
 }
 
+// The stages between the first and the last leapfrog step are purely element-wise (lines 141-148, then
+// 132-138 of the next step): one float4 of the flat [N*d] arrays per thread, perfectly coalesced 128-bit
+// accesses (the one-thread-per-chain kernel above walked a 64-byte row with scalar loads: 18 % of HBM peak).
+__global__ void hmc_step_mid_vec4_kernel(const float4* __restrict__ diag_g, const float4* __restrict__ gex,
+                                         int64_t total4, float eps, float lambda, float T2, int mode, float scale,
+                                         float4* __restrict__ rho_half, float4* __restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const float half_eps = eps / 2.f;
+  const float4 dg = __ldg(diag_g + i);
+  const float4 ge = gex ? __ldg(gex + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 rh = rho_half[i], zc = z[i];
+  const float dgv[4] = {dg.x, dg.y, dg.z, dg.w}, gev[4] = {ge.x, ge.y, ge.z, ge.w};
+  float rhv[4] = {rh.x, rh.y, rh.z, rh.w}, zv[4] = {zc.x, zc.y, zc.z, zc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float g = neg_grad(mode, dgv[e], gev[e], lambda, T2);
+    const float rho = scale * (rhv[e] - half_eps * g);
+    rhv[e] = rho - half_eps * g;
+    zv[e] = zv[e] + eps * rhv[e];
+  }
+  rho_half[i] = make_float4(rhv[0], rhv[1], rhv[2], rhv[3]);
+  z[i] = make_float4(zv[0], zv[1], zv[2], zv[3]);
+}
+
 __global__ void axpy_grad_modular_kernel(float* __restrict__ z, const float* __restrict__ diag_g,
                                          int64_t total, float step, float lambda, float T2) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +144,16 @@ int launch_hmc_step(const float* diag_g, const float* logabsdet, const float* si
                     const float* z_prev, const float* acc, const float* h0, float* h1, float* alpha,
                     float* moves, float* z_out, cudaStream_t s) {
   if (n == 0) return 0;
+  const int64_t total = n * d;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!last && (total & 3) == 0 && al16(diag_g) && al16(rho_half) && al16(z_cur) && (grad_exact == nullptr || al16(grad_exact))) {
+    const int64_t total4 = total / 4;
+    hmc_step_mid_vec4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(diag_g), reinterpret_cast<const float4*>(grad_exact), total4, eps, lambda, T2,
+        grad_mode, scale, reinterpret_cast<float4*>(rho_half), reinterpret_cast<float4*>(z_cur));
+    RLVAE_LAUNCH_OK();
+    return 0;
+  }
   hmc_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(
       diag_g, logabsdet, sign, grad_exact, n, d, eps, lambda, T2, grad_mode, scale, last, rho_half,
       z_cur, z_prev, acc, h0, h1, alpha, moves, z_out);

@@ -1354,11 +1354,10 @@ int tc_build_sym_descriptors(rlvae_tables* t) {
 
 // CTA pairs (cta_group::2) are the default; RLVAE_TC_PAIR=0 selects the single-CTA kernels.
 static bool use_pairs() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RLVAE_TC_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();   // initialised once, thread-safe (C++11 magic static)
   return v == 1;
 }
 
@@ -1479,11 +1478,10 @@ static int launch_grad_sym(const rlvae_tables* t, const float* z, const float* u
 // RLVAE_TC_GRAD = h16 (default: split-fp16 T GEMM, one CTA per 128 points) | tf32 (3xTF32, tensor-core
 // final contraction) | fma (3xTF32, final contraction on the FMA pipe)
 static int grad_variant() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RLVAE_TC_GRAD");
-    v = (e == nullptr) ? 2 : (e[0] == 'f' ? 0 : (e[0] == 't' ? 1 : 2));
-  }
+    return (e == nullptr) ? 2 : (e[0] == 'f' ? 0 : (e[0] == 't' ? 1 : 2));
+  }();   // initialised once, thread-safe (C++11 magic static)
   return v;
 }
 

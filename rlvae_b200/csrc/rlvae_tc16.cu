@@ -1865,11 +1865,10 @@ int tc_build_h16_descriptors(rlvae_tables* t) {
 }
 
 static bool h16_use_pairs() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RLVAE_TC_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();   // initialised once, thread-safe (C++11 magic static)
   return v == 1;
 }
 

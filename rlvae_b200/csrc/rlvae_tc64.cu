@@ -1167,11 +1167,10 @@ int tc_build_h64_tables(rlvae_tables* t, cudaStream_t s) {
 }
 
 static bool h64_use_pairs() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RLVAE_TC_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();   // initialised once, thread-safe (C++11 magic static)
   return v == 1;
 }
 

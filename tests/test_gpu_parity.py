@@ -737,3 +737,107 @@ def test_state_dict_and_device_moves_rebuild_tables():
     assert torch.equal(fresh.compute_inverse_metric(z), gb)
     mta.load_state_dict(mtb.state_dict())
     assert torch.equal(mta.compute_inverse_metric(z), gb) and not torch.equal(ga, gb)
+
+
+@pytest.mark.parametrize('d', [3, 10, 12, 20, 48])
+def test_latent_dims_that_are_not_powers_of_two(d):
+    """The reference is dimension-generic (metric_tensor.py:98-182).  Latent dims between the template sizes
+    run on the direct kernels + the per-point kernels, which embed the d x d matrix as diag(A, I) in the
+    next power of two: every public quantity against the oracle, HMC and the Working sampler included."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler, WorkingRiemannianSampler, _capi
+    from rlvae_b200.synthetic import make_hmc_streams, make_points, make_synthetic_metric
+    sm = make_synthetic_metric(60, d, seed=d)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    z = make_points(77, d, seed=d + 1)
+    mt = make_mt(t, 'auto')
+    ref_ginv = O.inverse_metric(z, *t)
+    ref_g = torch.linalg.inv(ref_ginv)
+    ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT
+    assert rel_fro(ev['g'].cpu(), ref_g) < 5e-5
+    close_ld(ev['logdet_g'], torch.linalg.slogdet(ref_g).logabsdet)
+    assert rel_fro(ev['grad_logdet_g'].cpu(), -2.0 * O.grad_log_sqrt_det_ginv_exact(z, *t)) < TOL_LD
+    assert rel_fro(mt.compute_metric(z.to(dev())).cpu(), ref_g) < 5e-5
+    close_ld(mt.compute_log_det_metric(z.to(dev())), O.log_det_metric(z, *t))
+    # general (non-symmetric) matrices through the padded Gauss-Jordan: inverse, log|det|, sign, diagonal
+    a = torch.randn(50, d, d, generator=torch.Generator().manual_seed(d))
+    inv, lad, sgn, diag = _capi.batched_inverse(a.to(dev()), True, True, True, True)
+    sl = torch.linalg.slogdet(a.double())
+    good = torch.linalg.cond(a.double()) < 1e3
+    assert rel_fro(inv.cpu()[good], torch.linalg.inv(a.double())[good].float()) < 1e-3
+    assert torch.equal(sgn.cpu()[good].double(), sl.sign[good])
+    close_ld(lad.cpu()[good], sl.logabsdet[good], 1e-4)
+    assert torch.allclose(diag.cpu(), torch.diagonal(inv.cpu(), dim1=1, dim2=2))
+    # samplers
+    model = MetricModel(mt)
+    s = RiemannianHMCSampler(model, mcmc_steps_nbr=2, n_lf=3, eps_lf=0.03)
+    z0, gam, acc = make_hmc_streams(40, d, 2, seed=5)
+    zf = s.sample_with_streams(z0.to(dev()), gam.to(dev()), acc.to(dev()))
+    torch.testing.assert_close(zf.cpu(), O.hmc_sample(t, z0, gam, acc, 3, 0.03), rtol=1e-4, atol=1e-4)
+    ws = WorkingRiemannianSampler(model)
+    mu, lv, eps = make_points(30, d, seed=6), torch.full((30, d), -1.0), make_points(30, d, seed=7)
+    torch.testing.assert_close(ws.enhanced_with_noise(mu.to(dev()), lv.to(dev()), eps.to(dev())).cpu(),
+                               O.sample_enhanced(mu, lv, eps, t), rtol=2e-5, atol=2e-5)
+    idx, dist = _capi.nearest2(mt._tables(dev()), mu.to(dev()))
+    ri, rd = O.nearest2(mu, t[0])
+    assert torch.equal(idx.cpu(), ri)
+    torch.testing.assert_close(dist.cpu(), rd, rtol=1e-5, atol=1e-6)
+
+
+def test_binding_rejects_wrong_buffers_and_latents():
+    """Everything below the ctypes binding is raw pointers: a latent batch of the wrong width / device or a
+    caller-supplied output buffer of the wrong shape, dtype or layout must fail in Python, not in a kernel."""
+    from rlvae_b200 import MetricModel, RiemannianHMCSampler, _capi
+    from rlvae_b200.synthetic import make_synthetic_metric
+    sm = make_synthetic_metric(40, 16, seed=1)
+    mt = make_mt((sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization))
+    tab = mt._tables(dev())
+    z = torch.randn(8, 16, device=dev())
+    with pytest.raises(ValueError):
+        _capi.inverse_metric(tab, torch.randn(8, 8, device=dev()))
+    with pytest.raises(ValueError):
+        _capi.nearest2(tab, torch.randn(8, 32, device=dev()))
+    for bad in (dict(ginv=torch.empty(7, 16, 16, device=dev())),                       # wrong batch
+                dict(ginv=torch.empty(8, 16, 16, device=dev(), dtype=torch.float64)),  # wrong dtype
+                dict(ginv=torch.empty(8, 16, 32, device=dev())[:, :, ::2]),            # strided
+                dict(logdet_g=torch.empty(8, 1, device=dev())),
+                dict(grad_logdet_g=torch.empty(8, 8, device=dev()))):
+        with pytest.raises((ValueError, RuntimeError)):
+            _capi.metric_eval(tab, z, want_ginv=True, want_logdet=True, want_grad=True, out=bad)
+    with pytest.raises(ValueError):
+        _capi.metric_grad(tab, z, torch.randn(8, 16, 8, device=dev()), 1.0)
+    with pytest.raises(ValueError):
+        _capi.hmc_iteration(tab, z.clone(), torch.randn(8, 16, device=dev()), torch.rand(7, device=dev()), 3, 0.03, 1.0,
+                            [1.0, 1.0, 1.0])
+    with pytest.raises(ValueError):
+        _capi.chol_apply(torch.randn(8, 16, 16, device=dev()), torch.randn(8, 8, device=dev()))
+    s = RiemannianHMCSampler(MetricModel(mt))
+    with pytest.raises(ValueError):
+        s.log_pi(torch.randn(4, 8, device=dev()))          # the sampler paths go through the same validator
+    # replaced tables stay alive for an autograd graph that still holds them
+    zg = z.clone().requires_grad_(True)
+    out = mt.compute_inverse_metric(zg)
+    mt.load_pretrained(sm.centroids * 1.5, sm.metric_matrices, temperature=sm.temperature, regularization=0.02)
+    mt.compute_inverse_metric(z)                           # rebuilds the tables handle
+    out.sum().backward()                                   # old handle must still be usable here
+    assert torch.isfinite(zg.grad).all()
+
+
+def test_cholesky_failure_takes_the_reference_eigh_fallback():
+    """riemannian_sampler.py:85-90 / 158-164 / 202-207 / 273-278: when cholesky(A + 1e-6 I) fails for ANY matrix
+    of the batch, the reference computes sqrt(A) @ eps from eigh(A) with eigenvalues clamped at 1e-6 for the
+    whole batch.  Same here (not a downgrade to standard reparameterisation)."""
+    from rlvae_b200.samplers.riemannian_sampler import chol_apply
+    gen = torch.Generator().manual_seed(3)
+    q, _ = torch.linalg.qr(torch.randn(16, 16, generator=gen))
+    a = torch.randn(20, 16, 16, generator=gen)
+    a = a @ a.transpose(1, 2) + 0.1 * torch.eye(16)
+    a[7] = q @ torch.diag(torch.linspace(-0.5, 1.0, 16)) @ q.T            # one indefinite matrix
+    eps = torch.randn(20, 16, generator=gen)
+    got = chol_apply(a.to(dev()), eps.to(dev()))
+    ev, evec = torch.linalg.eigh(a)
+    ref = torch.einsum('bij,bj->bi', evec @ torch.diag_embed(torch.sqrt(ev.clamp(min=1e-6))) @ evec.transpose(-2, -1), eps)
+    torch.testing.assert_close(got.cpu(), ref, rtol=2e-4, atol=2e-4)
+    # and the all-positive-definite batch keeps the Cholesky path
+    a[7] = a[6]
+    torch.testing.assert_close(chol_apply(a.to(dev()), eps.to(dev())).cpu(), O.chol_apply(a, eps), rtol=2e-5, atol=2e-5)
