@@ -168,7 +168,8 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
  * semi-definite with lambda > 0, RLVAE_GRAD_MODULAR, n_lf <= 64 for rlvae_hmc_iteration) the whole
  * iteration -- all n_lf + 1 metric evaluations, the momentum / position updates of lines 127-148 and
  * the accept step of lines 153-162 -- is ONE kernel launch: a CTA pair keeps its 256 chains' z and
- * rho_half on chip for the entire trajectory.  The int32 at byte offset
+ * rho_half on chip for the entire trajectory (rlvae_hmc_run: n_iters * n_lf + 1 metric evaluations in
+ * all -- the metric at the state an iteration starts from is the one its predecessor ended with).  The int32 at byte offset
  * rlvae_hmc_workspace(n,d) - 256 of `work` then counts chain-steps whose G^{-1} lost positive
  * definiteness to rounding (cond(G^{-1}) beyond ~1e5; log_pi takes its clamp value there); callers
  * that care re-run with RLVAE_HMC_FUSED=0 in the environment (per-step launches + pivoting fallback).

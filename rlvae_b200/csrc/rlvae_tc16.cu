@@ -76,8 +76,9 @@ constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
 constexpr int NUM_BARS = 3 * C_STAGES + 2 * M_STAGES + 2 * SP_BUFS + 4 + 3 + 2;   // + 3 pipe-trace barriers (profiling builds)
                                                                                    // + 2 "next position ready" barriers (HMC mode)
 // HMC mode: per-chain state rows in the (otherwise unused) A-tile region of shared memory:
-// [0,16) z, [16,32) rho_half, [32] zb, [33] s_scale
-constexpr int ST_LD = 36;
+// [0,16) z, [16,32) rho_half, [32] zb, [33] s_scale, [34] log det G^{-1} and [35] its validity at the state the
+// running MCMC iteration started from, [36,52) diag G there (re-used instead of re-evaluated after a rejection)
+constexpr int ST_LD = 52;
 constexpr uint32_t OFF_STATE = OFF_A1;
 static_assert(TILE_M * ST_LD * 4 <= 2 * A_BYTES, "HMC state rows must fit the A-tile region");
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
@@ -224,7 +225,10 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #endif
   // HMC: the main loop runs over ALL evaluations of the trajectory as one long block sequence
   // (num_blocks is even, so chunk / stage / buffer phases simply continue across evaluations)
-  const int n_evals = HMC ? hm.n_iters * (hm.n_lf + 1) : 1;
+  // (n_lf + 1 evaluations for the first MCMC iteration, n_lf for every later one: the metric at the state an
+  // iteration starts from is the one its predecessor ended with -- accepted: the last evaluation, rejected: the
+  // predecessor's own starting metric, kept in the state row)
+  const int n_evals = HMC ? hm.n_iters * hm.n_lf + 1 : 1;
   const int total_blocks = n_evals * num_blocks;
   // local names shadow the tc:: constants of the 3xTF32 kernels
   constexpr int THREADS = h16::THREADS, C_STAGES = h16::C_STAGES, SP_BUFS = h16::SP_BUFS,
@@ -702,8 +706,8 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       // Evaluation k of an iteration (k = 0 .. n_lf) is the metric at the chain's position after k
       // position updates: one metric evaluation per leapfrog step (the reference re-evaluates the same
       // gradient at the end of step k and the start of step k + 1).
-      const int per_it = hm.n_lf + 1;
-      const int it = ev / per_it, k = ev - it * per_it;
+      int it = 0, k = 0;               // evaluation 0 = start of iteration 0; then n_lf evaluations per iteration
+      if (ev > 0) { it = (ev - 1) / hm.n_lf; k = (ev - 1) - it * hm.n_lf + 1; }
       const int64_t r = row0 + prow;
       if (!live) {
 #pragma unroll
@@ -712,7 +716,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         for (int i = 0; i < 16; ++i) total[sym_index(i, i)] = 1.f;
       }
       float lad, dg[16];
-      const bool ok = sym16_factor(total, lad, dg, false);
+      bool ok = sym16_factor(total, lad, dg, false);
       if (!ok) {                       // certified tables: rounding only.  Counted; the host redoes the call unfused.
         if (live) atomicAdd(hm.fail_count, 1);
 #pragma unroll
@@ -727,28 +731,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       }
       const float half_eps = hm.eps / 2.f;
       bool moved_on = true;            // false after the accept step of the LAST iteration (nothing left to evaluate)
-      if (k == 0) {
-        // rho = gamma / beta_zero_sqrt (:123), H0 (:127), first half step (:132-138)
-        float ss = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) gm = __ldg(reinterpret_cast<const float4*>(hm.gamma + ((int64_t)it * n + r) * 16) + q);
-          const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jj = 4 * q + e;
-            const float rho = g4[e] / hm.b0;
-            ss = fmaf(rho, rho, ss);
-            const float g = -((1.f - lambda * dg[jj]) / hm.T2);
-            rh[jj] = rho - half_eps * g;
-            zc[jj] = zc[jj] + hm.eps * rh[jj];
-          }
-        }
-        const float nrm = sqrtf(ss);
-        h0_keep = -hmc_log_pi(lad, ok) + 0.5f * (nrm * nrm);
-        if (live && hm.h0 != nullptr) hm.h0[(int64_t)it * n + r] = h0_keep;
-      } else {
+      bool begin_iteration = (k == 0); // run the first stage of iteration `it_begin` on (dg, lad, ok) at zc
+      int it_begin = it;
+      if (k > 0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 v = *reinterpret_cast<const float4*>(st + 16 + 4 * q);
@@ -800,8 +785,50 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             if (hm.alpha != nullptr) hm.alpha[(int64_t)it * n + r] = a;
             if (hm.moves != nullptr) hm.moves[(int64_t)it * n + r] = mv ? 1.f : 0.f;
           }
-          moved_on = ev + 1 < n_evals;
+          moved_on = it + 1 < hm.n_iters;
+          if (moved_on) {
+            // the next iteration starts from the selected state, whose metric is already known: this
+            // evaluation's if the move was accepted, the one this iteration started from if not
+            if (!mv) {
+              lad = st[34];
+              ok = st[35] != 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(st + 36 + 4 * q);
+                dg[4 * q] = v.x; dg[4 * q + 1] = v.y; dg[4 * q + 2] = v.z; dg[4 * q + 3] = v.w;
+              }
+            }
+            begin_iteration = true;
+            it_begin = it + 1;
+          }
         }
+      }
+      if (begin_iteration) {
+        // rho = gamma / beta_zero_sqrt (:123), H0 (:127), first half step (:132-138); remember the metric here
+        st[34] = lad;
+        st[35] = ok ? 1.f : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(st + 36 + 4 * q) = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) gm = __ldg(reinterpret_cast<const float4*>(hm.gamma + ((int64_t)it_begin * n + r) * 16) + q);
+          const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = 4 * q + e;
+            const float rho = g4[e] / hm.b0;
+            ss = fmaf(rho, rho, ss);
+            const float g = -((1.f - lambda * dg[jj]) / hm.T2);
+            rh[jj] = rho - half_eps * g;
+            zc[jj] = zc[jj] + hm.eps * rh[jj];
+          }
+        }
+        const float nrm = sqrtf(ss);
+        h0_keep = -hmc_log_pi(lad, ok) + 0.5f * (nrm * nrm);
+        if (live && hm.h0 != nullptr) hm.h0[(int64_t)it_begin * n + r] = h0_keep;
       }
       if (moved_on) {
         // publish the position of the next evaluation: state row (z, rho_half, exponent constants) for this
@@ -1978,7 +2005,7 @@ int launch_hmc_trajectory_h16(const rlvae_tables* t, float* z, const float* gamm
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0,
                 "fused HMC trajectory needs 16-byte aligned z and gamma");
   RLVAE_REQUIRE(z_trace == nullptr || (reinterpret_cast<uintptr_t>(z_trace) & 15) == 0, "z_trace must be 16-byte aligned");
-  RLVAE_REQUIRE((int64_t)n_iters * (n_lf + 1) * (t->Kpad / tc::BK) < ((int64_t)1 << 30), "trajectory too long for one launch");
+  RLVAE_REQUIRE(((int64_t)n_iters * n_lf + 1) * (t->Kpad / tc::BK) < ((int64_t)1 << 30), "trajectory too long for one launch");
   tc::HmcArgs hm{};
   hm.z = z; hm.gamma = gamma; hm.acc = acc; hm.scales = scales_dev;
   hm.h0 = h0; hm.h1 = h1; hm.alpha = alpha; hm.moves = moves; hm.z_trace = z_trace; hm.fail_count = fail_count;
