@@ -143,15 +143,6 @@ def measure_bf16_rate(dev):
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def ncu_traffic(kernel_key):
-    """dram bytes per launch from the committed `ncu --set full` capture (profiles/r1_traffic.json)."""
-    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    try:
-        return json.load(open(p)).get(kernel_key)
-    except Exception:
-        return None
-
-
 def cpu_reference_rate(sm, budget_s=12.0, chunk=128, max_points=4096, threads=None):
     """The reference algorithm (CPU oracle port: [n,K,d,d] materialisation + LU inverse + slogdet +
     autograd) on the host cores: evals/s over a bounded sample of the same workload."""

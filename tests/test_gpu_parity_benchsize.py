@@ -141,7 +141,8 @@ def test_fused_hmc_trajectory_is_one_launch_and_matches_the_per_step_path():
     from rlvae_b200 import MetricModel, RiemannianHMCSampler, _capi
     from rlvae_b200.synthetic import make_hmc_streams, make_synthetic_metric
     lib = _capi.lib()
-    for K, n, iters, n_lf, beta0 in ((300, 777, 4, 7, 1.0), (300, 130, 3, 5, 0.3), (10000, 1000, 2, 20, 1.0)):
+    for K, n, iters, n_lf, beta0 in ((300, 777, 4, 7, 1.0), (300, 130, 3, 5, 0.3), (10000, 1000, 2, 20, 1.0),
+                                     (37, 300, 3, 1, 1.0), (100, 64, 2, 2, 0.5), (200, 1, 5, 3, 1.0)):
         sm = make_synthetic_metric(K, 16, seed=0)
         t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
         mt = make_mt(t, 'auto')
@@ -180,7 +181,7 @@ def test_fused_hmc_trajectory_is_one_launch_and_matches_the_per_step_path():
         torch.testing.assert_close(rf['trace'][0][same], ru['trace'][0][same], rtol=1e-4, atol=1e-5)
         # free-running: chains whose decisions never sat within 1e-4 of alpha end in the same state
         clear = ((acc - ru['stats'][2]).abs() > 1e-4).all(dim=0)
-        assert clear.float().mean() > 0.9
+        assert clear.float().mean() > 0.9 or n < 8
         torch.testing.assert_close(zf[clear], zu[clear], rtol=2e-4, atol=2e-4)
         assert torch.equal(rf['stats'][3][:, clear], ru['stats'][3][:, clear])
 
