@@ -784,14 +784,16 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     prof_next();
     return rc;
   }
+  if (ginv != nullptr) a_buf = ginv;            // the caller's buffer is the working copy: no device-to-device copy
   if (int rc = inverse_metric_full(t, z, n, a_buf, path, s, gt_buf)) return rc;
-  if (ginv != nullptr)
-    RLVAE_CUDA_OK(cudaMemcpyAsync(ginv, a_buf, sizeof(float) * mat, cudaMemcpyDeviceToDevice, s));
   // the gradient contracts M_k with G^T (d log det A = tr(A^{-1} dA)); for symmetric tables
   // G^T == G up to rounding, otherwise a transposed copy is produced.
   const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
   const bool plain_g = (g != nullptr) || ((grad_logdet_g != nullptr) && t->symmetric);
   if (plain_g || logdet_g != nullptr) {
+    // (d = 64: a one-warp-per-matrix Cholesky in shared memory was tried for the symmetric case and lost to this
+    // register-resident Gauss-Jordan, 36 vs 20 ms per 2^17 matrices: 133 KB of shared memory per CTA left one warp
+    // per scheduler and every dependent shared-memory load exposed)
     if (int rc = launch_batched_inverse(a_buf, n, d, plain_g ? g_buf : nullptr, logdet_g ? lad_buf : nullptr,
                                         nullptr, nullptr, 0, s))
       return rc;

@@ -402,14 +402,17 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
 // into partial[c][n][:]; reduce_partials64_kernel adds the 17 tiles in a fixed order (deterministic).
 // Every column tile recomputes the distance GEMM and the exp stage for its 128 points (as the forward
 // kernel does).  Per 64-centroid super-block, all on kind::f16 with the split hi + lo operands:
-//   GEMM1  S[128 x 64]  = Z'.C'^T           12 MMAs, A = z' tiles in SHARED memory (TMEM is full)
+//   GEMM1  S[128 x 64]  = Z'.C'^T           12 MMAs, A = z' (hi | lo) resident in TMEM
 //   T-GEMM T[128 x 64]  = U'.M'^T           24 MMAs (K = 128 columns), A = U' (hi | lo) resident in TMEM,
 //                                           B = natural table tiles [64 centroids x 128 columns]
 //   exp    u' = 2^-21 w t, split hi | lo fp16, written over S (the layout of the forward kernel's P)
 //   GEMM3  OUT[128 x 64] += u'.C'            12 MMAs, B = (c - shift)^T tiles [64 dims x 64 centroids]
-// = 384 + 768 + 384 tensor cycles.  u' <= 2^14 because |t'| <= 128 * 2^28; both fp16 operands of GEMM3 are exact
+// = 384 + 768 + 384 tensor cycles (A from shared memory cost 48 instead of 32 cycles per GEMM1 MMA -- measured
+// 126 -> 120 ms per 2^17 points at K = 50k -- so z' lives in TMEM and OUT has ONE chunk accumulator: its fold
+// runs under the next block's T-GEMM anyway).  u' <= 2^14 because |t'| <= 128 * 2^28; both fp16 operands of GEMM3 are exact
 // hi + lo sums down to 2^-25 absolute (2^-39 of the largest u').
-// TMEM: [0,64) U'_hi, [64,128) U'_lo, [128,384) two (S | T) buffers, [384,512) two OUT chunk accumulators.
+// TMEM: [0,64) U'_hi, [64,128) U'_lo, [128,384) two (S | T) buffers, [384,448) the OUT chunk accumulator,
+//       [448,480) z'_hi, [480,512) z'_lo.
 // Warps: 0 TMA (C, bias, C^T), 1 MMA issuer (GEMM1 + T), 2-5 / 6-9 exp groups (32 centroids each of every
 // super-block), 10 TMA (table tiles), 11 MMA issuer (GEMM3).
 // ==========================================================================================
@@ -421,14 +424,12 @@ constexpr int M_STAGES = 2;
 constexpr int NT = 128;                                   // packed columns per CTA = K of the T GEMM
 constexpr int KSTEPS = NT / 16;
 constexpr int NTILES = h64::NPAD / NT;                    // 17
-constexpr uint32_t ZA_BYTES = TILE_M * 128;               // [128 points x 64 dims] fp16: one swizzle row per point
 constexpr uint32_t C_TILE64 = h64::C_TILE64;              // [64 centroids x (hi atom | lo atom)]
 constexpr uint32_t CT_HALF = D * 128;                     // [64 dims x 64 centroids] fp16 (pair: 32 rows used)
 constexpr uint32_t CT_TILE = 2 * CT_HALF;                 // hi, lo
 constexpr uint32_t M_HALF = 2 * BK * 128;                 // 2 column atoms (64 fp16 each) x 64 centroid rows
 constexpr uint32_t M_TILE = 2 * M_HALF;                   // hi, lo
-constexpr uint32_t OFF_ZA = 0;
-constexpr uint32_t OFF_C = OFF_ZA + 2 * ZA_BYTES;
+constexpr uint32_t OFF_C = 0;
 constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE64;
 constexpr uint32_t OFF_M = OFF_CT + C_STAGES * CT_TILE;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE;
@@ -437,7 +438,7 @@ constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr uint32_t TM_UHI = 0, TM_ULO = 64, TM_ST = 128, TM_OUT = 384;
+constexpr uint32_t TM_UHI = 0, TM_ULO = 64, TM_ST = 128, TM_OUT = 384, TM_ZHI = 448, TM_ZLO = 480;
 constexpr int RED_LD = 68;
 static_assert(TILE_M * RED_LD * 4 <= M_STAGES * M_TILE, "group-combine staging must fit the M ring");
 constexpr float U_DOWN = 4.76837158203125e-07f;           // 2^-21
@@ -493,9 +494,10 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
   constexpr int C_STAGES = g64::C_STAGES, M_STAGES = g64::M_STAGES, RED_LD = g64::RED_LD, KSTEPS = g64::KSTEPS,
                 D = g64::D, NT = g64::NT;
   constexpr uint32_t C_TILE64 = g64::C_TILE64, CT_HALF = g64::CT_HALF, CT_TILE = g64::CT_TILE, M_HALF = g64::M_HALF,
-                     M_TILE = g64::M_TILE, OFF_ZA = g64::OFF_ZA, OFF_C = g64::OFF_C, OFF_CT = g64::OFF_CT,
-                     OFF_M = g64::OFF_M, OFF_BIAS = g64::OFF_BIAS, ZA_BYTES = g64::ZA_BYTES,
-                     TM_UHI = g64::TM_UHI, TM_ULO = g64::TM_ULO, TM_ST = g64::TM_ST, TM_OUT = g64::TM_OUT;
+                     M_TILE = g64::M_TILE, OFF_C = g64::OFF_C, OFF_CT = g64::OFF_CT,
+                     OFF_M = g64::OFF_M, OFF_BIAS = g64::OFF_BIAS,
+                     TM_UHI = g64::TM_UHI, TM_ULO = g64::TM_ULO, TM_ST = g64::TM_ST, TM_OUT = g64::TM_OUT,
+                     TM_ZHI = g64::TM_ZHI, TM_ZLO = g64::TM_ZLO;
   constexpr int CHUNK = 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -594,30 +596,23 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     }
     zb = -nrm * alpha;
     s_scale = 2.f * alpha * c_unscale * __uint_as_float((uint32_t)(127 - ez) << 23);
-    if (grp == 0) {
+    if (grp == 0) {                  // the A operand of GEMM1 (split fp16) goes into TMEM
       const float zsc = __uint_as_float((uint32_t)(ez + 127) << 23);
       const float4* src = reinterpret_cast<const float4*>(z + r * D);
-      uint8_t* ahi = gbase + OFF_ZA + prow * 128;
-      uint8_t* alo = ahi + ZA_BYTES;
+      uint32_t zh[32], zl[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                       // 16-byte chunk c = dims [8c, 8c + 8)
-        uint32_t h4[4], l4[4];
-#pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < n) {
-            v = __ldg(src + 2 * c + hq);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + 2 * c + hq);
-            v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
-          }
-          split_pair(v.x * zsc, v.y * zsc, h4[2 * hq], l4[2 * hq]);
-          split_pair(v.z * zsc, v.w * zsc, h4[2 * hq + 1], l4[2 * hq + 1]);
+      for (int q = 0; q < D / 4; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) {
+          v = __ldg(src + q);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+          v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
         }
-        const int pc = (c ^ (prow & 7)) * 16;               // 128-byte swizzle
-        *reinterpret_cast<uint4*>(ahi + pc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-        *reinterpret_cast<uint4*>(alo + pc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+        split_pair(v.x * zsc, v.y * zsc, zh[2 * q], zl[2 * q]);
+        split_pair(v.z * zsc, v.w * zsc, zh[2 * q + 1], zl[2 * q + 1]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> async proxy (UMMA)
+      TMEM_ST32(tmem_base + lane_addr + TM_ZHI, zh);
+      TMEM_ST32(tmem_base + lane_addr + TM_ZLO, zl);
     }
     // ---- U' = 2^eU Ut for this column tile: group g converts packed columns [64 g, 64 g + 64) of the tile
     int e_u = 0;
@@ -657,7 +652,6 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
   tc_fence_after();
 
 #define MMA_TS64(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_64, acc); else mma_ts_f16(d, a, b, IDESC_64, acc); } while (0)
-#define MMA_SS64(d, a, b, acc) do { if (PAIR) mma_ss_f16_pair(d, a, b, IDESC_64, acc); else mma_ss_f16(d, a, b, IDESC_64, acc); } while (0)
 #define COMMIT(bar) do { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); } while (0)
 
   if (warp == 0) {
@@ -712,8 +706,6 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     // =========================================================== MMA issuer 1 (pair: leader only): GEMM1 + T-GEMM
     if (leader) {
       static_assert(C_STAGES == 4 && M_STAGES == 2 && CHUNK == 2, "the 4x unrolled issue loops assume these periods");
-      const uint64_t za_hi = make_desc_sw128(base + OFF_ZA);
-      const uint64_t za_lo = make_desc_sw128(base + OFF_ZA + ZA_BYTES);
       const uint64_t c_desc0 = make_desc_sw128(base + OFF_C);
       const uint64_t m_desc0 = make_desc_sw128(base + OFF_M);
       auto issue_st = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
@@ -731,11 +723,11 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
         const uint64_t ml = mh + (M_HALF >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_hi + 2 * kk, ch + 2 * kk, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) MMA_TS64(s_t, tmem_base + TM_ZHI + 8 * kk, ch + 2 * kk, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_hi + 2 * kk, cl + 2 * kk, 1);
+          for (int kk = 0; kk < 4; ++kk) MMA_TS64(s_t, tmem_base + TM_ZHI + 8 * kk, cl + 2 * kk, 1);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) MMA_SS64(s_t, za_lo + 2 * kk, ch + 2 * kk, 1);
+          for (int kk = 0; kk < 4; ++kk) MMA_TS64(s_t, tmem_base + TM_ZLO + 8 * kk, ch + 2 * kk, 1);
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk)
             MMA_TS64(t_t, tmem_base + TM_UHI + 8 * kk, mh + (kk >> 2) * M_ATOM_DESC + 2 * (kk & 3), kk > 0);
@@ -761,20 +753,16 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     // =========================================================== MMA issuer 2 (pair: leader only): GEMM3
     if (leader) {
       const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
-      uint32_t free_phase = 0;
       auto issue_g3 = [&](auto Jc, const int j, const uint32_t qodd) {
         constexpr int J = decltype(Jc)::value;
-        constexpr int cs = J % C_STAGES, sb = J & 1, cb = (J >> 1) & 1;
+        constexpr int cs = J % C_STAGES, sb = J & 1, cpar = (J >> 1) & 1;     // cpar: parity of the chunk index j / 2
         constexpr int first = (J % CHUNK) == 0;
-        if (first && j >= 2 * CHUNK) {
-          mbar_wait(BAR_CH_FREE(cb), (free_phase >> cb) & 1u);
-          free_phase ^= 1u << cb;
-        }
+        if (first && j >= CHUNK) mbar_wait(BAR_CH_FREE(0), cpar ^ 1);        // the fold of chunk j/2 - 1 has drained OUT
         mbar_wait(BAR_CT_FULL(cs), qodd);
         mbar_wait(BAR_U_FULL(sb), (J >> 1) & 1);
         tc_fence_after();
         const uint32_t up = tmem_base + TM_ST + sb * 128;     // k-step kk: u'_hi at (kk>>1)*32 + (kk&1)*8, u'_lo 16 further
-        const uint32_t acc = tmem_base + TM_OUT + cb * 64;
+        const uint32_t acc = tmem_base + TM_OUT;
         const uint64_t th = ct_desc0 + ((cs * CT_TILE) >> 4);
         const uint64_t tl = th + (CT_HALF >> 4);
         if (elect_one()) {
@@ -789,7 +777,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
             MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, tl + 2 * kk, 1);
           COMMIT(BAR_CT_EMPTY(cs));
           COMMIT(BAR_G3_DONE(sb));
-          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(cb));
+          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(0));
         }
         __syncwarp();
       };
@@ -812,7 +800,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t a[32];
-        TMEM_LD32(tmem_base + lane_addr + TM_OUT + (c & 1) * 64 + hh * 32, a);
+        TMEM_LD32(tmem_base + lane_addr + TM_OUT + hh * 32, a);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) tot[hh * 32 + i] += __uint_as_float(a[i]);
@@ -820,10 +808,10 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
       if (signal) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(0)); else mbar_arrive(BAR_CH_FREE(0)); }
       }
     };
-    int next_chunk = grp;
+    int next_chunk = grp;            // chunk c is folded by group c & 1 (one accumulator: the chunks alternate in time)
     for (int j = 0; j < num_blocks; ++j) {
       const int cs = j % C_STAGES, sb = j & 1;
       const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
@@ -862,15 +850,20 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
         mbar_arrive(BAR_C_EMPTY(cs));
       }
       while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
-        mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
+        mbar_wait(BAR_CH_FULL(0), next_chunk & 1);
         tc_fence_after();
         fold_chunk(next_chunk, true);
         next_chunk += 2;
       }
     }
+    // the last one or two chunks: each still has to be handed back before the other group's chunk can be issued
+    while (next_chunk < num_chunks) {
+      mbar_wait(BAR_CH_FULL(0), next_chunk & 1);
+      tc_fence_after();
+      fold_chunk(next_chunk, next_chunk + 1 < num_chunks);
+      next_chunk += 2;
+    }
     mbar_wait(BAR_DONE, 0);
-    tc_fence_after();
-    while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
     // ---------------------------------------------------------- combine the two groups, write the tile's partial result
     asm volatile("bar.sync 1, 256;" ::: "memory");
     float* red = reinterpret_cast<float*>(gbase + OFF_M);
@@ -905,7 +898,6 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     }
   }
 #undef MMA_TS64
-#undef MMA_SS64
 #undef COMMIT
 
   tc_fence_before();

@@ -1,0 +1,28 @@
+"""One d = 64, K = 50,000 evaluation chunk (2^17 points: G^-1 + log det G + grad) for the ncu launch list.
+usage: python scripts/profile_d64.py [n_points] [K]"""
+import contextlib, io, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from rlvae_b200 import MetricTensor
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 17
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
+d = 64
+dev = torch.device('cuda:0')
+g = torch.Generator(device=dev).manual_seed(1234)
+c = torch.randn(K, d, device=dev, generator=g)
+L = torch.tril(torch.randn(K, d, d, device=dev, generator=g)) * d ** -0.5
+M = L @ L.transpose(1, 2)
+del L
+M = 0.5 * (M + M.transpose(1, 2))
+T, lam = 0.75 * d ** 0.5, 0.01
+z = torch.randn(n, d, device=dev, generator=g)
+w = torch.exp(-torch.cdist(z[:64].double(), c.double()) ** 2 / T ** 2).sum(1).mean().item()
+mt = MetricTensor(d, device=dev)
+with contextlib.redirect_stdout(io.StringIO()):
+    mt.load_pretrained(c, (M / w).contiguous(), temperature=T, regularization=lam)
+out = {}
+for _ in range(2):
+    out = mt.evaluate(z, want_ginv=True, want_logdet=True, want_grad=True, out=out)
+torch.cuda.synchronize()
+print('ok', float(out['logdet_g'][:4].sum()), float(out['grad_logdet_g'][:4].abs().sum()))
