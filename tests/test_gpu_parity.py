@@ -841,3 +841,32 @@ def test_cholesky_failure_takes_the_reference_eigh_fallback():
     # and the all-positive-definite batch keeps the Cholesky path
     a[7] = a[6]
     torch.testing.assert_close(chol_apply(a.to(dev()), eps.to(dev())).cpu(), O.chol_apply(a, eps), rtol=2e-5, atol=2e-5)
+
+
+def test_kmedoids_centroid_selection_invariants():
+    """8f rank 4, centroid selection (ref scripts/train_and_extract_vanilla_vae.py:187-197).  sklearn_extra is absent,
+    so the reference's indices cannot be pinned (parity unpinned for this one function); what can be
+    checked is the algorithm: medoids are data points, the cost never increases, the result is a fixed point of
+    the alternate update (every medoid minimises the distance sum of its own cluster), well-separated blobs are
+    recovered, and a seed reproduces."""
+    from rlvae_b200 import metric_builder
+    gen = torch.Generator().manual_seed(0)
+    centres = torch.randn(6, 16, generator=gen) * 8.0
+    x = (centres[:, None, :] + 0.3 * torch.randn(6, 150, 16, generator=gen)).reshape(-1, 16).to(dev())
+    idx, info = metric_builder.select_centroids_kmedoids(x, 6, seed=42, return_info=True)
+    assert idx.shape == (6,) and idx.unique().numel() == 6
+    hist = info['cost_history']
+    assert all(b <= a + 1e-3 for a, b in zip(hist, hist[1:]))
+    # one medoid per blob
+    assert sorted((idx // 150).tolist()) == list(range(6))
+    # fixed point: within every cluster no member has a smaller distance sum than the medoid
+    xs = (x - x.mean(0)) / x.std(0, unbiased=False)
+    dist = torch.cdist(xs, xs)
+    for k in range(6):
+        members = (info['labels'] == k).nonzero().flatten()
+        sums = dist[members][:, members].sum(1)
+        assert sums.min() >= dist[idx[k], members].sum() - 1e-3
+    assert torch.equal(metric_builder.select_centroids_kmedoids(x, 6, seed=42), idx)
+    # feeds the rest of the construction
+    data = metric_builder.build_metric_data(x, centroid_indices=idx, temperature=0.5)
+    assert data['centroids'].shape == (6, 16) and data['M_matrices'].shape == (6, 16, 16)
