@@ -1899,6 +1899,16 @@ static bool h16_use_pairs() {
   return v == 1;
 }
 
+// The gradient kernel has its own switch (RLVAE_TC_PAIR_GRAD, default: follow RLVAE_TC_PAIR): with its small
+// N = 64 / N = 16 MMAs the CTA-pair form saves little B-tile traffic and pays for cross-CTA barrier hops.
+static bool g16_use_pairs() {
+  static const int v = [] {
+    const char* e = getenv("RLVAE_TC_PAIR_GRAD");
+    return (e == nullptr) ? -1 : ((e[0] == '0') ? 0 : 1);
+  }();
+  return v < 0 ? h16_use_pairs() : v == 1;
+}
+
 template <bool PAIR, bool EXACT, bool HYBRID = false, bool HMC = false>
 static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s,
                       const tc::HmcArgs& hm = tc::HmcArgs{}) {
@@ -2065,12 +2075,12 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
   const int mode = h16_mode(t);
   if (mode == 1)
-    return h16_use_pairs() ? launch_g16<true, true>(t, z, u, n, scale, out, s, u_packed)
+    return g16_use_pairs() ? launch_g16<true, true>(t, z, u, n, scale, out, s, u_packed)
                            : launch_g16<false, true>(t, z, u, n, scale, out, s, u_packed);
   if (mode == 2)
-    return h16_use_pairs() ? launch_g16<true, false, true>(t, z, u, n, scale, out, s, u_packed)
+    return g16_use_pairs() ? launch_g16<true, false, true>(t, z, u, n, scale, out, s, u_packed)
                            : launch_g16<false, false, true>(t, z, u, n, scale, out, s, u_packed);
-  return h16_use_pairs() ? launch_g16<true, false>(t, z, u, n, scale, out, s, u_packed)
+  return g16_use_pairs() ? launch_g16<true, false>(t, z, u, n, scale, out, s, u_packed)
                          : launch_g16<false, false>(t, z, u, n, scale, out, s, u_packed);
 }
 
