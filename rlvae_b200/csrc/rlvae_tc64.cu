@@ -405,8 +405,12 @@ inverse_metric_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
 //   GEMM1  S[128 x 64]  = Z'.C'^T           12 MMAs, A = z' (hi | lo) resident in TMEM
 //   T-GEMM T[128 x 64]  = U'.M'^T           24 MMAs (K = 128 columns), A = U' (hi | lo) resident in TMEM,
 //                                           B = natural table tiles [64 centroids x 128 columns]
-//   exp    u' = 2^-21 w t, split hi | lo fp16, written over S (the layout of the forward kernel's P)
-//   GEMM3  OUT[128 x 64] += u'.C'            12 MMAs, B = (c - shift)^T tiles [64 dims x 64 centroids]
+//   exp    u = w t; the two threads that own a point (one per exp group, 32 centroids each) agree on one power
+//          of two per block through shared memory, u' = 2^s u has its largest element in [2^13, 2^14), split
+//          hi | lo fp16, written over S (the layout of the forward kernel's P).  A fixed scale would lose the
+//          RELATIVE accuracy of points whose weights are uniformly tiny (far from every centroid).
+//   GEMM3  OUT[128 x 64] = u'.C'             12 MMAs, B = (c - shift)^T tiles [64 dims x 64 centroids]; a fresh
+//          accumulation per block, folded as 2^-s OUT into fp32 registers (group g: output dims [32g, 32g+32))
 // = 384 + 768 + 384 tensor cycles (A from shared memory cost 48 instead of 32 cycles per GEMM1 MMA -- measured
 // 126 -> 120 ms per 2^17 points at K = 50k -- so z' lives in TMEM and OUT has ONE chunk accumulator: its fold
 // runs under the next block's T-GEMM anyway).  u' <= 2^14 because |t'| <= 128 * 2^28; both fp16 operands of GEMM3 are exact
@@ -433,16 +437,13 @@ constexpr uint32_t OFF_C = 0;
 constexpr uint32_t OFF_CT = OFF_C + C_STAGES * C_TILE64;
 constexpr uint32_t OFF_M = OFF_CT + C_STAGES * CT_TILE;
 constexpr uint32_t OFF_BIAS = OFF_M + M_STAGES * M_TILE;
-constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
+constexpr uint32_t OFF_UMAX = OFF_BIAS + C_STAGES * BIAS_BYTES;   // [2 block parities][2 groups][128 points] block maxima
+constexpr uint32_t OFF_BAR = OFF_UMAX + 2 * 2 * TILE_M * 4;
 constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 64, TM_ST = 128, TM_OUT = 384, TM_ZHI = 448, TM_ZLO = 480;
-constexpr int RED_LD = 68;
-static_assert(TILE_M * RED_LD * 4 <= M_STAGES * M_TILE, "group-combine staging must fit the M ring");
-constexpr float U_DOWN = 4.76837158203125e-07f;           // 2^-21
-constexpr float U_UP = 2097152.f;                         // 2^21
 }  // namespace g64
 
 // per-point exponent eU with max|2^eU Ut| in [2^13, 2^14): Ut_p = U_ij + U_ji <= 2 max|U|
@@ -491,8 +492,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
                        const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
                        float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
                        const float* __restrict__ cshift /* [64] */, float* __restrict__ partial /* [17, N, 64] */) {
-  constexpr int C_STAGES = g64::C_STAGES, M_STAGES = g64::M_STAGES, RED_LD = g64::RED_LD, KSTEPS = g64::KSTEPS,
-                D = g64::D, NT = g64::NT;
+  constexpr int C_STAGES = g64::C_STAGES, M_STAGES = g64::M_STAGES, KSTEPS = g64::KSTEPS, D = g64::D, NT = g64::NT;
   constexpr uint32_t C_TILE64 = g64::C_TILE64, CT_HALF = g64::CT_HALF, CT_TILE = g64::CT_TILE, M_HALF = g64::M_HALF,
                      M_TILE = g64::M_TILE, OFF_C = g64::OFF_C, OFF_CT = g64::OFF_CT,
                      OFF_M = g64::OFF_M, OFF_BIAS = g64::OFF_BIAS,
@@ -531,7 +531,6 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
   constexpr uint32_t M_ATOM_DESC = M_ATOM_BYTES >> 4;
   constexpr int CT_ROWS = D / NPAIR;                        // rows (latent dims) of a C^T tile held by this CTA
   constexpr uint32_t IDESC_64 = make_idesc_f16(PAIR ? 256 : 128, BK);     // N = 64 for all three GEMMs
-  const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C_STAGES; ++s) {
@@ -541,7 +540,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), 8 * NPAIR);
-      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
+      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 8 * NPAIR);     // both exp groups fold every block
       mbar_init(BAR_G3_DONE(b), 1);
     }
     mbar_init(BAR_DONE, 1);
@@ -755,9 +754,8 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
       const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
       auto issue_g3 = [&](auto Jc, const int j, const uint32_t qodd) {
         constexpr int J = decltype(Jc)::value;
-        constexpr int cs = J % C_STAGES, sb = J & 1, cpar = (J >> 1) & 1;     // cpar: parity of the chunk index j / 2
-        constexpr int first = (J % CHUNK) == 0;
-        if (first && j >= CHUNK) mbar_wait(BAR_CH_FREE(0), cpar ^ 1);        // the fold of chunk j/2 - 1 has drained OUT
+        constexpr int cs = J % C_STAGES, sb = J & 1;
+        if (j >= 1) mbar_wait(BAR_CH_FREE(0), (J + 1) & 1);                  // both groups have folded block j - 1 out of OUT
         mbar_wait(BAR_CT_FULL(cs), qodd);
         mbar_wait(BAR_U_FULL(sb), (J >> 1) & 1);
         tc_fence_after();
@@ -768,7 +766,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, th + 2 * kk, !(first && kk == 0));
+            MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, th + 2 * kk, kk > 0);       // a fresh sum per block
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             MMA_TS64(acc, up + (kk >> 1) * 32 + 16 + (kk & 1) * 8, th + 2 * kk, 1);
@@ -777,7 +775,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
             MMA_TS64(acc, up + (kk >> 1) * 32 + (kk & 1) * 8, tl + 2 * kk, 1);
           COMMIT(BAR_CT_EMPTY(cs));
           COMMIT(BAR_G3_DONE(sb));
-          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(0));
+          COMMIT(BAR_CH_FULL(0));
         }
         __syncwarp();
       };
@@ -792,26 +790,27 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     }
   } else {
     // =========================================================== exp groups (one thread per point, 32 centroids of every block)
-    float tot[D];                        // this group's share of OUT (chunks of parity grp)
-    float su = 0.f;                      // and of sum_k u'
+    float tot[32];                       // output dims [32 grp, 32 grp + 32) of sum_blocks 2^-s OUT
+    float su = 0.f;                      // this group's share of sum_k u
 #pragma unroll
-    for (int e = 0; e < D; ++e) tot[e] = 0.f;
-    auto fold_chunk = [&](int c, bool signal) {
+    for (int e = 0; e < 32; ++e) tot[e] = 0.f;
+    float* umax_sm = reinterpret_cast<float*>(gbase + g64::OFF_UMAX);
+    // fold block jb: this group's half of the output columns, un-scaled by the block's 2^-s
+    auto fold_block = [&](int jb, float unscale, bool signal) {
+      mbar_wait(BAR_CH_FULL(0), jb & 1);
+      tc_fence_after();
+      uint32_t a[32];
+      TMEM_LD32(tmem_base + lane_addr + TM_OUT + grp * 32, a);
+      tmem_wait_ld();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t a[32];
-        TMEM_LD32(tmem_base + lane_addr + TM_OUT + hh * 32, a);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tot[hh * 32 + i] += __uint_as_float(a[i]);
-      }
+      for (int i = 0; i < 32; ++i) tot[i] = fmaf(__uint_as_float(a[i]), unscale, tot[i]);
       if (signal) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(0)); else mbar_arrive(BAR_CH_FREE(0)); }
       }
     };
-    int next_chunk = grp;            // chunk c is folded by group c & 1 (one accumulator: the chunks alternate in time)
+    float unsc_prev = 0.f;               // 2^-s of the previous block (folded one block late: its GEMM3 runs meanwhile)
     for (int j = 0; j < num_blocks; ++j) {
       const int cs = j % C_STAGES, sb = j & 1;
       const uint32_t st = tmem_base + lane_addr + TM_ST + sb * 128;
@@ -823,23 +822,37 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
       TMEM_LD32(st + 64 + grp * 32, tv);
       const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + grp * 8;
       tmem_wait_ld();
-      float su_blk = 0.f;
+      float su_blk = 0.f, umax = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 bv = bias4[q];
         const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
-        float uv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * q + e;
           const float w = ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
-          uv[e] = w * (__uint_as_float(tv[i]) * g64::U_DOWN);
-          su_blk += uv[e];
+          const float uv = w * __uint_as_float(tv[i]);
+          su_blk += uv;
+          umax = fmaxf(umax, fabsf(uv));
+          tv[i] = __float_as_uint(uv);
         }
-        split_pair(uv[0], uv[1], ph[2 * q], pl[2 * q]);
-        split_pair(uv[2], uv[3], ph[2 * q + 1], pl[2 * q + 1]);
       }
       su += su_blk;
+      // one scale per (point, block): the larger of the two groups' maxima, exchanged through shared memory
+      umax_sm[(sb * 2 + grp) * TILE_M + prow] = umax;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      umax = fmaxf(umax, umax_sm[(sb * 2 + (grp ^ 1)) * TILE_M + prow]);
+      int es = 0;
+      if (umax > 0.f && umax < 3.0e38f) {
+        const int ex = (int)((__float_as_uint(umax) >> 23) & 0xffu) - 126;     // umax = f 2^ex, f in [0.5, 1)
+        es = 14 - ex;
+        es = es > 100 ? 100 : (es < -100 ? -100 : es);
+      }
+      const float usc_blk = __uint_as_float((uint32_t)(es + 127) << 23);
+      const float unsc_cur = __uint_as_float((uint32_t)(127 - es) << 23);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        split_pair(__uint_as_float(tv[2 * i]) * usc_blk, __uint_as_float(tv[2 * i + 1]) * usc_blk, ph[i], pl[i]);
       TMEM_ST16(st + grp * 32, ph);
       TMEM_ST16(st + grp * 32 + 16, pl);
       tmem_wait_st();
@@ -849,49 +862,31 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
         if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
         mbar_arrive(BAR_C_EMPTY(cs));
       }
-      while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
-        mbar_wait(BAR_CH_FULL(0), next_chunk & 1);
-        tc_fence_after();
-        fold_chunk(next_chunk, true);
-        next_chunk += 2;
-      }
+      if (j > 0) fold_block(j - 1, unsc_prev, true);      // GEMM3(j) starts a fresh sum in the same accumulator
+      unsc_prev = unsc_cur;
     }
-    // the last one or two chunks: each still has to be handed back before the other group's chunk can be issued
-    while (next_chunk < num_chunks) {
-      mbar_wait(BAR_CH_FULL(0), next_chunk & 1);
-      tc_fence_after();
-      fold_chunk(next_chunk, next_chunk + 1 < num_chunks);
-      next_chunk += 2;
-    }
+    if (num_blocks > 0) fold_block(num_blocks - 1, unsc_prev, false);
     mbar_wait(BAR_DONE, 0);
-    // ---------------------------------------------------------- combine the two groups, write the tile's partial result
+    // ---------------------------------------------------------- sum_k u over both groups, write this group's half of the row
+    umax_sm[grp * TILE_M + prow] = su;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    float* red = reinterpret_cast<float*>(gbase + OFF_M);
-    if (grp == 1) {
-#pragma unroll
-      for (int q = 0; q < D / 4; ++q)
-        *reinterpret_cast<float4*>(red + prow * RED_LD + 4 * q) = make_float4(tot[4 * q], tot[4 * q + 1], tot[4 * q + 2], tot[4 * q + 3]);
-      red[prow * RED_LD + D] = su;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (grp == 0) {
+    {
       const int64_t r = row0 + prow;
       if (r < n) {
-        const float sut = su + red[prow * RED_LD + D];
-        const float f = g64::U_UP * u_unscale * scale;
-        float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)col_tile * n + r) * D);
-        const float4* zsrc = reinterpret_cast<const float4*>(z + r * D);
+        const float sut = su + umax_sm[(grp ^ 1) * TILE_M + prow];
+        const float f = u_unscale * scale;
+        float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)col_tile * n + r) * D + grp * 32);
+        const float4* zsrc = reinterpret_cast<const float4*>(z + r * D + grp * 32);
 #pragma unroll
-        for (int q = 0; q < D / 4; ++q) {
-          const float4 rv = *reinterpret_cast<const float4*>(red + prow * RED_LD + 4 * q);
+        for (int q = 0; q < 8; ++q) {
           float4 zv = __ldg(zsrc + q);
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift) + q);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(cshift + grp * 32) + q);
           zv.x -= sh.x; zv.y -= sh.y; zv.z -= sh.z; zv.w -= sh.w;
           float4 o;
-          o.x = ((tot[4 * q] + rv.x) * c_unscale - zv.x * sut) * f;          // C^T tiles hold 2^ec (c - shift)
-          o.y = ((tot[4 * q + 1] + rv.y) * c_unscale - zv.y * sut) * f;
-          o.z = ((tot[4 * q + 2] + rv.z) * c_unscale - zv.z * sut) * f;
-          o.w = ((tot[4 * q + 3] + rv.w) * c_unscale - zv.w * sut) * f;
+          o.x = (tot[4 * q] * c_unscale - zv.x * sut) * f;          // C^T tiles hold 2^ec (c - shift)
+          o.y = (tot[4 * q + 1] * c_unscale - zv.y * sut) * f;
+          o.z = (tot[4 * q + 2] * c_unscale - zv.z * sut) * f;
+          o.w = (tot[4 * q + 3] * c_unscale - zv.w * sut) * f;
           dst[q] = o;
         }
       }

@@ -294,3 +294,33 @@ def test_d64_tensor_gradient_kernel_general_u_and_tile_tails():
     (mt.compute_inverse_metric(zg) * w).sum().backward()
     ref = O.metric_backward(zg.detach().cpu(), *t[:3], w.cpu())
     assert rel_fro(zg.grad.cpu(), ref) < TOL_LD
+
+
+@pytest.mark.parametrize('d,K', [(16, 300), (64, 300)])
+def test_gradient_rows_of_far_points_keep_relative_accuracy(d, K):
+    """The gradient kernels form u = w t and contract it on kind::f16.  A point far from every centroid has
+    uniformly tiny weights (down to e^-36 here), so a fixed fp16 scale would push its u into the subnormals
+    and lose the RELATIVE accuracy of its row (caught by golden scaled_T07 during development); u is scaled per
+    (point, block) instead.  Rows at increasing distance, arbitrary U, against the oracle formula."""
+    from rlvae_b200 import _capi
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(K, d, seed=13)
+    T = 0.9 if d == 16 else sm.temperature     # d = 64: the tensor path is only selected where the expanded distance form is accurate
+    t = (sm.centroids, sm.metric_matrices, T, sm.regularization)
+    mt = make_mt(t, 'auto')
+    tab = mt._tables(dev())
+    assert tab.tensor_auto
+    gen = torch.Generator().manual_seed(14)
+    base = sm.centroids[torch.arange(160) % K]
+    # (from 0.3 T outwards: exactly ON a centroid its own term vanishes and the row is a cancellation residue)
+    shift = torch.linspace(0.3, 6.0, 160)[:, None] * torch.nn.functional.normalize(torch.randn(160, d, generator=gen), dim=1)
+    z = (base + shift * T).contiguous()
+    U = torch.randn(160, d, d, generator=gen)
+    ref = torch.cat([O.metric_backward(z[i:i + 16].double(), t[0].double(), t[1].double(), T, U[i:i + 16].double())
+                     for i in range(0, 160, 16)]).float()
+    got = _capi.metric_grad(tab, z.to(dev()), U.to(dev()), 2.0 / T ** 2, _capi.PATH_AUTO).cpu()
+    rows = ref.norm(dim=1)
+    assert rows.min() < 1e-3 * rows.max()                      # the far rows really are tiny in absolute terms
+    live = rows > 0
+    err = ((got.double() - ref.double()).norm(dim=1) / rows.double().clamp_min(1e-300))[live]
+    assert err.max() < TOL_LD, float(err.max())
