@@ -347,8 +347,8 @@ def run_ours(args):
         prof = committed_profile()
         burst, sustained = float(peaks['bf16_tflops']), float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
         if sym_tensor and in_step is not None:
-            # Tensor work in fp16 flops (every MMA of both kernels is kind::f16 now).  Three conventions, printed
-            # side by side:
+            # Tensor work in fp16-equivalent flops: a TF32 MAC costs two fp16 MACs of pipe time (the measured
+            # TF32 GEMM rate is half the bf16 one).  Three conventions, printed side by side:
             #   packed   ALGORITHMIC work of this design: symmetric tables -> 136 packed columns (+16 distance
             #            dims), x3 split passes, no padding          
             #   dense_8d SURVEY.md 8d's dense-M count 2Kd(d+1) per eval and kernel, x3 split passes
@@ -378,9 +378,9 @@ def run_ours(args):
                         'peak_source': f'MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained ({peak_src})'}
 
             f_fwd = n * 3.0 * 2 * K * (136 + 16)
-            f_grad = n * 3.0 * 2 * K * (136 + 16 + 16)            # T GEMM + distance GEMM + final contraction, all kind::f16
+            f_grad = n * 3.0 * 2 * K * (136 + 16 + 2 * 16)
             issued_fwd = n * 3.0 * 2 * tab.Kpad * (144 + 16)
-            issued_grad = n * 3.0 * 2 * tab.Kpad * (144 + 16 + 16)
+            issued_grad = n * 3.0 * 2 * tab.Kpad * (144 + 16 + 2 * 16)
             roof_g = block('metric_grad_h16_kernel', in_step['gradient_ms'], grad_alone_ms, f_grad, issued_grad,
                            'metric_grad_h16_kernel')
             roof_fwd = block('inverse_metric_h16_kernel (fused G^-1 + Cholesky log det + packed G)',

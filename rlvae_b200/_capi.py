@@ -14,7 +14,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'librlvae_b200.so')
+# RLVAE_B200_LIB: another build of the same ABI (A/B timing of kernel variants on one box; never a fallback)
+LIB_PATH = os.environ.get('RLVAE_B200_LIB') or os.path.join(_HERE, 'lib', 'librlvae_b200.so')
 
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
 GRAD_MODULAR, GRAD_EXACT = 0, 1

@@ -129,8 +129,8 @@ __global__ void centroid_mean_kernel(const float* __restrict__ c, int K, float* 
 // bias_h[k] = -||c~_k||^2 log2(e)/T^2 (padding: -1e30); stats[5] accumulates sum ||c~||^2, [6] max |c~|.
 __global__ void pack_c16h_kernel(const float* __restrict__ c, const float* __restrict__ shift, int K, int Kpad,
                                  float scale, float inv_T2_log2e, __half* __restrict__ out,
-                                 float* __restrict__ bias_h, __half* __restrict__ cth_hi,
-                                 __half* __restrict__ cth_lo) {
+                                 float* __restrict__ bias_h, float* __restrict__ ctc_hi,
+                                 float* __restrict__ ctc_lo) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   float nrm = 0.f;
@@ -141,8 +141,9 @@ __global__ void pack_c16h_kernel(const float* __restrict__ c, const float* __res
     const __half h = __float2half_rn(v);
     out[(int64_t)k * 64 + j] = h;
     out[(int64_t)k * 64 + 16 + j] = __float2half_rn(v - __half2float(h));
-    cth_hi[(int64_t)j * Kpad + k] = h;                                   // the same split, transposed: GEMM3 of the gradient kernel
-    cth_lo[(int64_t)j * Kpad + k] = __float2half_rn(v - __half2float(h));
+    const float thi = tf32_hi(cv);
+    ctc_hi[(int64_t)j * Kpad + k] = thi;
+    ctc_lo[(int64_t)j * Kpad + k] = cv - thi;
   }
   for (int j = 32; j < 64; ++j) out[(int64_t)k * 64 + j] = __float2half_rn(0.f);
   bias_h[k] = (k < K) ? -nrm * inv_T2_log2e : -1.0e30f;
@@ -300,10 +301,9 @@ static void free_tables(rlvae_tables* t) {
   if (t->c16h) cudaFree(t->c16h);
   if (t->cbias_h) cudaFree(t->cbias_h);
   if (t->cshift) cudaFree(t->cshift);
-  if (t->cth_hi) cudaFree(t->cth_hi);
-  if (t->cth_lo) cudaFree(t->cth_lo);
-  t->cth_hi = t->cth_lo = nullptr;
-  t->cbias_h = t->cshift = nullptr;
+  if (t->ctc_hi) cudaFree(t->ctc_hi);
+  if (t->ctc_lo) cudaFree(t->ctc_lo);
+  t->cbias_h = t->cshift = t->ctc_hi = t->ctc_lo = nullptr;
   t->c64h = t->c16h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
   float** ptrs[] = {&t->c, &t->cn, &t->M, &t->cstack, &t->cbias, &t->Mt_hi, &t->Mt_lo,
@@ -487,8 +487,8 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           // c' = 2^ec (c - shift) with max|c'| in [2^13, 2^14)
           if (cudaMalloc(&t->c16h, sizeof(__half) * (size_t)Kpad * 64) != cudaSuccess ||
               cudaMalloc(&t->cbias_h, sizeof(float) * (size_t)Kpad) != cudaSuccess ||
-              cudaMalloc(&t->cth_hi, sizeof(__half) * (size_t)Kpad * 16) != cudaSuccess ||
-              cudaMalloc(&t->cth_lo, sizeof(__half) * (size_t)Kpad * 16) != cudaSuccess ||
+              cudaMalloc(&t->ctc_hi, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
+              cudaMalloc(&t->ctc_lo, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
               cudaMalloc(&t->cshift, sizeof(float) * 20) != cudaSuccess) {
             set_error("tables_create: cudaMalloc (fp16 centroid rows) failed");
             return fail(1);
@@ -511,8 +511,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           int ec = 14 - exc;
           ec = ec > 50 ? 50 : (ec < -50 ? -50 : ec);
           pack_c16h_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, t->cshift, K, Kpad, ldexpf(1.f, ec), inv_T2_log2e,
-                                                              static_cast<__half*>(t->c16h), t->cbias_h,
-                                                              static_cast<__half*>(t->cth_hi), static_cast<__half*>(t->cth_lo));
+                                                              static_cast<__half*>(t->c16h), t->cbias_h, t->ctc_hi, t->ctc_lo);
           OK_OR_FAIL(cudaGetLastError());
           t->c16_unscale = ldexpf(1.f, -ec);
           OK_OR_FAIL(cudaStreamSynchronize(s));
@@ -535,6 +534,8 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
           t->h16_m_unscale = ldexpf(1.f, -e);
           t->tensor_auto = 1;    // the split-fp16 kernels have an exact-distance mode: no restriction on T
           rc = tc_build_h16_descriptors(t);
+          if (rc != 0) return fail(rc);
+          rc = tc_build_ct_centred_descriptors(t);
           if (rc != 0) return fail(rc);
           // Positive semi-definiteness certificate: eigenvalues of every (symmetrised) M_k by the batched
           // Jacobi kernel.  With all M_k >= 0 and lambda > 0, G^{-1}(z) = sum_k w_k M_k + lambda I is

@@ -100,6 +100,7 @@ struct rlvae_tables {
   CUtensorMap tm_mt2_hi, tm_mt2_lo, tm_mts2_hi, tm_mts2_lo;
   CUtensorMap tm_mn2_hi, tm_mn2_lo, tm_mns_hi, tm_mns_lo, tm_mns2_hi, tm_mns2_lo;
   CUtensorMap tm_ct_hi, tm_ct_lo, tm_ct2_hi, tm_ct2_lo;
+  CUtensorMap tm_ct16_hi, tm_ct16_lo, tm_ct8_hi, tm_ct8_lo;   // boxes of 32 centroids x 16 (pair: 8) rows
   // split-fp16 tables (symmetric, d == 16): fp16(2^e M) and fp16 residual, packed-transposed [144, Kpad]
   void* Mh_hi = nullptr;
   void* Mh_lo = nullptr;
@@ -120,9 +121,8 @@ struct rlvae_tables {
   float hybrid_bits = 0.f;     //   weights below 2^-hybrid_bits cannot move G^{-1} by more than 1e-6 lambda
   float* cshift = nullptr;     // [d] mean centroid the fp16 GEMM1 operands are centred on (+ scratch; d == 16 or 64)
   float* cbias_h = nullptr;    // [Kpad] -||c - shift||^2 * log2(e)/T^2 (padding rows: -1e30)
-  void* cth_hi = nullptr;      // [16, Kpad] fp16 hi / lo of 2^ec (c - shift)^T: B operand of the split-fp16 gradient
-  void* cth_lo = nullptr;      //            kernel's final contraction (tm_cth16_*, tm_cth8_*)
-  CUtensorMap tm_cth16_hi, tm_cth16_lo, tm_cth8_hi, tm_cth8_lo;
+  float* ctc_hi = nullptr;     // [16, Kpad] TF32 hi / lo of (c - shift)^T: B operand of the fp16 gradient
+  float* ctc_lo = nullptr;     //            kernel's final contraction (tm_ct16_*, tm_ct8_*)
   float c_absmax = 0.f;
   CUtensorMap tm_c16h;
   void* c64h = nullptr;
@@ -202,6 +202,7 @@ int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* 
 
 // tensor path (rlvae_tc.cu)
 int tc_build_descriptors(rlvae_tables* t);
+int tc_build_ct_centred_descriptors(rlvae_tables* t);
 int launch_inverse_metric_tc(const rlvae_tables* t, const float* z, int64_t n, float* ginv,
                              cudaStream_t s);
 // symmetric tables: packed [N,144] result (lambda already on the packed diagonal)

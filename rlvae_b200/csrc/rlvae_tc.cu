@@ -1306,6 +1306,28 @@ int tc_build_descriptors(rlvae_tables* t) {
   if (int rc = make_map_2d(enc, &t->tm_ct_lo, t->ct_lo, Kpad, 32, 32, 32)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct2_hi, t->ct_hi, Kpad, 32, 32, 16)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct2_lo, t->ct_lo, Kpad, 32, 32, 16)) return rc;
+  // split-fp16 gradient kernel: only the 16 c^T rows (N = 16), pair: 8 rows per CTA
+  if (int rc = make_map_2d(enc, &t->tm_ct16_hi, t->ct_hi, Kpad, 32, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct16_lo, t->ct_lo, Kpad, 32, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_hi, t->ct_hi, Kpad, 32, 32, 8)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_lo, t->ct_lo, Kpad, 32, 32, 8)) return rc;
+  return 0;
+}
+
+// The split-fp16 gradient kernel contracts with the centred centroids (c - shift)^T [16, Kpad]: its
+// epilogue forms sum_k coef_k (c_k - z) as sum_k coef_k c~_k - z~ sum_k coef_k, which would cancel
+// badly for a latent cloud far from the origin if c and z were used as given.
+int tc_build_ct_centred_descriptors(rlvae_tables* t) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  RLVAE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  RLVAE_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+  PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(fn);
+  const uint64_t Kpad = (uint64_t)t->Kpad;
+  if (int rc = make_map_2d(enc, &t->tm_ct16_hi, t->ctc_hi, Kpad, 16, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct16_lo, t->ctc_lo, Kpad, 16, 32, 16)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_hi, t->ctc_hi, Kpad, 16, 32, 8)) return rc;
+  if (int rc = make_map_2d(enc, &t->tm_ct8_lo, t->ctc_lo, Kpad, 16, 32, 8)) return rc;
   return 0;
 }
 

@@ -987,16 +987,11 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 //   T-GEMM  T[128 x 64]  = U'_hi.M'_hi^T + U'_lo.M'_hi^T + U'_hi.M'_lo^T   (kind::f16, K = 144 = 9 steps)
 //           U' = 2^eU Ut (per point, max|U'| in [2^13, 2^14)), Ut_p = U_ij + U_ji (i<j), U_ii: valid for
 //           ANY U; M' = 2^eM M as in the forward kernel.  U' (hi|lo fp16) is resident in TMEM.
-//   exp     u = exp2(..) * t; every exp thread scales ITS 32 values of the block by a power of two so that the
-//           largest becomes ~2^13, splits u' = 2^s u in fp16 (hi | lo) and writes it over S in the forward kernel's P
-//           layout.  (A fixed scale fails: a point far from every centroid has uniformly tiny weights, its u' would
-//           sit in the fp16 subnormals and the RELATIVE accuracy of its gradient row would be lost.)
-//   GEMM3   OUT_g[128 x 16] = u'_hi.Ct_hi + u'_lo.Ct_hi + u'_hi.Ct_lo   (kind::f16, K = 16: 12 MMAs instead of the 24 of
-//           3xTF32; Ct = 2^ec (c - shift)^T split in fp16), ONE accumulator per exp group g and block parity: the
-//           32 centroids a group scaled together are contracted separately, and the group folds 2^-s OUT_g into
-//           its fp32 registers after every block (no accumulation across blocks in TMEM at all).  sum_k u is
-//           accumulated by the exp threads themselves.
-// out = scale 2^-(eU+eM) (2^-ec sum_blocks 2^-s OUT_g - z~ sum_k u).
+//   exp     u = exp2(..) * t, split u_hi | u_lo (fp32 / TF32), written over S | T
+//   GEMM3   OUT[128 x 16] += u_hi.Ct_hi + u_lo.Ct_hi + u_hi.Ct_lo   (3xTF32, N = 16; Ct = c^T; sum_k u is
+//           accumulated by the exp threads themselves: one FADD per element instead of 16 more columns)
+// OUT accumulates in two alternating chunk accumulators (2 super-blocks each) that the exp groups
+// fold into fp32 registers.  out = scale 2^-(eU+eM) (OUT - z sum_k u).
 // TMEM: [0,72) U'_hi, [72,144) U'_lo, [144,400) two (S|u_hi 64, T|u_lo 64) buffers, [400,464) OUT x 2,
 //       [464,496) z_hi | z_lo (TF32 split, A operand of GEMM1).
 // ==========================================================================================
@@ -1006,7 +1001,7 @@ constexpr int C_STAGES = 4;
 constexpr int M_STAGES = 2;                          // one stage = hi AND lo tile of a super-block
 constexpr int KSTEPS = 9;                           // 144 packed columns / 16
 constexpr bool COLSPLIT = true;                     // exp groups split every super-block by columns (see the exp loop)
-constexpr uint32_t CT_TILE_BYTES = 16 * 128;        // [16 rows (c^T) x 64 centroids] fp16: one 128-byte swizzle row per latent dim
+constexpr uint32_t CT_TILE_BYTES = 2 * 16 * 128;    // [16 rows (c^T) x 64 centroids] fp32 = 2 atoms of 32 centroids
 constexpr uint32_t M_HALF_BYTES = 3 * BK * 128;     // 3 column atoms (64 fp16) x 64 centroid rows
 constexpr uint32_t M_TILE_BYTES = 2 * M_HALF_BYTES;
 constexpr uint32_t OFF_C = 0;                       // (z lives in TMEM: no A tiles in shared memory)
@@ -1080,9 +1075,11 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
   constexpr uint32_t TILE_BYTES = 3 * ATOM_BYTES;
   constexpr uint32_t ATOM_DESC = ATOM_BYTES >> 4;
   constexpr uint32_t CT_ROWS = PAIR ? 8 : 16;
-  constexpr uint32_t CT_BYTES = CT_ROWS * 128;                      // per hi / lo tile per CTA
+  constexpr uint32_t CT_ATOM_BYTES = CT_ROWS * 128;
+  constexpr uint32_t CT_BYTES = 2 * CT_ATOM_BYTES;                  // per hi / lo tile per CTA
+  constexpr uint32_t CT_ATOM_DESC = CT_ATOM_BYTES >> 4;
   constexpr uint32_t IDESC_T = make_idesc_f16(PAIR ? 256 : 128, BK);
-  constexpr uint32_t IDESC_3 = make_idesc_f16(PAIR ? 256 : 128, 16);   // N = 16: the 16 components of sum_k u c_k
+  constexpr uint32_t IDESC_3 = make_idesc(PAIR ? 256 : 128, 16);   // N = 16: the 16 components of sum_k u c_k
   const int num_chunks = (num_blocks + CHUNK - 1) / CHUNK;
 
   if (warp == 0 && lane == 0) {
@@ -1093,7 +1090,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     for (int s = 0; s < M_STAGES; ++s) { mbar_init(BAR_M_FULL(s), 1); mbar_init(BAR_M_EMPTY(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR_ST_FULL(b), 1); mbar_init(BAR_U_FULL(b), (COLSPLIT ? 8 : 4) * NPAIR);
-      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 8 * NPAIR);   // both exp groups fold every block
+      mbar_init(BAR_CH_FULL(b), 1); mbar_init(BAR_CH_FREE(b), 4 * NPAIR);
     }
     mbar_init(BAR_DONE, 1);
     for (int b = 0; b < 2; ++b) mbar_init(BAR_G3_DONE(b), 1);
@@ -1270,12 +1267,15 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         if (leader) mbar_expect_tx(BAR_CT_FULL(cs), NPAIR * 2 * CT_BYTES);
         const uint32_t dst = base + OFF_CT + cs * 2 * CT_TILE_BYTES;
         const int row = PAIR ? 8 * (int)rank : 0;
-        if (PAIR) {
-          tma_load_2d_pair(dst, &tm_ct_hi, BAR_CT_FULL(cs), j * BK, row);
-          tma_load_2d_pair(dst + CT_TILE_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK, row);
-        } else {
-          tma_load_2d(dst, &tm_ct_hi, BAR_CT_FULL(cs), j * BK, row);
-          tma_load_2d(dst + CT_TILE_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK, row);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (PAIR) {
+            tma_load_2d_pair(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d_pair(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          } else {
+            tma_load_2d(dst + a * CT_ATOM_BYTES, &tm_ct_hi, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+            tma_load_2d(dst + CT_TILE_BYTES + a * CT_ATOM_BYTES, &tm_ct_lo, BAR_CT_FULL(cs), j * BK + 32 * a, row);
+          }
         }
       }
       __syncwarp();
@@ -1360,35 +1360,36 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     // =========================================================== MMA issuer 2 (pair: leader only): GEMM3
     if (leader) {
       const uint64_t ct_desc0 = make_desc_sw128(base + OFF_CT);
+      uint32_t free_phase = 0;     // bit b: parity of the next CH_FREE(b) completion to wait for
       auto issue_g3 = [&](auto Jc, const int j, const uint32_t qodd /* (j / 4) & 1 */) {
         constexpr int J = decltype(Jc)::value;
-        constexpr int cs = J % C_STAGES, sb = J & 1, upar = (J >> 1) & 1;     // upar: parity of j / 2 (uses of buffer / accumulators sb)
-        if (j >= 2) mbar_wait(BAR_CH_FREE(sb), upar ^ 1);                      // both groups have folded block j - 2
+        constexpr int cs = J % C_STAGES, sb = J & 1, cb = (J >> 1) & 1;
+        constexpr int first = (J % CHUNK) == 0;
+        if (first && j >= 2 * CHUNK) {
+          mbar_wait(BAR_CH_FREE(cb), (free_phase >> cb) & 1u);
+          free_phase ^= 1u << cb;
+        }
         mbar_wait(BAR_CT_FULL(cs), qodd);
-        mbar_wait(BAR_U_FULL(sb), upar);
+        mbar_wait(BAR_U_FULL(sb), (J >> 1) & 1);
         tc_fence_after();
-        const uint32_t up = tmem_base + TM_ST + sb * 128;     // k-step kk: u'_hi at (kk>>1)*32 + (kk&1)*8, u'_lo 16 further
-        const uint32_t acc0 = tmem_base + TM_OUT + sb * 32;   // accumulator of exp group g for this block parity: + g * 16
+        const uint32_t u_hi = tmem_base + TM_ST + sb * 128;
+        const uint32_t u_lo = u_hi + 64;
+        const uint32_t acc = tmem_base + TM_OUT + cb * 32;
         const uint64_t ch = ct_desc0 + ((cs * 2 * CT_TILE_BYTES) >> 4);
         const uint64_t cl = ch + (CT_TILE_BYTES >> 4);
         if (elect_one()) {
-#define MMA_G3(d, a, b, acc) do { if (PAIR) mma_ts_f16_pair(d, a, b, IDESC_3, acc); else mma_ts_f16(d, a, b, IDESC_3, acc); } while (0)
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {                       // the 32 centroids of exp group g: k-steps 2g, 2g + 1
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, !(first && kk == 0));
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-              MMA_G3(acc0 + g * 16, up + g * 32 + r * 8, ch + 2 * (2 * g + r), r);
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_lo + 8 * kk, ch + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-              MMA_G3(acc0 + g * 16, up + g * 32 + 16 + r * 8, ch + 2 * (2 * g + r), 1);
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-              MMA_G3(acc0 + g * 16, up + g * 32 + r * 8, cl + 2 * (2 * g + r), 1);
-          }
-#undef MMA_G3
+          for (int kk = 0; kk < 8; ++kk)
+            MMA_TS(acc, u_hi + 8 * kk, cl + (kk >> 2) * CT_ATOM_DESC + 2 * (kk & 3), IDESC_3, 1);
           COMMIT(BAR_CT_EMPTY(cs));
           COMMIT(BAR_G3_DONE(sb));
-          COMMIT(BAR_CH_FULL(sb));
+          if ((J % CHUNK) == CHUNK - 1 || j == num_blocks - 1) COMMIT(BAR_CH_FULL(cb));
         }
         __syncwarp();
       };
@@ -1409,23 +1410,19 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float tot[17];                       // this group's share of OUT (chunks of parity grp) and of sum_k u
 #pragma unroll
     for (int e = 0; e < 17; ++e) tot[e] = 0.f;
-    // fold block jb: this group's accumulator of parity jb & 1, un-scaled by the block's 2^-s
-    auto fold_block = [&](int jb, float unscale, bool signal) {
-      mbar_wait(BAR_CH_FULL(jb & 1), (jb >> 1) & 1);
-      tc_fence_after();
+    auto fold_chunk = [&](int c, bool signal) {
       uint32_t a[16];
-      TMEM_LD16(tmem_base + lane_addr + TM_OUT + (jb & 1) * 32 + grp * 16, a);
+      TMEM_LD16(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) tot[i] = fmaf(__uint_as_float(a[i]), unscale, tot[i]);
+      for (int i = 0; i < 16; ++i) tot[i] += __uint_as_float(a[i]);
       if (signal) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(jb & 1)); else mbar_arrive(BAR_CH_FREE(jb & 1)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_CH_FREE(c & 1)); else mbar_arrive(BAR_CH_FREE(c & 1)); }
       }
     };
-    float unsc_prev = 0.f;               // 2^-s of the previous block (folded one block late: its GEMM3 runs meanwhile)
-    static_assert(COLSPLIT, "one scale per (thread, block): each group must own a fixed half of every block");
+    int next_chunk = grp;                // chunks c with (c & 1) == grp belong to this group
     long long pe_wait = 0, pe_work = 0, pe_fold = 0;
     (void)pe_wait; (void)pe_work; (void)pe_fold;
     // COLSPLIT: both groups work on EVERY super-block, 32 centroids each, instead of alternating whole
@@ -1440,11 +1437,10 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tc_fence_after();
       PROF_ADD(pe_wait);
       float su_blk = 0.f;                // sum of u over this super-block (two-level fp32 summation)
-      float umax = 0.f, unsc_cur = 1.f;
 #pragma unroll
       for (int rr = 0; rr < (COLSPLIT ? 1 : 2); ++rr) {
         const int rnd = COLSPLIT ? grp : rr;
-        uint32_t sv[32], tv[32], ph[16], pl[16];
+        uint32_t sv[32], tv[32];
         if (!EXACT) TMEM_LD32(st + rnd * 32, sv);
         TMEM_LD32(st + 64 + rnd * 32, tv);
         const float4* bias4 = reinterpret_cast<const float4*>(gbase + OFF_BIAS + cs * BIAS_BYTES) + rnd * 8;
@@ -1471,8 +1467,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
           for (int i = 0; i < 32; ++i) {
             const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
             su_blk += uv;
-            umax = fmaxf(umax, fabsf(uv));
-            tv[i] = __float_as_uint(uv);
+            const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
+            sv[i] = uh;
+            tv[i] = __float_as_uint(uv - __uint_as_float(uh));
           }
         } else {
 #pragma unroll
@@ -1486,25 +1483,14 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                                     : ex2_approx(fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb));
               const float uv = w * __uint_as_float(tv[i]);
               su_blk += uv;
-              umax = fmaxf(umax, fabsf(uv));
-              tv[i] = __float_as_uint(uv);
+              const uint32_t uh = __float_as_uint(uv) & 0xFFFFE000u;
+              sv[i] = uh;
+              tv[i] = __float_as_uint(uv - __uint_as_float(uh));
             }
           }
         }
-        // this thread's 32 values of the block, scaled so that the largest lands in [2^13, 2^14), split in fp16
-        int es = 0;
-        if (umax > 0.f && umax < 3.0e38f) {
-          const int ex = (int)((__float_as_uint(umax) >> 23) & 0xffu) - 126;     // umax = f 2^ex, f in [0.5, 1)
-          es = 14 - ex;
-          es = es > 100 ? 100 : (es < -100 ? -100 : es);
-        }
-        const float usc_blk = __uint_as_float((uint32_t)(es + 127) << 23);
-        unsc_cur = __uint_as_float((uint32_t)(127 - es) << 23);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          split_pair(__uint_as_float(tv[2 * i]) * usc_blk, __uint_as_float(tv[2 * i + 1]) * usc_blk, ph[i], pl[i]);
-        TMEM_ST16(st + rnd * 32, ph);              // u'_hi | u'_lo over S (the T half of the buffer is dead now)
-        TMEM_ST16(st + rnd * 32 + 16, pl);
+        TMEM_ST32(st + rnd * 32, sv);
+        TMEM_ST32(st + 64 + rnd * 32, tv);
       }
       tot[16] += su_blk;
       tmem_wait_st();
@@ -1515,8 +1501,12 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
         mbar_arrive(BAR_C_EMPTY(cs));
       }
       PROF_ADD(pe_work);
-      if (j > 0) fold_block(j - 1, unsc_prev, j + 1 < num_blocks);      // block j + 1 re-uses these accumulators
-      unsc_prev = unsc_cur;
+      while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
+        mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
+        tc_fence_after();
+        fold_chunk(next_chunk, true);
+        next_chunk += 2;
+      }
       PROF_ADD(pe_fold);
     }
 #ifdef RLVAE_TC_PROFILE
@@ -1524,8 +1514,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       printf("[g16 prof] exp group A per own super-block: wait S|T %lld  work %lld  fold %lld\n",
              pe_wait / (num_blocks / 2), pe_work / (num_blocks / 2), pe_fold / (num_blocks / 2));
 #endif
-    if (num_blocks > 0) fold_block(num_blocks - 1, unsc_prev, false);
     mbar_wait(BAR_DONE, 0);
+    tc_fence_after();
+    while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
     // ---------------------------------------------------------- combine the two groups
     asm volatile("bar.sync 1, 256;" ::: "memory");
     float* red = reinterpret_cast<float*>(gbase + OFF_M);
@@ -1542,7 +1533,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float ge = tot[e] + red[prow * RED_LD + e];
-          o[e] = (ge * c_unscale - (zrow[e] - __ldg(cshift + e)) * su) * (u_unscale * scale);   // Ct holds 2^ec (c - shift)
+          o[e] = (ge - (zrow[e] - __ldg(cshift + e)) * su) * u_unscale * scale;   // Ct holds c - shift
         }
         float4* dst = reinterpret_cast<float4*>(out + r * 16);
 #pragma unroll
@@ -1897,11 +1888,6 @@ int tc_build_h16_descriptors(rlvae_tables* t) {
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh_lo, t->Mnh_lo, Kpad, tc::BK)) return rc;
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh2_hi, t->Mnh_hi, Kpad, tc::BK / 2)) return rc;
   if (int rc = make_map_h_atoms(enc, &t->tm_mnh2_lo, t->Mnh_lo, Kpad, tc::BK / 2)) return rc;
-  // (c - shift)^T split fp16 [16, Kpad]: one box = 64 centroids (128 B) x 16 (pair: 8) rows
-  if (int rc = make_map_h(enc, &t->tm_cth16_hi, t->cth_hi, Kpad, 16, tc::BK, 16)) return rc;
-  if (int rc = make_map_h(enc, &t->tm_cth16_lo, t->cth_lo, Kpad, 16, tc::BK, 16)) return rc;
-  if (int rc = make_map_h(enc, &t->tm_cth8_hi, t->cth_hi, Kpad, 16, tc::BK, 8)) return rc;
-  if (int rc = make_map_h(enc, &t->tm_cth8_lo, t->cth_lo, Kpad, 16, tc::BK, 8)) return rc;
   return 0;
 }
 
@@ -2069,11 +2055,11 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   const float cu = t->c16_unscale;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_cth8_hi,
-                                     t->tm_cth8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
+                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_cth16_hi,
-                                     t->tm_cth16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
+                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   }
   return 0;
 }

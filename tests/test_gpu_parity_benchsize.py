@@ -298,10 +298,11 @@ def test_d64_tensor_gradient_kernel_general_u_and_tile_tails():
 
 @pytest.mark.parametrize('d,K', [(16, 300), (64, 300)])
 def test_gradient_rows_of_far_points_keep_relative_accuracy(d, K):
-    """The gradient kernels form u = w t and contract it on kind::f16.  A point far from every centroid has
-    uniformly tiny weights (down to e^-36 here), so a fixed fp16 scale would push its u into the subnormals
-    and lose the RELATIVE accuracy of its row (caught by golden scaled_T07 during development); u is scaled per
-    (point, block) instead.  Rows at increasing distance, arbitrary U, against the oracle formula."""
+    """The gradient kernels form u = w t and contract it on the tensor core (d = 16: 3xTF32, fp32 exponent range;
+    d = 64: kind::f16).  A point far from every centroid has uniformly tiny weights (down to e^-36 here): with a
+    fixed fp16 scale its u would sit in the subnormals and the RELATIVE accuracy of its row would be lost, so
+    the d = 64 kernel scales u per (point, block) by a power of two.  Rows at increasing distance, arbitrary U,
+    against the oracle formula."""
     from rlvae_b200 import _capi
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
     sm = make_synthetic_metric(K, d, seed=13)
