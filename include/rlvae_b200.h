@@ -117,11 +117,19 @@ int rlvae_metric_grad_ws(const rlvae_tables_t* t, const float* z, const float* u
 
 /* ---- variant C (pythae): (1/T^2) G^T sum_k w_k M_k^T (c_k - z) -------------------------------
  * ref: src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187.
- * g [N,d,d] (the metric at z) -> out [N,d].  CUDA-core path.  `work` must hold
- * rlvae_metric_grad_pythae_workspace(n, d) bytes.                                             */
+ * g [N,d,d] (the metric at z) -> out [N,d].  `path` as everywhere: symmetric d == 16 tables run on the tensor
+ * cores (packed G^{-1} from the forward kernel, sum_k w_k M_k c_k from the gradient kernel's unit-weight mode),
+ * anything else on the CUDA-core kernels.  `work` must hold rlvae_metric_grad_pythae_workspace(n, d) bytes. */
 int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d);   /* bytes */
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
-                             float* out, void* work, void* stream);
+                             float* out, void* work, int path, void* stream);
+
+/* The same gradient together with log|det G^{-1}(z)| and its sign (the log_pi of ref :150-158 is
+ * log(sqrt(sign * exp(logabsdet)) + 1e-10)) in one call -- what one leapfrog step of RHVAESampler.hmc_sampling
+ * (ref :98-148) consumes.  grad [N,d]; logabsdet / sign [N] or NULL.  `work`: rlvae_pythae_eval_workspace(n, d). */
+int64_t rlvae_pythae_eval_workspace(int64_t n, int d);          /* bytes */
+int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* grad, float* logabsdet,
+                      float* sign, void* work, int path, void* stream);
 
 /* ---- fused metric evaluation -----------------------------------------------------------------
  * z -> any subset of { ginv [N,d,d], g [N,d,d], logdet_g [N] (= log|det G|, ref

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+from typing import Optional
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 import torch
@@ -41,7 +42,9 @@ _SIGNATURES = [
     ('rlvae_metric_grad_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_metric_grad_ws', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_grad_pythae_workspace', c_int64, [c_int64, c_int]),
-    ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    ('rlvae_metric_grad_pythae', c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    ('rlvae_pythae_eval_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_pythae_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_metric_eval_workspace', c_int64, [c_int64, c_int]),
     ('rlvae_metric_eval', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ('rlvae_sym_eigvalsh', c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
@@ -232,7 +235,7 @@ def metric_grad(tab: Tables, z: torch.Tensor, u: torch.Tensor, scale: float, pat
     return out
 
 
-def metric_grad_pythae(tab: Tables, z: torch.Tensor, g: torch.Tensor):
+def metric_grad_pythae(tab: Tables, z: torch.Tensor, g: torch.Tensor, path: int = PATH_AUTO):
     z = _req_z(tab, z)
     g = _req(g, 'g')
     if tuple(g.shape) != (z.shape[0], tab.d, tab.d) or g.device != z.device:
@@ -242,8 +245,24 @@ def metric_grad_pythae(tab: Tables, z: torch.Tensor, g: torch.Tensor):
     work = torch.empty(max(need, 1), device=z.device, dtype=torch.uint8)
     with torch.cuda.device(z.device):
         _check(lib().rlvae_metric_grad_pythae(tab.handle, _ptr(z), _ptr(g), z.shape[0], _ptr(out), _ptr(work),
-                                              _stream(z)), 'rlvae_metric_grad_pythae')
+                                              path, _stream(z)), 'rlvae_metric_grad_pythae')
     return out
+
+
+def pythae_eval(tab: Tables, z: torch.Tensor, path: int = PATH_AUTO, work: Optional[torch.Tensor] = None):
+    """-> (grad [N,d], logabsdet [N], sign [N]): variant-C gradient, log|det G^{-1}(z)| and its sign."""
+    z = _req_z(tab, z)
+    n = z.shape[0]
+    grad = torch.empty_like(z)
+    lad = torch.empty(n, device=z.device, dtype=torch.float32)
+    sgn = torch.empty(n, device=z.device, dtype=torch.float32)
+    need = int(lib().rlvae_pythae_eval_workspace(n, tab.d))
+    if work is None or work.numel() < need or work.device != z.device or work.dtype != torch.uint8:
+        work = torch.empty(max(need, 1), device=z.device, dtype=torch.uint8)
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_pythae_eval(tab.handle, _ptr(z), n, _ptr(grad), _ptr(lad), _ptr(sgn), _ptr(work), path,
+                                       _stream(z)), 'rlvae_pythae_eval')
+    return grad, lad, sgn
 
 
 def metric_eval(tab: Tables, z: torch.Tensor, want_ginv=True, want_g=False, want_logdet=True,

@@ -177,7 +177,9 @@ __global__ void centred_stats_kernel(const float* __restrict__ c, const float* _
   if (isfinite(amax)) atomicMax(reinterpret_cast<int*>(&out2[1]), __float_as_int(amax));
 }
 
-// split-fp16 natural tables [Kpad, 192] (136 packed columns + zeros) for the gradient kernel
+// split-fp16 natural tables [Kpad, 192] (136 packed columns, column 136 = 1, then zeros) for the gradient kernel.
+// The constant column is multiplied by U'_136, which is 0 for every real U (the kernel zero-fills p >= 136) and 1
+// in the kernel's unit-weight mode, where it makes t_k = <U', M'_k> = 1 exactly (pythae variant, sum_k w_k b_k).
 __global__ void pack_sym_nat_h_kernel(const float* __restrict__ M, int Kpad, float scale, __half* __restrict__ hi_n,
                                       __half* __restrict__ lo_n) {
   const int64_t total = (int64_t)Kpad * 192;
@@ -190,11 +192,71 @@ __global__ void pack_sym_nat_h_kernel(const float* __restrict__ M, int Kpad, flo
       while (p >= base + (16 - i)) { base += 16 - i; ++i; }
       const int j = i + (p - base);
       v = scale * 0.5f * (M[(int64_t)k * 256 + i * 16 + j] + M[(int64_t)k * 256 + j * 16 + i]);
+    } else if (p == 136) {
+      v = 1.f;
     }
     const __half h = __float2half_rn(v);
     hi_n[idx] = h;
     lo_n[idx] = __float2half_rn(v - __half2float(h));
   }
+}
+
+// pythae variant on the tensor path (d == 16, symmetric tables): b_k = sym(M_k) (c_k - shift), TF32 hi / lo,
+// transposed [16, Kpad] like ctc_hi / ctc_lo (ref pythae rhvae_sampler.py:160-187: sum_k w_k M_k (c_k - z)
+// = sum_k w_k b_k - (G^{-1} - lambda I)(z - shift))
+__global__ void pack_pythae_bt_kernel(const float* __restrict__ c, const float* __restrict__ M,
+                                      const float* __restrict__ shift, int K, int Kpad, float* __restrict__ bt_hi,
+                                      float* __restrict__ bt_lo) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  float cc[16];
+  for (int j = 0; j < 16; ++j) cc[j] = (k < K) ? c[(int64_t)k * 16 + j] - shift[j] : 0.f;
+  for (int i = 0; i < 16; ++i) {
+    float b = 0.f;
+    if (k < K)
+      for (int j = 0; j < 16; ++j)
+        b = fmaf(0.5f * (M[(int64_t)k * 256 + i * 16 + j] + M[(int64_t)k * 256 + j * 16 + i]), cc[j], b);
+    const float hi = tf32_hi(b);
+    bt_hi[(int64_t)i * Kpad + k] = hi;
+    bt_lo[(int64_t)i * Kpad + k] = b - hi;
+  }
+}
+
+// one half-warp per point: lane i forms v_i = B_i - sum_e S_ei zt_e (S = G^{-1} - lambda I: off-diagonal entries from
+// the packed G^{-1}, the diagonal from the kernel's lambda-free copy), lane j then contracts
+// out_j = (1/T^2) sum_i G_ij v_i
+__global__ void pythae_finish_sym_kernel(const float* __restrict__ z, const float* __restrict__ a_packed,
+                                         const float* __restrict__ s_diag /* [N,16] diagonal without lambda */,
+                                         const float* __restrict__ b, const float* __restrict__ g, int g_is_packed,
+                                         const float* __restrict__ shift, int64_t n, float inv_T2,
+                                         float* __restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = gid >> 4;
+  const int i = (int)(gid & 15);
+  const bool live = p < n;
+  auto pidx = [](int r, int cidx) {        // packed index of (min, max)
+    const int lo = r < cidx ? r : cidx, hi = r < cidx ? cidx : r;
+    return lo * 16 - (lo * (lo - 1)) / 2 + (hi - lo);
+  };
+  float v = 0.f;
+  if (live) {
+    const float* ap = a_packed + p * kSymCols;
+    v = b[p * 16 + i];
+    for (int e = 0; e < 16; ++e) {
+      const float zt = z[p * 16 + e] - shift[e];
+      const float m = (e == i) ? s_diag[p * 16 + i] : ap[pidx(e, i)];     // (G^{-1} - lambda I)_ei, lambda never added
+      v = fmaf(-m, zt, v);
+    }
+  }
+  float o = 0.f;
+  for (int q = 0; q < 16; ++q) {
+    const float vq = __shfl_sync(0xffffffffu, v, q, 16);
+    if (live) {
+      const float gq = g_is_packed ? g[p * kSymCols + pidx(q, i)] : g[p * 256 + q * 16 + i];   // G^T v: G[q][i] v_q
+      o = fmaf(gq, vq, o);
+    }
+  }
+  if (live) out[p * 16 + i] = o * inv_T2;
 }
 
 // split-fp16 packed-transposed tables [144, Kpad]: hi = fp16(scale * M), lo = fp16(scale * M - hi)
@@ -303,6 +365,9 @@ static void free_tables(rlvae_tables* t) {
   if (t->cshift) cudaFree(t->cshift);
   if (t->ctc_hi) cudaFree(t->ctc_hi);
   if (t->ctc_lo) cudaFree(t->ctc_lo);
+  if (t->bt_hi) cudaFree(t->bt_hi);
+  if (t->bt_lo) cudaFree(t->bt_lo);
+  t->bt_hi = t->bt_lo = nullptr;
   t->cbias_h = t->cshift = t->ctc_hi = t->ctc_lo = nullptr;
   t->c64h = t->c16h = nullptr;
   t->Mh_hi = t->Mh_lo = t->Mnh_hi = t->Mnh_lo = nullptr;
@@ -514,6 +579,13 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
                                                               static_cast<__half*>(t->c16h), t->cbias_h, t->ctc_hi, t->ctc_lo);
           OK_OR_FAIL(cudaGetLastError());
           t->c16_unscale = ldexpf(1.f, -ec);
+          if (cudaMalloc(&t->bt_hi, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess ||
+              cudaMalloc(&t->bt_lo, sizeof(float) * (size_t)Kpad * 16) != cudaSuccess) {
+            set_error("tables_create: cudaMalloc (pythae table) failed");
+            return fail(1);
+          }
+          pack_pythae_bt_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(t->c, t->M, t->cshift, K, Kpad, t->bt_hi, t->bt_lo);
+          OK_OR_FAIL(cudaGetLastError());
           OK_OR_FAIL(cudaStreamSynchronize(s));
           {   // the gate of the expanded form now looks at the centred norms
             const float r2c = h_cs[16] / (float)K;
@@ -620,13 +692,15 @@ static bool use_h16(const rlvae_tables* t) {
 // a_full (optional): the expanded [N,16,16] G^{-1} as well (same kernel on the split-fp16 path).
 static int sym_forward(const rlvae_tables* t, const float* z, int64_t n, float* a_packed, float* g_packed,
                        float* lad, float lad_scale, float* sgn, float* diag, int* fail_ws, cudaStream_t s,
-                       float* a_full = nullptr, float* g_full = nullptr, int a_packed_wanted = 1) {
+                       float* a_full = nullptr, float* g_full = nullptr, int a_packed_wanted = 1,
+                       float* s_diag = nullptr /* split-fp16 path only: diagonal of sum_k w_k M_k without lambda */) {
   if (use_h16(t)) {
     // a pivoting fallback can only write the packed G: expand it afterwards for the (rare) failures by
     // keeping g_packed alongside g_full
     return launch_inverse_metric_h16(t, z, n, a_packed, g_packed, lad, lad_scale, sgn, diag, fail_ws, s, a_full,
-                                     g_full, a_packed_wanted);
+                                     g_full, a_packed_wanted, s_diag);
   }
+  RLVAE_REQUIRE(s_diag == nullptr, "the lambda-free diagonal is an output of the split-fp16 kernel only");
   RLVAE_REQUIRE(a_packed != nullptr, "symmetric 3xTF32 path needs the packed buffer");
   if (int rc = launch_inverse_metric_tc_sym(t, z, n, a_packed, s)) return rc;
   if (a_full != nullptr) { if (int rc = launch_unpack_sym16(a_packed, n, a_full, s)) return rc; }
@@ -737,14 +811,88 @@ int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d) {
   return (int64_t)sizeof(float) * n * (d * d + d);
 }
 
+static bool pythae_tensor_available(const rlvae_tables* t) {
+  return t->d == 16 && t->symmetric && t->tensor_capable && use_h16(t) && t->Mnh_hi != nullptr && t->bt_hi != nullptr;
+}
+
+// variant C on the tensor path: out = (1/T^2) G^T (B - (A - lambda I)(z - shift)), A packed [N,144] G^{-1},
+// B [N,16] = sum_k w_k b_k, G expanded [N,16,16] (g_is_packed == 0) or packed [N,144]
+static int launch_pythae_finish_sym(const rlvae_tables* t, const float* z, const float* a_packed, const float* s_diag,
+                                    const float* b, const float* g, int g_is_packed, int64_t n, float* out,
+                                    cudaStream_t s) {
+  if (n == 0) return 0;
+  const int64_t threads = n * 16;
+  pythae_finish_sym_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(z, a_packed, s_diag, b, g, g_is_packed,
+                                                                             t->cshift, n, 1.f / t->T2, out);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
-                             float* out, void* work, void* stream) {
+                             float* out, void* work, int path, void* stream) {
   RLVAE_REQUIRE(t != nullptr, "metric_grad_pythae: tables handle is NULL");
   RLVAE_REQUIRE(n >= 0, "metric_grad_pythae: negative batch");
   if (n == 0) return 0;
   RLVAE_REQUIRE(z != nullptr && g != nullptr && out != nullptr, "metric_grad_pythae: NULL pointer");
   RLVAE_REQUIRE(work != nullptr, "metric_grad_pythae: workspace required");
-  return launch_metric_grad_pythae(t, z, g, n, out, static_cast<float*>(work), static_cast<cudaStream_t>(stream));
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* w = static_cast<float*>(work);
+  if (use_tc && pythae_tensor_available(t) && aligned16(z) && aligned16(w)) {
+    // tensor path: packed G^{-1} from the forward kernel, sum_k w_k b_k from the gradient kernel's unit-weight
+    // mode, then the two 16 x 16 products per point.  Workspace: A [n,144] | B [n,16] | lambda-free diagonal [n,16]
+    float* a_packed = w;
+    float* b = w + n * kSymCols;
+    float* sd = b + n * 16;
+    if (int rc = sym_forward(t, z, n, a_packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr, s, nullptr, nullptr, 1, sd))
+      return rc;
+    if (int rc = launch_metric_grad_h16(t, z, nullptr, n, 1.f, b, s, 2)) return rc;
+    return launch_pythae_finish_sym(t, z, a_packed, sd, b, g, 0, n, out, s);
+  }
+  // (non-symmetric or d != 16 tables: the contraction itself has no tensor kernel)
+  return launch_metric_grad_pythae(t, z, g, n, out, w, s);
+}
+
+// variant C in one call (what one leapfrog step of the pythae sampler needs): log|det G^{-1}|, its sign and
+// (1/T^2) G^T sum_k w_k M_k^T (c_k - z).  Tensor path: forward kernel (packed G^{-1}, packed G, log det) +
+// unit-weight gradient kernel + finish = 3 launches; otherwise the direct kernels.
+int64_t rlvae_pythae_eval_workspace(int64_t n, int d) {
+  return (int64_t)sizeof(float) * (n * (3 * (int64_t)d * d + d) + 4);
+}
+
+int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* grad, float* logabsdet,
+                      float* sign, void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "pythae_eval: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0, "pythae_eval: negative batch");
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(z != nullptr && grad != nullptr, "pythae_eval: NULL pointer");
+  RLVAE_REQUIRE(work != nullptr, "pythae_eval: workspace required");
+  bool use_tc;
+  if (int rc = resolve_path(t, path, &use_tc)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* w = static_cast<float*>(work);
+  const int d = t->d;
+  if (use_tc && pythae_tensor_available(t) && aligned16(z) && aligned16(w) && aligned16(grad)) {
+    float* a_packed = w;
+    float* g_packed = w + n * kSymCols;
+    float* b = g_packed + n * kSymCols;
+    float* sd = b + n * 16;
+    int* fail_ws = reinterpret_cast<int*>(sd + n * 16);
+    if (int rc = sym_forward(t, z, n, a_packed, g_packed, logabsdet, 1.f, sign, nullptr, fail_ws, s, nullptr, nullptr, 1, sd))
+      return rc;
+    if (int rc = launch_metric_grad_h16(t, z, nullptr, n, 1.f, b, s, 2)) return rc;
+    return launch_pythae_finish_sym(t, z, a_packed, sd, b, g_packed, 1, n, grad, s);
+  }
+  const int64_t mat = n * d * d;
+  float* ginv = w;
+  float* g = w + mat;
+  float* scratch = w + 2 * mat;
+  if (int rc = inverse_metric_full(t, z, n, ginv, path, s, nullptr)) return rc;
+  if (int rc = launch_batched_inverse(ginv, n, d, g, logabsdet, sign, nullptr, 0, s)) return rc;
+  return launch_metric_grad_pythae(t, z, g, n, grad, scratch, s);
 }
 
 int64_t rlvae_metric_eval_workspace(int64_t n, int d) {

@@ -259,7 +259,7 @@ int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float
 // The augmented table is built lazily by the caller (tables struct owns it).
 // ------------------------------------------------------------------------------------------
 __global__ void pythae_finish_kernel(const float* __restrict__ aug, const float* __restrict__ z,
-                                     const float* __restrict__ g, int64_t n, int d, float lambda,
+                                     const float* __restrict__ g, int64_t n, int d,
                                      float T2, float* __restrict__ out) {
   // one thread per (point, output dim)
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,14 +270,12 @@ __global__ void pythae_finish_kernel(const float* __restrict__ aug, const float*
   const float* row = aug + p * ncols;
   const float* zp = z + p * d;
   const float* gp = g + p * d * d;
-  // v_i = B_i - sum_e (Ginv[e][i] - lambda*delta) z_e ; out_j = (1/T2) sum_i G[i][j] v_i
+  // v_i = B_i - sum_e S[e][i] z_e, S = sum_k w_k M_k (accumulated WITHOUT lambda: fl(S_ii + lambda) - lambda
+  // would lose S_ii wherever the weights are small) ; out_j = (1/T2) sum_i G[i][j] v_i
   float o = 0.f;
   for (int i = 0; i < d; ++i) {
     float v = row[d * d + i];
-    for (int e = 0; e < d; ++e) {
-      float m = row[e * d + i] - ((e == i) ? lambda : 0.f);
-      v = fmaf(-m, zp[e], v);
-    }
+    for (int e = 0; e < d; ++e) v = fmaf(-row[e * d + i], zp[e], v);
     o = fmaf(gp[i * d + j], v, o);
   }
   out[gid] = o / T2;
@@ -315,11 +313,10 @@ int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float
   dim3 grid((unsigned)((n + DM_BM - 1) / DM_BM), (unsigned)((ncols + DM_BN - 1) / DM_BN));
   RLVAE_OPT_IN_SMEM(inverse_metric_direct_kernel, (int)dm_smem_bytes(kMaxLatentDim));
   inverse_metric_direct_kernel<<<grid, DM_THREADS, dm_smem_bytes(d), s>>>(
-      z, t->c, t->pythae_aug, n, t->K, d, ncols, t->T2, t->lambda, scratch);
+      z, t->c, t->pythae_aug, n, t->K, d, ncols, t->T2, 0.f /* no lambda: see pythae_finish_kernel */, scratch);
   RLVAE_LAUNCH_OK();
   const int64_t total = n * d;
-  pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(scratch, z, g, n, d,
-                                                                       t->lambda, t->T2, out);
+  pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(scratch, z, g, n, d, t->T2, out);
   RLVAE_LAUNCH_OK();
   return 0;
 }

@@ -136,6 +136,11 @@ struct rlvae_tables {
   CUtensorMap tm_ct64_hi, tm_ct64_lo, tm_ct64_2_hi, tm_ct64_2_lo;
   // pythae-variant gradient (A8): [K, d*d+d] = [M_k | M_k^T c_k], built on first use (derived cache)
   mutable float* pythae_aug = nullptr;
+  // ... on the tensor path (d == 16, symmetric): b_k = sym(M_k) (c_k - shift), TF32 hi / lo, transposed [16, Kpad] --
+  // the B operand of the gradient kernel's final contraction in its unit-weight mode (sum_k w_k b_k)
+  float* bt_hi = nullptr;
+  float* bt_lo = nullptr;
+  CUtensorMap tm_bt16_hi, tm_bt16_lo, tm_bt8_hi, tm_bt8_lo;
 };
 
 namespace rlvae {
@@ -177,6 +182,8 @@ int64_t metric_grad_h64_scratch_floats(int64_t n);
 int launch_metric_grad_h64(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
                            float* scratch, cudaStream_t s);
 int launch_nearest2_tc(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist, cudaStream_t s);
+// u_packed: 0 full [N,256] U, 1 packed symmetric [N,144] U, 2 unit mode (u unused): out = scale * sum_k w_k b_k
+// with the pythae table b (tm_bt*) in place of the centroids
 int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale,
                            float* out, cudaStream_t s, int u_packed);
 // a_full (optional): the expanded [N,16,16] G^{-1}, written by the same kernel
@@ -185,7 +192,7 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
                               int* fail_ws, cudaStream_t s, float* a_full = nullptr, float* g_full = nullptr,
-                              int a_packed_wanted = 1);
+                              int a_packed_wanted = 1, float* s_diag = nullptr);
 // single-launch HMC trajectory (variant-A drift): n_iters MCMC iterations, chain state on chip.
 // scales_dev [n_iters * n_lf] (device) or, for n_iters == 1 and n_lf <= 64, h_scales (host).
 int h16_hmc_available(const rlvae_tables* t);

@@ -1328,6 +1328,12 @@ int tc_build_ct_centred_descriptors(rlvae_tables* t) {
   if (int rc = make_map_2d(enc, &t->tm_ct16_lo, t->ctc_lo, Kpad, 16, 32, 16)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct8_hi, t->ctc_hi, Kpad, 16, 32, 8)) return rc;
   if (int rc = make_map_2d(enc, &t->tm_ct8_lo, t->ctc_lo, Kpad, 16, 32, 8)) return rc;
+  if (t->bt_hi != nullptr && t->bt_lo != nullptr) {     // pythae table: same shape, same boxes
+    if (int rc = make_map_2d(enc, &t->tm_bt16_hi, t->bt_hi, Kpad, 16, 32, 16)) return rc;
+    if (int rc = make_map_2d(enc, &t->tm_bt16_lo, t->bt_lo, Kpad, 16, 32, 16)) return rc;
+    if (int rc = make_map_2d(enc, &t->tm_bt8_hi, t->bt_hi, Kpad, 16, 32, 8)) return rc;
+    if (int rc = make_map_2d(enc, &t->tm_bt8_lo, t->bt_lo, Kpad, 16, 32, 8)) return rc;
+  }
   return 0;
 }
 

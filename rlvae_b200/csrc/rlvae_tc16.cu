@@ -176,6 +176,8 @@ struct FusedOut {
   float* diag_g;       // [N,16] or NULL
   int* fail_ws;        // counter + list (needed when any of g_packed / logabsdet / sign / diag_g is set)
   float lad_scale;
+  float* s_diag;       // [N,16] diagonal of sum_k w_k M_k WITHOUT lambda, or NULL (pythae variant: (G^{-1} - lambda I) z
+                       // must not be formed from fl(S_ii + lambda) - lambda when S_ii << lambda)
 };
 
 // HMC mode of the forward kernel: ONE launch runs n_iters MCMC iterations of
@@ -704,6 +706,14 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     const long long pf1 = clock64();     // (printed after the epilogue: a printf here would be timed as epilogue)
 #endif
     // ---------------------------------------------------------- epilogue (all TMA / MMA work of this evaluation is complete)
+    if (!HMC && fo.s_diag != nullptr && live) {
+      float4* dst = reinterpret_cast<float4*>(fo.s_diag + (row0 + prow) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_float4(total[sym_index(4 * q, 4 * q)] * out_scale, total[sym_index(4 * q + 1, 4 * q + 1)] * out_scale,
+                             total[sym_index(4 * q + 2, 4 * q + 2)] * out_scale,
+                             total[sym_index(4 * q + 3, 4 * q + 3)] * out_scale);
+    }
 #pragma unroll
     for (int pc = 0; pc < NCOLS; ++pc) {
       bool diag = false;
@@ -1177,10 +1187,13 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     }
     // ---- U' = 2^eU Ut, split into fp16 hi | lo, resident in TMEM as the A operand of the T GEMM.
     // group 0 converts packed columns [0,64), group 1 [64,144); both scan the whole row for the scale.
+    // unit mode (u_packed == 2, pythae variant): U' = e_136 against the table's constant pad column (= 1), so
+    // t_k = 1 and the kernel returns scale * sum_k w_k b_k for the table behind tm_ct_* (no "- z sum_k u" term)
+    const bool unit = u_packed == 2;
     const int row_len = u_packed ? SYM_COLS : NCOL;
     const float* urow = u + r * row_len;
     float m = 0.f;
-    if (r < n) {
+    if (r < n && !unit) {
       const float4* u4 = reinterpret_cast<const float4*>(urow);
       const int nq = u_packed ? 34 : 64;
       for (int q = 0; q < nq; ++q) {
@@ -1205,7 +1218,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       int cj = ri + (p - rb);
       auto next = [&]() -> float {      // Ut at packed index p, then advance
         float v = 0.f;
-        if (r < n && p < 136) {
+        if (unit) {
+          v = (p == 136) ? 1.f : 0.f;
+        } else if (r < n && p < 136) {
           if (u_packed) {
             v = __ldg(urow + p);
             if (cj != ri) v += v;
@@ -1543,7 +1558,8 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float ge = tot[e] + red[prow * RED_LD + e];
-          o[e] = (ge - (zrow[e] - __ldg(cshift + e)) * su) * u_unscale * scale;   // Ct holds c - shift
+          const float zt = (u_packed == 2) ? 0.f : zrow[e] - __ldg(cshift + e);   // Ct holds c - shift
+          o[e] = (ge - zt * su) * u_unscale * scale;
         }
         float4* dst = reinterpret_cast<float4*>(out + r * 16);
 #pragma unroll
@@ -1975,7 +1991,8 @@ int h16_mode(const rlvae_tables* t) {
 // which needs packed G^{-1}: a_packed must be given whenever a factor output is requested).
 int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, float* a_packed,
                               float* g_packed, float* logabsdet, float lad_scale, float* sign, float* diag_g,
-                              int* fail_ws, cudaStream_t s, float* a_full, float* g_full, int a_packed_wanted) {
+                              int* fail_ws, cudaStream_t s, float* a_full, float* g_full, int a_packed_wanted,
+                              float* s_diag) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 16 && t->tensor_capable && t->symmetric && t->Mh_hi != nullptr,
                 "split-fp16 tensor path needs latent_dim == 16 and symmetric tables");
@@ -1990,7 +2007,9 @@ int launch_inverse_metric_h16(const rlvae_tables* t, const float* z, int64_t n, 
   // certified tables: nobody reads the packed G^{-1} unless the caller asked for it (the fallback list is
   // recomputed from the tables in the rare rounding-level failure), so it is not stored
   const bool skip_packed = !a_packed_wanted && t->psd_certified;
-  tc::FusedOut fo{a_full, skip_packed ? nullptr : a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale};
+  RLVAE_REQUIRE(s_diag == nullptr || (reinterpret_cast<uintptr_t>(s_diag) & 15) == 0, "s_diag must be 16-byte aligned");
+  tc::FusedOut fo{a_full, skip_packed ? nullptr : a_packed, g_packed, g_full, logabsdet, sign, diag_g, fail_ws, lad_scale,
+                  s_diag};
   int rc;
   const int mode = h16_mode(t);
   prof_mark(0, s);
@@ -2062,14 +2081,17 @@ static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int
   const float* cbias = EXACT ? t->cmask : t->cbias_h;
   const float* cnat = t->c;
   const int nb = t->Kpad / tc::BK;
-  const float sc = scale * t->h16_m_unscale;          // 2^-eM of the table scaling
+  const bool unit = u_packed == 2;                     // t_k = 1 exactly: nothing to un-scale
+  const float sc = unit ? scale : scale * t->h16_m_unscale;          // 2^-eM of the table scaling
   const float cu = t->c16_unscale;
   if (PAIR) {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo, t->tm_ct8_hi,
-                                     t->tm_ct8_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh2_hi, t->tm_mnh2_lo,
+                                     unit ? t->tm_bt8_hi : t->tm_ct8_hi, unit ? t->tm_bt8_lo : t->tm_ct8_lo, z, u, cbias,
+                                     cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   } else {
-    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo, t->tm_ct16_hi,
-                                     t->tm_ct16_lo, z, u, cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
+    RLVAE_LAUNCH_EX(cudaLaunchKernelEx(&cfg, kern, t->tm_c16h, t->tm_mnh_hi, t->tm_mnh_lo,
+                                     unit ? t->tm_bt16_hi : t->tm_ct16_hi, unit ? t->tm_bt16_lo : t->tm_ct16_lo, z, u,
+                                     cbias, cnat, n, nb, alpha, sc, cu, t->cshift, -t->hybrid_bits, out, u_packed));
   }
   return 0;
 }
@@ -2083,6 +2105,7 @@ int launch_metric_grad_h16(const rlvae_tables* t, const float* z, const float* u
                 "split-fp16 gradient path needs latent_dim == 16 and symmetric tables");
   RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tensor path needs 16-byte aligned z, u and out");
+  RLVAE_REQUIRE(u_packed != 2 || t->bt_hi != nullptr, "unit-weight mode needs the pythae table");
   const int mode = h16_mode(t);
   if (mode == 1)
     return g16_use_pairs() ? launch_g16<true, true>(t, z, u, n, scale, out, s, u_packed)

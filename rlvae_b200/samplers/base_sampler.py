@@ -72,7 +72,9 @@ def tables_for(model) -> _capi.Tables:
 
 def kernel_path_for(model) -> int:
     mt = getattr(model, 'metric_tensor', None)
-    return mt._path() if isinstance(mt, MetricTensor) else _capi.PATH_AUTO
+    if isinstance(mt, MetricTensor):
+        return mt._path()
+    return int(getattr(model, '_rlvae_kernel_path', _capi.PATH_AUTO))     # wrappers forward their model's choice
 
 
 class BaseRiemannianSampler(ABC):

@@ -11,10 +11,11 @@ iterations, everything runs under ``no_grad``.  The wrapper class of the referen
 (``src/models/samplers/rhvae_sampler.py``) builds a full pythae ``RHVAE`` model around the
 encoder/decoder; that model object is out of scope, the sampling arithmetic is here.
 
-Per leapfrog step: ONE metric evaluation (fused forward kernel -> G) and one gradient contraction -- the
-reference evaluates the same gradient at the end of step k and at the start of step k + 1 (:110-131, z
-does not move in between), here it is carried over; the momentum / position updates are element-wise
-torch ops on the device.
+Per leapfrog step: ONE call of ``rlvae_pythae_eval`` (forward kernel -> packed G^{-1}, packed G, log det;
+the gradient kernel's unit-weight mode -> sum_k w_k M_k c_k; one finish kernel) -- the reference evaluates the
+same gradient at the end of step k and at the start of step k + 1 (:110-131, z does not move in between) and
+log_pi again at the accepted / rejected position (:108, :134); here the values are carried over (selected per
+chain by the accept mask).  The momentum / position updates are element-wise torch ops on the device.
 
 ``OfficialRHVAESampler`` mirrors the reference's wrapper class (ref src/models/samplers/rhvae_sampler.py:
 13-255) -- same name, methods and quirks (temperature hard-coded to 0.1 at :62/:80, prior batches of at
@@ -40,25 +41,20 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
         self.beta_zero_sqrt = float(beta_zero) ** 0.5
 
     # ------------------------------------------------------------------ the two callables (ref :150-187)
-    def _eval(self, z):
-        mt = getattr(self.model, 'metric_tensor', None)
+    def _logp_grad(self, z):
+        """(log_pi [N], grad log_pi [N,d]) at z from one fused evaluation."""
         tab = tables_for(self.model)
-        ev = _capi.metric_eval(tab, z, want_ginv=False, want_g=True, want_logdet=True, want_grad=False,
-                               path=kernel_path_for(self.model))
-        return tab, ev
+        grad, lad, sgn = _capi.pythae_eval(tab, z, path=kernel_path_for(self.model))
+        det = sgn * torch.exp(lad)
+        return torch.log(torch.sqrt(det) + 1e-10), grad
 
     def log_sqrt_det_G_inv(self, z: torch.Tensor) -> torch.Tensor:
         """log(sqrt(det G^{-1}(z)) + 1e-10)  (ref :157-158; a negative determinant gives NaN there too)."""
-        tab = tables_for(self.model)
-        ginv = _capi.inverse_metric(tab, z.contiguous().float(), kernel_path_for(self.model))
-        _, lad, sgn, _ = _capi.batched_inverse(ginv, want_inv=False, want_logabsdet=True, want_sign=True)
-        det = sgn * torch.exp(lad)
-        return torch.log(torch.sqrt(det) + 1e-10)
+        return self._logp_grad(z.contiguous().float())[0]
 
     def grad_log_sqrt_det_G_inv(self, z: torch.Tensor) -> torch.Tensor:
         """[N,d]  (the reference returns [N,d,1] and reshapes, ref :118-120)."""
-        tab, ev = self._eval(z.contiguous().float())
-        return _capi.metric_grad_pythae(tab, z.contiguous().float(), ev['g'])
+        return self._logp_grad(z.contiguous().float())[1]
 
     @staticmethod
     def tempering(k: int, K: int, beta_zero_sqrt: float) -> float:
@@ -79,28 +75,39 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
             beta_old = b0 if state is None else state['beta_old']
             z = z0
             eps = self.eps_lf
+            cached = None if state is None else state.get('logp_grad')
+            lp0, g0 = cached if cached is not None else self._logp_grad(z)
             for i in range(gammas.shape[0]):
                 rho = gammas[i] / b0
-                h0 = -self.log_sqrt_det_G_inv(z) + 0.5 * torch.norm(rho, dim=1) ** 2
-                g = -self.grad_log_sqrt_det_G_inv(z)
+                h0 = -lp0 + 0.5 * torch.norm(rho, dim=1) ** 2
+                lp, g = lp0, g0
                 for k in range(self.n_lf):
-                    rho_ = rho - (eps / 2) * g
+                    rho_ = rho + (eps / 2) * g                    # rho - (eps/2) * (-grad log_pi)
                     z = (z + eps * rho_).contiguous()
-                    g = -self.grad_log_sqrt_det_G_inv(z)          # also the first gradient of step k + 1
-                    rho__ = rho_ - (eps / 2) * g
+                    lp, g = self._logp_grad(z)                    # also the first gradient of step k + 1
+                    rho__ = rho_ + (eps / 2) * g
                     beta_new = self.tempering(k + 1, self.n_lf, b0)
                     rho = (beta_old / beta_new) * rho__
                     beta_old = beta_new
-                h = -self.log_sqrt_det_G_inv(z) + 0.5 * torch.norm(rho, dim=1) ** 2
+                h = -lp + 0.5 * torch.norm(rho, dim=1) ** 2
                 alpha = torch.exp(-h) / torch.exp(-h0)
-                moves = (accs[i] < alpha).to(torch.int).reshape(n, 1)
+                mv = accs[i] < alpha
+                moves = mv.to(torch.int).reshape(n, 1)
                 z = (z * moves + (1 - moves) * z0).contiguous()
                 z0 = z
+                lp0 = torch.where(mv, lp, lp0)                    # log_pi / gradient at the position kept
+                g0 = torch.where(mv.reshape(n, 1), g, g0)
+                # (a rejected proposal that overflowed leaves 0 * inf = NaN in z, exactly as in the reference,
+                # which then evaluates log_pi at NaN)
+                lost = ~torch.isfinite(z).all(dim=1)
+                lp0 = torch.where(lost, torch.full_like(lp0, float('nan')), lp0)
+                g0 = torch.where(lost.reshape(n, 1), torch.full_like(g0, float('nan')), g0)
                 if record is not None:
                     for name, val in (('H0', h0), ('H', h), ('alpha', alpha), ('moves', moves.reshape(-1)),
                                       ('z', z.clone())):
                         record.setdefault(name, []).append(val)
             if state is not None:
+                state['logp_grad'] = (lp0, g0)
                 state['beta_old'] = beta_old
             return z
 
@@ -155,6 +162,7 @@ class _FixedTemperatureModel:
     M_tens = property(lambda self: self._model.M_tens)
     lbd = property(lambda self: self._model.lbd)
     device = property(lambda self: self._model.centroids_tens.device)
+    _rlvae_kernel_path = property(lambda self: kernel_path_for(self._model))
 
     def parameters(self):
         return self._model.parameters()

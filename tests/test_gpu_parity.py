@@ -115,8 +115,15 @@ def test_hmc_callables_against_reference(case):
         # variant C (pythae) against the oracle restatement
         from rlvae_b200 import _capi
         mt = s.model.metric_tensor
-        gp = _capi.metric_grad_pythae(mt._tables(dev()), z, mt.compute_metric(z))
-        assert rel_fro(gp.cpu(), O.grad_pythae(g['z'], *t)) < 2e-4
+        gp = _capi.metric_grad_pythae(mt._tables(dev()), z, mt.compute_metric(z), path=mt._path())
+        ref_c = O.grad_pythae(g['z'], *t).reshape(gp.shape)
+        assert rel_fro(gp.cpu(), ref_c) < 2e-4
+        # ... and fused with log|det G^{-1}| (rlvae_pythae_eval: what one leapfrog step of the pythae loop consumes)
+        ge, lad, sgn = _capi.pythae_eval(mt._tables(dev()), z, path=mt._path())
+        assert rel_fro(ge.cpu(), ref_c) < 2e-4
+        lad_ref = torch.linalg.slogdet(O.inverse_metric(g['z'], *t).double())
+        close_ld(lad, lad_ref[1], 2e-5)
+        assert torch.equal(sgn.cpu().double(), lad_ref[0])
 
 
 def test_config1_shape_against_oracle():
