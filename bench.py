@@ -560,6 +560,39 @@ def run_ours(args):
     except Exception as e:
         flow = {'error': str(e)[:200]}
 
+    # ---- pythae variant: log_pi + grad log_pi of RHVAESampler at one position per point
+    # (rlvae_pythae_eval: forward kernel + unit-weight gradient kernel + finish), and the reference-sized use:
+    # OfficialRHVAESampler.sample_prior(32) = 100 MCMC x 15 leapfrog steps at the hard-coded T = 0.1
+    pythae = None
+    try:
+        from rlvae_b200 import MetricModel, OfficialRHVAESampler, _capi
+        tab = mt._tables(dev)
+        with torch.no_grad():
+            _capi.pythae_eval(tab, z)
+            barrier()
+            ts = []
+            for _ in range(3):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+                pg, pl, ps = _capi.pythae_eval(tab, z)
+                e1.record(); e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            tp = max_over_ranks(sum(ts) / len(ts))
+            osamp = OfficialRHVAESampler(MetricModel(mt))
+            osamp.sample_prior(32); torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            zo = osamp.sample_prior(32); torch.cuda.synchronize(dev)
+            t_off = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        pythae = {'what': 'log|det G^-1| + (1/T^2) G^T sum_k w_k M_k^T (c_k - z), 2^20 points per GPU', 'ms': tp,
+                  'value': world * n / (tp * 1e-3), 'unit': UNIT, 'kernel_launches': 3,
+                  'finite': bool(torch.isfinite(pg).all().item() and torch.isfinite(pl).all().item()),
+                  'official_sample_prior_32': {'mcmc_steps': 100, 'n_lf': 15, 'temperature': 0.1, 'wall_ms': t_off,
+                                               'finite': bool(torch.isfinite(zo).all().item())}}
+        del pg, pl, ps, zo, osamp
+    except Exception as e:
+        pythae = {'error': str(e)[:200]}
+
     # ---- large-metric stress (BASELINE.json configs[4]): d = 64, K = 50,000, N = 2^20 points per GPU
     # (8M over 8 GPUs), tables generated on the device from a fixed seed, evaluated in 2^17-point chunks
     d64 = None
@@ -606,7 +639,7 @@ def run_ours(args):
                                  'writes >1.6 GB of outputs'},
                 'roofline': roof, 'roofline_forward_kernel': roof_fwd, 'cpu_baseline': cpu, 'e2e': e2e,
                 'e2e_with_ginv': e2e_ginv, 'hmc': hmc, 'hmc_strong': hmc_strong, 'small_T': small_t, 'd64': d64,
-                'flow': flow, 'shard_check': shard_check, 'clocks': clocks,
+                'flow': flow, 'pythae': pythae, 'shard_check': shard_check, 'clocks': clocks,
                 'gpu_launches': launches_timed,
                 'tflops_fp32_equiv': value * flops_per_eval(True) / 1e12}
         print(json.dumps(line))

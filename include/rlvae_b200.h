@@ -131,6 +131,17 @@ int64_t rlvae_pythae_eval_workspace(int64_t n, int d);          /* bytes */
 int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float* grad, float* logabsdet,
                       float* sign, void* work, int path, void* stream);
 
+/* The whole loop of RHVAESampler.hmc_sampling (ref pythae rhvae_sampler.py:98-148; what
+ * OfficialRHVAESampler.sample_prior runs, ref src/models/samplers/rhvae_sampler.py:169-191): n_iters MCMC iterations of
+ * n_lf leapfrog steps, one rlvae_pythae_eval per step, momentum / position / accept arithmetic in two small kernels.
+ * z [N,d] in: start, out: final positions; gammas [n_iters,N,d] (:107), accs [n_iters,N] (:141);
+ * h_scales (HOST) [n_iters*n_lf] = beta_old/beta_new per leapfrog step (the tempering state is never reset, :104);
+ * h0 / h1 / alpha / moves [n_iters,N] and z_trace [n_iters,N,d]: optional records.  alpha is not clamped (:139). */
+int64_t rlvae_pythae_hmc_workspace(int64_t n, int d);           /* bytes */
+int rlvae_pythae_hmc_run(const rlvae_tables_t* t, float* z, const float* gammas, const float* accs, int64_t n,
+                         int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* h_scales, float* h0,
+                         float* h1, float* alpha, float* moves, float* z_trace, void* work, int path, void* stream);
+
 /* ---- fused metric evaluation -----------------------------------------------------------------
  * z -> any subset of { ginv [N,d,d], g [N,d,d], logdet_g [N] (= log|det G|, ref
  * metric_tensor.py:162-182), grad_logdet_g [N,d] (= grad_z log det G) }.  NULL outputs are

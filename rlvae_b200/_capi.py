@@ -59,6 +59,10 @@ _SIGNATURES = [
     ('rlvae_hmc_run', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float,
                               POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_void_p]),
+    ('rlvae_pythae_hmc_workspace', c_int64, [c_int64, c_int]),
+    ('rlvae_pythae_hmc_run', c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float,
+                                     POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_void_p]),
     ('rlvae_hmc_refine', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int, c_void_p]),
     ('rlvae_nearest2', c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ('rlvae_chol_apply', c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -406,6 +410,37 @@ def hmc_run(tab: Tables, z: torch.Tensor, gammas: torch.Tensor, accs: torch.Tens
                                    c_float(beta_zero_sqrt), sc, grad_mode, _ptr(stats[0]), _ptr(stats[1]),
                                    _ptr(stats[2]), _ptr(stats[3]), _ptr(trace), _ptr(work), path, _stream(z)),
                'rlvae_hmc_run')
+    return dict(work=work, stats=tuple(stats) if want_stats else None, trace=trace)
+
+
+def pythae_hmc_run(tab: Tables, z: torch.Tensor, gammas: torch.Tensor, accs: torch.Tensor, n_lf: int, eps_lf: float,
+                   beta_zero_sqrt: float, scales, path: int = PATH_AUTO, want_stats: bool = False,
+                   want_trace: bool = False, work: torch.Tensor | None = None):
+    """pythae's RHVAESampler.hmc_sampling loop in place on ``z``: gammas.shape[0] MCMC iterations x n_lf leapfrog
+    steps.  scales: n_iters * n_lf floats (host).  Returns dict(work, stats=(h0,h,alpha,moves) [I,n], trace [I,n,d])."""
+    if not (z.is_cuda and z.is_contiguous() and z.dtype == torch.float32):
+        raise RuntimeError('pythae_hmc_run: z must be a contiguous fp32 CUDA tensor (updated in place)')
+    _req_z(tab, z)
+    n, d = z.shape
+    gammas = _req(gammas, 'gammas')
+    accs = _req(accs, 'accs')
+    iters = int(gammas.shape[0])
+    if tuple(gammas.shape) != (iters, n, d) or tuple(accs.shape) != (iters, n) or gammas.device != z.device \
+            or accs.device != z.device:
+        raise ValueError(f'pythae_hmc_run: gammas must be [I, {n}, {d}] and accs [I, {n}] on {z.device}')
+    if len(scales) != iters * n_lf:
+        raise ValueError(f'pythae_hmc_run: need {iters * n_lf} tempering scales, got {len(scales)}')
+    need = int(lib().rlvae_pythae_hmc_workspace(n, d))
+    if work is None or work.numel() < need or work.device != z.device:
+        work = torch.empty(max(need, 1), device=z.device, dtype=torch.uint8)
+    sc = (c_float * max(len(scales), 1))(*[float(x) for x in scales])
+    stats = [torch.empty((iters, n), device=z.device) for _ in range(4)] if want_stats else [None] * 4
+    trace = torch.empty((iters, n, d), device=z.device) if want_trace else None
+    with torch.cuda.device(z.device):
+        _check(lib().rlvae_pythae_hmc_run(tab.handle, _ptr(z), _ptr(gammas), _ptr(accs), n, iters, n_lf,
+                                          c_float(eps_lf), c_float(beta_zero_sqrt), sc, _ptr(stats[0]), _ptr(stats[1]),
+                                          _ptr(stats[2]), _ptr(stats[3]), _ptr(trace), _ptr(work), path, _stream(z)),
+               'rlvae_pythae_hmc_run')
     return dict(work=work, stats=tuple(stats) if want_stats else None, trace=trace)
 
 

@@ -1146,6 +1146,53 @@ int rlvae_hmc_run(const rlvae_tables_t* t, float* z, const float* gammas, const 
   return 0;
 }
 
+// ---- pythae RHVAESampler.hmc_sampling: the whole loop behind OfficialRHVAESampler.sample_prior ---------------
+static int64_t round4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+int64_t rlvae_pythae_hmc_workspace(int64_t n, int d) {
+  // evaluation workspace | grad, rho_half, z0, g0 [n,d] | lad, sgn, lp0, h0 [n]
+  return rlvae_pythae_eval_workspace(n, d) + 16 + (int64_t)sizeof(float) * (4 * round4(n * d) + 4 * round4(n));
+}
+
+int rlvae_pythae_hmc_run(const rlvae_tables_t* t, float* z, const float* gammas, const float* accs, int64_t n,
+                         int n_iters, int n_lf, float eps_lf, float beta_zero_sqrt, const float* h_scales, float* h0,
+                         float* h1, float* alpha, float* moves, float* z_trace, void* work, int path, void* stream) {
+  RLVAE_REQUIRE(t != nullptr, "pythae_hmc_run: tables handle is NULL (metric not loaded)");
+  RLVAE_REQUIRE(n >= 0 && n_lf >= 1 && n_iters >= 0, "pythae_hmc_run: need n >= 0, n_lf >= 1, n_iters >= 0");
+  if (n == 0 || n_iters == 0) return 0;
+  RLVAE_REQUIRE(z && gammas && accs && h_scales && work, "pythae_hmc_run: NULL pointer");
+  const int d = t->d;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* wb = static_cast<char*>(work);
+  void* eval_ws = wb;
+  float* f = reinterpret_cast<float*>(wb + ((rlvae_pythae_eval_workspace(n, d) + 15) & ~(int64_t)15));
+  float* grad = f;                     f += round4(n * d);
+  float* rho = f;                      f += round4(n * d);
+  float* z0 = f;                       f += round4(n * d);
+  float* g0 = f;                       f += round4(n * d);
+  float* lad = f;                      f += round4(n);
+  float* sgn = f;                      f += round4(n);
+  float* lp0 = f;                      f += round4(n);
+  float* h0buf = f;
+  if (int rc = rlvae_pythae_eval(t, z, n, grad, lad, sgn, eval_ws, path, stream)) return rc;     // (log_pi, grad) at the start
+  for (int i = 0; i < n_iters; ++i) {
+    const int64_t on = (int64_t)i * n;
+    if (int rc = launch_pythae_hmc_begin(n, d, eps_lf, beta_zero_sqrt, i == 0, lad, sgn, grad, gammas + on * d, z, z0,
+                                         rho, g0, lp0, h0buf, h0 ? h0 + on : nullptr, s))
+      return rc;
+    for (int k = 0; k < n_lf; ++k) {
+      if (int rc = rlvae_pythae_eval(t, z, n, grad, lad, sgn, eval_ws, path, stream)) return rc;
+      const int last = (k == n_lf - 1);
+      if (int rc = launch_pythae_hmc_step(n, d, eps_lf, h_scales[(int64_t)i * n_lf + k], last, lad, sgn, grad, accs + on,
+                                          z, z0, rho, g0, lp0, h0buf, h1 ? h1 + on : nullptr,
+                                          alpha ? alpha + on : nullptr, moves ? moves + on : nullptr,
+                                          z_trace ? z_trace + on * d : nullptr, s))
+        return rc;
+    }
+  }
+  return 0;
+}
+
 int rlvae_hmc_refine(const rlvae_tables_t* t, float* z, int64_t n, int n_steps, float step_size,
                      void* work, int path, void* stream) {
   RLVAE_REQUIRE(t != nullptr, "hmc_refine: tables handle is NULL (metric not loaded)");

@@ -126,6 +126,120 @@ __global__ void axpy_grad_modular_kernel(float* __restrict__ z, const float* __r
   z[e] = z[e] + step * (-((1.f - lambda * diag_g[e]) / T2));
 }
 
+// ---- pythae RHVAESampler.hmc_sampling (ref src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:98-148) ----
+// log_pi = log(sqrt(det G^{-1}) + 1e-10) (:157-158), alpha = exp(-H)/exp(-H0) un-clamped (:139), the proposal mixed as
+// z*m + (1-m)*z0 (:143).  Every product / sum below is rounded separately (the reference is eager tensor arithmetic).
+__device__ __forceinline__ float pythae_log_pi(float lad, float sgn) {
+  return logf(sqrtf(sgn * expf(lad)) + 1e-10f);
+}
+
+// start of one MCMC iteration for every chain: rho = gamma / b0 (:107), H0 (:108), first half-step + position update
+// of leapfrog step 0 (:113-116).  from_eval: (lp0, g0) are first taken from a fresh evaluation (lad, sgn, grad) at z.
+__global__ void pythae_hmc_begin_kernel(int64_t n, int d, float eps, float b0, int from_eval, const float* __restrict__ lad,
+                                        const float* __restrict__ sgn, const float* __restrict__ grad,
+                                        const float* __restrict__ gamma, float* __restrict__ z, float* __restrict__ z0,
+                                        float* __restrict__ rho_half, float* __restrict__ g0, float* __restrict__ lp0,
+                                        float* __restrict__ h0, float* __restrict__ rec_h0) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float half_eps = eps / 2.f;
+  if (from_eval) lp0[p] = pythae_log_pi(lad[p], sgn[p]);
+  float ss = 0.f;
+  for (int j = 0; j < d; ++j) {
+    const int64_t e = p * d + j;
+    if (from_eval) g0[e] = grad[e];
+    const float rho = gamma[e] / b0;
+    ss = __fadd_rn(ss, __fmul_rn(rho, rho));
+    const float rh = __fadd_rn(rho, __fmul_rn(half_eps, g0[e]));      // rho - (eps/2) * (-grad log_pi)
+    rho_half[e] = rh;
+    const float zc = z[e];
+    z0[e] = zc;
+    z[e] = __fadd_rn(zc, __fmul_rn(eps, rh));
+  }
+  const float nrm = sqrtf(ss);
+  const float H0 = __fadd_rn(-lp0[p], __fmul_rn(0.5f, __fmul_rn(nrm, nrm)));
+  h0[p] = H0;
+  if (rec_h0) rec_h0[p] = H0;
+}
+
+// after the evaluation at the position of leapfrog step k: second half-step, tempering (:121-131); then either the
+// first half of step k + 1 (same gradient) or, on the last step, H, alpha, the accept decision and the bookkeeping of
+// (z0, log_pi, gradient) at the position that is kept (:134-146).
+__global__ void pythae_hmc_step_kernel(int64_t n, int d, float eps, float scale, int last, const float* __restrict__ lad,
+                                       const float* __restrict__ sgn, const float* __restrict__ grad,
+                                       const float* __restrict__ acc, float* __restrict__ z,
+                                       float* __restrict__ z0, float* __restrict__ rho_half, float* __restrict__ g0,
+                                       float* __restrict__ lp0, const float* __restrict__ h0, float* __restrict__ rec_h,
+                                       float* __restrict__ rec_alpha, float* __restrict__ rec_moves,
+                                       float* __restrict__ z_trace) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float half_eps = eps / 2.f;
+  if (!last) {
+    for (int j = 0; j < d; ++j) {
+      const int64_t e = p * d + j;
+      const float g = grad[e];
+      const float rho = __fmul_rn(scale, __fadd_rn(rho_half[e], __fmul_rn(half_eps, g)));
+      const float rh = __fadd_rn(rho, __fmul_rn(half_eps, g));
+      rho_half[e] = rh;
+      z[e] = __fadd_rn(z[e], __fmul_rn(eps, rh));
+    }
+    return;
+  }
+  float ss = 0.f;
+  for (int j = 0; j < d; ++j) {
+    const int64_t e = p * d + j;
+    const float rho = __fmul_rn(scale, __fadd_rn(rho_half[e], __fmul_rn(half_eps, grad[e])));
+    ss = __fadd_rn(ss, __fmul_rn(rho, rho));
+  }
+  const float nrm = sqrtf(ss);
+  const float lp = pythae_log_pi(lad[p], sgn[p]);
+  const float H = __fadd_rn(-lp, __fmul_rn(0.5f, __fmul_rn(nrm, nrm)));
+  const float a = expf(-H) / expf(-h0[p]);
+  const bool mv = acc[p] < a;                      // NaN alpha: stays
+  const float m = mv ? 1.f : 0.f;
+  bool lost = false;
+  for (int j = 0; j < d; ++j) {
+    const int64_t e = p * d + j;
+    const float zn = __fadd_rn(__fmul_rn(z[e], m), __fmul_rn(1.f - m, z0[e]));
+    lost |= !isfinite(zn);
+    z[e] = zn;
+    z0[e] = zn;
+    if (z_trace) z_trace[e] = zn;
+    if (mv) g0[e] = grad[e];
+  }
+  if (mv) lp0[p] = lp;
+  if (lost) {          // 0 * inf left NaN in z (as in the reference, which then evaluates log_pi at NaN)
+    lp0[p] = NAN;
+    for (int j = 0; j < d; ++j) g0[p * d + j] = NAN;
+  }
+  if (rec_h) rec_h[p] = H;
+  if (rec_alpha) rec_alpha[p] = a;
+  if (rec_moves) rec_moves[p] = m;
+}
+
+int launch_pythae_hmc_begin(int64_t n, int d, float eps, float b0, int from_eval, const float* lad, const float* sgn,
+                            const float* grad, const float* gamma, float* z, float* z0, float* rho_half, float* g0,
+                            float* lp0, float* h0, float* rec_h0, cudaStream_t s) {
+  if (n == 0) return 0;
+  pythae_hmc_begin_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, d, eps, b0, from_eval, lad, sgn, grad, gamma, z,
+                                                                      z0, rho_half, g0, lp0, h0, rec_h0);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
+int launch_pythae_hmc_step(int64_t n, int d, float eps, float scale, int last, const float* lad, const float* sgn,
+                           const float* grad, const float* acc, float* z, float* z0, float* rho_half, float* g0,
+                           float* lp0, const float* h0, float* rec_h, float* rec_alpha, float* rec_moves,
+                           float* z_trace, cudaStream_t s) {
+  if (n == 0) return 0;
+  pythae_hmc_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, d, eps, scale, last, lad, sgn, grad, acc, z, z0,
+                                                                     rho_half, g0, lp0, h0, rec_h, rec_alpha, rec_moves,
+                                                                     z_trace);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
 int launch_hmc_begin(const float* z, const float* gamma, const float* diag_g, const float* logabsdet,
                      const float* sign, const float* grad_exact, int64_t n, int d, float b0,
                      float eps, float lambda, float T2, int grad_mode, float* rho_half, float* z_new,

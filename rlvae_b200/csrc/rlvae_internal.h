@@ -202,6 +202,14 @@ int launch_hmc_trajectory_h16(const rlvae_tables* t, float* z, const float* gamm
                               float* z_trace, int* fail_count, cudaStream_t s);
 constexpr int kSymCols = 144;
 constexpr int kSymNatCols = 160;
+// pythae RHVAESampler.hmc_sampling stages (rlvae_hmc.cu)
+int launch_pythae_hmc_begin(int64_t n, int d, float eps, float b0, int from_eval, const float* lad, const float* sgn,
+                            const float* grad, const float* gamma, float* z, float* z0, float* rho_half, float* g0,
+                            float* lp0, float* h0, float* rec_h0, cudaStream_t s);
+int launch_pythae_hmc_step(int64_t n, int d, float eps, float scale, int last, const float* lad, const float* sgn,
+                           const float* grad, const float* acc, float* z, float* z0, float* rho_half, float* g0,
+                           float* lp0, const float* h0, float* rec_h, float* rec_alpha, float* rec_moves,
+                           float* z_trace, cudaStream_t s);
 int launch_chol_apply(const float* a, const float* eps, int64_t n, int d, float jitter, float* out,
                       int32_t* status, cudaStream_t s);
 int launch_nearest2(const rlvae_tables* t, const float* mu, int64_t n, int64_t* idx, float* dist,

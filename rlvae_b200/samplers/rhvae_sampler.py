@@ -67,7 +67,38 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
                                   state: Optional[dict] = None) -> torch.Tensor:
         """The loop with its random draws injected: ``idx0 [n]`` (line 100), ``gammas [steps,n,d]``
         (line 107), ``accs [steps,n]`` (line 141).  ``z_start`` / ``state`` continue a chain whose draws
-        arrive in several slabs (the tempering state is never reset, line 104)."""
+        arrive in several slabs (the tempering state is never reset, line 104).
+
+        One library call (``rlvae_pythae_hmc_run``): per leapfrog step one fused evaluation and one update kernel."""
+        with torch.no_grad():
+            z = (self.model.centroids_tens[idx0] if z_start is None else z_start).float().contiguous().clone()
+            iters = int(gammas.shape[0])
+            b0 = self.beta_zero_sqrt
+            beta_old = b0 if state is None else state['beta_old']
+            scales = []
+            for _ in range(iters):
+                for k in range(self.n_lf):
+                    beta_new = self.tempering(k + 1, self.n_lf, b0)
+                    scales.append(beta_old / beta_new)
+                    beta_old = beta_new
+            res = _capi.pythae_hmc_run(tables_for(self.model), z, gammas.float().contiguous(), accs.float().contiguous(),
+                                       self.n_lf, self.eps_lf, b0, scales, path=kernel_path_for(self.model),
+                                       want_stats=record is not None, want_trace=record is not None)
+            if record is not None:
+                h0, h, alpha, moves = res['stats']
+                for i in range(iters):
+                    for name, val in (('H0', h0[i]), ('H', h[i]), ('alpha', alpha[i]), ('moves', moves[i].to(torch.int)),
+                                      ('z', res['trace'][i])):
+                        record.setdefault(name, []).append(val)
+            if state is not None:
+                state['beta_old'] = beta_old
+            return z
+
+    def hmc_sampling_with_streams_stepwise(self, idx0: Optional[torch.Tensor], gammas: torch.Tensor, accs: torch.Tensor,
+                                           record: Optional[dict] = None, z_start: Optional[torch.Tensor] = None,
+                                           state: Optional[dict] = None) -> torch.Tensor:
+        """The same loop written out with device tensors, one ``rlvae_pythae_eval`` per leapfrog step (the
+        cross-check of the library loop; ~10x the launch overhead at the reference's batch of 32)."""
         with torch.no_grad():
             z0 = (self.model.centroids_tens[idx0] if z_start is None else z_start).float().contiguous()
             n, d = z0.shape

@@ -691,6 +691,14 @@ def test_pythae_variant_hmc_matches_reference_chain(case):
             assert int(flip.sum()) == 0
             close_ld(got['H0'][i], rec['H0'][i], 1e-4)
         torch.testing.assert_close(zf.cpu(), g['z_final'], rtol=2e-4, atol=2e-4)
+        # the library loop (rlvae_pythae_hmc_run) against the same loop written out with device tensors
+        got2 = {}
+        zf2 = s.hmc_sampling_with_streams_stepwise(g['idx0'].to(dev()), g['gamma'].to(dev()), g['acc'].to(dev()),
+                                                   record=got2)
+        for i in range(g['gamma'].shape[0]):
+            assert torch.equal(got['moves'][i].cpu(), got2['moves'][i].cpu())
+            close_ld(got['H'][i], got2['H'][i], 2e-5)
+        torch.testing.assert_close(zf, zf2, rtol=2e-5, atol=2e-5)
         assert s.sample_prior(5).shape == (5, 16)
         assert s.get_sampler_info()['n_lf'] == int(g['n_lf'])
 
