@@ -279,6 +279,15 @@ def test_small_temperature_runs_on_the_tensor_path(mode, monkeypatch):
     assert rel_fro(b['grad_logdet_g'][live].cpu(), a['grad_logdet_g'][live].cpu()) < TOL_LD
     ref = O.chunked(O.inverse_metric, z[3000:3064].cpu(), *t, chunk=32)
     assert rel_fro(b['ginv'][3000:3064].cpu(), ref) < TOL_MAT
+    # variant C (pythae) through the same weight mode: unit-weight pass of the gradient kernel vs the CUDA-core path
+    from rlvae_b200 import _capi
+    pc, lc, sc = _capi.pythae_eval(tab, z, path=_capi.PATH_TENSOR)
+    pd, ld_, sd = _capi.pythae_eval(tab, z, path=_capi.PATH_DIRECT)
+    livep = pd.norm(dim=1) > 1e-3 * pd.norm(dim=1).max()
+    assert livep.sum() > 500
+    assert rel_fro(pc[livep].cpu(), pd[livep].cpu()) < TOL_LD
+    close_ld(lc, ld_)
+    assert torch.equal(sc, sd)
 
 
 def test_reference_metric_file_takes_the_packed_tensor_path():
