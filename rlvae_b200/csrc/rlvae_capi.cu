@@ -890,7 +890,8 @@ int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   float* ginv = w;
   float* g = w + mat;
   float* scratch = w + 2 * mat;
-  if (int rc = inverse_metric_full(t, z, n, ginv, path, s, nullptr)) return rc;
+  // (d = 64 tensor forward: its packed tiles use the slot the augmented-table pass overwrites afterwards)
+  if (int rc = inverse_metric_full(t, z, n, ginv, path, s, scratch)) return rc;
   if (int rc = launch_batched_inverse(ginv, n, d, g, logabsdet, sign, nullptr, 0, s)) return rc;
   return launch_metric_grad_pythae(t, z, g, n, grad, scratch, s);
 }

@@ -568,6 +568,12 @@ def test_latent_dim_64_paths():
         close_ld(ev['logdet_g'], ref_ld)
         assert rel_fro(ev['grad_logdet_g'].cpu()[:64], ref_grad) < TOL_LD, path
         assert rel_fro(mt.compute_inverse_metric(z.to(dev())).cpu(), ref_ginv) < TOL_MAT, path
+        # variant C (pythae) + log|det G^{-1}| in one call at d = 64 (CUDA-core contraction behind either forward)
+        from rlvae_b200 import _capi
+        pg, pl, ps = _capi.pythae_eval(mt._tables(dev()), z[:64].to(dev()).contiguous(), path=mt._path())
+        assert rel_fro(pg.cpu(), O.grad_pythae(z[:64], *t).reshape(64, 64)) < 2e-4, path
+        close_ld(pl, -ref_ld[:64])
+        assert torch.all(ps == 1)
     # ragged batches around the tile sizes on the tensor path
     mt = make_mt(t, 'tensor')
     for n in (1, 127, 129, 257):
