@@ -117,9 +117,11 @@ int rlvae_metric_grad_ws(const rlvae_tables_t* t, const float* z, const float* u
 
 /* ---- variant C (pythae): (1/T^2) G^T sum_k w_k M_k^T (c_k - z) -------------------------------
  * ref: src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187.
- * g [N,d,d] (the metric at z) -> out [N,d].  `path` as everywhere: symmetric d == 16 tables run on the tensor
- * cores (packed G^{-1} from the forward kernel, sum_k w_k M_k c_k from the gradient kernel's unit-weight mode),
- * anything else on the CUDA-core kernels.  `work` must hold rlvae_metric_grad_pythae_workspace(n, d) bytes. */
+ * g [N,d,d] (the metric at z) -> out [N,d].  `path` as everywhere: long batches (> 2048 points) on symmetric
+ * d == 16 tables run as two table contractions on the tensor cores (packed G^{-1} from the forward kernel,
+ * sum_k w_k M_k c_k from the gradient kernel's unit-weight mode) with an error bound per row; flagged rows, short
+ * batches and every other table use the CUDA-core kernel that forms c_k - z per centroid like the reference.
+ * `work` must hold rlvae_metric_grad_pythae_workspace(n, d) bytes. */
 int64_t rlvae_metric_grad_pythae_workspace(int64_t n, int d);   /* bytes */
 int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const float* g, int64_t n,
                              float* out, void* work, int path, void* stream);

@@ -16,7 +16,6 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<long long> g_launch_count{0};
 void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
-void pythae_cache_release(const rlvae_tables* t);
 
 // ---- per-kernel timing of rlvae_metric_eval on the packed tensor path (bench.py's roofline block):
 // CUDA events recorded on the launching stream around the forward launch, the fallback pass and the
@@ -224,11 +223,19 @@ __global__ void pack_pythae_bt_kernel(const float* __restrict__ c, const float* 
 
 // one half-warp per point: lane i forms v_i = B_i - sum_e S_ei zt_e (S = G^{-1} - lambda I: off-diagonal entries from
 // the packed G^{-1}, the diagonal from the kernel's lambda-free copy), lane j then contracts
-// out_j = (1/T^2) sum_i G_ij v_i
+// out_j = (1/T^2) sum_i G_ij v_i.
+// Error bound -> fallback list.  B and S are table contractions accurate to ~2^-22 of THEIR size, while v is a
+// difference of the two; the rounding dv ~ eps (|B| + |S|_F |zt| / 4) is then multiplied by G.  For a rounding
+// vector of random direction |G dv| ~ |G|_F |dv| / 4, so with  err = |G|_F / (4 T^2) * (eps (|B| + |S|_F |zt| / 4)
+// + floor |zt|)  (floor: the fp16 weight floor 2^-39 of the forward kernel times the table's rms Frobenius norm) a
+// point whose err exceeds rtol |out| + atol goes to the list and is recomputed by pythae_exact_kernel, which forms
+// c_k - z per centroid like the reference.  Far from every centroid and at moderate temperatures nothing is listed;
+// next to a centroid at small T / small lambda (cond(G^{-1}) * |c| / |c_k - z| large) everything is.
 __global__ void pythae_finish_sym_kernel(const float* __restrict__ z, const float* __restrict__ a_packed,
                                          const float* __restrict__ s_diag /* [N,16] diagonal without lambda */,
                                          const float* __restrict__ b, const float* __restrict__ g, int g_is_packed,
-                                         const float* __restrict__ shift, int64_t n, float inv_T2,
+                                         const float* __restrict__ shift, int64_t n, float inv_T2, float floor_s,
+                                         int* __restrict__ fail_ws /* [0] count, [1..] rows; NULL: no bound */,
                                          float* __restrict__ out) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p = gid >> 4;
@@ -238,25 +245,51 @@ __global__ void pythae_finish_sym_kernel(const float* __restrict__ z, const floa
     const int lo = r < cidx ? r : cidx, hi = r < cidx ? cidx : r;
     return lo * 16 - (lo * (lo - 1)) / 2 + (hi - lo);
   };
-  float v = 0.f;
+  float v = 0.f, ns = 0.f, zti = 0.f, bi = 0.f;
   if (live) {
     const float* ap = a_packed + p * kSymCols;
-    v = b[p * 16 + i];
+    bi = b[p * 16 + i];
+    v = bi;
+    zti = z[p * 16 + i] - shift[i];
     for (int e = 0; e < 16; ++e) {
       const float zt = z[p * 16 + e] - shift[e];
       const float m = (e == i) ? s_diag[p * 16 + i] : ap[pidx(e, i)];     // (G^{-1} - lambda I)_ei, lambda never added
+      ns = fmaf(m, m, ns);
       v = fmaf(-m, zt, v);
     }
   }
-  float o = 0.f;
+  float o = 0.f, ng = 0.f;
   for (int q = 0; q < 16; ++q) {
     const float vq = __shfl_sync(0xffffffffu, v, q, 16);
     if (live) {
       const float gq = g_is_packed ? g[p * kSymCols + pidx(q, i)] : g[p * 256 + q * 16 + i];   // G^T v: G[q][i] v_q
+      ng = fmaf(gq, gq, ng);
       o = fmaf(gq, vq, o);
     }
   }
-  if (live) out[p * 16 + i] = o * inv_T2;
+  o *= inv_T2;
+  if (live) out[p * 16 + i] = o;
+  if (fail_ws != nullptr) {
+    float nb = bi * bi, nz = zti * zti, no = o * o;
+#pragma unroll
+    for (int sft = 8; sft > 0; sft >>= 1) {
+      ns += __shfl_xor_sync(0xffffffffu, ns, sft, 16);
+      ng += __shfl_xor_sync(0xffffffffu, ng, sft, 16);
+      nb += __shfl_xor_sync(0xffffffffu, nb, sft, 16);
+      nz += __shfl_xor_sync(0xffffffffu, nz, sft, 16);
+      no += __shfl_xor_sync(0xffffffffu, no, sft, 16);
+    }
+    if (live && i == 0) {
+      const float eps = 2.3841858e-7f;                      // 2^-22
+      const float zn = sqrtf(nz);
+      const float dv = eps * (sqrtf(nb) + 0.25f * sqrtf(ns) * zn) + floor_s * zn;
+      const float err = 0.25f * sqrtf(ng) * dv * inv_T2;
+      if (!(err <= 2.0e-5f * sqrtf(no) + 1.0e-6f)) {         // also catches NaN
+        const int slot = atomicAdd(fail_ws, 1);
+        fail_ws[1 + slot] = (int)p;
+      }
+    }
+  }
 }
 
 // split-fp16 packed-transposed tables [144, Kpad]: hi = fp16(scale * M), lo = fp16(scale * M - hi)
@@ -351,7 +384,6 @@ static int negate_copy(const float* x, float* y, int64_t n, cudaStream_t s) {
 }
 
 static void free_tables(rlvae_tables* t) {
-  pythae_cache_release(t);
   if (t->Mh_hi) cudaFree(t->Mh_hi);
   if (t->Mh_lo) cudaFree(t->Mh_lo);
   if (t->Mnh_hi) cudaFree(t->Mnh_hi);
@@ -594,6 +626,7 @@ int rlvae_tables_create(rlvae_tables_t** out, const float* centroids, const floa
             // Hybrid mode: the un-refined weights (each below 2^-bits, relative error relc) move G^{-1} by
             // at most relc * 2^-bits * sum_k ||M_k||_F <= 1e-6 lambda, and G^{-1} >= lambda I.
             const float mf = h_cs[18];
+            t->m_fro_rms = (mf > 0.f && isfinite(mf)) ? mf / sqrtf((float)K) : 0.f;
             if (t->lambda > 0.f && isfinite(t->lambda) && mf > 0.f && isfinite(mf)) {
               const float bits = log2f(relc * mf / (1.0e-6f * t->lambda));
               if (isfinite(bits) && bits < 48.f) {
@@ -816,17 +849,26 @@ static bool pythae_tensor_available(const rlvae_tables* t) {
 }
 
 // variant C on the tensor path: out = (1/T^2) G^T (B - (A - lambda I)(z - shift)), A packed [N,144] G^{-1},
-// B [N,16] = sum_k w_k b_k, G expanded [N,16,16] (g_is_packed == 0) or packed [N,144]
+// B [N,16] = sum_k w_k b_k, G expanded [N,16,16] (g_is_packed == 0) or packed [N,144]; rows whose error bound is too
+// large are appended to fail_ws (count zeroed here) for launch_pythae_exact
 static int launch_pythae_finish_sym(const rlvae_tables* t, const float* z, const float* a_packed, const float* s_diag,
-                                    const float* b, const float* g, int g_is_packed, int64_t n, float* out,
-                                    cudaStream_t s) {
+                                    const float* b, const float* g, int g_is_packed, int64_t n, int* fail_ws,
+                                    float* out, cudaStream_t s) {
   if (n == 0) return 0;
+  if (fail_ws != nullptr) RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
   const int64_t threads = n * 16;
+  const float floor_s = 1.8189894e-12f * t->m_fro_rms;      // 2^-39: absolute floor of the forward kernel's fp16 weights
   pythae_finish_sym_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(z, a_packed, s_diag, b, g, g_is_packed,
-                                                                             t->cshift, n, 1.f / t->T2, out);
+                                                                             t->cshift, n, 1.f / t->T2, floor_s, fail_ws,
+                                                                             out);
   RLVAE_LAUNCH_OK();
   return 0;
 }
+
+// batches up to this size skip the table-contraction form: the per-centroid kernel with the centroids split over
+// several CTAs per point is both faster (a single 128-point tile would walk the centroids serially) and as accurate
+// as the reference
+constexpr int64_t kPythaeSmallBatch = kPythaeSplitBatch;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -841,24 +883,28 @@ int rlvae_metric_grad_pythae(const rlvae_tables_t* t, const float* z, const floa
   if (int rc = resolve_path(t, path, &use_tc)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* w = static_cast<float*>(work);
-  if (use_tc && pythae_tensor_available(t) && aligned16(z) && aligned16(w)) {
+  if (use_tc && n > kPythaeSmallBatch && pythae_tensor_available(t) && aligned16(z) && aligned16(w)) {
     // tensor path: packed G^{-1} from the forward kernel, sum_k w_k b_k from the gradient kernel's unit-weight
-    // mode, then the two 16 x 16 products per point.  Workspace: A [n,144] | B [n,16] | lambda-free diagonal [n,16]
+    // mode, then the two 16 x 16 products per point; the rows its error bound flags are redone per centroid.
+    // Workspace: A [n,144] | B [n,16] | lambda-free diagonal [n,16] | fallback list (1 + n ints)
     float* a_packed = w;
     float* b = w + n * kSymCols;
     float* sd = b + n * 16;
+    int* fail_ws = reinterpret_cast<int*>(sd + n * 16);
     if (int rc = sym_forward(t, z, n, a_packed, nullptr, nullptr, 1.f, nullptr, nullptr, nullptr, s, nullptr, nullptr, 1, sd))
       return rc;
     if (int rc = launch_metric_grad_h16(t, z, nullptr, n, 1.f, b, s, 2)) return rc;
-    return launch_pythae_finish_sym(t, z, a_packed, sd, b, g, 0, n, out, s);
+    if (int rc = launch_pythae_finish_sym(t, z, a_packed, sd, b, g, 0, n, fail_ws, out, s)) return rc;
+    return launch_pythae_exact(t, z, g, 0, fail_ws + 1, fail_ws, n, out, nullptr, s);
   }
-  // (non-symmetric or d != 16 tables: the contraction itself has no tensor kernel)
-  return launch_metric_grad_pythae(t, z, g, n, out, w, s);
+  // (the workspace holds n * (d*d + d) floats >= n * kPythaeMaxSplits * d for every d >= 16; smaller d: no split)
+  return launch_pythae_exact(t, z, g, 0, nullptr, nullptr, n, out, t->d >= kPythaeMaxSplits ? w : nullptr, s);
 }
 
 // variant C in one call (what one leapfrog step of the pythae sampler needs): log|det G^{-1}|, its sign and
-// (1/T^2) G^T sum_k w_k M_k^T (c_k - z).  Tensor path: forward kernel (packed G^{-1}, packed G, log det) +
-// unit-weight gradient kernel + finish = 3 launches; otherwise the direct kernels.
+// (1/T^2) G^T sum_k w_k M_k^T (c_k - z).  Tensor path, long batches: forward kernel (packed G^{-1}, packed G, log det)
+// + unit-weight gradient kernel + finish (error bound) + the per-centroid kernel over the flagged rows; short
+// batches: forward kernel + the per-centroid kernel; other tables: the CUDA-core kernels.
 int64_t rlvae_pythae_eval_workspace(int64_t n, int d) {
   return (int64_t)sizeof(float) * (n * (3 * (int64_t)d * d + d) + 4);
 }
@@ -881,19 +927,24 @@ int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
     float* b = g_packed + n * kSymCols;
     float* sd = b + n * 16;
     int* fail_ws = reinterpret_cast<int*>(sd + n * 16);
-    if (int rc = sym_forward(t, z, n, a_packed, g_packed, logabsdet, 1.f, sign, nullptr, fail_ws, s, nullptr, nullptr, 1, sd))
+    const bool split = n > kPythaeSmallBatch;
+    if (int rc = sym_forward(t, z, n, a_packed, g_packed, logabsdet, 1.f, sign, nullptr, fail_ws, s, nullptr, nullptr, 1,
+                             split ? sd : nullptr))
       return rc;
+    if (!split) return launch_pythae_exact(t, z, g_packed, 1, nullptr, nullptr, n, grad, b /* 463 n floats free */, s);
     if (int rc = launch_metric_grad_h16(t, z, nullptr, n, 1.f, b, s, 2)) return rc;
-    return launch_pythae_finish_sym(t, z, a_packed, sd, b, g_packed, 1, n, grad, s);
+    if (int rc = launch_pythae_finish_sym(t, z, a_packed, sd, b, g_packed, 1, n, fail_ws, grad, s)) return rc;
+    return launch_pythae_exact(t, z, g_packed, 1, fail_ws + 1, fail_ws, n, grad, nullptr, s);
   }
   const int64_t mat = n * d * d;
   float* ginv = w;
   float* g = w + mat;
   float* scratch = w + 2 * mat;
-  // (d = 64 tensor forward: its packed tiles use the slot the augmented-table pass overwrites afterwards)
+  // (d = 64 tensor forward: its packed tiles live in the third slot of the workspace)
   if (int rc = inverse_metric_full(t, z, n, ginv, path, s, scratch)) return rc;
   if (int rc = launch_batched_inverse(ginv, n, d, g, logabsdet, sign, nullptr, 0, s)) return rc;
-  return launch_metric_grad_pythae(t, z, g, n, grad, scratch, s);
+  // (the third slot, n * (d*d + d) floats, is free again: partial sums of the split-centroid launch)
+  return launch_pythae_exact(t, z, g, 0, nullptr, nullptr, n, grad, d >= kPythaeMaxSplits ? scratch : nullptr, s);
 }
 
 int64_t rlvae_metric_eval_workspace(int64_t n, int d) {

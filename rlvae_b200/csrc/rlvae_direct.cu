@@ -254,76 +254,208 @@ int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float
 
 // ------------------------------------------------------------------------------------------
 // variant C (pythae): out = (1/T^2) G^T v,  v = sum_k w_k M_k^T (c_k - z)
-//   = sum_k w_k b_k - (G^{-1} - lambda I)^T z   with b_k = M_k^T c_k  folded into an
-// augmented table [M_k | b_k] so the same weighted-sum kernel produces both terms.
-// The augmented table is built lazily by the caller (tables struct owns it).
+//   ref src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:160-187
+// The difference c_k - z is formed PER CENTROID, as the reference does.  (Splitting the sum into
+// sum_k w_k M_k^T c_k - (sum_k w_k M_k)^T z -- two table contractions, which is what the tensor path does -- loses
+// |c| / |c_k - z| digits next to a centroid, multiplied by the condition number of G^{-1} when G is applied: measured
+// 1e-2 relative at T = 0.1, lambda = 1e-3 against 4e-5 for the reference's own fp32 arithmetic.  This kernel is the
+// accurate form: the whole CUDA-core path, and the fallback of the tensor path for the points its error bound flags.)
+// One CTA owns P points: per tile of 32 centroids the threads first form w_k (c_k - z) for every (point, centroid)
+// in shared memory, then thread e = (r, q) multiplies M_k[r][q] (one coalesced row of M per centroid, reused by the
+// P points) into its per-point partial of v_q; the partials are reduced over r at the end and G^T is applied.
 // ------------------------------------------------------------------------------------------
-__global__ void pythae_finish_kernel(const float* __restrict__ aug, const float* __restrict__ z,
-                                     const float* __restrict__ g, int64_t n, int d,
-                                     float T2, float* __restrict__ out) {
-  // one thread per (point, output dim)
+constexpr int PX_THREADS = 256;
+constexpr int PX_KT = 32;
+
+__device__ __forceinline__ int packed16_index(int r, int cidx) {
+  const int lo = r < cidx ? r : cidx, hi = r < cidx ? cidx : r;
+  return lo * 16 - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+
+template <int P, int SLOTS>
+__global__ void __launch_bounds__(PX_THREADS)
+pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ M, int K,
+                    int Kpad, int d, float T2, const float* __restrict__ g, int g_is_packed,
+                    const int* __restrict__ list, const int* __restrict__ count, int64_t n,
+                    float* __restrict__ partial /* [n, gridDim.y, d] when the centroids are split over blockIdx.y */,
+                    float* __restrict__ out) {
+  extern __shared__ float px_smem[];
+  const int dd = d * d;
+  float* zs = px_smem;                          // [P][d]
+  float* wd = zs + P * d;                       // [KT][d][P]   w_k (c_k - z), the P points contiguous
+  float* red = wd + P * PX_KT * d;              // [P][dd]      partials of v before the reduction over r
+  float* vs = red + P * dd;                     // [P][d]
+  __shared__ int64_t ids[P];
+  const int tid = threadIdx.x;
+  const int64_t total = (list != nullptr) ? (int64_t)*count : n;
+  // centroid range of this CTA (whole tiles of PX_KT; Kpad is a multiple of PX_KT)
+  const int tiles_k = Kpad / PX_KT;
+  const int per = (tiles_k + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int kbeg = (int)blockIdx.y * per * PX_KT;
+  const int kend = min(Kpad, kbeg + per * PX_KT);
+  for (int64_t tile = blockIdx.x; tile * P < total; tile += gridDim.x) {
+    __syncthreads();
+    if (tid < P) {
+      const int64_t i = tile * P + tid;
+      ids[tid] = (i < total) ? (list != nullptr ? (int64_t)list[i] : i) : -1;
+    }
+    __syncthreads();
+    for (int i = tid; i < P * d; i += PX_THREADS) {
+      const int p = i / d, j = i - p * d;
+      zs[i] = ids[p] >= 0 ? z[ids[p] * d + j] : 0.f;
+    }
+    float acc[P][SLOTS];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int sl = 0; sl < SLOTS; ++sl) acc[p][sl] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += PX_KT) {
+      __syncthreads();                           // zs ready / previous tile's wd consumed
+      for (int i = tid; i < P * PX_KT; i += PX_THREADS) {
+        const int p = i % P, kk = i / P;
+        const int k = k0 + kk;
+        const float* crow = c + (int64_t)k * d;
+        float sq = 0.f;
+        for (int j = 0; j < d; ++j) {
+          const float df = crow[j] - zs[p * d + j];
+          sq = fmaf(df, df, sq);
+        }
+        const float nrm = sqrtf(sq);             // ref :170-176: exp(-norm(c - z)^2 / T^2)
+        const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
+        for (int j = 0; j < d; ++j) wd[(kk * d + j) * P + p] = w * (crow[j] - zs[p * d + j]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int sl = 0; sl < SLOTS; ++sl) {
+        const int e = tid + sl * PX_THREADS;
+        if (e < dd) {
+          const int r = e / d;
+          const float* mrow = M + (int64_t)k0 * dd + e;
+          float m[PX_KT];
+#pragma unroll
+          for (int kk = 0; kk < PX_KT; ++kk) m[kk] = __ldg(mrow + (int64_t)kk * dd);     // 32 loads in flight
+#pragma unroll
+          for (int kk = 0; kk < PX_KT; ++kk) {
+            const float* wrow = wd + (kk * d + r) * P;
+            if (P % 4 == 0) {
+#pragma unroll
+              for (int p4 = 0; p4 < P / 4; ++p4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * p4);
+                acc[4 * p4 + 0][sl] = fmaf(m[kk], wv.x, acc[4 * p4 + 0][sl]);
+                acc[4 * p4 + 1][sl] = fmaf(m[kk], wv.y, acc[4 * p4 + 1][sl]);
+                acc[4 * p4 + 2][sl] = fmaf(m[kk], wv.z, acc[4 * p4 + 2][sl]);
+                acc[4 * p4 + 3][sl] = fmaf(m[kk], wv.w, acc[4 * p4 + 3][sl]);
+              }
+            } else {
+#pragma unroll
+              for (int p = 0; p < P; ++p) acc[p][sl] = fmaf(m[kk], wrow[p], acc[p][sl]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int e = tid + sl * PX_THREADS;
+      if (e < dd) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) red[p * dd + e] = acc[p][sl];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < P * d; i += PX_THREADS) {       // v_q = sum_r M[r][q] (c - z)_r
+      const int p = i / d, q = i - p * d;
+      float v = 0.f;
+      for (int r = 0; r < d; ++r) v += red[p * dd + r * d + q];
+      vs[i] = v;
+      if (gridDim.y > 1 && ids[p] >= 0) partial[(ids[p] * gridDim.y + blockIdx.y) * d + q] = v;
+    }
+    if (gridDim.y > 1) continue;                          // pythae_apply_g_kernel sums the splits and applies G
+    __syncthreads();
+    for (int i = tid; i < P * d; i += PX_THREADS) {       // out_j = (1/T^2) sum_i G[i][j] v_i
+      const int p = i / d, j = i - p * d;
+      if (ids[p] < 0) continue;
+      float o = 0.f;
+      if (g_is_packed) {
+        const float* gp = g + ids[p] * kSymCols;
+        for (int q = 0; q < d; ++q) o = fmaf(gp[packed16_index(q, j)], vs[p * d + q], o);
+      } else {
+        const float* gp = g + ids[p] * dd;
+        for (int q = 0; q < d; ++q) o = fmaf(gp[q * d + j], vs[p * d + q], o);
+      }
+      out[ids[p] * d + j] = o / T2;
+    }
+  }
+}
+
+// short batches: the centroids are split over several CTAs per point; this sums their partial v (fixed order) and
+// applies G^T / T^2.  One thread per (point, output dim).
+__global__ void pythae_apply_g_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ g,
+                                      int g_is_packed, int64_t n, int d, float T2, float* __restrict__ out) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n * d) return;
   const int64_t p = gid / d;
   const int j = (int)(gid - p * d);
-  const int ncols = d * d + d;
-  const float* row = aug + p * ncols;
-  const float* zp = z + p * d;
-  const float* gp = g + p * d * d;
-  // v_i = B_i - sum_e S[e][i] z_e, S = sum_k w_k M_k (accumulated WITHOUT lambda: fl(S_ii + lambda) - lambda
-  // would lose S_ii wherever the weights are small) ; out_j = (1/T2) sum_i G[i][j] v_i
   float o = 0.f;
-  for (int i = 0; i < d; ++i) {
-    float v = row[d * d + i];
-    for (int e = 0; e < d; ++e) v = fmaf(-row[e * d + i], zp[e], v);
-    o = fmaf(gp[i * d + j], v, o);
+  for (int q = 0; q < d; ++q) {
+    float v = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) v += partial[(p * splits + sidx) * d + q];
+    const float gq = g_is_packed ? g[p * kSymCols + packed16_index(q, j)] : g[p * d * d + q * d + j];
+    o = fmaf(gq, v, o);
   }
   out[gid] = o / T2;
 }
 
-__global__ void build_aug_table_kernel(const float* __restrict__ c, const float* __restrict__ M,
-                                       int K, int d, float* __restrict__ aug) {
-  const int k = blockIdx.x;
-  if (k >= K) return;
-  const int dd = d * d, ncols = dd + d;
-  for (int i = threadIdx.x; i < dd; i += blockDim.x) aug[(int64_t)k * ncols + i] = M[(int64_t)k * dd + i];
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    float b = 0.f;  // b_k[j] = sum_i M_k[i][j] c_k[i]
-    for (int i = 0; i < d; ++i) b = fmaf(M[(int64_t)k * dd + i * d + j], c[(int64_t)k * d + i], b);
-    aug[(int64_t)k * ncols + dd + j] = b;
-  }
-}
-
-// The augmented table [K, d*d+d] is a derived cache on the tables handle (built on first use, freed
-// with the handle); the [N, d*d+d] scratch comes from the caller (rlvae_metric_grad_pythae_workspace),
-// so nothing here is shared between devices, handles or streams.
-int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
-                              float* out, float* scratch, cudaStream_t s) {
-  if (n == 0) return 0;
-  const int d = t->d, ncols = d * d + d;
-  RLVAE_REQUIRE(scratch != nullptr, "metric_grad_pythae: workspace required");
-  if (t->pythae_aug == nullptr) {
-    float* aug = nullptr;
-    RLVAE_CUDA_OK(cudaMalloc(&aug, sizeof(float) * (size_t)t->K * ncols));
-    build_aug_table_kernel<<<t->K, 128, 0, s>>>(t->c, t->M, t->K, d, aug);
+template <int P, int SLOTS>
+static int launch_pythae_exact_t(const rlvae_tables* t, const float* z, const float* g, int g_is_packed, const int* list,
+                                 const int* count, int64_t n, float* out, float* partial, int splits, cudaStream_t s) {
+  const int d = t->d;
+  const size_t smem = sizeof(float) * ((size_t)P * d * (2 + PX_KT + d));
+  auto kern = pythae_exact_kernel<P, SLOTS>;
+  constexpr int DMAX = SLOTS == 1 ? 16 : (SLOTS == 4 ? 32 : 64);      // largest latent_dim this instantiation serves
+  RLVAE_OPT_IN_SMEM(kern, (int)(sizeof(float) * ((size_t)P * DMAX * (2 + PX_KT + DMAX))));
+  int64_t tiles = (n + P - 1) / P;
+  // a device-side list is usually short: a grid-stride launch of a few waves covers any length
+  const int64_t cap = (list != nullptr) ? 148 * 8 : ((int64_t)1 << 30);
+  dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)splits);
+  kern<<<grid, PX_THREADS, smem, s>>>(z, t->c, t->M, t->K, t->Kpad, d, t->T2, g, g_is_packed, list, count, n, partial,
+                                      out);
+  RLVAE_LAUNCH_OK();
+  if (splits > 1) {
+    const int64_t total = n * d;
+    pythae_apply_g_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, g, g_is_packed, n, d, t->T2,
+                                                                          out);
     RLVAE_LAUNCH_OK();
-    RLVAE_CUDA_OK(cudaStreamSynchronize(s));      // other streams may use the cached table next
-    t->pythae_aug = aug;
   }
-  dim3 grid((unsigned)((n + DM_BM - 1) / DM_BM), (unsigned)((ncols + DM_BN - 1) / DM_BN));
-  RLVAE_OPT_IN_SMEM(inverse_metric_direct_kernel, (int)dm_smem_bytes(kMaxLatentDim));
-  inverse_metric_direct_kernel<<<grid, DM_THREADS, dm_smem_bytes(d), s>>>(
-      z, t->c, t->pythae_aug, n, t->K, d, ncols, t->T2, 0.f /* no lambda: see pythae_finish_kernel */, scratch);
-  RLVAE_LAUNCH_OK();
-  const int64_t total = n * d;
-  pythae_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(scratch, z, g, n, d, t->T2, out);
-  RLVAE_LAUNCH_OK();
   return 0;
 }
 
-void pythae_cache_release(const rlvae_tables* t) {
-  if (t->pythae_aug) cudaFree(t->pythae_aug);
-  t->pythae_aug = nullptr;
+// g: [n,d,d] (g_is_packed == 0) or, d == 16, packed [n,144].  list / count (device): the rows to (re)compute, or
+// NULL for all n rows.  A long batch gets 8 (d <= 16) or 2 (d <= 32) points per CTA (each row of M is then read once
+// per CTA, not once per point); a short one (n <= kPythaeSplitBatch, no list) one CTA per (point, slice of the
+// centroids) so that the whole GPU works on it -- `partial` must then hold n * kPythaeMaxSplits * d floats.
+int launch_pythae_exact(const rlvae_tables* t, const float* z, const float* g, int g_is_packed, const int* list,
+                        const int* count, int64_t n, float* out, float* partial, cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(!g_is_packed || t->d == 16, "packed G is a latent_dim == 16 layout");
+  const int dd = t->d * t->d;
+  const bool small = n <= kPythaeSplitBatch;
+  int splits = 1;
+  if (small && list == nullptr && partial != nullptr) {
+    const int tiles_k = t->Kpad / PX_KT;
+    splits = (int)((148 * 4 + n - 1) / n);                       // ~4 CTAs per SM in total
+    if (splits > tiles_k / 4) splits = tiles_k / 4;              // at least 4 centroid tiles per CTA
+    if (splits > kPythaeMaxSplits) splits = kPythaeMaxSplits;
+    if (splits < 1) splits = 1;
+  }
+  if (dd <= PX_THREADS)
+    return small ? launch_pythae_exact_t<1, 1>(t, z, g, g_is_packed, list, count, n, out, partial, splits, s)
+                 : launch_pythae_exact_t<8, 1>(t, z, g, g_is_packed, list, count, n, out, partial, 1, s);
+  if (dd <= 4 * PX_THREADS)
+    return small ? launch_pythae_exact_t<1, 4>(t, z, g, g_is_packed, list, count, n, out, partial, splits, s)
+                 : launch_pythae_exact_t<2, 4>(t, z, g, g_is_packed, list, count, n, out, partial, 1, s);
+  return launch_pythae_exact_t<1, 16>(t, z, g, g_is_packed, list, count, n, out, partial, small ? splits : 1, s);
 }
 
 // ------------------------------------------------------------------------------------------

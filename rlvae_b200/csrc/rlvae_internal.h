@@ -134,12 +134,13 @@ struct rlvae_tables {
   void* ct64_hi = nullptr;
   void* ct64_lo = nullptr;
   CUtensorMap tm_ct64_hi, tm_ct64_lo, tm_ct64_2_hi, tm_ct64_2_lo;
-  // pythae-variant gradient (A8): [K, d*d+d] = [M_k | M_k^T c_k], built on first use (derived cache)
-  mutable float* pythae_aug = nullptr;
-  // ... on the tensor path (d == 16, symmetric): b_k = sym(M_k) (c_k - shift), TF32 hi / lo, transposed [16, Kpad] --
-  // the B operand of the gradient kernel's final contraction in its unit-weight mode (sum_k w_k b_k)
+  // pythae-variant gradient (A8) on the tensor path (d == 16, symmetric): b_k = sym(M_k) (c_k - shift), TF32 hi / lo,
+  // transposed [16, Kpad] -- the B operand of the gradient kernel's final contraction in its unit-weight mode
+  // (sum_k w_k b_k); m_fro_rms = (sum_k ||M_k||_F) / sqrt(K) enters the error bound that sends points to the
+  // per-centroid kernel
   float* bt_hi = nullptr;
   float* bt_lo = nullptr;
+  float m_fro_rms = 0.f;
   CUtensorMap tm_bt16_hi, tm_bt16_lo, tm_bt8_hi, tm_bt8_lo;
 };
 
@@ -150,8 +151,13 @@ int launch_inverse_metric_direct(const rlvae_tables* t, const float* z, int64_t 
                                  cudaStream_t s);
 int launch_metric_grad_direct(const rlvae_tables* t, const float* z, const float* u, int64_t n,
                               float scale, float* out, cudaStream_t s);
-int launch_metric_grad_pythae(const rlvae_tables* t, const float* z, const float* g, int64_t n,
-                              float* out, float* scratch, cudaStream_t s);
+// variant C (pythae) with the difference c_k - z formed per centroid, like the reference (rlvae_direct.cu)
+// partial (optional): n * kPythaeMaxSplits * d floats -- short batches (n <= kPythaeSplitBatch) then split the
+// centroids over several CTAs per point
+constexpr int64_t kPythaeSplitBatch = 2048;
+constexpr int kPythaeMaxSplits = 16;
+int launch_pythae_exact(const rlvae_tables* t, const float* z, const float* g, int g_is_packed, const int* list,
+                        const int* count, int64_t n, float* out, float* partial, cudaStream_t s);
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
                            float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 // d == 16 only: `a` is the packed symmetric layout [N,144] written by the symmetric tensor kernel
