@@ -585,7 +585,10 @@ def run_ours(args):
             zo = osamp.sample_prior(32); torch.cuda.synchronize(dev)
             t_off = max_over_ranks((time.perf_counter() - t0) * 1e3)
         pythae = {'what': 'log|det G^-1| + (1/T^2) G^T sum_k w_k M_k^T (c_k - z), 2^20 points per GPU', 'ms': tp,
-                  'value': world * n / (tp * 1e-3), 'unit': UNIT, 'kernel_launches': 3,
+                  'value': world * n / (tp * 1e-3), 'unit': UNIT,
+                  'launches': 'forward kernel (+ its normally-empty Cholesky fallback pass), unit-weight pass of the '
+                              'gradient kernel, finish kernel with the per-row error bound, per-centroid kernel over '
+                              'the flagged rows (none at this configuration)',
                   'finite': bool(torch.isfinite(pg).all().item() and torch.isfinite(pl).all().item()),
                   'official_sample_prior_32': {'mcmc_steps': 100, 'n_lf': 15, 'temperature': 0.1, 'wall_ms': t_off,
                                                'finite': bool(torch.isfinite(zo).all().item())}}
