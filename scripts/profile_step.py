@@ -37,3 +37,6 @@ if len(sys.argv) > 3 and sys.argv[3] == 'hmc':     # plus one short HMC iteratio
     sp = mt.compute_metric_spectrum(z)                          # A19: forward + per-thread Jacobi
     torch.cuda.synchronize()
     print('nearest2 / spectrum ok', int(idx[0, 0]), float(sp['condition_number'][:4].mean()))
+    pg, pl, ps = _capi.pythae_eval(mt._tables(dev), z)          # A8: forward + unit-weight gradient pass + finish
+    torch.cuda.synchronize()
+    print('pythae ok', float(pg[:4].sum()))
