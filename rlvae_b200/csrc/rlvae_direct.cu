@@ -316,13 +316,31 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
         const int k = k0 + kk;
         const float* crow = c + (int64_t)k * d;
         float sq = 0.f;
-        for (int j = 0; j < d; ++j) {
-          const float df = crow[j] - zs[p * d + j];
-          sq = fmaf(df, df, sq);
+        if (SLOTS == 1 && d == 16) {             // the common latent_dim: one 64-byte row, differences stay in registers
+          float df[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(crow) + q4);
+            df[4 * q4 + 0] = cv.x - zs[p * 16 + 4 * q4 + 0];
+            df[4 * q4 + 1] = cv.y - zs[p * 16 + 4 * q4 + 1];
+            df[4 * q4 + 2] = cv.z - zs[p * 16 + 4 * q4 + 2];
+            df[4 * q4 + 3] = cv.w - zs[p * 16 + 4 * q4 + 3];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sq = fmaf(df[j], df[j], sq);
+          const float nrm = sqrtf(sq);           // ref :170-176: exp(-norm(c - z)^2 / T^2)
+          const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) wd[(kk * 16 + j) * P + p] = w * df[j];
+        } else {
+          for (int j = 0; j < d; ++j) {
+            const float df = crow[j] - zs[p * d + j];
+            sq = fmaf(df, df, sq);
+          }
+          const float nrm = sqrtf(sq);
+          const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
+          for (int j = 0; j < d; ++j) wd[(kk * d + j) * P + p] = w * (crow[j] - zs[p * d + j]);
         }
-        const float nrm = sqrtf(sq);             // ref :170-176: exp(-norm(c - z)^2 / T^2)
-        const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
-        for (int j = 0; j < d; ++j) wd[(kk * d + j) * P + p] = w * (crow[j] - zs[p * d + j]);
       }
       __syncthreads();
 #pragma unroll
@@ -331,25 +349,29 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
         if (e < dd) {
           const int r = e / d;
           const float* mrow = M + (int64_t)k0 * dd + e;
-          float m[PX_KT];
 #pragma unroll
-          for (int kk = 0; kk < PX_KT; ++kk) m[kk] = __ldg(mrow + (int64_t)kk * dd);     // 32 loads in flight
+          for (int kb = 0; kb < PX_KT; kb += 16) {
+          float m[16];
 #pragma unroll
-          for (int kk = 0; kk < PX_KT; ++kk) {
+          for (int kk = 0; kk < 16; ++kk) m[kk] = __ldg(mrow + (int64_t)(kb + kk) * dd);     // 16 loads in flight
+#pragma unroll
+          for (int kq = 0; kq < 16; ++kq) {
+            const int kk = kb + kq;
             const float* wrow = wd + (kk * d + r) * P;
             if (P % 4 == 0) {
 #pragma unroll
               for (int p4 = 0; p4 < P / 4; ++p4) {
                 const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * p4);
-                acc[4 * p4 + 0][sl] = fmaf(m[kk], wv.x, acc[4 * p4 + 0][sl]);
-                acc[4 * p4 + 1][sl] = fmaf(m[kk], wv.y, acc[4 * p4 + 1][sl]);
-                acc[4 * p4 + 2][sl] = fmaf(m[kk], wv.z, acc[4 * p4 + 2][sl]);
-                acc[4 * p4 + 3][sl] = fmaf(m[kk], wv.w, acc[4 * p4 + 3][sl]);
+                acc[4 * p4 + 0][sl] = fmaf(m[kq], wv.x, acc[4 * p4 + 0][sl]);
+                acc[4 * p4 + 1][sl] = fmaf(m[kq], wv.y, acc[4 * p4 + 1][sl]);
+                acc[4 * p4 + 2][sl] = fmaf(m[kq], wv.z, acc[4 * p4 + 2][sl]);
+                acc[4 * p4 + 3][sl] = fmaf(m[kq], wv.w, acc[4 * p4 + 3][sl]);
               }
             } else {
 #pragma unroll
-              for (int p = 0; p < P; ++p) acc[p][sl] = fmaf(m[kk], wrow[p], acc[p][sl]);
+              for (int p = 0; p < P; ++p) acc[p][sl] = fmaf(m[kq], wrow[p], acc[p][sl]);
             }
+          }
           }
         }
       }

@@ -31,6 +31,14 @@ with torch.no_grad():
         for p in paths:
             nm = 'tensor' if p == _capi.PATH_TENSOR else 'direct'
             timeit(f'pythae_eval n={n} {nm}', lambda: _capi.pythae_eval(tab, z, path=p), n, reps=3 if n > 1000 else 50)
+    # the hard corner: T = 0.1, every point a fraction of T away from a centroid -> the error bound flags every row
+    # and the per-centroid kernel redoes it
+    mt01 = MetricTensor(16, device=dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt01.load_pretrained(sm.centroids, sm.metric_matrices, temperature=0.1, regularization=sm.regularization)
+    n = 1 << 16
+    zn = (sm.centroids[torch.randint(K, (n,))] + 0.0075 * make_points(n, 16, seed=5)).to(dev)
+    timeit(f'pythae_eval n={n} T=0.1 next to centroids (all rows flagged)', lambda: _capi.pythae_eval(mt01._tables(dev), zn), n)
     model = MetricModel(mt)
     for path in ('auto', 'direct'):
         mt.kernel_path = path
