@@ -278,6 +278,8 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
                     int Kpad, int d, float T2, const float* __restrict__ g, int g_is_packed,
                     const int* __restrict__ list, const int* __restrict__ count, int64_t n,
                     float* __restrict__ partial /* [n, gridDim.y, d] when the centroids are split over blockIdx.y */,
+                    float cut /* > 0: skip centroid tiles whose weights are all below exp(-cut / T^2) of the point's
+                                 largest weight (cut = 50 ln 2 T^2: 2^-50, far below fp32 resolution of the sum) */,
                     float* __restrict__ out) {
   extern __shared__ float px_smem[];
   const int dd = d * d;
@@ -286,6 +288,7 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
   float* red = wd + P * PX_KT * d;              // [P][dd]      partials of v before the reduction over r
   float* vs = red + P * dd;                     // [P][d]
   __shared__ int64_t ids[P];
+  __shared__ int dmin_s[P];                     // smallest squared distance of each point to a centroid (float bits)
   const int tid = threadIdx.x;
   const int64_t total = (list != nullptr) ? (int64_t)*count : n;
   // centroid range of this CTA (whole tiles of PX_KT; Kpad is a multiple of PX_KT)
@@ -309,8 +312,40 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
     for (int p = 0; p < P; ++p)
 #pragma unroll
       for (int sl = 0; sl < SLOTS; ++sl) acc[p][sl] = 0.f;
+    if (tid < P) dmin_s[tid] = 0x7f800000;       // +inf
+    __syncthreads();
+    if (cut > 0.f) {
+      // pass 0: distance of every point to its nearest centroid.  At small temperatures all but a few centroids
+      // carry weights that vanish against the largest one; whole tiles of them are then skipped below.
+      float dmin = __int_as_float(0x7f800000);
+      const int p = tid % P;                     // (PX_THREADS is a multiple of P: the same point in every round)
+      for (int i = tid; i < P * Kpad; i += PX_THREADS) {
+        const int k = i / P;
+        if (k >= K) break;
+        const float* crow = c + (int64_t)k * d;
+        float sq = 0.f;
+        if (SLOTS == 1 && d == 16) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(crow) + q4);
+            float df = cv.x - zs[p * 16 + 4 * q4 + 0]; sq = fmaf(df, df, sq);
+            df = cv.y - zs[p * 16 + 4 * q4 + 1]; sq = fmaf(df, df, sq);
+            df = cv.z - zs[p * 16 + 4 * q4 + 2]; sq = fmaf(df, df, sq);
+            df = cv.w - zs[p * 16 + 4 * q4 + 3]; sq = fmaf(df, df, sq);
+          }
+        } else {
+          for (int j = 0; j < d; ++j) {
+            const float df = crow[j] - zs[p * d + j];
+            sq = fmaf(df, df, sq);
+          }
+        }
+        dmin = fminf(dmin, sq);                  // (a NaN distance is ignored here and counts as live below)
+      }
+      atomicMin(&dmin_s[p], __float_as_int(dmin));     // sq >= 0: the int order is the float order
+    }
     for (int k0 = kbeg; k0 < kend; k0 += PX_KT) {
-      __syncthreads();                           // zs ready / previous tile's wd consumed
+      __syncthreads();                           // zs / dmin_s ready / previous tile's wd consumed
+      int live = 0;
       for (int i = tid; i < P * PX_KT; i += PX_THREADS) {
         const int p = i % P, kk = i / P;
         const int k = k0 + kk;
@@ -330,6 +365,7 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
           for (int j = 0; j < 16; ++j) sq = fmaf(df[j], df[j], sq);
           const float nrm = sqrtf(sq);           // ref :170-176: exp(-norm(c - z)^2 / T^2)
           const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
+          live |= (k < K && ids[p] >= 0 && !(sq >= __int_as_float(dmin_s[p]) + cut)) ? 1 : 0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) wd[(kk * 16 + j) * P + p] = w * df[j];
         } else {
@@ -339,10 +375,11 @@ pythae_exact_kernel(const float* __restrict__ z, const float* __restrict__ c, co
           }
           const float nrm = sqrtf(sq);
           const float w = (k < K && ids[p] >= 0) ? expf(-(nrm * nrm) / T2) : 0.f;
+          live |= (k < K && ids[p] >= 0 && !(sq >= __int_as_float(dmin_s[p]) + cut)) ? 1 : 0;
           for (int j = 0; j < d; ++j) wd[(kk * d + j) * P + p] = w * (crow[j] - zs[p * d + j]);
         }
       }
-      __syncthreads();
+      if (!__syncthreads_or(cut > 0.f ? live : 1)) continue;     // every weight of this tile vanishes: nothing to add
 #pragma unroll
       for (int sl = 0; sl < SLOTS; ++sl) {
         const int e = tid + sl * PX_THREADS;
@@ -441,8 +478,10 @@ static int launch_pythae_exact_t(const rlvae_tables* t, const float* z, const fl
   // a device-side list is usually short: a grid-stride launch of a few waves covers any length
   const int64_t cap = (list != nullptr) ? 148 * 8 : ((int64_t)1 << 30);
   dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)splits);
+  // tile skipping needs the nearest-centroid pass over ALL centroids: not worth it when the centroids are split
+  const float cut = (splits > 1) ? 0.f : 34.657359f * t->T2;           // 50 ln 2 T^2
   kern<<<grid, PX_THREADS, smem, s>>>(z, t->c, t->M, t->K, t->Kpad, d, t->T2, g, g_is_packed, list, count, n, partial,
-                                      out);
+                                      cut, out);
   RLVAE_LAUNCH_OK();
   if (splits > 1) {
     const int64_t total = n * d;
