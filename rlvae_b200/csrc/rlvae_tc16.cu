@@ -999,6 +999,68 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 }
 
 
+// HYBRID mode of the gradient kernel.  Like refine_exponents, the pairs flagged in `live` get their exponent from
+// exact differences -- and, because those are exactly the pairs whose weight is not negligible, i.e. the centroids
+// NEAR the point, their whole contribution u (c_k - z) is accumulated here from the exact difference vector and
+// taken out of the tensor contraction (exponent -> -1e30 -> u = 0 for GEMM3 and for sum_k u).  The contraction's
+// form sum_k u c~_k - z~ sum_k u loses |c~| / |c_k - z| digits next to a centroid (1.2e-4 relative at T = 0.1,
+// measured against fp64); with the near pairs handled here only far pairs go through it, where nothing cancels.
+__device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t (&tv)[32], uint32_t live,
+                                              const float4* __restrict__ crows, const float2 (&nz)[8], float neg_alpha,
+                                              float shift, float2 (&direct)[8]) {
+  if (!__any_sync(0xffffffffu, live != 0u)) return;
+  constexpr uint32_t NEG_BIG = 0xf149f2cau;        // -1e30f
+  const int total = __reduce_add_sync(0xffffffffu, __popc(live));
+  if (total > 160) {                               // dense tile: uniform sweep, broadcast loads
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float2 dv[8];
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 c = __ldg(crows + i * 4 + q);
+        dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
+        dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
+        ffma2_acc(acc, dv[2 * q], dv[2 * q]);
+        ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
+      }
+      if ((live >> i) & 1u) {
+        const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tv[i]);
+        const float2 u2 = make_float2(uv, uv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
+        ex[i] = NEG_BIG;
+      }
+    }
+    return;
+  }
+  while (__any_sync(0xffffffffu, live != 0u)) {
+    if (live != 0u) {
+      const int b = __ffs(live) - 1;
+      live &= live - 1u;
+      float2 dv[8];
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 c = __ldg(crows + b * 4 + q);
+        dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
+        dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
+        ffma2_acc(acc, dv[2 * q], dv[2 * q]);
+        ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
+      }
+      uint32_t tb = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tb = (i == b) ? tv[i] : tb;
+      const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tb);
+      const float2 u2 = make_float2(uv, uv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ex[i] = (i == b) ? NEG_BIG : ex[i];
+    }
+  }
+}
+
 // ==========================================================================================
 // Gradient / backward kernel, split-fp16 version (symmetric tables, d == 16):
 //   out[n,:] = scale * sum_k w_nk <U_n, M_k> (c_k - z_n)
@@ -1435,6 +1497,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float tot[17];                       // this group's share of OUT (chunks of parity grp) and of sum_k u
 #pragma unroll
     for (int e = 0; e < 17; ++e) tot[e] = 0.f;
+    float2 direct[8];                    // HYBRID: sum of u (c_k - z) over the near pairs, from exact differences
+#pragma unroll
+    for (int q = 0; q < 8; ++q) direct[q] = make_float2(0.f, 0.f);
     auto fold_chunk = [&](int c, bool signal) {
       uint32_t a[16];
       TMEM_LD16(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
@@ -1486,8 +1551,12 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
               sv[i] = __float_as_uint(ex);
             }
           }
-          refine_exponents(sv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
-                           -alpha, 0.f);
+          if (u_packed == 2)      // unit-weight mode: the table behind the contraction is not the centroids
+            refine_exponents(sv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
+                             -alpha, 0.f);
+          else
+            refine_direct(sv, tv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
+                          -alpha, 0.f, direct);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
@@ -1542,6 +1611,10 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     mbar_wait(BAR_DONE, 0);
     tc_fence_after();
     while (next_chunk < num_chunks) { fold_chunk(next_chunk, false); next_chunk += 2; }
+    if (HYBRID) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { tot[2 * q] += direct[q].x; tot[2 * q + 1] += direct[q].y; }
+    }
     // ---------------------------------------------------------- combine the two groups
     asm volatile("bar.sync 1, 256;" ::: "memory");
     float* red = reinterpret_cast<float*>(gbase + OFF_M);

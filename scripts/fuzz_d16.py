@@ -96,6 +96,23 @@ for case in range(cases):
     n64 = t64.norm(dim=1)
     lv = n64 > 1e-3 * n64.max()
     e_ref = rel_rows(t32, t64, lv)
+    # exact gradient (variant D) in fp64: grad_z log det G = -(2/T^2) sum_k w_k tr(G M_k) (c_k - z)
+    def grad_ref64():
+        cz, Mz, zz = c.to(dev).double(), M.to(dev).double(), z.double()
+        outs = []
+        for lo in range(0, n, 64):
+            delta = cz[None] - zz[lo:lo + 64][:, None]
+            w = torch.exp(-(delta ** 2).sum(-1) / T ** 2)
+            gm = torch.linalg.inv(torch.einsum('nk,kij->nij', w, Mz) + lam * torch.eye(16, device=dev, dtype=torch.float64))
+            tr = torch.einsum('nij,kji->nk', gm, Mz)
+            outs.append(-(2.0 / T ** 2) * torch.einsum('nk,nkj->nj', w * tr, delta))
+        return torch.cat(outs)
+    g64 = grad_ref64()
+    gl64 = g64.norm(dim=1) > 1e-6 * g64.norm(dim=1).max()
+    errs['grad64_tensor'] = rel_rows(a['grad_logdet_g'], g64, gl64)
+    errs['grad64_direct'] = rel_rows(b['grad_logdet_g'], g64, gl64)
+    if os.environ.get('FUZZ_FP64'):
+        print(tag, 'grad vs fp64: tensor %.2e  direct %.2e' % (errs['grad64_tensor'], errs['grad64_direct']), flush=True)
     errs['pythae64_tensor'] = rel_rows(pa, t64, lv) / max(10 * e_ref, 5e-5)
     errs['pythae64_direct'] = rel_rows(pb, t64, lv) / max(10 * e_ref, 5e-5)
     if os.environ.get('FUZZ_FP64'):
@@ -120,7 +137,7 @@ for case in range(cases):
         fin = torch.isfinite(al2)
         errs['hmc_alpha'] = ((al1 - al2)[fin].abs().max().item() if fin.any() else 0.0)
     lim = {'ginv': 1e-5, 'g': 1e-4, 'logdet': 2e-4, 'grad': 2e-4, 'pythae': 1e-2, 'pythae_abs': 1e-2, 'pythae_lad': 2e-4,
-           'pythae64_tensor': 1.0, 'pythae64_direct': 1.0,
+           'pythae64_tensor': 1.0, 'pythae64_direct': 3.0, 'grad64_tensor': 2e-4, 'grad64_direct': 2e-4,
            'hmc_flips_not_tie': 0.5, 'hmc_z': 1e-3, 'hmc_alpha': 1e-3}
     over = {k: v for k, v in errs.items() if not (v <= lim[k])}
     for k, v in errs.items():
