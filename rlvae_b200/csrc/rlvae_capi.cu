@@ -990,10 +990,15 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   // G^T == G up to rounding, otherwise a transposed copy is produced.
   const bool need_gt = (grad_logdet_g != nullptr) && !t->symmetric;
   const bool plain_g = (g != nullptr) || ((grad_logdet_g != nullptr) && t->symmetric);
-  if (plain_g || logdet_g != nullptr) {
-    // (d = 64: a one-warp-per-matrix Cholesky in shared memory was tried for the symmetric case and lost to this
-    // register-resident Gauss-Jordan, 36 vs 20 ms per 2^17 matrices: 133 KB of shared memory per CTA left one warp
-    // per scheduler and every dependent shared-memory load exposed)
+  bool lad_done = false;
+  if ((plain_g || logdet_g != nullptr) && d == 64 && t->symmetric) {
+    // symmetric tables: G^{-1} is symmetric positive definite -> register-resident elimination / sweep without
+    // pivoting or staging (spd64_kernel); the few matrices that are not PD re-run through the pivoting kernel.
+    // (The G^T slot is free here: the packed tiles were consumed by the unpack, the gradient kernel comes later.)
+    if (int rc = launch_spd64(a_buf, n, plain_g ? g_buf : nullptr, logdet_g, -1.f, reinterpret_cast<int*>(gt_buf), s))
+      return rc;
+    lad_done = true;
+  } else if (plain_g || logdet_g != nullptr) {
     if (int rc = launch_batched_inverse(a_buf, n, d, plain_g ? g_buf : nullptr, logdet_g ? lad_buf : nullptr,
                                         nullptr, nullptr, 0, s))
       return rc;
@@ -1001,7 +1006,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   if (need_gt) {
     if (int rc = launch_batched_inverse(a_buf, n, d, gt_buf, nullptr, nullptr, nullptr, 1, s)) return rc;
   }
-  if (logdet_g != nullptr) {
+  if (logdet_g != nullptr && !lad_done) {
     // log|det G| = -log|det G^{-1}|
     if (int rc = negate_copy(lad_buf, logdet_g, n, s)) return rc;
   }

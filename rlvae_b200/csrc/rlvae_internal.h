@@ -161,6 +161,10 @@ int launch_pythae_exact(const rlvae_tables* t, const float* z, const float* g, i
 int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* logabsdet,
                            float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 // d == 16 only: `a` is the packed symmetric layout [N,144] written by the symmetric tensor kernel
+// 64 x 64 symmetric positive definite batch (no pivoting; failures re-run through the pivoting kernel):
+// inv optional, logabsdet = lad_scale * log det, fail_ws = 1 + n ints
+int launch_spd64(const float* a, int64_t n, float* inv, float* logabsdet, float lad_scale, int* fail_ws,
+                 cudaStream_t s);
 int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv, float* logabsdet,
                                     float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s);

@@ -636,6 +636,128 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------- SPD 64 x 64
+// Symmetric positive definite 64 x 64 matrices (G^{-1} of symmetric tables at latent_dim 64): log det and,
+// optionally, the inverse WITHOUT pivoting, one warp per matrix, rows lane / lane + 32 in registers.
+//   * symmetry gives coalesced global accesses with no shared-memory staging (row i of A == column i: lane l
+//     reads / writes element (k, l) of every row k), so the kernel keeps 12 warps per SM instead of the staged
+//     Gauss-Jordan's 33 KB per two matrices;
+//   * the Schur complement of an SPD matrix stays symmetric, so the pivot ROW every elimination step needs is
+//     the pivot COLUMN the lanes already hold: two shared-memory stores per lane + broadcast reads replace the
+//     64 shuffles per step of batched_inverse_kernel, and there is no pivot search.
+//   WANT_INV == false: Gaussian elimination of the lower triangle only (2512 FMAs per lane), log det = sum of
+//     the log pivots.  WANT_INV == true: the symmetric sweep operator (pivot d: a_jj <- -1/d, a_ij <- a_ij/d,
+//     a_ik <- a_ik - a_ij a_jk / d) applied to all 64 pivots leaves -A^{-1}.
+// A pivot that is not > 0 (not positive definite, or NaN) appends the matrix to `fail` (fail[0] = count,
+// fail[1..] = indices); the caller re-runs those through the pivoting Gauss-Jordan (torch.linalg.inv /
+// slogdet semantics, ref src/models/components/metric_tensor.py:152,175).
+template <bool WANT_INV>
+__global__ void __launch_bounds__(128, WANT_INV ? 2 : 3)
+spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, float* __restrict__ logabsdet,
+             float lad_scale, int* __restrict__ fail) {
+  __shared__ __align__(16) float colbuf[4][2][64];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t mat = (int64_t)blockIdx.x * 4 + wrp;
+  if (mat >= n) return;                                    // (warp-uniform; no block-wide barrier below)
+  const float* src = a + mat * 4096;
+  float r0[64], r1[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    r0[k] = (WANT_INV || k < 32) ? __ldg(src + k * 64 + lane) : 0.f;     // A[lane][k] == A[k][lane]
+    r1[k] = __ldg(src + k * 64 + 32 + lane);
+  }
+  float lad = 0.f, prod = 1.f;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    float* col = colbuf[wrp][j & 1];
+    col[lane] = r0[j];                                     // (lower-triangle variant, j >= 32: never read)
+    col[lane + 32] = r1[j];
+    __syncwarp();
+    const float d = col[j];
+    if (!(d > 0.f)) bad = true;
+    const float dinv = 1.f / d;
+    prod *= d;
+    if ((j & 7) == 7) { lad += logf(prod); prod = 1.f; }
+    if (WANT_INV) {
+      // the pivot row becomes col / d, every other row r - (r_j / d) col: one FMA per entry, plus one select per
+      // entry in the slot that can hold the pivot row (known at compile time)
+      const bool own0 = (j < 32) && (lane == j), own1 = (j >= 32) && (lane == j - 32);
+      const float f0 = r0[j] * dinv, f1 = r1[j] * dinv;
+      const float x0 = own0 ? dinv : -f0, x1 = own1 ? dinv : -f1;
+#pragma unroll
+      for (int k4 = 0; k4 < 64; k4 += 4) {
+        const float4 c = *reinterpret_cast<const float4*>(col + k4);
+        const float cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k4 + q;
+          if (k == j) continue;
+          if (j < 32) {
+            r0[k] = fmaf(x0, cv[q], own0 ? 0.f : r0[k]);
+            r1[k] = fmaf(x1, cv[q], r1[k]);
+          } else {
+            r0[k] = fmaf(x0, cv[q], r0[k]);
+            r1[k] = fmaf(x1, cv[q], own1 ? 0.f : r1[k]);
+          }
+        }
+      }
+      r0[j] = own0 ? -dinv : f0;
+      r1[j] = own1 ? -dinv : f1;
+    } else {
+      // rows <= j are finished: their multipliers are garbage, but they only touch entries above the diagonal,
+      // which nothing reads
+      const float f0 = (j < 31) ? r0[j] * dinv : 0.f, f1 = r1[j] * dinv;
+#pragma unroll
+      for (int k4 = ((j + 1) & ~3); k4 < 64; k4 += 4) {
+        const float4 c = *reinterpret_cast<const float4*>(col + k4);
+        const float cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k4 + q;
+          if (k <= j) continue;
+          if (k < 32) r0[k] = fmaf(-f0, cv[q], r0[k]);
+          r1[k] = fmaf(-f1, cv[q], r1[k]);
+        }
+      }
+    }
+  }
+  if (bad) {
+    if (lane == 0) {
+      const int slot = atomicAdd(fail, 1);
+      fail[1 + slot] = (int)mat;
+    }
+    return;
+  }
+  if (WANT_INV) {
+    float* dst = inv + mat * 4096;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+      dst[k * 64 + lane] = -r0[k];
+      dst[k * 64 + 32 + lane] = -r1[k];
+    }
+  }
+  if (lane == 0 && logabsdet != nullptr) logabsdet[mat] = lad_scale * lad;
+}
+
+// 64 x 64 SPD batch: inv (optional, [n,64,64]) and lad_scale * log det; `fail_ws`: 1 + n ints.
+// Matrices that are not positive definite fall through to the pivoting Gauss-Jordan.
+int launch_spd64(const float* a, int64_t n, float* inv, float* logabsdet, float lad_scale, int* fail_ws,
+                 cudaStream_t s) {
+  if (n == 0) return 0;
+  RLVAE_REQUIRE(n < ((int64_t)1 << 31), "spd64: batch too large for the fallback list");
+  RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
+  const unsigned grid = (unsigned)((n + 3) / 4);
+  if (inv != nullptr) spd64_kernel<true><<<grid, 128, 0, s>>>(a, n, inv, logabsdet, lad_scale, fail_ws);
+  else spd64_kernel<false><<<grid, 128, 0, s>>>(a, n, nullptr, logabsdet, lad_scale, fail_ws);
+  RLVAE_LAUNCH_OK();
+  const unsigned fgrid = (unsigned)(n / 2 < 296 ? (n + 1) / 2 : 296);
+  batched_inverse_kernel<64><<<fgrid, PP<64>::THREADS, 0, s>>>(a, n, inv, logabsdet, nullptr, nullptr, 0, fail_ws + 1,
+                                                               fail_ws, nullptr, lad_scale, 64);
+  RLVAE_LAUNCH_OK();
+  return 0;
+}
+
 // out = L @ eps, L = cholesky(A + jitter I) (lower; only the lower triangle of A is read,
 // like LAPACK potrf('L') behind torch.linalg.cholesky).  Right-looking, column by column.
 template <int D>

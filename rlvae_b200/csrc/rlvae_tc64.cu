@@ -446,25 +446,56 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 64, TM_ST = 128, TM_OUT = 384, TM_ZHI = 448, TM_ZLO = 480;
 }  // namespace g64
 
-// per-point exponent eU with max|2^eU Ut| in [2^13, 2^14): Ut_p = U_ij + U_ji <= 2 max|U|
-__global__ void u_scale64_kernel(const float* __restrict__ u, int64_t n, int* __restrict__ eu) {
-  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t p = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); p < n; p += (int64_t)gridDim.x * warps) {
-    const float4* row = reinterpret_cast<const float4*>(u + p * 4096);
+// U [N,64,64] (any matrix) -> packed Ut [N,2176] fp32 (Ut_p = U_ij + U_ji for the packed column p = (i < j), U_ii on
+// the diagonal, zeros in the padding columns) + the per-point exponent eU with max|2^eU Ut| in [2^13, 2^14).
+// One CTA per point: the matrix goes through shared memory (coalesced 128-bit loads; row stride 65 so the
+// transposed reads hit distinct banks), the packed row leaves coalesced -- the gradient kernel's prologue then reads
+// 256 contiguous bytes per thread and column tile instead of 128 scattered words (7.5 -> ~1 ms per 2^17 points).
+__global__ void __launch_bounds__(256)
+pack_u64_kernel(const float* __restrict__ u, int64_t n, float* __restrict__ up, int* __restrict__ eu) {
+  __shared__ float sm[64 * 65];
+  __shared__ float wmax[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(u + p * 4096);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i4 = tid + 256 * q;                 // float4 index: row i4 / 16, columns 4 (i4 % 16) ..
+      const float4 v = __ldg(src + i4);
+      float* dst = sm + (i4 >> 4) * 65 + ((i4 & 15) << 2);
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
     float m = 0.f;
-    for (int i = lane; i < 1024; i += 32) {
-      const float4 v = __ldg(row + i);
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    float* dst = up + p * h64::NPAD;
+    for (int c = tid; c < h64::NPAD; c += 256) {
+      float v = 0.f;
+      if (c < h64::NPACK) {
+        // packed column c -> (i, j), i <= j: base(i) = i (129 - i) / 2 <= c < base(i + 1)
+        int i = (int)((129.f - sqrtf(16641.f - 8.f * (float)c)) * 0.5f);
+        i = i < 0 ? 0 : (i > 63 ? 63 : i);
+        while (i < 63 && ((i + 1) * (128 - i)) / 2 <= c) ++i;
+        while (i > 0 && (i * (129 - i)) / 2 > c) --i;
+        const int j = i + (c - (i * (129 - i)) / 2);
+        v = sm[i * 65 + j];
+        if (j != i) v += sm[j * 65 + i];
+      }
+      dst[c] = v;
+      m = fmaxf(m, fabsf(v));
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    m *= 2.f;
-    int e = 0;
-    if (m > 0.f && m < 3.0e38f) {
-      const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;    // m = f 2^ex, f in [0.5, 1)
-      e = 14 - ex;
-      e = e > 50 ? 50 : (e < -50 ? -50 : e);
+    if (lane == 0) wmax[warp] = m;
+    __syncthreads();                                // (also: every thread is done reading sm)
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, wmax[w]);
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) {
+        const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;    // m = f 2^ex, f in [0.5, 1)
+        e = 14 - ex;
+        e = e > 50 ? 50 : (e < -50 ? -50 : e);
+      }
+      eu[p] = e;
     }
-    if (lane == 0) eu[p] = e;
   }
 }
 
@@ -487,7 +518,7 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
                        const __grid_constant__ CUtensorMap tm_mn_lo,
                        const __grid_constant__ CUtensorMap tm_ct_hi,
                        const __grid_constant__ CUtensorMap tm_ct_lo,
-                       const float* __restrict__ z, const float* __restrict__ u /* [N,64,64] */,
+                       const float* __restrict__ z, const float* __restrict__ up /* [N,2176] packed Ut (pack_u64_kernel) */,
                        const int* __restrict__ eu /* [N] per-point exponent of U' */,
                        const float* __restrict__ cbias, int64_t n, int num_blocks, float alpha,
                        float scale /* includes 2^-eM */, float c_unscale /* 2^-ec */,
@@ -619,27 +650,14 @@ metric_grad_h64_kernel(const __grid_constant__ CUtensorMap tm_c64,
     const float usc = __uint_as_float((uint32_t)(e_u + 127) << 23);
     u_unscale = __uint_as_float((uint32_t)(127 - e_u) << 23);
     {
-      const float* urow = u + r * 4096;
-      int p = col_tile * NT + grp * 64;
-      int ri = 0, rb = 0;
-      while (ri < 63 && p >= rb + (64 - ri)) { rb += 64 - ri; ++ri; }
-      int cj = ri + (p - rb);
-      auto next = [&]() -> float {
-        float v = 0.f;
-        if (r < n && p < h64::NPACK) {
-          v = __ldg(urow + ri * 64 + cj);
-          if (cj != ri) v += __ldg(urow + cj * 64 + ri);
-        }
-        ++p; ++cj;
-        if (cj == 64) { ++ri; cj = ri; }
-        return v;
-      };
+      const float4* urow = reinterpret_cast<const float4*>(up + r * h64::NPAD + col_tile * NT + grp * 64);
       uint32_t h[32], l[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e0 = next();
-        const float e1 = next();
-        split_pair(e0 * usc, e1 * usc, h[i], l[i]);
+      for (int i = 0; i < 16; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) v = __ldg(urow + i);
+        split_pair(v.x * usc, v.y * usc, h[2 * i], l[2 * i]);
+        split_pair(v.z * usc, v.w * usc, h[2 * i + 1], l[2 * i + 1]);
       }
       TMEM_ST32(tmem_base + lane_addr + TM_UHI + grp * 32, h);
       TMEM_ST32(tmem_base + lane_addr + TM_ULO + grp * 32, l);
@@ -1245,7 +1263,8 @@ static int launch_g64(const rlvae_tables* t, const float* z, const float* u, con
 }
 
 int64_t metric_grad_h64_scratch_floats(int64_t n) {
-  return n * (int64_t)(tc::g64::NTILES * 64) + ((n + 3) & ~(int64_t)3);     // partial tiles + per-point exponents
+  return n * (int64_t)(tc::g64::NTILES * 64) + ((n + 3) & ~(int64_t)3) +      // partial tiles + per-point exponents
+         n * (int64_t)tc::h64::NPAD;                                           // + packed Ut
 }
 
 bool metric_grad_h64_available(const rlvae_tables* t) {
@@ -1264,11 +1283,12 @@ int launch_metric_grad_h64(const rlvae_tables* t, const float* z, const float* u
                 "tensor path needs 16-byte aligned z, u, out and workspace");
   float* partial = scratch;
   int* eu = reinterpret_cast<int*>(scratch + n * (int64_t)(tc::g64::NTILES * 64));
-  const unsigned g1 = (unsigned)((n + 7) / 8 < 2368 ? (n + 7) / 8 : 2368);
-  tc::u_scale64_kernel<<<g1, 256, 0, s>>>(u, n, eu);
+  float* up = scratch + n * (int64_t)(tc::g64::NTILES * 64) + ((n + 3) & ~(int64_t)3);
+  const unsigned g1 = (unsigned)(n < 148 * 64 ? n : 148 * 64);
+  tc::pack_u64_kernel<<<g1, 256, 0, s>>>(u, n, up, eu);
   RLVAE_LAUNCH_OK();
-  if (int rc = h64_use_pairs() ? launch_g64<true>(t, z, u, eu, n, scale, partial, s)
-                               : launch_g64<false>(t, z, u, eu, n, scale, partial, s))
+  if (int rc = h64_use_pairs() ? launch_g64<true>(t, z, up, eu, n, scale, partial, s)
+                               : launch_g64<false>(t, z, up, eu, n, scale, partial, s))
     return rc;
   const int64_t total4 = n * 16;
   tc::reduce_partials64_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(partial, n, tc::g64::NTILES, out);

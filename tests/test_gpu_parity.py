@@ -581,6 +581,44 @@ def test_latent_dim_64_paths():
         assert rel_fro(got.cpu(), ref_ginv[:n]) < TOL_MAT, n
 
 
+def test_latent_dim_64_spd_elimination_and_its_pivoting_fallback():
+    """d = 64, symmetric tables: log det G (elimination of the lower triangle) and G (symmetric sweep) come from the
+    no-pivoting SPD kernel; a batch that mixes positive definite and indefinite G^{-1} must still have
+    torch.linalg.inv / slogdet semantics (ref metric_tensor.py:152,175) -- the indefinite ones go through the fallback
+    list to the pivoting Gauss-Jordan.  The log-det-only request and the request with G take different variants."""
+    gen = torch.Generator().manual_seed(33)
+    K, d = 96, 64
+    q, _ = torch.linalg.qr(torch.randn(d, d, generator=gen))
+    c = torch.randn(K, d, generator=gen)
+    sign = torch.ones(d); sign[d // 2:] = -1.0
+    dk = 0.05 * (0.5 + torch.rand(K, d, generator=gen))
+    dk = torch.where((c[:, :1] > 0), dk * sign, dk)
+    M = torch.einsum('ij,kj,lj->kil', q, dk, q)
+    M = 0.5 * (M + M.transpose(1, 2))
+    t = (c, M, 6.0, 0.01)
+    z = torch.randn(301, d, generator=gen)
+    z[:100, 0] += 9.0       # dominated by indefinite centroids
+    z[100:200, 0] -= 9.0    # dominated by positive definite centroids
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=16)
+    ev_min = torch.linalg.eigvalsh(ref_ginv.double())[:, 0]
+    assert (ev_min < 0).sum() > 50 and (ev_min > 0).sum() > 50
+    ref_g = torch.linalg.inv(ref_ginv.double())
+    sl = torch.linalg.slogdet(ref_g)
+    good = torch.linalg.cond(ref_ginv.double()) < 500      # fp32 inverse error ~ cond * eps
+    assert (good & (ev_min < 0)).sum() > 30 and (good & (ev_min > 0)).sum() > 100
+    for path in paths_for(t):
+        mt = make_mt(t, path)
+        only_ld = mt.evaluate(z.to(dev()), want_ginv=True, want_logdet=True)
+        assert rel_fro(only_ld['ginv'].cpu(), ref_ginv) < TOL_MAT, path
+        close_ld(only_ld['logdet_g'].cpu()[good], sl.logabsdet[good].float())
+        ev = mt.evaluate(z.to(dev()), want_ginv=True, want_g=True, want_logdet=True)
+        assert rel_fro(ev['g'].cpu()[good], ref_g[good].float()) < 2e-4, path
+        close_ld(ev['logdet_g'].cpu()[good], sl.logabsdet[good].float())
+        # positive definite rows: both variants agree with each other to rounding
+        pd = ev_min > 0
+        close_ld(ev['logdet_g'].cpu()[pd], only_ld['logdet_g'].cpu()[pd], 1e-5)
+
+
 def test_latent_dim_64_large_k_tensor_vs_direct():
     """d = 64 with K = 5,000 centroids: the tensor kernel against the direct kernel on 512 points."""
     from rlvae_b200.synthetic import make_points, make_synthetic_metric
