@@ -83,7 +83,10 @@ constexpr uint32_t OFF_STATE = OFF_A1;
 static_assert(TILE_M * ST_LD * 4 <= 2 * A_BYTES, "HMC state rows must fit the A-tile region");
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t OFF_HYB = (OFF_TMEM_PTR + 16 + 15) & ~15u;   // HYBRID only: one scratch row per exp warp (8 warps)
+constexpr uint32_t OFF_HYBC = OFF_HYB + 8 * HYB_ROW_BYTES;      // HYBRID only: natural fp32 rows of the block's 64 centroids, per C stage
+constexpr uint32_t SMEM_BYTES_HYB = OFF_HYBC + C_STAGES * BK * 64 + 1024;
+static_assert(OFF_HYB % 16 == 0 && SMEM_BYTES_HYB <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_SP = 0;        // + buf*64
 constexpr uint32_t TM_ACC = 192;     // + buf*160
 constexpr uint32_t TM_ZHI = 336;     // z (tf32 hi) 16 columns: A operand of GEMM1, in the hole between the accumulators
@@ -404,7 +407,12 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
               tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
               tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
             }
-            mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+            if (HYBRID) {   // + the natural rows of the block (4 KB): the refinement reads them from shared memory
+              mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES + BK * 64);
+              bulk_load_1d(base + h16::OFF_HYBC + cs * (BK * 64), cnat + (int64_t)j * BK * 16, BK * 64, BAR_BIAS_FULL(cs));
+            } else {
+              mbar_expect_tx(BAR_BIAS_FULL(cs), BIAS_BYTES);
+            }
           }
           bulk_load_1d(base + h16::OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_BIAS_FULL(cs));
         }
@@ -547,6 +555,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     reg_dec<104>();
     const int grp = wg - 1;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    // HYBRID: this lane's scratch row (the launch adds HYB_BYTES of shared memory behind the barriers)
+    float* hyb_row = reinterpret_cast<float*>(gbase + h16::OFF_HYB + (warp - 4) * HYB_ROW_BYTES) + lane * 4;
+    (void)hyb_row;
     long long pe_wait = 0, pe_work = 0;
     (void)pe_wait; (void)pe_work;
     // COLSPLIT: both groups work on every super-block, 32 centroids each (halves the latency between
@@ -613,8 +624,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                 live |= (ex > hyb_thr ? 1u : 0u) << i;
               }
             }
-            refine_exponents(s, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
-                             -alpha, P_SHIFT);
+            refine_exponents(s, live,
+                             reinterpret_cast<const float4*>(gbase + h16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
+                             -alpha, P_SHIFT, hyb_row);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float w0 = ex2_approx(__uint_as_float(s[4 * q])), w1 = ex2_approx(__uint_as_float(s[4 * q + 1]));
@@ -999,7 +1011,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 }
 
 
-// HYBRID mode of the gradient kernel.  Like refine_exponents, the pairs flagged in `live` get their exponent from
+// HYBRID mode of the gradient kernel (crows: the block's natural rows in shared memory).  Like refine_exponents, the pairs flagged in `live` get their exponent from
 // exact differences -- and, because those are exactly the pairs whose weight is not negligible, i.e. the centroids
 // NEAR the point, their whole contribution u (c_k - z) is accumulated here from the exact difference vector and
 // taken out of the tensor contraction (exponent -> -1e30 -> u = 0 for GEMM3 and for sum_k u).  The contraction's
@@ -1007,9 +1019,9 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 // measured against fp64); with the near pairs handled here only far pairs go through it, where nothing cancels.
 __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t (&tv)[32], uint32_t live,
                                               const float4* __restrict__ crows, const float2 (&nz)[8], float neg_alpha,
-                                              float shift, float2 (&direct)[8]) {
+                                              float shift, float2 (&direct)[8], float* row) {
+  // (the caller has already set the flagged exponents to -1e30: they leave the contraction whatever happens here)
   if (!__any_sync(0xffffffffu, live != 0u)) return;
-  constexpr uint32_t NEG_BIG = 0xf149f2cau;        // -1e30f
   const int total = __reduce_add_sync(0xffffffffu, __popc(live));
   if (total > 160) {                               // dense tile: uniform sweep, broadcast loads
 #pragma unroll
@@ -1018,7 +1030,7 @@ __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 c = __ldg(crows + i * 4 + q);
+        const float4 c = crows[i * 4 + q];
         dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
         dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
         ffma2_acc(acc, dv[2 * q], dv[2 * q]);
@@ -1029,11 +1041,12 @@ __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t
         const float2 u2 = make_float2(uv, uv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
-        ex[i] = NEG_BIG;
       }
     }
     return;
   }
+  // sparse: t_k of the lane's flagged centroid is read from the lane's shared-memory row (run-time index)
+  hyb_row_spill(row, tv);
   while (__any_sync(0xffffffffu, live != 0u)) {
     if (live != 0u) {
       const int b = __ffs(live) - 1;
@@ -1042,21 +1055,16 @@ __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 c = __ldg(crows + b * 4 + q);
+        const float4 c = crows[b * 4 + q];
         dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
         dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
         ffma2_acc(acc, dv[2 * q], dv[2 * q]);
         ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
       }
-      uint32_t tb = 0u;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tb = (i == b) ? tv[i] : tb;
-      const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tb);
+      const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * row[hyb_row_word(b)];
       const float2 u2 = make_float2(uv, uv);
 #pragma unroll
       for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) ex[i] = (i == b) ? NEG_BIG : ex[i];
     }
   }
 }
@@ -1094,7 +1102,10 @@ constexpr uint32_t OFF_BAR = OFF_BIAS + C_STAGES * BIAS_BYTES;
 constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t OFF_HYB = (OFF_TMEM_PTR + 16 + 15) & ~15u;   // HYBRID only: one scratch row per exp warp (8 warps)
+constexpr uint32_t OFF_HYBC = OFF_HYB + 8 * HYB_ROW_BYTES;      // HYBRID only: natural fp32 rows of the block's 64 centroids, per C stage
+constexpr uint32_t SMEM_BYTES_HYB = OFF_HYBC + C_STAGES * BK * 64 + 1024;
+static_assert(OFF_HYB % 16 == 0 && SMEM_BYTES_HYB <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400, TM_ZHI = 464, TM_ZLO = 480;
 constexpr int RED_LD = 20;
 }  // namespace g16
@@ -1344,7 +1355,12 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
             tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
           }
-          mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
+          if (HYBRID) {     // + the natural rows of the block (4 KB): the refinement reads them from shared memory
+            mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES + BK * 64);
+            bulk_load_1d(base + g16::OFF_HYBC + cs * (BK * 64), cnat + (int64_t)j * BK * 16, BK * 64, BAR_B_FULL(cs));
+          } else {
+            mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
+          }
         }
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
       }
@@ -1500,6 +1516,8 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
     float2 direct[8];                    // HYBRID: sum of u (c_k - z) over the near pairs, from exact differences
 #pragma unroll
     for (int q = 0; q < 8; ++q) direct[q] = make_float2(0.f, 0.f);
+    float* hyb_row = reinterpret_cast<float*>(gbase + g16::OFF_HYB + (warp - 2) * HYB_ROW_BYTES) + lane * 4;
+    (void)hyb_row;
     auto fold_chunk = [&](int c, bool signal) {
       uint32_t a[16];
       TMEM_LD16(tmem_base + lane_addr + TM_OUT + (c & 1) * 32, a);
@@ -1547,16 +1565,20 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             for (int e = 0; e < 4; ++e) {
               const int i = 4 * q + e;
               const float ex = fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb);
-              live |= (ex > hyb_thr ? 1u : 0u) << i;
-              sv[i] = __float_as_uint(ex);
+              const bool near = ex > hyb_thr;
+              live |= (near ? 1u : 0u) << i;
+              // near pairs leave the contraction (refine_direct adds them from exact differences)
+              sv[i] = (near && u_packed != 2) ? 0xf149f2cau /* -1e30f */ : __float_as_uint(ex);
             }
           }
           if (u_packed == 2)      // unit-weight mode: the table behind the contraction is not the centroids
-            refine_exponents(sv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
-                             -alpha, 0.f);
+            refine_exponents(sv, live,
+                             reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
+                             -alpha, 0.f, hyb_row);
           else
-            refine_direct(sv, tv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
-                          -alpha, 0.f, direct);
+            refine_direct(sv, tv, live,
+                          reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
+                          -alpha, 0.f, direct, hyb_row);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
@@ -2012,13 +2034,13 @@ template <bool PAIR, bool EXACT, bool HYBRID = false, bool HMC = false>
 static int launch_h16(const rlvae_tables* t, const float* z, int64_t n, const tc::FusedOut& fo, cudaStream_t s,
                       const tc::HmcArgs& hm = tc::HmcArgs{}) {
   auto kern = tc::inverse_metric_h16_kernel<PAIR, EXACT, HYBRID, HMC>;
-  RLVAE_OPT_IN_SMEM(kern, (int)tc::h16::SMEM_BYTES);
+  RLVAE_OPT_IN_SMEM(kern, (int)(HYBRID ? tc::h16::SMEM_BYTES_HYB : tc::h16::SMEM_BYTES));
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles, 1, 1);
   cfg.blockDim = dim3(tc::h16::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = tc::h16::SMEM_BYTES;
+  cfg.dynamicSmemBytes = HYBRID ? tc::h16::SMEM_BYTES_HYB : tc::h16::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2135,13 +2157,13 @@ template <bool PAIR, bool EXACT, bool HYBRID = false>
 static int launch_g16(const rlvae_tables* t, const float* z, const float* u, int64_t n, float scale, float* out,
                       cudaStream_t s, int u_packed) {
   auto kern = tc::metric_grad_h16_kernel<PAIR, EXACT, HYBRID>;
-  RLVAE_OPT_IN_SMEM(kern, (int)tc::g16::SMEM_BYTES);
+  RLVAE_OPT_IN_SMEM(kern, (int)(HYBRID ? tc::g16::SMEM_BYTES_HYB : tc::g16::SMEM_BYTES));
   unsigned tiles = (unsigned)((n + tc::TILE_M - 1) / tc::TILE_M);
   if (PAIR) tiles = (tiles + 1) & ~1u;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles, 1, 1);
   cfg.blockDim = dim3(tc::g16::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = tc::g16::SMEM_BYTES;
+  cfg.dynamicSmemBytes = HYBRID ? tc::g16::SMEM_BYTES_HYB : tc::g16::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
