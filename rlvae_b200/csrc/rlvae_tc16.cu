@@ -1017,10 +1017,11 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 // taken out of the tensor contraction (exponent -> -1e30 -> u = 0 for GEMM3 and for sum_k u).  The contraction's
 // form sum_k u c~_k - z~ sum_k u loses |c~| / |c_k - z| digits next to a centroid (1.2e-4 relative at T = 0.1,
 // measured against fp64); with the near pairs handled here only far pairs go through it, where nothing cancels.
-__device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t (&tv)[32], uint32_t live,
-                                              const float4* __restrict__ crows, const float2 (&nz)[8], float neg_alpha,
-                                              float shift, float2 (&direct)[8], float* row) {
-  // (the caller has already set the flagged exponents to -1e30: they leave the contraction whatever happens here)
+__device__ __forceinline__ void refine_direct(uint32_t live, const float4* __restrict__ crows, const float2 (&nz)[8],
+                                              float neg_alpha, float shift, float2 (&direct)[8], const float* row) {
+  // The caller has already set the flagged exponents to -1e30 (they leave the contraction whatever happens here)
+  // and, if any lane of the warp has a flagged pair, spilled the thread's 32 t_k into its shared-memory row: this
+  // function only ADDS to `direct`, so the gradient kernel runs it after u has been handed to the tensor pipe.
   if (!__any_sync(0xffffffffu, live != 0u)) return;
   const int total = __reduce_add_sync(0xffffffffu, __popc(live));
   if (total > 160) {                               // dense tile: uniform sweep, broadcast loads
@@ -1037,7 +1038,7 @@ __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t
         ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
       }
       if ((live >> i) & 1u) {
-        const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tv[i]);
+        const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * row[hyb_row_word(i)];
         const float2 u2 = make_float2(uv, uv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
@@ -1045,8 +1046,6 @@ __device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t
     }
     return;
   }
-  // sparse: t_k of the lane's flagged centroid is read from the lane's shared-memory row (run-time index)
-  hyb_row_spill(row, tv);
   while (__any_sync(0xffffffffu, live != 0u)) {
     if (live != 0u) {
       const int b = __ffs(live) - 1;
@@ -1545,6 +1544,9 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tc_fence_after();
       PROF_ADD(pe_wait);
       float su_blk = 0.f;                // sum of u over this super-block (two-level fp32 summation)
+      uint32_t live_def = 0u;            // HYBRID: near pairs whose exact contribution is added after the hand-off
+      const float4* crows_def = nullptr;
+      (void)live_def; (void)crows_def;
 #pragma unroll
       for (int rr = 0; rr < (COLSPLIT ? 1 : 2); ++rr) {
         const int rnd = COLSPLIT ? grp : rr;
@@ -1571,14 +1573,14 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
               sv[i] = (near && u_packed != 2) ? 0xf149f2cau /* -1e30f */ : __float_as_uint(ex);
             }
           }
-          if (u_packed == 2)      // unit-weight mode: the table behind the contraction is not the centroids
-            refine_exponents(sv, live,
-                             reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
-                             -alpha, 0.f, hyb_row);
-          else
-            refine_direct(sv, tv, live,
-                          reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
-                          -alpha, 0.f, direct, hyb_row);
+          const float4* crows = reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4;
+          if (u_packed == 2) {    // unit-weight mode: the table behind the contraction is not the centroids
+            refine_exponents(sv, live, crows, nz, -alpha, 0.f, hyb_row);
+          } else {
+            if (__any_sync(0xffffffffu, live != 0u)) hyb_row_spill(hyb_row, tv);      // t_k for refine_direct
+            if (COLSPLIT) { live_def = live; crows_def = crows; }                      // deferred: see below
+            else refine_direct(live, crows, nz, -alpha, 0.f, direct, hyb_row);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
@@ -1612,10 +1614,14 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
-        mbar_arrive(BAR_C_EMPTY(cs));
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb)); }
+      if (HYBRID && COLSPLIT && u_packed != 2) {
+        // the near pairs are out of the contraction already (exponent -1e30): their exact contribution only adds to
+        // registers, so it runs AFTER u went to the tensor pipe -- off the T-GEMM(j) -> GEMM3(j) critical path
+        refine_direct(live_def, crows_def, nz, -alpha, 0.f, direct, hyb_row);
+        __syncwarp();
       }
+      if (lane == 0) mbar_arrive(BAR_C_EMPTY(cs));       // (after the refinement: it reads the stage's natural rows)
       PROF_ADD(pe_work);
       while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
         mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);
