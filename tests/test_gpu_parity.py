@@ -617,6 +617,14 @@ def test_latent_dim_64_spd_elimination_and_its_pivoting_fallback():
         # positive definite rows: both variants agree with each other to rounding
         pd = ev_min > 0
         close_ld(ev['logdet_g'].cpu()[pd], only_ld['logdet_g'].cpu()[pd], 1e-5)
+        # batches smaller than one CTA of the per-matrix kernel (4 matrices), mixed definite / indefinite
+        for lo, n in ((0, 1), (98, 3), (198, 5)):
+            small = mt.evaluate(z[lo:lo + n].to(dev()), want_ginv=True, want_g=True, want_logdet=True)
+            sel = good[lo:lo + n]
+            if sel.any():
+                assert rel_fro(small['g'].cpu()[sel], ref_g[lo:lo + n][sel].float()) < 2e-4, (path, n)
+                close_ld(small['logdet_g'].cpu()[sel], sl.logabsdet[lo:lo + n][sel].float())
+            assert rel_fro(small['ginv'].cpu(), ref_ginv[lo:lo + n]) < TOL_MAT, (path, n)
 
 
 def test_latent_dim_64_large_k_tensor_vs_direct():
