@@ -163,6 +163,38 @@ class RHVAEStyleHMCSampler(BaseRiemannianSampler):
             done += it
         return z
 
+    def hmc_sampling_batches(self, sizes) -> torch.Tensor:
+        """``hmc_sampling(b)`` for every b in ``sizes`` -- what pythae's ``RHVAESampler.sample`` loops over (ref
+        src/lib/src/pythae/samplers/manifold_sampler/rhvae_sampler.py:61-67) -- as ONE library call per group of
+        batches.  Chains are independent: the only thing that ties a chain to its batch is the ORDER of the random
+        draws, so the draws are made here batch by batch exactly as the sequential loop makes them (start centroids
+        :100, then per MCMC iteration gamma :107 and acc :141) into slices of the stacked streams; with the same
+        generator state the samples are those of the sequential loop, at the cost of one batch."""
+        sizes = [int(b) for b in sizes if int(b) > 0]
+        dev, d, steps = self.device, self.model.latent_dim, self.mcmc_steps_nbr
+        k_cent = len(self.model.centroids_tens)
+        per_call = max(1, (1 << 26) // max(steps * (d + 1), 1))      # chains per call: <= ~256 MB of draws
+        out, i = [], 0
+        while i < len(sizes):
+            grp, tot = [], 0
+            while i < len(sizes) and (not grp or tot + sizes[i] <= per_call):
+                grp.append(sizes[i]); tot += sizes[i]; i += 1
+            if len(grp) == 1:
+                out.append(self.hmc_sampling(grp[0]))
+                continue
+            idx = torch.empty(tot, dtype=torch.long, device=dev)
+            gammas = torch.empty(steps, tot, d, device=dev)
+            accs = torch.empty(steps, tot, device=dev)
+            lo = 0
+            for b in grp:
+                idx[lo:lo + b] = torch.randint(k_cent, (b,), device=dev)
+                for it in range(steps):
+                    gammas[it, lo:lo + b].normal_()
+                    accs[it, lo:lo + b].uniform_()
+                lo += b
+            out.append(self.hmc_sampling_with_streams(idx, gammas, accs))
+        return torch.cat(out, dim=0) if out else torch.empty(0, d, device=dev)
+
     # ------------------------------------------------------------------ BaseRiemannianSampler surface
     def sample_prior(self, num_samples: int, method: str = 'official') -> torch.Tensor:
         return self.hmc_sampling(num_samples).detach()
@@ -269,13 +301,12 @@ class OfficialRHVAESampler(BaseRiemannianSampler):
         if self._rhvae_sampler is None:
             self.setup_official_rhvae()
         bs = min(self.PRIOR_BATCH, num_samples)
-        out = []
+        if bs <= 0:
+            return torch.empty(0, self.model.latent_dim, device=self.device)
+        sizes = [bs] * (num_samples // bs) + ([num_samples % bs] if num_samples % bs else [])
         with torch.no_grad():
-            for _ in range(num_samples // bs):                       # pythae RHVAESampler.sample :61-67
-                out.append(self._rhvae_sampler.hmc_sampling(bs))
-            if num_samples % bs:
-                out.append(self._rhvae_sampler.hmc_sampling(num_samples % bs))
-        return torch.cat(out, dim=0)
+            # the batches of pythae RHVAESampler.sample :61-67, drawn in its order, run as one library call
+            return self._rhvae_sampler.hmc_sampling_batches(sizes)
 
     def get_sampling_methods(self) -> Dict[str, str]:
         return {'official': 'Official RHVAE sampling with HMC',

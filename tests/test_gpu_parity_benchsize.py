@@ -305,6 +305,16 @@ def test_prior_samplers_and_official_sampler_match_the_reference():
     zp = off.sample_prior(40)                                  # test_pythae_variant_hmc_matches_reference_chain
     assert zp.shape == (40, 16) and torch.isfinite(zp).all()
     assert off.sample_prior(5, method='basic').shape == (5, 16)
+    # the 32-chain batches run as ONE library call with the draws made in the sequential loop's order: same generator
+    # state -> the samples of the batch-by-batch loop (pythae RHVAESampler.sample :61-67)
+    off._rhvae_sampler.mcmc_steps_nbr = 4
+    torch.manual_seed(1234)
+    merged = off.sample_prior(100)
+    torch.manual_seed(1234)
+    seq = torch.cat([off._rhvae_sampler.hmc_sampling(b) for b in (32, 32, 32, 4)])
+    assert merged.shape == (100, 16)
+    same = ((merged - seq).abs().max(dim=1).values < 1e-4)
+    assert same.float().mean() >= 0.97, same.float().mean()       # (a borderline accept may flip a chain)
 
 
 def test_d64_tensor_gradient_kernel_general_u_and_tile_tails():
