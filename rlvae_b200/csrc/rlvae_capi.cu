@@ -942,7 +942,11 @@ int rlvae_pythae_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   float* scratch = w + 2 * mat;
   // (d = 64 tensor forward: its packed tiles live in the third slot of the workspace)
   if (int rc = inverse_metric_full(t, z, n, ginv, path, s, scratch)) return rc;
-  if (int rc = launch_batched_inverse(ginv, n, d, g, logabsdet, sign, nullptr, 0, s)) return rc;
+  if (d == 64 && t->symmetric) {       // SPD sweep; the third slot is free again and holds its fallback list
+    if (int rc = launch_spd64(ginv, n, g, logabsdet, 1.f, reinterpret_cast<int*>(scratch), s, sign, nullptr)) return rc;
+  } else if (int rc = launch_batched_inverse(ginv, n, d, g, logabsdet, sign, nullptr, 0, s)) {
+    return rc;
+  }
   // (the third slot, n * (d*d + d) floats, is free again: partial sums of the split-centroid launch)
   return launch_pythae_exact(t, z, g, 0, nullptr, nullptr, n, grad, d >= kPythaeMaxSplits ? scratch : nullptr, s);
 }
@@ -993,7 +997,7 @@ int rlvae_metric_eval(const rlvae_tables_t* t, const float* z, int64_t n, float*
   bool lad_done = false;
   if ((plain_g || logdet_g != nullptr) && d == 64 && t->symmetric) {
     // symmetric tables: G^{-1} is symmetric positive definite -> register-resident elimination / sweep without
-    // pivoting or staging (spd64_kernel); the few matrices that are not PD re-run through the pivoting kernel.
+    // pivoting or staging (spd64_logdet_kernel / spd64_inverse_kernel); the few matrices that are not PD re-run through the pivoting kernel.
     // (The G^T slot is free here: the packed tiles were consumed by the unpack, the gradient kernel comes later.)
     if (int rc = launch_spd64(a_buf, n, plain_g ? g_buf : nullptr, logdet_g, -1.f, reinterpret_cast<int*>(gt_buf), s))
       return rc;
@@ -1146,7 +1150,14 @@ int rlvae_hmc_iteration(const rlvae_tables_t* t, float* z, const float* gamma, c
     }
     if (int rc = inverse_metric_full(t, zz, n, ginv, path, s, gfull)) return rc;   // gfull doubles as the d = 64 scratch
     // exact mode wants G^T for the contraction (see rlvae_metric_eval)
-    if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) return rc;
+    if (d == 64 && t->symmetric) {
+      // symmetric tables: G^{-1} is SPD -> no-pivoting sweep (diag G, log det, sign = 1; G^T == G); the gradient
+      // slot is free until the contraction below and holds the fallback list
+      if (int rc = launch_spd64(ginv, n, exact ? gfull : nullptr, lad, 1.f, reinterpret_cast<int*>(gex), s, sgn, diag))
+        return rc;
+    } else if (int rc = launch_batched_inverse(ginv, n, d, exact ? gfull : nullptr, lad, sgn, diag, 1, s)) {
+      return rc;
+    }
     if (exact)  // grad_z 1/2 log det G^{-1} = (1/T^2) sum_k w_k tr(G M_k)(c_k - z)
       if (int rc = rlvae_metric_grad(t, zz, gfull, n, 1.f / t->T2, gex, path, stream)) return rc;
     return 0;

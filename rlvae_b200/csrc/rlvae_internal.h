@@ -164,7 +164,7 @@ int launch_batched_inverse(const float* a, int64_t n, int d, float* inv, float* 
 // 64 x 64 symmetric positive definite batch (no pivoting; failures re-run through the pivoting kernel):
 // inv optional, logabsdet = lad_scale * log det, fail_ws = 1 + n ints
 int launch_spd64(const float* a, int64_t n, float* inv, float* logabsdet, float lad_scale, int* fail_ws,
-                 cudaStream_t s);
+                 cudaStream_t s, float* sign = nullptr, float* diag_inv = nullptr);
 int launch_batched_inverse_packed16(const float* a_packed, int64_t n, float* inv, float* logabsdet,
                                     float* sign, float* diag_inv, int transpose_inv, cudaStream_t s);
 int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStream_t s);

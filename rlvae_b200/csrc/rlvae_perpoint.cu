@@ -636,6 +636,11 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
   return 0;
 }
 
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // ---------------------------------------------------------------------------------------- SPD 64 x 64
 // Symmetric positive definite 64 x 64 matrices (G^{-1} of symmetric tables at latent_dim 64): log det and,
 // optionally, the inverse WITHOUT pivoting, one warp per matrix, rows lane / lane + 32 in registers.
@@ -645,25 +650,25 @@ int launch_unpack_sym16(const float* a_packed, int64_t n, float* full, cudaStrea
 //   * the Schur complement of an SPD matrix stays symmetric, so the pivot ROW every elimination step needs is
 //     the pivot COLUMN the lanes already hold: two shared-memory stores per lane + broadcast reads replace the
 //     64 shuffles per step of batched_inverse_kernel, and there is no pivot search.
-//   WANT_INV == false: Gaussian elimination of the lower triangle only (2512 FMAs per lane), log det = sum of
-//     the log pivots.  WANT_INV == true: the symmetric sweep operator (pivot d: a_jj <- -1/d, a_ij <- a_ij/d,
+//   spd64_logdet_kernel: Gaussian elimination of the lower triangle only (2512 FMAs per lane), log det = sum of
+//     the log pivots.  spd64_inverse_kernel: the symmetric sweep operator (pivot d: a_jj <- -1/d, a_ij <- a_ij/d,
 //     a_ik <- a_ik - a_ij a_jk / d) applied to all 64 pivots leaves -A^{-1}.
 // A pivot that is not > 0 (not positive definite, or NaN) appends the matrix to `fail` (fail[0] = count,
 // fail[1..] = indices); the caller re-runs those through the pivoting Gauss-Jordan (torch.linalg.inv /
 // slogdet semantics, ref src/models/components/metric_tensor.py:152,175).
-template <bool WANT_INV>
-__global__ void __launch_bounds__(128, WANT_INV ? 2 : 3)
-spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, float* __restrict__ logabsdet,
-             float lad_scale, int* __restrict__ fail) {
+// ---- log det only: elimination of the lower triangle, fully unrolled (4.2 k instructions per matrix)
+__global__ void __launch_bounds__(128, 3)
+spd64_logdet_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ logabsdet, float lad_scale,
+                    int* __restrict__ fail) {
   __shared__ __align__(16) float colbuf[4][2][64];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t mat = (int64_t)blockIdx.x * 4 + wrp;
   if (mat >= n) return;                                    // (warp-uniform; no block-wide barrier below)
   const float* src = a + mat * 4096;
-  float r0[64], r1[64];
+  float r0[32], r1[64];                                    // row lane needs columns <= 31 only
 #pragma unroll
   for (int k = 0; k < 64; ++k) {
-    r0[k] = (WANT_INV || k < 32) ? __ldg(src + k * 64 + lane) : 0.f;     // A[lane][k] == A[k][lane]
+    if (k < 32) r0[k] = __ldg(src + k * 64 + lane);        // A[lane][k] == A[k][lane]
     r1[k] = __ldg(src + k * 64 + 32 + lane);
   }
   float lad = 0.f, prod = 1.f;
@@ -671,7 +676,7 @@ spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, fl
 #pragma unroll
   for (int j = 0; j < 64; ++j) {
     float* col = colbuf[wrp][j & 1];
-    col[lane] = r0[j];                                     // (lower-triangle variant, j >= 32: never read)
+    if (j < 32) col[lane] = r0[j];
     col[lane + 32] = r1[j];
     __syncwarp();
     const float d = col[j];
@@ -679,46 +684,19 @@ spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, fl
     const float dinv = 1.f / d;
     prod *= d;
     if ((j & 7) == 7) { lad += logf(prod); prod = 1.f; }
-    if (WANT_INV) {
-      // the pivot row becomes col / d, every other row r - (r_j / d) col: one FMA per entry, plus one select per
-      // entry in the slot that can hold the pivot row (known at compile time)
-      const bool own0 = (j < 32) && (lane == j), own1 = (j >= 32) && (lane == j - 32);
-      const float f0 = r0[j] * dinv, f1 = r1[j] * dinv;
-      const float x0 = own0 ? dinv : -f0, x1 = own1 ? dinv : -f1;
+    // rows <= j are finished: their multipliers are garbage, but they only touch entries above the diagonal,
+    // which nothing reads
+    const float f0 = (j < 31) ? r0[j] * dinv : 0.f, f1 = r1[j] * dinv;
 #pragma unroll
-      for (int k4 = 0; k4 < 64; k4 += 4) {
-        const float4 c = *reinterpret_cast<const float4*>(col + k4);
-        const float cv[4] = {c.x, c.y, c.z, c.w};
+    for (int k4 = ((j + 1) & ~3); k4 < 64; k4 += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(col + k4);
+      const float cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = k4 + q;
-          if (k == j) continue;
-          if (j < 32) {
-            r0[k] = fmaf(x0, cv[q], own0 ? 0.f : r0[k]);
-            r1[k] = fmaf(x1, cv[q], r1[k]);
-          } else {
-            r0[k] = fmaf(x0, cv[q], r0[k]);
-            r1[k] = fmaf(x1, cv[q], own1 ? 0.f : r1[k]);
-          }
-        }
-      }
-      r0[j] = own0 ? -dinv : f0;
-      r1[j] = own1 ? -dinv : f1;
-    } else {
-      // rows <= j are finished: their multipliers are garbage, but they only touch entries above the diagonal,
-      // which nothing reads
-      const float f0 = (j < 31) ? r0[j] * dinv : 0.f, f1 = r1[j] * dinv;
-#pragma unroll
-      for (int k4 = ((j + 1) & ~3); k4 < 64; k4 += 4) {
-        const float4 c = *reinterpret_cast<const float4*>(col + k4);
-        const float cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = k4 + q;
-          if (k <= j) continue;
-          if (k < 32) r0[k] = fmaf(-f0, cv[q], r0[k]);
-          r1[k] = fmaf(-f1, cv[q], r1[k]);
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int k = k4 + q;
+        if (k <= j) continue;
+        if (k < 32) r0[k] = fmaf(-f0, cv[q], r0[k]);
+        r1[k] = fmaf(-f1, cv[q], r1[k]);
       }
     }
   }
@@ -729,7 +707,93 @@ spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, fl
     }
     return;
   }
-  if (WANT_INV) {
+  if (lane == 0) logabsdet[mat] = lad_scale * lad;
+}
+
+// ---- inverse (+ log det, sign, diagonal): the symmetric sweep.  Fully unrolled it is 14.5 k instructions (232 KB of
+// straight-line code per matrix) and bound by instruction FETCH (ncu: `no_instruction` 4.2 stalls per issue), so the
+// pivots go in groups of 8: inside a group the pivot column is register u (compile time), between groups the
+// column registers rotate by 8 -- register m holds column (m + j0) mod 64, and the shared-memory column is written
+// at the rotated position, so its reads stay compile-time 128-bit loads.  SLOT = the row slot that holds the pivot
+// rows of this half of the sweep (rows 0..31: slot 0), which keeps the pivot-row select out of the other slot.
+template <int SLOT>
+__device__ __forceinline__ void spd64_sweep_group(float (&r0)[64], float (&r1)[64], float* colw, int j0, int lane,
+                                                  float& lad, bool& bad) {
+  float prod = 1.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float* col = colw + (u & 1) * 64;
+    col[(lane - j0) & 63] = r0[u];
+    col[(lane + 32 - j0) & 63] = r1[u];
+    __syncwarp();
+    const float d = col[u];                                // row j0 + u sits at position u
+    if (!(d > 0.f)) bad = true;
+    const float dinv = 1.f / d;
+    prod *= d;
+    const bool own = lane == ((j0 + u) & 31);              // this lane's SLOT row is the pivot row
+    const float f0 = r0[u] * dinv, f1 = r1[u] * dinv;
+    const float x0 = (SLOT == 0 && own) ? dinv : -f0, x1 = (SLOT == 1 && own) ? dinv : -f1;
+#pragma unroll
+    for (int m4 = 0; m4 < 64; m4 += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(col + m4);
+      const float cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m4 + q;
+        if (m == u) continue;
+        // the pivot row becomes col / d, every other row r - (r_j / d) col
+        if (SLOT == 0) {
+          r0[m] = fmaf(x0, cv[q], own ? 0.f : r0[m]);
+          r1[m] = fmaf(x1, cv[q], r1[m]);
+        } else {
+          r0[m] = fmaf(x0, cv[q], r0[m]);
+          r1[m] = fmaf(x1, cv[q], own ? 0.f : r1[m]);
+        }
+      }
+    }
+    r0[u] = (SLOT == 0 && own) ? -dinv : f0;
+    r1[u] = (SLOT == 1 && own) ? -dinv : f1;
+  }
+  lad += logf(prod);
+  // rotate the column registers by one group
+  float t0[8], t1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { t0[i] = r0[i]; t1[i] = r1[i]; }
+#pragma unroll
+  for (int m = 0; m < 56; ++m) { r0[m] = r0[m + 8]; r1[m] = r1[m + 8]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { r0[56 + i] = t0[i]; r1[56 + i] = t1[i]; }
+}
+
+__global__ void __launch_bounds__(128, 2)
+spd64_inverse_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, float* __restrict__ logabsdet,
+                     float* __restrict__ sign, float* __restrict__ diag_inv, float lad_scale, int* __restrict__ fail) {
+  __shared__ __align__(16) float colbuf[4][2][64];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t mat = (int64_t)blockIdx.x * 4 + wrp;
+  if (mat >= n) return;
+  const float* src = a + mat * 4096;
+  float r0[64], r1[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    r0[k] = __ldg(src + k * 64 + lane);                    // A[lane][k] == A[k][lane]
+    r1[k] = __ldg(src + k * 64 + 32 + lane);
+  }
+  float lad = 0.f;
+  bool bad = false;
+#pragma unroll 1
+  for (int j0 = 0; j0 < 32; j0 += 8) spd64_sweep_group<0>(r0, r1, &colbuf[wrp][0][0], j0, lane, lad, bad);
+#pragma unroll 1
+  for (int j0 = 32; j0 < 64; j0 += 8) spd64_sweep_group<1>(r0, r1, &colbuf[wrp][0][0], j0, lane, lad, bad);
+  // (eight rotations by 8: the registers are back in natural column order; they hold -A^{-1})
+  if (bad) {
+    if (lane == 0) {
+      const int slot = atomicAdd(fail, 1);
+      fail[1 + slot] = (int)mat;
+    }
+    return;
+  }
+  if (inv != nullptr) {
     float* dst = inv + mat * 4096;
 #pragma unroll
     for (int k = 0; k < 64; ++k) {
@@ -737,22 +801,39 @@ spd64_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ inv, fl
       dst[k * 64 + 32 + lane] = -r1[k];
     }
   }
-  if (lane == 0 && logabsdet != nullptr) logabsdet[mat] = lad_scale * lad;
+  if (diag_inv != nullptr) {
+    float* dd = diag_inv + mat * 64;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (lane == k) { dd[k] = -r0[k]; dd[k + 32] = -r1[k + 32]; }
+    }
+  }
+  if (lane == 0) {
+    if (logabsdet != nullptr) logabsdet[mat] = lad_scale * lad;
+    if (sign != nullptr) sign[mat] = 1.f;
+  }
 }
 
-// 64 x 64 SPD batch: inv (optional, [n,64,64]) and lad_scale * log det; `fail_ws`: 1 + n ints.
-// Matrices that are not positive definite fall through to the pivoting Gauss-Jordan.
+// 64 x 64 SPD batch: inv (optional, [n,64,64]), lad_scale * log det, sign (= 1), diag of the inverse (optional);
+// `fail_ws`: 1 + n ints.  Matrices that are not positive definite fall through to the pivoting Gauss-Jordan.
 int launch_spd64(const float* a, int64_t n, float* inv, float* logabsdet, float lad_scale, int* fail_ws,
-                 cudaStream_t s) {
+                 cudaStream_t s, float* sign, float* diag_inv) {
   if (n == 0) return 0;
   RLVAE_REQUIRE(n < ((int64_t)1 << 31), "spd64: batch too large for the fallback list");
   RLVAE_CUDA_OK(cudaMemsetAsync(fail_ws, 0, sizeof(int), s));
   const unsigned grid = (unsigned)((n + 3) / 4);
-  if (inv != nullptr) spd64_kernel<true><<<grid, 128, 0, s>>>(a, n, inv, logabsdet, lad_scale, fail_ws);
-  else spd64_kernel<false><<<grid, 128, 0, s>>>(a, n, nullptr, logabsdet, lad_scale, fail_ws);
+  if (inv != nullptr || diag_inv != nullptr)
+    spd64_inverse_kernel<<<grid, 128, 0, s>>>(a, n, inv, logabsdet, sign, diag_inv, lad_scale, fail_ws);
+  else {
+    spd64_logdet_kernel<<<grid, 128, 0, s>>>(a, n, logabsdet, lad_scale, fail_ws);
+    if (sign != nullptr) {
+      RLVAE_LAUNCH_OK();
+      fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sign, n, 1.f);
+    }
+  }
   RLVAE_LAUNCH_OK();
   const unsigned fgrid = (unsigned)(n / 2 < 296 ? (n + 1) / 2 : 296);
-  batched_inverse_kernel<64><<<fgrid, PP<64>::THREADS, 0, s>>>(a, n, inv, logabsdet, nullptr, nullptr, 0, fail_ws + 1,
+  batched_inverse_kernel<64><<<fgrid, PP<64>::THREADS, 0, s>>>(a, n, inv, logabsdet, sign, diag_inv, 0, fail_ws + 1,
                                                                fail_ws, nullptr, lad_scale, 64);
   RLVAE_LAUNCH_OK();
   return 0;

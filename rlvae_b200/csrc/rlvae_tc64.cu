@@ -13,7 +13,7 @@
 //    S = 2^-(ez+ec) S' is folded into the exponent's FFMA.  Error class: 2^-22 relative to
 //    |z||c|, the same as the 3xTF32 split of the d = 16 kernels.
 // Per 64-centroid super-block and column tile: GEMM1 12 x 32 + GEMM2 12 x 64 = 1152 tensor cycles.
-// The per-point 64 x 64 inverse / log det stays a separate kernel (spd64_kernel, one warp per matrix;
+// The per-point 64 x 64 inverse / log det stays a separate kernel (spd64_*_kernel, one warp per matrix;
 // pivoting fallback batched_inverse_kernel<64>): a 2080-entry matrix does not fit one thread's registers.
 //
 //   TMEM: [0,192) three S/P buffers, [192,320) / [320,448) chunk accumulators (N = 128),
