@@ -18,6 +18,7 @@ There is no CPU fallback: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
+import math
 import warnings
 from typing import Any, Dict, Optional
 
@@ -27,14 +28,28 @@ import torch.nn as nn
 from . import _capi
 
 
+def _pad_cols(z: torch.Tensor, dp: int) -> torch.Tensor:
+    zp = torch.zeros((z.shape[0], dp), device=z.device, dtype=z.dtype)
+    zp[:, :z.shape[1]] = z
+    return zp
+
+
 class _InverseMetricFn(torch.autograd.Function):
     """G^{-1}(z); backward dL/dz = (2/T^2) sum_k w_k <dL/dG^{-1}, M_k> (c_k - z)."""
 
     @staticmethod
     def forward(ctx, z, owner, path):
-        tab = owner._tables(z.device)
         zc = z.detach().contiguous()
-        ctx.tab, ctx.path = tab, path
+        emb = owner._embedded(z.device) if hasattr(owner, '_embedded') else None
+        if emb is not None:
+            # latent_dim without a tensor kernel of its own: evaluated as a block of the zero-padded problem
+            d = zc.shape[1]
+            zp = _pad_cols(zc, emb.d)
+            ctx.tab, ctx.path, ctx.embed_d = emb, path, d
+            ctx.save_for_backward(zp)
+            return _capi.inverse_metric(emb, zp, path)[:, :d, :d].contiguous()
+        tab = owner._tables(z.device)
+        ctx.tab, ctx.path, ctx.embed_d = tab, path, None
         ctx.save_for_backward(zc)
         return _capi.inverse_metric(tab, zc, path)
 
@@ -42,7 +57,14 @@ class _InverseMetricFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         (zc,) = ctx.saved_tensors
         tab = ctx.tab
-        gz = _capi.metric_grad(tab, zc, grad_out.contiguous(), 2.0 / (tab.temperature ** 2), ctx.path)
+        u = grad_out.contiguous()
+        if ctx.embed_d is not None:
+            d = ctx.embed_d
+            up = torch.zeros((u.shape[0], tab.d, tab.d), device=u.device, dtype=u.dtype)
+            up[:, :d, :d] = u
+            gz = _capi.metric_grad(tab, zc, up, 2.0 / (tab.temperature ** 2), ctx.path)
+            return gz[:, :d].contiguous(), None, None
+        gz = _capi.metric_grad(tab, zc, u, 2.0 / (tab.temperature ** 2), ctx.path)
         return gz, None, None
 
 
@@ -103,6 +125,8 @@ class MetricTensor(nn.Module):
         self.check_singular = True   # one [N]-sized device->host check per compute_metric call
         self._tab = None
         self._tab_key = None
+        self._emb = None             # zero-padded tables (latent dims other than 16 / 64), see _embedded()
+        self._emb_key = None
 
     # ------------------------------------------------------------------ loading / caches
     def load_pretrained(self, centroids: torch.Tensor, metric_matrices: torch.Tensor,
@@ -126,6 +150,7 @@ class MetricTensor(nn.Module):
             self.register_buffer('regularization', torch.tensor(regularization, device=self.device))
         self._is_loaded = True
         self._tab = None
+        self._emb_key = None
         print(f'✅ MetricTensor loaded: {len(centroids)} centroids, T={self.temperature.item():.3f}, '
               f'λ={self.regularization.item():.3f}')
 
@@ -149,6 +174,41 @@ class MetricTensor(nn.Module):
             self._tab_key = key
         return self._tab
 
+    # latent dims other than 16 / 64 have no tensor kernel of their own.  With K >= EMBED_MIN_CENTROIDS centroids the
+    # metric is evaluated as the leading d x d block of the same problem zero-padded to 16 / 64 dims: distances and
+    # weights are unchanged, G^{-1} = diag(G^{-1}_d, lambda I), so G, the gradient and the backward are the leading
+    # blocks and log det G = log det G_padded + (dp - d) log lambda.  (The samplers keep the native tables: the HMC
+    # quirks -- det + clamp(1e-10) -- do not commute with the padding.)
+    EMBED_MIN_CENTROIDS = 512
+
+    def _table_key(self):
+        c, m = self.centroids, self.metric_matrices
+        return (c.data_ptr(), c._version, m.data_ptr(), m._version, tuple(c.shape),
+                self.temperature.data_ptr(), self.temperature._version,
+                self.regularization.data_ptr(), self.regularization._version)
+
+    def _embedded(self, device) -> Optional[_capi.Tables]:
+        d = self.latent_dim
+        if d in (16, 64) or d > 64 or self.kernel_path == 'direct' or not self._is_loaded:
+            return None
+        c, m = self.centroids, self.metric_matrices
+        if c.device != device or c.shape[0] < self.EMBED_MIN_CENTROIDS:
+            return None
+        key = self._table_key()
+        if self._emb_key != key:
+            self._emb, self._emb_key = None, key
+            lam = float(self.regularization.item())
+            if lam > 0.0 and math.isfinite(lam):
+                dp = 16 if d < 16 else 64
+                cp = torch.zeros((c.shape[0], dp), device=device, dtype=torch.float32)
+                cp[:, :d] = c
+                mp = torch.zeros((c.shape[0], dp, dp), device=device, dtype=torch.float32)
+                mp[:, :d, :d] = m
+                tab = _capi.Tables(cp, mp, float(self.temperature.item()), lam)
+                if tab.tensor_capable and (tab.tensor_auto or self.kernel_path == 'tensor'):
+                    self._emb = tab
+        return self._emb
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         # buffers registered empty must take the checkpoint's shapes (ref keeps tables in state_dict)
         for name in ('centroids', 'metric_matrices'):
@@ -159,11 +219,13 @@ class MetricTensor(nn.Module):
         if self.centroids.numel() > 0:
             self._is_loaded = True
         self._tab = None
+        self._emb_key = None
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self.device = self.centroids.device
         self._tab = None
+        self._emb_key = None
         return out
 
     def _path(self) -> int:
@@ -221,6 +283,18 @@ class MetricTensor(nn.Module):
         analytic grad_z log det G, through ``rlvae_metric_eval``."""
         self._check_ready(z)
         with torch.no_grad():
+            emb = self._embedded(z.device)
+            if emb is not None:
+                d = self.latent_dim
+                ev = _capi.metric_eval(emb, _pad_cols(z.float(), emb.d), want_ginv, want_g, want_logdet, want_grad,
+                                       self._path(), None)
+                blk = lambda t: None if t is None else t[:, :d, :d].contiguous()
+                ld = ev['logdet_g']
+                if ld is not None:      # log det G_d = log det G_padded + (dp - d) log lambda
+                    ld = (ld.double() + (emb.d - d) * math.log(float(self.regularization.item()))).float()
+                gr = ev['grad_logdet_g']
+                return dict(ginv=blk(ev['ginv']), g=blk(ev['g']), logdet_g=ld,
+                            grad_logdet_g=None if gr is None else gr[:, :d].contiguous(), work=None)
             return _capi.metric_eval(self._tables(z.device), z.float(), want_ginv, want_g, want_logdet,
                                      want_grad, self._path(), out)
 
@@ -291,8 +365,10 @@ class MetricTensor(nn.Module):
         """Which implementation `kernel_path='auto'` resolves to for the loaded tables."""
         if not self._is_loaded or not self.centroids.is_cuda:
             return {'loaded': self._is_loaded, 'device': str(self.centroids.device)}
-        tab = self._tables(self.centroids.device)
+        emb = self._embedded(self.centroids.device)
+        tab = emb if emb is not None else self._tables(self.centroids.device)
         tensor = tab.tensor_capable and tab.tensor_auto and self.kernel_path != 'direct'
+
         if self.kernel_path == 'tensor':
             tensor = tab.tensor_capable
         if not tensor:
@@ -305,7 +381,9 @@ class MetricTensor(nn.Module):
                      'hybrid mode (small temperature: expanded-distance GEMM + exact refinement of the live weights)')[tab.weight_mode])
         else:
             kind = '3xTF32 tcgen05 kernels (non-symmetric tables)'
-        return {'loaded': True, 'device': str(self.centroids.device), 'latent_dim': tab.d, 'n_centroids': tab.K,
+        if emb is not None:
+            kind += f' (latent_dim {self.latent_dim} evaluated as a block of the problem zero-padded to {emb.d} dims)'
+        return {'loaded': True, 'device': str(self.centroids.device), 'latent_dim': self.latent_dim, 'n_centroids': tab.K,
                 'symmetric_tables': tab.symmetric, 'tensor_path': bool(tensor), 'expanded_form_accurate': tab.expanded_ok,
                 'implementation': kind, 'kernel_path': self.kernel_path}
 

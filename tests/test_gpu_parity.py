@@ -948,6 +948,57 @@ def test_kmedoids_centroid_selection_invariants():
     assert data['centroids'].shape == (6, 16) and data['M_matrices'].shape == (6, 16, 16)
 
 
+@pytest.mark.parametrize('d', [5, 10, 32, 48])
+def test_other_latent_dims_with_many_centroids_run_as_a_block_of_the_padded_tensor_problem(d):
+    """latent dims other than 16 / 64 with K >= 512 centroids: MetricTensor evaluates them on the tensor kernels as
+    the leading block of the zero-padded problem (G^{-1} = diag(G^{-1}_d, lambda I)).  Every public quantity of the
+    metric API, forward and backward, against the oracle / reference autograd; kernel_path='direct' and small
+    tables keep the native kernels."""
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    K = 640
+    sm = make_synthetic_metric(K, d, seed=100 + d)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    n = 150
+    z = make_points(n, d, seed=d + 7)
+    mt = make_mt(t, 'auto')
+    info = mt.kernel_info()
+    assert info['tensor_path'] and 'zero-padded' in info['implementation'], info
+    assert make_mt(t, 'direct')._embedded(dev()) is None
+    small = make_synthetic_metric(100, d, seed=3)
+    assert make_mt((small.centroids, small.metric_matrices, small.temperature, small.regularization))._embedded(dev()) is None
+    ref_ginv = O.chunked(O.inverse_metric, z, *t, chunk=16)
+    ref_g = torch.linalg.inv(ref_ginv)
+    ref_ld = torch.linalg.slogdet(ref_g).logabsdet
+    ref_grad = -2.0 * O.chunked(O.grad_log_sqrt_det_ginv_exact, z[:48], *t, chunk=8)
+    zd = z.to(dev())
+    ev = mt.evaluate(zd, want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    assert ev['ginv'].shape == (n, d, d) and ev['g'].shape == (n, d, d) and ev['grad_logdet_g'].shape == (n, d)
+    assert rel_fro(ev['ginv'].cpu(), ref_ginv) < TOL_MAT
+    assert rel_fro(ev['g'].cpu(), ref_g) < 5e-5
+    close_ld(ev['logdet_g'], ref_ld)
+    assert rel_fro(ev['grad_logdet_g'].cpu()[:48], ref_grad) < TOL_LD
+    # against the native CUDA-core path (the padding must not change anything beyond rounding)
+    nat = make_mt(t, 'direct').evaluate(zd, want_ginv=True, want_g=True, want_logdet=True, want_grad=True)
+    assert rel_fro(ev['ginv'].cpu(), nat['ginv'].cpu()) < TOL_MAT
+    close_ld(ev['logdet_g'], nat['logdet_g'])
+    assert rel_fro(ev['grad_logdet_g'].cpu(), nat['grad_logdet_g'].cpu()) < TOL_LD
+    # reference API + autograd: backward of <G^{-1}, U> and of log det G w.r.t. z
+    assert rel_fro(mt.compute_inverse_metric(zd).cpu(), ref_ginv) < TOL_MAT
+    assert rel_fro(mt.compute_metric(zd).cpu(), ref_g) < 5e-5
+    close_ld(mt.compute_log_det_metric(zd), ref_ld)
+    U = torch.randn(32, d, d, generator=torch.Generator().manual_seed(d))
+    zr = z[:32].clone().requires_grad_(True)
+    (O.inverse_metric(zr, *t) * U).sum().backward()
+    zq = z[:32].to(dev()).requires_grad_(True)
+    (mt.compute_inverse_metric(zq) * U.to(dev())).sum().backward()
+    assert rel_fro(zq.grad.cpu(), zr.grad) < TOL_LD
+    zr2 = z[:32].clone().requires_grad_(True)
+    O.log_det_metric(zr2, *t).sum().backward()
+    zq2 = z[:32].to(dev()).requires_grad_(True)
+    mt.compute_log_det_metric(zq2).sum().backward()
+    assert rel_fro(zq2.grad.cpu(), zr2.grad) < TOL_LD
+
+
 def test_hmc_at_latent_dim_64_matches_the_oracle_chain():
     """The per-step HMC path at d = 64 (column-tiled tensor forward kernel + 64 x 64 Gauss-Jordan for diag G /
     log det + the vectorised element-wise stage) against the oracle chain, on both kernel paths."""
