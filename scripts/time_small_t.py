@@ -45,6 +45,8 @@ def timed(fn, reps=3):
 fwd = timed(lambda: mt.evaluate(z, want_ginv=False, want_logdet=True))
 full = timed(lambda: mt.evaluate(z, want_ginv=False, want_logdet=True, want_grad=True))
 print(f'forward {fwd:.2f} ms   forward+gradient {full:.2f} ms   ({N / full / 1e3:.1f} M evals/s)')
+step = timed(lambda: mt.evaluate(z, want_ginv=True, want_logdet=True, want_grad=True))
+print(f'the bench step (expanded G^-1 written as well): {step:.2f} ms')
 m = 1 << 14
 sel = torch.cat([torch.arange(m // 2), torch.arange(N - m // 2, N)]).to(dev)
 zs = z[sel].contiguous()
