@@ -624,7 +624,7 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
                 live |= (ex > hyb_thr ? 1u : 0u) << i;
               }
             }
-            refine_exponents(s, live,
+            refine_exponents<true>(s, live,
                              reinterpret_cast<const float4*>(gbase + h16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4, nz,
                              -alpha, P_SHIFT, hyb_row);
 #pragma unroll
@@ -1011,18 +1011,21 @@ inverse_metric_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
 }
 
 
-// HYBRID mode of the gradient kernel (crows: the block's natural rows in shared memory).  Like refine_exponents, the pairs flagged in `live` get their exponent from
+// HYBRID mode of the gradient kernel.  (Measured against the alternatives of the forward kernel -- natural rows staged in
+// shared memory, t_k through a shared-memory row, refinement deferred past the hand-off of u: same-box A/B 11.6 ms for
+// this version, 12.0 ms with all three, 12.9-13.4 ms with subsets.  Near pairs are rare per (warp, block) when every point
+// sits next to a few centroids, and the unconditional per-block cost of the staging outweighs cheaper rounds.)
+// Like refine_exponents, the pairs flagged in `live` get their exponent from
 // exact differences -- and, because those are exactly the pairs whose weight is not negligible, i.e. the centroids
 // NEAR the point, their whole contribution u (c_k - z) is accumulated here from the exact difference vector and
 // taken out of the tensor contraction (exponent -> -1e30 -> u = 0 for GEMM3 and for sum_k u).  The contraction's
 // form sum_k u c~_k - z~ sum_k u loses |c~| / |c_k - z| digits next to a centroid (1.2e-4 relative at T = 0.1,
 // measured against fp64); with the near pairs handled here only far pairs go through it, where nothing cancels.
-__device__ __forceinline__ void refine_direct(uint32_t live, const float4* __restrict__ crows, const float2 (&nz)[8],
-                                              float neg_alpha, float shift, float2 (&direct)[8], const float* row) {
-  // The caller has already set the flagged exponents to -1e30 (they leave the contraction whatever happens here)
-  // and, if any lane of the warp has a flagged pair, spilled the thread's 32 t_k into its shared-memory row: this
-  // function only ADDS to `direct`, so the gradient kernel runs it after u has been handed to the tensor pipe.
+__device__ __forceinline__ void refine_direct(uint32_t (&ex)[32], const uint32_t (&tv)[32], uint32_t live,
+                                              const float4* __restrict__ crows, const float2 (&nz)[8], float neg_alpha,
+                                              float shift, float2 (&direct)[8]) {
   if (!__any_sync(0xffffffffu, live != 0u)) return;
+  constexpr uint32_t NEG_BIG = 0xf149f2cau;        // -1e30f
   const int total = __reduce_add_sync(0xffffffffu, __popc(live));
   if (total > 160) {                               // dense tile: uniform sweep, broadcast loads
 #pragma unroll
@@ -1031,17 +1034,18 @@ __device__ __forceinline__ void refine_direct(uint32_t live, const float4* __res
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 c = crows[i * 4 + q];
+        const float4 c = __ldg(crows + i * 4 + q);
         dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
         dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
         ffma2_acc(acc, dv[2 * q], dv[2 * q]);
         ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
       }
       if ((live >> i) & 1u) {
-        const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * row[hyb_row_word(i)];
+        const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tv[i]);
         const float2 u2 = make_float2(uv, uv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
+        ex[i] = NEG_BIG;
       }
     }
     return;
@@ -1054,16 +1058,21 @@ __device__ __forceinline__ void refine_direct(uint32_t live, const float4* __res
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 c = crows[b * 4 + q];
+        const float4 c = __ldg(crows + b * 4 + q);
         dv[2 * q] = fadd2(make_float2(c.x, c.y), nz[2 * q]);
         dv[2 * q + 1] = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
         ffma2_acc(acc, dv[2 * q], dv[2 * q]);
         ffma2_acc(acc, dv[2 * q + 1], dv[2 * q + 1]);
       }
-      const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * row[hyb_row_word(b)];
+      uint32_t tb = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tb = (i == b) ? tv[i] : tb;
+      const float uv = ex2_approx(fmaf(acc.x + acc.y, neg_alpha, shift)) * __uint_as_float(tb);
       const float2 u2 = make_float2(uv, uv);
 #pragma unroll
       for (int q = 0; q < 8; ++q) ffma2_acc(direct[q], u2, dv[q]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ex[i] = (i == b) ? NEG_BIG : ex[i];
     }
   }
 }
@@ -1102,8 +1111,7 @@ constexpr int NUM_BARS = 5 * C_STAGES + 2 * M_STAGES + 11;
 constexpr uint32_t OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 constexpr uint32_t OFF_HYB = (OFF_TMEM_PTR + 16 + 15) & ~15u;   // HYBRID only: one scratch row per exp warp (8 warps)
-constexpr uint32_t OFF_HYBC = OFF_HYB + 8 * HYB_ROW_BYTES;      // HYBRID only: natural fp32 rows of the block's 64 centroids, per C stage
-constexpr uint32_t SMEM_BYTES_HYB = OFF_HYBC + C_STAGES * BK * 64 + 1024;
+constexpr uint32_t SMEM_BYTES_HYB = OFF_HYB + 8 * HYB_ROW_BYTES + 1024;   // (rows: the unit-weight mode's refine_exponents)
 static_assert(OFF_HYB % 16 == 0 && SMEM_BYTES_HYB <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TM_UHI = 0, TM_ULO = 72, TM_ST = 144, TM_OUT = 400, TM_ZHI = 464, TM_ZLO = 480;
 constexpr int RED_LD = 20;
@@ -1354,12 +1362,7 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             tma_load_2d(dst, &tm_cstack, BAR_C_FULL(cs), 0, j * BK);
             tma_load_2d(dst + C_TILE_BYTES / 2, &tm_cstack, BAR_C_FULL(cs), 0, j * BK + 32);
           }
-          if (HYBRID) {     // + the natural rows of the block (4 KB): the refinement reads them from shared memory
-            mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES + BK * 64);
-            bulk_load_1d(base + g16::OFF_HYBC + cs * (BK * 64), cnat + (int64_t)j * BK * 16, BK * 64, BAR_B_FULL(cs));
-          } else {
-            mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
-          }
+          mbar_expect_tx(BAR_B_FULL(cs), BIAS_BYTES);
         }
         bulk_load_1d(base + OFF_BIAS + cs * BIAS_BYTES, cbias + (int64_t)j * BK, BIAS_BYTES, BAR_B_FULL(cs));
       }
@@ -1544,9 +1547,6 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tc_fence_after();
       PROF_ADD(pe_wait);
       float su_blk = 0.f;                // sum of u over this super-block (two-level fp32 summation)
-      uint32_t live_def = 0u;            // HYBRID: near pairs whose exact contribution is added after the hand-off
-      const float4* crows_def = nullptr;
-      (void)live_def; (void)crows_def;
 #pragma unroll
       for (int rr = 0; rr < (COLSPLIT ? 1 : 2); ++rr) {
         const int rnd = COLSPLIT ? grp : rr;
@@ -1567,20 +1567,16 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
             for (int e = 0; e < 4; ++e) {
               const int i = 4 * q + e;
               const float ex = fmaf(__uint_as_float(sv[i]), s_scale, b4[e] + zb);
-              const bool near = ex > hyb_thr;
-              live |= (near ? 1u : 0u) << i;
-              // near pairs leave the contraction (refine_direct adds them from exact differences)
-              sv[i] = (near && u_packed != 2) ? 0xf149f2cau /* -1e30f */ : __float_as_uint(ex);
+              live |= (ex > hyb_thr ? 1u : 0u) << i;
+              sv[i] = __float_as_uint(ex);
             }
           }
-          const float4* crows = reinterpret_cast<const float4*>(gbase + g16::OFF_HYBC + cs * (BK * 64)) + rnd * 32 * 4;
-          if (u_packed == 2) {    // unit-weight mode: the table behind the contraction is not the centroids
-            refine_exponents(sv, live, crows, nz, -alpha, 0.f, hyb_row);
-          } else {
-            if (__any_sync(0xffffffffu, live != 0u)) hyb_row_spill(hyb_row, tv);      // t_k for refine_direct
-            if (COLSPLIT) { live_def = live; crows_def = crows; }                      // deferred: see below
-            else refine_direct(live, crows, nz, -alpha, 0.f, direct, hyb_row);
-          }
+          if (u_packed == 2)      // unit-weight mode: the table behind the contraction is not the centroids
+            refine_exponents<false>(sv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4,
+                                    nz, -alpha, 0.f, hyb_row);
+          else
+            refine_direct(sv, tv, live, reinterpret_cast<const float4*>(cnat) + ((int64_t)j * BK + rnd * 32) * 4, nz,
+                          -alpha, 0.f, direct);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float uv = ex2_approx(__uint_as_float(sv[i])) * __uint_as_float(tv[i]);
@@ -1614,14 +1610,10 @@ metric_grad_h16_kernel(const __grid_constant__ CUtensorMap tm_cstack,
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb)); }
-      if (HYBRID && COLSPLIT && u_packed != 2) {
-        // the near pairs are out of the contraction already (exponent -1e30): their exact contribution only adds to
-        // registers, so it runs AFTER u went to the tensor pipe -- off the T-GEMM(j) -> GEMM3(j) critical path
-        refine_direct(live_def, crows_def, nz, -alpha, 0.f, direct, hyb_row);
-        __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(BAR_U_FULL(sb)); else mbar_arrive(BAR_U_FULL(sb));
+        mbar_arrive(BAR_C_EMPTY(cs));
       }
-      if (lane == 0) mbar_arrive(BAR_C_EMPTY(cs));       // (after the refinement: it reads the stage's natural rows)
       PROF_ADD(pe_work);
       while (next_chunk < num_chunks && min((next_chunk + 1) * CHUNK - 1, num_blocks - 1) <= j - 1) {
         mbar_wait(BAR_CH_FULL(next_chunk & 1), (next_chunk >> 1) & 1);

@@ -391,6 +391,20 @@ __device__ __forceinline__ float dist2_row16(const float4* __restrict__ crow, co
   return acc.x + acc.y;
 }
 
+// the same from global memory (read-only path)
+__device__ __forceinline__ float dist2_row16_ldg(const float4* __restrict__ crow, const float2 (&nz)[8]) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 c = __ldg(crow + q);
+    const float2 d0 = fadd2(make_float2(c.x, c.y), nz[2 * q]);
+    const float2 d1 = fadd2(make_float2(c.z, c.w), nz[2 * q + 1]);
+    ffma2_acc(acc, d0, d0);
+    ffma2_acc(acc, d1, d1);
+  }
+  return acc.x + acc.y;
+}
+
 // Per-lane scratch row of 32 words in shared memory for the HYBRID refinement: word i of lane l is component
 // i % 4 of the float4 at [plane i / 4][lane l] -- the 128-bit spills / reloads of a warp touch 512 contiguous
 // bytes per plane (conflict free), and a lane can address ITS word i with a run-time i, which a register array
@@ -412,13 +426,15 @@ __device__ __forceinline__ int hyb_row_word(int i) { return (i >> 2) * 128 + (i 
 
 // HYBRID weight mode: ex[i] (i < 32, float bits) are this thread's exponents for 32 consecutive
 // centroids from the expanded form; the ones flagged in `live` are replaced by
-// neg_alpha * ||z - c_i||^2 + shift from exact differences (crows: the 32 natural centroid rows, in SHARED memory --
-// a per-lane row from L2 costs a full memory latency per round and made the exp warps latency bound).
+// neg_alpha * ||z - c_i||^2 + shift from exact differences (crows: the 32 natural centroid rows; SMEM_ROWS: staged in
+// shared memory by the producer warp -- the forward kernel, where per-lane rows from L2 made the exp warps latency
+// bound -- otherwise in global memory, read-only path).
 // Must be called by the whole warp.
 // Sparse case (the usual one at small T): every lane works on its own flagged centroid at the same
 // time, so a round costs one distance however many lanes need one; the exponents sit in the lane's
 // shared-memory row (`row` = this lane's float4 of plane 0) while the rounds run, so a refined value is ONE store.
 // Dense case: a uniform sweep with broadcast loads, like the exact mode.
+template <bool SMEM_ROWS>
 __device__ __forceinline__ void refine_exponents(uint32_t (&ex)[32], uint32_t live, const float4* __restrict__ crows,
                                                  const float2 (&nz)[8], float neg_alpha, float shift, float* row) {
   if (!__any_sync(0xffffffffu, live != 0u)) return;
@@ -426,7 +442,7 @@ __device__ __forceinline__ void refine_exponents(uint32_t (&ex)[32], uint32_t li
   if (total > 160) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float v = fmaf(dist2_row16(crows + i * 4, nz), neg_alpha, shift);
+      const float v = fmaf((SMEM_ROWS ? dist2_row16(crows + i * 4, nz) : dist2_row16_ldg(crows + i * 4, nz)), neg_alpha, shift);
       if ((live >> i) & 1u) ex[i] = __float_as_uint(v);
     }
     return;
@@ -436,7 +452,7 @@ __device__ __forceinline__ void refine_exponents(uint32_t (&ex)[32], uint32_t li
     if (live != 0u) {
       const int b = __ffs(live) - 1;
       live &= live - 1u;
-      row[hyb_row_word(b)] = fmaf(dist2_row16(crows + b * 4, nz), neg_alpha, shift);
+      row[hyb_row_word(b)] = fmaf((SMEM_ROWS ? dist2_row16(crows + b * 4, nz) : dist2_row16_ldg(crows + b * 4, nz)), neg_alpha, shift);
     }
   }
   hyb_row_reload(row, ex);

@@ -54,6 +54,7 @@ class HostEvaluator:
         n = z_host.shape[0]
         tab = self.metric._tables(self.dev)
         path = self.metric._path()
+        embedded = self.metric._embedded(self.dev) is not None
         cur = torch.cuda.current_stream(self.dev)
         h2d = d2h = 0
         for s in self.streams:
@@ -66,14 +67,22 @@ class HostEvaluator:
                 b['z'][:m].copy_(z_host[lo:hi], non_blocking=True)
                 h2d += m * self.d * 4
                 ginv = ginv_dev[lo:hi] if ginv_dev is not None else b['ginv'][:m]
-                _capi.metric_eval(tab, b['z'][:m], want_ginv=True, want_g=False, want_logdet=True,
-                                  want_grad=self.want_grad, path=path,
-                                  out=dict(ginv=ginv, logdet_g=b['ld'][:m], grad_logdet_g=b['grad'][:m],
-                                           work=b['work']))
-                logdet_host[lo:hi].copy_(b['ld'][:m], non_blocking=True)
+                if embedded:
+                    # latent_dim evaluated as a block of the zero-padded problem (MetricTensor._embedded): the
+                    # module's own entry point pads, evaluates and slices
+                    ev = self.metric.evaluate(b['z'][:m], want_ginv=True, want_logdet=True, want_grad=self.want_grad)
+                    ginv.copy_(ev['ginv'])
+                    ld_dev, grad_dev = ev['logdet_g'], ev['grad_logdet_g']
+                else:
+                    _capi.metric_eval(tab, b['z'][:m], want_ginv=True, want_g=False, want_logdet=True,
+                                      want_grad=self.want_grad, path=path,
+                                      out=dict(ginv=ginv, logdet_g=b['ld'][:m], grad_logdet_g=b['grad'][:m],
+                                               work=b['work']))
+                    ld_dev, grad_dev = b['ld'][:m], b['grad'][:m]
+                logdet_host[lo:hi].copy_(ld_dev, non_blocking=True)
                 d2h += m * 4
                 if self.want_grad and grad_host is not None:
-                    grad_host[lo:hi].copy_(b['grad'][:m], non_blocking=True)
+                    grad_host[lo:hi].copy_(grad_dev, non_blocking=True)
                     d2h += m * self.d * 4
                 if ginv_host is not None:
                     ginv_host[lo:hi].copy_(ginv, non_blocking=True)

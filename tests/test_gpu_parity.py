@@ -999,6 +999,37 @@ def test_other_latent_dims_with_many_centroids_run_as_a_block_of_the_padded_tens
     assert rel_fro(zq2.grad.cpu(), zr2.grad) < TOL_LD
 
 
+@pytest.mark.parametrize('d,K', [(16, 300), (10, 640)])
+def test_host_evaluator_matches_the_device_evaluation(d, K):
+    """The host-buffer entry point bench.py times for `e2e` (pinned z in, log det + gradient [+ G^-1] out, chunks
+    double-buffered over two streams, a ragged last chunk) returns what MetricTensor.evaluate returns on the device;
+    d = 10 with K = 640 goes through the zero-padded tensor path."""
+    from rlvae_b200.host_pipeline import HostEvaluator
+    from rlvae_b200.synthetic import make_points, make_synthetic_metric
+    sm = make_synthetic_metric(K, d, seed=11)
+    t = (sm.centroids, sm.metric_matrices, sm.temperature, sm.regularization)
+    mt = make_mt(t, 'auto')
+    n = 2500
+    z = make_points(n, d, seed=12)
+    ref = mt.evaluate(z.to(dev()), want_ginv=True, want_logdet=True, want_grad=True)
+    zh = z.pin_memory()
+    ld = torch.empty(n).pin_memory()
+    gr = torch.empty(n, d).pin_memory()
+    gi = torch.empty(n, d, d).pin_memory()
+    he = HostEvaluator(mt, chunk=1000)
+    io = he(zh, ld, gr, ginv_host=gi)
+    assert io['h2d_bytes'] == n * d * 4 and io['d2h_bytes'] == n * 4 + n * d * 4 + n * d * d * 4
+    assert torch.equal(ld, ref['logdet_g'].cpu()) and torch.equal(gr, ref['grad_logdet_g'].cpu())
+    assert torch.equal(gi, ref['ginv'].cpu())
+    # G^-1 kept on the device instead
+    gd = torch.empty(n, d, d, device=dev())
+    ld.zero_()
+    he(zh, ld, gr, ginv_dev=gd)
+    assert torch.equal(gd, ref['ginv']) and torch.equal(ld, ref['logdet_g'].cpu())
+    with pytest.raises(RuntimeError):
+        he(z, ld, gr)                       # pageable host memory is refused
+
+
 def test_hmc_at_latent_dim_64_matches_the_oracle_chain():
     """The per-step HMC path at d = 64 (column-tiled tensor forward kernel + 64 x 64 Gauss-Jordan for diag G /
     log det + the vectorised element-wise stage) against the oracle chain, on both kernel paths."""
