@@ -40,12 +40,35 @@ class HostEvaluator:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def submit(self, z_host: torch.Tensor, logdet_host: torch.Tensor, grad_host: Optional[torch.Tensor] = None,
+               ginv_dev: Optional[torch.Tensor] = None, ginv_host: Optional[torch.Tensor] = None):
+        """The same evaluation WITHOUT the final synchronisation: returns (events, byte counts); the host buffers
+        are valid once every event has completed (``HostEvaluator.wait(events)``).  Successive submissions queue
+        behind each other on the evaluator's two streams (the device-side chunk buffers are reused in stream order),
+        so the copies of batch i + 1 overlap the kernels of batch i -- a streaming caller keeps one batch in flight
+        and reads batch i while batch i + 1 runs.  Give successive in-flight batches different host buffers."""
+        io = self._run(z_host, logdet_host, grad_host, ginv_dev, ginv_host, sync=False)
+        events = []
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            events.append(ev)
+        return events, io
+
+    @staticmethod
+    def wait(events) -> None:
+        for ev in events:
+            ev.synchronize()
+
     def __call__(self, z_host: torch.Tensor, logdet_host: torch.Tensor,
                  grad_host: Optional[torch.Tensor] = None, ginv_dev: Optional[torch.Tensor] = None,
                  ginv_host: Optional[torch.Tensor] = None) -> Dict:
         """z_host [N,d] pinned fp32 -> fills logdet_host [N], grad_host [N,d] and, if given, ginv_host
         [N,d,d] (all pinned; G^{-1} is 4 d^2 bytes per point, so copying it out makes the call PCIe
         bound).  Returns byte counts.  Synchronises before returning."""
+        return self._run(z_host, logdet_host, grad_host, ginv_dev, ginv_host, sync=True)
+
+    def _run(self, z_host, logdet_host, grad_host, ginv_dev, ginv_host, sync: bool) -> Dict:
         for name, t in (('logdet_host', logdet_host), ('grad_host', grad_host), ('ginv_host', ginv_host)):
             if t is not None and (t.is_cuda or not t.is_pinned() or not t.is_contiguous() or t.dtype != torch.float32):
                 raise RuntimeError(f'HostEvaluator: {name} must be a contiguous pinned fp32 host tensor')
@@ -87,8 +110,9 @@ class HostEvaluator:
                 if ginv_host is not None:
                     ginv_host[lo:hi].copy_(ginv, non_blocking=True)
                     d2h += m * self.d * self.d * 4
-        for s in self.streams:
-            cur.wait_stream(s)
-        cur.synchronize()
+        if sync:
+            for s in self.streams:
+                cur.wait_stream(s)
+            cur.synchronize()
         self.h2d_bytes, self.d2h_bytes = h2d, d2h
         return dict(h2d_bytes=h2d, d2h_bytes=d2h)

@@ -1028,6 +1028,16 @@ def test_host_evaluator_matches_the_device_evaluation(d, K):
     assert torch.equal(gd, ref['ginv']) and torch.equal(ld, ref['logdet_g'].cpu())
     with pytest.raises(RuntimeError):
         he(z, ld, gr)                       # pageable host memory is refused
+    # streaming use: two batches in flight behind each other, each into its own host buffers
+    ld_a, gr_a = torch.empty(n).pin_memory(), torch.empty(n, d).pin_memory()
+    ld_b, gr_b = torch.empty(n).pin_memory(), torch.empty(n, d).pin_memory()
+    zh2 = (z.flip(0).contiguous()).pin_memory()
+    ev_a, _ = he.submit(zh, ld_a, gr_a)
+    ev_b, _ = he.submit(zh2, ld_b, gr_b)
+    he.wait(ev_a)
+    assert torch.equal(ld_a, ref['logdet_g'].cpu()) and torch.equal(gr_a, ref['grad_logdet_g'].cpu())
+    he.wait(ev_b)
+    assert torch.equal(ld_b, ref['logdet_g'].cpu().flip(0)) and torch.equal(gr_b, ref['grad_logdet_g'].cpu().flip(0))
 
 
 def test_hmc_at_latent_dim_64_matches_the_oracle_chain():
