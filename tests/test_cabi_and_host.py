@@ -122,3 +122,65 @@ def test_new_host_modules_refuse_cpu_tensors_and_keep_reference_surfaces():
     assert list(sig.parameters)[1:] == ['model', 'mcmc_steps_nbr', 'n_lf', 'eps_lf', 'beta_zero']
     assert sig.parameters['mcmc_steps_nbr'].default == 100 and sig.parameters['n_lf'].default == 15
     assert RHVAEStyleHMCSampler.tempering(5, 10, 0.5) == pytest.approx(1.0 / ((1 - 2.0) * 0.25 + 2.0))
+
+
+def test_merged_prior_batches_draw_in_the_sequential_order():
+    """OfficialRHVAESampler.sample_prior runs the reference's 32-chain batches as one library call; what ties a
+    chain to its batch is only the order of the random draws (pythae RHVAESampler.sample :61-67 -> hmc_sampling
+    :100, :107, :141).  Host logic, checked on the CPU generator: the stacked streams are exactly the streams the
+    batch-by-batch loop draws."""
+    import torch.nn as nn
+    from rlvae_b200.samplers.rhvae_sampler import RHVAEStyleHMCSampler
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = nn.Parameter(torch.zeros(1))
+            self.latent_dim = 5
+            self.centroids_tens = torch.arange(70.0).reshape(14, 5)
+
+    class Recording(RHVAEStyleHMCSampler):
+        def __init__(self, model):
+            super().__init__(model, mcmc_steps_nbr=3)
+            self.calls = []
+
+        def hmc_sampling_with_streams(self, idx0, gammas, accs, record=None, z_start=None, state=None):
+            self.calls.append((None if idx0 is None else idx0.clone(), gammas.clone(), accs.clone()))
+            return self.model.centroids_tens[idx0] if z_start is None else z_start
+
+    sizes = [4, 4, 3]
+    merged = Recording(Model())
+    torch.manual_seed(7)
+    out = merged.hmc_sampling_batches(sizes)
+    assert out.shape == (11, 5) and len(merged.calls) == 1
+    seq = Recording(Model())
+    torch.manual_seed(7)
+    for b in sizes:
+        seq.hmc_sampling(b)
+    assert len(seq.calls) == 3
+    idx_m, gam_m, acc_m = merged.calls[0]
+    assert torch.equal(idx_m, torch.cat([c[0] for c in seq.calls]))
+    assert torch.equal(gam_m, torch.cat([c[1] for c in seq.calls], dim=1))
+    assert torch.equal(acc_m, torch.cat([c[2] for c in seq.calls], dim=1))
+    # a single batch goes through hmc_sampling itself; empty input is an empty result
+    one = Recording(Model())
+    assert one.hmc_sampling_batches([6]).shape == (6, 5) and one.hmc_sampling_batches([]).shape == (0, 5)
+
+
+def test_zero_padded_path_is_off_where_it_does_not_apply():
+    """MetricTensor._embedded: only for loaded CUDA tables with latent_dim not in {16, 64}, K >= 512, lambda > 0 and
+    kernel_path != 'direct' -- everything else keeps the native tables (no CUDA call is made for these answers)."""
+    from rlvae_b200 import MetricTensor
+    cpu = torch.device('cpu')
+    assert MetricTensor(16, device=cpu)._embedded(cpu) is None
+    assert MetricTensor(10, device=cpu)._embedded(cpu) is None                       # not loaded
+    mt = MetricTensor(10, device=cpu, kernel_path='direct')
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt.load_pretrained(torch.zeros(600, 10), torch.eye(10).repeat(600, 1, 1), temperature=1.0, regularization=0.01)
+    assert mt._embedded(cpu) is None                                                 # direct path requested
+    few = MetricTensor(10, device=cpu)
+    with contextlib.redirect_stdout(io.StringIO()):
+        few.load_pretrained(torch.zeros(100, 10), torch.eye(10).repeat(100, 1, 1), temperature=1.0, regularization=0.01)
+    assert few._embedded(cpu) is None                                                # small table
+    assert MetricTensor.EMBED_MIN_CENTROIDS == 512
