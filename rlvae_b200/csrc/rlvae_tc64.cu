@@ -1030,15 +1030,33 @@ __global__ void pack_ct64_kernel(const float* __restrict__ c, const float* __res
   }
 }
 
-// packed [N, 2176] -> full symmetric [N, 64, 64], + lambda on the diagonal
-__global__ void unpack_sym64_kernel(const float* __restrict__ packed, int64_t n, float lambda,
-                                    float* __restrict__ full) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n * 4096) return;
-  const int64_t p = gid >> 12;
-  const int e = (int)(gid & 4095), i = e >> 6, j = e & 63;
-  const float v = packed[p * tc::h64::NPAD + (i <= j ? sym64_index(i, j) : sym64_index(j, i))];
-  full[gid] = v + (i == j ? lambda : 0.f);
+// packed [N, 2176] -> full symmetric [N, 64, 64], + lambda on the diagonal.  One CTA per point: the packed row goes
+// through shared memory (coalesced 128-bit loads), the 64 x 64 matrix leaves as coalesced 128-bit stores -- a thread per
+// output element gathering from global memory was long-scoreboard bound (1.6 ms per 2^17 points, 2.0 TB/s).
+__global__ void __launch_bounds__(256)
+unpack_sym64_kernel(const float* __restrict__ packed, int64_t n, float lambda, float* __restrict__ full) {
+  __shared__ __align__(16) float sm[tc::h64::NPAD];
+  const int tid = threadIdx.x;
+  for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(packed + p * tc::h64::NPAD);
+    for (int c4 = tid; c4 < tc::h64::NPAD / 4; c4 += 256) reinterpret_cast<float4*>(sm)[c4] = __ldg(src + c4);
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(full + p * 4096);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e4 = tid + 256 * q;                  // float4 index: row e4 / 16, columns 4 (e4 % 16) ..
+      const int i = e4 >> 4, j0 = (e4 & 15) << 2;
+      float v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = j0 + t;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        v[t] = sm[(lo * (129 - lo)) / 2 + (hi - lo)] + (i == j ? lambda : 0.f);
+      }
+      dst[e4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+  }
 }
 
 typedef CUresult (*PFN_encodeTiled64)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1217,13 +1235,13 @@ int launch_inverse_metric_h64(const rlvae_tables* t, const float* z, int64_t n, 
   if (n == 0) return 0;
   RLVAE_REQUIRE(t->d == 64 && t->symmetric && t->c64h != nullptr, "d = 64 tensor path needs symmetric tables");
   RLVAE_REQUIRE(packed_scratch != nullptr, "d = 64 tensor path needs the packed scratch buffer");
-  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_scratch) & 15) == 0,
-                "tensor path needs 16-byte aligned z and scratch");
+  RLVAE_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_scratch) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(ginv) & 15) == 0,
+                "tensor path needs 16-byte aligned z, G^-1 buffer and scratch");
   if (int rc = h64_use_pairs() ? launch_h64<true>(t, z, n, packed_scratch, s)
                                : launch_h64<false>(t, z, n, packed_scratch, s))
     return rc;
-  const int64_t total = n * 4096;
-  unpack_sym64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(packed_scratch, n, t->lambda, ginv);
+  unpack_sym64_kernel<<<(unsigned)(n < 148 * 64 ? n : 148 * 64), 256, 0, s>>>(packed_scratch, n, t->lambda, ginv);
   RLVAE_LAUNCH_OK();
   return 0;
 }
